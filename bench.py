@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""Headline benchmark: 3D patches/s of the MultiTalent training step (Generic_UNet 3d_fullres, 192x160x128, bs 4 per
+GPU, 13-dataset multi-head loss, clip + Nesterov SGD) on N B200s -- BASELINE.json `configs[1]`.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run by the driver)
+    python bench.py --impl reference ...                     (the reference algorithm's CPU arm: oracle port on host cores)
+
+Prints ONE JSON line (rank 0).  `value` = whole-job patches/s with inputs resident in HBM; `e2e` = the same through
+`MultiTalent_trainer_ddp.run_iteration` with pinned HOST batches (H2D of data+targets and D2H of the loss inside the timed
+region); `roofline` = the dominant kernel family against MEASURED_PEAKS.json; `cpu_baseline` = the oracle on host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "3D patches/sec (192x160x128, bs4) training step"
+FULL_PATCH = (192, 160, 128)
+TRAIN_GFLOP_PER_PATCH = 4769.7   # BASELINE.md section 2 (fwd + dgrad + wgrad, true channel counts)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [s.strip() for s in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_oracle_step_factory(patch, seed=0):
+    """One training step of the reference algorithm on host cores: oracle forward + MultiTalent loss + backward +
+    clip/SGD, bs 1, fp32 (the reference's own CPU path, restated)."""
+    from oracle import unet_oracle as O
+    from multitalent_b200.network_architecture.generic_UNet import Generic_UNet, InitWeights_He
+    from torch import nn
+    pool = [[2, 2, 2]] * 4 + [[1, 2, 2]]
+    convk = [[3, 3, 3]] * 6
+    torch.manual_seed(seed)
+    net = Generic_UNet(1, 30, 47, 5, 2, 2, nn.Conv3d, nn.InstanceNorm3d, {'eps': 1e-5, 'affine': True}, nn.Dropout3d,
+                       {'p': 0, 'inplace': True}, nn.LeakyReLU, {'negative_slope': 1e-2, 'inplace': True}, True, False,
+                       lambda x: x, InitWeights_He(1e-2), pool, convk, False, True, True)
+    names = [n for n, _ in net.named_parameters()]
+    state = {"p": [p.detach().clone() for _, p in net.named_parameters()], "buf": [None] * len(names)}
+    rng = np.random.RandomState(1234)
+    task = O.TASK_IDS[6]
+    vol, lab = O.synthetic_ct_and_labels(patch, task, rng)
+    x = torch.from_numpy(vol[None, None])
+    scales = [[1, 1, 1], [.5] * 3, [.25] * 3, [.125] * 3, [1 / 16] * 3]
+    tg = [torch.from_numpy(t) for t in O.downsample_targets(lab[None, None], scales)]
+    valid = [O.VALID_REGIONS[task]]
+    w = O.multitalent_ds_loss_weights(5)
+
+    def step():
+        sd = {n: p.clone().requires_grad_(True) for n, p in zip(names, state["p"])}
+        out = O.generic_unet_forward(x, sd, pool, convk)
+        l, _, _ = O.multitalent_loss(out, tg, valid, w)
+        l.backward()
+        state["p"], state["buf"], _ = O.clip_and_sgd_step(state["p"], [sd[n].grad for n in names], state["buf"], 1e-2)
+        return float(l)
+    return step
+
+
+def run_reference(args, rank):
+    """`--impl reference`: the reference's algorithm on the box's host cores (oracle port; the reference is pure Python
+    over torch CPU ops, so there is no separate oracle/_ref binary)."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_patch = (96, 96, 64)  # 0.15 of the benchmark patch: keeps K+W steps within minutes on a few cores
+    frac = float(np.prod(sample_patch)) / float(np.prod(FULL_PATCH))
+    step = cpu_oracle_step_factory(sample_patch)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = frac / dt
+    sample = ("oracle port (torch CPU fp32): fwd + MultiTalent loss + bwd + clip/SGD, bs1, patch %dx%dx%d = %.3f of a "
+              "192x160x128 patch per step, scaled by voxel count" % (sample_patch + (frac,)))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Generic_UNet 3d_fullres training step, 13-dataset multi-head loss, CPU sample",
+                       "patch": list(sample_patch), "batch_per_step": 1},
+            "cpu_baseline": {"value": value, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--patch", type=int, nargs=3, default=list(FULL_PATCH))
+    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 force CUDA-core kernels, 2 force tcgen05")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    from multitalent_b200 import _lib as L
+    from multitalent_b200.plans import default_plans
+    from multitalent_b200.synthetic import synthetic_batch
+    from multitalent_b200.training.network_training.MultiTalent_Trainer_DDP import MultiTalent_trainer_ddp
+
+    assert torch.cuda.is_available(), "bench.py (native arm) needs a GPU; there is no CPU fallback"
+    L.lib()
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.dtype]
+    patch = tuple(args.patch)
+    tr = MultiTalent_trainer_ddp(default_plans(patch_size=patch, batch_size=args.batch), 0, local_rank,
+                                 native_dtype=dt, init_distributed=world > 1)
+    torch.manual_seed(0)  # same initial weights on every rank (they are broadcast anyway)
+    tr.initialize(True)
+    tr.network._engine.impl = args.kernel_impl
+    if args.dtype == "fp16":
+        tr.loss_scale = 4096.0  # static loss scale (the reference uses a dynamic GradScaler, MT:350-354)
+    dev = torch.device("cuda", local_rank)
+
+    batch = synthetic_batch(patch, args.batch, rank, tr.deep_supervision_scales)
+    valid = [p['valid_regions'] for p in batch['properties']]
+    host_data = torch.from_numpy(batch['data']).pin_memory()
+    host_tgt = [torch.from_numpy(t).pin_memory() for t in batch['target']]
+    d_data = host_data.to(dev)
+    d_tgt = [t.to(dev) for t in host_tgt]
+    h2d = host_data.numel() * 4 + sum(t.numel() * 4 for t in host_tgt)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        tr.train_step(d_data, d_tgt, valid, True)
+    barrier()
+
+    # ---- timed region: K steps, inputs resident in HBM, per-launch events for the roofline section
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    n0 = L.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with L.KernelProfile() as kp:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            l, ce, dc = tr.train_step(d_data, d_tgt, valid, True)
+        e1.record()
+        barrier()
+    clocks = sampler.stop()
+    launches = L.launch_count - n0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    loss_val = float(l.item())
+    ksum = kp.summary()
+
+    # ---- end to end through run_iteration: pinned host batch -> H2D -> step -> D2H of (l, ce, dc)
+    def gen():
+        while True:
+            yield {'data': host_data, 'target': host_tgt, 'properties': batch['properties']}
+    g = gen()
+    tr.run_iteration(g, True)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        tr.run_iteration(g, True)
+    t1.record()
+    barrier()
+    e2e_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms_per_step = float(e2e_ms.item()) / args.steps
+
+    if rank != 0:
+        return
+    pk = peaks()
+    patches_per_step = args.batch * world
+    vox_frac = float(np.prod(patch)) / float(np.prod(FULL_PATCH))
+    value = patches_per_step / (ms_per_step * 1e-3)
+    e2e_value = patches_per_step / (e2e_ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel family (by device time inside the timed region)
+    conv = {k: v for k, v in ksum.items() if k.startswith("conv_")}
+    top = max(conv, key=lambda k: conv[k]["ms"]) if conv else None
+    total_kernel_ms = sum(v["ms"] for v in ksum.values())
+    roof = None
+    if top:
+        t = conv[top]
+        achieved = t["flops"] / (t["ms"] * 1e-3) / 1e12
+        peak = pk["bf16_tflops_sustained"]
+        roof = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": pk["source"] + " (sustained bf16)",
+                "launches": t["launches"], "share_of_kernel_time": t["ms"] / total_kernel_ms,
+                "flops_per_launch_avg": t["flops"] / t["launches"], "ms_per_launch_avg": t["ms"] / t["launches"]}
+    step_tflops = TRAIN_GFLOP_PER_PATCH * vox_frac * args.batch / ms_per_step  # GFLOP/ms == TFLOP/s
+    line = {"metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "Generic_UNet 3d_fullres (MultiTalent_bs4 plan) training step: fwd + 13-dataset "
+                                   "multi-head BCE+Dice loss + bwd + clip12 + Nesterov SGD",
+                       "patch": list(patch), "batch_per_gpu": args.batch, "global_batch": patches_per_step,
+                       "parallelism": "dp%d" % world, "l2": "working set (activations > 8 GB) far exceeds the 126 MB L2",
+                       "loss": loss_val},
+            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 12,
+                    "ms_per_step": e2e_ms_per_step},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "step_tflops_algorithmic": step_tflops / world * world if world == 1 else step_tflops,
+            "step_frac_of_bf16_peak": step_tflops / pk["bf16_tflops_sustained"],
+            "kernels": {k: {"launches": v["launches"], "ms_per_step": v["ms"] / args.steps,
+                            "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] and v["ms"] else None}
+                        for k, v in sorted(ksum.items(), key=lambda kv: -kv[1]["ms"])}}
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sample_patch = (96, 96, 64)
+        frac = float(np.prod(sample_patch)) / float(np.prod(FULL_PATCH))
+        step = cpu_oracle_step_factory(sample_patch)
+        step()
+        c0 = time.perf_counter()
+        nrep = 2
+        for _ in range(nrep):
+            step()
+        cdt = (time.perf_counter() - c0) / nrep
+        line["cpu_baseline"] = {"value": frac / cdt, "unit": "patches/s", "cores": torch.get_num_threads(),
+                                "kind": "port",
+                                "sample": "oracle fwd+loss+bwd+SGD, bs1, patch 96x96x64 (0.15 of 192x160x128), %d timed "
+                                          "steps after 1 warm-up, scaled by voxel count" % nrep}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,206 @@
+/*
+ * mtb200.h -- C ABI of libmtb200.so: the B200-native (sm_100a) hot path of MultiTalent's 3D U-Net training step and
+ * sliding-window predictor.
+ *
+ * The reference (MIC-DKFZ/MultiTalent, a fork of nnU-Net V1) is 100 % Python over PyTorch library ops: it has no FFI
+ * of its own.  Each entry point below therefore cites the reference *call site* (file:line under /root/reference)
+ * whose arithmetic it replaces; the Python host side (multitalent_b200/) binds these through ctypes and mirrors the
+ * reference's module / trainer interface on top.  INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative mtb200_status on failure; the message of the last failure on the
+ *    calling thread is returned by mtb200_last_error().  Nothing here aborts, exits or throws across the boundary.
+ *  - pointers are raw device pointers unless the name says host; the library owns NO device memory: workspaces are
+ *    allocated by the caller (PyTorch's caching allocator) and passed in.
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  All launches are asynchronous.
+ *  - activations are channels-last NDHWC ("voxel-major") with a channel stride `ldc` and a channel offset `coff`, so a
+ *    producer can write straight into one half of a concatenated skip buffer (replaces torch.cat, generic_UNet.py:392).
+ *  - dtype enum: 0 = float32 (T0 parity mode), 1 = bfloat16, 2 = float16 (T1 production modes).
+ */
+#ifndef MTB200_H
+#define MTB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTB200_VERSION 100
+
+typedef enum {
+  MTB200_OK = 0,
+  MTB200_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  MTB200_ERR_CUDA = -2,        /* a CUDA runtime/driver call failed (launch error etc.) */
+  MTB200_ERR_UNSUPPORTED = -3, /* valid request, not supported by this kernel (caller should pick another path) */
+} mtb200_status;
+
+typedef enum { MTB200_F32 = 0, MTB200_BF16 = 1, MTB200_F16 = 2 } mtb200_dtype;
+
+#define MTB200_MAX_TAPS 32
+#define MTB200_MAX_GROUPS 8
+
+/* One "tap-table" convolution problem:
+ *     out[b, o*os + ooff_g, co] (+)= bias[co] + sum_{t in group g} sum_ci  W[widx_t][co][ci] * f(in[b, o*is + off_t, ci])
+ * for o over the logical output grid (Do,Ho,Wo); f = optional on-load transform  v = x*scale+shift; v>0 ? v : v*slope
+ * (InstanceNorm apply + LeakyReLU of the PRODUCER fused into the consumer's load); reads outside the input volume are 0
+ * AFTER the transform (the reference zero-pads the normalised tensor, generic_UNet.py:46,245).
+ * With the right tap table this one form covers Conv3d forward (stride 1 / strided), its data gradient (stride 1: flipped
+ * taps; strided: 8 parity groups), ConvTranspose3d(kernel==stride) forward (8 groups of 1 tap, os=2) and its data
+ * gradient (8 taps, is=2), and the 1x1x1 heads.  Weights are packed [n_widx][Cout][Cin] ("K-major").            */
+typedef struct {
+  const void* in;       /* NDHWC activations, dtype `dtype` */
+  void* out;            /* NDHWC, dtype `dtype` */
+  const void* w;        /* packed weights [n_widx][Cout][Cin], dtype `wdtype` */
+  const float* bias;    /* [Cout] or NULL */
+  const float* xform;   /* [B][Cin][4] = {scale, shift, slope, unused} or NULL (input already normalised) */
+  double* stats;        /* [B][Cout][2] running {sum, sum of squares} of the ROUNDED outputs, or NULL */
+  int32_t dtype, wdtype;
+  int32_t B;
+  int32_t Di, Hi, Wi, in_ldc, in_coff, Cin;       /* full input volume */
+  int32_t Dof, Hof, Wof, out_ldc, out_coff, Cout; /* full output volume */
+  int32_t Do, Ho, Wo;                             /* logical output grid (per group) */
+  int32_t is[3], os[3];                           /* input / output coordinate strides */
+  int32_t ngroups;
+  int32_t group_tap_begin[MTB200_MAX_GROUPS + 1];
+  int32_t group_ooff[MTB200_MAX_GROUPS][3];
+  int32_t ntaps;
+  int32_t tap_off[MTB200_MAX_TAPS][3];
+  int32_t tap_widx[MTB200_MAX_TAPS];
+  int32_t accumulate;   /* 1: out += result (gradient accumulation into a skip buffer) */
+  int32_t impl;         /* 0 = auto, 1 = CUDA-core FFMA kernel, 2 = tcgen05 tensor-core kernel */
+} mtb200_conv_params;
+
+/* Weight-gradient of the same tap-table problem:
+ *     dw[widx_t][co][ci] += sum_{b,o} dy[b, o*os + ooff_g, co] * f(x[b, o*is + off_t, ci])      (fp32, atomically)
+ * `x`/`xform`/in_* describe the forward input, `dy`/out_* the gradient w.r.t. the forward output.               */
+typedef struct {
+  const void* x;
+  const void* dy;
+  float* dw;            /* [n_widx][Cout][Cin] fp32, caller zero-initialises */
+  const float* xform;   /* as in mtb200_conv_params */
+  int32_t dtype;
+  int32_t B;
+  int32_t Di, Hi, Wi, in_ldc, in_coff, Cin;
+  int32_t Dof, Hof, Wof, out_ldc, out_coff, Cout;
+  int32_t Do, Ho, Wo;
+  int32_t is[3], os[3];
+  int32_t ngroups;
+  int32_t group_tap_begin[MTB200_MAX_GROUPS + 1];
+  int32_t group_ooff[MTB200_MAX_GROUPS][3];
+  int32_t ntaps;
+  int32_t tap_off[MTB200_MAX_TAPS][3];
+  int32_t tap_widx[MTB200_MAX_TAPS];
+  int32_t impl;
+} mtb200_wgrad_params;
+
+/* ---- library / error handling -------------------------------------------------------------------------------- */
+int mtb200_version(void);
+const char* mtb200_last_error(void);
+/* 1 if the tcgen05 path was compiled in and the current device is sm_100; 0 otherwise. */
+int mtb200_has_tcgen05(void);
+
+/* ---- a1/a2/a4/a5: conv -> (stats) ; replaces nn.Conv3d / nn.ConvTranspose3d calls at
+ *      generic_UNet.py:57,66 (conv in ConvDropoutNormNonlin), :335-336 + :391 (tu), :350-351 + :394 (seg_outputs),
+ *      custom_modules/conv_blocks.py:161-172,188-199 (BasicResidualBlock convs), generic_modular_UNet.py:235-251      */
+int mtb200_conv_taps(const mtb200_conv_params* p, void* stream);
+/* autograd of the above w.r.t. the weights (replaces cuDNN wgrad behind loss.backward(),
+ * MultiTalent_Trainer_DDP.py:350,362) */
+int mtb200_wgrad_taps(const mtb200_wgrad_params* p, void* stream);
+/* column sums: out[c] (+)= sum_rows m[row*ldc + coff + c]   (bias gradients), fp32 out */
+int mtb200_colsum(const void* m, int32_t dtype, int64_t rows, int32_t ldc, int32_t coff, int32_t C, float* out,
+                  void* stream);
+
+/* ---- a1: InstanceNorm3d(eps, affine) + LeakyReLU; replaces generic_UNet.py:63-64,70 / conv_blocks.py:173-186 ------ */
+/* stats [B][C][2] doubles {sum, sumsq} over `nvox` voxels -> xform [B][C][4] {scale=gamma*rstd, shift=beta-mean*scale,
+ * slope, 0} and meanrstd [B][C][2].  gamma/beta are [C] (C = padded channel count; padded entries must be 0).    */
+int mtb200_in_finalize(const double* stats, const float* gamma, const float* beta, int32_t B, int32_t C, int64_t nvox,
+                       float eps, float slope, float* xform, float* meanrstd, void* stream);
+/* per-(b,c) sum / sum-of-squares of an NDHWC tensor (used when the producer had no stats epilogue) */
+int mtb200_in_stats(const void* y, int32_t dtype, int32_t B, int64_t nvox, int32_t ldc, int32_t coff, int32_t C,
+                    double* stats, void* stream);
+/* out = f(y) with f from xform (materialise the normalised activation); optional residual:
+ * out = lrelu_slope2( f(y) + g(res) ) where g is res's own transform (identity if res_xform NULL)  -- the tail of
+ * BasicResidualBlock.forward (conv_blocks.py:205-213) */
+int mtb200_norm_act(const void* y, int32_t in_ldc, int32_t in_coff, void* out, int32_t out_ldc, int32_t out_coff,
+                    int32_t dtype, int32_t B, int64_t nvox, int32_t C, const float* xform, const void* res,
+                    int32_t res_ldc, int32_t res_coff, const float* res_xform, float slope2, void* stream);
+/* backward of act = lrelu(gamma*xhat+beta): pass 1 accumulates red[B][C][2] doubles {sum dv, sum dv*xhat} */
+int mtb200_in_bwd_reduce(const void* dact, int32_t d_ldc, int32_t d_coff, const void* y, int32_t y_ldc, int32_t y_coff,
+                         int32_t dtype, int32_t B, int64_t nvox, int32_t C, const float* xform, const float* meanrstd,
+                         double* red, void* stream);
+/* pass 2: dy = rstd*gamma*(dv - mean(dv) - xhat*mean(dv*xhat)); also dgamma[c] += sum_b red[..][1], dbeta += red[..][0]
+ * (done once by the first block).  dy may alias dact. */
+int mtb200_in_bwd_apply(const void* dact, int32_t d_ldc, int32_t d_coff, const void* y, int32_t y_ldc, int32_t y_coff,
+                        void* dy, int32_t dy_ldc, int32_t dy_coff, int32_t dtype, int32_t B, int64_t nvox, int32_t C,
+                        const float* xform, const float* meanrstd, const float* gamma, const double* red,
+                        float* dgamma, float* dbeta, void* stream);
+/* dv = dact * lrelu'(f(y))  only (no norm): used for the second LeakyReLU of a residual block */
+int mtb200_lrelu_bwd(const void* dact, const void* act, void* dv, int32_t dtype, int64_t n, float slope, void* stream);
+
+/* ---- a9/a10: MultiTalent multi-head loss (sigmoid + BCE + pooled soft Dice); replaces the python loop at
+ *      MultiTalent_Trainer_DDP.py:567-594 (stats), :596-606 (Dice), and its autograd ------------------------------ */
+/* pass 1: stats[b][j][4] doubles += {sum bce, sum sigma*y, sum sigma, sum y} over the voxels of sample b for every
+ * channel j whose bit is set in valid_mask[b]; y = bit j of pos_mask[label].  logits NDHWC [B][nvox][ldc]; target
+ * float32 label map [B][nvox] (integer-valued, MultiTalent_Trainer_DDP.py:580-584). */
+int mtb200_mt_loss_stats(const void* logits, int32_t dtype, int32_t ldc, int32_t C, const float* target, int32_t B,
+                         int64_t nvox, const uint64_t* valid_mask, const uint64_t* pos_mask, int32_t n_labels,
+                         double* stats, void* stream);
+/* tiny on-device finalize for one scale: local stats [B][C][4] + pooled {tp, sigma+y} of ALL ranks
+ * pooled[B][C][2] (= sum over ranks of local {tp, sum sigma + sum y}; NULL = derive from the local stats, world 1)
+ * -> losses[3] += w*{ce - dc, ce, dc}; coef[B][C][4] = {w/nvox, w*W*2/D, w*W*2*TP/D^2, valid} for pass 2 */
+int mtb200_mt_loss_finalize(const double* stats, const double* pooled, const uint64_t* valid_mask, int32_t B, int32_t C,
+                            int64_t nvox, float weight, float world_size, float* losses, float* coef, void* stream);
+/* pass 2: dlogits[b][v][j] = gscale * ( coef0*(sigma - y) - sigma*(1-sigma)*(y*coef1 - coef2) ) for valid (b,j), else 0 */
+int mtb200_mt_loss_bwd(const void* logits, int32_t dtype, int32_t ldc, int32_t C, const float* target, int32_t B,
+                       int64_t nvox, const uint64_t* pos_mask, int32_t n_labels, const float* coef, const float* gscale,
+                       void* dlogits, int32_t d_ldc, void* stream);
+
+/* ---- a14/a15/a16: sliding-window predictor; replaces neural_network.py:374-394 (tile loop + host numpy accumulate),
+ *      :531-589 (mirror TTA), :405 (normalise), :415-417 (threshold) ------------------------------------------------ */
+/* tile[0][d][h][w][c] = vol[c][x0+fd(d)][y0+fh(h)][z0+fw(w)] with optional flips (bit0: W, bit1: H, bit2: D);
+ * vol is float32 [Cin][X][Y][Z] (the reference's (c,x,y,z) numpy contract), tile NDHWC of `dtype` with ldc channels */
+int mtb200_sw_gather_tile(const float* vol, int32_t Cin, int32_t X, int32_t Y, int32_t Z, int32_t x0, int32_t y0,
+                          int32_t z0, int32_t pd, int32_t ph, int32_t pw, int32_t flip, void* tile, int32_t dtype,
+                          int32_t ldc, void* stream);
+/* acc[c][x0+d][y0+h][z0+w] += weight * gauss[d][h][w] * sigmoid(logits[fd(d)][fh(h)][fw(w)][c]),  c < C;
+ * if nb != NULL also nb[x0+d][..] += gauss[d][h][w]  (one weight volume instead of the reference's 47 copies).
+ * gauss may be NULL (= 1).  apply_sigmoid=0 accumulates the raw values. */
+int mtb200_sw_aggregate(const void* logits, int32_t dtype, int32_t ldc, int32_t C, int32_t pd, int32_t ph, int32_t pw,
+                        int32_t flip, const float* gauss, float weight, int32_t apply_sigmoid, float* acc, float* nb,
+                        int32_t X, int32_t Y, int32_t Z, int32_t x0, int32_t y0, int32_t z0, void* stream);
+/* acc[c][v] /= nb[v] in place; seg[v] = class_order[last c with prob > 0.5] else 0 (float32, neural_network.py:415-417)
+ * or argmax if class_order == NULL (seg then holds the channel index as float). */
+int mtb200_sw_finalize(float* acc, const float* nb, int32_t C, int64_t nvox, const float* class_order, float* seg,
+                       void* stream);
+
+/* ---- a12: clip_grad_norm_(12) + SGD(nesterov) on a flat fp32 parameter arena; replaces
+ *      MultiTalent_Trainer_DDP.py:351-353 / nnUNetTrainerV2.py:166-170 ---------------------------------------------- */
+int mtb200_sumsq(const float* g, int64_t n, double* out /* [1], caller zeroes */, void* stream);
+/* coef = min(1, max_norm/(sqrt(sumsq)*inv_scale + 1e-6)) * inv_scale; g' = g*coef + wd*p; buf = first ? g' : m*buf+g';
+ * p -= lr*(g' + m*buf).  skip the whole update if sumsq is not finite (GradScaler semantics). */
+int mtb200_sgd_step(float* p, const float* g, float* buf, int64_t n, const double* sumsq, float inv_scale,
+                    float max_norm, float lr, float momentum, float weight_decay, int32_t first_step, void* stream);
+
+/* ---- layout plumbing ------------------------------------------------------------------------------------------- */
+/* reference weight [Cout][Cin][kd][kh][kw] fp32 (Conv3d) or [Cin][Cout][kd][kh][kw] (ConvTranspose3d, transposed=1)
+ * -> packed [ntap][Cout_p][Cin_p] of `wdtype`, zero padded.  swap_io=1 packs the transpose [ntap][Cin_p][Cout_p]
+ * (operand of the data-gradient problem).  split/split_p describe a concatenated input whose two halves are padded
+ * separately: logical input channel ci >= split lives at packed index ci - split + split_p (split = 0: no split). */
+int mtb200_pack_weights(const float* w, int32_t Cout, int32_t Cin, int32_t ntap, int32_t transposed, int32_t swap_io,
+                        void* packed, int32_t wdtype, int32_t Cout_p, int32_t Cin_p, int32_t split, int32_t split_p,
+                        void* stream);
+/* packed fp32 gradient [ntap][Cout_p][Cin_p] -> reference layout, grad (+)= scale * dw */
+int mtb200_unpack_wgrad(const float* dw, int32_t Cout, int32_t Cin, int32_t ntap, int32_t transposed, int32_t Cout_p,
+                        int32_t Cin_p, int32_t split, int32_t split_p, float scale, int32_t accumulate, float* grad,
+                        void* stream);
+/* NCDHW fp32 [B][C][nvox] <-> NDHWC `dtype` [B][nvox][ldc] (+coff); padded channels are written as 0 */
+int mtb200_ncdhw_to_ndhwc(const float* src, int32_t B, int32_t C, int64_t nvox, void* dst, int32_t dtype, int32_t ldc,
+                          int32_t coff, int32_t Cp, void* stream);
+int mtb200_ndhwc_to_ncdhw(const void* src, int32_t dtype, int32_t ldc, int32_t coff, int32_t B, int32_t C, int64_t nvox,
+                          float* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTB200_H */

@@ -1,0 +1,103 @@
+// Shared device/host helpers for libmtb200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "mtb200.h"
+
+namespace mtb {
+
+// ---- error plumbing: never abort/throw across the C boundary ----------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);  // cudaGetLastError -> status
+
+#define MTB_REQUIRE(cond, ...)          \
+  do {                                  \
+    if (!(cond)) {                      \
+      mtb::set_error(__VA_ARGS__);      \
+      return MTB200_ERR_INVALID;        \
+    }                                   \
+  } while (0)
+
+// ---- storage-type traits ------------------------------------------------------------------------------------------
+template <typename T> struct Traits;
+template <> struct Traits<float> {
+  static __device__ __forceinline__ float ld(const float* p) { return *p; }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+  static __device__ __forceinline__ float round(float v) { return v; }
+};
+template <> struct Traits<__nv_bfloat16> {
+  static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+  static __device__ __forceinline__ float round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+};
+template <> struct Traits<__half> {
+  static __device__ __forceinline__ float ld(const __half* p) { return __half2float(*p); }
+  static __device__ __forceinline__ void st(__half* p, float v) { *p = __float2half_rn(v); }
+  static __device__ __forceinline__ float round(float v) { return __half2float(__float2half_rn(v)); }
+};
+
+// load / store 8 consecutive elements (16-byte aligned for 16-bit types, 32-byte for float) as floats
+template <typename T> __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  uint4 r = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <> __device__ __forceinline__ void load8<__half>(const __half* p, float (&v)[8]) {
+  uint4 r = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+template <> __device__ __forceinline__ void store8<__half>(__half* p, const float (&v)[8]) {
+  uint4 r;
+  __half2* h = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// dispatch on the activation dtype enum
+#define MTB_DISPATCH_DTYPE(dt, T, ...)                                        \
+  switch (dt) {                                                               \
+    case MTB200_F32: { using T = float; __VA_ARGS__; break; }                 \
+    case MTB200_BF16: { using T = __nv_bfloat16; __VA_ARGS__; break; }        \
+    case MTB200_F16: { using T = __half; __VA_ARGS__; break; }                \
+    default: mtb::set_error("bad dtype %d", (int)(dt)); return MTB200_ERR_INVALID; \
+  }
+
+int num_sms();
+
+}  // namespace mtb

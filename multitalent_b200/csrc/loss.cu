@@ -1,0 +1,207 @@
+// MultiTalent multi-head loss: sigmoid + BCE-with-logits (mean over voxels per (sample, region)) - soft Dice on the
+// sigmoid pooled over ranks per (local batch index, channel).  Two streaming passes over the logits (HBM-bound):
+// pass 1 = statistics, pass 2 = d(loss)/d(logits).  Replaces the python double loop at
+// MultiTalent_Trainer_DDP.py:567-606 and its autograd graph (~1e3 tiny kernel launches per step in the reference).
+#include "common.cuh"
+
+namespace mtb {
+
+constexpr int LT = 256;
+constexpr int MAX_LABELS = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(LT) mt_loss_stats_kernel(const T* __restrict__ logits, int ldc, int C,
+                                                           const float* __restrict__ target, long long nvox,
+                                                           const uint64_t* __restrict__ valid_mask,
+                                                           const uint64_t* __restrict__ pos_mask, int n_labels,
+                                                           double* __restrict__ stats) {
+  __shared__ uint64_t s_pos[MAX_LABELS];
+  __shared__ float sh[LT][8];
+  const int b = blockIdx.y;
+  const int G = C / 8;
+  const int vstride = LT / G;
+  const int cg = threadIdx.x % G, vlane = threadIdx.x / G;
+  const bool active = vlane < vstride;
+  if (threadIdx.x < MAX_LABELS) s_pos[threadIdx.x] = threadIdx.x < n_labels ? pos_mask[threadIdx.x] : 0ull;
+  __syncthreads();
+  const uint64_t valid = valid_mask[b];
+  const unsigned vbits = (unsigned)((valid >> (cg * 8)) & 0xffull);
+  const long long per = (nvox + gridDim.x - 1) / gridDim.x;
+  const long long v0 = (long long)blockIdx.x * per, v1 = min(nvox, v0 + per);
+
+  float part[4][8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[q][j] = 0.f;
+
+  if (active && vbits) {
+    const T* base = logits + (long long)b * nvox * ldc + cg * 8;
+    const float* tb = target + (long long)b * nvox;
+    for (long long v = v0 + vlane; v < v1; v += vstride) {
+      float z[8];
+      load8<T>(base + v * ldc, z);
+      const int lab = (int)tb[v];
+      const uint64_t pm = ((unsigned)lab < (unsigned)MAX_LABELS) ? s_pos[lab] : 0ull;
+      const unsigned ybits = (unsigned)((pm >> (cg * 8)) & 0xffull);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (vbits & (1u << j)) {
+          const float y = (ybits >> j) & 1u ? 1.f : 0.f;
+          const float e = expf(-fabsf(z[j]));
+          const float bce = fmaxf(z[j], 0.f) - z[j] * y + log1pf(e);
+          const float sig = z[j] >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+          part[0][j] += bce;
+          part[1][j] = fmaf(sig, y, part[1][j]);
+          part[2][j] += sig;
+          part[3][j] += y;
+        }
+      }
+    }
+  }
+  // block reduce over the voxel lanes, one double atomic per (channel, stat)
+  double* dst = stats + (long long)b * C * 4;
+  for (int q = 0; q < 4; ++q) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] = active ? part[q][j] : 0.f;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < G * 8; idx += LT) {
+      const int g = idx / 8, j = idx % 8;
+      float s = 0.f;
+      for (int vl = 0; vl < vstride; ++vl) s += sh[vl * G + g][j];
+      if (s != 0.f) atomicAdd(dst + (long long)(g * 8 + j) * 4 + q, (double)s);
+    }
+  }
+}
+
+static dim3 loss_grid(long long nvox, int B, int C) {
+  const int vstride = LT / (C / 8);
+  long long want = (8LL * num_sms() + B - 1) / B;
+  long long maxb = (nvox + (long long)vstride * 8 - 1) / ((long long)vstride * 8);
+  return dim3((unsigned)max(1LL, min(want, maxb)), (unsigned)B);
+}
+
+int mt_loss_stats(const void* logits, int dtype, int ldc, int C, const float* target, int B, long long nvox,
+                  const uint64_t* valid_mask, const uint64_t* pos_mask, int n_labels, double* stats, cudaStream_t s) {
+  MTB_REQUIRE(C % 8 == 0 && C <= 64 && ldc % 8 == 0 && C <= ldc, "mt_loss_stats: C=%d (padded, <=64) ldc=%d", C, ldc);
+  MTB_REQUIRE(n_labels <= MAX_LABELS, "mt_loss_stats: n_labels=%d > %d", n_labels, MAX_LABELS);
+  dim3 grid = loss_grid(nvox, B, C);
+  MTB_DISPATCH_DTYPE(dtype, T, (mt_loss_stats_kernel<T><<<grid, LT, 0, s>>>(
+      reinterpret_cast<const T*>(logits), ldc, C, target, nvox, valid_mask, pos_mask, n_labels, stats)));
+  return check_launch("mt_loss_stats");
+}
+
+// ---- finalize (tiny): loss scalars and per-(b,j) gradient coefficients --------------------------------------------
+__global__ void mt_loss_finalize_kernel(const double* __restrict__ stats, const double* __restrict__ pooled,
+                                        const uint64_t* __restrict__ valid_mask, int B, int C, double inv_nvox,
+                                        float weight, float world, float* __restrict__ losses,
+                                        float4* __restrict__ coef) {
+  __shared__ double s_ce[256], s_dc[256];
+  double ce = 0.0, dc = 0.0;
+  for (int i = threadIdx.x; i < B * C; i += blockDim.x) {
+    const int b = i / C, j = i % C;
+    const bool valid = (valid_mask[b] >> j) & 1ull;
+    const double TP = pooled ? pooled[2 * i] : stats[4 * i + 1];
+    const double D = pooled ? pooled[2 * i + 1] : stats[4 * i + 2] + stats[4 * i + 3];
+    const double Dc = D < 1e-7 ? 1e-7 : D;
+    dc += 2.0 * TP / Dc;
+    float c1 = 0.f, c2 = 0.f;
+    if (valid) {
+      ce += stats[4 * i] * inv_nvox;
+      c1 = (float)((double)weight * world * 2.0 / Dc);
+      c2 = D < 1e-7 ? 0.f : (float)((double)weight * world * 2.0 * TP / (D * D));
+    }
+    coef[i] = make_float4(valid ? (float)(weight * inv_nvox) : 0.f, c1, c2, valid ? 1.f : 0.f);
+  }
+  s_ce[threadIdx.x] = ce;
+  s_dc[threadIdx.x] = dc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, d = 0.0;
+    for (int i = 0; i < blockDim.x; ++i) { a += s_ce[i]; d += s_dc[i]; }
+    losses[0] += weight * (float)(a - d);
+    losses[1] += weight * (float)a;
+    losses[2] += weight * (float)d;
+  }
+}
+
+int mt_loss_finalize(const double* stats, const double* pooled, const uint64_t* valid_mask, int B, int C, long long nvox,
+                     float weight, float world_size, float* losses, float* coef, cudaStream_t s) {
+  MTB_REQUIRE(C <= 64, "mt_loss_finalize: C=%d", C);
+  mt_loss_finalize_kernel<<<1, 256, 0, s>>>(stats, pooled, valid_mask, B, C, 1.0 / (double)nvox, weight, world_size,
+                                            losses, reinterpret_cast<float4*>(coef));
+  return check_launch("mt_loss_finalize");
+}
+
+// ---- pass 2: dlogits ----------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LT) mt_loss_bwd_kernel(const T* __restrict__ logits, int ldc, int C,
+                                                         const float* __restrict__ target, long long nvox,
+                                                         const uint64_t* __restrict__ pos_mask, int n_labels,
+                                                         const float4* __restrict__ coef,
+                                                         const float* __restrict__ gscale, T* __restrict__ dlogits,
+                                                         int d_ldc) {
+  __shared__ uint64_t s_pos[MAX_LABELS];
+  const int b = blockIdx.y;
+  const int G = C / 8;
+  const int vstride = LT / G;
+  const int cg = threadIdx.x % G, vlane = threadIdx.x / G;
+  if (threadIdx.x < MAX_LABELS) s_pos[threadIdx.x] = threadIdx.x < n_labels ? pos_mask[threadIdx.x] : 0ull;
+  __syncthreads();
+  if (vlane >= vstride) return;
+  const float gs = gscale ? *gscale : 1.f;
+  float4 cf[8];
+  unsigned vbits = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    cf[j] = coef[(long long)b * C + cg * 8 + j];
+    if (cf[j].w != 0.f) vbits |= 1u << j;
+    cf[j].x *= gs; cf[j].y *= gs; cf[j].z *= gs;
+  }
+  const long long per = (nvox + gridDim.x - 1) / gridDim.x;
+  const long long v0 = (long long)blockIdx.x * per, v1 = min(nvox, v0 + per);
+  const T* base = logits + (long long)b * nvox * ldc + cg * 8;
+  T* obase = dlogits + (long long)b * nvox * d_ldc + cg * 8;
+  const float* tb = target + (long long)b * nvox;
+  for (long long v = v0 + vlane; v < v1; v += vstride) {
+    float d[8];
+    if (vbits) {
+      float z[8];
+      load8<T>(base + v * ldc, z);
+      const int lab = (int)tb[v];
+      const uint64_t pm = ((unsigned)lab < (unsigned)MAX_LABELS) ? s_pos[lab] : 0ull;
+      const unsigned ybits = (unsigned)((pm >> (cg * 8)) & 0xffull);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (vbits & (1u << j)) {
+          const float y = (ybits >> j) & 1u ? 1.f : 0.f;
+          const float e = expf(-fabsf(z[j]));
+          const float sig = z[j] >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+          d[j] = cf[j].x * (sig - y) - sig * (1.f - sig) * (y * cf[j].y - cf[j].z);
+        } else {
+          d[j] = 0.f;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = 0.f;
+    }
+    store8<T>(obase + v * d_ldc, d);
+  }
+}
+
+int mt_loss_bwd(const void* logits, int dtype, int ldc, int C, const float* target, int B, long long nvox,
+                const uint64_t* pos_mask, int n_labels, const float* coef, const float* gscale, void* dlogits, int d_ldc,
+                cudaStream_t s) {
+  MTB_REQUIRE(C % 8 == 0 && C <= 64 && ldc % 8 == 0 && d_ldc % 8 == 0 && C <= ldc && C <= d_ldc,
+              "mt_loss_bwd: C=%d ldc=%d d_ldc=%d", C, ldc, d_ldc);
+  MTB_REQUIRE(n_labels <= MAX_LABELS, "mt_loss_bwd: n_labels=%d > %d", n_labels, MAX_LABELS);
+  dim3 grid = loss_grid(nvox, B, C);
+  MTB_DISPATCH_DTYPE(dtype, T, (mt_loss_bwd_kernel<T><<<grid, LT, 0, s>>>(
+      reinterpret_cast<const T*>(logits), ldc, C, target, nvox, pos_mask, n_labels,
+      reinterpret_cast<const float4*>(coef), gscale, reinterpret_cast<T*>(dlogits), d_ldc)));
+  return check_launch("mt_loss_bwd");
+}
+
+}  // namespace mtb

@@ -1,0 +1,182 @@
+// Optimizer step on a flat fp32 arena (clip_grad_norm_ + SGD nesterov) and layout plumbing (weight packing,
+// NCDHW <-> NDHWC).
+#include "common.cuh"
+
+namespace mtb {
+
+// ---- sum of squares ----------------------------------------------------------------------------------------------
+__global__ void sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ out) {
+  double acc = 0.0;
+  const long long n4 = n / 4;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = g4[i];
+    acc += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; ++i) acc += (double)g[i] * g[i];
+  acc = warp_sum(acc);
+  __shared__ double sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    atomicAdd(out, t);
+  }
+}
+
+int sumsq(const float* g, long long n, double* out, cudaStream_t s) {
+  MTB_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "sumsq: pointer must be 16-byte aligned");
+  const int blocks = (int)max(1LL, min((long long)num_sms() * 4, (n / 4 + 255) / 256));
+  sumsq_kernel<<<blocks, 256, 0, s>>>(g, n, out);
+  return check_launch("sumsq");
+}
+
+// ---- clip + SGD(nesterov) ------------------------------------------------------------------------------------------
+__global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n,
+                                const double* __restrict__ sumsq, float inv_scale, float max_norm, float lr,
+                                float momentum, float wd, int first) {
+  const double ss = *sumsq;
+  if (!isfinite(ss)) return;  // GradScaler: skip the step on inf/nan gradients
+  const float total_norm = (float)sqrt(ss) * inv_scale;
+  float clip = max_norm / (total_norm + 1e-6f);
+  clip = clip > 1.f ? 1.f : clip;
+  const float coef = clip * inv_scale;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float pi = p[i];
+    const float gi = fmaf(g[i], coef, wd * pi);
+    const float b = first ? gi : fmaf(momentum, buf[i], gi);
+    buf[i] = b;
+    p[i] = pi - lr * fmaf(momentum, b, gi);
+  }
+}
+
+int sgd_step(float* p, const float* g, float* buf, long long n, const double* sumsq_, float inv_scale, float max_norm,
+             float lr, float momentum, float wd, int first, cudaStream_t s) {
+  const int blocks = (int)max(1LL, min((long long)num_sms() * 8, (n + 255) / 256));
+  sgd_step_kernel<<<blocks, 256, 0, s>>>(p, g, buf, n, sumsq_, inv_scale, max_norm, lr, momentum, wd, first);
+  return check_launch("sgd_step");
+}
+
+// ---- weight packing ---------------------------------------------------------------------------------------------------
+// W(co, ci, t) = transposed ? w[ci][co][t] : w[co][ci][t];  packed[t][r][c] with (r,c) = swap_io ? (ci,co) : (co,ci)
+template <typename WT>
+__global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int ntap, int transposed, int swap_io,
+                                    WT* __restrict__ packed, int Cout_p, int Cin_p, int split, int split_p) {
+  const int R = swap_io ? Cin_p : Cout_p, S = swap_io ? Cout_p : Cin_p;
+  const long long n = (long long)ntap * R * S;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % S);
+    const int r = (int)((i / S) % R);
+    const int t = (int)(i / ((long long)S * R));
+    const int co = swap_io ? c : r;
+    int cip = swap_io ? r : c;
+    // packed input channel -> logical input channel (two separately padded halves of a concatenated input)
+    int ci;
+    if (split > 0) ci = cip < split_p ? (cip < split ? cip : -1) : (cip - split_p + split);
+    else ci = cip;
+    float v = 0.f;
+    if (co < Cout && ci >= 0 && ci < Cin)
+      v = transposed ? w[((long long)ci * Cout + co) * ntap + t] : w[((long long)co * Cin + ci) * ntap + t];
+    Traits<WT>::st(packed + i, v);
+  }
+}
+
+int pack_weights(const float* w, int Cout, int Cin, int ntap, int transposed, int swap_io, void* packed, int wdtype,
+                 int Cout_p, int Cin_p, int split, int split_p, cudaStream_t s) {
+  MTB_REQUIRE(Cout <= Cout_p && (split > 0 ? (split <= split_p && Cin - split <= Cin_p - split_p) : Cin <= Cin_p),
+              "pack_weights: padded sizes too small (Cout %d/%d Cin %d/%d split %d/%d)", Cout, Cout_p, Cin, Cin_p, split,
+              split_p);
+  const long long n = (long long)ntap * Cout_p * Cin_p;
+  const int blocks = (int)max(1LL, min((long long)num_sms() * 8, (n + 255) / 256));
+  MTB_DISPATCH_DTYPE(wdtype, WT, (pack_weights_kernel<WT><<<blocks, 256, 0, s>>>(
+      w, Cout, Cin, ntap, transposed, swap_io, reinterpret_cast<WT*>(packed), Cout_p, Cin_p, split, split_p)));
+  return check_launch("pack_weights");
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dw, int Cout, int Cin, int ntap, int transposed, int Cout_p,
+                                    int Cin_p, int split, int split_p, float scale, int accumulate,
+                                    float* __restrict__ grad) {
+  const long long n = (long long)Cout * Cin * ntap;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % ntap);
+    const int a = (int)((i / ntap) % (transposed ? Cout : Cin));
+    const int b = (int)(i / ((long long)ntap * (transposed ? Cout : Cin)));
+    const int co = transposed ? a : b, ci = transposed ? b : a;
+    const int cip = (split > 0 && ci >= split) ? ci - split + split_p : ci;
+    const float v = scale * dw[((long long)t * Cout_p + co) * Cin_p + cip];
+    grad[i] = accumulate ? grad[i] + v : v;
+  }
+}
+
+int unpack_wgrad(const float* dw, int Cout, int Cin, int ntap, int transposed, int Cout_p, int Cin_p, int split,
+                 int split_p, float scale, int accumulate, float* grad, cudaStream_t s) {
+  const long long n = (long long)Cout * Cin * ntap;
+  const int blocks = (int)max(1LL, min((long long)num_sms() * 8, (n + 255) / 256));
+  unpack_wgrad_kernel<<<blocks, 256, 0, s>>>(dw, Cout, Cin, ntap, transposed, Cout_p, Cin_p, split, split_p, scale,
+                                             accumulate, grad);
+  return check_launch("unpack_wgrad");
+}
+
+// ---- NCDHW fp32 <-> NDHWC --------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, int C, long long nvox, T* __restrict__ dst, int ldc,
+                                      int coff, int Cp) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const long long v0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const long long v = v0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && v < nvox) ? src[((long long)b * C + c) * nvox + v] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long v = v0 + i;
+    const int c = c0 + threadIdx.x;
+    if (v < nvox && c < Cp) Traits<T>::st(dst + ((long long)b * nvox + v) * ldc + coff + c, tile[threadIdx.x][i]);
+  }
+}
+
+int ncdhw_to_ndhwc(const float* src, int B, int C, long long nvox, void* dst, int dtype, int ldc, int coff, int Cp,
+                   cudaStream_t s) {
+  MTB_REQUIRE(C <= Cp && coff + Cp <= ldc, "ncdhw_to_ndhwc: C=%d Cp=%d coff=%d ldc=%d", C, Cp, coff, ldc);
+  if (nvox == 0 || B == 0) return MTB200_OK;
+  dim3 grid((unsigned)((nvox + 31) / 32), (Cp + 31) / 32, B), block(32, 8);
+  MTB_DISPATCH_DTYPE(dtype, T, (ncdhw_to_ndhwc_kernel<T><<<grid, block, 0, s>>>(src, C, nvox, reinterpret_cast<T*>(dst),
+                                                                                 ldc, coff, Cp)));
+  return check_launch("ncdhw_to_ndhwc");
+}
+
+template <typename T>
+__global__ void ndhwc_to_ncdhw_kernel(const T* __restrict__ src, int ldc, int coff, int C, long long nvox,
+                                      float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const long long v0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long v = v0 + i;
+    const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (v < nvox && c < C) ? Traits<T>::ld(src + ((long long)b * nvox + v) * ldc + coff + c) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const long long v = v0 + threadIdx.x;
+    if (c < C && v < nvox) dst[((long long)b * C + c) * nvox + v] = tile[threadIdx.x][i];
+  }
+}
+
+int ndhwc_to_ncdhw(const void* src, int dtype, int ldc, int coff, int B, int C, long long nvox, float* dst,
+                   cudaStream_t s) {
+  if (nvox == 0 || B == 0) return MTB200_OK;
+  dim3 grid((unsigned)((nvox + 31) / 32), (C + 31) / 32, B), block(32, 8);
+  MTB_DISPATCH_DTYPE(dtype, T, (ndhwc_to_ncdhw_kernel<T><<<grid, block, 0, s>>>(reinterpret_cast<const T*>(src), ldc,
+                                                                                 coff, C, nvox, dst)));
+  return check_launch("ndhwc_to_ncdhw");
+}
+
+}  // namespace mtb

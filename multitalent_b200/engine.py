@@ -1,0 +1,484 @@
+"""Host-side executor for the native U-Net path: channels-last (NDHWC) feature buffers, tap tables for every
+convolution variant, and a closure tape for the backward pass.  All arithmetic happens in libmtb200.so (ctypes);
+PyTorch is used for device memory, streams and tiny bookkeeping tensors only.
+
+Data layout (DESIGN.md section "HBM layout"): a feature map is a slice [coff, coff+Cp) of a buffer [B, D, H, W, ldc];
+channel counts are padded (30->32, 60->64, 120->128, 240->256, 320->320, 47->48, 1->16) and padded channels are zero.
+A conv writes its RAW output plus per-(b, c) sum / sum-of-squares; InstanceNorm + LeakyReLU are carried as a pending
+per-(b, c) affine `xform` and applied by the CONSUMER while it loads the tile (norm-on-load), so the reference's
+instnorm/lrelu read+write passes (generic_UNet.py:70) and torch.cat (generic_UNet.py:392) disappear.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+LRELU_SLOPE = 0.01
+IN_EPS = 1e-5
+
+
+_weights_epoch = 0
+
+
+def bump_weights_epoch():
+    """Call after parameters were modified behind torch's version counters (in-place arena update by a kernel)."""
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+def pad_channels(c: int) -> int:
+    p = max(16, (c + 15) // 16 * 16)
+    if p > 128 and p % 64:
+        p = (p + 63) // 64 * 64
+    return p
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# tap tables
+# --------------------------------------------------------------------------------------------------------------------
+@dataclass
+class TapTable:
+    taps: List[Tuple[Tuple[int, int, int], int]]            # ((dz, dy, dx), weight slice)
+    group_begin: List[int]
+    group_ooff: List[Tuple[int, int, int]]
+    in_stride: Tuple[int, int, int]
+    out_stride: Tuple[int, int, int]
+
+    def fill(self, p):
+        assert len(self.taps) <= L.MAX_TAPS and len(self.group_ooff) <= L.MAX_GROUPS
+        p.ntaps = len(self.taps)
+        p.ngroups = len(self.group_ooff)
+        for i, v in enumerate(self.group_begin):
+            p.group_tap_begin[i] = v
+        for g, o in enumerate(self.group_ooff):
+            for k in range(3):
+                p.group_ooff[g][k] = o[k]
+        for t, (off, widx) in enumerate(self.taps):
+            for k in range(3):
+                p.tap_off[t][k] = off[k]
+            p.tap_widx[t] = widx
+        for k in range(3):
+            p.is_[k] = self.in_stride[k]
+            p.os_[k] = self.out_stride[k]
+
+
+def _widx(k, kernel):
+    return (k[0] * kernel[1] + k[1]) * kernel[2] + k[2]
+
+
+def _kernel_positions(kernel):
+    return [(a, b, c) for a in range(kernel[0]) for b in range(kernel[1]) for c in range(kernel[2])]
+
+
+def taps_conv_fwd(kernel, stride) -> TapTable:
+    """Conv3d(kernel, stride, padding=(k-1)//2): out[o] = sum_k W[k] in[o*s + k - p]."""
+    pad = [(k - 1) // 2 for k in kernel]
+    taps = [(tuple(k[i] - pad[i] for i in range(3)), _widx(k, kernel)) for k in _kernel_positions(kernel)]
+    return TapTable(taps, [0, len(taps)], [(0, 0, 0)], tuple(stride), (1, 1, 1))
+
+
+def taps_conv_dgrad(kernel, stride) -> TapTable:
+    """Data gradient of the above: d_in[s*q + r] = sum_{k: (r - k + p) % s == 0} W[k]^T dy[q + (r - k + p)/s].
+    One group per residue class r (prod(stride) groups); every input voxel is written exactly once."""
+    pad = [(k - 1) // 2 for k in kernel]
+    taps, begin, ooff = [], [0], []
+    for r in _kernel_positions(stride):
+        for k in _kernel_positions(kernel):
+            if all((r[i] - k[i] + pad[i]) % stride[i] == 0 for i in range(3)):
+                off = tuple((r[i] - k[i] + pad[i]) // stride[i] for i in range(3))
+                taps.append((off, _widx(k, kernel)))
+        begin.append(len(taps))
+        ooff.append(r)
+    return TapTable(taps, begin, ooff, (1, 1, 1), tuple(stride))
+
+
+def taps_convT_fwd(kernel) -> TapTable:
+    """ConvTranspose3d(kernel == stride): out[q*s + k] = W[k] in[q]; one single-tap group per kernel position."""
+    taps, begin, ooff = [], [0], []
+    for k in _kernel_positions(kernel):
+        taps.append(((0, 0, 0), _widx(k, kernel)))
+        begin.append(len(taps))
+        ooff.append(k)
+    return TapTable(taps, begin, ooff, (1, 1, 1), tuple(kernel))
+
+
+def taps_convT_dgrad(kernel) -> TapTable:
+    """Data gradient of ConvTranspose3d(kernel == stride): d_in[q] = sum_k W[k]^T dy[q*s + k]."""
+    taps = [(k, _widx(k, kernel)) for k in _kernel_positions(kernel)]
+    return TapTable(taps, [0, len(taps)], [(0, 0, 0)], tuple(kernel), (1, 1, 1))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# feature maps
+# --------------------------------------------------------------------------------------------------------------------
+@dataclass
+class Feat:
+    buf: torch.Tensor                   # [B, D, H, W, ldc]
+    coff: int
+    C: int                              # logical channels
+    Cp: int                             # padded channels (slice width)
+    xform: Optional[torch.Tensor] = None     # [B, Cp, 4] pending {scale, shift, slope, 0}; None = already materialised
+    meanrstd: Optional[torch.Tensor] = None  # [B, Cp, 2]
+
+    @property
+    def dims(self):
+        return tuple(self.buf.shape[:4])
+
+    @property
+    def ldc(self):
+        return self.buf.shape[4]
+
+    @property
+    def nvox(self):
+        return self.buf.shape[1] * self.buf.shape[2] * self.buf.shape[3]
+
+    def ptr(self):
+        return self.buf.data_ptr()
+
+    def as_ncdhw(self):
+        """NCDHW-shaped strided view of the logical channels (what the reference's callers index)."""
+        return self.buf[..., self.coff:self.coff + self.C].permute(0, 4, 1, 2, 3)
+
+
+def ndhwc_view_info(t: torch.Tensor):
+    """If `t` (NCDHW-shaped) is a channels-last view of an NDHWC buffer, return (ldc); else None."""
+    if t.dim() != 5:
+        return None
+    B, Cc, D, H, W = t.shape
+    s = t.stride()
+    if s[1] != 1:
+        return None
+    ldc = s[4]
+    if ldc < Cc or ldc % 8 or s[3] != W * ldc or s[2] != H * W * ldc or s[0] != D * H * W * ldc:
+        return None
+    if t.data_ptr() % 16:
+        return None
+    return ldc
+
+
+class ConvOp:
+    """One convolution's parameters + packed copies.  `weight` is the reference-layout nn.Parameter
+    ([Cout, Cin, kd, kh, kw], or [Cin, Cout, kd, kh, kw] for ConvTranspose3d)."""
+
+    def __init__(self, weight, bias, kernel, stride, transposed=False, split=0):
+        self.weight, self.bias = weight, bias
+        self.kernel, self.stride = tuple(int(k) for k in kernel), tuple(int(s) for s in stride)
+        self.transposed = transposed
+        if transposed:
+            self.Cin, self.Cout = weight.shape[0], weight.shape[1]
+            assert self.kernel == self.stride, "only ConvTranspose3d with kernel == stride is on the native path"
+        else:
+            self.Cout, self.Cin = weight.shape[0], weight.shape[1]
+        self.split = split  # logical channels of the first half of a concatenated input (0 = plain input)
+        if split:
+            self.split_p = pad_channels(split)
+            self.Cin_p = self.split_p + pad_channels(self.Cin - split)
+        else:
+            self.split_p = 0
+            self.Cin_p = pad_channels(self.Cin)
+        self.Cout_p = pad_channels(self.Cout)
+        self.ntap = self.kernel[0] * self.kernel[1] * self.kernel[2]
+        if transposed:
+            self.fwd_taps = taps_convT_fwd(self.kernel)
+            self.dgrad_taps = taps_convT_dgrad(self.kernel)
+        else:
+            self.fwd_taps = taps_conv_fwd(self.kernel, self.stride)
+            self.dgrad_taps = taps_conv_dgrad(self.kernel, self.stride)
+        self._packed = {}
+
+    def out_dims(self, dims):
+        B, D, H, W = dims
+        if self.transposed:
+            return (B, D * self.stride[0], H * self.stride[1], W * self.stride[2])
+        for n, s in zip((D, H, W), self.stride):
+            assert n % s == 0, "spatial size %s not divisible by stride %s" % ((D, H, W), self.stride)
+        return (B, D // self.stride[0], H // self.stride[1], W // self.stride[2])
+
+    def packed(self, wdtype, swap_io):
+        """[ntap][Cout_p][Cin_p] (forward / wgrad layout) or, swap_io, [ntap][Cin_p][Cout_p] (dgrad operand)."""
+        key = (wdtype, swap_io)
+        ver = (self.weight._version, _weights_epoch, self.weight.data_ptr())
+        hit = self._packed.get(key)
+        if hit is not None and hit[0] == ver and hit[1].device == self.weight.device:
+            return hit[1]
+        w = self.weight.detach()
+        assert w.dtype == torch.float32 and w.is_contiguous()
+        out = torch.empty((self.ntap, self.Cin_p, self.Cout_p) if swap_io else (self.ntap, self.Cout_p, self.Cin_p),
+                          dtype=wdtype, device=w.device)
+        L.call("mtb200_pack_weights", L.ptr(w), self.Cout, self.Cin, self.ntap, int(self.transposed), int(swap_io),
+               L.ptr(out), L.dtype_enum(wdtype), self.Cout_p, self.Cin_p, self.split, self.split_p, L.stream_ptr())
+        self._packed[key] = (ver, out)
+        return out
+
+
+def _padded(v: Optional[torch.Tensor], n: int, fill=0.0):
+    if v is None:
+        return None
+    v = v.detach().float()
+    if v.numel() == n:
+        return v.contiguous()
+    out = torch.full((n,), fill, dtype=torch.float32, device=v.device)
+    out[:v.numel()] = v
+    return out
+
+
+class Tape:
+    """Records what backward needs.  Gradients w.r.t. feature buffers are kept per underlying buffer so that the two
+    halves of a concatenated skip buffer share one gradient buffer."""
+
+    def __init__(self):
+        self.closures: List[Callable] = []
+        self.grad_bufs: Dict[int, torch.Tensor] = {}
+        self.grad_init: Dict[int, set] = {}
+        self.param_grads: Dict[int, torch.Tensor] = {}
+        self.keep = []  # keep python references to buffers alive
+
+    def grad_feat(self, f: Feat) -> Tuple[Feat, bool]:
+        """Gradient slice matching `f` and whether it already holds a value (=> producers must accumulate)."""
+        k = id(f.buf)
+        if k not in self.grad_bufs:
+            self.grad_bufs[k] = torch.empty_like(f.buf)
+            self.grad_init[k] = set()
+        blocks = set(range(f.coff // 16, (f.coff + f.Cp) // 16))
+        have = blocks & self.grad_init[k]
+        assert not have or have == blocks, "partially initialised gradient slice"
+        return Feat(self.grad_bufs[k], f.coff, f.C, f.Cp), bool(have)
+
+    def mark(self, f: Feat):
+        self.grad_init[id(f.buf)] |= set(range(f.coff // 16, (f.coff + f.Cp) // 16))
+
+    def has_grad(self, f: Feat) -> bool:
+        k = id(f.buf)
+        return k in self.grad_init and set(range(f.coff // 16, (f.coff + f.Cp) // 16)) <= self.grad_init[k]
+
+    def add_param_grad(self, p, g):
+        if p is None:
+            return
+        k = id(p)
+        if k in self.param_grads:
+            self.param_grads[k] = self.param_grads[k] + g
+        else:
+            self.param_grads[k] = g
+
+
+class Engine:
+    """Kernel-call layer.  `dtype` is the activation storage type: torch.float32 (T0 parity mode, CUDA-core kernels),
+    torch.bfloat16 / torch.float16 (T1, tensor-core kernels where available)."""
+
+    def __init__(self, dtype=torch.float32, impl=0):
+        self.dtype = dtype
+        self.impl = impl  # 0 auto, 1 force FFMA, 2 force tcgen05
+        self.wdtype = torch.float32 if dtype == torch.float32 else dtype
+
+    # ---- helpers ------------------------------------------------------------------------------------------------
+    def new_buf(self, dims, ldc, device, zero=False):
+        f = torch.zeros if zero else torch.empty
+        return f(tuple(dims) + (ldc,), dtype=self.dtype, device=device)
+
+    def input_feat(self, x: torch.Tensor) -> Feat:
+        """NCDHW fp32 input (to_torch.py:18-31 contract) -> NDHWC materialised feature (zero-padded channels)."""
+        assert x.dim() == 5 and x.is_cuda, "input must be a [B, C, D, H, W] CUDA tensor"
+        x = x.detach().float().contiguous()
+        B, Cc, D, H, W = x.shape
+        Cp = pad_channels(Cc)
+        buf = self.new_buf((B, D, H, W), Cp, x.device)
+        L.call("mtb200_ncdhw_to_ndhwc", L.ptr(x), B, Cc, D * H * W, L.ptr(buf), L.dtype_enum(self.dtype), Cp, 0, Cp,
+               L.stream_ptr())
+        return Feat(buf, 0, Cc, Cp)
+
+    @staticmethod
+    def conv_flops(op: "ConvOp", out_dims):
+        """Algorithmic FLOPs (2 x MAC, true channel counts) of one convolution; dgrad and wgrad cost the same."""
+        n = out_dims[0] * out_dims[1] * out_dims[2] * out_dims[3]
+        return 2.0 * op.Cin * op.Cout * n * (1 if op.transposed else op.ntap)
+
+    def _conv_call(self, table: TapTable, x: Feat, w_packed, bias_p, out: Feat, grid_dims, stats, accumulate, Cin_p,
+                   Cout_p, flops=0.0, tag="conv_fwd"):
+        p = L.ConvParams()
+        p.inp, p.out, p.w = x.ptr(), out.ptr(), w_packed.data_ptr()
+        p.bias = bias_p.data_ptr() if bias_p is not None else None
+        p.xform = x.xform.data_ptr() if x.xform is not None else None
+        p.stats = stats.data_ptr() if stats is not None else None
+        p.dtype, p.wdtype = L.dtype_enum(self.dtype), L.dtype_enum(w_packed.dtype)
+        p.B, p.Di, p.Hi, p.Wi = x.dims
+        p.in_ldc, p.in_coff, p.Cin = x.ldc, x.coff, Cin_p
+        _, p.Dof, p.Hof, p.Wof = out.dims
+        p.out_ldc, p.out_coff, p.Cout = out.ldc, out.coff, Cout_p
+        p.Do, p.Ho, p.Wo = grid_dims
+        table.fill(p)
+        p.accumulate = int(accumulate)
+        p.impl = self.impl
+        L.call("mtb200_conv_taps", C.byref(p), L.stream_ptr(), flops=flops, tag=tag)
+
+    # ---- forward primitives -------------------------------------------------------------------------------------
+    def conv(self, op: ConvOp, x: Feat, out: Optional[Feat] = None, want_stats=False):
+        """Raw convolution (or transposed convolution) of `x` into `out` (allocated if None).  Returns (out, stats)."""
+        assert x.Cp == op.Cin_p, "input slice width %d != conv's padded Cin %d" % (x.Cp, op.Cin_p)
+        odims = op.out_dims(x.dims)
+        dev = x.buf.device
+        if out is None:
+            out = Feat(self.new_buf(odims, op.Cout_p, dev), 0, op.Cout, op.Cout_p)
+        assert out.dims == odims and out.Cp == op.Cout_p
+        stats = torch.zeros((odims[0], op.Cout_p, 2), dtype=torch.float64, device=dev) if want_stats else None
+        grid = x.dims[1:] if op.transposed else odims[1:]
+        self._conv_call(op.fwd_taps, x, op.packed(self.wdtype, False), _padded(op.bias, op.Cout_p), out, grid, stats,
+                        False, op.Cin_p, op.Cout_p, flops=self.conv_flops(op, odims), tag="conv_fwd")
+        return out, stats
+
+    def finalize_norm(self, y: Feat, stats, gamma, beta, slope=LRELU_SLOPE):
+        B = y.dims[0]
+        dev = y.buf.device
+        y.xform = torch.empty((B, y.Cp, 4), dtype=torch.float32, device=dev)
+        y.meanrstd = torch.empty((B, y.Cp, 2), dtype=torch.float32, device=dev)
+        L.call("mtb200_in_finalize", L.ptr(stats), L.ptr(gamma), L.ptr(beta), B, y.Cp, y.nvox, IN_EPS, slope,
+               L.ptr(y.xform), L.ptr(y.meanrstd), L.stream_ptr())
+
+    def materialize(self, x: Feat, res: Optional[Feat] = None, slope2=LRELU_SLOPE, out: Optional[Feat] = None) -> Feat:
+        """act = f(x) [+ g(res), then LeakyReLU(slope2)] written to a fresh buffer (or `out`)."""
+        if out is None:
+            out = Feat(self.new_buf(x.dims, x.Cp, x.buf.device), 0, x.C, x.Cp)
+        B = x.dims[0]
+        L.call("mtb200_norm_act", x.ptr(), x.ldc, x.coff, out.ptr(), out.ldc, out.coff, L.dtype_enum(self.dtype), B,
+               x.nvox, x.Cp, L.ptr(x.xform), res.ptr() if res is not None else None,
+               res.ldc if res is not None else 0, res.coff if res is not None else 0,
+               L.ptr(res.xform) if res is not None else None, float(slope2), L.stream_ptr())
+        return out
+
+    # ---- composite layers with tape ------------------------------------------------------------------------------
+    def conv_norm(self, tape: Optional[Tape], op: ConvOp, gamma_param, beta_param, x: Feat, out: Optional[Feat] = None,
+                  slope=LRELU_SLOPE, need_input_grad=True) -> Feat:
+        """conv -> InstanceNorm (-> LeakyReLU(slope)); the norm/activation stay pending on the returned Feat."""
+        y, stats = self.conv(op, x, out, want_stats=True)
+        gamma = _padded(gamma_param, op.Cout_p)
+        beta = _padded(beta_param, op.Cout_p)
+        self.finalize_norm(y, stats, gamma, beta, slope)
+        if tape is not None:
+            tape.closures.append(lambda: self._conv_norm_bwd(tape, op, gamma_param, beta_param, gamma, x, y,
+                                                             need_input_grad))
+        return y
+
+    def _conv_norm_bwd(self, tape, op, gamma_param, beta_param, gamma, x: Feat, y: Feat, need_input_grad):
+        dev = y.buf.device
+        B = y.dims[0]
+        if not tape.has_grad(y):  # output never used downstream: all gradients are exactly zero
+            self._zero_param_grads(tape, op, gamma_param, beta_param)
+            return
+        g, _ = tape.grad_feat(y)
+        red = torch.zeros((B, y.Cp, 2), dtype=torch.float64, device=dev)
+        dt = L.dtype_enum(self.dtype)
+        L.call("mtb200_in_bwd_reduce", g.ptr(), g.ldc, g.coff, y.ptr(), y.ldc, y.coff, dt, B, y.nvox, y.Cp,
+               L.ptr(y.xform), L.ptr(y.meanrstd), L.ptr(red), L.stream_ptr())
+        dgamma = torch.zeros(y.Cp, dtype=torch.float32, device=dev)
+        dbeta = torch.zeros(y.Cp, dtype=torch.float32, device=dev)
+        L.call("mtb200_in_bwd_apply", g.ptr(), g.ldc, g.coff, y.ptr(), y.ldc, y.coff, g.ptr(), g.ldc, g.coff, dt, B,
+               y.nvox, y.Cp, L.ptr(y.xform), L.ptr(y.meanrstd), L.ptr(gamma), L.ptr(red), L.ptr(dgamma), L.ptr(dbeta),
+               L.stream_ptr())
+        tape.add_param_grad(gamma_param, dgamma[:op.Cout])
+        tape.add_param_grad(beta_param, dbeta[:op.Cout])
+        self._conv_bwd(tape, op, x, g, need_input_grad)
+
+    def _zero_param_grads(self, tape, op, *others):
+        tape.add_param_grad(op.weight, torch.zeros_like(op.weight))
+        for p in (op.bias,) + others:
+            if p is not None:
+                tape.add_param_grad(p, torch.zeros_like(p))
+
+    def _conv_bwd(self, tape, op: ConvOp, x: Feat, dy: Feat, need_input_grad):
+        """Weight / bias gradient and data gradient of a (transposed) convolution given d(raw output)."""
+        dev = dy.buf.device
+        dt = L.dtype_enum(self.dtype)
+        # ---- weight gradient (same tap table as the forward problem)
+        dw = torch.zeros((op.ntap, op.Cout_p, op.Cin_p), dtype=torch.float32, device=dev)
+        p = L.WgradParams()
+        p.x, p.dy, p.dw = x.ptr(), dy.ptr(), dw.data_ptr()
+        p.xform = x.xform.data_ptr() if x.xform is not None else None
+        p.dtype = dt
+        p.B, p.Di, p.Hi, p.Wi = x.dims
+        p.in_ldc, p.in_coff, p.Cin = x.ldc, x.coff, op.Cin_p
+        _, p.Dof, p.Hof, p.Wof = dy.dims
+        p.out_ldc, p.out_coff, p.Cout = dy.ldc, dy.coff, op.Cout_p
+        p.Do, p.Ho, p.Wo = x.dims[1:] if op.transposed else dy.dims[1:]
+        op.fwd_taps.fill(p)
+        p.impl = self.impl
+        fl = self.conv_flops(op, dy.dims)
+        L.call("mtb200_wgrad_taps", C.byref(p), L.stream_ptr(), flops=fl, tag="conv_wgrad")
+        gw = torch.empty_like(op.weight)
+        L.call("mtb200_unpack_wgrad", L.ptr(dw), op.Cout, op.Cin, op.ntap, int(op.transposed), op.Cout_p, op.Cin_p,
+               op.split, op.split_p, 1.0, 0, L.ptr(gw), L.stream_ptr())
+        tape.add_param_grad(op.weight, gw)
+        if op.bias is not None:
+            gb = torch.zeros(op.Cout_p, dtype=torch.float32, device=dev)
+            L.call("mtb200_colsum", dy.ptr(), dt, dy.dims[0] * dy.nvox, dy.ldc, dy.coff, op.Cout_p, L.ptr(gb),
+                   L.stream_ptr())
+            tape.add_param_grad(op.bias, gb[:op.Cout])
+        # ---- data gradient
+        if not need_input_grad:
+            return
+        gx, have = tape.grad_feat(x)
+        grid = gx.dims[1:] if op.transposed else tuple(n // s for n, s in zip(gx.dims[1:], op.stride))
+        dyv = Feat(dy.buf, dy.coff, dy.C, dy.Cp)  # gradients carry no pending transform
+        self._conv_call(op.dgrad_taps, dyv, op.packed(self.wdtype, True), None, gx, grid, None, have, op.Cout_p,
+                        op.Cin_p, flops=fl, tag="conv_dgrad")
+        tape.mark(gx)
+
+    def conv_plain(self, tape: Optional[Tape], op: ConvOp, x: Feat, out: Optional[Feat] = None,
+                   need_input_grad=True) -> Feat:
+        """Convolution with no normalisation after it (transposed-conv upsampling, 1x1x1 heads)."""
+        y, _ = self.conv(op, x, out)
+        if tape is not None:
+            def bwd():
+                if not tape.has_grad(y):
+                    self._zero_param_grads(tape, op)
+                    return
+                g, _ = tape.grad_feat(y)
+                self._conv_bwd(tape, op, x, g, need_input_grad)
+            tape.closures.append(bwd)
+        return y
+
+    def residual_act(self, tape: Optional[Tape], a: Feat, r: Feat, slope2=LRELU_SLOPE) -> Feat:
+        """out = LeakyReLU(f(a) + g(r)) -- tail of BasicResidualBlock.forward (conv_blocks.py:205-213)."""
+        out = self.materialize(a, res=r, slope2=slope2)
+        if tape is not None:
+            def bwd():
+                if not tape.has_grad(out):
+                    return
+                g, _ = tape.grad_feat(out)
+                n = out.buf.numel()
+                L.call("mtb200_lrelu_bwd", g.ptr(), out.ptr(), g.ptr(), L.dtype_enum(self.dtype), n, float(slope2),
+                       L.stream_ptr())
+                for t in (a, r):
+                    gt, have = tape.grad_feat(t)
+                    if have:
+                        gt.buf[..., gt.coff:gt.coff + gt.Cp] += g.buf[..., g.coff:g.coff + g.Cp]
+                    else:
+                        gt.buf[..., gt.coff:gt.coff + gt.Cp] = g.buf[..., g.coff:g.coff + g.Cp]
+                    tape.mark(gt)
+            tape.closures.append(bwd)
+        return out
+
+    def seed_grad(self, tape: Tape, y: Feat, dy: torch.Tensor):
+        """Install d(loss)/d(y) for an output feature.  `dy` is NCDHW-shaped; a channels-last view of an NDHWC buffer of
+        the engine dtype is adopted without a copy."""
+        ldc = ndhwc_view_info(dy) if dy.dtype == self.dtype else None
+        if ldc is not None and ldc == y.ldc and y.coff == 0:
+            B, Cc, D, H, W = dy.shape
+            buf = torch.as_strided(dy, (B, D, H, W, ldc), (D * H * W * ldc, H * W * ldc, W * ldc, ldc, 1))
+            tape.grad_bufs[id(y.buf)] = buf
+            tape.grad_init[id(y.buf)] = set()
+            tape.keep.append(dy)
+        else:
+            g, _ = tape.grad_feat(y)
+            B, Cc, D, H, W = dy.shape
+            src = dy.detach().float().contiguous()
+            L.call("mtb200_ncdhw_to_ndhwc", L.ptr(src), B, Cc, D * H * W, g.ptr(), L.dtype_enum(self.dtype), g.ldc,
+                   g.coff, g.Cp, L.stream_ptr())
+            tape.keep.append(src)
+        tape.mark(Feat(tape.grad_bufs[id(y.buf)], y.coff, y.C, y.Cp))
+
+    def run_backward(self, tape: Tape):
+        for c in reversed(tape.closures):
+            c()
+        tape.closures = []

@@ -1,0 +1,281 @@
+"""`SegmentationNetwork` -- mirror of nnunet/network_architecture/neural_network.py:48-163 (predict_3D) and :245-428,
+:502-591 (Gaussian map, step list, tiled sliding window, mirror TTA) with the aggregation moved into HBM.
+
+Same method names, argument meaning, return contract (numpy seg [X,Y,Z] + numpy probabilities [C,X,Y,Z]) and error
+behaviour as the reference; what differs is where the work happens:
+
+ * tiles are gathered on the device straight from the resident volume (flip folded into the gather indexing),
+ * every (mirrored) forward's logits go through ONE fused kernel: sigmoid * 1/n_mirror * gaussian, un-flip, scatter-add
+   into fp32 accumulators [C, X, Y, Z] that never leave HBM (the reference does `.cpu().numpy()` of 739 MB per tile
+   and a host numpy `+=`, neural_network.py:391-394),
+ * ONE single-channel weight volume replaces the reference's C identical copies (`aggregated_nb_of_predictions`,
+   :363,372,394) -- same quotient,
+ * normalisation + in-order threshold (:405, :415-417) is one kernel; a single D2H of the result at the end.
+"""
+from typing import List, Tuple, Union
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import _lib as L
+from ..engine import Feat, ndhwc_view_info
+
+
+class NeuralNetwork(nn.Module):
+    def __init__(self):
+        super(NeuralNetwork, self).__init__()
+
+    def get_device(self):
+        p = next(self.parameters())
+        return "cpu" if p.device.type == "cpu" else p.device.index
+
+    def set_device(self, device):
+        if device == "cpu":
+            self.cpu()
+        else:
+            self.cuda(device)
+
+    def forward(self, x):
+        raise NotImplementedError
+
+
+def pad_nd_image(image, new_shape=None, mode="constant", kwargs=None, return_slicer=False,
+                 shape_must_be_divisible_by=None):
+    """Host-side symmetric padding up to `new_shape` (batchgenerators.augmentations.utils.pad_nd_image, third party;
+    call site neural_network.py:301): floor(diff/2) below, rest above; returns the slicer that undoes it."""
+    if kwargs is None:
+        kwargs = {'constant_values': 0}
+    if new_shape is None:
+        assert shape_must_be_divisible_by is not None
+        new_shape = image.shape[-len(shape_must_be_divisible_by):]
+    nd = len(new_shape)
+    cur = np.array(image.shape[-nd:])
+    want = np.maximum(np.array(new_shape), cur)
+    if shape_must_be_divisible_by is not None:
+        div = np.array(shape_must_be_divisible_by if isinstance(shape_must_be_divisible_by, (list, tuple, np.ndarray))
+                       else [shape_must_be_divisible_by] * nd)
+        want = (want + div - 1) // div * div
+    extra = want - cur
+    lo = extra // 2
+    hi = extra - lo
+    pads = [[0, 0]] * (image.ndim - nd) + [[int(a), int(b)] for a, b in zip(lo, hi)]
+    res = np.pad(image, pads, mode, **kwargs) if extra.any() else image
+    if not return_slicer:
+        return res
+    return res, [slice(p[0], res.shape[i] - p[1]) for i, p in enumerate(pads)]
+
+
+_MIRROR_FLIPS = [(), (4,), (3,), (4, 3), (2,), (4, 2), (3, 2), (4, 3, 2)]  # order of neural_network.py:531-586
+
+
+def _flip_bits(dims):
+    """tensor dims (2,3,4) = (D,H,W) -> flip bitmask used by the kernels (bit0 W, bit1 H, bit2 D)."""
+    return sum({4: 1, 3: 2, 2: 4}[d] for d in dims)
+
+
+class SegmentationNetwork(NeuralNetwork):
+    def __init__(self):
+        super(NeuralNetwork, self).__init__()
+        self.input_shape_must_be_divisible_by = None
+        self.conv_op = None
+        self.num_classes = None
+        self.inference_apply_nonlin = lambda x: x
+        self._gaussian_3d = self._patch_size_for_gaussian_3d = None
+        self._gaussian_2d = self._patch_size_for_gaussian_2d = None
+        self._gaussian_3d_dev = None
+
+    # ---- hooks a concrete network provides for the native predictor ------------------------------------------------
+    def native_logits(self, tile: Feat) -> Feat:
+        """Full-resolution logits (NDHWC) for an NDHWC input tile, no tape.  Implemented by Generic_UNet/FabiansUNet."""
+        raise NotImplementedError
+
+    def native_input_channels_padded(self) -> int:
+        raise NotImplementedError
+
+    def native_dtype(self):
+        raise NotImplementedError
+
+    # ---- reference API ----------------------------------------------------------------------------------------------
+    def predict_3D(self, x: np.ndarray, do_mirroring: bool, mirror_axes: Tuple[int, ...] = (0, 1, 2),
+                   use_sliding_window: bool = False, step_size: float = 0.5, patch_size: Tuple[int, ...] = None,
+                   regions_class_order: Tuple[int, ...] = None, use_gaussian: bool = False,
+                   pad_border_mode: str = "constant", pad_kwargs: dict = None, all_in_gpu: bool = False,
+                   verbose: bool = True, mixed_precision: bool = True, region_vec=None,
+                   return_device_tensors: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+        """neural_network.py:73-163.  `x` is (c, x, y, z) numpy; returns (segmentation, class probabilities).
+        `all_in_gpu` / `mixed_precision` are accepted for signature compatibility: accumulators are always fp32 in HBM
+        and the arithmetic type is the network's native dtype.  `return_device_tensors=True` (extension) skips the
+        final D2H copy and returns CUDA tensors."""
+        assert step_size <= 1, 'step_size must be smaller than 1. Otherwise there will be a gap between consecutive ' \
+                               'predictions'
+        if pad_kwargs is None:
+            pad_kwargs = {'constant_values': 0}
+        if len(mirror_axes):
+            if self.conv_op == nn.Conv2d and max(mirror_axes) > 1:
+                raise ValueError("mirror axes. duh")
+            if self.conv_op == nn.Conv3d and max(mirror_axes) > 2:
+                raise ValueError("mirror axes. duh")
+        if self.training:
+            print('WARNING! Network is in train mode during inference. This may be intended, or not...')
+        assert len(x.shape) == 4, "data must have shape (c,x,y,z)"
+        if self.conv_op != nn.Conv3d:
+            raise RuntimeError("the native predictor implements the 3D-conv path only (3d_fullres)")
+        if region_vec is not None:
+            raise NotImplementedError("region_vec conditioning is not part of the MultiTalent 3d_fullres path")
+        with torch.no_grad():
+            if use_sliding_window:
+                return self._internal_predict_3D_3Dconv_tiled(x, step_size, do_mirroring, mirror_axes, patch_size,
+                                                              regions_class_order, use_gaussian, pad_border_mode,
+                                                              pad_kwargs, all_in_gpu, verbose,
+                                                              return_device_tensors=return_device_tensors)
+            return self._internal_predict_3D_3Dconv(x, patch_size, do_mirroring, mirror_axes, regions_class_order,
+                                                    pad_border_mode, pad_kwargs, verbose,
+                                                    return_device_tensors=return_device_tensors)
+
+    @staticmethod
+    def _get_gaussian(patch_size, sigma_scale=1. / 8) -> np.ndarray:
+        """neural_network.py:245-259 (scipy's gaussian_filter is host-side and runs once per patch size)."""
+        from scipy.ndimage import gaussian_filter
+        tmp = np.zeros(patch_size)
+        tmp[tuple(i // 2 for i in patch_size)] = 1
+        g = gaussian_filter(tmp, [i * sigma_scale for i in patch_size], 0, mode='constant', cval=0)
+        g = (g / np.max(g) * 1).astype(np.float32)
+        g[g == 0] = np.min(g[g != 0])  # zero weights would produce NaNs in the normalisation
+        return g
+
+    @staticmethod
+    def _compute_steps_for_sliding_window(patch_size: Tuple[int, ...], image_size: Tuple[int, ...],
+                                          step_size: float) -> List[List[int]]:
+        """neural_network.py:261-285."""
+        assert [i >= j for i, j in zip(image_size, patch_size)], "image size must be as large or larger than patch_size"
+        assert 0 < step_size <= 1, 'step_size must be larger than 0 and smaller or equal to 1'
+        out = []
+        for p, im in zip(patch_size, image_size):
+            n = int(np.ceil((im - p) / (p * step_size))) + 1
+            span = im - p
+            actual = span / (n - 1) if n > 1 else 99999999999
+            out.append([int(np.round(actual * i)) for i in range(n)])
+        return out
+
+    # ---- native tiled predictor ---------------------------------------------------------------------------------
+    def _mirror_list(self, do_mirroring, mirror_axes):
+        if not do_mirroring:
+            return [()], 1
+        keep = [dims for dims in _MIRROR_FLIPS if all((d - 2) in mirror_axes for d in dims)]
+        return keep, 2 ** len(mirror_axes)
+
+    def _internal_predict_3D_3Dconv_tiled(self, x: np.ndarray, step_size: float, do_mirroring: bool, mirror_axes: tuple,
+                                          patch_size: tuple, regions_class_order: tuple, use_gaussian: bool,
+                                          pad_border_mode: str, pad_kwargs: dict, all_in_gpu: bool, verbose: bool,
+                                          region_vec=None, return_device_tensors=False):
+        """neural_network.py:287-428."""
+        assert len(x.shape) == 4, "x must be (c, x, y, z)"
+        assert patch_size is not None, "patch_size cannot be None for tiled prediction"
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise L.Mtb200Error("the native predictor needs the network on a CUDA device (no CPU fallback)")
+        patch_size = tuple(int(p) for p in patch_size)
+        data, slicer = pad_nd_image(x, patch_size, pad_border_mode, pad_kwargs, True, None)
+        Cin, X, Y, Z = data.shape
+        steps = self._compute_steps_for_sliding_window(patch_size, data.shape[1:], step_size)
+        num_tiles = len(steps[0]) * len(steps[1]) * len(steps[2])
+        if verbose:
+            print("data shape:", data.shape, "patch size:", patch_size, "steps:", steps, "number of tiles:", num_tiles)
+
+        gauss = None
+        if use_gaussian and num_tiles > 1:
+            if self._gaussian_3d is None or tuple(self._patch_size_for_gaussian_3d) != patch_size:
+                self._gaussian_3d = self._get_gaussian(patch_size, sigma_scale=1. / 8)
+                self._patch_size_for_gaussian_3d = patch_size
+                self._gaussian_3d_dev = None
+            if self._gaussian_3d_dev is None or self._gaussian_3d_dev.device != dev:
+                self._gaussian_3d_dev = torch.from_numpy(self._gaussian_3d).to(dev)
+            gauss = self._gaussian_3d_dev
+
+        vol = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).to(dev, non_blocking=True)
+        C = self.num_classes
+        acc = torch.zeros((C, X, Y, Z), dtype=torch.float32, device=dev)
+        nb = torch.zeros((X, Y, Z), dtype=torch.float32, device=dev)
+        mirrors, n_results = self._mirror_list(do_mirroring, mirror_axes)
+        dt = self.native_dtype()
+        cin_p = self.native_input_channels_padded()
+        pd, ph, pw = patch_size
+        tile = torch.empty((1, pd, ph, pw, cin_p), dtype=dt, device=dev)
+        st = L.stream_ptr()
+        for sx in steps[0]:
+            for sy in steps[1]:
+                for sz in steps[2]:
+                    for mi, dims in enumerate(mirrors):
+                        fb = _flip_bits(dims)
+                        L.call("mtb200_sw_gather_tile", L.ptr(vol), Cin, X, Y, Z, sx, sy, sz, pd, ph, pw, fb, L.ptr(tile),
+                               L.dtype_enum(dt), cin_p, st)
+                        logits = self.native_logits(Feat(tile, 0, Cin, cin_p))
+                        L.call("mtb200_sw_aggregate", logits.ptr(), L.dtype_enum(dt), logits.ldc, C, pd, ph, pw, fb,
+                               L.ptr(gauss), 1.0 / n_results, 1, L.ptr(acc), L.ptr(nb) if mi == 0 else None, X, Y, Z,
+                               sx, sy, sz, st)
+        # undo the padding (neural_network.py:397-402) -- crop BEFORE normalising, as the reference does
+        sl = tuple([slice(0, C)] + list(slicer[1:]))
+        if any(s.start != 0 or s.stop != n for s, n in zip(sl[1:], (X, Y, Z))):
+            acc = acc[sl].contiguous()
+            nb = nb[tuple(slicer[1:])].contiguous()
+        nvox = nb.numel()
+        seg = torch.empty(nb.shape, dtype=torch.float32, device=dev)
+        order = None
+        if regions_class_order is not None:
+            order = torch.tensor([float(c) for c in regions_class_order], dtype=torch.float32, device=dev)
+            assert order.numel() == C
+        L.call("mtb200_sw_finalize", L.ptr(acc), L.ptr(nb), C, nvox, L.ptr(order), L.ptr(seg), st)
+        if regions_class_order is None:
+            seg = seg.long()
+        if return_device_tensors:
+            return seg, acc
+        if verbose:
+            print("prediction done")
+        return seg.cpu().numpy(), acc.cpu().numpy()
+
+    def _internal_predict_3D_3Dconv(self, x: np.ndarray, min_size: Tuple[int, ...], do_mirroring: bool,
+                                    mirror_axes: tuple = (0, 1, 2), regions_class_order: tuple = None,
+                                    pad_border_mode: str = "constant", pad_kwargs: dict = None, verbose: bool = True,
+                                    region_vec=None, return_device_tensors=False):
+        """Fully convolutional variant (neural_network.py:465-500): pad to divisibility, one (mirrored) pass."""
+        assert len(x.shape) == 4, "x must be (c, x, y, z)"
+        assert self.input_shape_must_be_divisible_by is not None
+        data, slicer = pad_nd_image(x, min_size, pad_border_mode, pad_kwargs, True,
+                                    self.input_shape_must_be_divisible_by)
+        res = self._internal_predict_3D_3Dconv_tiled(data, 1.0, do_mirroring, mirror_axes, tuple(data.shape[1:]),
+                                                     regions_class_order, False, pad_border_mode, pad_kwargs, False,
+                                                     False, return_device_tensors=True)
+        seg, prob = res
+        sl = tuple(slicer[1:])
+        seg, prob = seg[sl], prob[(slice(None),) + sl]
+        if return_device_tensors:
+            return seg, prob
+        return seg.cpu().numpy(), prob.cpu().numpy()
+
+    def _internal_maybe_mirror_and_pred_3D(self, x: Union[np.ndarray, torch.Tensor], mirror_axes: tuple,
+                                           do_mirroring: bool = True, mult: Union[np.ndarray, torch.Tensor] = None,
+                                           region_vec=None) -> torch.Tensor:
+        """neural_network.py:502-591: (1/n) sum over mirrors of un-flipped sigmoid(net(flipped x)), times `mult`.
+        Returns a CUDA fp32 tensor [1, C, X, Y, Z] like the reference."""
+        assert len(x.shape) == 5, 'x must be (b, c, x, y, z)'
+        assert x.shape[0] == 1, "the reference calls this with one tile at a time"
+        dev = next(self.parameters()).device
+        xt = torch.as_tensor(x, dtype=torch.float32, device=dev)[0].contiguous()
+        Cin, X, Y, Z = xt.shape
+        C = self.num_classes
+        acc = torch.zeros((C, X, Y, Z), dtype=torch.float32, device=dev)
+        g = None if mult is None else torch.as_tensor(mult, dtype=torch.float32, device=dev).contiguous()
+        mirrors, n_results = self._mirror_list(do_mirroring, mirror_axes)
+        dt = self.native_dtype()
+        cin_p = self.native_input_channels_padded()
+        tile = torch.empty((1, X, Y, Z, cin_p), dtype=dt, device=dev)
+        st = L.stream_ptr()
+        for dims in mirrors:
+            fb = _flip_bits(dims)
+            L.call("mtb200_sw_gather_tile", L.ptr(xt), Cin, X, Y, Z, 0, 0, 0, X, Y, Z, fb, L.ptr(tile), L.dtype_enum(dt),
+                   cin_p, st)
+            logits = self.native_logits(Feat(tile, 0, Cin, cin_p))
+            L.call("mtb200_sw_aggregate", logits.ptr(), L.dtype_enum(dt), logits.ldc, C, X, Y, Z, fb, L.ptr(g),
+                   1.0 / n_results, 1, L.ptr(acc), None, X, Y, Z, 0, 0, 0, st)
+        return acc[None]

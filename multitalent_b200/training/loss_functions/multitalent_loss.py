@@ -1,0 +1,145 @@
+"""MultiTalent multi-head loss on the native kernels -- replaces `MultiTalent_trainer_ddp.compute_loss`
+(nnunet/training/network_training/custom_trainers/MultiTalent/MultiTalent/MultiTalent_Trainer_DDP.py:544-623) and the
+differentiable all-gather it uses (nnunet/utilities/distributed.py:28-73).
+
+Per deep-supervision scale i (weight w_i, MT:85-96):  CE_i = sum over (b, r in valid_regions[b]) of the voxel-mean
+BCE-with-logits of channel j_r against y = OR_{l in regions[r]} (target == l);  tp/fp/fn[b, j_r] = sums of sigma*y,
+sigma*(1-y), (1-sigma)*y;  all-gathered over ranks and summed over the RANK axis only (pooling per local batch index b,
+MT:596-604);  DC_i = sum_{b,j} 2tp / clamp(2tp + fp + fn, 1e-7);  loss = sum_i w_i (CE_i - DC_i).
+
+Native form: two streaming kernels per scale.  Pass 1 accumulates {sum bce, tp, sum sigma, sum y} per (b, j)
+(note 2tp + fp + fn = sum sigma + sum y).  ONE all-gather of the packed [scales, B, C, 2] buffer replaces the
+reference's 15 tiny collectives; the backward needs NO collective: every rank holds the same pooled Dice, so the
+all-reduced gradient (distributed.py:71) is exactly world_size x the local closed form, which pass 2 evaluates:
+    dL/dz = w_i [ (sigma - y)/N_vox  -  W * sigma (1 - sigma) (2 y D - 2 TP) / D^2 ]        for supervised (b, j), else 0.
+"""
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from ... import _lib as L
+from ...dataset_conversion.Task100_MultiTalent import NUM_LABELS, region_bitmasks, valid_channel_mask
+from ...engine import ndhwc_view_info, pad_channels
+
+_POS_MASK_CACHE = {}
+
+
+def _pos_mask(device):
+    t = _POS_MASK_CACHE.get(device)
+    if t is None:
+        pos, _ = region_bitmasks()
+        t = torch.tensor(pos, dtype=torch.int64, device=device)
+        _POS_MASK_CACHE[device] = t
+    return t
+
+
+def pool_stats_over_ranks(packed: torch.Tensor, group=None) -> torch.Tensor:
+    """`packed` [..., 2] = this rank's {tp, sum sigma + sum y}; returns the sum over ranks (all_gather + sum(0), the
+    forward of awesome_allgather_function followed by `.sum(0, keepdim=True)`, MT:598-604).  Works on any backend
+    (NCCL on GPUs, gloo in the CPU tests)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return packed
+    bufs = [torch.empty_like(packed) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(bufs, packed.contiguous(), group=group)
+    return torch.stack(bufs, 0).sum(0)
+
+
+def _as_ndhwc(t: torch.Tensor, dtype):
+    """(buffer-like tensor, ldc) for an NCDHW-shaped logits tensor; adopts channels-last views, converts otherwise."""
+    if t.dtype == dtype:
+        ldc = ndhwc_view_info(t)
+        if ldc is not None:
+            return t, ldc
+    B, Cc, D, H, W = t.shape
+    Cp = pad_channels(Cc)
+    src = t.detach().float().contiguous()
+    buf = torch.empty((B, D, H, W, Cp), dtype=dtype, device=t.device)
+    L.call("mtb200_ncdhw_to_ndhwc", L.ptr(src), B, Cc, D * H * W, L.ptr(buf), L.dtype_enum(dtype), Cp, 0, Cp,
+           L.stream_ptr())
+    return buf.permute(0, 4, 1, 2, 3)[:, :Cc], Cp
+
+
+class _MultiTalentLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, valid_mask, weights, group, targets, *logits):
+        dev = logits[0].device
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        pos = _pos_mask(dev)
+        st = L.stream_ptr()
+        B, Cc = logits[0].shape[:2]
+        C8 = (Cc + 7) // 8 * 8
+        active = [i for i, w in enumerate(weights) if w != 0]
+        views, stats = {}, {}
+        for i in active:
+            z = logits[i]
+            dt = z.dtype if z.dtype in (torch.float32, torch.bfloat16, torch.float16) else torch.float32
+            zv, ldc = _as_ndhwc(z, dt)
+            tgt = targets[i]
+            assert tgt.shape[0] == B and tgt.numel() == B * z.shape[2] * z.shape[3] * z.shape[4], \
+                "target %s does not match logits %s" % (tuple(tgt.shape), tuple(z.shape))
+            tgt = tgt.detach().float().contiguous()
+            nvox = z.shape[2] * z.shape[3] * z.shape[4]
+            s = torch.zeros((B, C8, 4), dtype=torch.float64, device=dev)
+            L.call("mtb200_mt_loss_stats", L.ptr(zv), L.dtype_enum(dt), ldc, C8, L.ptr(tgt), B, nvox, L.ptr(valid_mask),
+                   L.ptr(pos), NUM_LABELS, L.ptr(s), st)
+            views[i] = (zv, ldc, dt, tgt, nvox)
+            stats[i] = s
+        pooled = {i: None for i in active}
+        if world > 1 and active:
+            packed = torch.stack([torch.stack((stats[i][..., 1], stats[i][..., 2] + stats[i][..., 3]), -1)
+                                  for i in active], 0)
+            allp = pool_stats_over_ranks(packed, group)
+            pooled = {i: allp[k].contiguous() for k, i in enumerate(active)}
+        losses = torch.zeros(3, dtype=torch.float32, device=dev)
+        coefs = {}
+        for i in active:
+            coef = torch.empty((B, C8, 4), dtype=torch.float32, device=dev)
+            L.call("mtb200_mt_loss_finalize", L.ptr(stats[i]), L.ptr(pooled[i]), L.ptr(valid_mask), B, C8, views[i][4],
+                   float(weights[i]), float(world), L.ptr(losses), L.ptr(coef), st)
+            coefs[i] = coef
+        ctx.views, ctx.coefs, ctx.active, ctx.n = views, coefs, active, len(logits)
+        ctx.shapes = [tuple(z.shape) for z in logits]
+        ctx.pos = pos
+        ctx.C8 = C8
+        return losses[0], losses[1], losses[2]
+
+    @staticmethod
+    def backward(ctx, g_loss, g_ce, g_dc):
+        st = L.stream_ptr()
+        grads: List[Optional[torch.Tensor]] = [None] * ctx.n
+        gs = g_loss.detach().float().contiguous()
+        for i in ctx.active:
+            zv, ldc, dt, tgt, nvox = ctx.views[i]
+            B, Cc, D, H, W = ctx.shapes[i]
+            dz = torch.empty((B, D, H, W, ldc), dtype=dt, device=zv.device)
+            if ldc > ctx.C8:
+                dz[..., ctx.C8:].zero_()
+            L.call("mtb200_mt_loss_bwd", L.ptr(zv), L.dtype_enum(dt), ldc, ctx.C8, L.ptr(tgt), B, nvox, L.ptr(ctx.pos),
+                   NUM_LABELS, L.ptr(ctx.coefs[i]), L.ptr(gs), L.ptr(dz), ldc, st)
+            grads[i] = dz.permute(0, 4, 1, 2, 3)[:, :Cc]
+        for i in range(ctx.n):
+            if grads[i] is None and ctx.needs_input_grad[4 + i]:
+                B, Cc, D, H, W = ctx.shapes[i]
+                Cp = pad_channels(Cc)
+                grads[i] = torch.zeros((B, D, H, W, Cp), dtype=ctx.views[ctx.active[0]][2],
+                                       device=g_loss.device).permute(0, 4, 1, 2, 3)[:, :Cc]
+        return (None, None, None, None) + tuple(grads)
+
+
+def valid_mask_tensor(valid_regions: Sequence[Sequence[str]], device) -> torch.Tensor:
+    """[B] int64 bitmasks of supervised channels from the per-sample region-name tuples
+    (`data_dict['properties'][b]['valid_regions']`, MT:328-329)."""
+    return torch.tensor([valid_channel_mask(v) for v in valid_regions], dtype=torch.int64, device=device)
+
+
+def multitalent_loss(outputs, targets, valid_regions, ds_loss_weights, group=None):
+    """(total_loss, total_ce, total_dc) as 0-dim CUDA tensors; `total_loss` is differentiable w.r.t. `outputs`.
+    Only d(total_loss) is propagated (the trainer calls `l.backward()`; ce/dc are reporting values, MT:370)."""
+    if not isinstance(outputs, (tuple, list)):
+        outputs, targets = (outputs,), (targets,) if not isinstance(targets, (tuple, list)) else targets
+    if not outputs[0].is_cuda:
+        raise L.Mtb200Error("multitalent_loss runs on the native CUDA path only; logits are on %s" % outputs[0].device)
+    vm = valid_regions if torch.is_tensor(valid_regions) else valid_mask_tensor(valid_regions, outputs[0].device)
+    weights = [float(w) for w in ds_loss_weights][:len(outputs)]
+    return _MultiTalentLossFn.apply(vm, weights, group, list(targets), *outputs)

@@ -1,0 +1,312 @@
+"""`MultiTalent_trainer_ddp` (alias `nnUNetTrainerV2_MultiTalent`) -- the hot-path half of
+nnunet/training/network_training/custom_trainers/MultiTalent/MultiTalent/MultiTalent_Trainer_DDP.py:30-127, 324-370,
+544-623 and of the nnUNetTrainerV2_DDP pieces it inherits (nnUNetTrainerV2_DDP.py:50-133, 601-634;
+nnUNetTrainerV2.py:131-170, 393-408), on the native kernels.
+
+Same constructor signature, same hook names (`initialize`, `initialize_network`, `compute_loss`, `run_iteration`,
+`predict_preprocessed_data_return_seg_and_softmax`, `maybe_update_lr`), same return contracts.  Everything around the
+hot path that the reference trainer also does (data loaders, augmentation, validation export, plotting, checkpoint
+files) is out of scope and stays in the reference; INTEGRATION.md shows how the reference
+trainer picks up the native network + loss with a 3-line subclass.
+
+Two step modes:
+  * autograd mode (`run_iteration`): exactly the reference's statement sequence -- `network(data)`, `compute_loss`,
+    `backward()`, clip, SGD -- where the network and the loss are single autograd nodes backed by the kernels.  Works
+    under torch DDP unchanged.
+  * `flat_optimizer=True` (default): parameters and gradients live in one fp32 arena each; the clip-norm and the
+    Nesterov-SGD update are two kernels over the arena and the DDP gradient exchange is one NCCL all-reduce of it.
+"""
+import os
+import pickle
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from ... import _lib as L
+from ...dataset_conversion.Task100_MultiTalent import MultiTalent_regions
+from ...engine import bump_weights_epoch
+from ...network_architecture.generic_UNet import Generic_UNet, InitWeights_He
+from ...plans import default_plans
+from ..loss_functions.multitalent_loss import multitalent_loss
+
+
+def poly_lr(epoch, max_epochs, initial_lr, exponent=0.9):
+    """nnunet/training/learning_rate/poly_lr.py:16-17."""
+    return initial_lr * (1 - epoch / max_epochs) ** exponent
+
+
+class FlatArena:
+    """All parameters (and their gradients) of a module as views into one contiguous fp32 buffer each."""
+
+    def __init__(self, module: nn.Module):
+        params = [p for p in module.parameters()]
+        n = sum((p.numel() + 3) // 4 * 4 for p in params)
+        dev = params[0].device
+        self.params = params
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.mom = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p.data)
+            p.grad = self.grad[off:off + k].view_as(p.data)
+            off += (k + 3) // 4 * 4
+        self.n = n
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.first = True
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def step(self, lr, momentum, weight_decay, max_norm, inv_scale=1.0):
+        st = L.stream_ptr()
+        self.sumsq.zero_()
+        L.call("mtb200_sumsq", L.ptr(self.grad), self.n, L.ptr(self.sumsq), st)
+        L.call("mtb200_sgd_step", L.ptr(self.flat), L.ptr(self.grad), L.ptr(self.mom), self.n, L.ptr(self.sumsq),
+               float(inv_scale), float(max_norm), float(lr), float(momentum), float(weight_decay), int(self.first), st)
+        self.first = False
+        # the kernel updated the arena behind torch's version counters: invalidate the packed-weight caches
+        bump_weights_epoch()
+
+
+class MultiTalent_trainer_ddp(object):
+    def __init__(self, plans_file, fold, local_rank, output_folder=None, dataset_directory=None, batch_dice=True,
+                 stage=None, unpack_data=True, deterministic=True, distribute_batch_size=False, fp16=False,
+                 native_dtype=None, flat_optimizer=True, init_distributed=True):
+        """Positional signature of MultiTalent_Trainer_DDP.py:31-32 (the tuple is pickled and replayed by
+        model_restore.py:90).  Keyword-only extensions: `native_dtype` (torch.float32 | bfloat16 | float16; default
+        fp16 if `fp16` else fp32), `flat_optimizer`, `init_distributed`."""
+        self.init_args = (plans_file, fold, local_rank, output_folder, dataset_directory, batch_dice, stage, unpack_data,
+                          deterministic, distribute_batch_size, fp16)
+        self.plans_file, self.fold, self.local_rank = plans_file, fold, local_rank
+        self.output_folder, self.dataset_directory = output_folder, dataset_directory
+        self.batch_dice = True  # forced, MT:33
+        self.stage, self.unpack_data, self.deterministic = stage, unpack_data, deterministic
+        self.distribute_batch_size, self.fp16 = distribute_batch_size, fp16
+        self.native_dtype = native_dtype if native_dtype is not None else (torch.float16 if fp16 else torch.float32)
+        self.flat_optimizer = flat_optimizer
+        self.regions = MultiTalent_regions
+        self.max_num_epochs, self.initial_lr, self.weight_decay = 1000, 1e-2, 3e-5  # nnUNetTrainerV2.py:47-48
+        self.num_batches_per_epoch, self.num_val_batches_per_epoch = 250, 50         # network_trainer.py:96-97
+        self.epoch = 0
+        self.was_initialized = False
+        self.plans = None
+        self.network = self.optimizer = self.arena = self.amp_grad_scaler = None
+        self.ds_loss_weights = None
+        self.loss_scale = 1.0
+        np.random.seed(local_rank)
+        torch.manual_seed(local_rank)
+        if torch.cuda.is_available():
+            torch.cuda.manual_seed_all(local_rank)
+            torch.cuda.set_device(local_rank)
+        # nnUNetTrainerV2_DDP.py:68 -- one process per GPU, env:// rendezvous (launcher provides the env)
+        if init_distributed and dist.is_available() and not dist.is_initialized() and "RANK" in os.environ:
+            dist.init_process_group(backend='nccl' if torch.cuda.is_available() else 'gloo', init_method='env://')
+
+    # ---- plans -------------------------------------------------------------------------------------------------
+    def load_plans_file(self):
+        if isinstance(self.plans_file, dict):
+            self.plans = self.plans_file
+        elif self.plans_file is None:
+            self.plans = default_plans()
+        else:
+            with open(self.plans_file, 'rb') as f:
+                self.plans = pickle.load(f)
+
+    def process_plans(self, plans):
+        """nnUNetTrainer.py:326-392 (the fields the hot path needs) + MT:48-51 (num_classes := 47 regions)."""
+        if self.stage is None:
+            self.stage = max(plans['plans_per_stage'].keys())
+        sp = plans['plans_per_stage'][self.stage]
+        self.plans = plans
+        self.batch_size = int(sp['batch_size'])
+        self.net_pool_per_axis = sp['num_pool_per_axis']
+        self.patch_size = np.array(sp['patch_size']).astype(int)
+        self.net_num_pool_op_kernel_sizes = [list(map(int, k)) for k in sp['pool_op_kernel_sizes']]
+        self.net_conv_kernel_sizes = [list(map(int, k)) for k in sp['conv_kernel_sizes']]
+        self.base_num_features = int(plans['base_num_features'])
+        self.num_input_channels = int(plans['num_modalities'])
+        self.conv_per_stage = int(plans.get('conv_per_stage', 2))
+        self.threeD = len(self.patch_size) == 3
+        self.num_classes = len(self.regions)
+
+    def setup_DA_params(self):
+        """nnUNetTrainerV2.py:350-351: scales of the deep-supervision targets."""
+        self.deep_supervision_scales = [[1, 1, 1]] + list(
+            list(i) for i in 1 / np.cumprod(np.vstack(self.net_num_pool_op_kernel_sizes), axis=0))[:-1]
+
+    # ---- initialisation -------------------------------------------------------------------------------------------
+    def initialize(self, training=True, force_load_plans=False):
+        if self.was_initialized:
+            return
+        if force_load_plans or self.plans is None:
+            self.load_plans_file()
+        self.process_plans(self.plans)
+        self.setup_DA_params()
+        if training:
+            n = len(self.net_num_pool_op_kernel_sizes)
+            w = np.array([1 / (2 ** i) for i in range(n)])
+            w[n - 1] = 0                       # lowest resolution output is not supervised (MT:93-95)
+            self.ds_loss_weights = w / w.sum()
+        self.initialize_network()
+        self.initialize_optimizer_and_scheduler()
+        self._wrap_ddp()
+        self.was_initialized = True
+        self.regions_class_order = list(range(self.num_classes))
+
+    def initialize_network(self):
+        """nnUNetTrainerV2.initialize_network (nnUNetTrainerV2.py:131-164) + sigmoid inference nonlinearity (MT:43-46)."""
+        assert self.threeD, "MultiTalent is a 3d_fullres configuration"
+        self.network = Generic_UNet(self.num_input_channels, self.base_num_features, self.num_classes,
+                                    len(self.net_num_pool_op_kernel_sizes), self.conv_per_stage, 2, nn.Conv3d,
+                                    nn.InstanceNorm3d, {'eps': 1e-5, 'affine': True}, nn.Dropout3d,
+                                    {'p': 0, 'inplace': True}, nn.LeakyReLU,
+                                    {'negative_slope': 1e-2, 'inplace': True}, True, False, lambda x: x,
+                                    InitWeights_He(1e-2), self.net_num_pool_op_kernel_sizes,
+                                    self.net_conv_kernel_sizes, False, True, True, native_dtype=self.native_dtype)
+        if torch.cuda.is_available():
+            self.network.cuda()
+        self.network.inference_apply_nonlin = nn.Sigmoid()
+
+    def initialize_optimizer_and_scheduler(self):
+        """nnUNetTrainerV2.py:166-170: SGD(lr, wd 3e-5, momentum .99, nesterov); no scheduler object (poly LR)."""
+        assert self.network is not None, "self.initialize_network must be called first"
+        if self.flat_optimizer and next(self.network.parameters()).is_cuda:
+            self.arena = FlatArena(self.network)
+            self.optimizer = None
+        else:
+            self.optimizer = torch.optim.SGD(self.network.parameters(), self.initial_lr,
+                                             weight_decay=self.weight_decay, momentum=0.99, nesterov=True)
+        self.lr = self.initial_lr
+        self.lr_scheduler = None
+
+    def _wrap_ddp(self):
+        self.world_size = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        if self.world_size > 1:
+            with torch.no_grad():  # parameter broadcast at construction, as torch DDP does (MT:121)
+                flat = self.arena.flat if self.arena is not None else None
+                if flat is not None:
+                    dist.broadcast(flat, 0)
+                else:
+                    for p in self.network.parameters():
+                        dist.broadcast(p.data, 0)
+
+    def maybe_update_lr(self, epoch=None):
+        """nnUNetTrainerV2.py:393-408."""
+        ep = self.epoch + 1 if epoch is None else epoch
+        self.lr = poly_lr(ep, self.max_num_epochs, self.initial_lr, 0.9)
+        if self.optimizer is not None:
+            self.optimizer.param_groups[0]['lr'] = self.lr
+
+    # ---- the hot path ----------------------------------------------------------------------------------------------
+    def compute_loss(self, output, target, valid_regions):
+        """MT:544-623 -> (total_loss, total_ce, total_dc)."""
+        return multitalent_loss(output, target, valid_regions, self.ds_loss_weights)
+
+    def run_iteration(self, data_generator, do_backprop=True, run_online_evaluation=False):
+        """MT:324-370.  Returns three numpy scalars (the D2H sync of the reference is kept: it is the contract)."""
+        data_dict = next(data_generator)
+        data, target = data_dict['data'], data_dict['target']
+        valid_regions = [p['valid_regions'] for p in data_dict['properties']]
+        data = torch.as_tensor(data)
+        target = [torch.as_tensor(t) for t in target]
+        if torch.cuda.is_available():
+            data = data.cuda(non_blocking=True)
+            target = [t.cuda(non_blocking=True) for t in target]
+        l, ce, dc = self.train_step(data, target, valid_regions, do_backprop)
+        res = torch.stack((l.detach(), ce.detach(), dc.detach())).cpu().numpy()
+        return res[0], res[1], res[2]
+
+    def train_step(self, data, target, valid_regions, do_backprop=True):
+        """One optimisation step on device-resident tensors; returns device scalars (no sync)."""
+        if self.arena is not None:
+            self.arena.zero_grad()
+        elif self.optimizer is not None:
+            self.optimizer.zero_grad()
+        with torch.set_grad_enabled(do_backprop):
+            output = self.network(data)
+            l, ce, dc = self.compute_loss(output, target, valid_regions)
+            if do_backprop:
+                (l * self.loss_scale if self.loss_scale != 1.0 else l).backward()
+        if do_backprop:
+            if self.arena is not None:
+                if self.world_size > 1:
+                    dist.all_reduce(self.arena.grad)
+                    inv = 1.0 / (self.loss_scale * self.world_size)
+                else:
+                    inv = 1.0 / self.loss_scale
+                self.arena.step(self.lr, 0.99, self.weight_decay, 12.0, inv)
+            else:
+                if self.world_size > 1:
+                    for p in self.network.parameters():
+                        if p.grad is not None:
+                            dist.all_reduce(p.grad)
+                            p.grad.div_(self.world_size)
+                torch.nn.utils.clip_grad_norm_(self.network.parameters(), 12)
+                self.optimizer.step()
+        return l, ce, dc
+
+    def predict_preprocessed_data_return_seg_and_softmax(self, data, do_mirroring=True, mirror_axes=None,
+                                                         use_sliding_window=True, step_size=0.5, use_gaussian=True,
+                                                         pad_border_mode='constant', pad_kwargs=None, all_in_gpu=False,
+                                                         verbose=True, mixed_precision=True, region_vec=None):
+        """nnUNetTrainerV2_DDP.py:601-634: do_ds off, eval mode, predict_3D with regions_class_order, restore state."""
+        if pad_border_mode == 'constant' and pad_kwargs is None:
+            pad_kwargs = {'constant_values': 0}
+        if do_mirroring and mirror_axes is None:
+            mirror_axes = (0, 1, 2)  # default_data_augmentation.py:70
+        net = self.network
+        ds, mode = net.do_ds, net.training
+        net.do_ds = False
+        net.eval()
+        try:
+            ret = net.predict_3D(data, do_mirroring=do_mirroring, mirror_axes=mirror_axes or (),
+                                 use_sliding_window=use_sliding_window, step_size=step_size,
+                                 patch_size=tuple(self.patch_size), regions_class_order=self.regions_class_order,
+                                 use_gaussian=use_gaussian, pad_border_mode=pad_border_mode, pad_kwargs=pad_kwargs,
+                                 all_in_gpu=all_in_gpu, verbose=verbose, mixed_precision=mixed_precision)
+        finally:
+            net.train(mode)
+            net.do_ds = ds
+        return ret
+
+    # ---- checkpoints (network_trainer.py:256-286, nnUNetTrainerV2_DDP.py:636-669: key names are the contract) -------
+    def save_checkpoint(self, fname, save_optimizer=True):
+        sd = {k: v.detach().cpu().clone() for k, v in self.network.state_dict().items()}
+        state = {'epoch': self.epoch + 1, 'state_dict': sd}
+        if save_optimizer and self.arena is not None:
+            state['optimizer_state_dict'] = {'flat_momentum': self.arena.mom.cpu(), 'first': self.arena.first}
+        elif save_optimizer and self.optimizer is not None:
+            state['optimizer_state_dict'] = self.optimizer.state_dict()
+        torch.save(state, fname)
+        with open(fname + ".pkl", 'wb') as f:
+            pickle.dump({'init': self.init_args, 'name': self.__class__.__name__, 'class': str(self.__class__),
+                         'plans': self.plans}, f)
+
+    def load_checkpoint_ram(self, checkpoint, train=True):
+        if not self.was_initialized:
+            self.initialize(train)
+        cur = self.network.state_dict()
+        new = {}
+        for k, v in checkpoint['state_dict'].items():
+            key = k[7:] if (k not in cur and k.startswith('module.')) else k
+            new[key] = v
+        with torch.no_grad():
+            for k, v in new.items():
+                cur[k].copy_(v)  # in place: parameters may be views of the flat arena
+        self.epoch = checkpoint.get('epoch', 0)
+
+
+class MultiTalent_trainer_ddp_2000ep(MultiTalent_trainer_ddp):
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.max_num_epochs = 2000
+
+
+# BASELINE.json names the trainer `nnUNetTrainerV2_MultiTalent`; the reference class is `MultiTalent_trainer_ddp`.
+nnUNetTrainerV2_MultiTalent = MultiTalent_trainer_ddp

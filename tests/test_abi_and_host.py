@@ -1,0 +1,159 @@
+"""CPU tests: the C-ABI library loads and exports exactly what include/mtb200.h declares; host logic (tap tables,
+module tree / state_dict keys, trainer bookkeeping, no-fallback behaviour)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from conftest import ROOT, build_small_net
+
+from multitalent_b200 import _lib as L
+from multitalent_b200 import engine as E
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "mtb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mtb200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(L.LIB_PATH):
+        from multitalent_b200.build import build
+        build()
+    lib = ctypes.CDLL(L.LIB_PATH)
+    names = _header_symbols()
+    assert len(names) >= 24
+    for n in names:
+        assert hasattr(lib, n), "libmtb200.so does not export %s" % n
+    assert sorted(L.SIGNATURES) == names, "ctypes binding and header disagree"
+    lib.mtb200_version.restype = ctypes.c_int
+    assert lib.mtb200_version() == 100
+
+
+def test_struct_layout_matches_header():
+    # sizes derived from the header: 6 pointers + ints; guards against ctypes/C drift
+    n_int_conv = 2 + 1 + 6 + 6 + 3 + 3 + 3 + 1 + (L.MAX_GROUPS + 1) + 3 * L.MAX_GROUPS + 1 + 3 * L.MAX_TAPS + L.MAX_TAPS + 2
+    assert ctypes.sizeof(L.ConvParams) == 6 * 8 + 4 * n_int_conv + (4 * n_int_conv) % 8
+    n_int_wg = 1 + 1 + 6 + 6 + 3 + 3 + 3 + 1 + (L.MAX_GROUPS + 1) + 3 * L.MAX_GROUPS + 1 + 3 * L.MAX_TAPS + L.MAX_TAPS + 1
+    assert ctypes.sizeof(L.WgradParams) == 4 * 8 + 4 * n_int_wg + (4 * n_int_wg) % 8
+
+
+def test_pad_channels():
+    assert [E.pad_channels(c) for c in (1, 30, 47, 60, 120, 240, 320)] == [16, 32, 48, 64, 128, 256, 320]
+
+
+def _dense_conv_from_taps(table, x, w, out_shape, grid):
+    """Evaluate a tap table with numpy loops (tiny sizes) -- checks the tables against torch's conv semantics."""
+    B, Cin = x.shape[0], x.shape[1]
+    Cout = w.shape[1]
+    out = np.zeros((B, Cout) + tuple(out_shape))
+    for g, ooff in enumerate(table.group_ooff):
+        for t in range(table.group_begin[g], table.group_begin[g + 1]):
+            off, widx = table.taps[t]
+            for d in range(grid[0]):
+                for h in range(grid[1]):
+                    for ww in range(grid[2]):
+                        src = [d * table.in_stride[0] + off[0], h * table.in_stride[1] + off[1],
+                               ww * table.in_stride[2] + off[2]]
+                        if any(s < 0 or s >= n for s, n in zip(src, x.shape[2:])):
+                            continue
+                        dst = (d * table.out_stride[0] + ooff[0], h * table.out_stride[1] + ooff[1],
+                               ww * table.out_stride[2] + ooff[2])
+                        out[(slice(None), slice(None)) + dst] += x[:, :, src[0], src[1], src[2]] @ w[widx].T
+    return out
+
+
+@pytest.mark.parametrize("kernel,stride", [((3, 3, 3), (1, 1, 1)), ((3, 3, 3), (2, 2, 2)), ((3, 3, 3), (1, 2, 2)),
+                                           ((1, 3, 3), (1, 1, 1)), ((1, 1, 1), (2, 2, 2))])
+def test_tap_tables_conv(kernel, stride):
+    torch.manual_seed(0)
+    x = torch.randn(1, 3, 4, 6, 4, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(2, 3, *kernel, dtype=torch.float64)
+    pad = [(k - 1) // 2 for k in kernel]
+    y = torch.nn.functional.conv3d(x, w, stride=stride, padding=pad)
+    wp = w.permute(2, 3, 4, 0, 1).reshape(-1, 2, 3).numpy()  # [tap][co][ci]
+    got = _dense_conv_from_taps(E.taps_conv_fwd(kernel, stride), x.detach().numpy(), wp, y.shape[2:], y.shape[2:])
+    np.testing.assert_allclose(got, y.detach().numpy(), atol=1e-10)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    wpt = np.transpose(wp, (0, 2, 1))  # [tap][ci][co]
+    grid = [n // s for n, s in zip(x.shape[2:], stride)]
+    got = _dense_conv_from_taps(E.taps_conv_dgrad(kernel, stride), gy.numpy(), wpt, x.shape[2:], grid)
+    np.testing.assert_allclose(got, x.grad.numpy(), atol=1e-10)
+
+
+@pytest.mark.parametrize("kernel", [(2, 2, 2), (1, 2, 2)])
+def test_tap_tables_conv_transpose(kernel):
+    torch.manual_seed(0)
+    x = torch.randn(1, 3, 2, 3, 2, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(3, 2, *kernel, dtype=torch.float64)  # [Cin][Cout][k]
+    y = torch.nn.functional.conv_transpose3d(x, w, stride=kernel)
+    wp = w.permute(2, 3, 4, 1, 0).reshape(-1, 2, 3).numpy()  # [tap][co][ci]
+    got = _dense_conv_from_taps(E.taps_convT_fwd(kernel), x.detach().numpy(), wp, y.shape[2:], x.shape[2:])
+    np.testing.assert_allclose(got, y.detach().numpy(), atol=1e-10)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    got = _dense_conv_from_taps(E.taps_convT_dgrad(kernel), gy.numpy(), np.transpose(wp, (0, 2, 1)), x.shape[2:],
+                                x.shape[2:])
+    np.testing.assert_allclose(got, x.grad.numpy(), atol=1e-10)
+
+
+def test_module_tree_matches_fixture_keys(golden_small):
+    blob, meta = golden_small
+    net = build_small_net(meta, blob, device="cpu")
+    keys = [k[len("param/"):] for k in blob if k.startswith("param/")]
+    assert list(net.state_dict().keys()) == keys  # same names AND same registration order as the reference
+    assert net._native_ok and net.do_ds and net._deep_supervision
+    assert list(net.input_shape_must_be_divisible_by) == [4, 8, 8]
+    assert net.conv_op == nn.Conv3d and net.num_classes == 47
+
+
+def test_no_cpu_fallback_on_native_configuration(golden_small):
+    blob, meta = golden_small
+    net = build_small_net(meta, blob, device="cpu")
+    with pytest.raises(L.Mtb200Error):
+        net(torch.zeros(1, 1, 8, 16, 16))
+    from multitalent_b200.training.loss_functions.multitalent_loss import multitalent_loss
+    with pytest.raises(L.Mtb200Error):
+        multitalent_loss([torch.zeros(1, 47, 8, 16, 16)], [torch.zeros(1, 1, 8, 16, 16)], [("03_liver",)], [1.0])
+
+
+def test_non_native_configuration_uses_torch_modules():
+    """2D / BatchNorm / dropout configurations are outside the native path and run through the torch leaf modules."""
+    from multitalent_b200.network_architecture.generic_UNet import Generic_UNet
+    net = Generic_UNet(1, 4, 3, 2, conv_op=nn.Conv2d, norm_op=nn.BatchNorm2d, dropout_op=nn.Dropout2d,
+                       final_nonlin=lambda x: x, convolutional_pooling=False, convolutional_upsampling=False)
+    assert not net._native_ok
+    out = net(torch.zeros(2, 1, 16, 16))
+    assert out[0].shape == (2, 3, 16, 16)
+
+
+def test_trainer_bookkeeping():
+    from multitalent_b200.training.network_training.MultiTalent_Trainer_DDP import (
+        MultiTalent_trainer_ddp, nnUNetTrainerV2_MultiTalent, poly_lr)
+    assert nnUNetTrainerV2_MultiTalent is MultiTalent_trainer_ddp
+    t = MultiTalent_trainer_ddp(None, 0, 0, init_distributed=False)
+    t.initialize(True)
+    np.testing.assert_allclose(t.ds_loss_weights, np.array([8, 4, 2, 1, 0]) / 15)
+    assert [list(map(float, s)) for s in t.deep_supervision_scales] == [[1, 1, 1], [.5] * 3, [.25] * 3, [.125] * 3,
+                                                                         [1 / 16] * 3]
+    assert t.num_classes == 47 and len(t.init_args) == 11
+    assert abs(poly_lr(500, 1000, 1e-2) - 1e-2 * 0.5 ** 0.9) < 1e-12
+    n_params = sum(p.numel() for p in t.network.parameters())
+    assert n_params == 29319560
+    assert len(t.network.state_dict()) == 98
+
+
+def test_region_bitmasks():
+    from multitalent_b200.dataset_conversion.Task100_MultiTalent import region_bitmasks, valid_channel_mask
+    pos, chan = region_bitmasks()
+    assert len(pos) == 48 and pos[0] == 0
+    assert pos[2] == (1 << chan['03_liver']) | (1 << chan['03_cancer'])  # label 2 (liver tumour) is in both regions
+    assert pos[43] == (1 << chan['64_both_kidneys']) | (1 << chan['64_kidney_tumor'])
+    assert valid_channel_mask(('03_liver', '03_cancer')) == 0b11
+    assert bin(valid_channel_mask(tuple(chan))).count("1") == 47

@@ -1,0 +1,335 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle and the committed
+reference fixtures.  Tolerances: T0 (fp32 storage, FFMA) <= 1e-3 max-abs on logits / probabilities / loss as
+BASELINE.json states; T1 (bf16/fp16 storage) within the reference's own autocast-vs-fp32 envelope (BASELINE.md section 5:
+bf16 0.19 / fp16 0.024 max-abs on logits of O(7))."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from conftest import build_small_net
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _engine(dtype=torch.float32, impl=0):
+    from multitalent_b200.engine import Engine
+    return Engine(dtype, impl)
+
+
+def _feat_to_ncdhw(f):
+    return f.as_ncdhw().float().cpu()
+
+
+# ---- single kernels --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cin,cout,kernel,stride,dims", [
+    (1, 30, (3, 3, 3), (1, 1, 1), (2, 6, 10, 12)),
+    (30, 30, (3, 3, 3), (1, 1, 1), (2, 6, 10, 12)),
+    (30, 60, (3, 3, 3), (2, 2, 2), (2, 8, 12, 16)),
+    (60, 70, (3, 3, 3), (1, 2, 2), (1, 5, 8, 12)),
+    (20, 24, (1, 3, 3), (1, 1, 1), (2, 4, 9, 7)),
+    (30, 47, (1, 1, 1), (1, 1, 1), (2, 4, 9, 7)),
+    (40, 40, (1, 1, 1), (2, 2, 2), (1, 4, 8, 6)),
+])
+def test_conv_fwd_dgrad_wgrad_fp32(cin, cout, kernel, stride, dims):
+    from multitalent_b200.engine import ConvOp, Tape
+    torch.manual_seed(0)
+    eng = _engine()
+    B, D, H, W = dims
+    x = torch.randn(B, cin, D, H, W)
+    conv = nn.Conv3d(cin, cout, kernel, stride, [(k - 1) // 2 for k in kernel], bias=True)
+    xr = x.clone().requires_grad_(True)
+    y_ref = conv(xr)
+    gy = torch.randn_like(y_ref)
+    y_ref.backward(gy)
+
+    convd = nn.Conv3d(cin, cout, kernel, stride, [(k - 1) // 2 for k in kernel], bias=True).to(DEV)
+    convd.load_state_dict(conv.state_dict())
+    op = ConvOp(convd.weight, convd.bias, kernel, stride)
+    tape = Tape()
+    xf = eng.input_feat(x.to(DEV))
+    y = eng.conv_plain(tape, op, xf, need_input_grad=True)
+    np.testing.assert_allclose(_feat_to_ncdhw(y).numpy(), y_ref.detach().numpy(), atol=2e-4, rtol=1e-4)
+    assert float(y.buf[..., cout:].abs().max()) == 0 if y.Cp > cout else True  # padded channels stay zero
+    eng.seed_grad(tape, y, gy.to(DEV))
+    eng.run_backward(tape)
+    gw = tape.param_grads[id(convd.weight)].cpu()
+    gb = tape.param_grads[id(convd.bias)].cpu()
+    np.testing.assert_allclose(gw.numpy(), conv.weight.grad.numpy(), atol=2e-3, rtol=1e-3)
+    np.testing.assert_allclose(gb.numpy(), conv.bias.grad.numpy(), atol=2e-3, rtol=1e-3)
+    gx, have = tape.grad_feat(xf)
+    assert have
+    np.testing.assert_allclose(_feat_to_ncdhw(gx).numpy(), xr.grad.numpy(), atol=2e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("kernel", [(2, 2, 2), (1, 2, 2)])
+def test_conv_transpose_fp32(kernel):
+    from multitalent_b200.engine import ConvOp, Tape
+    torch.manual_seed(1)
+    eng = _engine()
+    cin, cout = 60, 30
+    x = torch.randn(2, cin, 3, 5, 4)
+    tu = nn.ConvTranspose3d(cin, cout, kernel, kernel, bias=False)
+    xr = x.clone().requires_grad_(True)
+    y_ref = tu(xr)
+    gy = torch.randn_like(y_ref)
+    y_ref.backward(gy)
+    tud = nn.ConvTranspose3d(cin, cout, kernel, kernel, bias=False).to(DEV)
+    tud.load_state_dict(tu.state_dict())
+    op = ConvOp(tud.weight, None, kernel, kernel, transposed=True)
+    tape = Tape()
+    xf = eng.input_feat(x.to(DEV))
+    y = eng.conv_plain(tape, op, xf)
+    np.testing.assert_allclose(_feat_to_ncdhw(y).numpy(), y_ref.detach().numpy(), atol=2e-4, rtol=1e-4)
+    eng.seed_grad(tape, y, gy.to(DEV))
+    eng.run_backward(tape)
+    np.testing.assert_allclose(tape.param_grads[id(tud.weight)].cpu().numpy(), tu.weight.grad.numpy(), atol=2e-3,
+                               rtol=1e-3)
+    gx, _ = tape.grad_feat(xf)
+    np.testing.assert_allclose(_feat_to_ncdhw(gx).numpy(), xr.grad.numpy(), atol=2e-4, rtol=1e-4)
+
+
+def test_conv_norm_lrelu_chain_fp32():
+    """conv -> IN -> LReLU -> conv(stride 2) -> IN -> LReLU with norm-on-load, forward and all gradients."""
+    from multitalent_b200.engine import ConvOp, Tape
+    torch.manual_seed(2)
+    eng = _engine()
+    x = torch.randn(2, 1, 8, 12, 16) * 3 + 1
+
+    def make():
+        c1, n1 = nn.Conv3d(1, 30, 3, 1, 1), nn.InstanceNorm3d(30, affine=True)
+        c2, n2 = nn.Conv3d(30, 60, 3, 2, 1), nn.InstanceNorm3d(60, affine=True)
+        return c1, n1, c2, n2
+
+    mods = make()
+    with torch.no_grad():
+        for n in (mods[1], mods[3]):
+            n.weight.copy_(0.5 + torch.rand_like(n.weight))
+            n.bias.copy_(torch.randn_like(n.bias) * 0.3)
+    c1, n1, c2, n2 = mods
+    a1 = F.leaky_relu(n1(c1(x)), 0.01)
+    a2 = F.leaky_relu(n2(c2(a1)), 0.01)
+    ga = torch.randn_like(a2)
+    a2.backward(ga)
+
+    dm = make()
+    for s, d in zip(mods, dm):
+        d.load_state_dict(s.state_dict())
+        d.to(DEV)
+    d1, dn1, d2, dn2 = dm
+    op1 = ConvOp(d1.weight, d1.bias, (3, 3, 3), (1, 1, 1))
+    op2 = ConvOp(d2.weight, d2.bias, (3, 3, 3), (2, 2, 2))
+    tape = Tape()
+    xf = eng.input_feat(x.to(DEV))
+    f1 = eng.conv_norm(tape, op1, dn1.weight, dn1.bias, xf, need_input_grad=False)
+    f2 = eng.conv_norm(tape, op2, dn2.weight, dn2.bias, f1)
+    act2 = eng.materialize(f2)
+    np.testing.assert_allclose(_feat_to_ncdhw(act2).numpy(), a2.detach().numpy(), atol=5e-4)
+    eng.seed_grad(tape, f2, ga.to(DEV))
+    eng.run_backward(tape)
+    for dmod, smod in zip(dm, mods):
+        for (n, dp), (_, sp) in zip(dmod.named_parameters(), smod.named_parameters()):
+            g = tape.param_grads[id(dp)].cpu().numpy()
+            r = sp.grad.numpy()
+            np.testing.assert_allclose(g, r, atol=2e-3 + 2e-3 * np.abs(r).max(), err_msg=n)
+
+
+# ---- whole network against the reference fixtures ------------------------------------------------------------------
+def _fixture_tensors(blob, n_scales=3):
+    x = torch.from_numpy(blob["x"]).to(DEV)
+    tg = [torch.from_numpy(blob["target_%d" % i]).to(DEV) for i in range(n_scales)]
+    return x, tg
+
+
+def test_network_forward_matches_reference_fixture(golden_small):
+    blob, meta = golden_small
+    net = build_small_net(meta, blob)
+    x, _ = _fixture_tensors(blob)
+    with torch.no_grad():
+        out = net(x)
+    assert isinstance(out, tuple) and len(out) == 3
+    for i, o in enumerate(out):
+        assert tuple(o.shape) == blob["logits_%d" % i].shape
+        np.testing.assert_allclose(o.float().cpu().numpy(), blob["logits_%d" % i], atol=1e-3)
+    net.do_ds = False
+    with torch.no_grad():
+        o = net(x)
+    np.testing.assert_allclose(o.float().cpu().numpy(), blob["logits_0"], atol=1e-3)
+
+
+def test_loss_matches_reference_fixture(golden_small):
+    from multitalent_b200.training.loss_functions.multitalent_loss import multitalent_loss
+    from oracle import unet_oracle as O
+    blob, meta = golden_small
+    _, tg = _fixture_tensors(blob)
+    # (1) on the reference's own logits (generic NCDHW tensors -> conversion path)
+    zs = [torch.from_numpy(blob["logits_%d" % i]).to(DEV).requires_grad_(True) for i in range(3)]
+    l, ce, dc = multitalent_loss(zs, tg, meta["valid_regions"], blob["ds_loss_weights"])
+    np.testing.assert_allclose([l.item(), ce.item(), dc.item()], blob["loss"], rtol=2e-5, atol=1e-5)
+    l.backward()
+    zc = [torch.from_numpy(blob["logits_%d" % i]).requires_grad_(True) for i in range(3)]
+    lo, _, _ = O.multitalent_loss(zc, [t.cpu() for t in tg], meta["valid_regions"], blob["ds_loss_weights"])
+    lo.backward()
+    for a, b in zip(zs[:2], zc[:2]):
+        np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), atol=1e-8 + 1e-4 * float(b.grad.abs().max()))
+    assert zs[2].grad is None or float(zs[2].grad.abs().max()) == 0.0  # weight-0 scale
+
+
+def test_train_step_gradients_match_reference_fixture(golden_small):
+    from multitalent_b200.training.loss_functions.multitalent_loss import multitalent_loss
+    blob, meta = golden_small
+    net = build_small_net(meta, blob)
+    x, tg = _fixture_tensors(blob)
+    out = net(x)
+    l, ce, dc = multitalent_loss(out, tg, meta["valid_regions"], blob["ds_loss_weights"])
+    np.testing.assert_allclose([l.item(), ce.item(), dc.item()], blob["loss"], rtol=1e-4, atol=1e-4)
+    l.backward()
+    worst = 0.0
+    for n, p in net.named_parameters():
+        r = blob["grad/" + n]
+        assert p.grad is not None, "parameter %s received no gradient (DDP needs one for every parameter)" % n
+        g = p.grad.cpu().numpy()
+        scale = max(np.abs(r).max(), 1e-6)
+        err = np.abs(g - r).max() / scale
+        worst = max(worst, err)
+        assert err < 5e-3, "%s: rel-to-max error %.3e" % (n, err)
+    print("worst gradient error relative to max |g|: %.2e" % worst)
+
+
+def test_sliding_window_matches_reference_fixture(golden_small, golden_sliding):
+    blob, meta = golden_small
+    net = build_small_net(meta, blob)
+    net.eval()
+    net.do_ds = False
+    vol = golden_sliding["vol"][None]
+    for mirror, key in ((True, "mirror"), (False, "nomirror")):
+        seg, prob = net.predict_3D(vol, do_mirroring=mirror, mirror_axes=(0, 1, 2), use_sliding_window=True,
+                                   step_size=0.5, patch_size=(8, 16, 16), regions_class_order=tuple(range(47)),
+                                   use_gaussian=True, verbose=False)
+        assert prob.shape == (47, 12, 24, 28) and seg.shape == (12, 24, 28) and seg.dtype == np.float32
+        np.testing.assert_allclose(prob[:, ::2, ::2, ::2], golden_sliding["prob_%s_sub" % key], atol=1e-3)
+        # voxels whose decisive probability is within 1e-3 of the threshold may flip
+        assert (seg != golden_sliding["seg_%s" % key]).mean() < 5e-3
+
+
+def test_mirror_and_pred_api(golden_small):
+    from oracle import unet_oracle as O
+    blob, meta = golden_small
+    net = build_small_net(meta, blob).eval()
+    net.do_ds = False
+    sd = {k[len("param/"):]: torch.from_numpy(v) for k, v in blob.items() if k.startswith("param/")}
+    x = torch.from_numpy(blob["x"][:1])
+    g = O.get_gaussian((8, 16, 16))
+    res = net._internal_maybe_mirror_and_pred_3D(x.numpy(), (0, 2), True, g)
+
+    def net_fn(t):
+        with torch.no_grad():
+            return torch.sigmoid(O.generic_unet_forward(t, sd, meta["pool"], meta["convk"], do_ds=False))
+    ref = O.mirror_and_predict(net_fn, x, (0, 2), True, torch.from_numpy(g), 47)
+    np.testing.assert_allclose(res.cpu().numpy(), ref.numpy(), atol=1e-3)
+
+
+def test_flat_sgd_step_matches_oracle():
+    from multitalent_b200.training.network_training.MultiTalent_Trainer_DDP import FlatArena
+    from oracle import unet_oracle as O
+    torch.manual_seed(3)
+    m = nn.Sequential(nn.Conv3d(3, 5, 3), nn.Conv3d(5, 7, 1)).to(DEV)
+    ps = [p.detach().cpu().clone() for p in m.parameters()]
+    arena = FlatArena(m)
+    bufs = [None] * len(ps)
+    for step in range(3):
+        gs = [torch.randn_like(p) * (30.0 if step == 0 else 0.1) for p in ps]  # first step clips, others do not
+        arena.zero_grad()
+        for p, g in zip(m.parameters(), gs):
+            p.grad.copy_(g.to(DEV))
+        arena.step(1e-2, 0.99, 3e-5, 12.0)
+        ps, bufs, _ = O.clip_and_sgd_step(ps, gs, bufs, 1e-2)
+        for p, r in zip(m.parameters(), ps):
+            np.testing.assert_allclose(p.detach().cpu().numpy(), r.numpy(), atol=2e-6)
+
+
+def test_trainer_step_matches_oracle_step(golden_small):
+    """One full run_iteration (forward, loss, backward, clip 12, Nesterov SGD) vs the oracle's step on the CPU."""
+    from multitalent_b200.plans import default_plans
+    from multitalent_b200.training.network_training.MultiTalent_Trainer_DDP import MultiTalent_trainer_ddp
+    from oracle import unet_oracle as O
+    blob, meta = golden_small
+    plans = default_plans(patch_size=(8, 16, 16), batch_size=2)
+    plans['plans_per_stage'][1]['pool_op_kernel_sizes'] = meta["pool"]
+    plans['plans_per_stage'][1]['conv_kernel_sizes'] = meta["convk"]
+    plans['base_num_features'] = meta["base"]
+    tr = MultiTalent_trainer_ddp(plans, 0, 0, init_distributed=False)
+    tr.initialize(True)
+    sd = {k[len("param/"):]: torch.from_numpy(v) for k, v in blob.items() if k.startswith("param/")}
+    tr.load_checkpoint_ram({'state_dict': {"module." + k: v for k, v in sd.items()}, 'epoch': 0})
+    batch = {'data': blob["x"], 'target': [blob["target_%d" % i] for i in range(3)],
+             'properties': [{'valid_regions': tuple(v)} for v in meta["valid_regions"]]}
+    l, ce, dc = tr.run_iteration(iter([batch]), True)
+    np.testing.assert_allclose([l, ce, dc], blob["loss"], rtol=1e-4, atol=1e-4)
+    names = [n for n, _ in tr.network.named_parameters()]
+    ps = [sd[n] for n in names]
+    gs = [torch.from_numpy(blob["grad/" + n]) for n in names]
+    new_p, _, _ = O.clip_and_sgd_step(ps, gs, [None] * len(ps), tr.lr)
+    for n, p, r in zip(names, tr.network.parameters(), new_p):
+        d = (p.detach().cpu() - r).abs().max().item()
+        step = (r - sd[n]).abs().max().item()
+        assert d <= 1e-6 + 1e-2 * step, "%s: update differs by %.3e (step size %.3e)" % (n, d, step)
+    # a second iteration must run on the updated (re-packed) weights and change the loss
+    l2, _, _ = tr.run_iteration(iter([batch]), True)
+    assert np.isfinite(l2) and l2 != l
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 0.19), (torch.float16, 0.024)])
+def test_reduced_precision_within_reference_envelope(golden_small, dtype, tol):
+    from multitalent_b200.training.loss_functions.multitalent_loss import multitalent_loss
+    blob, meta = golden_small
+    net = build_small_net(meta, blob, dtype=dtype)
+    x, tg = _fixture_tensors(blob)
+    out = net(x)
+    assert out[0].dtype == dtype
+    for i, o in enumerate(out):
+        assert float((o.float().cpu() - torch.from_numpy(blob["logits_%d" % i])).abs().max()) < tol
+    l, ce, dc = multitalent_loss(out, tg, meta["valid_regions"], blob["ds_loss_weights"])
+    assert abs(l.item() - blob["loss"][0]) < 1e-2 * abs(blob["loss"][0]) + 1e-2
+    l.backward()
+    # gradient direction agrees with the fp32 reference
+    num = den_a = den_b = 0.0
+    for n, p in net.named_parameters():
+        r = torch.from_numpy(blob["grad/" + n]).double()
+        g = p.grad.cpu().double()
+        num += float((g * r).sum()); den_a += float((g * g).sum()); den_b += float((r * r).sum())
+    cos = num / (den_a ** 0.5 * den_b ** 0.5)
+    assert cos > 0.98, "gradient cosine vs fp32 reference = %.4f" % cos
+
+
+# ---- BASELINE.json config 0: 1 x 192x160x128, bs1, forward + loss against the CPU oracle --------------------------------
+def test_config0_full_patch_forward_and_loss_vs_cpu_oracle():
+    from multitalent_b200.plans import default_plans
+    from multitalent_b200.training.network_training.MultiTalent_Trainer_DDP import MultiTalent_trainer_ddp
+    from oracle import unet_oracle as O
+    patch = (192, 160, 128)
+    tr = MultiTalent_trainer_ddp(default_plans(patch_size=patch, batch_size=1), 0, 0, init_distributed=False)
+    torch.manual_seed(0)
+    tr.initialize(True)
+    rng = np.random.RandomState(1234)
+    task = O.TASK_IDS[6]
+    vol, lab = O.synthetic_ct_and_labels(patch, task, rng)
+    x = torch.from_numpy(vol[None, None])
+    scales = [[1, 1, 1], [.5] * 3, [.25] * 3, [.125] * 3, [1 / 16] * 3]
+    tg = [torch.from_numpy(t) for t in O.downsample_targets(lab[None, None], scales)]
+    valid = [O.VALID_REGIONS[task]]
+    sd = {k: v.detach().cpu() for k, v in tr.network.state_dict().items()}
+    with torch.no_grad():
+        ref = O.generic_unet_forward(x, sd, tr.net_num_pool_op_kernel_sizes, tr.net_conv_kernel_sizes)
+        ref_l = O.multitalent_loss(ref, tg, valid, tr.ds_loss_weights)
+        out = tr.network(x.to(DEV))
+        l = tr.compute_loss(out, [t.to(DEV) for t in tg], valid)
+    for a, b in zip(out, ref):
+        err = float((a.float().cpu() - b).abs().max())
+        assert err < 1e-3, "max-abs logit error %.3e" % err
+        assert float((torch.sigmoid(a.float().cpu()) - torch.sigmoid(b)).abs().max()) < 1e-3
+    for a, b in zip(l, ref_l):
+        assert abs(a.item() - b.item()) < 1e-3 * max(1.0, abs(b.item()))
