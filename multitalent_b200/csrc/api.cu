@@ -108,7 +108,7 @@ int mtb200_wgrad_taps(const mtb200_wgrad_params* p, void* stream) {
   if (int r = validate_taps(p->ngroups, p->group_tap_begin, p->ntaps)) return r;
   if (p->impl == 2 || (p->impl == 0 && umma_available() && p->dtype != MTB200_F32)) {
     int r = wgrad_taps_umma(*p, STREAM(stream));
-    if (r != MTB200_ERR_UNSUPPORTED || p->impl == 2) return r;
+    if (r != MTB200_ERR_UNSUPPORTED) return r;  // shapes the tensor-core kernel does not cover use the CUDA-core one
   }
   return wgrad_taps_ffma(*p, STREAM(stream));
 }

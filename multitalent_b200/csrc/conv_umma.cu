@@ -1,17 +1,484 @@
-// tcgen05 (UMMA) + TMA implementation of the tap-table convolution -- placeholder until the kernel lands.
+// tcgen05 (UMMA) + TMA implementation of the tap-table convolution for 16-bit activations (bf16 / fp16), sm_100a.
+//
+// Implicit GEMM, im2col-free:  D[128 voxels x BN couts] (fp32, TMEM) = sum over (tap, channel chunk) A_tap * W_tap^T
+//   * A_tap  : [128 rows = a (bd,bh,bw) brick of output voxels] x [KC channels], K-major, fetched by ONE 5-D TMA box
+//              per (tap, chunk) at the tap-shifted coordinates; out-of-volume reads are zero-filled by TMA (= the conv's
+//              zero padding).  Strided problems use one tensor map per input parity class (base shifted by the parity,
+//              strides doubled), so no element-stride gathers are needed.
+//   * W_tap  : [BN couts] x [KC channels] K-major slice of the packed weights [tap][Cout][Cin], 3-D TMA box.
+//   * both operands land in shared memory in the canonical 128B/64B/32B-swizzled K-major layout (swizzle span = KC*2 B)
+//     and are consumed by tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) issued by one thread.
+//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+//     (TMEM -> registers -> +bias -> round -> global; per-(b, cout) sum / sum-of-squares for InstanceNorm).
+//   * one output tile per CTA, two CTAs per SM (<= 256 TMEM columns and <= ~100 KB smem each) so that one CTA's
+//     epilogue overlaps the other's main loop.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace mtb {
 
-int umma_available() { return 0; }
+// ---------------------------------------------------------------------------------------------------------------------
+// driver entry point for tensor-map encoding (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int conv_taps_umma(const mtb200_conv_params&, cudaStream_t) {
-  set_error("conv_taps(umma): not built");
-  return MTB200_ERR_UNSUPPORTED;
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+int umma_available() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0, major = 0;
+    cached = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess && major == 10 &&
+        get_encode_fn() != nullptr)
+      cached = 1;
+    cudaGetLastError();
+  }
+  return cached;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, K-major, swizzle span == row pitch (KC * 2 bytes), atoms of 8 rows
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t row_bytes) {
+  const uint32_t sbo = 8u * row_bytes;  // byte distance between 8-row groups
+  const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);  // SWIZZLE_128B / 64B / 32B
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);        // start address            bits [0,14)
+  d |= (uint64_t)0 << 16;                              // leading byte offset      bits [16,30) (unused: 1 atom on K)
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;         // stride byte offset       bits [32,46)
+  d |= 1ull << 46;                                     // descriptor version (sm_100)
+  d |= layout << 61;                                   // swizzle mode             bits [61,64)
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int UM_MAX_STAGES = 8;
+constexpr int UM_THREADS = 192;
+
+struct UmmaConvParams {
+  CUtensorMap a_maps[8];
+  CUtensorMap w_map;
+  void* out;
+  const float* bias;
+  double* stats;
+  int B, Do, Ho, Wo;
+  int bd, bh, bw, tiles_d, tiles_h, tiles_w;
+  int Dof, Hof, Wof, out_ldc, out_coff, Cout;
+  int os[3];
+  int group_tap_begin[MTB200_MAX_GROUPS + 1];
+  int group_ooff[MTB200_MAX_GROUPS][3];
+  int tap_map[MTB200_MAX_TAPS];
+  int tap_coff[MTB200_MAX_TAPS][3];
+  int tap_widx[MTB200_MAX_TAPS];
+  int nkc, KC, BN, stages, tmem_cols;
+  int accumulate, is_f16;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(UM_THREADS, 1) conv_taps_umma_kernel(const __grid_constant__ UmmaConvParams p) {
+  extern __shared__ uint8_t dsmem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[UM_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[UM_MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_sum[256], s_sq[256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t row_bytes = p.KC * 2;
+  const uint32_t a_bytes = 128u * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
+  const uint32_t stage_bytes = ((a_bytes + b_bytes + 1023u) / 1024u) * 1024u;
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w; t /= p.tiles_w;
+  const int th = t % p.tiles_h; t /= p.tiles_h;
+  const int td = t % p.tiles_d;
+  const int b = t / p.tiles_d;
+  const int d0 = td * p.bd, h0 = th * p.bh, w0 = tw * p.bw;
+  const int n0 = blockIdx.y * p.BN;
+  const int g = blockIdx.z;
+  const int tap_begin = p.group_tap_begin[g], tap_end = p.group_tap_begin[g + 1];
+  const int niter = (tap_end - tap_begin) * p.nkc;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 256; i += UM_THREADS) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      tma_prefetch_desc(&p.w_map);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < niter; ++it) {
+        const int tp = tap_begin + it / p.nkc;
+        const int kc = it % p.nkc;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sa = dsmem + (size_t)stage * stage_bytes;
+        uint8_t* sb = sa + a_bytes;
+        mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+        tma_load_5d(sa, &p.a_maps[p.tap_map[tp]], &full_bar[stage], kc * p.KC, w0 + p.tap_coff[tp][2],
+                    h0 + p.tap_coff[tp][1], d0 + p.tap_coff[tp][0], b);
+        tma_load_3d(sb, &p.w_map, &full_bar[stage], kc * p.KC, n0, p.tap_widx[tp]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A/B = bf16 or f16, both K-major, N, M=128
+      const uint32_t fmt = p.is_f16 ? 0u : 1u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < niter; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(dsmem + (size_t)stage * stage_bytes);
+        const uint32_t sb = sa + a_bytes;
+        const int ksteps = p.KC / 16;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t da = make_kmajor_desc(sa + k * 32, row_bytes);
+          const uint64_t db = make_kmajor_desc(sb + k * 32, row_bytes);
+          umma_f16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot once the MMAs above have read it
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(&tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5; warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;  // row of the tile == TMEM lane
+    const int rw = row % p.bw, rh = (row / p.bw) % p.bh, rd = row / (p.bw * p.bh);
+    const int od = d0 + rd, oh = h0 + rh, ow = w0 + rw;
+    const bool valid = od < p.Do && oh < p.Ho && ow < p.Wo;
+    T* out = reinterpret_cast<T*>(p.out);
+    const long long ovox = (((long long)b * p.Dof + (od * p.os[0] + p.group_ooff[g][0])) * p.Hof +
+                            (oh * p.os[1] + p.group_ooff[g][1])) * p.Wof + (ow * p.os[2] + p.group_ooff[g][2]);
+    T* orow = out + ovox * p.out_ldc + p.out_coff + n0;
+    if (niter > 0) {
+      mbar_wait(&tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      uint32_t r[16];
+      float v[16];
+      if (niter > 0) {
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+      }
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + n0 + c0 + j);
+      }
+      if (valid) {
+        if (p.accumulate) {
+          float o[8];
+          load8<T>(orow + c0, o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += o[j];
+          load8<T>(orow + c0 + 8, o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[8 + j] += o[j];
+        }
+        float lo[8], hi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+        store8<T>(orow + c0, lo);
+        store8<T>(orow + c0 + 8, hi);
+      }
+      if (p.stats) {
+        // column sums over the 32 rows of this warp: transposing butterfly (16 shuffles per statistic)
+        float s[16], ss[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float x = valid ? Traits<T>::round(v[j]) : 0.f;
+          s[j] = x;
+          ss[j] = x * x;
+        }
+#pragma unroll
+        for (int off = 16, w = 16; off >= 2; off >>= 1, w >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int j = 0; j < w / 2; ++j) {
+            const float send_s = up ? s[j] : s[j + w / 2];
+            const float send_q = up ? ss[j] : ss[j + w / 2];
+            const float rs = __shfl_xor_sync(0xffffffffu, send_s, off);
+            const float rq = __shfl_xor_sync(0xffffffffu, send_q, off);
+            s[j] = (up ? s[j + w / 2] : s[j]) + rs;
+            ss[j] = (up ? ss[j + w / 2] : ss[j]) + rq;
+          }
+        }
+        s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+        ss[0] += __shfl_xor_sync(0xffffffffu, ss[0], 1);
+        if ((lane & 1) == 0) {
+          const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          atomicAdd(&s_sum[c0 + col], s[0]);
+          atomicAdd(&s_sq[c0 + col], ss[0]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (p.stats) {
+    for (int c = threadIdx.x; c < p.BN; c += UM_THREADS) {
+      if (s_sum[c] != 0.f || s_sq[c] != 0.f) {
+        double* st = p.stats + ((long long)b * p.Cout + n0 + c) * 2;
+        atomicAdd(st, (double)s_sum[c]);
+        atomicAdd(st + 1, (double)s_sq[c]);
+      }
+    }
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+static int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+static bool encode_map(EncodeTiledFn enc, CUtensorMap* m, CUtensorMapDataType dt, int rank, void* base,
+                       const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box, int row_bytes) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                 : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = enc(m, dt, (cuuint32_t)rank, base, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu box %u %u %u", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0], box[1], box[2]);
+    return false;
+  }
+  return true;
+}
+
+int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
+  if (!umma_available()) { set_error("conv_taps(umma): no sm_100 device / driver entry point"); return MTB200_ERR_UNSUPPORTED; }
+  if (p.dtype != MTB200_BF16 && p.dtype != MTB200_F16) { set_error("conv_taps(umma): 16-bit activations only"); return MTB200_ERR_UNSUPPORTED; }
+  if (p.wdtype != p.dtype) { set_error("conv_taps(umma): weights must have the activation dtype"); return MTB200_ERR_UNSUPPORTED; }
+  if (p.xform) { set_error("conv_taps(umma): on-load transform not supported (materialise the input)"); return MTB200_ERR_UNSUPPORTED; }
+  if (p.Cin % 16 || p.Cout % 16 || p.in_ldc % 8 || p.in_coff % 8 || p.out_ldc % 8 || p.out_coff % 8) {
+    set_error("conv_taps(umma): channel alignment (Cin %d Cout %d)", p.Cin, p.Cout);
+    return MTB200_ERR_UNSUPPORTED;
+  }
+  for (int k = 0; k < 3; ++k)
+    if (p.is[k] < 1 || p.is[k] > 2) { set_error("conv_taps(umma): input stride %d", p.is[k]); return MTB200_ERR_UNSUPPORTED; }
+  const long long M = (long long)p.B * p.Do * p.Ho * p.Wo;
+  if (M == 0) return MTB200_OK;
+  EncodeTiledFn enc = get_encode_fn();
+
+  static UmmaConvParams q;  // large: keep off the stack (host calls are serialised by the GIL / one thread per process)
+  memset(&q, 0, sizeof(q));
+  q.KC = (p.Cin % 64 == 0) ? 64 : ((p.Cin % 32 == 0) ? 32 : 16);
+  q.nkc = p.Cin / q.KC;
+  // N tile: whole Cout if <= 128, else the largest multiple-of-16 divisor <= 160
+  q.BN = p.Cout;
+  if (q.BN > 128) {
+    q.BN = 0;
+    for (int c = 160; c >= 16; c -= 16)
+      if (p.Cout % c == 0) { q.BN = c; break; }
+  }
+  q.tmem_cols = 32;
+  while (q.tmem_cols < q.BN) q.tmem_cols *= 2;
+  // brick: powers of two with product 128 minimising the number of tiles (ties: widest in w)
+  long long best = -1;
+  for (int bw = 128; bw >= 1; bw >>= 1)
+    for (int bh = 128 / bw; bh >= 1; bh >>= 1) {
+      const int bd = 128 / (bw * bh);
+      const long long nt = (long long)((p.Do + bd - 1) / bd) * ((p.Ho + bh - 1) / bh) * ((p.Wo + bw - 1) / bw);
+      if (best < 0 || nt < best) { best = nt; q.bd = bd; q.bh = bh; q.bw = bw; }
+    }
+  q.tiles_d = (p.Do + q.bd - 1) / q.bd; q.tiles_h = (p.Ho + q.bh - 1) / q.bh; q.tiles_w = (p.Wo + q.bw - 1) / q.bw;
+  const long long ntiles = (long long)p.B * q.tiles_d * q.tiles_h * q.tiles_w;
+  MTB_REQUIRE(ntiles < (1LL << 31), "conv_taps(umma): too many tiles");
+
+  const int row_bytes = q.KC * 2;
+  const CUtensorMapDataType dt = p.dtype == MTB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  // one activation map per parity class used by the taps
+  int parity_slot[8];
+  for (int i = 0; i < 8; ++i) parity_slot[i] = -1;
+  int nmaps = 0;
+  const int Dims[3] = {p.Di, p.Hi, p.Wi};
+  for (int t = 0; t < p.ntaps; ++t) {
+    int par[3], coord[3];
+    for (int k = 0; k < 3; ++k) {
+      const int off = p.tap_off[t][k];
+      par[k] = ((off % p.is[k]) + p.is[k]) % p.is[k];
+      coord[k] = floor_div(off - par[k], p.is[k]);
+    }
+    const int code = par[0] * 4 + par[1] * 2 + par[2];
+    if (parity_slot[code] < 0) {
+      // extents of the parity sub-lattice; an empty sub-lattice (possible only for degenerate sizes) is unsupported
+      cuuint64_t dims[5], strides[4];
+      cuuint32_t box[5] = {(cuuint32_t)q.KC, (cuuint32_t)q.bw, (cuuint32_t)q.bh, (cuuint32_t)q.bd, 1};
+      long long ext[3];
+      for (int k = 0; k < 3; ++k) {
+        ext[k] = (Dims[k] - par[k] + p.is[k] - 1) / p.is[k];
+        if (ext[k] < 1) { set_error("conv_taps(umma): empty parity lattice"); return MTB200_ERR_UNSUPPORTED; }
+      }
+      dims[0] = p.Cin; dims[1] = ext[2]; dims[2] = ext[1]; dims[3] = ext[0]; dims[4] = p.B;
+      const long long e = 2;  // bytes per element
+      strides[0] = (cuuint64_t)p.in_ldc * e * p.is[2];
+      strides[1] = (cuuint64_t)p.Wi * p.in_ldc * e * p.is[1];
+      strides[2] = (cuuint64_t)p.Hi * p.Wi * p.in_ldc * e * p.is[0];
+      strides[3] = (cuuint64_t)p.Di * p.Hi * p.Wi * p.in_ldc * e;
+      uint8_t* base = (uint8_t*)p.in + ((((long long)par[0] * p.Hi + par[1]) * p.Wi + par[2]) * p.in_ldc + p.in_coff) * e;
+      if (!encode_map(enc, &q.a_maps[nmaps], dt, 5, base, dims, strides, box, row_bytes)) return MTB200_ERR_CUDA;
+      parity_slot[code] = nmaps++;
+    }
+    q.tap_map[t] = parity_slot[code];
+    for (int k = 0; k < 3; ++k) q.tap_coff[t][k] = coord[k];
+    q.tap_widx[t] = p.tap_widx[t];
+  }
+  {
+    int n_widx = 0;
+    for (int t = 0; t < p.ntaps; ++t) n_widx = max(n_widx, p.tap_widx[t] + 1);
+    cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, (cuuint64_t)n_widx};
+    cuuint64_t strides[2] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Cin * p.Cout * 2};
+    cuuint32_t box[3] = {(cuuint32_t)q.KC, (cuuint32_t)q.BN, 1};
+    if (!encode_map(enc, &q.w_map, dt, 3, (void*)p.w, dims, strides, box, row_bytes)) return MTB200_ERR_CUDA;
+  }
+  q.out = p.out; q.bias = p.bias; q.stats = p.stats;
+  q.B = p.B; q.Do = p.Do; q.Ho = p.Ho; q.Wo = p.Wo;
+  q.Dof = p.Dof; q.Hof = p.Hof; q.Wof = p.Wof; q.out_ldc = p.out_ldc; q.out_coff = p.out_coff; q.Cout = p.Cout;
+  for (int k = 0; k < 3; ++k) q.os[k] = p.os[k];
+  for (int g = 0; g <= p.ngroups; ++g) q.group_tap_begin[g] = p.group_tap_begin[g];
+  for (int g = 0; g < p.ngroups; ++g)
+    for (int k = 0; k < 3; ++k) q.group_ooff[g][k] = p.group_ooff[g][k];
+  q.accumulate = p.accumulate;
+  q.is_f16 = p.dtype == MTB200_F16;
+
+  const int stage_bytes = ((128 * row_bytes + q.BN * row_bytes + 1023) / 1024) * 1024;
+  const int budget = 100 * 1024;
+  q.stages = max(2, min(UM_MAX_STAGES, budget / stage_bytes));
+  const int smem = q.stages * stage_bytes + 1024;
+  dim3 grid((unsigned)ntiles, p.Cout / q.BN, p.ngroups);
+  cudaError_t e;
+  if (p.dtype == MTB200_BF16) {
+    e = cudaFuncSetAttribute(conv_taps_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) conv_taps_umma_kernel<__nv_bfloat16><<<grid, UM_THREADS, smem, s>>>(q);
+  } else {
+    e = cudaFuncSetAttribute(conv_taps_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) conv_taps_umma_kernel<__half><<<grid, UM_THREADS, smem, s>>>(q);
+  }
+  if (e != cudaSuccess) { set_error("conv_taps(umma): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
+  return check_launch("conv_taps_umma");
 }
 
 int wgrad_taps_umma(const mtb200_wgrad_params&, cudaStream_t) {
-  set_error("wgrad_taps(umma): not built");
+  set_error("wgrad_taps(umma): not implemented yet");
   return MTB200_ERR_UNSUPPORTED;
 }
 

@@ -122,6 +122,7 @@ class Feat:
     Cp: int                             # padded channels (slice width)
     xform: Optional[torch.Tensor] = None     # [B, Cp, 4] pending {scale, shift, slope, 0}; None = already materialised
     meanrstd: Optional[torch.Tensor] = None  # [B, Cp, 2]
+    act: Optional["Feat"] = None             # cached materialised activation f(raw) (tensor-core path)
 
     @property
     def dims(self):
@@ -272,6 +273,24 @@ class Engine:
         self.dtype = dtype
         self.impl = impl  # 0 auto, 1 force FFMA, 2 force tcgen05
         self.wdtype = torch.float32 if dtype == torch.float32 else dtype
+        self._materialize = None
+
+    @property
+    def materialize_inputs(self) -> bool:
+        """The tcgen05 conv kernel feeds TMA tiles straight to the tensor core, so its inputs must already be
+        normalised + activated; the CUDA-core kernels apply the pending transform while loading instead."""
+        if self._materialize is None:
+            self._materialize = bool(self.dtype != torch.float32 and self.impl != 1
+                                     and L.lib().mtb200_has_tcgen05() == 1)
+        return self._materialize
+
+    def operand(self, x: Feat) -> Feat:
+        """The tensor a conv kernel reads for `x`: `x` itself (norm-on-load) or its cached materialised activation."""
+        if x.xform is None or not self.materialize_inputs:
+            return x
+        if x.act is None:
+            x.act = self.materialize(x)
+        return x.act
 
     # ---- helpers ------------------------------------------------------------------------------------------------
     def new_buf(self, dims, ldc, device, zero=False):
@@ -317,6 +336,7 @@ class Engine:
     def conv(self, op: ConvOp, x: Feat, out: Optional[Feat] = None, want_stats=False):
         """Raw convolution (or transposed convolution) of `x` into `out` (allocated if None).  Returns (out, stats)."""
         assert x.Cp == op.Cin_p, "input slice width %d != conv's padded Cin %d" % (x.Cp, op.Cin_p)
+        x = self.operand(x)
         odims = op.out_dims(x.dims)
         dev = x.buf.device
         if out is None:
@@ -363,10 +383,11 @@ class Engine:
     def _conv_norm_bwd(self, tape, op, gamma_param, beta_param, gamma, x: Feat, y: Feat, need_input_grad):
         dev = y.buf.device
         B = y.dims[0]
-        if not tape.has_grad(y):  # output never used downstream: all gradients are exactly zero
+        src = y.act if y.act is not None else y  # consumers of a materialised activation left their gradient there
+        if not tape.has_grad(src):  # output never used downstream: all gradients are exactly zero
             self._zero_param_grads(tape, op, gamma_param, beta_param)
             return
-        g, _ = tape.grad_feat(y)
+        g, _ = tape.grad_feat(src)
         red = torch.zeros((B, y.Cp, 2), dtype=torch.float64, device=dev)
         dt = L.dtype_enum(self.dtype)
         L.call("mtb200_in_bwd_reduce", g.ptr(), g.ldc, g.coff, y.ptr(), y.ldc, y.coff, dt, B, y.nvox, y.Cp,
@@ -390,6 +411,7 @@ class Engine:
         """Weight / bias gradient and data gradient of a (transposed) convolution given d(raw output)."""
         dev = dy.buf.device
         dt = L.dtype_enum(self.dtype)
+        x = self.operand(x)
         # ---- weight gradient (same tap table as the forward problem)
         dw = torch.zeros((op.ntap, op.Cout_p, op.Cin_p), dtype=torch.float32, device=dev)
         p = L.WgradParams()
@@ -422,7 +444,7 @@ class Engine:
         dyv = Feat(dy.buf, dy.coff, dy.C, dy.Cp)  # gradients carry no pending transform
         self._conv_call(op.dgrad_taps, dyv, op.packed(self.wdtype, True), None, gx, grid, None, have, op.Cout_p,
                         op.Cin_p, flops=fl, tag="conv_dgrad")
-        tape.mark(gx)
+        tape.mark(x)
 
     def conv_plain(self, tape: Optional[Tape], op: ConvOp, x: Feat, out: Optional[Feat] = None,
                    need_input_grad=True) -> Feat:
@@ -455,7 +477,7 @@ class Engine:
                         gt.buf[..., gt.coff:gt.coff + gt.Cp] += g.buf[..., g.coff:g.coff + g.Cp]
                     else:
                         gt.buf[..., gt.coff:gt.coff + gt.Cp] = g.buf[..., g.coff:g.coff + g.Cp]
-                    tape.mark(gt)
+                    tape.mark(t)
             tape.closures.append(bwd)
         return out
 
@@ -476,7 +498,7 @@ class Engine:
             L.call("mtb200_ncdhw_to_ndhwc", L.ptr(src), B, Cc, D * H * W, g.ptr(), L.dtype_enum(self.dtype), g.ldc,
                    g.coff, g.Cp, L.stream_ptr())
             tape.keep.append(src)
-        tape.mark(Feat(tape.grad_bufs[id(y.buf)], y.coff, y.C, y.Cp))
+        tape.mark(y)
 
     def run_backward(self, tape: Tape):
         for c in reversed(tape.closures):

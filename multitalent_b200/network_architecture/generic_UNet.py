@@ -347,15 +347,21 @@ class Generic_UNet(SegmentationNetwork):
         dev = f.buf.device
         skips = []
         first = True
+        mat = eng.materialize_inputs
         for stage in ops['enc']:
             for i, (op, g, b) in enumerate(stage):
                 out = None
-                if i == len(stage) - 1:
-                    # the stage output is the skip: write it straight into the second half of the concat buffer
+                last = i == len(stage) - 1
+                if last:
+                    # the stage output is the skip: it goes straight into the second half of the concat buffer --
+                    # raw (norm-on-load kernels) or, for the TMA-fed tensor-core kernels, as the materialised activation
                     od = op.out_dims(f.dims)
                     cat = eng.new_buf(od, 2 * op.Cout_p, dev)
-                    out = Feat(cat, op.Cout_p, op.Cout, op.Cout_p)
+                    if not mat:
+                        out = Feat(cat, op.Cout_p, op.Cout, op.Cout_p)
                 f = eng.conv_norm(tape, op, g, b, f, out, need_input_grad=not first)
+                if last and mat:
+                    f.act = eng.materialize(f, out=Feat(cat, op.Cout_p, op.Cout, op.Cout_p))
                 first = False
             skips.append(f)
         for (op, g, b) in ops['bott']:
@@ -364,15 +370,18 @@ class Generic_UNet(SegmentationNetwork):
         nu = len(ops['tu'])
         for u in range(nu):
             skip = skips[-(u + 1)]
-            cat = skip.buf
+            cat = skip.act.buf if mat else skip.buf
             top = ops['tu'][u]
             assert top.Cout_p == skip.Cp and cat.shape[4] == 2 * skip.Cp
             # the transposed conv writes the first half of the same buffer: torch.cat (generic_UNet.py:392) vanishes
             eng.conv_plain(tape, top, f, Feat(cat, 0, top.Cout, top.Cout_p))
-            ident = torch.zeros((cat.shape[0], skip.Cp, 4), dtype=torch.float32, device=dev)
-            ident[:, :, 0] = 1.0
-            ident[:, :, 2] = 1.0
-            f = Feat(cat, 0, top.Cout + skip.C, 2 * skip.Cp, xform=torch.cat((ident, skip.xform), dim=1))
+            if mat:
+                f = Feat(cat, 0, top.Cout + skip.C, 2 * skip.Cp)
+            else:
+                ident = torch.zeros((cat.shape[0], skip.Cp, 4), dtype=torch.float32, device=dev)
+                ident[:, :, 0] = 1.0
+                ident[:, :, 2] = 1.0
+                f = Feat(cat, 0, top.Cout + skip.C, 2 * skip.Cp, xform=torch.cat((ident, skip.xform), dim=1))
             for (op, g, b) in ops['dec'][u]:
                 f = eng.conv_norm(tape, op, g, b, f)
             if only_full_res and u != nu - 1:

@@ -194,6 +194,8 @@ def test_train_step_gradients_match_reference_fixture(golden_small):
         g = p.grad.cpu().numpy()
         scale = max(np.abs(r).max(), 1e-6)
         err = np.abs(g - r).max() / scale
+        if np.abs(g - r).max() < 2e-6:
+            continue  # conv biases in front of an InstanceNorm: the true gradient is 0, both sides hold rounding noise
         worst = max(worst, err)
         assert err < 5e-3, "%s: rel-to-max error %.3e" % (n, err)
     print("worst gradient error relative to max |g|: %.2e" % worst)
