@@ -477,9 +477,331 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
   return check_launch("conv_taps_umma");
 }
 
-int wgrad_taps_umma(const mtb200_wgrad_params&, cudaStream_t) {
-  set_error("wgrad_taps(umma): not implemented yet");
-  return MTB200_ERR_UNSUPPORTED;
+// =====================================================================================================================
+// weight gradient on tcgen05:  dW[t][co][ci] += sum_v dY[v][co] * X[v + off_t][ci]
+//
+// GEMM with K = voxels (split over CTAs), both operands MN-major (channels are the contiguous axis):
+//   A  [K = 64 voxels][M = 128 rows = (tap, ci) "row blocks"]   each row block = the tap-shifted X brick, one TMA box
+//   B  [K = 64 voxels][N = BN couts]                            the dY brick
+//   D_j[128 x BN] fp32 in TMEM, one accumulator per M-tile j handled by this CTA (sum of BN over tiles <= 512 columns)
+// A row block is `cb` channels wide (cb = 64 / 32 / 16 = the 128B / 64B / 32B swizzle span); blocks of one M-tile sit at
+// a uniform distance (= LBO) in shared memory, 8-voxel groups at SBO = 8 * cb * 2 bytes.
+// Grid: x = split over voxel bricks, y = group of M-tiles (taps), z = N tile.  Epilogue: fp32 atomics into dW.
+// =====================================================================================================================
+constexpr int WG_KB = 64;        // voxels per pipeline stage
+constexpr int WG_MAX_ASTAGES = 8;
+
+struct UmmaWgradParams {
+  CUtensorMap x_maps[8];
+  CUtensorMap dy_map;
+  float* dw;
+  int B, tiles_d, tiles_h, tiles_w, bd, bh, bw;
+  long long nbricks;
+  int bricks_per_cta;
+  int Cin, Cout;            // padded channel counts
+  int cbx, cby, BN;         // block widths (channels) of the X / dY boxes, N tile
+  int tap_begin, tap_end;   // taps of this launch (one group)
+  int blocks_per_tap;       // Cin / cbx
+  int nblocks;              // (tap_end - tap_begin) * blocks_per_tap
+  int blocks_per_tile;      // 128 / cbx
+  int ntiles, tiles_per_cta;
+  int astages, tmem_cols;
+  int dy_off[3];
+  int tap_map[MTB200_MAX_TAPS];
+  int tap_coff[MTB200_MAX_TAPS][3];
+  int tap_widx[MTB200_MAX_TAPS];
+  int is_f16;
+};
+
+// MN-major descriptor: blocks of `cb` channels (swizzle span cb*2 bytes), LBO = distance between blocks along M/N,
+// SBO = distance between 8-row (voxel) groups
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t cb_bytes, uint32_t lbo) {
+  const uint32_t sbo = 8u * cb_bytes;
+  const uint64_t layout = cb_bytes == 128 ? 2ull : (cb_bytes == 64 ? 4ull : 6ull);
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  d |= layout << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(UM_THREADS, 1) wgrad_taps_umma_kernel(const __grid_constant__ UmmaWgradParams p) {
+  extern __shared__ uint8_t dsmem_raw[];
+  __shared__ __align__(8) uint64_t a_full[WG_MAX_ASTAGES], a_empty[WG_MAX_ASTAGES];
+  __shared__ __align__(8) uint64_t b_full[2], b_empty[2];
+  __shared__ __align__(8) uint64_t acc_full;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_stage_bytes = WG_KB * 128 * 2;                         // 16 KB: [64 voxels][128 rows]
+  const uint32_t b_stage_bytes = ((WG_KB * p.BN * 2 + 1023) / 1024) * 1024;
+  uint8_t* a_base = dsmem;
+  uint8_t* b_base = dsmem + (size_t)p.astages * a_stage_bytes;
+  const uint32_t xblock_bytes = WG_KB * p.cbx * 2, yblock_bytes = WG_KB * p.cby * 2;
+
+  const long long brick0 = (long long)blockIdx.x * p.bricks_per_cta;
+  const long long brick1 = min(p.nbricks, brick0 + p.bricks_per_cta);
+  const int tile0 = blockIdx.y * p.tiles_per_cta;
+  const int tile1 = min(p.ntiles, tile0 + p.tiles_per_cta);
+  const int n0 = blockIdx.z * p.BN;
+  const int nbricks = (int)max(0LL, brick1 - brick0);
+  const int ntl = tile1 - tile0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.astages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(&acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0 && nbricks > 0 && ntl > 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (long long br = brick0; br < brick1; ++br) {
+        long long t = br;
+        const int tw = (int)(t % p.tiles_w); t /= p.tiles_w;
+        const int th = (int)(t % p.tiles_h); t /= p.tiles_h;
+        const int td = (int)(t % p.tiles_d);
+        const int b = (int)(t / p.tiles_d);
+        const int d0 = td * p.bd, h0 = th * p.bh, w0 = tw * p.bw;
+        // dY brick (shared by every M-tile of this brick)
+        mbar_wait(&b_empty[bs], bph ^ 1u);
+        mbar_expect_tx(&b_full[bs], WG_KB * p.BN * 2);
+        for (int j = 0; j < p.BN / p.cby; ++j)
+          tma_load_5d(b_base + (size_t)bs * b_stage_bytes + (size_t)j * yblock_bytes, &p.dy_map, &b_full[bs],
+                      n0 + j * p.cby, w0 + p.dy_off[2], h0 + p.dy_off[1], d0 + p.dy_off[0], b);
+        if (++bs == 2) { bs = 0; bph ^= 1u; }
+        // X row blocks, one stage per M-tile
+        for (int tl = tile0; tl < tile1; ++tl) {
+          mbar_wait(&a_empty[as], aph ^ 1u);
+          mbar_expect_tx(&a_full[as], a_stage_bytes);
+          for (int i = 0; i < p.blocks_per_tile; ++i) {
+            int gb = tl * p.blocks_per_tile + i;
+            if (gb >= p.nblocks) gb = 0;  // padding rows of the last tile: duplicate block 0 (never written back)
+            const int tp = p.tap_begin + gb / p.blocks_per_tap;
+            const int c0 = (gb % p.blocks_per_tap) * p.cbx;
+            tma_load_5d(a_base + (size_t)as * a_stage_bytes + (size_t)i * xblock_bytes, &p.x_maps[p.tap_map[tp]],
+                        &a_full[as], c0, w0 + p.tap_coff[tp][2], h0 + p.tap_coff[tp][1], d0 + p.tap_coff[tp][0], b);
+          }
+          if (++as == p.astages) { as = 0; aph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0 && nbricks > 0 && ntl > 0) {
+      const uint32_t fmt = p.is_f16 ? 0u : 1u;
+      // D=f32, A/B 16-bit, both MN-major (bits 15, 16), N = BN, M = 128
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t cbx_bytes = p.cbx * 2, cby_bytes = p.cby * 2;
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int br = 0; br < nbricks; ++br) {
+        mbar_wait(&b_full[bs], bph);
+        const uint32_t sb = smem_u32(b_base + (size_t)bs * b_stage_bytes);
+        for (int tl = 0; tl < ntl; ++tl) {
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(a_base + (size_t)as * a_stage_bytes);
+#pragma unroll
+          for (int k = 0; k < WG_KB / 16; ++k) {
+            // 16 voxels = two 8-row groups further along K
+            const uint64_t da = make_mnmajor_desc(sa + k * 2 * 8 * cbx_bytes, cbx_bytes, xblock_bytes);
+            const uint64_t db = make_mnmajor_desc(sb + k * 2 * 8 * cby_bytes, cby_bytes, yblock_bytes);
+            umma_f16(tmem_base + (uint32_t)(tl * p.BN), da, db, idesc, (br > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&a_empty[as]);
+          if (++as == p.astages) { as = 0; aph ^= 1u; }
+        }
+        umma_commit(&b_empty[bs]);
+        if (++bs == 2) { bs = 0; bph ^= 1u; }
+      }
+      umma_commit(&acc_full);
+    }
+  } else if (nbricks > 0 && ntl > 0) {
+    // ===== epilogue: TMEM -> fp32 atomics into dW[widx][co][ci] =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    for (int tl = 0; tl < ntl; ++tl) {
+      const int gb = (tile0 + tl) * p.blocks_per_tile + row / p.cbx;
+      const bool valid = gb < p.nblocks;
+      const int tp = p.tap_begin + (valid ? gb / p.blocks_per_tap : 0);
+      const int ci = (valid ? (gb % p.blocks_per_tap) * p.cbx : 0) + row % p.cbx;
+      float* dst = p.dw + ((long long)p.tap_widx[tp] * p.Cout + n0) * p.Cin + ci;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * p.BN + c0), r);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float v = __uint_as_float(r[j]);
+            if (v != 0.f) atomicAdd(dst + (long long)(c0 + j) * p.Cin, v);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+static int block_width(int C) { return (C % 64 == 0) ? 64 : ((C % 32 == 0) ? 32 : 16); }
+
+int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
+  if (!umma_available()) { set_error("wgrad_taps(umma): no sm_100 device"); return MTB200_ERR_UNSUPPORTED; }
+  if (p.dtype != MTB200_BF16 && p.dtype != MTB200_F16) { set_error("wgrad_taps(umma): 16-bit only"); return MTB200_ERR_UNSUPPORTED; }
+  if (p.xform) { set_error("wgrad_taps(umma): on-load transform not supported"); return MTB200_ERR_UNSUPPORTED; }
+  if (p.Cin % 16 || p.Cout % 16 || p.in_ldc % 8 || p.in_coff % 8 || p.out_ldc % 8 || p.out_coff % 8) {
+    set_error("wgrad_taps(umma): channel alignment"); return MTB200_ERR_UNSUPPORTED;
+  }
+  for (int k = 0; k < 3; ++k)
+    if (p.is[k] < 1 || p.is[k] > 2 || p.os[k] < 1 || p.os[k] > 2) { set_error("wgrad_taps(umma): stride"); return MTB200_ERR_UNSUPPORTED; }
+  const long long M = (long long)p.B * p.Do * p.Ho * p.Wo;
+  if (M == 0) return MTB200_OK;
+  EncodeTiledFn enc = get_encode_fn();
+  const CUtensorMapDataType dt = p.dtype == MTB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+
+  static UmmaWgradParams q;
+  memset(&q, 0, sizeof(q));
+  q.dw = p.dw;
+  q.B = p.B; q.Cin = p.Cin; q.Cout = p.Cout;
+  q.cbx = block_width(p.Cin);
+  q.BN = p.Cout;
+  if (q.BN > 256) {
+    q.BN = 0;
+    for (int c = 256; c >= 16; c -= 16)
+      if (p.Cout % c == 0) { q.BN = c; break; }
+  }
+  q.cby = block_width(q.BN);
+  q.blocks_per_tap = p.Cin / q.cbx;
+  q.blocks_per_tile = 128 / q.cbx;
+  q.is_f16 = p.dtype == MTB200_F16;
+  // voxel brick: 64 voxels, powers of two, minimise the number of bricks (ties: widest in w)
+  long long best = -1;
+  for (int bw = 64; bw >= 1; bw >>= 1)
+    for (int bh = 64 / bw; bh >= 1; bh >>= 1) {
+      const int bd = 64 / (bw * bh);
+      const long long nt = (long long)((p.Do + bd - 1) / bd) * ((p.Ho + bh - 1) / bh) * ((p.Wo + bw - 1) / bw);
+      if (best < 0 || nt < best) { best = nt; q.bd = bd; q.bh = bh; q.bw = bw; }
+    }
+  q.tiles_d = (p.Do + q.bd - 1) / q.bd; q.tiles_h = (p.Ho + q.bh - 1) / q.bh; q.tiles_w = (p.Wo + q.bw - 1) / q.bw;
+  q.nbricks = (long long)p.B * q.tiles_d * q.tiles_h * q.tiles_w;
+
+  // X parity maps (as in the forward kernel)
+  int parity_slot[8];
+  for (int i = 0; i < 8; ++i) parity_slot[i] = -1;
+  int nmaps = 0;
+  const int Dims[3] = {p.Di, p.Hi, p.Wi};
+  const long long e = 2;
+  for (int t = 0; t < p.ntaps; ++t) {
+    int par[3], coord[3];
+    for (int k = 0; k < 3; ++k) {
+      const int off = p.tap_off[t][k];
+      par[k] = ((off % p.is[k]) + p.is[k]) % p.is[k];
+      coord[k] = floor_div(off - par[k], p.is[k]);
+    }
+    const int code = par[0] * 4 + par[1] * 2 + par[2];
+    if (parity_slot[code] < 0) {
+      cuuint64_t dims[5], strides[4];
+      cuuint32_t box[5] = {(cuuint32_t)q.cbx, (cuuint32_t)q.bw, (cuuint32_t)q.bh, (cuuint32_t)q.bd, 1};
+      long long ext[3];
+      for (int k = 0; k < 3; ++k) {
+        ext[k] = (Dims[k] - par[k] + p.is[k] - 1) / p.is[k];
+        if (ext[k] < 1) { set_error("wgrad_taps(umma): empty parity lattice"); return MTB200_ERR_UNSUPPORTED; }
+      }
+      dims[0] = p.Cin; dims[1] = ext[2]; dims[2] = ext[1]; dims[3] = ext[0]; dims[4] = p.B;
+      strides[0] = (cuuint64_t)p.in_ldc * e * p.is[2];
+      strides[1] = (cuuint64_t)p.Wi * p.in_ldc * e * p.is[1];
+      strides[2] = (cuuint64_t)p.Hi * p.Wi * p.in_ldc * e * p.is[0];
+      strides[3] = (cuuint64_t)p.Di * p.Hi * p.Wi * p.in_ldc * e;
+      uint8_t* base = (uint8_t*)p.x + ((((long long)par[0] * p.Hi + par[1]) * p.Wi + par[2]) * p.in_ldc + p.in_coff) * e;
+      if (!encode_map(enc, &q.x_maps[nmaps], dt, 5, base, dims, strides, box, q.cbx * 2)) return MTB200_ERR_CUDA;
+      parity_slot[code] = nmaps++;
+    }
+    q.tap_map[t] = parity_slot[code];
+    for (int k = 0; k < 3; ++k) q.tap_coff[t][k] = coord[k];
+    q.tap_widx[t] = p.tap_widx[t];
+  }
+
+  // pipeline / TMEM sizing
+  const int max_tiles_tmem = 512 / q.BN;
+  if (max_tiles_tmem < 1) { set_error("wgrad_taps(umma): BN too large"); return MTB200_ERR_UNSUPPORTED; }
+  const int b_stage_bytes = ((WG_KB * q.BN * 2 + 1023) / 1024) * 1024;
+  const int a_stage_bytes = WG_KB * 128 * 2;
+  q.astages = max(2, min(WG_MAX_ASTAGES, (190 * 1024 - 2 * b_stage_bytes) / a_stage_bytes));
+  const int smem = q.astages * a_stage_bytes + 2 * b_stage_bytes + 1024;
+  cudaError_t ce = cudaFuncSetAttribute(wgrad_taps_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (ce != cudaSuccess) { set_error("wgrad_taps(umma): cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return MTB200_ERR_CUDA; }
+
+  // one launch per group (the dY brick depends on the group's output offset)
+  for (int g = 0; g < p.ngroups; ++g) {
+    q.tap_begin = p.group_tap_begin[g];
+    q.tap_end = p.group_tap_begin[g + 1];
+    if (q.tap_end == q.tap_begin) continue;
+    q.nblocks = (q.tap_end - q.tap_begin) * q.blocks_per_tap;
+    q.ntiles = (q.nblocks + q.blocks_per_tile - 1) / q.blocks_per_tile;
+    // dY map for this group: out coordinate = o * os + ooff
+    {
+      int par[3], coord[3];
+      const int ODims[3] = {p.Dof, p.Hof, p.Wof};
+      cuuint64_t dims[5], strides[4];
+      long long ext[3];
+      for (int k = 0; k < 3; ++k) {
+        const int off = p.group_ooff[g][k];
+        par[k] = ((off % p.os[k]) + p.os[k]) % p.os[k];
+        coord[k] = floor_div(off - par[k], p.os[k]);
+        ext[k] = (ODims[k] - par[k] + p.os[k] - 1) / p.os[k];
+        if (ext[k] < 1) { set_error("wgrad_taps(umma): empty dY lattice"); return MTB200_ERR_UNSUPPORTED; }
+        q.dy_off[k] = coord[k];
+      }
+      cuuint32_t box[5] = {(cuuint32_t)q.cby, (cuuint32_t)q.bw, (cuuint32_t)q.bh, (cuuint32_t)q.bd, 1};
+      dims[0] = p.Cout; dims[1] = ext[2]; dims[2] = ext[1]; dims[3] = ext[0]; dims[4] = p.B;
+      strides[0] = (cuuint64_t)p.out_ldc * e * p.os[2];
+      strides[1] = (cuuint64_t)p.Wof * p.out_ldc * e * p.os[1];
+      strides[2] = (cuuint64_t)p.Hof * p.Wof * p.out_ldc * e * p.os[0];
+      strides[3] = (cuuint64_t)p.Dof * p.Hof * p.Wof * p.out_ldc * e;
+      uint8_t* base = (uint8_t*)p.dy + ((((long long)par[0] * p.Hof + par[1]) * p.Wof + par[2]) * p.out_ldc + p.out_coff) * e;
+      if (!encode_map(enc, &q.dy_map, dt, 5, base, dims, strides, box, q.cby * 2)) return MTB200_ERR_CUDA;
+    }
+    q.tiles_per_cta = min(q.ntiles, max_tiles_tmem);
+    const int tile_groups = (q.ntiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
+    q.tmem_cols = 32;
+    while (q.tmem_cols < q.tiles_per_cta * q.BN) q.tmem_cols *= 2;
+    const int nz = p.Cout / q.BN;
+    // split over voxel bricks so that the grid covers the machine about twice, with >= 4 bricks per CTA
+    long long want = max(1LL, (2LL * num_sms()) / ((long long)tile_groups * nz));
+    long long ksplit = min(want, max(1LL, q.nbricks / 4));
+    q.bricks_per_cta = (int)((q.nbricks + ksplit - 1) / ksplit);
+    ksplit = (q.nbricks + q.bricks_per_cta - 1) / q.bricks_per_cta;
+    dim3 grid((unsigned)ksplit, tile_groups, nz);
+    wgrad_taps_umma_kernel<<<grid, UM_THREADS, smem, s>>>(q);
+    int r = check_launch("wgrad_taps_umma");
+    if (r) return r;
+  }
+  return MTB200_OK;
 }
 
 }  // namespace mtb

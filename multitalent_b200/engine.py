@@ -399,7 +399,9 @@ class Engine:
                L.stream_ptr())
         tape.add_param_grad(gamma_param, dgamma[:op.Cout])
         tape.add_param_grad(beta_param, dbeta[:op.Cout])
-        self._conv_bwd(tape, op, x, g, need_input_grad)
+        # A bias in front of an InstanceNorm has an identically-zero gradient: sum_v dy = k1 (S1 - N m1 - m2 sum xhat)
+        # = 0.  (The reference's autograd produces rounding noise ~1e-9 there.)  Emit exact zeros, skip the reduction.
+        self._conv_bwd(tape, op, x, g, need_input_grad, bias_grad_is_zero=True)
 
     def _zero_param_grads(self, tape, op, *others):
         tape.add_param_grad(op.weight, torch.zeros_like(op.weight))
@@ -407,7 +409,7 @@ class Engine:
             if p is not None:
                 tape.add_param_grad(p, torch.zeros_like(p))
 
-    def _conv_bwd(self, tape, op: ConvOp, x: Feat, dy: Feat, need_input_grad):
+    def _conv_bwd(self, tape, op: ConvOp, x: Feat, dy: Feat, need_input_grad, bias_grad_is_zero=False):
         """Weight / bias gradient and data gradient of a (transposed) convolution given d(raw output)."""
         dev = dy.buf.device
         dt = L.dtype_enum(self.dtype)
@@ -431,7 +433,9 @@ class Engine:
         L.call("mtb200_unpack_wgrad", L.ptr(dw), op.Cout, op.Cin, op.ntap, int(op.transposed), op.Cout_p, op.Cin_p,
                op.split, op.split_p, 1.0, 0, L.ptr(gw), L.stream_ptr())
         tape.add_param_grad(op.weight, gw)
-        if op.bias is not None:
+        if op.bias is not None and bias_grad_is_zero:
+            tape.add_param_grad(op.bias, torch.zeros_like(op.bias))
+        elif op.bias is not None:
             gb = torch.zeros(op.Cout_p, dtype=torch.float32, device=dev)
             L.call("mtb200_colsum", dy.ptr(), dt, dy.dims[0] * dy.nvox, dy.ldc, dy.coff, op.Cout_p, L.ptr(gb),
                    L.stream_ptr())

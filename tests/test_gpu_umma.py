@@ -75,6 +75,10 @@ def test_conv_umma_matches_ffma(dtype, cin, cout, kernel, stride, dims):
         gws.append(tape.param_grads[id(conv.weight)].clone())
     _close(outs[1], outs[0], dtype)
     _close(gxs[1], gxs[0], dtype)
+    # weight gradient: same 16-bit operands, fp32 accumulation on both paths -> only the summation order differs
+    gw0, gw1 = gws[0].cpu().numpy(), gws[1].cpu().numpy()
+    assert np.abs(gw1 - gw0).max() <= 2e-3 * np.abs(gw0).max() + 1e-6, \
+        "wgrad differs: %.3e (max |g| %.3e)" % (np.abs(gw1 - gw0).max(), np.abs(gw0).max())
     np.testing.assert_allclose(stats[1].cpu().numpy(), stats[0].cpu().numpy(),
                                atol=2e-2 * float(stats[0].abs().max()) + 1e-3)
     # and against the fp32 torch op on the bf16-rounded operands (absolute sanity, loose)
@@ -109,9 +113,10 @@ def test_conv_transpose_umma_matches_ffma(kernel):
         eng.seed_grad(tape, y, gy)
         eng.run_backward(tape)
         gx, _ = tape.grad_feat(xf)
-        res.append((cat.clone(), gx.buf.clone()))
+        res.append((cat.clone(), gx.buf.clone(), tape.param_grads[id(tu.weight)].cpu().numpy()))
     _close(res[1][0], res[0][0], dtype)
     _close(res[1][1], res[0][1], dtype)
+    assert np.abs(res[1][2] - res[0][2]).max() <= 2e-3 * np.abs(res[0][2]).max() + 1e-6
     assert float(res[1][0][..., op.Cout_p:].abs().max()) == 0.0  # the other half of the buffer is untouched
 
 
