@@ -96,9 +96,9 @@ int mtb200_conv_taps(const mtb200_conv_params* p, void* stream) {
   MTB_REQUIRE(p->in_coff + p->Cin <= p->in_ldc && p->out_coff + p->Cout <= p->out_ldc,
               "conv_taps: channel slice exceeds ldc (in %d+%d/%d, out %d+%d/%d)", p->in_coff, p->Cin, p->in_ldc,
               p->out_coff, p->Cout, p->out_ldc);
-  if (p->impl == 2 || (p->impl == 0 && umma_available() && p->dtype != MTB200_F32)) {
+  if (p->impl >= 2 || (p->impl == 0 && umma_available() && p->dtype != MTB200_F32)) {
     int r = conv_taps_umma(*p, STREAM(stream));
-    if (r != MTB200_ERR_UNSUPPORTED || p->impl == 2) return r;
+    if (r != MTB200_ERR_UNSUPPORTED || p->impl >= 2) return r;
   }
   return conv_taps_ffma(*p, STREAM(stream));
 }
@@ -106,7 +106,7 @@ int mtb200_conv_taps(const mtb200_conv_params* p, void* stream) {
 int mtb200_wgrad_taps(const mtb200_wgrad_params* p, void* stream) {
   MTB_REQUIRE(p && p->x && p->dy && p->dw, "wgrad_taps: null pointer");
   if (int r = validate_taps(p->ngroups, p->group_tap_begin, p->ntaps)) return r;
-  if (p->impl == 2 || (p->impl == 0 && umma_available() && p->dtype != MTB200_F32)) {
+  if (p->impl >= 2 || (p->impl == 0 && umma_available() && p->dtype != MTB200_F32)) {
     int r = wgrad_taps_umma(*p, STREAM(stream));
     if (r != MTB200_ERR_UNSUPPORTED) return r;  // shapes the tensor-core kernel does not cover use the CUDA-core one
   }

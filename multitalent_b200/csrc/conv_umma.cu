@@ -40,6 +40,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+int conv_halo_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_halo.cu
+
 int umma_available() {
   static int cached = -1;
   if (cached < 0) {
@@ -377,6 +379,11 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
     if (p.is[k] < 1 || p.is[k] > 2) { set_error("conv_taps(umma): input stride %d", p.is[k]); return MTB200_ERR_UNSUPPORTED; }
   const long long M = (long long)p.B * p.Do * p.Ho * p.Wo;
   if (M == 0) return MTB200_OK;
+  if (p.impl != 3) {  // plane-streaming kernel first (impl 3 = per-tap kernel only, impl 4 = plane-streaming only)
+    const int r = conv_halo_umma(p, s);
+    if (r != MTB200_ERR_UNSUPPORTED) return r;
+    if (p.impl == 4) { set_error("conv_taps(umma): problem outside the plane-streaming kernel's envelope"); return r; }
+  }
   EncodeTiledFn enc = get_encode_fn();
 
   static UmmaConvParams q;  // large: keep off the stack (host calls are serialised by the GIL / one thread per process)
@@ -802,6 +809,16 @@ int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
     if (r) return r;
   }
   return MTB200_OK;
+}
+
+EncodeTiledFn umma_encode_fn() { return get_encode_fn(); }
+
+bool umma_encode_map(CUtensorMap* m, int dtype, int rank, void* base, const cuuint64_t* dims,
+                     const cuuint64_t* strides_bytes, const cuuint32_t* box, int swizzle_bytes) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
+  return encode_map(enc, m, dtype == MTB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                    rank, base, dims, strides_bytes, box, swizzle_bytes);
 }
 
 }  // namespace mtb

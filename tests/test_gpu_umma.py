@@ -12,7 +12,7 @@ DEV = "cuda"
 
 def _engines(dtype):
     from multitalent_b200.engine import Engine
-    return Engine(dtype, 1), Engine(dtype, 2)
+    return Engine(dtype, 1), Engine(dtype, 3)  # 3 = per-tap tcgen05 kernel (the plane-streaming one has its own tests)
 
 
 def _require_tcgen05():
@@ -86,6 +86,74 @@ def test_conv_umma_matches_ffma(dtype, cin, cout, kernel, stride, dims):
                                      [(k - 1) // 2 for k in kernel])
     got = outs[1][..., :cout].permute(0, 4, 1, 2, 3).float()
     assert float((got - ref).abs().max()) <= 2e-2 * float(ref.abs().max()) + 1e-3
+
+
+HALO_CASES = [
+    # cin, cout, kernel, dims(B,D,H,W) -- stride 1, taps in [-1,1]^3, Cin_p <= 64: the plane-streaming kernel's envelope
+    (30, 30, (3, 3, 3), (2, 8, 16, 32)),
+    (30, 30, (3, 3, 3), (1, 5, 19, 27)),     # ragged in h and w, short in d
+    (30, 30, (3, 3, 3), (1, 40, 16, 16)),    # long in d: ring wrap-around, several d segments
+    (60, 30, (3, 3, 3), (1, 9, 32, 24)),     # Cin_p 64 (128-byte rows)
+    (30, 60, (3, 3, 3), (2, 6, 16, 40)),     # N = 64
+    (60, 120, (3, 3, 3), (1, 6, 16, 16)),    # N = 128
+    (1, 30, (3, 3, 3), (1, 7, 16, 32)),      # Cin_p 16 (32-byte rows)
+    (20, 24, (1, 3, 3), (1, 4, 12, 16)),     # 9 taps, no d extent
+    (60, 240, (3, 3, 3), (1, 4, 16, 8)),     # Cout 256 -> two N tiles
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("cin,cout,kernel,dims", HALO_CASES)
+def test_conv_plane_streaming_matches_ffma(dtype, cin, cout, kernel, dims):
+    """impl=4 forces the plane-streaming kernel (error if the shape is outside its envelope) for forward AND the
+    stride-1 data gradient (flipped taps)."""
+    _require_tcgen05()
+    from multitalent_b200.engine import ConvOp, Engine, Tape
+    torch.manual_seed(0)
+    B, D, H, W = dims
+    x = torch.randn(B, cin, D, H, W, device=DEV)
+    conv = nn.Conv3d(cin, cout, kernel, 1, [(k - 1) // 2 for k in kernel], bias=True).to(DEV)
+    op = ConvOp(conv.weight, conv.bias, kernel, (1, 1, 1))
+    gy = torch.randn(B, cout, D, H, W, device=DEV)
+    res = []
+    for impl in (1, 4):
+        eng = Engine(dtype, impl)
+        tape = Tape()
+        xf = eng.input_feat(x)
+        y, st = eng.conv(op, xf, want_stats=True)
+        dgrad_ok = op.Cout_p <= 64  # the data gradient is a conv with Cin := Cout_p
+        gx = None
+        if dgrad_ok:
+            y2 = eng.conv_plain(tape, op, xf)
+            eng.seed_grad(tape, y2, gy)
+            eng.run_backward(tape)
+            gx = tape.grad_feat(xf)[0].buf.clone()
+        res.append((y.buf.clone(), st.clone(), gx))
+    _close(res[1][0], res[0][0], dtype)
+    np.testing.assert_allclose(res[1][1].cpu().numpy(), res[0][1].cpu().numpy(),
+                               atol=2e-2 * float(res[0][1].abs().max()) + 1e-3)
+    if res[0][2] is not None:
+        _close(res[1][2], res[0][2], dtype)
+
+
+def test_plane_streaming_accumulate_flag():
+    _require_tcgen05()
+    from multitalent_b200.engine import ConvOp, Engine, Feat
+    torch.manual_seed(2)
+    dtype = torch.bfloat16
+    x = torch.randn(1, 32, 6, 16, 16, device=DEV)
+    conv = nn.Conv3d(32, 32, 3, 1, 1, bias=False).to(DEV)
+    op = ConvOp(conv.weight, None, (3, 3, 3), (1, 1, 1))
+    base = torch.randn(1, 6, 16, 16, 64, device=DEV).to(dtype)   # write into the second half of a wider buffer
+    res = []
+    for impl in (1, 4):
+        eng = Engine(dtype, impl)
+        xf = eng.input_feat(x)
+        out = Feat(base.clone(), 32, 32, 32)
+        eng._conv_call(op.fwd_taps, xf, op.packed(eng.wdtype, False), None, out, (6, 16, 16), None, True, 32, 32)
+        res.append(out.buf)
+    _close(res[1], res[0], dtype)
+    assert torch.equal(res[1][..., :32], base[..., :32])  # the other half is untouched
 
 
 @pytest.mark.parametrize("kernel", [(2, 2, 2), (1, 2, 2)])
