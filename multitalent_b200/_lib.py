@@ -140,10 +140,15 @@ class KernelProfile:
         global _profile
         _profile = None
 
+    def per_launch(self):
+        """[(tag, info, ms, flops, bytes)] in launch order (tools/layer_profile.py)."""
+        torch.cuda.synchronize()
+        return [(name, info, e0.elapsed_time(e1), flops, nbytes) for name, e0, e1, flops, nbytes, info in self.records]
+
     def summary(self):
         torch.cuda.synchronize()
         out = {}
-        for name, e0, e1, flops, nbytes in self.records:
+        for name, e0, e1, flops, nbytes, _info in self.records:
             d = out.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
             d["launches"] += 1
             d["ms"] += e0.elapsed_time(e1)
@@ -155,7 +160,7 @@ class KernelProfile:
 _profile = None
 
 
-def call(name, *args, flops=0.0, nbytes=0.0, tag=None):
+def call(name, *args, flops=0.0, nbytes=0.0, tag=None, info=None):
     """Invoke an entry point, raise Mtb200Error with the library's message on a negative status.
     `flops` / `nbytes` = ALGORITHMIC work of this launch (only used when a KernelProfile is active)."""
     global launch_count
@@ -169,7 +174,7 @@ def call(name, *args, flops=0.0, nbytes=0.0, tag=None):
         raise Mtb200Error("%s failed (%d): %s" % (name, r, msg.decode() if msg else "?"))
     if _profile is not None:
         e1.record()
-        _profile.records.append((tag or name, e0, e1, flops, nbytes))
+        _profile.records.append((tag or name, e0, e1, flops, nbytes, info))
     launch_count += 1
     return r
 

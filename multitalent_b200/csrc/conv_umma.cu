@@ -15,16 +15,13 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace mtb {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // driver entry point for tensor-map encoding (no link-time dependency on libcuda)
 // ---------------------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 static EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
@@ -57,72 +54,11 @@ int umma_available() {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// PTX wrappers
+// PTX wrappers: umma.cuh
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
-      "[%2];" ::"r"(smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
-          "r"(smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
+using namespace um;
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 // shared-memory matrix descriptor, K-major, swizzle span == row pitch (KC * 2 bytes), atoms of 8 rows
@@ -208,47 +144,55 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_taps_umma_kernel(const __g
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      tma_prefetch_desc(&p.w_map);
+    // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < niter; ++it) {
         const int tp = tap_begin + it / p.nkc;
         const int kc = it % p.nkc;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        uint8_t* sa = dsmem + (size_t)stage * stage_bytes;
-        uint8_t* sb = sa + a_bytes;
-        mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-        tma_load_5d(sa, &p.a_maps[p.tap_map[tp]], &full_bar[stage], kc * p.KC, w0 + p.tap_coff[tp][2],
-                    h0 + p.tap_coff[tp][1], d0 + p.tap_coff[tp][0], b);
-        tma_load_3d(sb, &p.w_map, &full_bar[stage], kc * p.KC, n0, p.tap_widx[tp]);
+        if (elect_one()) {
+          uint8_t* sa = dsmem + (size_t)stage * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+          tma_load_5d(sa, &p.a_maps[p.tap_map[tp]], &full_bar[stage], kc * p.KC, w0 + p.tap_coff[tp][2],
+                      h0 + p.tap_coff[tp][1], d0 + p.tap_coff[tp][0], b);
+          tma_load_3d(sb, &p.w_map, &full_bar[stage], kc * p.KC, n0, p.tap_widx[tp]);
+        }
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues (keeps the descriptors in uniform registers) =====
+    {
       // instruction descriptor: D=f32, A/B = bf16 or f16, both K-major, N, M=128
       const uint32_t fmt = p.is_f16 ? 0u : 1u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t s0 = __shfl_sync(0xffffffffu, smem_u32(dsmem), 0);
+      const int ksteps = p.KC / 16;
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < niter; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(dsmem + (size_t)stage * stage_bytes);
+        const uint32_t sa = s0 + (uint32_t)stage * stage_bytes;
         const uint32_t sb = sa + a_bytes;
-        const int ksteps = p.KC / 16;
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t da = make_kmajor_desc(sa + k * 32, row_bytes);
-          const uint64_t db = make_kmajor_desc(sb + k * 32, row_bytes);
-          umma_f16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        if (elect_one()) {
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t da = make_kmajor_desc(sa + k * 32, row_bytes);
+            const uint64_t db = make_kmajor_desc(sb + k * 32, row_bytes);
+            umma_f16(tmem_u, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once the MMAs above have read it
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot once the MMAs above have read it
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(&tmem_full_bar);  // accumulator complete
+      if (elect_one()) umma_commit(&tmem_full_bar);  // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===== epilogue: warps 2..5; warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
@@ -379,7 +323,9 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
     if (p.is[k] < 1 || p.is[k] > 2) { set_error("conv_taps(umma): input stride %d", p.is[k]); return MTB200_ERR_UNSUPPORTED; }
   const long long M = (long long)p.B * p.Do * p.Ho * p.Wo;
   if (M == 0) return MTB200_OK;
-  if (p.impl != 3) {  // plane-streaming kernel first (impl 3 = per-tap kernel only, impl 4 = plane-streaming only)
+  // impl 3 = per-tap kernel only, impl 4 = plane-streaming only; auto: plane-streaming where it measured faster on the
+  // B200 (tools/conv_bench.py, profiles/r1d_conv_bench.txt): narrow layers whose 27 weight tiles stay resident.
+  if (p.impl == 4 || (p.impl != 3 && p.Cin <= 32 && p.Cout <= 32)) {
     const int r = conv_halo_umma(p, s);
     if (r != MTB200_ERR_UNSUPPORTED) return r;
     if (p.impl == 4) { set_error("conv_taps(umma): problem outside the plane-streaming kernel's envelope"); return r; }
@@ -575,8 +521,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) wgrad_taps_umma_kernel(const __
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0 && nbricks > 0 && ntl > 0) {
+    // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
+    if (nbricks > 0 && ntl > 0) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (long long br = brick0; br < brick1; ++br) {
@@ -588,58 +534,72 @@ __global__ void __launch_bounds__(UM_THREADS, 1) wgrad_taps_umma_kernel(const __
         const int d0 = td * p.bd, h0 = th * p.bh, w0 = tw * p.bw;
         // dY brick (shared by every M-tile of this brick)
         mbar_wait(&b_empty[bs], bph ^ 1u);
-        mbar_expect_tx(&b_full[bs], WG_KB * p.BN * 2);
-        for (int j = 0; j < p.BN / p.cby; ++j)
-          tma_load_5d(b_base + (size_t)bs * b_stage_bytes + (size_t)j * yblock_bytes, &p.dy_map, &b_full[bs],
-                      n0 + j * p.cby, w0 + p.dy_off[2], h0 + p.dy_off[1], d0 + p.dy_off[0], b);
+        if (elect_one()) {
+          mbar_expect_tx(&b_full[bs], WG_KB * p.BN * 2);
+          for (int j = 0; j < p.BN / p.cby; ++j)
+            tma_load_5d(b_base + (size_t)bs * b_stage_bytes + (size_t)j * yblock_bytes, &p.dy_map, &b_full[bs],
+                        n0 + j * p.cby, w0 + p.dy_off[2], h0 + p.dy_off[1], d0 + p.dy_off[0], b);
+        }
+        __syncwarp();
         if (++bs == 2) { bs = 0; bph ^= 1u; }
         // X row blocks, one stage per M-tile
         for (int tl = tile0; tl < tile1; ++tl) {
           mbar_wait(&a_empty[as], aph ^ 1u);
-          mbar_expect_tx(&a_full[as], a_stage_bytes);
-          for (int i = 0; i < p.blocks_per_tile; ++i) {
-            int gb = tl * p.blocks_per_tile + i;
-            if (gb >= p.nblocks) gb = 0;  // padding rows of the last tile: duplicate block 0 (never written back)
-            const int tp = p.tap_begin + gb / p.blocks_per_tap;
-            const int c0 = (gb % p.blocks_per_tap) * p.cbx;
-            tma_load_5d(a_base + (size_t)as * a_stage_bytes + (size_t)i * xblock_bytes, &p.x_maps[p.tap_map[tp]],
-                        &a_full[as], c0, w0 + p.tap_coff[tp][2], h0 + p.tap_coff[tp][1], d0 + p.tap_coff[tp][0], b);
+          if (elect_one()) {
+            mbar_expect_tx(&a_full[as], a_stage_bytes);
+            for (int i = 0; i < p.blocks_per_tile; ++i) {
+              int gb = tl * p.blocks_per_tile + i;
+              if (gb >= p.nblocks) gb = 0;  // padding rows of the last tile: duplicate block 0 (never written back)
+              const int tp = p.tap_begin + gb / p.blocks_per_tap;
+              const int c0 = (gb % p.blocks_per_tap) * p.cbx;
+              tma_load_5d(a_base + (size_t)as * a_stage_bytes + (size_t)i * xblock_bytes, &p.x_maps[p.tap_map[tp]],
+                          &a_full[as], c0, w0 + p.tap_coff[tp][2], h0 + p.tap_coff[tp][1], d0 + p.tap_coff[tp][0], b);
+            }
           }
+          __syncwarp();
           if (++as == p.astages) { as = 0; aph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0 && nbricks > 0 && ntl > 0) {
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
+    if (nbricks > 0 && ntl > 0) {
       const uint32_t fmt = p.is_f16 ? 0u : 1u;
       // D=f32, A/B 16-bit, both MN-major (bits 15, 16), N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t cbx_bytes = p.cbx * 2, cby_bytes = p.cby * 2;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t a0 = __shfl_sync(0xffffffffu, smem_u32(a_base), 0);
+      const uint32_t b0 = __shfl_sync(0xffffffffu, smem_u32(b_base), 0);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int br = 0; br < nbricks; ++br) {
         mbar_wait(&b_full[bs], bph);
-        const uint32_t sb = smem_u32(b_base + (size_t)bs * b_stage_bytes);
+        const uint32_t sb = b0 + (uint32_t)bs * b_stage_bytes;
         for (int tl = 0; tl < ntl; ++tl) {
           mbar_wait(&a_full[as], aph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(a_base + (size_t)as * a_stage_bytes);
+          const uint32_t sa = a0 + (uint32_t)as * a_stage_bytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < WG_KB / 16; ++k) {
-            // 16 voxels = two 8-row groups further along K
-            const uint64_t da = make_mnmajor_desc(sa + k * 2 * 8 * cbx_bytes, cbx_bytes, xblock_bytes);
-            const uint64_t db = make_mnmajor_desc(sb + k * 2 * 8 * cby_bytes, cby_bytes, yblock_bytes);
-            umma_f16(tmem_base + (uint32_t)(tl * p.BN), da, db, idesc, (br > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < WG_KB / 16; ++k) {
+              // 16 voxels = two 8-row groups further along K
+              const uint64_t da = make_mnmajor_desc(sa + k * 2 * 8 * cbx_bytes, cbx_bytes, xblock_bytes);
+              const uint64_t db = make_mnmajor_desc(sb + k * 2 * 8 * cby_bytes, cby_bytes, yblock_bytes);
+              umma_f16(tmem_u + (uint32_t)(tl * p.BN), da, db, idesc, (br > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&a_empty[as]);
           }
-          umma_commit(&a_empty[as]);
+          __syncwarp();
           if (++as == p.astages) { as = 0; aph ^= 1u; }
         }
-        umma_commit(&b_empty[bs]);
+        if (elect_one()) umma_commit(&b_empty[bs]);
+        __syncwarp();
         if (++bs == 2) { bs = 0; bph ^= 1u; }
       }
-      umma_commit(&acc_full);
+      if (elect_one()) umma_commit(&acc_full);
+      __syncwarp();
     }
   } else if (nbricks > 0 && ntl > 0) {
     // ===== epilogue: TMEM -> fp32 atomics into dW[widx][co][ci] =====

@@ -330,7 +330,8 @@ class Engine:
         table.fill(p)
         p.accumulate = int(accumulate)
         p.impl = self.impl
-        L.call("mtb200_conv_taps", C.byref(p), L.stream_ptr(), flops=flops, tag=tag)
+        L.call("mtb200_conv_taps", C.byref(p), L.stream_ptr(), flops=flops, tag=tag,
+               info=(Cin_p, Cout_p, tuple(grid_dims), len(table.taps), table.in_stride, table.out_stride))
 
     # ---- forward primitives -------------------------------------------------------------------------------------
     def conv(self, op: ConvOp, x: Feat, out: Optional[Feat] = None, want_stats=False):
@@ -428,7 +429,8 @@ class Engine:
         op.fwd_taps.fill(p)
         p.impl = self.impl
         fl = self.conv_flops(op, dy.dims)
-        L.call("mtb200_wgrad_taps", C.byref(p), L.stream_ptr(), flops=fl, tag="conv_wgrad")
+        L.call("mtb200_wgrad_taps", C.byref(p), L.stream_ptr(), flops=fl, tag="conv_wgrad",
+               info=(op.Cin_p, op.Cout_p, (p.Do, p.Ho, p.Wo), op.ntap, op.fwd_taps.in_stride, op.fwd_taps.out_stride))
         gw = torch.empty_like(op.weight)
         L.call("mtb200_unpack_wgrad", L.ptr(dw), op.Cout, op.Cin, op.ntap, int(op.transposed), op.Cout_p, op.Cin_p,
                op.split, op.split_p, 1.0, 0, L.ptr(gw), L.stream_ptr())
