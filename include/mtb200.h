@@ -68,8 +68,9 @@ typedef struct {
   int32_t tap_off[MTB200_MAX_TAPS][3];
   int32_t tap_widx[MTB200_MAX_TAPS];
   int32_t accumulate;   /* 1: out += result (gradient accumulation into a skip buffer) */
-  int32_t impl;         /* 0 = auto, 1 = CUDA-core FFMA kernel, 2 = tcgen05 kernels (plane-streaming if applicable,
-                           else per-tap), 3 = tcgen05 per-tap kernel only, 4 = tcgen05 plane-streaming kernel only */
+  int32_t impl;         /* 0 = auto, 1 = CUDA-core FFMA kernel, 2 = tcgen05 kernels (fastest applicable of the three),
+                           3 = tcgen05 per-tap kernel only, 4 = tcgen05 plane-streaming kernel only,
+                           5 = tcgen05 line-streaming kernel (dy taps merged into N) only */
 } mtb200_conv_params;
 
 /* Weight-gradient of the same tap-table problem:

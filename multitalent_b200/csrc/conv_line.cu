@@ -1,0 +1,388 @@
+// Line-streaming tcgen05 convolution with the dy taps merged into the MMA's N dimension -- for the NARROW full-resolution
+// layers of the U-Net (Cout_p tile = 32, Cin_p <= 64; generic_UNet.py:46 at 192x160x128), stride 1, taps in [-1,1]^3.
+//
+// Why: measured on the B200 (profiles/r1d_conv_bench.txt) one tcgen05.mma M=128 costs ~50 ns whatever N <= 128 is (the
+// 128 x 16 A tile has to be fetched from shared memory), so an implicit GEMM with N = Cout = 32 cannot exceed ~17 % of
+// the tensor peak.  Here the three dy taps of every (dz, dx) share ONE MMA with N = 3 x 32 = 96:
+//     Q[h'][w][(dy, co)] = sum_{dz, dx, ci} X[d+dz][h'][w+dx][ci] * W[dz, dy, dx][ci][co]        (h' = an INPUT line)
+//     out[d][h][w][co]   = Q[h-1][..][(dy=-1, co)] + Q[h][..][(dy=0, co)] + Q[h+1][..][(dy=+1, co)]
+// i.e. 3x fewer MMAs; the dy recombination is three TMEM column blocks of three different accumulators added in the
+// epilogue registers -- no data moves between threads because an M tile is ONE h-line (128 consecutive w voxels).
+//
+// A CTA owns (b, d, a range of h-lines, a 128-wide w tile, a 32-channel block of Cout).  Per step h' it needs the three
+// input lines (d-1, d, d+1) x h' (TMA boxes [130 w][chunk], halo columns and out-of-volume lines zero-filled = padding);
+// a dx tap is a one-row shift of the descriptor start.  All weight tiles stay resident in shared memory as 9 groups
+// (dz, dx) of [96 = (dy, co)][Cin] K-major.  Four Q accumulators (96 TMEM columns each) rotate: the MMAs of line h'+1
+// overlap the epilogue of output line h'-1.
+//
+// Warp roles (11 warps): 0 = line producer (TMA), 1 = TMEM owner + MMA issuer, 2 = weight loader, 3..10 = epilogue
+// (two warps per TMEM lane quarter, 16 of the 32 output channels each).
+#include "umma.cuh"
+
+namespace mtb {
+
+using namespace um;
+
+constexpr int LN_THREADS = 352;   // 3 service warps + 8 epilogue warps
+constexpr int LN_MAX_STAGES = 6;
+constexpr int LN_QSLOTS = 4;
+constexpr int LN_WROWS = 130;   // 128 output columns + halo
+constexpr int LN_BN = 32;       // Cout block per CTA; N = 3 * LN_BN
+
+struct LineParams {
+  CUtensorMap a_map, w_map;
+  void* out;
+  const float* bias;
+  double* stats;
+  int B, D, H, W;
+  int out_ldc, out_coff, Cout;
+  int kcw, nchunk;
+  int sub_bytes;                 // one chunk of one line, 1024-aligned
+  int line_bytes;                // nchunk * sub_bytes
+  int stage_bytes, stage_tx;     // ndz lines
+  int stages;
+  int wchunk_bytes, wgroup_bytes;  // [96][kcw] tile, one (dz,dx) group = nchunk tiles
+  int ngroups;
+  int ndz, dz0;                  // planes d+dz0 .. d+dz0+ndz-1 are staged
+  int grp_dzslot[9], grp_dxrow[9];    // which staged line, row offset (dx + 1)
+  int grp_widx[9][3];            // weight slice of (group, dy = j - 1)
+  int nhr, hlen, ntw;
+  int accumulate, is_f16;
+};
+
+__device__ __forceinline__ uint64_t ln_desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
+__device__ __forceinline__ uint32_t ln_kmajor_hi(uint32_t row_bytes, uint32_t sbo) {
+  const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+  return ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+}
+
+template <typename T, int ROWB>
+__global__ void __launch_bounds__(LN_THREADS, 1) conv_line_umma_kernel(const __grid_constant__ LineParams p) {
+  extern __shared__ uint8_t dsmem_raw[];
+  __shared__ __align__(8) uint64_t st_full[LN_MAX_STAGES], st_empty[LN_MAX_STAGES];
+  __shared__ __align__(8) uint64_t q_full[LN_QSLOTS], q_empty[LN_QSLOTS];
+  __shared__ __align__(8) uint64_t w_full;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_bias[LN_BN], s_sum[LN_BN], s_sq[LN_BN];
+
+  constexpr int KSTEPS = ROWB / 32;
+  constexpr uint32_t NCOLS = 3 * LN_BN;  // accumulator width
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* st_base = dsmem;
+  uint8_t* w_base = dsmem + (size_t)p.stages * p.stage_bytes;
+
+  // work unit: (b, d, h range, w tile)
+  int u = blockIdx.x;
+  const int hr = u % p.nhr; u /= p.nhr;
+  const int twi = u % p.ntw; u /= p.ntw;
+  const int d = u % p.D;
+  const int b = u / p.D;
+  const int hs = hr * p.hlen, he = min(p.H, hs + p.hlen);
+  const int w0 = twi * 128;
+  const int n0 = blockIdx.y * LN_BN;
+  const int hfirst = max(hs - 1, 0), hlast = min(he, p.H - 1);
+  const int nsteps = hlast - hfirst + 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 1); }
+    for (int i = 0; i < LN_QSLOTS; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 8); }
+    mbar_init(&w_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < LN_BN) {
+    s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f;
+    s_bias[threadIdx.x] = p.bias ? p.bias[n0 + threadIdx.x] : 0.f;
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===== line producer =====
+    for (int s = 0; s < nsteps; ++s) {
+      const int slot = s % p.stages;
+      mbar_wait(&st_empty[slot], (((uint32_t)(s / p.stages)) & 1u) ^ 1u);
+      if (elect_one()) {
+        mbar_expect_tx(&st_full[slot], (uint32_t)p.stage_tx);
+        uint8_t* dst = st_base + (size_t)slot * p.stage_bytes;
+        for (int z = 0; z < p.ndz; ++z)
+          for (int c = 0; c < p.nchunk; ++c)
+            tma_load_5d(dst + (size_t)z * p.line_bytes + (size_t)c * p.sub_bytes, &p.a_map, &st_full[slot], c * p.kcw,
+                        w0 - 1, hfirst + s, d + p.dz0 + z, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 2) {
+    // ===== weight loader: every (group, dy, chunk) tile once =====
+    if (elect_one()) {
+      mbar_expect_tx(&w_full, (uint32_t)(p.ngroups * 3 * p.nchunk * LN_BN * ROWB));
+      for (int g = 0; g < p.ngroups; ++g)
+        for (int c = 0; c < p.nchunk; ++c)
+          for (int j = 0; j < 3; ++j)
+            tma_load_3d(w_base + (size_t)g * p.wgroup_bytes + (size_t)c * p.wchunk_bytes + (size_t)j * (LN_BN * ROWB),
+                        &p.w_map, &w_full, c * p.kcw, n0, p.grp_widx[g][j]);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t idesc = idesc_f16(p.is_f16 != 0, NCOLS, false, false);
+    const uint32_t hi = ln_kmajor_hi(ROWB, 8u * ROWB);
+    const uint32_t st16 = __shfl_sync(0xffffffffu, (smem_u32(st_base) & 0x3FFFFu) >> 4, 0);
+    const uint32_t w16 = __shfl_sync(0xffffffffu, (smem_u32(w_base) & 0x3FFFFu) >> 4, 0);
+    const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, line16 = (uint32_t)p.line_bytes >> 4;
+    const uint32_t wgroup16 = (uint32_t)p.wgroup_bytes >> 4;
+    const int ngroups = p.ngroups;
+    // per-group descriptor offsets live in (uniform) registers: the issue loop is a handful of adds per MMA.  The single
+    // issuing warp pays the full latency of every dependent instruction, so nothing else may sit between two MMAs.
+    uint32_t a_goff[9], b_goff[9];
+#pragma unroll
+    for (int g = 0; g < 9; ++g) {
+      a_goff[g] = (uint32_t)p.grp_dzslot[g] * line16 + (uint32_t)(p.grp_dxrow[g] * (ROWB / 16));
+      b_goff[g] = w16 + (uint32_t)g * wgroup16;
+    }
+    mbar_wait(&w_full, 0);
+    tc_fence_after();
+    for (int s = 0; s < nsteps; ++s) {
+      const int slot = s % p.stages;
+      const int qs = s % LN_QSLOTS;
+      mbar_wait(&q_empty[qs], (((uint32_t)(s / LN_QSLOTS)) & 1u) ^ 1u);
+      mbar_wait(&st_full[slot], ((uint32_t)(s / p.stages)) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_s = st16 + (uint32_t)slot * stage16;
+        const uint32_t dq = tmem_u + (uint32_t)qs * NCOLS;
+#pragma unroll
+        for (int g = 0; g < 9; ++g) {
+          if (g < ngroups) {
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k)
+              umma_f16(dq, ln_desc64(hi, a_s + a_goff[g] + (uint32_t)(k * 2)), ln_desc64(hi, b_goff[g] + (uint32_t)(k * 2)),
+                       idesc, (g | k) ? 1u : 0u);
+          }
+        }
+        umma_commit(&st_empty[slot]);
+        umma_commit(&q_full[qs]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue warps 3..10: TMEM lane quarter = warp % 4, channel half = (warp - 3) / 4; thread = one w column =====
+    const int q = warp & 3;
+    const int half = (warp - 3) >> 2;
+    const int ww = w0 + q * 32 + lane;
+    const bool wvalid = ww < p.W;
+    T* out = reinterpret_cast<T*>(p.out);
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 16);
+    float csum[16], csq[16], bias[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { csum[j] = 0.f; csq[j] = 0.f; bias[j] = s_bias[half * 16 + j]; }
+    const bool want_stats = p.stats != nullptr;
+
+    auto emit = [&](int h) {
+      uint32_t r[3][16];
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int hq = h + dy;
+        if (hq >= 0 && hq < p.H) {
+          tmem_ld16_async(tlane + (uint32_t)((hq - hfirst) % LN_QSLOTS) * NCOLS + (uint32_t)((dy + 1) * LN_BN), r[dy + 1]);
+        } else {  // out-of-volume line: zero contribution
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[dy + 1][j] = 0u;
+        }
+      }
+      tmem_ld_fence(r[0]);
+      tmem_ld_fence(r[1]);
+      tmem_ld_fence(r[2]);
+      // the three accumulators are in registers: Q[h-1] is not needed by any later output line
+      tc_fence_before();
+      __syncwarp();
+      if (h - 1 >= hfirst && lane == 0) mbar_arrive(&q_empty[(h - 1 - hfirst) % LN_QSLOTS]);
+      if (wvalid) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          v[j] = bias[j] + __uint_as_float(r[0][j]) + __uint_as_float(r[1][j]) + __uint_as_float(r[2][j]);
+        T* orow = out + ((((long long)b * p.D + d) * p.H + h) * p.W + ww) * p.out_ldc + p.out_coff + n0 + half * 16;
+        if (p.accumulate) {
+          float ov[8];
+          load8<T>(orow, ov);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += ov[j];
+          load8<T>(orow + 8, ov);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[8 + j] += ov[j];
+        }
+        float lo[8], hi8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi8[j] = v[8 + j]; }
+        store8<T>(orow, lo);
+        store8<T>(orow + 8, hi8);
+        if (want_stats) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x = Traits<T>::round(v[j]);
+            csum[j] += x;
+            csq[j] = fmaf(x, x, csq[j]);
+          }
+        }
+      }
+    };
+
+    for (int s = 0; s < nsteps; ++s) {
+      const int hp = hfirst + s;
+      mbar_wait(&q_full[s % LN_QSLOTS], ((uint32_t)(s / LN_QSLOTS)) & 1u);
+      tc_fence_after();
+      if (hp - 1 >= hs) emit(hp - 1);
+      if (hp == p.H - 1 && hp < he) emit(hp);  // last line of the volume: Q[H] does not exist
+    }
+    if (want_stats) {
+      warp_colsum16(csum, lane);
+      warp_colsum16(csq, lane);
+      if ((lane & 1) == 0) {
+        const int col = colsum16_column(lane);
+        atomicAdd(&s_sum[half * 16 + col], csum[0]);
+        atomicAdd(&s_sq[half * 16 + col], csq[0]);
+      }
+    }
+  }
+  __syncthreads();
+  if (p.stats && threadIdx.x < LN_BN) {
+    const int c = threadIdx.x;
+    if (s_sum[c] != 0.f || s_sq[c] != 0.f) {
+      double* st = p.stats + ((long long)b * p.Cout + n0 + c) * 2;
+      atomicAdd(st, (double)s_sum[c]);
+      atomicAdd(st + 1, (double)s_sq[c]);
+    }
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+template <typename T, int ROWB>
+static cudaError_t launch_line(const LineParams& q, dim3 grid, int smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(conv_line_umma_kernel<T, ROWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) conv_line_umma_kernel<T, ROWB><<<grid, LN_THREADS, smem, s>>>(q);
+  return e;
+}
+
+static inline int ln_align1k(long long v) { return (int)(((v + 1023) / 1024) * 1024); }
+
+// Returns MTB200_ERR_UNSUPPORTED when the problem is outside this kernel's envelope (caller falls back).
+int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s) {
+  if (p.ngroups != 1) return MTB200_ERR_UNSUPPORTED;
+  for (int k = 0; k < 3; ++k)
+    if (p.is[k] != 1 || p.os[k] != 1 || p.group_ooff[0][k] != 0) return MTB200_ERR_UNSUPPORTED;
+  if (p.Do != p.Di || p.Ho != p.Hi || p.Wo != p.Wi || p.Dof != p.Do || p.Hof != p.Ho || p.Wof != p.Wo)
+    return MTB200_ERR_UNSUPPORTED;
+  if (p.Cin != 16 && p.Cin != 32 && p.Cin != 64) return MTB200_ERR_UNSUPPORTED;  // one chunk (nchunk == 1)
+  if (p.Cout % LN_BN) return MTB200_ERR_UNSUPPORTED;
+  if (p.Wo < 72 || p.Ho < 4) return MTB200_ERR_UNSUPPORTED;  // an M tile is one h-line of 128 w voxels
+
+  static LineParams q;
+  memset(&q, 0, sizeof(q));
+  // groups (dz, dx), each with all three dy taps
+  int gid[3][3];
+  for (int a = 0; a < 3; ++a)
+    for (int c = 0; c < 3; ++c) gid[a][c] = -1;
+  int dzmin = 1, dzmax = -1;
+  for (int t = 0; t < p.ntaps; ++t) {
+    for (int k = 0; k < 3; ++k)
+      if (p.tap_off[t][k] < -1 || p.tap_off[t][k] > 1) return MTB200_ERR_UNSUPPORTED;
+    dzmin = min(dzmin, p.tap_off[t][0]); dzmax = max(dzmax, p.tap_off[t][0]);
+  }
+  q.dz0 = dzmin; q.ndz = dzmax - dzmin + 1;
+  for (int g = 0; g < 9; ++g)
+    for (int j = 0; j < 3; ++j) q.grp_widx[g][j] = -1;
+  for (int t = 0; t < p.ntaps; ++t) {
+    const int dz = p.tap_off[t][0], dy = p.tap_off[t][1], dx = p.tap_off[t][2];
+    int& g = gid[dz + 1][dx + 1];
+    if (g < 0) {
+      g = q.ngroups++;
+      q.grp_dzslot[g] = dz - dzmin;
+      q.grp_dxrow[g] = dx + 1;
+    }
+    if (q.grp_widx[g][dy + 1] >= 0) return MTB200_ERR_UNSUPPORTED;  // duplicate tap
+    q.grp_widx[g][dy + 1] = p.tap_widx[t];
+  }
+  for (int g = 0; g < q.ngroups; ++g)
+    for (int j = 0; j < 3; ++j)
+      if (q.grp_widx[g][j] < 0) return MTB200_ERR_UNSUPPORTED;  // needs all three dy taps of every (dz, dx)
+
+  q.kcw = p.Cin < 64 ? p.Cin : 64;
+  q.nchunk = p.Cin / q.kcw;
+  const int rowb = q.kcw * 2;
+  q.sub_bytes = ln_align1k((long long)LN_WROWS * rowb);
+  q.line_bytes = q.sub_bytes * q.nchunk;
+  q.stage_bytes = q.line_bytes * q.ndz;
+  q.stage_tx = q.ndz * q.nchunk * LN_WROWS * rowb;
+  q.wchunk_bytes = ln_align1k(3LL * LN_BN * rowb);
+  q.wgroup_bytes = q.wchunk_bytes * q.nchunk;
+  const int wbytes = q.wgroup_bytes * q.ngroups;
+  const int smem_budget = 224 * 1024;
+  q.stages = min(LN_MAX_STAGES, (smem_budget - wbytes) / q.stage_bytes);
+  if (q.stages < 2) return MTB200_ERR_UNSUPPORTED;
+
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.Di, (cuuint64_t)p.B};
+    cuuint64_t strides[4] = {(cuuint64_t)p.in_ldc * 2, (cuuint64_t)p.Wi * p.in_ldc * 2,
+                             (cuuint64_t)p.Hi * p.Wi * p.in_ldc * 2, (cuuint64_t)p.Di * p.Hi * p.Wi * p.in_ldc * 2};
+    cuuint32_t box[5] = {(cuuint32_t)q.kcw, (cuuint32_t)LN_WROWS, 1, 1, 1};
+    if (!umma_encode_map(&q.a_map, p.dtype, 5, (uint8_t*)p.in + (size_t)p.in_coff * 2, dims, strides, box, rowb))
+      return MTB200_ERR_CUDA;
+  }
+  {
+    int n_widx = 0;
+    for (int t = 0; t < p.ntaps; ++t) n_widx = max(n_widx, p.tap_widx[t] + 1);
+    cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, (cuuint64_t)n_widx};
+    cuuint64_t strides[2] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Cin * p.Cout * 2};
+    cuuint32_t box[3] = {(cuuint32_t)q.kcw, (cuuint32_t)LN_BN, 1};
+    if (!umma_encode_map(&q.w_map, p.dtype, 3, (void*)p.w, dims, strides, box, rowb)) return MTB200_ERR_CUDA;
+  }
+  q.out = p.out; q.bias = p.bias; q.stats = p.stats;
+  q.B = p.B; q.D = p.Do; q.H = p.Ho; q.W = p.Wo;
+  q.out_ldc = p.out_ldc; q.out_coff = p.out_coff; q.Cout = p.Cout;
+  q.accumulate = p.accumulate;
+  q.is_f16 = p.dtype == MTB200_F16;
+  q.ntw = (p.Wo + 127) / 128;
+  const int ny = p.Cout / LN_BN;
+  // split H into ranges: whole waves of the machine (one CTA per SM); every range recomputes two halo lines
+  {
+    const int sms = num_sms();
+    const long long base = (long long)p.B * p.Do * q.ntw * ny;
+    double best = -1;
+    int best_nhr = 1;
+    for (int nhr = 1; nhr <= max(1, p.Ho / 8); ++nhr) {
+      const int hlen = (p.Ho + nhr - 1) / nhr;
+      if ((p.Ho + hlen - 1) / hlen != nhr) continue;
+      const long long ctas = base * nhr;
+      const long long waves = (ctas + sms - 1) / sms;
+      const double eff = (double)ctas / (double)(waves * sms) * hlen / (hlen + 2.0 + 3.0);  // halo lines + prologue
+      if (eff > best) { best = eff; best_nhr = nhr; }
+    }
+    q.nhr = best_nhr;
+    q.hlen = (p.Ho + q.nhr - 1) / q.nhr;
+  }
+  const long long units = (long long)p.B * p.Do * q.ntw * q.nhr;
+  MTB_REQUIRE(units < (1LL << 31), "conv_line: too many work units");
+  const int smem = max(116 * 1024, q.stages * q.stage_bytes + wbytes + 1024);  // one CTA per SM (512 TMEM columns each)
+  dim3 grid((unsigned)units, ny, 1);
+  cudaError_t e;
+  if (p.dtype == MTB200_BF16) {
+    e = rowb == 128 ? launch_line<__nv_bfloat16, 128>(q, grid, smem, s)
+                    : (rowb == 64 ? launch_line<__nv_bfloat16, 64>(q, grid, smem, s)
+                                  : launch_line<__nv_bfloat16, 32>(q, grid, smem, s));
+  } else {
+    e = rowb == 128 ? launch_line<__half, 128>(q, grid, smem, s)
+                    : (rowb == 64 ? launch_line<__half, 64>(q, grid, smem, s) : launch_line<__half, 32>(q, grid, smem, s));
+  }
+  if (e != cudaSuccess) { set_error("conv_line: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
+  return check_launch("conv_line_umma");
+}
+
+}  // namespace mtb

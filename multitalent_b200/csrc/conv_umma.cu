@@ -38,6 +38,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int conv_halo_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_halo.cu
+int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_line.cu
 
 int umma_available() {
   static int cached = -1;
@@ -323,8 +324,14 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
     if (p.is[k] < 1 || p.is[k] > 2) { set_error("conv_taps(umma): input stride %d", p.is[k]); return MTB200_ERR_UNSUPPORTED; }
   const long long M = (long long)p.B * p.Do * p.Ho * p.Wo;
   if (M == 0) return MTB200_OK;
-  // impl 3 = per-tap kernel only, impl 4 = plane-streaming only; auto: plane-streaming where it measured faster on the
-  // B200 (tools/conv_bench.py, profiles/r1d_conv_bench.txt): narrow layers whose 27 weight tiles stay resident.
+  // impl 3 = per-tap kernel only, 4 = plane-streaming only, 5 = line-streaming (dy merged into N) only; auto = what
+  // measured fastest on the B200 (tools/conv_bench.py, profiles/): line-streaming for the wide-W narrow-channel layers,
+  // plane-streaming for other narrow layers whose 27 weight tiles stay resident, per-tap otherwise.
+  if (p.impl == 5 || (p.impl != 3 && p.impl != 4)) {
+    const int r = conv_line_umma(p, s);
+    if (r != MTB200_ERR_UNSUPPORTED) return r;
+    if (p.impl == 5) { set_error("conv_taps(umma): problem outside the line-streaming kernel's envelope"); return r; }
+  }
   if (p.impl == 4 || (p.impl != 3 && p.Cin <= 32 && p.Cout <= 32)) {
     const int r = conv_halo_umma(p, s);
     if (r != MTB200_ERR_UNSUPPORTED) return r;

@@ -138,6 +138,70 @@ def test_conv_plane_streaming_matches_ffma(dtype, cin, cout, kernel, dims):
         _close(res[1][2], res[0][2], dtype)
 
 
+LINE_CASES = [
+    # cin, cout, kernel, dims(B,D,H,W): stride 1, W >= 72 (an M tile is one h-line of 128 w voxels), Cin_p <= 64
+    (30, 30, (3, 3, 3), (1, 6, 20, 128)),
+    (30, 30, (3, 3, 3), (2, 3, 9, 100)),      # ragged w (masked columns), odd h
+    (60, 30, (3, 3, 3), (1, 4, 12, 128)),     # Cin_p 64 (128-byte rows, 2 stages)
+    (30, 60, (3, 3, 3), (1, 4, 16, 128)),     # two Cout blocks
+    (1, 30, (3, 3, 3), (1, 5, 24, 160)),      # Cin_p 16, two w tiles (the second one 32 wide)
+    (20, 24, (1, 3, 3), (1, 3, 40, 96)),      # 9 taps, a single staged plane; h split into ranges
+    (30, 30, (3, 3, 3), (1, 2, 160, 128)),    # long in h: accumulator / stage ring wrap-around
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("cin,cout,kernel,dims", LINE_CASES)
+def test_conv_line_streaming_matches_ffma(dtype, cin, cout, kernel, dims):
+    """impl=5 forces the line-streaming kernel (dy taps merged into N = 96) for forward AND the stride-1 data gradient."""
+    _require_tcgen05()
+    from multitalent_b200.engine import ConvOp, Engine, Tape
+    torch.manual_seed(0)
+    B, D, H, W = dims
+    x = torch.randn(B, cin, D, H, W, device=DEV)
+    conv = nn.Conv3d(cin, cout, kernel, 1, [(k - 1) // 2 for k in kernel], bias=True).to(DEV)
+    op = ConvOp(conv.weight, conv.bias, kernel, (1, 1, 1))
+    gy = torch.randn(B, cout, D, H, W, device=DEV)
+    res = []
+    for impl in (1, 5):
+        eng = Engine(dtype, impl)
+        tape = Tape()
+        xf = eng.input_feat(x)
+        y, st = eng.conv(op, xf, want_stats=True)
+        gx = None
+        if op.Cout_p <= 64 and op.Cin_p % 32 == 0:  # the data gradient = same kernel, Cin := Cout_p, Cout := Cin_p
+            y2 = eng.conv_plain(tape, op, xf)
+            eng.seed_grad(tape, y2, gy)
+            eng.run_backward(tape)
+            gx = tape.grad_feat(xf)[0].buf.clone()
+        res.append((y.buf.clone(), st.clone(), gx))
+    _close(res[1][0], res[0][0], dtype)
+    np.testing.assert_allclose(res[1][1].cpu().numpy(), res[0][1].cpu().numpy(),
+                               atol=2e-2 * float(res[0][1].abs().max()) + 1e-3)
+    if res[0][2] is not None:
+        _close(res[1][2], res[0][2], dtype)
+
+
+def test_line_streaming_accumulate_flag():
+    _require_tcgen05()
+    from multitalent_b200.engine import ConvOp, Engine, Feat
+    torch.manual_seed(2)
+    dtype = torch.bfloat16
+    x = torch.randn(1, 32, 3, 8, 128, device=DEV)
+    conv = nn.Conv3d(32, 32, 3, 1, 1, bias=False).to(DEV)
+    op = ConvOp(conv.weight, None, (3, 3, 3), (1, 1, 1))
+    base = torch.randn(1, 3, 8, 128, 64, device=DEV).to(dtype)   # write into the second half of a wider buffer
+    res = []
+    for impl in (1, 5):
+        eng = Engine(dtype, impl)
+        xf = eng.input_feat(x)
+        out = Feat(base.clone(), 32, 32, 32)
+        eng._conv_call(op.fwd_taps, xf, op.packed(eng.wdtype, False), None, out, (3, 8, 128), None, True, 32, 32)
+        res.append(out.buf)
+    _close(res[1], res[0], dtype)
+    assert torch.equal(res[1][..., :32], base[..., :32])  # the other half is untouched
+
+
 def test_plane_streaming_accumulate_flag():
     _require_tcgen05()
     from multitalent_b200.engine import ConvOp, Engine, Feat

@@ -29,7 +29,7 @@ LAYERS = {
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--impl", type=int, nargs="+", default=[3, 4])
+    ap.add_argument("--impl", type=int, nargs="+", default=[3, 4, 5])
     ap.add_argument("--what", nargs="+", default=["fwd", "dgrad", "wgrad"])
     ap.add_argument("--layers", nargs="+", default=list(LAYERS))
     ap.add_argument("--reps", type=int, default=5)
