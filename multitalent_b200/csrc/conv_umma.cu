@@ -39,6 +39,7 @@ static EncodeTiledFn get_encode_fn() {
 
 int conv_halo_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_halo.cu
 int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_line.cu
+int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s);  // wgrad_line.cu
 
 int umma_available() {
   static int cached = -1;
@@ -655,6 +656,11 @@ int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
     if (p.is[k] < 1 || p.is[k] > 2 || p.os[k] < 1 || p.os[k] > 2) { set_error("wgrad_taps(umma): stride"); return MTB200_ERR_UNSUPPORTED; }
   const long long M = (long long)p.B * p.Do * p.Ho * p.Wo;
   if (M == 0) return MTB200_OK;
+  if (p.impl != 3) {  // line-streaming kernel first (impl 3 = per-tap kernel only, impl 5 = line-streaming only)
+    const int r = wgrad_line_umma(p, s);
+    if (r != MTB200_ERR_UNSUPPORTED) return r;
+    if (p.impl == 5) { set_error("wgrad_taps(umma): problem outside the line-streaming kernel's envelope"); return r; }
+  }
   EncodeTiledFn enc = get_encode_fn();
   const CUtensorMapDataType dt = p.dtype == MTB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 

@@ -1,0 +1,273 @@
+// Line-streaming tcgen05 weight gradient for the narrow full-resolution 3x3x3 layers (stride 1, taps in [-1,1]^3,
+// Cout tile 32, Cin chunks of <= 32 channels) -- the autograd of conv_line.cu's layers w.r.t. their weights:
+//     dW[(dz,dy,dx)][co][ci] = sum_{b,d,h,w} dY[b,d,h,w][co] * X[b,d+dz,h+dy,w+dx][ci]
+//
+// GEMM view with K = voxels along w (16 per MMA), both operands MN-major straight out of the NDHWC tensors:
+//   A = an X line [K = w][M = 128]: the M blocks are ROW-SHIFTED VIEWS of the same shared-memory line (LBO = one row),
+//       block j = the line shifted by j voxels = tap dx = j - 1  (4 blocks of 32 channels, or 8 of 16; dx <= 1 are used)
+//   B = three consecutive dY lines [K = w][N = 96]: block jj = line h'-1+jj = tap dy = 1 - jj  (LBO = one line)
+//   D_dz [128 = (dx, ci)][96 = (dy, co)] fp32 in TMEM, one accumulator per dz, resident for the whole kernel.
+// tools/umma_probe_mn.cu verified on the B200 that MN-major descriptors accept any start row, any 8-row-group stride and
+// an M-block stride of one row (overlapping blocks).  One MMA therefore does 9 taps' worth of useful work (of 12).
+//
+// Persistent CTAs (one per SM) walk a list of (b, d, h-range, w-tile) units; every step h' stages the three X lines
+// (d-1, d, d+1) x h' and the dY lines h'-1 .. h'+1 of plane d (TMA, out-of-volume = zero fill), so steps are independent
+// and the pipeline never drains between units.  Epilogue once per CTA: fp32 atomics into dW.
+//
+// Warp roles (6 warps): 0 = producer (TMA), 1 = TMEM owner + MMA issuer, 2..5 = epilogue.
+#include "umma.cuh"
+
+namespace mtb {
+
+using namespace um;
+
+constexpr int WL_THREADS = 192;
+constexpr int WL_MAX_STAGES = 6;
+constexpr int WL_XROWS = 130;
+constexpr int WL_BN = 32;
+
+struct WgradLineParams {
+  CUtensorMap x_map, dy_map;
+  float* dw;
+  int B, D, H, W;
+  int Cin, Cout;             // padded channel counts (dw strides)
+  int kcw;                   // channels of this launch's X chunk (16 or 32)
+  int xline_bytes;           // one staged X line, 1024-aligned
+  int ybase;                 // offset of the dY window inside a stage
+  int stage_bytes, stage_tx, stages;
+  int ndz, dz0;
+  int nhr, hlen, ntw;
+  long long units;
+  int lut[27];               // [dz+1][dy+1][dx+1] -> weight slice or -1
+  int is_f16;
+};
+
+__device__ __forceinline__ uint64_t wl_desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
+
+template <int ROWB>  // bytes per X row = kcw * 2 (64: four 32-channel blocks, 32: eight 16-channel blocks)
+__global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __grid_constant__ WgradLineParams p) {
+  extern __shared__ uint8_t dsmem_raw[];
+  __shared__ __align__(8) uint64_t st_full[WL_MAX_STAGES], st_empty[WL_MAX_STAGES];
+  __shared__ __align__(8) uint64_t acc_full;
+  __shared__ uint32_t tmem_slot;
+
+  constexpr uint32_t NCOLS = 3 * WL_BN;
+  constexpr uint32_t YROWB = WL_BN * 2;           // bytes per dY row
+  constexpr uint32_t YLINE = 128 * YROWB;         // one dY line
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
+  const int c0 = blockIdx.y * p.kcw;
+  const int n0 = blockIdx.z * WL_BN;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 1); }
+    mbar_init(&acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const bool have_work = (long long)blockIdx.x < p.units;
+
+  if (warp == 0) {
+    // ===== producer =====
+    uint32_t sc = 0;  // global step counter of this CTA
+    for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+      long long t = u;
+      const int hr = (int)(t % p.nhr); t /= p.nhr;
+      const int twi = (int)(t % p.ntw); t /= p.ntw;
+      const int d = (int)(t % p.D);
+      const int b = (int)(t / p.D);
+      const int hs = hr * p.hlen, he = min(p.H, hs + p.hlen);
+      const int w0 = twi * 128;
+      for (int hp = hs; hp < he; ++hp, ++sc) {
+        const uint32_t slot = sc % (uint32_t)p.stages;
+        mbar_wait(&st_empty[slot], ((sc / (uint32_t)p.stages) & 1u) ^ 1u);
+        if (elect_one()) {
+          uint8_t* dst = dsmem + (size_t)slot * p.stage_bytes;
+          mbar_expect_tx(&st_full[slot], (uint32_t)p.stage_tx);
+          for (int z = 0; z < p.ndz; ++z)
+            tma_load_5d(dst + (size_t)z * p.xline_bytes, &p.x_map, &st_full[slot], c0, w0 - 1, hp, d + p.dz0 + z, b);
+          tma_load_5d(dst + p.ybase, &p.dy_map, &st_full[slot], n0, w0, hp - 1, d, b);  // lines hp-1, hp, hp+1
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t fmt = p.is_f16 ? 0u : 1u;
+    // D = f32, A/B 16-bit, both MN-major (bits 15, 16), N = 96, M = 128
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((NCOLS >> 3) << 17) |
+                           ((128u >> 4) << 24);
+    const uint32_t layout_a = ROWB == 64 ? 4u : 6u;  // SWIZZLE_64B / SWIZZLE_32B
+    const uint32_t hi_a = ((8u * ROWB) >> 4) | (1u << 14) | (layout_a << 29);
+    const uint32_t hi_b = ((8u * YROWB) >> 4) | (1u << 14) | (4u << 29);
+    const uint32_t lbo_a = ((uint32_t)ROWB >> 4) << 16, lbo_b = (YLINE >> 4) << 16;
+    const uint32_t s16 = __shfl_sync(0xffffffffu, (smem_u32(dsmem) & 0x3FFFFu) >> 4, 0);
+    const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, xline16 = (uint32_t)p.xline_bytes >> 4;
+    const uint32_t y16 = (uint32_t)p.ybase >> 4;
+    const int ndz = p.ndz;
+    uint32_t sc = 0;
+    for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+      const int hr = (int)(u % p.nhr);
+      const int hs = hr * p.hlen, he = min(p.H, hs + p.hlen);
+      for (int hp = hs; hp < he; ++hp, ++sc) {
+        const uint32_t slot = sc % (uint32_t)p.stages;
+        mbar_wait(&st_full[slot], (sc / (uint32_t)p.stages) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_s = (s16 + slot * stage16) | lbo_a;
+          const uint32_t b_s = (s16 + slot * stage16 + y16) | lbo_b;
+          const uint32_t acc = sc > 0 ? 1u : 0u;
+#pragma unroll
+          for (int z = 0; z < 3; ++z) {
+            if (z < ndz) {
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk)
+                umma_f16(tmem_u + (uint32_t)z * NCOLS, wl_desc64(hi_a, a_s + (uint32_t)z * xline16 + (uint32_t)(kk * ROWB)),
+                         wl_desc64(hi_b, b_s + (uint32_t)(kk * YROWB)), idesc, kk ? 1u : acc);
+            }
+          }
+          umma_commit(&st_empty[slot]);
+        }
+        __syncwarp();
+      }
+    }
+    if (have_work) {
+      if (elect_one()) umma_commit(&acc_full);
+      __syncwarp();
+    }
+  } else if (have_work) {
+    // ===== epilogue: TMEM -> fp32 atomics into dW[widx][co][ci] =====
+    constexpr int CB = ROWB / 2;  // channels per M block
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int j = m / CB, ci = m % CB;
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    // every lane takes part in the .sync.aligned TMEM loads; only rows of used blocks (dx = j - 1 <= 1) write back
+    if ((q * 32) / CB <= 2) {
+      for (int z = 0; z < p.ndz; ++z) {
+        const int dzi = p.dz0 + z + 1;
+#pragma unroll
+        for (int c16 = 0; c16 < 6; ++c16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)z * NCOLS + (uint32_t)(c16 * 16), r);
+          const int jj = c16 >> 1;  // dY line of the window: dy = 1 - jj
+          const int widx = j <= 2 ? p.lut[(dzi * 3 + (2 - jj)) * 3 + j] : -1;
+          if (widx >= 0) {
+            float* dst = p.dw + ((long long)widx * p.Cout + n0 + (c16 & 1) * 16) * p.Cin + c0 + ci;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float v = __uint_as_float(r[e]);
+              if (v != 0.f) atomicAdd(dst + (long long)e * p.Cin, v);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+static inline int wl_align1k(long long v) { return (int)(((v + 1023) / 1024) * 1024); }
+
+// Returns MTB200_ERR_UNSUPPORTED when the problem is outside this kernel's envelope (caller falls back).
+int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
+  if (p.ngroups != 1 || p.xform) return MTB200_ERR_UNSUPPORTED;
+  for (int k = 0; k < 3; ++k)
+    if (p.is[k] != 1 || p.os[k] != 1 || p.group_ooff[0][k] != 0) return MTB200_ERR_UNSUPPORTED;
+  if (p.Do != p.Di || p.Ho != p.Hi || p.Wo != p.Wi || p.Dof != p.Do || p.Hof != p.Ho || p.Wof != p.Wo)
+    return MTB200_ERR_UNSUPPORTED;
+  if (p.Cin != 16 && p.Cin % 32 != 0) return MTB200_ERR_UNSUPPORTED;
+  if (p.Cin > 64 || p.Cout % WL_BN || p.Cout > 64) return MTB200_ERR_UNSUPPORTED;
+  if (p.Wo < 72 || p.Ho < 4 || p.ntaps < 9) return MTB200_ERR_UNSUPPORTED;
+
+  static WgradLineParams q;
+  memset(&q, 0, sizeof(q));
+  for (int i = 0; i < 27; ++i) q.lut[i] = -1;
+  int dzmin = 1, dzmax = -1;
+  for (int t = 0; t < p.ntaps; ++t) {
+    for (int k = 0; k < 3; ++k)
+      if (p.tap_off[t][k] < -1 || p.tap_off[t][k] > 1) return MTB200_ERR_UNSUPPORTED;
+    int& e = q.lut[((p.tap_off[t][0] + 1) * 3 + (p.tap_off[t][1] + 1)) * 3 + (p.tap_off[t][2] + 1)];
+    if (e >= 0) return MTB200_ERR_UNSUPPORTED;
+    e = p.tap_widx[t];
+    dzmin = min(dzmin, p.tap_off[t][0]); dzmax = max(dzmax, p.tap_off[t][0]);
+  }
+  q.dz0 = dzmin; q.ndz = dzmax - dzmin + 1;
+  q.kcw = p.Cin < 32 ? p.Cin : 32;
+  const int nchunk = p.Cin / q.kcw;
+  const int rowb = q.kcw * 2;
+  q.xline_bytes = wl_align1k((long long)WL_XROWS * rowb);
+  q.ybase = q.xline_bytes * q.ndz;
+  const int ybytes = 3 * 128 * WL_BN * 2;
+  q.stage_bytes = q.ybase + ybytes;
+  q.stage_tx = q.ndz * WL_XROWS * rowb + ybytes;
+  q.stages = min(WL_MAX_STAGES, (224 * 1024) / q.stage_bytes);
+  if (q.stages < 2) return MTB200_ERR_UNSUPPORTED;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.Di, (cuuint64_t)p.B};
+    cuuint64_t strides[4] = {(cuuint64_t)p.in_ldc * 2, (cuuint64_t)p.Wi * p.in_ldc * 2,
+                             (cuuint64_t)p.Hi * p.Wi * p.in_ldc * 2, (cuuint64_t)p.Di * p.Hi * p.Wi * p.in_ldc * 2};
+    cuuint32_t box[5] = {(cuuint32_t)q.kcw, (cuuint32_t)WL_XROWS, 1, 1, 1};
+    if (!umma_encode_map(&q.x_map, p.dtype, 5, (uint8_t*)p.x + (size_t)p.in_coff * 2, dims, strides, box, rowb))
+      return MTB200_ERR_CUDA;
+  }
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wof, (cuuint64_t)p.Hof, (cuuint64_t)p.Dof, (cuuint64_t)p.B};
+    cuuint64_t strides[4] = {(cuuint64_t)p.out_ldc * 2, (cuuint64_t)p.Wof * p.out_ldc * 2,
+                             (cuuint64_t)p.Hof * p.Wof * p.out_ldc * 2,
+                             (cuuint64_t)p.Dof * p.Hof * p.Wof * p.out_ldc * 2};
+    cuuint32_t box[5] = {(cuuint32_t)WL_BN, 128, 3, 1, 1};
+    if (!umma_encode_map(&q.dy_map, p.dtype, 5, (uint8_t*)p.dy + (size_t)p.out_coff * 2, dims, strides, box, WL_BN * 2))
+      return MTB200_ERR_CUDA;
+  }
+  q.dw = p.dw;
+  q.B = p.B; q.D = p.Do; q.H = p.Ho; q.W = p.Wo;
+  q.Cin = p.Cin; q.Cout = p.Cout;
+  q.is_f16 = p.dtype == MTB200_F16;
+  q.ntw = (p.Wo + 127) / 128;
+  const int sms = num_sms();
+  {
+    // split H into ranges so that every persistent CTA gets (almost) the same number of steps
+    const long long base = (long long)p.B * p.Do * q.ntw;
+    double best = -1;
+    int best_nhr = 1;
+    for (int nhr = 1; nhr <= max(1, p.Ho / 8); ++nhr) {
+      const int hlen = (p.Ho + nhr - 1) / nhr;
+      if ((p.Ho + hlen - 1) / hlen != nhr) continue;
+      const long long units = base * nhr;
+      const long long g = units < sms ? units : sms;
+      const long long per = (units + g - 1) / g;
+      const double eff = (double)units / (double)(per * g);
+      if (eff > best + 1e-9) { best = eff; best_nhr = nhr; }
+    }
+    q.nhr = best_nhr;
+    q.hlen = (p.Ho + q.nhr - 1) / q.nhr;
+  }
+  q.units = (long long)p.B * p.Do * q.ntw * q.nhr;
+  const int gx = (int)(q.units < sms ? q.units : sms);
+  const int smem = max(116 * 1024, q.stages * q.stage_bytes + 1024);  // one CTA per SM (512 TMEM columns each)
+  dim3 grid((unsigned)gx, nchunk, p.Cout / WL_BN);
+  cudaError_t e;
+  if (rowb == 64) {
+    e = cudaFuncSetAttribute(wgrad_line_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) wgrad_line_umma_kernel<64><<<grid, WL_THREADS, smem, s>>>(q);
+  } else {
+    e = cudaFuncSetAttribute(wgrad_line_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) wgrad_line_umma_kernel<32><<<grid, WL_THREADS, smem, s>>>(q);
+  }
+  if (e != cudaSuccess) { set_error("wgrad_line: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
+  return check_launch("wgrad_line_umma");
+}
+
+}  // namespace mtb
