@@ -78,6 +78,36 @@ template <> __device__ __forceinline__ void store8<__half>(__half* p, const floa
   *reinterpret_cast<uint4*>(p) = r;
 }
 
+// 8 consecutive elements kept in their storage format (4 registers for the 16-bit types): lets a streaming kernel
+// keep several vectors in flight without paying 8 fp32 registers per vector
+template <typename T> struct Raw8;
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ float get(int i) const {
+    return i == 0 ? a.x : i == 1 ? a.y : i == 2 ? a.z : i == 3 ? a.w : i == 4 ? b.x : i == 5 ? b.y : i == 6 ? b.z : b.w;
+  }
+};
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 r;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ float get(int i) const {
+    const uint32_t w = i < 2 ? r.x : i < 4 ? r.y : i < 6 ? r.z : r.w;
+    return __uint_as_float((i & 1) ? (w & 0xFFFF0000u) : (w << 16));
+  }
+};
+template <> struct Raw8<__half> {
+  uint4 r;
+  __device__ __forceinline__ void load(const __half* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ float get(int i) const {
+    const uint32_t w = i < 2 ? r.x : i < 4 ? r.y : i < 6 ? r.z : r.w;
+    const __half2 h = *reinterpret_cast<const __half2*>(&w);
+    return (i & 1) ? __high2float(h) : __low2float(h);
+  }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -1,6 +1,8 @@
 // InstanceNorm3d(affine) + LeakyReLU: statistics finalisation, materialisation, and the two-pass backward.
 // All kernels are HBM-bound streaming passes over NDHWC slices: one thread owns a group of 8 channels (one 16/32-byte
 // vector) and strides over voxels, so the per-(b,c) coefficients live in registers.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mtb {
@@ -26,10 +28,18 @@ __device__ __forceinline__ Span make_span(long long nvox, int C) {
   return s;
 }
 
+// tuning knobs (environment overrides are for tools/norm_bench.py only; defaults = what measured best on the B200)
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+static int norm_nu() { static int v = env_int("MTB200_NORM_NU", 4); return v; }
+static int norm_waves() { static int v = env_int("MTB200_NORM_WAVES", 8); return v; }
+
 static dim3 span_grid(long long nvox, int B, int C) {
   const int G = C / 8;
   const int vstride = NT / G;
-  long long want = (8LL * num_sms() + B - 1) / B;
+  long long want = ((long long)norm_waves() * num_sms() + B - 1) / B;
   long long maxb = (nvox + (long long)vstride * 4 - 1) / ((long long)vstride * 4);  // >= 4 iterations per block
   long long nb = max(1LL, min(want, maxb));
   return dim3((unsigned)nb, (unsigned)B);
@@ -110,7 +120,7 @@ int in_stats(const void* y, int dtype, int B, long long nvox, int ldc, int coff,
 }
 
 // ---- materialise act = f(y) (+ residual) ---------------------------------------------------------------------------
-template <typename T>
+template <typename T, int NU>
 __global__ void __launch_bounds__(NT) norm_act_kernel(const T* __restrict__ y, int in_ldc, int in_coff, T* __restrict__ out,
                                                       int out_ldc, int out_coff, long long nvox, int C,
                                                       const float4* __restrict__ xform, const T* __restrict__ res,
@@ -128,26 +138,47 @@ __global__ void __launch_bounds__(NT) norm_act_kernel(const T* __restrict__ y, i
   const T* ybase = y + (long long)b * nvox * in_ldc + in_coff + sp.cg * 8;
   T* obase = out + (long long)b * nvox * out_ldc + out_coff + sp.cg * 8;
   const T* rbase = res ? res + (long long)b * nvox * res_ldc + res_coff + sp.cg * 8 : nullptr;
-  for (long long v = sp.v0 + sp.vlane; v < sp.v1; v += sp.vstride) {
-    float x[8];
-    load8<T>(ybase + v * in_ldc, x);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float t = fmaf(x[j], f[j].x, f[j].y);
-      x[j] = t > 0.f ? t : t * f[j].z;
-    }
-    if (rbase) {
-      float r[8];
+  if (rbase) {
+    for (long long v = sp.v0 + sp.vlane; v < sp.v1; v += sp.vstride) {
+      float x[8], r[8];
+      load8<T>(ybase + v * in_ldc, x);
       load8<T>(rbase + v * res_ldc, r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float t = fmaf(r[j], rf[j].x, rf[j].y);
-        t = t > 0.f ? t : t * rf[j].z;
-        t += x[j];
-        x[j] = t > 0.f ? t : t * slope2;
+        float t = fmaf(x[j], f[j].x, f[j].y);
+        t = t > 0.f ? t : t * f[j].z;
+        float u = fmaf(r[j], rf[j].x, rf[j].y);
+        u = u > 0.f ? u : u * rf[j].z;
+        u += t;
+        x[j] = u > 0.f ? u : u * slope2;
+      }
+      store8<T>(obase + v * out_ldc, x);
+    }
+    return;
+  }
+  // streaming pass: NU voxels per thread per iteration, every load issued before the arithmetic (memory-level
+  // parallelism: ~6.5 MB must be in flight chip-wide to saturate HBM3e)
+  const long long chunk = (long long)NU * sp.vstride;  // grid-stride over chunks: the active blocks form a compact
+                                                       // moving front in DRAM instead of 1000+ scattered streams
+  for (long long base = (long long)blockIdx.x * chunk; base < nvox; base += (long long)gridDim.x * chunk) {
+    float x[NU][8];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const long long vv = base + sp.vlane + (long long)u * sp.vstride;
+      if (vv < nvox) load8<T>(ybase + vv * in_ldc, x[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const long long vv = base + sp.vlane + (long long)u * sp.vstride;
+      if (vv < nvox) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = fmaf(x[u][j], f[j].x, f[j].y);
+          x[u][j] = t > 0.f ? t : t * f[j].z;
+        }
+        store8<T>(obase + vv * out_ldc, x[u]);
       }
     }
-    store8<T>(obase + v * out_ldc, x);
   }
 }
 
@@ -158,15 +189,18 @@ int norm_act(const void* y, int in_ldc, int in_coff, void* out, int out_ldc, int
               "norm_act: channel counts/strides must be multiples of 8 (C=%d)", C);
   if (res) MTB_REQUIRE(res_ldc % 8 == 0 && res_coff % 8 == 0, "norm_act: residual stride/offset must be x8");
   dim3 grid = span_grid(nvox, B, C);
-  MTB_DISPATCH_DTYPE(dtype, T, (norm_act_kernel<T><<<grid, NT, 0, s>>>(
-      reinterpret_cast<const T*>(y), in_ldc, in_coff, reinterpret_cast<T*>(out), out_ldc, out_coff, nvox, C,
-      reinterpret_cast<const float4*>(xform), reinterpret_cast<const T*>(res), res_ldc, res_coff,
-      reinterpret_cast<const float4*>(res_xform), slope2)));
+#define MTB_NORM_ACT(NU_)                                                                                        \
+  MTB_DISPATCH_DTYPE(dtype, T, (norm_act_kernel<T, NU_><<<grid, NT, 0, s>>>(                                     \
+      reinterpret_cast<const T*>(y), in_ldc, in_coff, reinterpret_cast<T*>(out), out_ldc, out_coff, nvox, C,     \
+      reinterpret_cast<const float4*>(xform), reinterpret_cast<const T*>(res), res_ldc, res_coff,                \
+      reinterpret_cast<const float4*>(res_xform), slope2)))
+  switch (norm_nu()) { case 1: MTB_NORM_ACT(1); break; case 2: MTB_NORM_ACT(2); break; default: MTB_NORM_ACT(4); }
+#undef MTB_NORM_ACT
   return check_launch("norm_act");
 }
 
 // ---- backward pass 1: red[b][c] = {sum dv, sum dv*xhat}, dv = dact * lrelu'(v) --------------------------------------
-template <typename T>
+template <typename T, int NU>
 __global__ void __launch_bounds__(NT) in_bwd_reduce_kernel(const T* __restrict__ dact, int d_ldc, int d_coff,
                                                            const T* __restrict__ y, int y_ldc, int y_coff, long long nvox,
                                                            int C, const float4* __restrict__ xform,
@@ -186,17 +220,29 @@ __global__ void __launch_bounds__(NT) in_bwd_reduce_kernel(const T* __restrict__
     }
     const T* dbase = dact + (long long)b * nvox * d_ldc + d_coff + sp.cg * 8;
     const T* ybase = y + (long long)b * nvox * y_ldc + y_coff + sp.cg * 8;
-    for (long long v = sp.v0 + sp.vlane; v < sp.v1; v += sp.vstride) {
-      float d[8], x[8];
-      load8<T>(dbase + v * d_ldc, d);
-      load8<T>(ybase + v * y_ldc, x);
+    // NU voxels per thread per iteration: all loads are issued before the arithmetic
+    const long long chunk = (long long)NU * sp.vstride;
+    for (long long base = (long long)blockIdx.x * chunk; base < nvox; base += (long long)gridDim.x * chunk) {
+      Raw8<T> d[NU], x[NU];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float t = fmaf(x[j], f[j].x, f[j].y);
-        const float dv = t > 0.f ? d[j] : d[j] * f[j].z;
-        const float xhat = (x[j] - mr[j].x) * mr[j].y;
-        part[0][j] += dv;
-        part[1][j] = fmaf(dv, xhat, part[1][j]);
+      for (int u = 0; u < NU; ++u) {
+        const long long vv = min(base + sp.vlane + (long long)u * sp.vstride, nvox - 1);  // clamped tail re-reads
+        d[u].load(dbase + vv * d_ldc);
+        x[u].load(ybase + vv * y_ldc);
+      }
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        if (base + sp.vlane + (long long)u * sp.vstride < nvox) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xv = x[u].get(j), dd = d[u].get(j);
+            const float t = fmaf(xv, f[j].x, f[j].y);
+            const float dv = t > 0.f ? dd : dd * f[j].z;
+            const float xhat = (xv - mr[j].x) * mr[j].y;
+            part[0][j] += dv;
+            part[1][j] = fmaf(dv, xhat, part[1][j]);
+          }
+        }
       }
     }
   }
@@ -208,14 +254,17 @@ int in_bwd_reduce(const void* dact, int d_ldc, int d_coff, const void* y, int y_
   MTB_REQUIRE(C % 8 == 0 && C / 8 <= NT && d_ldc % 8 == 0 && d_coff % 8 == 0 && y_ldc % 8 == 0 && y_coff % 8 == 0,
               "in_bwd_reduce: channel counts/strides must be multiples of 8 (C=%d)", C);
   dim3 grid = span_grid(nvox, B, C);
-  MTB_DISPATCH_DTYPE(dtype, T, (in_bwd_reduce_kernel<T><<<grid, NT, 0, s>>>(
-      reinterpret_cast<const T*>(dact), d_ldc, d_coff, reinterpret_cast<const T*>(y), y_ldc, y_coff, nvox, C,
-      reinterpret_cast<const float4*>(xform), reinterpret_cast<const float2*>(meanrstd), red)));
+#define MTB_IN_RED(NU_)                                                                                          \
+  MTB_DISPATCH_DTYPE(dtype, T, (in_bwd_reduce_kernel<T, NU_><<<grid, NT, 0, s>>>(                                \
+      reinterpret_cast<const T*>(dact), d_ldc, d_coff, reinterpret_cast<const T*>(y), y_ldc, y_coff, nvox, C,    \
+      reinterpret_cast<const float4*>(xform), reinterpret_cast<const float2*>(meanrstd), red)))
+  switch (norm_nu()) { case 1: MTB_IN_RED(1); break; case 2: MTB_IN_RED(2); break; default: MTB_IN_RED(4); }
+#undef MTB_IN_RED
   return check_launch("in_bwd_reduce");
 }
 
 // ---- backward pass 2 ------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int NU>
 __global__ void __launch_bounds__(NT) in_bwd_apply_kernel(const T* __restrict__ dact, int d_ldc, int d_coff,
                                                           const T* __restrict__ y, int y_ldc, int y_coff, T* __restrict__ dy,
                                                           int dy_ldc, int dy_coff, long long nvox, int B, int C,
@@ -251,18 +300,32 @@ __global__ void __launch_bounds__(NT) in_bwd_apply_kernel(const T* __restrict__ 
   const T* dbase = dact + (long long)b * nvox * d_ldc + d_coff + sp.cg * 8;
   const T* ybase = y + (long long)b * nvox * y_ldc + y_coff + sp.cg * 8;
   T* obase = dy + (long long)b * nvox * dy_ldc + dy_coff + sp.cg * 8;
-  for (long long v = sp.v0 + sp.vlane; v < sp.v1; v += sp.vstride) {
-    float d[8], x[8];
-    load8<T>(dbase + v * d_ldc, d);
-    load8<T>(ybase + v * y_ldc, x);
+  // NU voxels per thread per iteration: all loads are issued before the arithmetic
+  const long long chunk = (long long)NU * sp.vstride;
+  for (long long base = (long long)blockIdx.x * chunk; base < nvox; base += (long long)gridDim.x * chunk) {
+    Raw8<T> d[NU], x[NU];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float t = fmaf(x[j], f[j].x, f[j].y);
-      const float dv = t > 0.f ? d[j] : d[j] * f[j].z;
-      const float xhat = (x[j] - mr[j].x) * mr[j].y;
-      d[j] = k1[j] * (dv - m1[j] - xhat * m2[j]);
+    for (int u = 0; u < NU; ++u) {
+      const long long vv = min(base + sp.vlane + (long long)u * sp.vstride, nvox - 1);
+      d[u].load(dbase + vv * d_ldc);
+      x[u].load(ybase + vv * y_ldc);
     }
-    store8<T>(obase + v * dy_ldc, d);
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const long long vv = base + sp.vlane + (long long)u * sp.vstride;
+      if (vv < nvox) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xv = x[u].get(j), dd = d[u].get(j);
+          const float t = fmaf(xv, f[j].x, f[j].y);
+          const float dv = t > 0.f ? dd : dd * f[j].z;
+          const float xhat = (xv - mr[j].x) * mr[j].y;
+          o[j] = k1[j] * (dv - m1[j] - xhat * m2[j]);
+        }
+        store8<T>(obase + vv * dy_ldc, o);
+      }
+    }
   }
 }
 
@@ -273,10 +336,13 @@ int in_bwd_apply(const void* dact, int d_ldc, int d_coff, const void* y, int y_l
                   dy_ldc % 8 == 0 && dy_coff % 8 == 0,
               "in_bwd_apply: channel counts/strides must be multiples of 8 (C=%d)", C);
   dim3 grid = span_grid(nvox, B, C);
-  MTB_DISPATCH_DTYPE(dtype, T, (in_bwd_apply_kernel<T><<<grid, NT, 0, s>>>(
-      reinterpret_cast<const T*>(dact), d_ldc, d_coff, reinterpret_cast<const T*>(y), y_ldc, y_coff,
-      reinterpret_cast<T*>(dy), dy_ldc, dy_coff, nvox, B, C, reinterpret_cast<const float4*>(xform),
-      reinterpret_cast<const float2*>(meanrstd), gamma, red, dgamma, dbeta)));
+#define MTB_IN_APPLY(NU_)                                                                                        \
+  MTB_DISPATCH_DTYPE(dtype, T, (in_bwd_apply_kernel<T, NU_><<<grid, NT, 0, s>>>(                                 \
+      reinterpret_cast<const T*>(dact), d_ldc, d_coff, reinterpret_cast<const T*>(y), y_ldc, y_coff,             \
+      reinterpret_cast<T*>(dy), dy_ldc, dy_coff, nvox, B, C, reinterpret_cast<const float4*>(xform),             \
+      reinterpret_cast<const float2*>(meanrstd), gamma, red, dgamma, dbeta)))
+  switch (norm_nu()) { case 1: MTB_IN_APPLY(1); break; case 2: MTB_IN_APPLY(2); break; default: MTB_IN_APPLY(4); }
+#undef MTB_IN_APPLY
   return check_launch("in_bwd_apply");
 }
 

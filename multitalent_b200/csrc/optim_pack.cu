@@ -140,10 +140,41 @@ __global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, int C, long
   }
 }
 
+// few input channels (the network input: C = 1 padded to 16): one thread per voxel, coalesced plane reads, one 16-byte
+// vector store per 8 output channels -- a pure streaming pass instead of 32x32 transposes of mostly padding
+template <typename T, int CMAX>
+__global__ void ncdhw_to_ndhwc_small_kernel(const float* __restrict__ src, int C, long long nvox, T* __restrict__ dst,
+                                            int ldc, int coff, int Cp) {
+  const int b = blockIdx.y;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (long long)gridDim.x * blockDim.x) {
+    float x[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) x[c] = c < C ? src[((long long)b * C + c) * nvox + v] : 0.f;
+    T* o = dst + ((long long)b * nvox + v) * ldc + coff;
+    for (int c0 = 0; c0 < Cp; c0 += 8) {
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = 0.f;
+      if (c0 < CMAX) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < CMAX) y[j] = x[(c0 + j) % CMAX];
+      }
+      store8<T>(o + c0, y);
+    }
+  }
+}
+
 int ncdhw_to_ndhwc(const float* src, int B, int C, long long nvox, void* dst, int dtype, int ldc, int coff, int Cp,
                    cudaStream_t s) {
   MTB_REQUIRE(C <= Cp && coff + Cp <= ldc, "ncdhw_to_ndhwc: C=%d Cp=%d coff=%d ldc=%d", C, Cp, coff, ldc);
   if (nvox == 0 || B == 0) return MTB200_OK;
+  if (C <= 8 && Cp % 8 == 0 && ldc % 8 == 0 && coff % 8 == 0) {
+    dim3 grid((unsigned)min((nvox + 255) / 256, (long long)num_sms() * 16), B);
+    MTB_DISPATCH_DTYPE(dtype, T, (ncdhw_to_ndhwc_small_kernel<T, 8><<<grid, 256, 0, s>>>(
+        src, C, nvox, reinterpret_cast<T*>(dst), ldc, coff, Cp)));
+    return check_launch("ncdhw_to_ndhwc");
+  }
   dim3 grid((unsigned)((nvox + 31) / 32), (Cp + 31) / 32, B), block(32, 8);
   MTB_DISPATCH_DTYPE(dtype, T, (ncdhw_to_ndhwc_kernel<T><<<grid, block, 0, s>>>(src, C, nvox, reinterpret_cast<T*>(dst),
                                                                                  ldc, coff, Cp)));

@@ -23,7 +23,6 @@ using namespace um;
 
 constexpr int WL_THREADS = 192;
 constexpr int WL_MAX_STAGES = 6;
-constexpr int WL_XROWS = 130;
 constexpr int WL_BN = 32;
 
 struct WgradLineParams {
@@ -37,6 +36,7 @@ struct WgradLineParams {
   int stage_bytes, stage_tx, stages;
   int ndz, dz0;
   int nhr, hlen, ntw;
+  int wt, nkk;               // w tile (128 / 64 / 32 voxels of one line) and its number of 16-voxel K steps
   long long units;
   int lut[27];               // [dz+1][dy+1][dx+1] -> weight slice or -1
   int is_f16;
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __
 
   constexpr uint32_t NCOLS = 3 * WL_BN;
   constexpr uint32_t YROWB = WL_BN * 2;           // bytes per dY row
-  constexpr uint32_t YLINE = 128 * YROWB;         // one dY line
+  const uint32_t YLINE = (uint32_t)p.wt * YROWB;  // one dY line
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
   const int c0 = blockIdx.y * p.kcw;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __
       const int d = (int)(t % p.D);
       const int b = (int)(t / p.D);
       const int hs = hr * p.hlen, he = min(p.H, hs + p.hlen);
-      const int w0 = twi * 128;
+      const int w0 = twi * p.wt;
       for (int hp = hs; hp < he; ++hp, ++sc) {
         const uint32_t slot = sc % (uint32_t)p.stages;
         mbar_wait(&st_empty[slot], ((sc / (uint32_t)p.stages) & 1u) ^ 1u);
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __
     const uint32_t s16 = __shfl_sync(0xffffffffu, (smem_u32(dsmem) & 0x3FFFFu) >> 4, 0);
     const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, xline16 = (uint32_t)p.xline_bytes >> 4;
     const uint32_t y16 = (uint32_t)p.ybase >> 4;
-    const int ndz = p.ndz;
+    const int ndz = p.ndz, nkk = p.nkk;
     uint32_t sc = 0;
     for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
       const int hr = (int)(u % p.nhr);
@@ -127,8 +127,10 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __
             if (z < ndz) {
 #pragma unroll
               for (int kk = 0; kk < 8; ++kk)
-                umma_f16(tmem_u + (uint32_t)z * NCOLS, wl_desc64(hi_a, a_s + (uint32_t)z * xline16 + (uint32_t)(kk * ROWB)),
-                         wl_desc64(hi_b, b_s + (uint32_t)(kk * YROWB)), idesc, kk ? 1u : acc);
+                if (kk < nkk)
+                  umma_f16(tmem_u + (uint32_t)z * NCOLS,
+                           wl_desc64(hi_a, a_s + (uint32_t)z * xline16 + (uint32_t)(kk * ROWB)),
+                           wl_desc64(hi_b, b_s + (uint32_t)(kk * YROWB)), idesc, kk ? 1u : acc);
             }
           }
           umma_commit(&st_empty[slot]);
@@ -188,8 +190,9 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   if (p.Do != p.Di || p.Ho != p.Hi || p.Wo != p.Wi || p.Dof != p.Do || p.Hof != p.Ho || p.Wof != p.Wo)
     return MTB200_ERR_UNSUPPORTED;
   if (p.Cin != 16 && p.Cin % 32 != 0) return MTB200_ERR_UNSUPPORTED;
-  if (p.Cin > 64 || p.Cout % WL_BN || p.Cout > 64) return MTB200_ERR_UNSUPPORTED;
-  if (p.Wo < 72 || p.Ho < 4 || p.ntaps < 9) return MTB200_ERR_UNSUPPORTED;
+  if (p.Cin > 128 || p.Cout % WL_BN || p.Cout > 64) return MTB200_ERR_UNSUPPORTED;  // every (chunk, Cout block) pair
+                                                                                     // re-streams both operands
+  if (p.Wo < 48 || p.Ho < 4 || p.ntaps < 9) return MTB200_ERR_UNSUPPORTED;
 
   static WgradLineParams q;
   memset(&q, 0, sizeof(q));
@@ -207,18 +210,21 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   q.kcw = p.Cin < 32 ? p.Cin : 32;
   const int nchunk = p.Cin / q.kcw;
   const int rowb = q.kcw * 2;
-  q.xline_bytes = wl_align1k((long long)WL_XROWS * rowb);
+  q.wt = p.Wo > 64 ? 128 : 64;
+  q.nkk = q.wt / 16;
+  const int xrows = q.wt + 2;
+  q.xline_bytes = wl_align1k((long long)(xrows + 8) * rowb);  // + rows touched by the unused shifted blocks
   q.ybase = q.xline_bytes * q.ndz;
-  const int ybytes = 3 * 128 * WL_BN * 2;
-  q.stage_bytes = q.ybase + ybytes;
-  q.stage_tx = q.ndz * WL_XROWS * rowb + ybytes;
+  const int ybytes = 3 * q.wt * WL_BN * 2;
+  q.stage_bytes = wl_align1k(q.ybase + ybytes);
+  q.stage_tx = q.ndz * xrows * rowb + ybytes;
   q.stages = min(WL_MAX_STAGES, (224 * 1024) / q.stage_bytes);
   if (q.stages < 2) return MTB200_ERR_UNSUPPORTED;
   {
     cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.Di, (cuuint64_t)p.B};
     cuuint64_t strides[4] = {(cuuint64_t)p.in_ldc * 2, (cuuint64_t)p.Wi * p.in_ldc * 2,
                              (cuuint64_t)p.Hi * p.Wi * p.in_ldc * 2, (cuuint64_t)p.Di * p.Hi * p.Wi * p.in_ldc * 2};
-    cuuint32_t box[5] = {(cuuint32_t)q.kcw, (cuuint32_t)WL_XROWS, 1, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)q.kcw, (cuuint32_t)xrows, 1, 1, 1};
     if (!umma_encode_map(&q.x_map, p.dtype, 5, (uint8_t*)p.x + (size_t)p.in_coff * 2, dims, strides, box, rowb))
       return MTB200_ERR_CUDA;
   }
@@ -227,7 +233,7 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
     cuuint64_t strides[4] = {(cuuint64_t)p.out_ldc * 2, (cuuint64_t)p.Wof * p.out_ldc * 2,
                              (cuuint64_t)p.Hof * p.Wof * p.out_ldc * 2,
                              (cuuint64_t)p.Dof * p.Hof * p.Wof * p.out_ldc * 2};
-    cuuint32_t box[5] = {(cuuint32_t)WL_BN, 128, 3, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)WL_BN, (cuuint32_t)q.wt, 3, 1, 1};
     if (!umma_encode_map(&q.dy_map, p.dtype, 5, (uint8_t*)p.dy + (size_t)p.out_coff * 2, dims, strides, box, WL_BN * 2))
       return MTB200_ERR_CUDA;
   }
@@ -235,7 +241,7 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   q.B = p.B; q.D = p.Do; q.H = p.Ho; q.W = p.Wo;
   q.Cin = p.Cin; q.Cout = p.Cout;
   q.is_f16 = p.dtype == MTB200_F16;
-  q.ntw = (p.Wo + 127) / 128;
+  q.ntw = (p.Wo + q.wt - 1) / q.wt;
   const int sms = num_sms();
   {
     // split H into ranges so that every persistent CTA gets (almost) the same number of steps

@@ -191,6 +191,9 @@ WGRAD_LINE_CASES = [
     (30, 60, (3, 3, 3), (1, 3, 8, 128), 0),      # two Cout blocks (grid.z)
     (20, 24, (1, 3, 3), (1, 3, 24, 96), 0),      # 9 taps, one staged plane
     (30, 30, (3, 3, 3), (2, 40, 16, 128), 0),    # more units than SMs: persistent CTAs walk several units
+    (60, 60, (3, 3, 3), (1, 6, 10, 64), 0),      # 64-wide lines (4 K steps), 2 chunks x 2 Cout blocks
+    (120, 60, (3, 3, 3), (1, 4, 8, 64), 60),     # 4 chunks
+    (60, 60, (3, 3, 3), (1, 3, 6, 56), 0),       # ragged 64-wide tile
 ]
 
 
