@@ -79,8 +79,9 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
 // ---------------------------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int UM_MAX_STAGES = 8;
-constexpr int UM_THREADS = 192;
+constexpr int UM_MAX_STAGES = 12;
+constexpr int UM_THREADS = 192;       // weight-gradient kernel: producer, MMA, 4 epilogue warps
+constexpr int UMC_THREADS = 192;      // conv kernel: producer, MMA, 4 epilogue warps (two CTAs per SM when N <= 128)
 
 struct UmmaConvParams {
   CUtensorMap a_maps[8];
@@ -98,17 +99,24 @@ struct UmmaConvParams {
   int tap_coff[MTB200_MAX_TAPS][3];
   int tap_widx[MTB200_MAX_TAPS];
   int nkc, KC, BN, stages, tmem_cols;
+  int ny, ncombo, ctas_per_combo;   // N tiles, (N tile, group) combinations, persistent CTAs per combination
+  long long ntiles;                 // spatial tiles (all batches)
   int accumulate, is_f16;
 };
 
+// Persistent: CTA c owns the (N tile, tap group) combination c % ncombo and walks the spatial tiles c / ncombo,
+// c / ncombo + ctas_per_combo, ...  Two TMEM accumulators alternate, so the epilogue warps drain tile k while the
+// TMA / MMA warps are already on tile k+1; barrier setup, TMEM allocation and descriptor fetch are paid once per CTA.
+// Two CTAs share an SM when the N tile is <= 128 (2 x 2 x BN <= 512 TMEM columns): their MMA-issue loops interleave,
+// which hides the per-stage barrier round trip of the single issuing thread.
 template <typename T>
-__global__ void __launch_bounds__(UM_THREADS, 1) conv_taps_umma_kernel(const __grid_constant__ UmmaConvParams p) {
+__global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __grid_constant__ UmmaConvParams p) {
   extern __shared__ uint8_t dsmem_raw[];
   __shared__ __align__(8) uint64_t full_bar[UM_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[UM_MAX_STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_sum[256], s_sq[256];
+  __shared__ float s_sum[256], s_sq[256], s_bias[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
@@ -116,30 +124,24 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_taps_umma_kernel(const __g
   const uint32_t a_bytes = 128u * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
   const uint32_t stage_bytes = ((a_bytes + b_bytes + 1023u) / 1024u) * 1024u;
 
-  // tile coordinates
-  int t = blockIdx.x;
-  const int tw = t % p.tiles_w; t /= p.tiles_w;
-  const int th = t % p.tiles_h; t /= p.tiles_h;
-  const int td = t % p.tiles_d;
-  const int b = t / p.tiles_d;
-  const int d0 = td * p.bd, h0 = th * p.bh, w0 = tw * p.bw;
-  const int n0 = blockIdx.y * p.BN;
-  const int g = blockIdx.z;
+  const int combo = blockIdx.x % p.ncombo;
+  const int nb = combo % p.ny, g = combo / p.ny;
+  const long long tile0 = blockIdx.x / p.ncombo;
+  const int n0 = nb * p.BN;
   const int tap_begin = p.group_tap_begin[g], tap_end = p.group_tap_begin[g + 1];
   const int niter = (tap_end - tap_begin) * p.nkc;
+  const long long tiles_per_b = (long long)p.tiles_d * p.tiles_h * p.tiles_w;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(&tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 256; i += UM_THREADS) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
-                 "r"((uint32_t)p.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  for (int i = threadIdx.x; i < 256; i += UMC_THREADS) {
+    s_sum[i] = 0.f; s_sq[i] = 0.f;
+    s_bias[i] = (p.bias && i < p.BN) ? p.bias[n0 + i] : 0.f;
   }
+  if (warp == 1) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -147,148 +149,164 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_taps_umma_kernel(const __g
 
   if (warp == 0) {
     // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
-    {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < niter; ++it) {
-        const int tp = tap_begin + it / p.nkc;
-        const int kc = it % p.nkc;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        if (elect_one()) {
-          uint8_t* sa = dsmem + (size_t)stage * stage_bytes;
-          uint8_t* sb = sa + a_bytes;
-          mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-          tma_load_5d(sa, &p.a_maps[p.tap_map[tp]], &full_bar[stage], kc * p.KC, w0 + p.tap_coff[tp][2],
-                      h0 + p.tap_coff[tp][1], d0 + p.tap_coff[tp][0], b);
-          tma_load_3d(sb, &p.w_map, &full_bar[stage], kc * p.KC, n0, p.tap_widx[tp]);
+    if (niter > 0) {
+      uint32_t gi = 0;  // global pipeline iteration of this CTA
+      for (long long tile = tile0; tile < p.ntiles; tile += p.ctas_per_combo) {
+        long long t = tile;
+        const int tw = (int)(t % p.tiles_w); t /= p.tiles_w;
+        const int th = (int)(t % p.tiles_h); t /= p.tiles_h;
+        const int td = (int)(t % p.tiles_d);
+        const int b = (int)(t / p.tiles_d);
+        const int d0 = td * p.bd, h0 = th * p.bh, w0 = tw * p.bw;
+        int tp = tap_begin, kc = 0;
+        for (int it = 0; it < niter; ++it, ++gi) {
+          const uint32_t stage = gi % (uint32_t)p.stages;
+          mbar_wait(&empty_bar[stage], ((gi / (uint32_t)p.stages) & 1u) ^ 1u);
+          if (elect_one()) {
+            uint8_t* sa = dsmem + (size_t)stage * stage_bytes;
+            mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+            tma_load_5d(sa, &p.a_maps[p.tap_map[tp]], &full_bar[stage], kc * p.KC, w0 + p.tap_coff[tp][2],
+                        h0 + p.tap_coff[tp][1], d0 + p.tap_coff[tp][0], b);
+            tma_load_3d(sa + a_bytes, &p.w_map, &full_bar[stage], kc * p.KC, n0, p.tap_widx[tp]);
+          }
+          __syncwarp();
+          if (++kc == p.nkc) { kc = 0; ++tp; }
         }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: warp-uniform loop, one elected lane issues (keeps the descriptors in uniform registers) =====
-    {
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues (descriptors stay in uniform registers) =====
+    if (niter > 0) {
       // instruction descriptor: D=f32, A/B = bf16 or f16, both K-major, N, M=128
       const uint32_t fmt = p.is_f16 ? 0u : 1u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t s0 = __shfl_sync(0xffffffffu, smem_u32(dsmem), 0);
+      const uint32_t s16 = __shfl_sync(0xffffffffu, (smem_u32(dsmem) & 0x3FFFFu) >> 4, 0);
+      const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+      const uint32_t hi = (((8u * row_bytes) >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+      const uint32_t stage16 = stage_bytes >> 4, a16 = a_bytes >> 4;
       const int ksteps = p.KC / 16;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < niter; ++it) {
-        mbar_wait(&full_bar[stage], phase);
+      uint32_t gi = 0, k = 0;
+      for (long long tile = tile0; tile < p.ntiles; tile += p.ctas_per_combo, ++k) {
+        const uint32_t buf = k & 1u;
+        mbar_wait(&acc_empty[buf], ((k >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t sa = s0 + (uint32_t)stage * stage_bytes;
-        const uint32_t sb = sa + a_bytes;
-        if (elect_one()) {
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t da = make_kmajor_desc(sa + k * 32, row_bytes);
-            const uint64_t db = make_kmajor_desc(sb + k * 32, row_bytes);
-            umma_f16(tmem_u, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        const uint32_t dcol = tmem_u + buf * (uint32_t)p.BN;
+        for (int it = 0; it < niter; ++it, ++gi) {
+          const uint32_t stage = gi % (uint32_t)p.stages;
+          mbar_wait(&full_bar[stage], (gi / (uint32_t)p.stages) & 1u);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = s16 + stage * stage16;
+            const uint32_t sb = sa + a16;
+            for (int ks = 0; ks < ksteps; ++ks)
+              umma_f16(dcol, ((uint64_t)hi << 32) | (uint64_t)(sa + 2u * ks), ((uint64_t)hi << 32) | (uint64_t)(sb + 2u * ks),
+                       idesc, (it > 0 || ks > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once the MMAs above have read it
+            if (it == niter - 1) umma_commit(&acc_full[buf]);  // accumulator complete
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once the MMAs above have read it
+          __syncwarp();
         }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
-      if (elect_one()) umma_commit(&tmem_full_bar);  // accumulator complete
-      __syncwarp();
     }
   } else {
     // ===== epilogue: warps 2..5; warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
     const int q = warp & 3;
     const int row = q * 32 + lane;  // row of the tile == TMEM lane
     const int rw = row % p.bw, rh = (row / p.bw) % p.bh, rd = row / (p.bw * p.bh);
-    const int od = d0 + rd, oh = h0 + rh, ow = w0 + rw;
-    const bool valid = od < p.Do && oh < p.Ho && ow < p.Wo;
     T* out = reinterpret_cast<T*>(p.out);
-    const long long ovox = (((long long)b * p.Dof + (od * p.os[0] + p.group_ooff[g][0])) * p.Hof +
-                            (oh * p.os[1] + p.group_ooff[g][1])) * p.Wof + (ow * p.os[2] + p.group_ooff[g][2]);
-    T* orow = out + ovox * p.out_ldc + p.out_coff + n0;
-    if (niter > 0) {
-      mbar_wait(&tmem_full_bar, 0);
-      tc_fence_after();
-    }
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
-      uint32_t r[16];
-      float v[16];
+    const bool want_stats = p.stats != nullptr;
+    uint32_t k = 0;
+    for (long long tile = tile0; tile < p.ntiles; tile += p.ctas_per_combo, ++k) {
+      long long t = tile;
+      const int tw = (int)(t % p.tiles_w); t /= p.tiles_w;
+      const int th = (int)(t % p.tiles_h); t /= p.tiles_h;
+      const int td = (int)(t % p.tiles_d);
+      const int b = (int)(t / p.tiles_d);
+      const int od = td * p.bd + rd, oh = th * p.bh + rh, ow = tw * p.bw + rw;
+      const bool valid = od < p.Do && oh < p.Ho && ow < p.Wo;
+      const long long ovox = (((long long)b * p.Dof + (od * p.os[0] + p.group_ooff[g][0])) * p.Hof +
+                              (oh * p.os[1] + p.group_ooff[g][1])) * p.Wof + (ow * p.os[2] + p.group_ooff[g][2]);
+      T* orow = out + ovox * p.out_ldc + p.out_coff + n0;
+      const uint32_t buf = k & 1u;
+      const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.BN;
       if (niter > 0) {
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        mbar_wait(&acc_full[buf], (k >> 1) & 1u);
+        tc_fence_after();
       }
-      if (p.bias) {
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        float v[16];
+        if (niter > 0) {
+          uint32_t r[16];
+          tmem_ld16(tcol + (uint32_t)c0, r);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + n0 + c0 + j);
-      }
-      if (valid) {
-        if (p.accumulate) {
-          float o[8];
-          load8<T>(orow + c0, o);
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
+        } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += o[j];
-          load8<T>(orow + c0 + 8, o);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[8 + j] += o[j];
+          for (int j = 0; j < 16; ++j) v[j] = s_bias[c0 + j];
         }
-        float lo[8], hi[8];
+        if (valid) {
+          if (p.accumulate) {
+            float o[8];
+            load8<T>(orow + c0, o);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
-        store8<T>(orow + c0, lo);
-        store8<T>(orow + c0 + 8, hi);
-      }
-      if (p.stats) {
-        // column sums over the 32 rows of this warp: transposing butterfly (16 shuffles per statistic)
-        float s[16], ss[16];
+            for (int j = 0; j < 8; ++j) v[j] += o[j];
+            load8<T>(orow + c0 + 8, o);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float x = valid ? Traits<T>::round(v[j]) : 0.f;
-          s[j] = x;
-          ss[j] = x * x;
+            for (int j = 0; j < 8; ++j) v[8 + j] += o[j];
+          }
+          float lo[8], hi8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi8[j] = v[8 + j]; }
+          store8<T>(orow + c0, lo);
+          store8<T>(orow + c0 + 8, hi8);
         }
+        if (want_stats) {
+          // column sums over the 32 rows of this warp: transposing butterfly (16 shuffles per statistic)
+          float sv[16], ss[16];
 #pragma unroll
-        for (int off = 16, w = 16; off >= 2; off >>= 1, w >>= 1) {
-          const bool up = (lane & off) != 0;
-#pragma unroll
-          for (int j = 0; j < w / 2; ++j) {
-            const float send_s = up ? s[j] : s[j + w / 2];
-            const float send_q = up ? ss[j] : ss[j + w / 2];
-            const float rs = __shfl_xor_sync(0xffffffffu, send_s, off);
-            const float rq = __shfl_xor_sync(0xffffffffu, send_q, off);
-            s[j] = (up ? s[j + w / 2] : s[j]) + rs;
-            ss[j] = (up ? ss[j + w / 2] : ss[j]) + rq;
+          for (int j = 0; j < 16; ++j) {
+            const float x = valid ? Traits<T>::round(v[j]) : 0.f;
+            sv[j] = x;
+            ss[j] = x * x;
+          }
+          warp_colsum16(sv, lane);
+          warp_colsum16(ss, lane);
+          if ((lane & 1) == 0) {
+            const int col = colsum16_column(lane);
+            atomicAdd(&s_sum[c0 + col], sv[0]);
+            atomicAdd(&s_sq[c0 + col], ss[0]);
           }
         }
-        s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
-        ss[0] += __shfl_xor_sync(0xffffffffu, ss[0], 1);
-        if ((lane & 1) == 0) {
-          const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-          atomicAdd(&s_sum[c0 + col], s[0]);
-          atomicAdd(&s_sq[c0 + col], ss[0]);
+      }
+      if (niter > 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
+      if (want_stats) {
+        // flush the per-(b, channel) partials when this CTA moves on to another sample (or is done)
+        const long long next = tile + p.ctas_per_combo;
+        if (next >= p.ntiles || next / tiles_per_b != tile / tiles_per_b) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int c = threadIdx.x - 64; c < p.BN; c += 128) {
+            if (s_sum[c] != 0.f || s_sq[c] != 0.f) {
+              double* st = p.stats + ((long long)b * p.Cout + n0 + c) * 2;
+              atomicAdd(st, (double)s_sum[c]);
+              atomicAdd(st + 1, (double)s_sq[c]);
+              s_sum[c] = 0.f;
+              s_sq[c] = 0.f;
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       }
     }
-    tc_fence_before();
   }
   __syncthreads();
-  if (p.stats) {
-    for (int c = threadIdx.x; c < p.BN; c += UM_THREADS) {
-      if (s_sum[c] != 0.f || s_sq[c] != 0.f) {
-        double* st = p.stats + ((long long)b * p.Cout + n0 + c) * 2;
-        atomicAdd(st, (double)s_sum[c]);
-        atomicAdd(st + 1, (double)s_sq[c]);
-      }
-    }
-  }
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
-                 : "memory");
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -352,7 +370,7 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
       if (p.Cout % c == 0) { q.BN = c; break; }
   }
   q.tmem_cols = 32;
-  while (q.tmem_cols < q.BN) q.tmem_cols *= 2;
+  while (q.tmem_cols < 2 * q.BN) q.tmem_cols *= 2;  // two accumulators (tile k drains while tile k+1 accumulates)
   // brick: powers of two with product 128 minimising the number of tiles (ties: widest in w)
   long long best = -1;
   for (int bw = 128; bw >= 1; bw >>= 1)
@@ -422,17 +440,25 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
   q.is_f16 = p.dtype == MTB200_F16;
 
   const int stage_bytes = ((128 * row_bytes + q.BN * row_bytes + 1023) / 1024) * 1024;
-  const int budget = 100 * 1024;
+  const int per_sm = q.tmem_cols <= 256 ? 2 : 1;  // CTAs per SM (TMEM: 512 columns per SM)
+  const int budget = per_sm == 2 ? 100 * 1024 : 200 * 1024;
   q.stages = max(2, min(UM_MAX_STAGES, budget / stage_bytes));
-  const int smem = q.stages * stage_bytes + 1024;
-  dim3 grid((unsigned)ntiles, p.Cout / q.BN, p.ngroups);
+  int smem = q.stages * stage_bytes + 1024;
+  if (per_sm == 1) smem = max(smem, 116 * 1024);
+  q.ntiles = ntiles;
+  q.ny = p.Cout / q.BN;
+  q.ncombo = q.ny * p.ngroups;
+  const int slots = num_sms() * per_sm;
+  if (q.ncombo > slots) { set_error("conv_taps(umma): %d (N tile, group) combinations exceed the CTA slots", q.ncombo); return MTB200_ERR_UNSUPPORTED; }
+  q.ctas_per_combo = (int)min((long long)(slots / q.ncombo), ntiles);
+  dim3 grid((unsigned)(q.ctas_per_combo * q.ncombo), 1, 1);
   cudaError_t e;
   if (p.dtype == MTB200_BF16) {
     e = cudaFuncSetAttribute(conv_taps_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) conv_taps_umma_kernel<__nv_bfloat16><<<grid, UM_THREADS, smem, s>>>(q);
+    if (e == cudaSuccess) conv_taps_umma_kernel<__nv_bfloat16><<<grid, UMC_THREADS, smem, s>>>(q);
   } else {
     e = cudaFuncSetAttribute(conv_taps_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) conv_taps_umma_kernel<__half><<<grid, UM_THREADS, smem, s>>>(q);
+    if (e == cudaSuccess) conv_taps_umma_kernel<__half><<<grid, UMC_THREADS, smem, s>>>(q);
   }
   if (e != cudaSuccess) { set_error("conv_taps(umma): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
   return check_launch("conv_taps_umma");

@@ -122,12 +122,14 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __
           const uint32_t a_s = (s16 + slot * stage16) | lbo_a;
           const uint32_t b_s = (s16 + slot * stage16 + y16) | lbo_b;
           const uint32_t acc = sc > 0 ? 1u : 0u;
+          // kk-major order: consecutive MMAs go to DIFFERENT accumulators (dz), so they pipeline in the tensor core
+          // instead of each waiting for the previous accumulate into the same TMEM columns
 #pragma unroll
-          for (int z = 0; z < 3; ++z) {
-            if (z < ndz) {
+          for (int kk = 0; kk < 8; ++kk) {
+            if (kk < nkk) {
 #pragma unroll
-              for (int kk = 0; kk < 8; ++kk)
-                if (kk < nkk)
+              for (int z = 0; z < 3; ++z)
+                if (z < ndz)
                   umma_f16(tmem_u + (uint32_t)z * NCOLS,
                            wl_desc64(hi_a, a_s + (uint32_t)z * xline16 + (uint32_t)(kk * ROWB)),
                            wl_desc64(hi_b, b_s + (uint32_t)(kk * YROWB)), idesc, kk ? 1u : acc);
