@@ -139,6 +139,24 @@ int mtb200_in_bwd_apply(const void* dact, int32_t d_ldc, int32_t d_coff, const v
                         float* dgamma, float* dbeta, void* stream);
 /* dv = dact * lrelu'(f(y))  only (no norm): used for the second LeakyReLU of a residual block */
 int mtb200_lrelu_bwd(const void* dact, const void* act, void* dv, int32_t dtype, int64_t n, float slope, void* stream);
+/* backward of the tail of BasicResidualBlock.forward (custom_modules/conv_blocks.py:205-213, `out += residual;
+ * nonlin2(out)`): dv = dact * lrelu'(act) is written (acc = 0) or added (acc = 1) to the gradient slices of the two
+ * summands; NDHWC slices [nrows][ldc] + coff of C channels each; either destination may be NULL. */
+int mtb200_residual_bwd(const void* dact, int32_t d_ldc, int32_t d_coff, const void* act, int32_t a_ldc, int32_t a_coff,
+                        void* dst0, int32_t ldc0, int32_t coff0, int32_t acc0, void* dst1, int32_t ldc1, int32_t coff1,
+                        int32_t acc1, int32_t dtype, int64_t nrows, int32_t C, float slope, void* stream);
+
+/* ---- a11: generic nnU-Net loss, softmax + cross entropy + soft Dice; replaces DC_and_CE_loss.forward
+ *      (training/loss_functions/dice_loss.py:488-545, :155-195, :100-152; crossentropy.py:4-11) and its autograd ------- */
+/* pass 1: stats[b][c][3] doubles += {sum p_c*[y==c], sum p_c, sum [y==c]}, ce_sum[b] += sum -log p_y over the voxels of
+ * sample b; p = softmax over the C real classes of the NDHWC logits [B][nvox][ldc]; target = float label map [B][nvox]. */
+int mtb200_dcce_stats(const void* logits, int32_t dtype, int32_t ldc, int32_t C, int32_t Cp, const float* target, int32_t B,
+                      int64_t nvox, double* stats, double* ce_sum, void* stream);
+/* pass 2: dz[b][v][k] = gscale[0] * ( ce_weight * (p_k - [y==k]) + p_k * (G_k - sum_c G_c p_c) ),
+ * G_c = coef[b][c][0] * [y==c] + coef[b][c][1]  (the Dice term's d/dp, computed by the caller from the pooled stats) */
+int mtb200_dcce_bwd(const void* logits, int32_t dtype, int32_t ldc, int32_t C, int32_t Cp, const float* target, int32_t B,
+                    int64_t nvox, const float* coef, float ce_weight, const float* gscale, void* dz, int32_t dz_ldc,
+                    void* stream);
 
 /* ---- a9/a10: MultiTalent multi-head loss (sigmoid + BCE + pooled soft Dice); replaces the python loop at
  *      MultiTalent_Trainer_DDP.py:567-594 (stats), :596-606 (Dice), and its autograd ------------------------------ */

@@ -83,6 +83,10 @@ SIGNATURES = {
     "mtb200_in_bwd_apply": [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp,
                             _vp, _vp, _vp, _vp],
     "mtb200_lrelu_bwd": [_vp, _vp, _vp, _i32, _i64, _f32, _vp],
+    "mtb200_residual_bwd": [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i64,
+                            _i32, _f32, _vp],
+    "mtb200_dcce_stats": [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _vp, _vp, _vp],
+    "mtb200_dcce_bwd": [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _vp, _f32, _vp, _vp, _i32, _vp],
     "mtb200_mt_loss_stats": [_vp, _i32, _i32, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp],
     "mtb200_mt_loss_finalize": [_vp, _vp, _vp, _i32, _i32, _i64, _f32, _f32, _vp, _vp, _vp],
     "mtb200_mt_loss_bwd": [_vp, _i32, _i32, _i32, _vp, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _vp],

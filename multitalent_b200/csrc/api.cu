@@ -53,6 +53,11 @@ int in_bwd_reduce(const void*, int, int, const void*, int, int, int, int, long l
 int in_bwd_apply(const void*, int, int, const void*, int, int, void*, int, int, int, int, long long, int, const float*,
                  const float*, const float*, const double*, float*, float*, cudaStream_t);
 int lrelu_bwd(const void*, const void*, void*, int, long long, float, cudaStream_t);
+int dcce_stats(const void*, int, int, int, int, const float*, int, long long, double*, double*, cudaStream_t);
+int dcce_bwd(const void*, int, int, int, int, const float*, int, long long, const float*, float, const float*, void*, int,
+             cudaStream_t);
+int residual_bwd(const void*, int, int, const void*, int, int, void*, int, int, int, void*, int, int, int, int, long long, int,
+                 float, cudaStream_t);
 int mt_loss_stats(const void*, int, int, int, const float*, int, long long, const uint64_t*, const uint64_t*, int,
                   double*, cudaStream_t);
 int mt_loss_finalize(const double*, const double*, const uint64_t*, int, int, long long, float, float, float*, float*,
@@ -159,6 +164,27 @@ int mtb200_in_bwd_apply(const void* dact, int32_t d_ldc, int32_t d_coff, const v
 int mtb200_lrelu_bwd(const void* dact, const void* act, void* dv, int32_t dtype, int64_t n, float slope, void* stream) {
   MTB_REQUIRE(dact && act && dv, "lrelu_bwd: null pointer");
   return lrelu_bwd(dact, act, dv, dtype, n, slope, STREAM(stream));
+}
+
+int mtb200_residual_bwd(const void* dact, int32_t d_ldc, int32_t d_coff, const void* act, int32_t a_ldc, int32_t a_coff,
+                        void* dst0, int32_t ldc0, int32_t coff0, int32_t acc0, void* dst1, int32_t ldc1, int32_t coff1,
+                        int32_t acc1, int32_t dtype, int64_t nrows, int32_t C, float slope, void* stream) {
+  MTB_REQUIRE(dact && act && (dst0 || dst1), "residual_bwd: null pointer");
+  return residual_bwd(dact, d_ldc, d_coff, act, a_ldc, a_coff, dst0, ldc0, coff0, acc0, dst1, ldc1, coff1, acc1, dtype,
+                      nrows, C, slope, STREAM(stream));
+}
+
+int mtb200_dcce_stats(const void* logits, int32_t dtype, int32_t ldc, int32_t C, int32_t Cp, const float* target, int32_t B,
+                      int64_t nvox, double* stats, double* ce_sum, void* stream) {
+  MTB_REQUIRE(logits && target && stats && ce_sum, "dcce_stats: null pointer");
+  return dcce_stats(logits, dtype, ldc, C, Cp, target, B, nvox, stats, ce_sum, STREAM(stream));
+}
+
+int mtb200_dcce_bwd(const void* logits, int32_t dtype, int32_t ldc, int32_t C, int32_t Cp, const float* target, int32_t B,
+                    int64_t nvox, const float* coef, float ce_weight, const float* gscale, void* dz, int32_t dz_ldc,
+                    void* stream) {
+  MTB_REQUIRE(logits && target && coef && gscale && dz, "dcce_bwd: null pointer");
+  return dcce_bwd(logits, dtype, ldc, C, Cp, target, B, nvox, coef, ce_weight, gscale, dz, dz_ldc, STREAM(stream));
 }
 
 int mtb200_mt_loss_stats(const void* logits, int32_t dtype, int32_t ldc, int32_t C, const float* target, int32_t B,

@@ -370,4 +370,65 @@ int lrelu_bwd(const void* dact, const void* act, void* dv, int dtype, long long 
   return check_launch("lrelu_bwd");
 }
 
+// ---- tail of a residual block, backward: dv = dact * lrelu'(act) fanned out to the two summands -----------------------
+// out = lrelu(f(a) + g(r))  =>  d f(a) = d g(r) = dact * (out > 0 ? 1 : slope); each destination is written or accumulated.
+template <typename T>
+__global__ void __launch_bounds__(NT) residual_bwd_kernel(const T* __restrict__ dact, int d_ldc, int d_coff,
+                                                          const T* __restrict__ act, int a_ldc, int a_coff, T* dst0,
+                                                          int ldc0, int coff0, int acc0, T* dst1, int ldc1, int coff1,
+                                                          int acc1, long long nrows, int C, float slope) {
+  const int G = C / 8;
+  const long long total = nrows * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i / G;
+    const int c = (int)(i % G) * 8;
+    float d[8], a[8];
+    load8<T>(dact + v * d_ldc + d_coff + c, d);
+    load8<T>(act + v * a_ldc + a_coff + c, a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = a[j] > 0.f ? d[j] : d[j] * slope;
+    if (dst0) {
+      float o[8];
+      T* q = dst0 + v * ldc0 + coff0 + c;
+      if (acc0) {
+        load8<T>(q, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += d[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = d[j];
+      }
+      store8<T>(q, o);
+    }
+    if (dst1) {
+      float o[8];
+      T* q = dst1 + v * ldc1 + coff1 + c;
+      if (acc1) {
+        load8<T>(q, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += d[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = d[j];
+      }
+      store8<T>(q, o);
+    }
+  }
+}
+
+int residual_bwd(const void* dact, int d_ldc, int d_coff, const void* act, int a_ldc, int a_coff, void* dst0, int ldc0,
+                 int coff0, int acc0, void* dst1, int ldc1, int coff1, int acc1, int dtype, long long nrows, int C,
+                 float slope, cudaStream_t s) {
+  MTB_REQUIRE(C % 8 == 0 && d_ldc % 8 == 0 && d_coff % 8 == 0 && a_ldc % 8 == 0 && a_coff % 8 == 0 && ldc0 % 8 == 0 &&
+                  coff0 % 8 == 0 && ldc1 % 8 == 0 && coff1 % 8 == 0,
+              "residual_bwd: channel counts/strides must be multiples of 8 (C=%d)", C);
+  const long long total = nrows * (C / 8);
+  if (total == 0) return MTB200_OK;
+  const int blocks = (int)min((long long)num_sms() * 16, (total + NT - 1) / NT);
+  MTB_DISPATCH_DTYPE(dtype, T, (residual_bwd_kernel<T><<<blocks, NT, 0, s>>>(
+      reinterpret_cast<const T*>(dact), d_ldc, d_coff, reinterpret_cast<const T*>(act), a_ldc, a_coff,
+      reinterpret_cast<T*>(dst0), ldc0, coff0, acc0, reinterpret_cast<T*>(dst1), ldc1, coff1, acc1, nrows, C, slope)));
+  return check_launch("residual_bwd");
+}
+
 }  // namespace mtb

@@ -466,24 +466,23 @@ class Engine:
             tape.closures.append(bwd)
         return y
 
-    def residual_act(self, tape: Optional[Tape], a: Feat, r: Feat, slope2=LRELU_SLOPE) -> Feat:
-        """out = LeakyReLU(f(a) + g(r)) -- tail of BasicResidualBlock.forward (conv_blocks.py:205-213)."""
-        out = self.materialize(a, res=r, slope2=slope2)
+    def residual_act(self, tape: Optional[Tape], a: Feat, r: Feat, slope2=LRELU_SLOPE, out: Optional[Feat] = None) -> Feat:
+        """out = LeakyReLU(f(a) + g(r)) -- tail of BasicResidualBlock.forward (conv_blocks.py:205-213).  `out` may be a
+        channel slice of a wider buffer (the skip half of a decoder concat buffer)."""
+        out = self.materialize(a, res=r, slope2=slope2, out=out)
         if tape is not None:
             def bwd():
                 if not tape.has_grad(out):
                     return
                 g, _ = tape.grad_feat(out)
-                n = out.buf.numel()
-                L.call("mtb200_lrelu_bwd", g.ptr(), out.ptr(), g.ptr(), L.dtype_enum(self.dtype), n, float(slope2),
-                       L.stream_ptr())
-                for t in (a, r):
-                    gt, have = tape.grad_feat(t)
-                    if have:
-                        gt.buf[..., gt.coff:gt.coff + gt.Cp] += g.buf[..., g.coff:g.coff + g.Cp]
-                    else:
-                        gt.buf[..., gt.coff:gt.coff + gt.Cp] = g.buf[..., g.coff:g.coff + g.Cp]
-                    tape.mark(t)
+                ga, have_a = tape.grad_feat(a)
+                gr, have_r = tape.grad_feat(r)
+                B = out.dims[0]
+                L.call("mtb200_residual_bwd", g.ptr(), g.ldc, g.coff, out.ptr(), out.ldc, out.coff,
+                       ga.ptr(), ga.ldc, ga.coff, int(have_a), gr.ptr(), gr.ldc, gr.coff, int(have_r),
+                       L.dtype_enum(self.dtype), B * out.nvox, out.Cp, float(slope2), L.stream_ptr())
+                tape.mark(a)
+                tape.mark(r)
             tape.closures.append(bwd)
         return out
 
