@@ -604,25 +604,31 @@ __global__ void __launch_bounds__(UM_THREADS, 1) wgrad_taps_umma_kernel(const __
                              ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t cbx_bytes = p.cbx * 2, cby_bytes = p.cby * 2;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t a0 = __shfl_sync(0xffffffffu, smem_u32(a_base), 0);
-      const uint32_t b0 = __shfl_sync(0xffffffffu, smem_u32(b_base), 0);
+      const uint32_t a0 = __shfl_sync(0xffffffffu, (smem_u32(a_base) & 0x3FFFFu) >> 4, 0);
+      const uint32_t b0 = __shfl_sync(0xffffffffu, (smem_u32(b_base) & 0x3FFFFu) >> 4, 0);
+      // descriptor words precomputed: hi = SBO | version | swizzle, lo = (address >> 4) | LBO << 16
+      const uint32_t lay_a = cbx_bytes == 128 ? 2u : (cbx_bytes == 64 ? 4u : 6u);
+      const uint32_t lay_b = cby_bytes == 128 ? 2u : (cby_bytes == 64 ? 4u : 6u);
+      const uint32_t hi_a = (((8u * cbx_bytes) >> 4) & 0x3FFFu) | (1u << 14) | (lay_a << 29);
+      const uint32_t hi_b = (((8u * cby_bytes) >> 4) & 0x3FFFu) | (1u << 14) | (lay_b << 29);
+      const uint32_t lbo_a = ((xblock_bytes >> 4) & 0x3FFFu) << 16, lbo_b = ((yblock_bytes >> 4) & 0x3FFFu) << 16;
+      const uint32_t astage16 = a_stage_bytes >> 4, bstage16 = b_stage_bytes >> 4;
+      const uint32_t ka = cbx_bytes, kb = cby_bytes;  // 16 voxels further along K = 16 * row bytes = (row bytes) x 16 B
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int br = 0; br < nbricks; ++br) {
         mbar_wait(&b_full[bs], bph);
-        const uint32_t sb = b0 + (uint32_t)bs * b_stage_bytes;
+        const uint32_t sb = (b0 + (uint32_t)bs * bstage16) | lbo_b;
         for (int tl = 0; tl < ntl; ++tl) {
           mbar_wait(&a_full[as], aph);
           tc_fence_after();
-          const uint32_t sa = a0 + (uint32_t)as * a_stage_bytes;
+          const uint32_t sa = (a0 + (uint32_t)as * astage16) | lbo_a;
           if (elect_one()) {
+            const uint32_t dcol = tmem_u + (uint32_t)(tl * p.BN);
 #pragma unroll
-            for (int k = 0; k < WG_KB / 16; ++k) {
-              // 16 voxels = two 8-row groups further along K
-              const uint64_t da = make_mnmajor_desc(sa + k * 2 * 8 * cbx_bytes, cbx_bytes, xblock_bytes);
-              const uint64_t db = make_mnmajor_desc(sb + k * 2 * 8 * cby_bytes, cby_bytes, yblock_bytes);
-              umma_f16(tmem_u + (uint32_t)(tl * p.BN), da, db, idesc, (br > 0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < WG_KB / 16; ++k)
+              umma_f16(dcol, ((uint64_t)hi_a << 32) | (uint64_t)(sa + k * ka), ((uint64_t)hi_b << 32) | (uint64_t)(sb + k * kb),
+                       idesc, (br > 0 || k > 0) ? 1u : 0u);
             umma_commit(&a_empty[as]);
           }
           __syncwarp();

@@ -192,9 +192,9 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   if (p.Do != p.Di || p.Ho != p.Hi || p.Wo != p.Wi || p.Dof != p.Do || p.Hof != p.Ho || p.Wof != p.Wo)
     return MTB200_ERR_UNSUPPORTED;
   if (p.Cin != 16 && p.Cin % 32 != 0) return MTB200_ERR_UNSUPPORTED;
-  if (p.Cin > 128 || p.Cout % WL_BN || p.Cout > 64) return MTB200_ERR_UNSUPPORTED;  // every (chunk, Cout block) pair
-                                                                                     // re-streams both operands
-  if (p.Wo < 48 || p.Ho < 4 || p.ntaps < 9) return MTB200_ERR_UNSUPPORTED;
+  // every (Cin chunk, Cout block) pair re-streams both operands from L2: worth it while the pair count is small
+  if (p.Cout % WL_BN || (p.Cin / 32) * (p.Cout / WL_BN) > 32) return MTB200_ERR_UNSUPPORTED;
+  if (p.Wo < 48 || p.Ho < 4 || p.ntaps < 9) return MTB200_ERR_UNSUPPORTED;  // narrower maps: no gain over per-tap
 
   static WgradLineParams q;
   memset(&q, 0, sizeof(q));

@@ -216,14 +216,59 @@ class ConvOp:
 
 
 def _padded(v: Optional[torch.Tensor], n: int, fill=0.0):
+    """1-D parameter zero-padded to `n` entries.  Parameters that live in a FlatArena own a padded slot (the tail stays
+    zero under SGD): they are viewed in place, no copy."""
     if v is None:
         return None
+    if getattr(v, "_mtb_padded_len", 0) >= n and v.dtype == torch.float32:
+        return v.detach().as_strided((n,), (1,))
     v = v.detach().float()
     if v.numel() == n:
         return v.contiguous()
     out = torch.full((n,), fill, dtype=torch.float32, device=v.device)
     out[:v.numel()] = v
     return out
+
+
+def direct_grad(p, n: Optional[int] = None):
+    """The gradient slot of an arena parameter (FlatArena sets `_mtb_direct_grad`): kernels accumulate into it in place
+    and autograd is handed no tensor for it.  `n`: padded length for 1-D parameters.  None = go through autograd."""
+    if p is None or not getattr(p, "_mtb_direct_grad", False) or p.grad is None:
+        return None
+    if n is None:
+        return p.grad
+    if getattr(p, "_mtb_padded_len", 0) >= n:
+        return p.grad.as_strided((n,), (1,))
+    return None
+
+
+class ZeroPool:
+    """Bump allocator over zero-filled device memory for the per-step accumulation buffers (statistics, reductions,
+    packed weight gradients): one memset per step instead of ~80 torch.zeros launches."""
+
+    def __init__(self, dtype, chunk_elems):
+        self.dtype, self.chunk_elems = dtype, chunk_elems
+        self.chunks = []  # [tensor, used]
+
+    def reset(self):
+        for c in self.chunks:
+            if c[1]:
+                c[0][:c[1]].zero_()
+                c[1] = 0
+
+    def take(self, shape, device):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        n16 = (n + 15) // 16 * 16
+        for c in self.chunks:
+            if c[0].device == device and c[0].numel() - c[1] >= n16:
+                t = c[0][c[1]:c[1] + n].view(shape)
+                c[1] += n16
+                return t
+        c = [torch.zeros(max(n16, self.chunk_elems), dtype=self.dtype, device=device), n16]
+        self.chunks.append(c)
+        return c[0][:n].view(shape)
 
 
 class Tape:
@@ -235,6 +280,7 @@ class Tape:
         self.grad_bufs: Dict[int, torch.Tensor] = {}
         self.grad_init: Dict[int, set] = {}
         self.param_grads: Dict[int, torch.Tensor] = {}
+        self.direct_done = set()  # ids of parameters whose gradient went straight into their arena slot
         self.keep = []  # keep python references to buffers alive
 
     def grad_feat(self, f: Feat) -> Tuple[Feat, bool]:
@@ -274,6 +320,13 @@ class Engine:
         self.impl = impl  # 0 auto, 1 force FFMA, 2 force tcgen05
         self.wdtype = torch.float32 if dtype == torch.float32 else dtype
         self._materialize = None
+        self._z64 = ZeroPool(torch.float64, 1 << 16)
+        self._z32 = ZeroPool(torch.float32, 1 << 22)
+
+    def begin_step(self):
+        """Called at the start of every network forward: re-zero what the previous step took from the pools."""
+        self._z64.reset()
+        self._z32.reset()
 
     @property
     def materialize_inputs(self) -> bool:
@@ -343,7 +396,7 @@ class Engine:
         if out is None:
             out = Feat(self.new_buf(odims, op.Cout_p, dev), 0, op.Cout, op.Cout_p)
         assert out.dims == odims and out.Cp == op.Cout_p
-        stats = torch.zeros((odims[0], op.Cout_p, 2), dtype=torch.float64, device=dev) if want_stats else None
+        stats = self._z64.take((odims[0], op.Cout_p, 2), dev) if want_stats else None
         grid = x.dims[1:] if op.transposed else odims[1:]
         self._conv_call(op.fwd_taps, x, op.packed(self.wdtype, False), _padded(op.bias, op.Cout_p), out, grid, stats,
                         False, op.Cin_p, op.Cout_p, flops=self.conv_flops(op, odims), tag="conv_fwd")
@@ -389,25 +442,34 @@ class Engine:
             self._zero_param_grads(tape, op, gamma_param, beta_param)
             return
         g, _ = tape.grad_feat(src)
-        red = torch.zeros((B, y.Cp, 2), dtype=torch.float64, device=dev)
+        red = self._z64.take((B, y.Cp, 2), dev)
         dt = L.dtype_enum(self.dtype)
         L.call("mtb200_in_bwd_reduce", g.ptr(), g.ldc, g.coff, y.ptr(), y.ldc, y.coff, dt, B, y.nvox, y.Cp,
                L.ptr(y.xform), L.ptr(y.meanrstd), L.ptr(red), L.stream_ptr())
-        dgamma = torch.zeros(y.Cp, dtype=torch.float32, device=dev)
-        dbeta = torch.zeros(y.Cp, dtype=torch.float32, device=dev)
+        dgamma, dbeta = direct_grad(gamma_param, y.Cp), direct_grad(beta_param, y.Cp)
+        direct = dgamma is not None and dbeta is not None
+        if not direct:
+            dgamma = torch.zeros(y.Cp, dtype=torch.float32, device=dev)
+            dbeta = torch.zeros(y.Cp, dtype=torch.float32, device=dev)
         L.call("mtb200_in_bwd_apply", g.ptr(), g.ldc, g.coff, y.ptr(), y.ldc, y.coff, g.ptr(), g.ldc, g.coff, dt, B,
                y.nvox, y.Cp, L.ptr(y.xform), L.ptr(y.meanrstd), L.ptr(gamma), L.ptr(red), L.ptr(dgamma), L.ptr(dbeta),
                L.stream_ptr())
-        tape.add_param_grad(gamma_param, dgamma[:op.Cout])
-        tape.add_param_grad(beta_param, dbeta[:op.Cout])
+        if direct:
+            tape.direct_done.update((id(gamma_param), id(beta_param)))
+        else:
+            tape.add_param_grad(gamma_param, dgamma[:op.Cout])
+            tape.add_param_grad(beta_param, dbeta[:op.Cout])
         # A bias in front of an InstanceNorm has an identically-zero gradient: sum_v dy = k1 (S1 - N m1 - m2 sum xhat)
         # = 0.  (The reference's autograd produces rounding noise ~1e-9 there.)  Emit exact zeros, skip the reduction.
         self._conv_bwd(tape, op, x, g, need_input_grad, bias_grad_is_zero=True)
 
     def _zero_param_grads(self, tape, op, *others):
-        tape.add_param_grad(op.weight, torch.zeros_like(op.weight))
-        for p in (op.bias,) + others:
-            if p is not None:
+        for p in (op.weight, op.bias) + others:
+            if p is None:
+                continue
+            if direct_grad(p) is not None:
+                tape.direct_done.add(id(p))  # the arena slot already holds this step's (zero) contribution
+            else:
                 tape.add_param_grad(p, torch.zeros_like(p))
 
     def _conv_bwd(self, tape, op: ConvOp, x: Feat, dy: Feat, need_input_grad, bias_grad_is_zero=False):
@@ -416,7 +478,7 @@ class Engine:
         dt = L.dtype_enum(self.dtype)
         x = self.operand(x)
         # ---- weight gradient (same tap table as the forward problem)
-        dw = torch.zeros((op.ntap, op.Cout_p, op.Cin_p), dtype=torch.float32, device=dev)
+        dw = self._z32.take((op.ntap, op.Cout_p, op.Cin_p), dev)
         p = L.WgradParams()
         p.x, p.dy, p.dw = x.ptr(), dy.ptr(), dw.data_ptr()
         p.xform = x.xform.data_ptr() if x.xform is not None else None
@@ -431,12 +493,21 @@ class Engine:
         fl = self.conv_flops(op, dy.dims)
         L.call("mtb200_wgrad_taps", C.byref(p), L.stream_ptr(), flops=fl, tag="conv_wgrad",
                info=(op.Cin_p, op.Cout_p, (p.Do, p.Ho, p.Wo), op.ntap, op.fwd_taps.in_stride, op.fwd_taps.out_stride))
-        gw = torch.empty_like(op.weight)
-        L.call("mtb200_unpack_wgrad", L.ptr(dw), op.Cout, op.Cin, op.ntap, int(op.transposed), op.Cout_p, op.Cin_p,
-               op.split, op.split_p, 1.0, 0, L.ptr(gw), L.stream_ptr())
-        tape.add_param_grad(op.weight, gw)
+        gw = direct_grad(op.weight)
+        if gw is not None:  # accumulate straight into the arena's gradient slot
+            L.call("mtb200_unpack_wgrad", L.ptr(dw), op.Cout, op.Cin, op.ntap, int(op.transposed), op.Cout_p, op.Cin_p,
+                   op.split, op.split_p, 1.0, 1, L.ptr(gw), L.stream_ptr())
+            tape.direct_done.add(id(op.weight))
+        else:
+            gw = torch.empty_like(op.weight)
+            L.call("mtb200_unpack_wgrad", L.ptr(dw), op.Cout, op.Cin, op.ntap, int(op.transposed), op.Cout_p, op.Cin_p,
+                   op.split, op.split_p, 1.0, 0, L.ptr(gw), L.stream_ptr())
+            tape.add_param_grad(op.weight, gw)
         if op.bias is not None and bias_grad_is_zero:
-            tape.add_param_grad(op.bias, torch.zeros_like(op.bias))
+            if direct_grad(op.bias) is not None:
+                tape.direct_done.add(id(op.bias))
+            else:
+                tape.add_param_grad(op.bias, torch.zeros_like(op.bias))
         elif op.bias is not None:
             gb = torch.zeros(op.Cout_p, dtype=torch.float32, device=dev)
             L.call("mtb200_colsum", dy.ptr(), dt, dy.dims[0] * dy.nvox, dy.ldc, dy.coff, op.Cout_p, L.ptr(gb),

@@ -128,6 +128,7 @@ class _UNetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, x, n_out, *params):
         tape = Tape() if any(p.requires_grad for p in params) else None
+        net._engine.begin_step()
         feats = net._native_forward(x, tape)
         feats = feats[:n_out]
         ctx.net, ctx.tape, ctx.feats, ctx.params = net, tape, feats, params
@@ -146,6 +147,11 @@ class _UNetFunction(torch.autograd.Function):
         out = []
         for p in ctx.params:
             g = tape.param_grads.get(id(p))
+            if id(p) in tape.direct_done:
+                # the kernels accumulated into the parameter's arena gradient slot: nothing for autograd to add
+                assert g is None
+                out.append(None)
+                continue
             if g is None and p.requires_grad:
                 g = torch.zeros_like(p)
             out.append(g if p.requires_grad else None)
@@ -397,6 +403,7 @@ class Generic_UNet(SegmentationNetwork):
                 n_out = len(self.tu) if want_ds else 1
                 outs = _UNetFunction.apply(self, x, n_out, *params)
             else:
+                self._engine.begin_step()
                 feats = self._native_forward(x, None, only_full_res=not want_ds)
                 outs = tuple(f.as_ncdhw() for f in feats)
             outs = tuple(self.final_nonlin(o) for o in outs)
@@ -427,6 +434,7 @@ class Generic_UNet(SegmentationNetwork):
         return seg_outputs[-1]
 
     def native_logits(self, tile: Feat) -> Feat:
+        self._engine.begin_step()
         return self._native_forward(tile, None, only_full_res=True)[0]
 
     @staticmethod

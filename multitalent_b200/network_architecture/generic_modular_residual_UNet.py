@@ -424,6 +424,11 @@ class FabiansUNet(SegmentationNetwork):
             logits.append(eng.conv_plain(tape, ConvOpCache.get(self, head), f))
         return logits[::-1]
 
+    def native_logits(self, tile: Feat) -> Feat:
+        """Full-resolution logits for the sliding-window predictor (neural_network.py)."""
+        self._engine.begin_step()
+        return self._native_forward(tile, None, only_full_res=True)[0]
+
     def forward(self, x):
         if self._native_ok and x.is_cuda:
             want_ds = bool(self.decoder.deep_supervision)
@@ -432,6 +437,7 @@ class FabiansUNet(SegmentationNetwork):
                 n_out = len(self.decoder.tus) if want_ds else 1
                 outs = _UNetFunction.apply(self, x, n_out, *params)
             else:
+                self._engine.begin_step()
                 feats = self._native_forward(x, None, only_full_res=not want_ds)
                 outs = tuple(f.as_ncdhw() for f in feats)
             return list(outs) if want_ds else outs[0]

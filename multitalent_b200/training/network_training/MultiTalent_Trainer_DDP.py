@@ -27,7 +27,7 @@ from torch import nn
 
 from ... import _lib as L
 from ...dataset_conversion.Task100_MultiTalent import MultiTalent_regions
-from ...engine import bump_weights_epoch
+from ...engine import bump_weights_epoch, pad_channels
 from ...network_architecture.generic_UNet import Generic_UNet, InitWeights_He
 from ...plans import default_plans
 from ..loss_functions.multitalent_loss import multitalent_loss
@@ -43,7 +43,12 @@ class FlatArena:
 
     def __init__(self, module: nn.Module):
         params = [p for p in module.parameters()]
-        n = sum((p.numel() + 3) // 4 * 4 for p in params)
+
+        def slot(p):
+            # 1-D parameters (bias, norm weight / bias) get a slot padded to the kernels' channel padding: the engine
+            # views them in place (engine._padded) and accumulates their gradients in place (engine.direct_grad)
+            return pad_channels(p.numel()) if p.dim() == 1 else (p.numel() + 3) // 4 * 4
+        n = sum(slot(p) for p in params)
         dev = params[0].device
         self.params = params
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -55,7 +60,10 @@ class FlatArena:
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view_as(p.data)
             p.grad = self.grad[off:off + k].view_as(p.data)
-            off += (k + 3) // 4 * 4
+            p._mtb_direct_grad = True
+            if p.dim() == 1:
+                p._mtb_padded_len = slot(p)
+            off += slot(p)
         self.n = n
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.first = True
@@ -215,21 +223,38 @@ class MultiTalent_trainer_ddp(object):
         valid_regions = [p['valid_regions'] for p in data_dict['properties']]
         data = torch.as_tensor(data)
         target = [torch.as_tensor(t) for t in target]
+        ready = None
         if torch.cuda.is_available():
+            # the targets are not needed before the loss: their H2D copy runs on a side stream under the forward pass
+            main = torch.cuda.current_stream()
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream()
+            if all(t.is_pinned() for t in target if not t.is_cuda):
+                self._copy_stream.wait_stream(main)
+                with torch.cuda.stream(self._copy_stream):
+                    target = [t.cuda(non_blocking=True) for t in target]
+                    ready = torch.cuda.Event()
+                    ready.record(self._copy_stream)
+                for t in target:
+                    t.record_stream(main)
+            else:
+                target = [t.cuda(non_blocking=True) for t in target]
             data = data.cuda(non_blocking=True)
-            target = [t.cuda(non_blocking=True) for t in target]
-        l, ce, dc = self.train_step(data, target, valid_regions, do_backprop)
+        l, ce, dc = self.train_step(data, target, valid_regions, do_backprop, target_ready=ready)
         res = torch.stack((l.detach(), ce.detach(), dc.detach())).cpu().numpy()
         return res[0], res[1], res[2]
 
-    def train_step(self, data, target, valid_regions, do_backprop=True):
-        """One optimisation step on device-resident tensors; returns device scalars (no sync)."""
+    def train_step(self, data, target, valid_regions, do_backprop=True, target_ready=None):
+        """One optimisation step on device-resident tensors; returns device scalars (no sync).  `target_ready`: CUDA
+        event after which `target` may be read (asynchronous H2D copy issued by `run_iteration`)."""
         if self.arena is not None:
             self.arena.zero_grad()
         elif self.optimizer is not None:
             self.optimizer.zero_grad()
         with torch.set_grad_enabled(do_backprop):
             output = self.network(data)
+            if target_ready is not None:
+                torch.cuda.current_stream().wait_event(target_ready)
             l, ce, dc = self.compute_loss(output, target, valid_regions)
             if do_backprop:
                 (l * self.loss_scale if self.loss_scale != 1.0 else l).backward()

@@ -194,6 +194,7 @@ WGRAD_LINE_CASES = [
     (60, 60, (3, 3, 3), (1, 6, 10, 64), 0),      # 64-wide lines (4 K steps), 2 chunks x 2 Cout blocks
     (120, 60, (3, 3, 3), (1, 4, 8, 64), 60),     # 4 chunks
     (60, 60, (3, 3, 3), (1, 3, 6, 56), 0),       # ragged 64-wide tile
+    (120, 120, (3, 3, 3), (1, 3, 5, 64), 0),     # 4 chunks x 4 Cout blocks
 ]
 
 
