@@ -14,6 +14,10 @@
 // (d-1, d, d+1) x h' and the dY lines h'-1 .. h'+1 of plane d (TMA, out-of-volume = zero fill), so steps are independent
 // and the pipeline never drains between units.  Epilogue once per CTA: fp32 atomics into dW.
 //
+// The same kernel covers the 1x1x1 heads (generic_UNet.py:349-351): window of ONE dY line (nb = 1, only the tap
+// (0,0,0) is written back) and a 48-channel Cout as two column segments (32 channels / SWIZZLE_64B + 16 / SWIZZLE_32B,
+// two MMAs per K step into adjacent TMEM columns) -- that layer is pure HBM streaming.
+//
 // Warp roles (6 warps): 0 = producer (TMA), 1 = TMEM owner + MMA issuer, 2..5 = epilogue.
 #include "umma.cuh"
 
@@ -26,7 +30,12 @@ constexpr int WL_MAX_STAGES = 6;
 constexpr int WL_BN = 32;
 
 struct WgradLineParams {
-  CUtensorMap x_map, dy_map;
+  CUtensorMap x_map, dy_map[2];
+  int nb;                    // dY lines in the window: 3 (dy = +1, 0, -1) or 1 (all taps have dy == 0)
+  int nseg;                  // Cout segments of this CTA: {32} or {32, 16}
+  int seg_w[2], seg_c0[2], seg_off[2];  // channels, first channel, byte offset inside the dY window
+  int ntot;                  // TMEM columns per dz accumulator = nb * sum(seg_w)
+  int cout_blk;              // channels covered by one CTA (grid.z stride)
   float* dw;
   int B, D, H, W;
   int Cin, Cout;             // padded channel counts (dw strides)
@@ -44,20 +53,19 @@ struct WgradLineParams {
 
 __device__ __forceinline__ uint64_t wl_desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
 
-template <int ROWB>  // bytes per X row = kcw * 2 (64: four 32-channel blocks, 32: eight 16-channel blocks)
+// ROWB = bytes per X row = kcw * 2 (64: four 32-channel blocks, 32: eight 16-channel blocks); NSEG = Cout segments per CTA
+template <int ROWB, int NSEG>
 __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __grid_constant__ WgradLineParams p) {
   extern __shared__ uint8_t dsmem_raw[];
   __shared__ __align__(8) uint64_t st_full[WL_MAX_STAGES], st_empty[WL_MAX_STAGES];
   __shared__ __align__(8) uint64_t acc_full;
   __shared__ uint32_t tmem_slot;
 
-  constexpr uint32_t NCOLS = 3 * WL_BN;
-  constexpr uint32_t YROWB = WL_BN * 2;           // bytes per dY row
-  const uint32_t YLINE = (uint32_t)p.wt * YROWB;  // one dY line
+  const uint32_t NCOLS = (uint32_t)p.ntot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
   const int c0 = blockIdx.y * p.kcw;
-  const int n0 = blockIdx.z * WL_BN;
+  const int n0 = blockIdx.z * p.cout_blk;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 1); }
@@ -90,7 +98,9 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __
           mbar_expect_tx(&st_full[slot], (uint32_t)p.stage_tx);
           for (int z = 0; z < p.ndz; ++z)
             tma_load_5d(dst + (size_t)z * p.xline_bytes, &p.x_map, &st_full[slot], c0, w0 - 1, hp, d + p.dz0 + z, b);
-          tma_load_5d(dst + p.ybase, &p.dy_map, &st_full[slot], n0, w0, hp - 1, d, b);  // lines hp-1, hp, hp+1
+          for (int sg = 0; sg < p.nseg; ++sg)  // lines hp-1, hp, hp+1 (or hp alone)
+            tma_load_5d(dst + p.ybase + p.seg_off[sg], &p.dy_map[sg], &st_full[slot], n0 + p.seg_c0[sg], w0,
+                        hp - (p.nb == 3 ? 1 : 0), d, b);
         }
         __syncwarp();
       }
@@ -99,16 +109,24 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __
     // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t fmt = p.is_f16 ? 0u : 1u;
-    // D = f32, A/B 16-bit, both MN-major (bits 15, 16), N = 96, M = 128
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((NCOLS >> 3) << 17) |
-                           ((128u >> 4) << 24);
+    // D = f32, A/B 16-bit, both MN-major (bits 15, 16), N = nb * segment width, M = 128
+    const uint32_t idesc0 = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((128u >> 4) << 24);
     const uint32_t layout_a = ROWB == 64 ? 4u : 6u;  // SWIZZLE_64B / SWIZZLE_32B
     const uint32_t hi_a = ((8u * ROWB) >> 4) | (1u << 14) | (layout_a << 29);
-    const uint32_t hi_b = ((8u * YROWB) >> 4) | (1u << 14) | (4u << 29);
-    const uint32_t lbo_a = ((uint32_t)ROWB >> 4) << 16, lbo_b = (YLINE >> 4) << 16;
+    const uint32_t lbo_a = ((uint32_t)ROWB >> 4) << 16;
+    uint32_t idesc_s[NSEG], hi_b[NSEG], lbo_b[NSEG], yrow[NSEG], yoff16[NSEG], colo[NSEG];
+#pragma unroll
+    for (int sg = 0; sg < NSEG; ++sg) {
+      const uint32_t w = sg == 0 ? 32u : 16u;                  // segment widths are fixed: 32 (+ 16)
+      yrow[sg] = w * 2;                                        // bytes per dY row of this segment
+      idesc_s[sg] = idesc0 | ((((uint32_t)p.nb * w) >> 3) << 17);
+      hi_b[sg] = ((8u * yrow[sg]) >> 4) | (1u << 14) | ((w == 32 ? 4u : 6u) << 29);
+      lbo_b[sg] = (((uint32_t)p.wt * yrow[sg]) >> 4) << 16;     // LBO = one dY line
+      yoff16[sg] = (uint32_t)(p.ybase + p.seg_off[sg]) >> 4;
+      colo[sg] = sg == 0 ? 0u : (uint32_t)(p.nb * 32);
+    }
     const uint32_t s16 = __shfl_sync(0xffffffffu, (smem_u32(dsmem) & 0x3FFFFu) >> 4, 0);
     const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, xline16 = (uint32_t)p.xline_bytes >> 4;
-    const uint32_t y16 = (uint32_t)p.ybase >> 4;
     const int ndz = p.ndz, nkk = p.nkk;
     uint32_t sc = 0;
     for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
@@ -120,19 +138,25 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_s = (s16 + slot * stage16) | lbo_a;
-          const uint32_t b_s = (s16 + slot * stage16 + y16) | lbo_b;
+          uint32_t b_s[NSEG];
+#pragma unroll
+          for (int sg = 0; sg < NSEG; ++sg) b_s[sg] = (s16 + slot * stage16 + yoff16[sg]) | lbo_b[sg];
           const uint32_t acc = sc > 0 ? 1u : 0u;
-          // kk-major order: consecutive MMAs go to DIFFERENT accumulators (dz), so they pipeline in the tensor core
-          // instead of each waiting for the previous accumulate into the same TMEM columns
+          // kk-major order: consecutive MMAs go to DIFFERENT accumulators (dz / segment), so they pipeline in the tensor
+          // core instead of each waiting for the previous accumulate into the same TMEM columns
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
             if (kk < nkk) {
 #pragma unroll
-              for (int z = 0; z < 3; ++z)
-                if (z < ndz)
-                  umma_f16(tmem_u + (uint32_t)z * NCOLS,
-                           wl_desc64(hi_a, a_s + (uint32_t)z * xline16 + (uint32_t)(kk * ROWB)),
-                           wl_desc64(hi_b, b_s + (uint32_t)(kk * YROWB)), idesc, kk ? 1u : acc);
+              for (int z = 0; z < 3; ++z) {
+                if (z < ndz) {
+#pragma unroll
+                  for (int sg = 0; sg < NSEG; ++sg)
+                    umma_f16(tmem_u + (uint32_t)z * NCOLS + colo[sg],
+                             wl_desc64(hi_a, a_s + (uint32_t)z * xline16 + (uint32_t)(kk * ROWB)),
+                             wl_desc64(hi_b[sg], b_s[sg] + (uint32_t)kk * yrow[sg]), idesc_s[sg], kk ? 1u : acc);
+                }
+              }
             }
           }
           umma_commit(&st_empty[slot]);
@@ -154,16 +178,23 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __
     tc_fence_after();
     // every lane takes part in the .sync.aligned TMEM loads; only rows of used blocks (dx = j - 1 <= 1) write back
     if ((q * 32) / CB <= 2) {
+      const int nchunks = p.ntot / 16;
+      const int seg0_cols = p.nb * p.seg_w[0];
       for (int z = 0; z < p.ndz; ++z) {
         const int dzi = p.dz0 + z + 1;
-#pragma unroll
-        for (int c16 = 0; c16 < 6; ++c16) {
+        for (int c16 = 0; c16 < nchunks; ++c16) {
           uint32_t r[16];
           tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)z * NCOLS + (uint32_t)(c16 * 16), r);
-          const int jj = c16 >> 1;  // dY line of the window: dy = 1 - jj
-          const int widx = j <= 2 ? p.lut[(dzi * 3 + (2 - jj)) * 3 + j] : -1;
+          // column -> (segment, window line jj, channel)
+          const int col = c16 * 16;
+          const int sg = col < seg0_cols ? 0 : 1;
+          const int rel = col - (sg ? seg0_cols : 0);
+          const int jj = rel / p.seg_w[sg];
+          const int co = p.seg_c0[sg] + rel % p.seg_w[sg];
+          const int dyi = p.nb == 3 ? 2 - jj : 1;  // dy + 1
+          const int widx = j <= 2 ? p.lut[(dzi * 3 + dyi) * 3 + j] : -1;
           if (widx >= 0) {
-            float* dst = p.dw + ((long long)widx * p.Cout + n0 + (c16 & 1) * 16) * p.Cin + c0 + ci;
+            float* dst = p.dw + ((long long)widx * p.Cout + n0 + co) * p.Cin + c0 + ci;
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               const float v = __uint_as_float(r[e]);
@@ -193,8 +224,12 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
     return MTB200_ERR_UNSUPPORTED;
   if (p.Cin != 16 && p.Cin % 32 != 0) return MTB200_ERR_UNSUPPORTED;
   // every (Cin chunk, Cout block) pair re-streams both operands from L2: worth it while the pair count is small
-  if (p.Cout % WL_BN || (p.Cin / 32) * (p.Cout / WL_BN) > 32) return MTB200_ERR_UNSUPPORTED;
-  if (p.Wo < 48 || p.Ho < 4 || p.ntaps < 9) return MTB200_ERR_UNSUPPORTED;  // narrower maps: no gain over per-tap
+  const bool cout48 = p.Cout == 48 && p.Cin <= 32;  // the 47 heads on the widest maps: one column block of 32 + 16
+  if (!cout48 && (p.Cout % WL_BN || (p.Cin / 32) * (p.Cout / WL_BN) > 32)) return MTB200_ERR_UNSUPPORTED;
+  if (p.Wo < 48 || p.Ho < 4) return MTB200_ERR_UNSUPPORTED;  // narrower maps: no gain over the per-tap kernel
+  bool all_dy0 = true;
+  for (int t = 0; t < p.ntaps; ++t) all_dy0 = all_dy0 && p.tap_off[t][1] == 0;
+  if (p.ntaps < 9 && !(p.ntaps == 1 && all_dy0)) return MTB200_ERR_UNSUPPORTED;
 
   static WgradLineParams q;
   memset(&q, 0, sizeof(q));
@@ -217,8 +252,16 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   const int xrows = q.wt + 2;
   q.xline_bytes = wl_align1k((long long)(xrows + 8) * rowb);  // + rows touched by the unused shifted blocks
   q.ybase = q.xline_bytes * q.ndz;
-  const int ybytes = 3 * q.wt * WL_BN * 2;
-  q.stage_bytes = wl_align1k(q.ybase + ybytes);
+  q.nb = all_dy0 ? 1 : 3;
+  q.nseg = cout48 ? 2 : 1;
+  q.seg_w[0] = 32; q.seg_c0[0] = 0; q.seg_off[0] = 0;
+  q.seg_w[1] = 16; q.seg_c0[1] = 32; q.seg_off[1] = wl_align1k((long long)q.nb * q.wt * 64);
+  q.cout_blk = cout48 ? 48 : WL_BN;
+  int wsum = 0, ybytes = 0;
+  for (int sg = 0; sg < q.nseg; ++sg) { wsum += q.seg_w[sg]; ybytes += q.nb * q.wt * q.seg_w[sg] * 2; }
+  q.ntot = q.nb * wsum;
+  const int ywin_bytes = q.nseg == 2 ? q.seg_off[1] + wl_align1k((long long)q.nb * q.wt * 32) : wl_align1k((long long)q.nb * q.wt * 64);
+  q.stage_bytes = wl_align1k(q.ybase + ywin_bytes);
   q.stage_tx = q.ndz * xrows * rowb + ybytes;
   q.stages = min(WL_MAX_STAGES, (224 * 1024) / q.stage_bytes);
   if (q.stages < 2) return MTB200_ERR_UNSUPPORTED;
@@ -235,9 +278,12 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
     cuuint64_t strides[4] = {(cuuint64_t)p.out_ldc * 2, (cuuint64_t)p.Wof * p.out_ldc * 2,
                              (cuuint64_t)p.Hof * p.Wof * p.out_ldc * 2,
                              (cuuint64_t)p.Dof * p.Hof * p.Wof * p.out_ldc * 2};
-    cuuint32_t box[5] = {(cuuint32_t)WL_BN, (cuuint32_t)q.wt, 3, 1, 1};
-    if (!umma_encode_map(&q.dy_map, p.dtype, 5, (uint8_t*)p.dy + (size_t)p.out_coff * 2, dims, strides, box, WL_BN * 2))
-      return MTB200_ERR_CUDA;
+    for (int sg = 0; sg < q.nseg; ++sg) {
+      cuuint32_t box[5] = {(cuuint32_t)q.seg_w[sg], (cuuint32_t)q.wt, (cuuint32_t)q.nb, 1, 1};
+      if (!umma_encode_map(&q.dy_map[sg], p.dtype, 5, (uint8_t*)p.dy + (size_t)p.out_coff * 2, dims, strides, box,
+                           q.seg_w[sg] * 2))
+        return MTB200_ERR_CUDA;
+    }
   }
   q.dw = p.dw;
   q.B = p.B; q.D = p.Do; q.H = p.Ho; q.W = p.Wo;
@@ -265,15 +311,19 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   q.units = (long long)p.B * p.Do * q.ntw * q.nhr;
   const int gx = (int)(q.units < sms ? q.units : sms);
   const int smem = max(116 * 1024, q.stages * q.stage_bytes + 1024);  // one CTA per SM (512 TMEM columns each)
-  dim3 grid((unsigned)gx, nchunk, p.Cout / WL_BN);
-  cudaError_t e;
+  dim3 grid((unsigned)gx, nchunk, p.Cout / q.cout_blk);
+  cudaError_t e = cudaSuccess;
+#define WL_LAUNCH(RB, NS)                                                                                         \
+  do {                                                                                                            \
+    e = cudaFuncSetAttribute(wgrad_line_umma_kernel<RB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
+    if (e == cudaSuccess) wgrad_line_umma_kernel<RB, NS><<<grid, WL_THREADS, smem, s>>>(q);                       \
+  } while (0)
   if (rowb == 64) {
-    e = cudaFuncSetAttribute(wgrad_line_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) wgrad_line_umma_kernel<64><<<grid, WL_THREADS, smem, s>>>(q);
+    if (q.nseg == 1) WL_LAUNCH(64, 1); else WL_LAUNCH(64, 2);
   } else {
-    e = cudaFuncSetAttribute(wgrad_line_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) wgrad_line_umma_kernel<32><<<grid, WL_THREADS, smem, s>>>(q);
+    if (q.nseg == 1) WL_LAUNCH(32, 1); else WL_LAUNCH(32, 2);
   }
+#undef WL_LAUNCH
   if (e != cudaSuccess) { set_error("wgrad_line: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
   return check_launch("wgrad_line_umma");
 }

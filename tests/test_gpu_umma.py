@@ -195,6 +195,9 @@ WGRAD_LINE_CASES = [
     (120, 60, (3, 3, 3), (1, 4, 8, 64), 60),     # 4 chunks
     (60, 60, (3, 3, 3), (1, 3, 6, 56), 0),       # ragged 64-wide tile
     (120, 120, (3, 3, 3), (1, 3, 5, 64), 0),     # 4 chunks x 4 Cout blocks
+    (30, 47, (1, 1, 1), (1, 4, 10, 128), 0),     # 1x1x1 head: one-line window, Cout 48 = segments of 32 + 16 channels
+    (1, 47, (1, 1, 1), (2, 3, 6, 64), 0),        # Cin_p 16, 64-wide lines
+    (30, 47, (1, 1, 1), (1, 2, 5, 100), 0),      # ragged
 ]
 
 
