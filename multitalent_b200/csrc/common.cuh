@@ -81,10 +81,14 @@ template <> __device__ __forceinline__ void store8<__half>(__half* p, const floa
 // 8 consecutive elements kept in their storage format (4 registers for the 16-bit types): lets a streaming kernel
 // keep several vectors in flight without paying 8 fp32 registers per vector
 template <typename T> struct Raw8;
+// `load` is an asm volatile read-only-path load: the compiler keeps volatile asm statements in program order, so a batch
+// of loads written before the arithmetic is really issued before it (plain loads get sunk next to their first use, which
+// serialises one DRAM round trip per vector -- measured on in_bwd_apply: 3.8 -> 5.6 TB/s)
 template <> struct Raw8<float> {
   float4 a, b;
   __device__ __forceinline__ void load(const float* p) {
-    a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4);
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p));
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p + 4));
   }
   __device__ __forceinline__ float get(int i) const {
     return i == 0 ? a.x : i == 1 ? a.y : i == 2 ? a.z : i == 3 ? a.w : i == 4 ? b.x : i == 5 ? b.y : i == 6 ? b.z : b.w;
@@ -92,7 +96,9 @@ template <> struct Raw8<float> {
 };
 template <> struct Raw8<__nv_bfloat16> {
   uint4 r;
-  __device__ __forceinline__ void load(const __nv_bfloat16* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  }
   __device__ __forceinline__ float get(int i) const {
     const uint32_t w = i < 2 ? r.x : i < 4 ? r.y : i < 6 ? r.z : r.w;
     return __uint_as_float((i & 1) ? (w & 0xFFFF0000u) : (w << 16));
@@ -100,7 +106,9 @@ template <> struct Raw8<__nv_bfloat16> {
 };
 template <> struct Raw8<__half> {
   uint4 r;
-  __device__ __forceinline__ void load(const __half* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void load(const __half* p) {
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  }
   __device__ __forceinline__ float get(int i) const {
     const uint32_t w = i < 2 ? r.x : i < 4 ? r.y : i < 6 ? r.z : r.w;
     const __half2 h = *reinterpret_cast<const __half2*>(&w);

@@ -87,11 +87,22 @@ __global__ void __launch_bounds__(AGG_T) sw_aggregate_kernel(const T* __restrict
   // phase 2
   const long long plane = (long long)Y * Z;
   const long long rowbase = ((long long)(x0 + d) * Y + (y0 + h)) * Z + z0 + w0;
-  for (int i = threadIdx.x; i < C * SEG; i += AGG_T) {
-    const int c = i / SEG, wl = i % SEG;
-    if (wl < nw) {
-      float* a = acc + (long long)c * X * plane + rowbase + wl;
-      *a += sm[c * (SEG + 1) + wl];
+  // all loads of a batch are issued before the first store: the compiler cannot reorder a load above an earlier store
+  // through a different pointer, so a plain `*a += v` loop serialises one DRAM round trip per element
+  constexpr int RB = 8;
+  for (int i0 = threadIdx.x; i0 < C * SEG; i0 += AGG_T * RB) {
+    float old[RB];
+#pragma unroll
+    for (int k = 0; k < RB; ++k) {
+      const int i = i0 + k * AGG_T;
+      const int c = i / SEG, wl = i % SEG;
+      old[k] = (i < C * SEG && wl < nw) ? acc[(long long)c * X * plane + rowbase + wl] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < RB; ++k) {
+      const int i = i0 + k * AGG_T;
+      const int c = i / SEG, wl = i % SEG;
+      if (i < C * SEG && wl < nw) acc[(long long)c * X * plane + rowbase + wl] = old[k] + sm[c * (SEG + 1) + wl];
     }
   }
   if (nb) {

@@ -18,6 +18,8 @@ import numpy as np
 import torch
 from torch import nn
 
+from ctypes import c_void_p as C_void
+
 from .. import _lib as L
 from ..engine import Feat, ndhwc_view_info
 
@@ -201,19 +203,25 @@ class SegmentationNetwork(NeuralNetwork):
         dt = self.native_dtype()
         cin_p = self.native_input_channels_padded()
         pd, ph, pw = patch_size
-        tile = torch.empty((1, pd, ph, pw, cin_p), dtype=dt, device=dev)
+        # TB tiles go through the network as one batch (the deep levels of a single 192x160x128 tile cannot fill 148 SMs)
+        TB = max(1, int(getattr(self, "inference_tile_batch", 4)))
+        tile = torch.empty((TB, pd, ph, pw, cin_p), dtype=dt, device=dev)
         st = L.stream_ptr()
-        for sx in steps[0]:
-            for sy in steps[1]:
-                for sz in steps[2]:
-                    for mi, dims in enumerate(mirrors):
-                        fb = _flip_bits(dims)
-                        L.call("mtb200_sw_gather_tile", L.ptr(vol), Cin, X, Y, Z, sx, sy, sz, pd, ph, pw, fb, L.ptr(tile),
-                               L.dtype_enum(dt), cin_p, st)
-                        logits = self.native_logits(Feat(tile, 0, Cin, cin_p))
-                        L.call("mtb200_sw_aggregate", logits.ptr(), L.dtype_enum(dt), logits.ldc, C, pd, ph, pw, fb,
-                               L.ptr(gauss), 1.0 / n_results, 1, L.ptr(acc), L.ptr(nb) if mi == 0 else None, X, Y, Z,
-                               sx, sy, sz, st)
+        work = [(sx, sy, sz, mi, dims) for sx in steps[0] for sy in steps[1] for sz in steps[2]
+                for mi, dims in enumerate(mirrors)]
+        tile_elems = pd * ph * pw * cin_p
+        esize = tile.element_size()
+        for w0 in range(0, len(work), TB):
+            chunk = work[w0:w0 + TB]
+            for b, (sx, sy, sz, mi, dims) in enumerate(chunk):
+                L.call("mtb200_sw_gather_tile", L.ptr(vol), Cin, X, Y, Z, sx, sy, sz, pd, ph, pw, _flip_bits(dims),
+                       C_void(tile.data_ptr() + b * tile_elems * esize), L.dtype_enum(dt), cin_p, st)
+            logits = self.native_logits(Feat(tile[:len(chunk)], 0, Cin, cin_p))
+            lstride = pd * ph * pw * logits.ldc * esize
+            for b, (sx, sy, sz, mi, dims) in enumerate(chunk):
+                L.call("mtb200_sw_aggregate", C_void(logits.ptr() + b * lstride), L.dtype_enum(dt), logits.ldc, C, pd, ph,
+                       pw, _flip_bits(dims), L.ptr(gauss), 1.0 / n_results, 1, L.ptr(acc), L.ptr(nb) if mi == 0 else None,
+                       X, Y, Z, sx, sy, sz, st)
         # undo the padding (neural_network.py:397-402) -- crop BEFORE normalising, as the reference does
         sl = tuple([slice(0, C)] + list(slicer[1:]))
         if any(s.start != 0 or s.stop != n for s, n in zip(sl[1:], (X, Y, Z))):
