@@ -481,6 +481,10 @@ constexpr int WG_MAX_ASTAGES = 8;
 struct UmmaWgradParams {
   CUtensorMap x_maps[8];
   CUtensorMap dy_map;
+  CUtensorMap dy_maps_merged[MTB200_MAX_GROUPS];  // merge mode: one dY lattice per tap group
+  int merge_ng, merge_cout;                       // merge mode: groups side by side in N (N = ng * Cout), else 0
+  int merge_widx[MTB200_MAX_GROUPS];
+  int merge_off[MTB200_MAX_GROUPS][3];
   float* dw;
   int B, tiles_d, tiles_h, tiles_w, bd, bh, bw;
   long long nbricks;
@@ -570,9 +574,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) wgrad_taps_umma_kernel(const __
         mbar_wait(&b_empty[bs], bph ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(&b_full[bs], WG_KB * p.BN * 2);
-          for (int j = 0; j < p.BN / p.cby; ++j)
-            tma_load_5d(b_base + (size_t)bs * b_stage_bytes + (size_t)j * yblock_bytes, &p.dy_map, &b_full[bs],
-                        n0 + j * p.cby, w0 + p.dy_off[2], h0 + p.dy_off[1], d0 + p.dy_off[0], b);
+          if (p.merge_ng) {  // one dY brick per tap group (its own output lattice), side by side along N
+            for (int j = 0; j < p.merge_ng; ++j)
+              tma_load_5d(b_base + (size_t)bs * b_stage_bytes + (size_t)j * yblock_bytes, &p.dy_maps_merged[j],
+                          &b_full[bs], 0, w0 + p.merge_off[j][2], h0 + p.merge_off[j][1], d0 + p.merge_off[j][0], b);
+          } else {
+            for (int j = 0; j < p.BN / p.cby; ++j)
+              tma_load_5d(b_base + (size_t)bs * b_stage_bytes + (size_t)j * yblock_bytes, &p.dy_map, &b_full[bs],
+                          n0 + j * p.cby, w0 + p.dy_off[2], h0 + p.dy_off[1], d0 + p.dy_off[0], b);
+          }
         }
         __syncwarp();
         if (++bs == 2) { bs = 0; bph ^= 1u; }
@@ -657,10 +667,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) wgrad_taps_umma_kernel(const __
         uint32_t r[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * p.BN + c0), r);
         if (valid) {
+          float* dc = dst + (long long)c0 * p.Cin;
+          if (p.merge_ng) {  // column block -> (tap group, channel)
+            const int g = c0 / p.merge_cout;
+            dc = p.dw + ((long long)p.merge_widx[g] * p.Cout + (c0 - g * p.merge_cout)) * p.Cin + ci;
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float v = __uint_as_float(r[j]);
-            if (v != 0.f) atomicAdd(dst + (long long)(c0 + j) * p.Cin, v);
+            if (v != 0.f) atomicAdd(dc + (long long)j * p.Cin, v);
           }
         }
       }
@@ -701,13 +716,22 @@ int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   q.dw = p.dw;
   q.B = p.B; q.Cin = p.Cin; q.Cout = p.Cout;
   q.cbx = block_width(p.Cin);
-  q.BN = p.Cout;
+  // Merge mode (ConvTranspose3d(k == s) weight gradient, generic_UNet.py:335-336): every tap group holds ONE tap with the
+  // same input offset and differs only in its output lattice -> all groups share the X brick; their dY bricks sit side by
+  // side along N (N = ngroups * Cout <= 256) and the activations are streamed once instead of once per group.
+  bool merge = p.ngroups > 1 && p.ngroups * p.Cout <= 256 && (p.Cout == 16 || p.Cout == 32 || p.Cout == 64);
+  for (int g = 0; g < p.ngroups && merge; ++g) {
+    merge = p.group_tap_begin[g + 1] - p.group_tap_begin[g] == 1;
+    for (int k = 0; k < 3 && merge; ++k)
+      merge = p.tap_off[p.group_tap_begin[g]][k] == p.tap_off[p.group_tap_begin[0]][k];
+  }
+  q.BN = merge ? p.ngroups * p.Cout : p.Cout;
   if (q.BN > 256) {
     q.BN = 0;
     for (int c = 256; c >= 16; c -= 16)
       if (p.Cout % c == 0) { q.BN = c; break; }
   }
-  q.cby = block_width(q.BN);
+  q.cby = merge ? p.Cout : block_width(q.BN);
   q.blocks_per_tap = p.Cin / q.cbx;
   q.blocks_per_tile = 128 / q.cbx;
   q.is_f16 = p.dtype == MTB200_F16;
@@ -768,8 +792,34 @@ int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   cudaError_t ce = cudaFuncSetAttribute(wgrad_taps_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (ce != cudaSuccess) { set_error("wgrad_taps(umma): cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return MTB200_ERR_CUDA; }
 
-  // one launch per group (the dY brick depends on the group's output offset)
-  for (int g = 0; g < p.ngroups; ++g) {
+  if (merge) {
+    q.merge_ng = p.ngroups;
+    q.merge_cout = p.Cout;
+    const int ODims[3] = {p.Dof, p.Hof, p.Wof};
+    for (int g = 0; g < p.ngroups; ++g) {
+      int par[3];
+      cuuint64_t dims[5], strides[4];
+      long long ext[3];
+      for (int k = 0; k < 3; ++k) {
+        const int off = p.group_ooff[g][k];
+        par[k] = ((off % p.os[k]) + p.os[k]) % p.os[k];
+        q.merge_off[g][k] = floor_div(off - par[k], p.os[k]);
+        ext[k] = (ODims[k] - par[k] + p.os[k] - 1) / p.os[k];
+        if (ext[k] < 1) { set_error("wgrad_taps(umma): empty dY lattice"); return MTB200_ERR_UNSUPPORTED; }
+      }
+      q.merge_widx[g] = p.tap_widx[p.group_tap_begin[g]];
+      cuuint32_t box[5] = {(cuuint32_t)q.cby, (cuuint32_t)q.bw, (cuuint32_t)q.bh, (cuuint32_t)q.bd, 1};
+      dims[0] = p.Cout; dims[1] = ext[2]; dims[2] = ext[1]; dims[3] = ext[0]; dims[4] = p.B;
+      strides[0] = (cuuint64_t)p.out_ldc * e * p.os[2];
+      strides[1] = (cuuint64_t)p.Wof * p.out_ldc * e * p.os[1];
+      strides[2] = (cuuint64_t)p.Hof * p.Wof * p.out_ldc * e * p.os[0];
+      strides[3] = (cuuint64_t)p.Dof * p.Hof * p.Wof * p.out_ldc * e;
+      uint8_t* base = (uint8_t*)p.dy + ((((long long)par[0] * p.Hof + par[1]) * p.Wof + par[2]) * p.out_ldc + p.out_coff) * e;
+      if (!encode_map(enc, &q.dy_maps_merged[g], dt, 5, base, dims, strides, box, q.cby * 2)) return MTB200_ERR_CUDA;
+    }
+  }
+  // one launch per group (the dY brick depends on the group's output offset); merge mode: a single launch
+  for (int g = 0; g < (merge ? 1 : p.ngroups); ++g) {
     q.tap_begin = p.group_tap_begin[g];
     q.tap_end = p.group_tap_begin[g + 1];
     if (q.tap_end == q.tap_begin) continue;
@@ -802,7 +852,7 @@ int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
     const int tile_groups = (q.ntiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
     q.tmem_cols = 32;
     while (q.tmem_cols < q.tiles_per_cta * q.BN) q.tmem_cols *= 2;
-    const int nz = p.Cout / q.BN;
+    const int nz = merge ? 1 : p.Cout / q.BN;
     // split over voxel bricks so that the grid covers the machine about twice, with >= 4 bricks per CTA
     long long want = max(1LL, (2LL * num_sms()) / ((long long)tile_groups * nz));
     long long ksplit = min(want, max(1LL, q.nbricks / 4));
