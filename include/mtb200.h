@@ -70,7 +70,8 @@ typedef struct {
   int32_t accumulate;   /* 1: out += result (gradient accumulation into a skip buffer) */
   int32_t impl;         /* 0 = auto, 1 = CUDA-core FFMA kernel, 2 = tcgen05 kernels (fastest applicable of the three),
                            3 = tcgen05 per-tap kernel only, 4 = tcgen05 plane-streaming kernel only,
-                           5 = tcgen05 line-streaming kernel (dy taps merged into N) only */
+                           5 = tcgen05 line-streaming kernel (dy taps merged into N) only,
+                           6 = tcgen05 pointwise (1x1x1) streaming kernel only */
 } mtb200_conv_params;
 
 /* Weight-gradient of the same tap-table problem:

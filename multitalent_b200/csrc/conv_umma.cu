@@ -40,6 +40,7 @@ static EncodeTiledFn get_encode_fn() {
 int conv_halo_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_halo.cu
 int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_line.cu
 int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s);  // wgrad_line.cu
+int conv_pw_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_pw.cu
 
 int umma_available() {
   static int cached = -1;
@@ -319,7 +320,8 @@ static bool encode_map(EncodeTiledFn enc, CUtensorMap* m, CUtensorMapDataType dt
                        const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box, int row_bytes) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                                 : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+                                 : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                    : (row_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_32B));
   CUresult r = enc(m, dt, (cuuint32_t)rank, base, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -343,10 +345,16 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
     if (p.is[k] < 1 || p.is[k] > 2) { set_error("conv_taps(umma): input stride %d", p.is[k]); return MTB200_ERR_UNSUPPORTED; }
   const long long M = (long long)p.B * p.Do * p.Ho * p.Wo;
   if (M == 0) return MTB200_OK;
-  // impl 3 = per-tap kernel only, 4 = plane-streaming only, 5 = line-streaming (dy merged into N) only; auto = what
-  // measured fastest on the B200 (tools/conv_bench.py, profiles/): line-streaming for the wide-W narrow-channel layers,
-  // plane-streaming for other narrow layers whose 27 weight tiles stay resident, per-tap otherwise.
-  if (p.impl == 5 || (p.impl != 3 && p.impl != 4)) {
+  // impl 3 = per-tap kernel only, 4 = plane-streaming only, 5 = line-streaming (dy merged into N) only, 6 = pointwise
+  // streaming only; auto = what measured fastest on the B200 (tools/conv_bench.py, profiles/): the flat streaming GEMM
+  // for 1x1x1 layers, line-streaming for the wide-W narrow-channel layers, plane-streaming for other narrow layers whose
+  // 27 weight tiles stay resident, per-tap otherwise.
+  if (p.impl == 0 || p.impl == 2 || p.impl == 6) {
+    const int r = conv_pw_umma(p, s);
+    if (r != MTB200_ERR_UNSUPPORTED) return r;
+    if (p.impl == 6) { set_error("conv_taps(umma): problem outside the pointwise kernel's envelope"); return r; }
+  }
+  if (p.impl == 5 || (p.impl != 3 && p.impl != 4 && p.impl != 6)) {
     const int r = conv_line_umma(p, s);
     if (r != MTB200_ERR_UNSUPPORTED) return r;
     if (p.impl == 5) { set_error("conv_taps(umma): problem outside the line-streaming kernel's envelope"); return r; }
@@ -575,9 +583,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) wgrad_taps_umma_kernel(const __
         if (elect_one()) {
           mbar_expect_tx(&b_full[bs], WG_KB * p.BN * 2);
           if (p.merge_ng) {  // one dY brick per tap group (its own output lattice), side by side along N
+            const int nblk = p.merge_cout / p.cby;
             for (int j = 0; j < p.merge_ng; ++j)
-              tma_load_5d(b_base + (size_t)bs * b_stage_bytes + (size_t)j * yblock_bytes, &p.dy_maps_merged[j],
-                          &b_full[bs], 0, w0 + p.merge_off[j][2], h0 + p.merge_off[j][1], d0 + p.merge_off[j][0], b);
+              for (int h = 0; h < nblk; ++h)
+                tma_load_5d(b_base + (size_t)bs * b_stage_bytes + (size_t)(j * nblk + h) * yblock_bytes,
+                            &p.dy_maps_merged[j], &b_full[bs], h * p.cby, w0 + p.merge_off[j][2], h0 + p.merge_off[j][1],
+                            d0 + p.merge_off[j][0], b);
           } else {
             for (int j = 0; j < p.BN / p.cby; ++j)
               tma_load_5d(b_base + (size_t)bs * b_stage_bytes + (size_t)j * yblock_bytes, &p.dy_map, &b_full[bs],
@@ -718,20 +729,22 @@ int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   q.cbx = block_width(p.Cin);
   // Merge mode (ConvTranspose3d(k == s) weight gradient, generic_UNet.py:335-336): every tap group holds ONE tap with the
   // same input offset and differs only in its output lattice -> all groups share the X brick; their dY bricks sit side by
-  // side along N (N = ngroups * Cout <= 256) and the activations are streamed once instead of once per group.
-  bool merge = p.ngroups > 1 && p.ngroups * p.Cout <= 256 && (p.Cout == 16 || p.Cout == 32 || p.Cout == 64);
+  // side along N (N = groups * Cout <= 256, `merge_per` groups per launch) and the activations are streamed once per
+  // launch instead of once per group.
+  int merge_per = (p.Cout == 16 || p.Cout == 32 || p.Cout == 64 || p.Cout == 128) ? min(p.ngroups, 256 / p.Cout) : 1;
+  bool merge = p.ngroups > 1 && merge_per > 1 && p.ngroups % merge_per == 0;
   for (int g = 0; g < p.ngroups && merge; ++g) {
     merge = p.group_tap_begin[g + 1] - p.group_tap_begin[g] == 1;
     for (int k = 0; k < 3 && merge; ++k)
       merge = p.tap_off[p.group_tap_begin[g]][k] == p.tap_off[p.group_tap_begin[0]][k];
   }
-  q.BN = merge ? p.ngroups * p.Cout : p.Cout;
+  q.BN = merge ? merge_per * p.Cout : p.Cout;
   if (q.BN > 256) {
     q.BN = 0;
     for (int c = 256; c >= 16; c -= 16)
       if (p.Cout % c == 0) { q.BN = c; break; }
   }
-  q.cby = merge ? p.Cout : block_width(q.BN);
+  q.cby = merge ? min(p.Cout, 64) : block_width(q.BN);
   q.blocks_per_tap = p.Cin / q.cbx;
   q.blocks_per_tile = 128 / q.cbx;
   q.is_f16 = p.dtype == MTB200_F16;
@@ -792,8 +805,10 @@ int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   cudaError_t ce = cudaFuncSetAttribute(wgrad_taps_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (ce != cudaSuccess) { set_error("wgrad_taps(umma): cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return MTB200_ERR_CUDA; }
 
+  static CUtensorMap group_maps[MTB200_MAX_GROUPS];
+  int group_off[MTB200_MAX_GROUPS][3];
   if (merge) {
-    q.merge_ng = p.ngroups;
+    q.merge_ng = merge_per;
     q.merge_cout = p.Cout;
     const int ODims[3] = {p.Dof, p.Hof, p.Wof};
     for (int g = 0; g < p.ngroups; ++g) {
@@ -803,11 +818,10 @@ int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
       for (int k = 0; k < 3; ++k) {
         const int off = p.group_ooff[g][k];
         par[k] = ((off % p.os[k]) + p.os[k]) % p.os[k];
-        q.merge_off[g][k] = floor_div(off - par[k], p.os[k]);
+        group_off[g][k] = floor_div(off - par[k], p.os[k]);
         ext[k] = (ODims[k] - par[k] + p.os[k] - 1) / p.os[k];
         if (ext[k] < 1) { set_error("wgrad_taps(umma): empty dY lattice"); return MTB200_ERR_UNSUPPORTED; }
       }
-      q.merge_widx[g] = p.tap_widx[p.group_tap_begin[g]];
       cuuint32_t box[5] = {(cuuint32_t)q.cby, (cuuint32_t)q.bw, (cuuint32_t)q.bh, (cuuint32_t)q.bd, 1};
       dims[0] = p.Cout; dims[1] = ext[2]; dims[2] = ext[1]; dims[3] = ext[0]; dims[4] = p.B;
       strides[0] = (cuuint64_t)p.out_ldc * e * p.os[2];
@@ -815,13 +829,18 @@ int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
       strides[2] = (cuuint64_t)p.Hof * p.Wof * p.out_ldc * e * p.os[0];
       strides[3] = (cuuint64_t)p.Dof * p.Hof * p.Wof * p.out_ldc * e;
       uint8_t* base = (uint8_t*)p.dy + ((((long long)par[0] * p.Hof + par[1]) * p.Wof + par[2]) * p.out_ldc + p.out_coff) * e;
-      if (!encode_map(enc, &q.dy_maps_merged[g], dt, 5, base, dims, strides, box, q.cby * 2)) return MTB200_ERR_CUDA;
+      if (!encode_map(enc, &group_maps[g], dt, 5, base, dims, strides, box, q.cby * 2)) return MTB200_ERR_CUDA;
     }
   }
-  // one launch per group (the dY brick depends on the group's output offset); merge mode: a single launch
-  for (int g = 0; g < (merge ? 1 : p.ngroups); ++g) {
+  // one launch per group (the dY brick depends on the group's output offset); merge mode: `merge_per` groups per launch
+  for (int g = 0; g < p.ngroups; g += (merge ? merge_per : 1)) {
     q.tap_begin = p.group_tap_begin[g];
     q.tap_end = p.group_tap_begin[g + 1];
+    for (int j = 0; j < merge_per && merge; ++j) {
+      q.dy_maps_merged[j] = group_maps[g + j];
+      q.merge_widx[j] = p.tap_widx[p.group_tap_begin[g + j]];
+      for (int k = 0; k < 3; ++k) q.merge_off[j][k] = group_off[g + j][k];
+    }
     if (q.tap_end == q.tap_begin) continue;
     q.nblocks = (q.tap_end - q.tap_begin) * q.blocks_per_tap;
     q.ntiles = (q.nblocks + q.blocks_per_tile - 1) / q.blocks_per_tile;

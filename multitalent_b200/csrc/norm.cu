@@ -329,6 +329,73 @@ __global__ void __launch_bounds__(NT) in_bwd_apply_kernel(const T* __restrict__ 
   }
 }
 
+// Second generation of the pass above: the per-channel constants live in SHARED memory (two float4 per channel) instead
+// of 72 registers, so three to four blocks fit on an SM and ~4x more loads are in flight -- this pass mixes two read
+// streams with one write stream and needs the extra memory-level parallelism to reach the HBM roofline.
+//   dv = dact * lrelu'(sc * y + sh),   dy = k1 * (dv - m1 - xhat * m2) = k1 * dv + c1 * y + c0
+template <typename T, int NU>
+__global__ void __launch_bounds__(NT, 3) in_bwd_apply_smem_kernel(const T* __restrict__ dact, int d_ldc, int d_coff,
+                                                                  const T* __restrict__ y, int y_ldc, int y_coff,
+                                                                  T* __restrict__ dy, int dy_ldc, int dy_coff, long long nvox,
+                                                                  int B, int C, const float4* __restrict__ xform,
+                                                                  const float2* __restrict__ meanrstd,
+                                                                  const float* __restrict__ gamma,
+                                                                  const double* __restrict__ red, float* __restrict__ dgamma,
+                                                                  float* __restrict__ dbeta) {
+  extern __shared__ float4 s_const[];  // [C][2] = {sc, sh, slope, k1}, {c1, c0, -, -}
+  const Span sp = make_span(nvox, C);
+  const int b = blockIdx.y;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && dgamma) {
+    for (int c = threadIdx.x; c < C; c += NT) {
+      double g = 0.0, bt = 0.0;
+      for (int bb = 0; bb < B; ++bb) { bt += red[((long long)bb * C + c) * 2]; g += red[((long long)bb * C + c) * 2 + 1]; }
+      dgamma[c] += (float)g;
+      dbeta[c] += (float)bt;
+    }
+  }
+  const double inv_n = 1.0 / (double)nvox;
+  for (int c = threadIdx.x; c < C; c += NT) {
+    const long long i = (long long)b * C + c;
+    const float4 f = xform[i];
+    const float2 mr = meanrstd[i];
+    const float k1 = mr.y * gamma[c];
+    const float m1 = (float)(red[2 * i] * inv_n), m2 = (float)(red[2 * i + 1] * inv_n);
+    s_const[2 * c] = make_float4(f.x, f.y, f.z, k1);
+    s_const[2 * c + 1] = make_float4(-k1 * m2 * mr.y, k1 * (m2 * mr.y * mr.x - m1), 0.f, 0.f);
+  }
+  __syncthreads();
+  if (!sp.active) return;
+  const T* dbase = dact + (long long)b * nvox * d_ldc + d_coff + sp.cg * 8;
+  const T* ybase = y + (long long)b * nvox * y_ldc + y_coff + sp.cg * 8;
+  T* obase = dy + (long long)b * nvox * dy_ldc + dy_coff + sp.cg * 8;
+  const long long chunk = (long long)NU * sp.vstride;
+  for (long long base = (long long)blockIdx.x * chunk; base < nvox; base += (long long)gridDim.x * chunk) {
+    Raw8<T> d[NU], x[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const long long vv = min(base + sp.vlane + (long long)u * sp.vstride, nvox - 1);
+      d[u].load(dbase + vv * d_ldc);
+      x[u].load(ybase + vv * y_ldc);
+    }
+    int cg = sp.cg;
+    asm volatile("" : "+r"(cg));  // keeps the constant fetches inside the loop (no 48-register hoist)
+    const float4* cc = s_const + cg * 16;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const long long vv = base + sp.vlane + (long long)u * sp.vstride;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 P = cc[2 * j], Q = cc[2 * j + 1];
+        const float xv = x[u].get(j), dd = d[u].get(j);
+        const float dv = fmaf(xv, P.x, P.y) > 0.f ? dd : dd * P.z;
+        o[j] = fmaf(P.w, dv, fmaf(Q.x, xv, Q.y));
+      }
+      if (vv < nvox) store8<T>(obase + vv * dy_ldc, o);
+    }
+  }
+}
+
 int in_bwd_apply(const void* dact, int d_ldc, int d_coff, const void* y, int y_ldc, int y_coff, void* dy, int dy_ldc,
                  int dy_coff, int dtype, int B, long long nvox, int C, const float* xform, const float* meanrstd,
                  const float* gamma, const double* red, float* dgamma, float* dbeta, cudaStream_t s) {
@@ -341,8 +408,19 @@ int in_bwd_apply(const void* dact, int d_ldc, int d_coff, const void* y, int y_l
       reinterpret_cast<const T*>(dact), d_ldc, d_coff, reinterpret_cast<const T*>(y), y_ldc, y_coff,             \
       reinterpret_cast<T*>(dy), dy_ldc, dy_coff, nvox, B, C, reinterpret_cast<const float4*>(xform),             \
       reinterpret_cast<const float2*>(meanrstd), gamma, red, dgamma, dbeta)))
-  switch (norm_nu()) { case 1: MTB_IN_APPLY(1); break; case 2: MTB_IN_APPLY(2); break; default: MTB_IN_APPLY(4); }
+#define MTB_IN_APPLY2(NU_)                                                                                       \
+  MTB_DISPATCH_DTYPE(dtype, T, (in_bwd_apply_smem_kernel<T, NU_><<<grid, NT, (size_t)C * 32, s>>>(               \
+      reinterpret_cast<const T*>(dact), d_ldc, d_coff, reinterpret_cast<const T*>(y), y_ldc, y_coff,             \
+      reinterpret_cast<T*>(dy), dy_ldc, dy_coff, nvox, B, C, reinterpret_cast<const float4*>(xform),             \
+      reinterpret_cast<const float2*>(meanrstd), gamma, red, dgamma, dbeta)))
+  static const int variant = env_int("MTB200_APPLY_V", 2);
+  if (variant == 2 && dtype != MTB200_F32) {
+    switch (norm_nu()) { case 2: MTB_IN_APPLY2(2); break; case 8: MTB_IN_APPLY2(8); break; default: MTB_IN_APPLY2(4); }
+  } else {
+    switch (norm_nu()) { case 1: MTB_IN_APPLY(1); break; case 2: MTB_IN_APPLY(2); break; default: MTB_IN_APPLY(4); }
+  }
 #undef MTB_IN_APPLY
+#undef MTB_IN_APPLY2
   return check_launch("in_bwd_apply");
 }
 

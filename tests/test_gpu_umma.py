@@ -138,6 +138,54 @@ def test_conv_plane_streaming_matches_ffma(dtype, cin, cout, kernel, dims):
         _close(res[1][2], res[0][2], dtype)
 
 
+PW_CASES = [
+    # cin, cout, dims(B,D,H,W): 1x1x1 layers through the flat streaming kernel (impl=6)
+    (30, 47, (2, 4, 8, 16)),        # head: Cin_p 32 (64-byte rows), Cout_p 48 (dense 96-byte staging rows)
+    (47, 30, (2, 4, 8, 16)),        # head data gradient shape: Cin_p 48 runs as one zero-filled 64-channel chunk
+    (30, 47, (1, 5, 7, 11)),        # 385 voxels: ragged last tile (TMA clips the store)
+    (320, 47, (2, 4, 5, 4)),        # five K chunks
+    (60, 60, (1, 8, 8, 16)),        # Cout_p 64: 128-byte swizzled staging rows
+    (120, 240, (1, 4, 8, 8)),       # Cout_p 256: four staged column blocks, one CTA per SM
+    (1, 30, (1, 4, 8, 8)),          # Cin_p 16 (32-byte rows), Cout_p 32 (64-byte swizzled staging rows)
+    (240, 120, (2, 2, 8, 8)),       # four K chunks, two column blocks
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("cin,cout,dims", PW_CASES)
+def test_conv_pointwise_streaming_matches_ffma(dtype, cin, cout, dims):
+    """impl=6 forces the pointwise streaming kernel (error if the shape is outside its envelope): forward with bias and
+    InstanceNorm statistics, and the data gradient (the same kernel with the channel roles swapped)."""
+    _require_tcgen05()
+    from multitalent_b200.engine import ConvOp, Engine, Tape
+    torch.manual_seed(0)
+    B, D, H, W = dims
+    x = torch.randn(B, cin, D, H, W, device=DEV)
+    conv = nn.Conv3d(cin, cout, 1, 1, 0, bias=True).to(DEV)
+    op = ConvOp(conv.weight, conv.bias, (1, 1, 1), (1, 1, 1))
+    gy = torch.randn(B, cout, D, H, W, device=DEV)
+    want_stats = (D * H * W) % 128 == 0
+    res = []
+    for impl in (1, 6):
+        eng = Engine(dtype, impl)
+        tape = Tape()
+        xf = eng.input_feat(x)
+        y, st = eng.conv(op, xf, want_stats=want_stats)
+        y2 = eng.conv_plain(tape, op, xf)
+        eng.seed_grad(tape, y2, gy)
+        eng.run_backward(tape)
+        gx = tape.grad_feat(xf)[0].buf.clone()
+        res.append((y.buf.clone(), st.clone() if want_stats else None, gx))
+    _close(res[1][0], res[0][0], dtype)
+    _close(res[1][2], res[0][2], dtype)
+    if want_stats:
+        np.testing.assert_allclose(res[1][1].cpu().numpy(), res[0][1].cpu().numpy(),
+                                   atol=2e-2 * float(res[0][1].abs().max()) + 1e-3)
+    ref = torch.nn.functional.conv3d(x.to(dtype).float(), conv.weight.to(dtype).float(), conv.bias)
+    got = res[1][0][..., :cout].permute(0, 4, 1, 2, 3).float()
+    assert float((got - ref).abs().max()) <= 2e-2 * float(ref.abs().max()) + 1e-3
+
+
 LINE_CASES = [
     # cin, cout, kernel, dims(B,D,H,W): stride 1, W >= 72 (an M tile is one h-line of 128 w voxels), Cin_p <= 64
     (30, 30, (3, 3, 3), (1, 6, 20, 128)),
@@ -264,14 +312,14 @@ def test_plane_streaming_accumulate_flag():
     assert torch.equal(res[1][..., :32], base[..., :32])  # the other half is untouched
 
 
+@pytest.mark.parametrize("cin,cout", [(60, 30), (120, 60), (240, 120), (320, 240)])  # wgrad: 8 / 4 / 2 / 1 groups per launch
 @pytest.mark.parametrize("kernel", [(2, 2, 2), (1, 2, 2)])
-def test_conv_transpose_umma_matches_ffma(kernel):
+def test_conv_transpose_umma_matches_ffma(kernel, cin, cout):
     _require_tcgen05()
     from multitalent_b200.engine import ConvOp, Feat, Tape
     torch.manual_seed(1)
     dtype = torch.bfloat16
     e1, e2 = _engines(dtype)
-    cin, cout = 60, 30
     x = torch.randn(2, cin, 4, 6, 8, device=DEV)
     tu = nn.ConvTranspose3d(cin, cout, kernel, kernel, bias=False).to(DEV)
     op = ConvOp(tu.weight, None, kernel, kernel, transposed=True)
