@@ -71,7 +71,8 @@ typedef struct {
   int32_t impl;         /* 0 = auto, 1 = CUDA-core FFMA kernel, 2 = tcgen05 kernels (fastest applicable of the three),
                            3 = tcgen05 per-tap kernel only, 4 = tcgen05 plane-streaming kernel only,
                            5 = tcgen05 line-streaming kernel (dy taps merged into N) only,
-                           6 = tcgen05 pointwise (1x1x1) streaming kernel only */
+                           6 = tcgen05 pointwise (1x1x1) streaming kernel only,
+                           7 = tcgen05 group-merged lattice kernel (stride-2 dgrad / ConvTranspose fwd) only */
 } mtb200_conv_params;
 
 /* Weight-gradient of the same tap-table problem:
@@ -211,6 +212,19 @@ int mtb200_sgd_step(float* p, const float* g, float* buf, int64_t n, const doubl
 int mtb200_pack_weights(const float* w, int32_t Cout, int32_t Cin, int32_t ntap, int32_t transposed, int32_t swap_io,
                         void* packed, int32_t wdtype, int32_t Cout_p, int32_t Cin_p, int32_t split, int32_t split_p,
                         void* stream);
+/* One launch for every convolution of a network (the optimizer step invalidates all packed copies at once).  `descs` is
+ * a DEVICE array of `n` descriptors sorted by blk_begin; descriptor i owns thread blocks [blk_begin_i, blk_begin_{i+1}),
+ * (Cout_p/16) * (Cin_p/16) of them, `total_blocks` in all.  Either destination may be NULL; ntap <= 32; Cout_p and Cin_p
+ * are multiples of 16.  Same element semantics as mtb200_pack_weights. */
+typedef struct {
+  const float* w;
+  void* packed;        /* [ntap][Cout_p][Cin_p] */
+  void* packed_swap;   /* [ntap][Cin_p][Cout_p] */
+  int32_t Cout, Cin, ntap, transposed, Cout_p, Cin_p, split, split_p;
+  int32_t blk_begin, reserved;
+} mtb200_pack_desc;
+int mtb200_pack_weights_batched(const mtb200_pack_desc* descs, int32_t n, int32_t total_blocks, int32_t wdtype,
+                                void* stream);
 /* packed fp32 gradient [ntap][Cout_p][Cin_p] -> reference layout, grad (+)= scale * dw */
 int mtb200_unpack_wgrad(const float* dw, int32_t Cout, int32_t Cin, int32_t ntap, int32_t transposed, int32_t Cout_p,
                         int32_t Cin_p, int32_t split, int32_t split_p, float scale, int32_t accumulate, float* grad,

@@ -73,6 +73,7 @@ int sgd_step(float*, const float*, float*, long long, const double*, float, floa
              cudaStream_t);
 int pack_weights(const float*, int, int, int, int, int, void*, int, int, int, int, int, cudaStream_t);
 int unpack_wgrad(const float*, int, int, int, int, int, int, int, int, float, int, float*, cudaStream_t);
+int pack_weights_batched(const void*, int, int, int, cudaStream_t);
 int ncdhw_to_ndhwc(const float*, int, int, long long, void*, int, int, int, int, cudaStream_t);
 int ndhwc_to_ncdhw(const void*, int, int, int, int, int, long long, float*, cudaStream_t);
 
@@ -246,6 +247,12 @@ int mtb200_pack_weights(const float* w, int32_t Cout, int32_t Cin, int32_t ntap,
   MTB_REQUIRE(w && packed, "pack_weights: null pointer");
   return pack_weights(w, Cout, Cin, ntap, transposed, swap_io, packed, wdtype, Cout_p, Cin_p, split, split_p,
                       STREAM(stream));
+}
+
+int mtb200_pack_weights_batched(const mtb200_pack_desc* descs, int32_t n, int32_t total_blocks, int32_t wdtype,
+                                void* stream) {
+  MTB_REQUIRE(descs || n == 0, "pack_weights_batched: null descriptor table");
+  return pack_weights_batched(descs, n, total_blocks, wdtype, STREAM(stream));
 }
 
 int mtb200_unpack_wgrad(const float* dw, int32_t Cout, int32_t Cin, int32_t ntap, int32_t transposed, int32_t Cout_p,

@@ -268,15 +268,20 @@ int conv_pw_umma(const mtb200_conv_params& p, cudaStream_t s) {
   q.out_buf_bytes = pw_align1k(128LL * out_rowb);
   q.tmem_cols = 32;
   while (q.tmem_cols < 2 * q.BN) q.tmem_cols *= 2;
-  const int per_sm = q.tmem_cols <= 256 ? 2 : 1;
-  const int budget = (per_sm == 2 ? 110 : 220) * 1024;
-  q.obufs = 2;
-  int fixed = q.nkc * q.w_chunk_bytes + 2 * q.out_buf_bytes + 1024;
-  if ((budget - fixed) / q.a_stage_bytes < 3) {
-    q.obufs = 1;
-    fixed -= q.out_buf_bytes;
+  // two CTAs per SM when TMEM and shared memory allow it (small N, small weights), else one
+  int per_sm = q.tmem_cols <= 256 ? 2 : 1;
+  int fixed = 0;
+  for (;; per_sm = 1) {
+    const int budget = (per_sm == 2 ? 110 : 220) * 1024;
+    q.obufs = 2;
+    fixed = q.nkc * q.w_chunk_bytes + 2 * q.out_buf_bytes + 1024;
+    if ((budget - fixed) / q.a_stage_bytes < 3) {
+      q.obufs = 1;
+      fixed -= q.out_buf_bytes;
+    }
+    q.stages = min(PW_MAX_STAGES, (budget - fixed) / q.a_stage_bytes);
+    if (q.stages >= 2 || per_sm == 1) break;
   }
-  q.stages = min(PW_MAX_STAGES, (budget - fixed) / q.a_stage_bytes);
   if (q.stages < 2) return MTB200_ERR_UNSUPPORTED;
   q.ntiles = (int)((M + 127) / 128);
   q.tiles_per_b = max(1LL, nvox / 128);

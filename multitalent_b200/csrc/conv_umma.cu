@@ -41,6 +41,7 @@ int conv_halo_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_halo.c
 int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_line.cu
 int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s);  // wgrad_line.cu
 int conv_pw_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_pw.cu
+int conv_gm_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_gm.cu
 
 int umma_available() {
   static int cached = -1;
@@ -353,6 +354,11 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
     const int r = conv_pw_umma(p, s);
     if (r != MTB200_ERR_UNSUPPORTED) return r;
     if (p.impl == 6) { set_error("conv_taps(umma): problem outside the pointwise kernel's envelope"); return r; }
+  }
+  if (p.impl == 0 || p.impl == 2 || p.impl == 7) {  // 7 = group-merged lattice kernel only
+    const int r = conv_gm_umma(p, s);
+    if (r != MTB200_ERR_UNSUPPORTED) return r;
+    if (p.impl == 7) { set_error("conv_taps(umma): problem outside the group-merged kernel's envelope"); return r; }
   }
   if (p.impl == 5 || (p.impl != 3 && p.impl != 4 && p.impl != 6)) {
     const int r = conv_line_umma(p, s);

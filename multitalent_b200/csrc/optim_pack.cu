@@ -95,6 +95,61 @@ int pack_weights(const float* w, int Cout, int Cin, int ntap, int transposed, in
   return check_launch("pack_weights");
 }
 
+// ---- all weights of a network in ONE launch --------------------------------------------------------------------------
+// The optimizer step invalidates every packed copy, so each training step used to pay ~60 tiny pack launches with
+// strided 4-byte gathers.  Here a block owns one (layer, 16 couts x 16 cins) tile for all taps: the reference-layout
+// slab is read with consecutive threads on consecutive addresses ([ci][tap] runs of one cout row), staged in shared
+// memory, and written out as full 32-byte rows of both packed layouts.
+template <typename WT>
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const mtb200_pack_desc* __restrict__ descs, int n) {
+  __shared__ float tile[16 * 16 * 33];
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (descs[mid].blk_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const mtb200_pack_desc d = descs[lo];
+  const int local = (int)blockIdx.x - d.blk_begin;
+  const int tiles_ci = d.Cin_p / 16;
+  const int co0 = (local / tiles_ci) * 16, cip0 = (local % tiles_ci) * 16;
+  const int ntap = d.ntap, ntp = d.ntap | 1, row = 16 * ntap, total = 256 * ntap;
+  for (int e = threadIdx.x; e < total; e += 256) {
+    const int a = e / row, rem = e - a * row;
+    const int bq = rem / ntap, t = rem - bq * ntap;
+    const int co_l = d.transposed ? bq : a, ci_l = d.transposed ? a : bq;
+    const int co = co0 + co_l, cip = cip0 + ci_l;
+    int ci;
+    if (d.split > 0) ci = cip < d.split_p ? (cip < d.split ? cip : -1) : (cip - d.split_p + d.split);
+    else ci = cip;
+    float v = 0.f;
+    if (co < d.Cout && ci >= 0 && ci < d.Cin)
+      v = d.transposed ? d.w[((long long)ci * d.Cout + co) * ntap + t] : d.w[((long long)co * d.Cin + ci) * ntap + t];
+    tile[(co_l * 16 + ci_l) * ntp + t] = v;
+  }
+  __syncthreads();
+  if (d.packed) {
+    WT* out = reinterpret_cast<WT*>(d.packed);
+    for (int e = threadIdx.x; e < total; e += 256) {
+      const int ci_l = e & 15, co_l = (e >> 4) & 15, t = e >> 8;
+      Traits<WT>::st(out + ((long long)t * d.Cout_p + co0 + co_l) * d.Cin_p + cip0 + ci_l, tile[(co_l * 16 + ci_l) * ntp + t]);
+    }
+  }
+  if (d.packed_swap) {
+    WT* out = reinterpret_cast<WT*>(d.packed_swap);
+    for (int e = threadIdx.x; e < total; e += 256) {
+      const int co_l = e & 15, ci_l = (e >> 4) & 15, t = e >> 8;
+      Traits<WT>::st(out + ((long long)t * d.Cin_p + cip0 + ci_l) * d.Cout_p + co0 + co_l, tile[(co_l * 16 + ci_l) * ntp + t]);
+    }
+  }
+}
+
+int pack_weights_batched(const void* descs, int n, int total_blocks, int wdtype, cudaStream_t s) {
+  if (n <= 0 || total_blocks <= 0) return MTB200_OK;
+  MTB_DISPATCH_DTYPE(wdtype, WT, (pack_weights_batched_kernel<WT><<<total_blocks, 256, 0, s>>>(
+      reinterpret_cast<const mtb200_pack_desc*>(descs), n)));
+  return check_launch("pack_weights_batched");
+}
+
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, int Cout, int Cin, int ntap, int transposed, int Cout_p,
                                     int Cin_p, int split, int split_p, float scale, int accumulate,
                                     float* __restrict__ grad) {

@@ -189,6 +189,7 @@ class ConvOp:
             self.fwd_taps = taps_conv_fwd(self.kernel, self.stride)
             self.dgrad_taps = taps_conv_dgrad(self.kernel, self.stride)
         self._packed = {}
+        self.group = None  # PackGroup: every op of the network refreshed by one launch
 
     def out_dims(self, dims):
         B, D, H, W = dims
@@ -205,6 +206,8 @@ class ConvOp:
         hit = self._packed.get(key)
         if hit is not None and hit[0] == ver and hit[1].device == self.weight.device:
             return hit[1]
+        if self.group is not None and self.group.refresh(wdtype):
+            return self._packed[key][1]
         w = self.weight.detach()
         assert w.dtype == torch.float32 and w.is_contiguous()
         out = torch.empty((self.ntap, self.Cin_p, self.Cout_p) if swap_io else (self.ntap, self.Cout_p, self.Cin_p),
@@ -213,6 +216,67 @@ class ConvOp:
                L.ptr(out), L.dtype_enum(wdtype), self.Cout_p, self.Cin_p, self.split, self.split_p, L.stream_ptr())
         self._packed[key] = (ver, out)
         return out
+
+
+class PackGroup:
+    """The convolutions of one network.  The optimizer step invalidates every packed weight copy at once, so the copies
+    of ALL ops (forward layout and the data-gradient layout) are rebuilt by ONE launch (`mtb200_pack_weights_batched`)
+    the first time any of them is asked for after a step, instead of ~60 per-layer launches."""
+
+    def __init__(self, ops: Sequence["ConvOp"]):
+        self.ops = list(ops)
+        for op in self.ops:
+            op.group = self
+        self._state = {}  # wdtype -> (descriptor table on the device, total blocks, [(packed, packed_swap)], pointers)
+
+    def _build(self, wdtype):
+        dev = self.ops[0].weight.device
+        descs = (L.PackDesc * len(self.ops))()
+        bufs, blk = [], 0
+        for d, op in zip(descs, self.ops):
+            w = op.weight.detach()
+            a = torch.empty((op.ntap, op.Cout_p, op.Cin_p), dtype=wdtype, device=dev)
+            b = torch.empty((op.ntap, op.Cin_p, op.Cout_p), dtype=wdtype, device=dev)
+            d.w, d.packed, d.packed_swap = w.data_ptr(), a.data_ptr(), b.data_ptr()
+            d.Cout, d.Cin, d.ntap, d.transposed = op.Cout, op.Cin, op.ntap, int(op.transposed)
+            d.Cout_p, d.Cin_p, d.split, d.split_p = op.Cout_p, op.Cin_p, op.split, op.split_p
+            d.blk_begin = blk
+            blk += (op.Cout_p // 16) * (op.Cin_p // 16)
+            bufs.append((a, b))
+        table = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(dev)
+        ptrs = tuple(op.weight.data_ptr() for op in self.ops)
+        self._state[wdtype] = (table, blk, bufs, ptrs)
+
+    def refresh(self, wdtype) -> bool:
+        """Repack every op for `wdtype`; False if the group cannot serve the request (caller packs the single op)."""
+        ops = self.ops
+        w0 = ops[0].weight
+        if not w0.is_cuda or any(op.ntap > 32 or op.weight.dtype != torch.float32 or not op.weight.is_contiguous()
+                                 or op.weight.device != w0.device for op in ops):
+            return False
+        st = self._state.get(wdtype)
+        if st is None or st[3] != tuple(op.weight.data_ptr() for op in ops) or st[0].device != w0.device:
+            self._build(wdtype)
+            st = self._state[wdtype]
+        table, blocks, bufs, _ = st
+        L.call("mtb200_pack_weights_batched", L.ptr(table), len(ops), blocks, L.dtype_enum(wdtype), L.stream_ptr(),
+               tag="mtb200_pack_weights")
+        for op, (a, b) in zip(ops, bufs):
+            ver = (op.weight._version, _weights_epoch, op.weight.data_ptr())
+            op._packed[(wdtype, False)] = (ver, a)
+            op._packed[(wdtype, True)] = (ver, b)
+        return True
+
+
+def collect_ops(tree) -> List["ConvOp"]:
+    """Every ConvOp inside nested tuples / lists / dicts, in traversal order."""
+    if isinstance(tree, ConvOp):
+        return [tree]
+    if isinstance(tree, dict):
+        tree = list(tree.values())
+    if isinstance(tree, (list, tuple)):
+        return [op for t in tree for op in collect_ops(t)]
+    return []
 
 
 def _padded(v: Optional[torch.Tensor], n: int, fill=0.0):

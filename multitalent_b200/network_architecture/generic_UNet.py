@@ -17,7 +17,7 @@ import torch
 from torch import nn
 
 from .. import _lib as L
-from ..engine import ConvOp, Engine, Feat, Tape, pad_channels
+from ..engine import ConvOp, Engine, Feat, PackGroup, Tape, collect_ops, pad_channels
 from .neural_network import SegmentationNetwork
 
 
@@ -340,6 +340,7 @@ class Generic_UNet(SegmentationNetwork):
             h = self.seg_outputs[u]
             heads.append(ConvOp(h.weight, h.bias, h.kernel_size, h.stride))
         self._ops = dict(enc=enc, bott=bott, dec=dec, tu=tus, head=heads)
+        PackGroup(collect_ops(self._ops))
 
     def _native_forward(self, x, tape, only_full_res=False):
         """Kernel sequence of Generic_UNet.forward (generic_UNet.py:379-401).  `x` is an NCDHW tensor or an NDHWC Feat.

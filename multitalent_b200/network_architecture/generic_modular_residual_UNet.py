@@ -18,7 +18,7 @@ import torch
 from torch import nn
 
 from .. import _lib as L
-from ..engine import ConvOp, Engine, Feat, pad_channels
+from ..engine import ConvOp, Engine, Feat, PackGroup, collect_ops, pad_channels
 from .generic_UNet import Upsample, _UNetFunction
 from .neural_network import SegmentationNetwork
 
@@ -374,6 +374,7 @@ class FabiansUNet(SegmentationNetwork):
             dec.append((tu, convs, h))
         ops['dec'] = dec
         self._ops = ops
+        PackGroup(collect_ops(ops))
         self.__dict__['_ops_key'] = e.initial_conv.weight  # plain attribute: must not be registered as a parameter
 
     def _native_forward(self, x, tape, only_full_res=False):

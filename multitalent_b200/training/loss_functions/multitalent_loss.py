@@ -127,10 +127,22 @@ class _MultiTalentLossFn(torch.autograd.Function):
         return (None, None, None, None) + tuple(grads)
 
 
+_VALID_MASK_CACHE = {}
+
+
 def valid_mask_tensor(valid_regions: Sequence[Sequence[str]], device) -> torch.Tensor:
     """[B] int64 bitmasks of supervised channels from the per-sample region-name tuples
-    (`data_dict['properties'][b]['valid_regions']`, MT:328-329)."""
-    return torch.tensor([valid_channel_mask(v) for v in valid_regions], dtype=torch.int64, device=device)
+    (`data_dict['properties'][b]['valid_regions']`, MT:328-329).  Cached per combination of datasets in the batch: a
+    fresh `torch.tensor(..., device=cuda)` is a pageable H2D copy that blocks the host until the whole forward pass has
+    drained, which would stop the launch queue from running ahead of the GPU once per step."""
+    key = (str(device), tuple(tuple(v) for v in valid_regions))
+    t = _VALID_MASK_CACHE.get(key)
+    if t is None:
+        if len(_VALID_MASK_CACHE) > 4096:
+            _VALID_MASK_CACHE.clear()
+        t = torch.tensor([valid_channel_mask(v) for v in valid_regions], dtype=torch.int64, device=device)
+        _VALID_MASK_CACHE[key] = t
+    return t
 
 
 def multitalent_loss(outputs, targets, valid_regions, ds_loss_weights, group=None):

@@ -186,6 +186,62 @@ def test_conv_pointwise_streaming_matches_ffma(dtype, cin, cout, dims):
     assert float((got - ref).abs().max()) <= 2e-2 * float(ref.abs().max()) + 1e-3
 
 
+GM_CASES = [
+    # kind, cin, cout, stride, input dims (B, D, H, W) of the FORWARD op, accumulate
+    ("dgrad", 30, 60, (2, 2, 2), (2, 16, 16, 32), False),   # stride-2 conv 30 -> 60: dgrad 64 -> 32, 8 loads / 14 MMA runs
+    ("dgrad", 30, 60, (2, 2, 2), (1, 10, 12, 20), True),    # ragged bricks + TMA reduce-add into an existing gradient
+    ("dgrad", 30, 60, (1, 2, 2), (1, 6, 16, 16), True),     # 4 groups, taps with dz in [-1, 1]
+    ("dgrad", 16, 30, (2, 2, 2), (1, 8, 8, 16), False),     # 32 -> 16 channels (32-byte staging rows)
+    ("convT", 60, 30, (2, 2, 2), (2, 4, 6, 8), False),      # ConvTranspose3d 60 -> 30: one load, one N = 256 MMA
+    ("convT", 60, 30, (1, 2, 2), (1, 3, 8, 8), False),
+    ("convT", 30, 30, (2, 2, 2), (1, 5, 7, 9), False),      # ragged, Cin_p 32
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("kind,cin,cout,stride,dims,accumulate", GM_CASES)
+def test_conv_group_merged_matches_ffma(dtype, kind, cin, cout, stride, dims, accumulate):
+    """impl=7 forces the group-merged lattice kernel: data gradient of a strided 3x3x3 convolution (optionally
+    accumulating into an existing gradient through the TMA reduce-add) and ConvTranspose3d(k == s) forward, both writing
+    one half of a wider (concat-style) buffer."""
+    _require_tcgen05()
+    from multitalent_b200.engine import ConvOp, Engine, Feat
+    torch.manual_seed(3)
+    B, D, H, W = dims
+    res = []
+    if kind == "dgrad":
+        conv = nn.Conv3d(cin, cout, 3, stride, 1, bias=False).to(DEV)
+        op = ConvOp(conv.weight, None, (3, 3, 3), stride)
+        od = op.out_dims(dims)
+        dy_t = torch.zeros(od + (op.Cout_p,), device=DEV)
+        dy_t[..., :cout] = torch.randn(od + (cout,), device=DEV)
+        base = torch.randn(B, D, H, W, 2 * op.Cin_p, device=DEV).to(dtype)
+        for impl in (1, 7):
+            eng = Engine(dtype, impl)
+            dy = Feat(dy_t.to(dtype), 0, cout, op.Cout_p)
+            gx = Feat(base.clone(), op.Cin_p, cin, op.Cin_p)
+            eng._conv_call(op.dgrad_taps, dy, op.packed(eng.wdtype, True), None, gx, od[1:], None, accumulate, op.Cout_p,
+                           op.Cin_p)
+            res.append(gx.buf)
+        assert torch.equal(res[1][..., :op.Cin_p], base[..., :op.Cin_p])  # the other half is untouched
+    else:
+        tu = nn.ConvTranspose3d(cin, cout, stride, stride, bias=False).to(DEV)
+        op = ConvOp(tu.weight, None, stride, stride, transposed=True)
+        x = torch.randn(B, cin, D, H, W, device=DEV)
+        od = op.out_dims(dims)
+        for impl in (1, 7):
+            eng = Engine(dtype, impl)
+            xf = eng.input_feat(x)
+            cat = eng.new_buf(od, 2 * op.Cout_p, DEV, zero=True)
+            eng.conv(op, xf, Feat(cat, 0, cout, op.Cout_p))
+            res.append(cat)
+        assert float(res[1][..., op.Cout_p:].abs().max()) == 0.0
+        ref = torch.nn.functional.conv_transpose3d(x.to(dtype).float(), tu.weight.to(dtype).float(), None, stride)
+        got = res[1][..., :cout].permute(0, 4, 1, 2, 3).float()
+        assert float((got - ref).abs().max()) <= 2e-2 * float(ref.abs().max()) + 1e-3
+    _close(res[1], res[0], dtype)
+
+
 LINE_CASES = [
     # cin, cout, kernel, dims(B,D,H,W): stride 1, W >= 72 (an M tile is one h-line of 128 w voxels), Cin_p <= 64
     (30, 30, (3, 3, 3), (1, 6, 20, 128)),
