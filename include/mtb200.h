@@ -111,6 +111,18 @@ int mtb200_conv_taps(const mtb200_conv_params* p, void* stream);
 /* autograd of the above w.r.t. the weights (replaces cuDNN wgrad behind loss.backward(),
  * MultiTalent_Trainer_DDP.py:350,362) */
 int mtb200_wgrad_taps(const mtb200_wgrad_params* p, void* stream);
+/* ---- a1 (first layer): Conv3d(1 -> Cout, 3x3x3, stride 1, padding 1) on the single-channel patch
+ *      (generic_UNet.py:46 with input_channels = 1, conv_blocks_context.0.blocks.0) and its weight gradient, with the
+ *      GEMM K dimension = the 27 taps (im2col tile built in shared memory).  `x` = [B][D][H][W] voxels of `dtype`
+ *      (bf16 / fp16), `x_stride` elements apart (1 = compact volume, ldc = channel 0 of an NDHWC buffer).
+ *      `w` = packed [27][Cout_p][Cin_p] (only ci = 0 is read); `dw` the same shape in fp32 (atomically accumulated).
+ *      out / dy: NDHWC slices [B*D*H*W][ldc] + coff of Cout_p in {16, 32, 64} channels; stats as in mtb200_conv_taps. */
+int mtb200_conv_c1_fwd(const void* x, int64_t x_stride, const void* w, int32_t Cin_p, const float* bias, void* out,
+                       int32_t out_ldc, int32_t out_coff, int32_t Cout_p, double* stats, int32_t dtype, int32_t B,
+                       int32_t D, int32_t H, int32_t W, void* stream);
+int mtb200_conv_c1_wgrad(const void* x, int64_t x_stride, const void* dy, int32_t dy_ldc, int32_t dy_coff,
+                         int32_t Cout_p, float* dw, int32_t Cin_p, int32_t dtype, int32_t B, int32_t D, int32_t H,
+                         int32_t W, void* stream);
 /* column sums: out[c] (+)= sum_rows m[row*ldc + coff + c]   (bias gradients), fp32 out */
 int mtb200_colsum(const void* m, int32_t dtype, int64_t rows, int32_t ldc, int32_t coff, int32_t C, float* out,
                   void* stream);

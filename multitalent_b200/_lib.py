@@ -84,6 +84,8 @@ SIGNATURES = {
     "mtb200_has_tcgen05": [],
     "mtb200_conv_taps": [C.POINTER(ConvParams), _vp],
     "mtb200_wgrad_taps": [C.POINTER(WgradParams), _vp],
+    "mtb200_conv_c1_fwd": [_vp, _i64, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "mtb200_conv_c1_wgrad": [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "mtb200_colsum": [_vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp],
     "mtb200_in_finalize": [_vp, _vp, _vp, _i32, _i32, _i64, _f32, _f32, _vp, _vp, _vp],
     "mtb200_in_stats": [_vp, _i32, _i32, _i64, _i32, _i32, _i32, _vp, _vp],

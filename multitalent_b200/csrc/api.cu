@@ -42,6 +42,9 @@ int wgrad_taps_ffma(const mtb200_wgrad_params& p, cudaStream_t s);
 int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s);   // conv_umma.cu
 int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s); // conv_umma.cu
 int umma_available();
+int conv_c1_fwd(const void*, long long, const void*, int, const float*, void*, int, int, int, double*, int, int, int, int,
+                int, cudaStream_t);  // conv_c1.cu
+int conv_c1_wgrad(const void*, long long, const void*, int, int, int, float*, int, int, int, int, int, int, cudaStream_t);
 int colsum(const void* m, int dtype, long long rows, int ldc, int coff, int C, float* out, cudaStream_t s);
 int in_finalize(const double*, const float*, const float*, int, int, long long, float, float, float*, float*,
                 cudaStream_t);
@@ -117,6 +120,22 @@ int mtb200_wgrad_taps(const mtb200_wgrad_params* p, void* stream) {
     if (r != MTB200_ERR_UNSUPPORTED) return r;  // shapes the tensor-core kernel does not cover use the CUDA-core one
   }
   return wgrad_taps_ffma(*p, STREAM(stream));
+}
+
+int mtb200_conv_c1_fwd(const void* x, int64_t x_stride, const void* w, int32_t Cin_p, const float* bias, void* out,
+                       int32_t out_ldc, int32_t out_coff, int32_t Cout_p, double* stats, int32_t dtype, int32_t B,
+                       int32_t D, int32_t H, int32_t W, void* stream) {
+  MTB_REQUIRE(x && w && out && x_stride >= 1 && Cin_p >= 1, "conv_c1_fwd: bad arguments");
+  MTB_REQUIRE(out_coff + Cout_p <= out_ldc, "conv_c1_fwd: channel slice exceeds ldc");
+  return conv_c1_fwd(x, x_stride, w, Cin_p, bias, out, out_ldc, out_coff, Cout_p, stats, dtype, B, D, H, W, STREAM(stream));
+}
+
+int mtb200_conv_c1_wgrad(const void* x, int64_t x_stride, const void* dy, int32_t dy_ldc, int32_t dy_coff,
+                         int32_t Cout_p, float* dw, int32_t Cin_p, int32_t dtype, int32_t B, int32_t D, int32_t H,
+                         int32_t W, void* stream) {
+  MTB_REQUIRE(x && dy && dw && x_stride >= 1 && Cin_p >= 1, "conv_c1_wgrad: bad arguments");
+  MTB_REQUIRE(dy_coff + Cout_p <= dy_ldc, "conv_c1_wgrad: channel slice exceeds ldc");
+  return conv_c1_wgrad(x, x_stride, dy, dy_ldc, dy_coff, Cout_p, dw, Cin_p, dtype, B, D, H, W, STREAM(stream));
 }
 
 int mtb200_colsum(const void* m, int32_t dtype, int64_t rows, int32_t ldc, int32_t coff, int32_t C, float* out,

@@ -1,0 +1,458 @@
+// First layer of the U-Net: Conv3d(1 -> 30, 3x3x3, stride 1, padding 1) on the single-channel CT patch
+// (generic_UNet.py:46 with input_channels = 1; conv_blocks_context.0.blocks.0) and its weight gradient.
+//
+// With one input channel the generic kernels pad Cin to 16 and spend 9 (forward) / 24 (wgrad) N = 96 MMAs per 128 voxels
+// on a layer that does 54 FLOP per output byte -- it is an HBM stream (1 GB of bf16 output per bs4 step).  Here the GEMM
+// K dimension is the TAP index instead: four builder warps assemble the im2col tile A[128 voxels][32 = 27 taps + 5 zeros]
+// (64-byte rows, SWIZZLE_64B image) straight from the 1-channel volume (27 two-byte loads per voxel, L1-resident), and
+//   forward : D[128 vox][Cout] = A . B^T,  B[co][tap] resident (K-major), 2 MMAs per tile, pointwise-style epilogue
+//             (+bias, InstanceNorm sum / sum-of-squares, staged TMA store);
+//   wgrad   : D[tap][co] += A^T . dY -- the SAME shared-memory image read as an MN-major operand (rows = K = voxels),
+//             dY tiles by TMA, one TMEM accumulator per CTA for the whole kernel, 27 x Cout fp32 atomics at the end.
+// Persistent CTAs (several per SM), work unit = (b, d, h, 128-wide w tile).
+#include "umma.cuh"
+
+namespace mtb {
+
+using namespace um;
+
+constexpr int C1_STAGES = 4;
+constexpr int C1_FWD_THREADS = 416;    // 8 builder warps, MMA warp, 4 epilogue warps
+constexpr int C1_WG_THREADS = 448;     // 8 builder warps, MMA warp, dY producer warp, 4 epilogue warps
+constexpr int C1_ROWB = 64;            // bytes per im2col row (32 taps x 2 B)
+
+struct C1Params {
+  CUtensorMap o_map;       // forward: output / wgrad: dY, both {C, W, B*D*H} with box {C, 128, 1}
+  const void* x;           // single-channel volume, element stride xs between consecutive voxels
+  long long xs;
+  const void* w;           // packed [27][Cout][Cin_p] (only ci = 0 is read)
+  int Cin_p;
+  const float* bias;
+  double* stats;
+  float* dw;               // wgrad: [27][Cout][Cin_p] fp32
+  int B, D, H, W, Cout;
+  int ntw;
+  uint32_t units;
+  int out_mask;            // staging swizzle mask of the Cout * 2-byte rows
+  int is_f16;
+};
+
+// one im2col row per thread: 27 taps of voxel (b, d, h, w) -> four swizzled 16-byte chunks of stage row r.
+// COMPACT (voxel stride 1): the three dx taps of a line are immediate offsets of one pointer.
+template <bool COMPACT>
+__device__ __forceinline__ void c1_build_row(const C1Params& p, uint8_t* stage, int r, int b, int d, int h, int w) {
+  const uint16_t* x = reinterpret_cast<const uint16_t*>(p.x);
+  const long long xs = COMPACT ? 1 : p.xs;
+  const bool okl = w >= 1 && w <= p.W, okc = w < p.W, okr = w + 1 < p.W;
+  const uint16_t* center = x + ((((long long)b * p.D + d) * p.H + h) * p.W + w) * xs;
+  const long long sh = (long long)p.W * xs, sd = (long long)p.H * sh;
+  uint32_t v[27];
+#pragma unroll
+  for (int dz = -1; dz <= 1; ++dz) {
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const bool line_ok = (unsigned)(d + dz) < (unsigned)p.D && (unsigned)(h + dy) < (unsigned)p.H;
+      const uint16_t* line = center + dz * sd + dy * sh;
+      const int t = ((dz + 1) * 3 + (dy + 1)) * 3;
+      v[t] = 0u; v[t + 1] = 0u; v[t + 2] = 0u;
+      if (line_ok && okl) v[t] = (uint32_t)__ldg(line - xs);
+      if (line_ok && okc) v[t + 1] = (uint32_t)__ldg(line);
+      if (line_ok && okr) v[t + 2] = (uint32_t)__ldg(line + xs);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t wd[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t0 = c * 8 + 2 * j, t1 = t0 + 1;
+      const uint32_t lo = t0 < 27 ? v[t0 < 27 ? t0 : 0] : 0u, hi = t1 < 27 ? v[t1 < 27 ? t1 : 0] : 0u;
+      wd[j] = lo | (hi << 16);
+    }
+    uint32_t off = (uint32_t)r * C1_ROWB + (uint32_t)c * 16u;
+    off ^= ((off >> 7) & 3u) << 4;
+    *reinterpret_cast<uint4*>(stage + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+  }
+}
+
+// work unit -> (b, d, h, w tile); 32-bit arithmetic (64-bit divisions here cost more than the tile's real work)
+__device__ __forceinline__ void c1_unit(const C1Params& p, uint32_t u, int& b, int& d, int& h, int& w0) {
+  const uint32_t ntw = (uint32_t)p.ntw, H = (uint32_t)p.H, D = (uint32_t)p.D;
+  const uint32_t tw = ntw == 1 ? 0u : u % ntw;
+  uint32_t row = ntw == 1 ? u : u / ntw;
+  const uint32_t rh = row / H;
+  h = (int)(row - rh * H);
+  const uint32_t rd = rh / D;
+  d = (int)(rh - rd * D);
+  b = (int)rd;
+  w0 = (int)tw * 128;
+}
+
+__device__ __forceinline__ void tma_load_3d_tile(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  tma_load_3d(dst, map, bar, c0, c1, c2);
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+// =====================================================================================================================
+// forward
+// =====================================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(C1_FWD_THREADS, 2) conv_c1_fwd_kernel(const __grid_constant__ C1Params p) {
+  extern __shared__ uint8_t dsmem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[C1_STAGES], empty_bar[C1_STAGES];
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_sum[64], s_sq[64], s_bias[64];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
+  const int a_stage_bytes = 128 * C1_ROWB;                           // 8 KB
+  uint8_t* a_base = dsmem;
+  uint8_t* b_tile = a_base + C1_STAGES * a_stage_bytes;              // [Cout][64 B], K-major, SWIZZLE_64B image
+  const int out_buf_bytes = ((128 * p.Cout * 2 + 1023) / 1024) * 1024;
+  uint8_t* o_base = b_tile + 4096;
+  const uint32_t tmem_cols = p.Cout <= 16 ? 32u : (uint32_t)(2 * p.Cout);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C1_STAGES; ++i) { mbar_init(&full_bar[i], 4); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 64) {
+    s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f;
+    s_bias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.Cout) ? p.bias[threadIdx.x] : 0.f;
+  }
+  // weight tile B[co][tap] from the packed weights (ci = 0), zero for taps 27..31
+  for (int i = threadIdx.x; i < p.Cout * 4; i += blockDim.x) {
+    const int co = i >> 2, c = i & 3;
+    const uint16_t* wp = reinterpret_cast<const uint16_t*>(p.w);
+    uint32_t wd[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t0 = c * 8 + 2 * j, t1 = t0 + 1;
+      const uint32_t lo = t0 < 27 ? (uint32_t)wp[((long long)t0 * p.Cout + co) * p.Cin_p] : 0u;
+      const uint32_t hi = t1 < 27 ? (uint32_t)wp[((long long)t1 * p.Cout + co) * p.Cin_p] : 0u;
+      wd[j] = lo | (hi << 16);
+    }
+    uint32_t off = (uint32_t)co * C1_ROWB + (uint32_t)c * 16u;
+    off ^= ((off >> 7) & 3u) << 4;
+    *reinterpret_cast<uint4*>(b_tile + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 8) tmem_alloc(&tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp < 8) {
+    // ===== im2col builders: thread = one voxel of the tile =====
+    // two groups of four builder warps take alternate tiles: one group's load latency (a new input line from L2 / HBM
+    // per tile, exposed by the proxy fence before the arrive) overlaps the other group's packing
+    const int grp = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
+    for (uint32_t gi = (uint32_t)grp, u = blockIdx.x + (uint32_t)grp * gridDim.x; u < p.units; gi += 2, u += 2 * gridDim.x) {
+      int b, d, h, w0;
+      c1_unit(p, u, b, d, h, w0);
+      const uint32_t stage = gi % C1_STAGES;
+      mbar_wait(&empty_bar[stage], ((gi / C1_STAGES) & 1u) ^ 1u);
+      uint8_t* st = a_base + (size_t)stage * a_stage_bytes;
+      if (p.xs == 1) c1_build_row<true>(p, st, r, b, d, h, w0 + r);
+      else c1_build_row<false>(p, st, r, b, d, h, w0 + r);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+    }
+  } else if (warp == 8) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = idesc_f16(p.is_f16 != 0, (uint32_t)p.Cout, false, false);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t a16 = __shfl_sync(0xffffffffu, (smem_u32(a_base) & 0x3FFFFu) >> 4, 0);
+    const uint32_t b16 = __shfl_sync(0xffffffffu, (smem_u32(b_tile) & 0x3FFFFu) >> 4, 0);
+    const uint32_t hi = (((8u * C1_ROWB) >> 4) & 0x3FFFu) | (1u << 14) | (4u << 29);  // SWIZZLE_64B
+    uint32_t gi = 0;
+    for (uint32_t u = blockIdx.x; u < p.units; u += gridDim.x, ++gi) {
+      const uint32_t stage = gi % C1_STAGES, buf = gi & 1u;
+      mbar_wait(&acc_empty[buf], ((gi >> 1) & 1u) ^ 1u);
+      mbar_wait(&full_bar[stage], (gi / C1_STAGES) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = a16 + stage * (uint32_t)(a_stage_bytes >> 4);
+        const uint32_t dcol = tmem_u + buf * (uint32_t)p.Cout;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+          umma_f16(dcol, ((uint64_t)hi << 32) | (uint64_t)(sa + 2u * ks), ((uint64_t)hi << 32) | (uint64_t)(b16 + 2u * ks),
+                   idesc, ks ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&acc_full[buf]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: warps 9..12, TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool want_stats = p.stats != nullptr;
+    const bool issuer = warp == 9 && lane == 0;
+    const int et = threadIdx.x - 288;  // 0..127
+    uint32_t gi = 0;
+    for (uint32_t u = blockIdx.x; u < p.units; u += gridDim.x, ++gi) {
+      int b, d, h, w0;
+      c1_unit(p, u, b, d, h, w0);
+      const uint32_t buf = gi & 1u;
+      uint8_t* stage_out = o_base + (size_t)buf * out_buf_bytes;
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&acc_full[buf], (gi >> 1) & 1u);
+      tc_fence_after();
+      const bool valid = w0 + row < p.W;
+      const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.Cout;
+      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tcol + (uint32_t)c0, r);
+        float lo[8], hi8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          lo[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
+          hi8[j] = __uint_as_float(r[8 + j]) + s_bias[c0 + 8 + j];
+        }
+        uint32_t off0 = (uint32_t)row * (uint32_t)p.Cout * 2u + (uint32_t)c0 * 2u;
+        uint32_t off1 = off0 + 16u;
+        off0 ^= ((off0 >> 7) & (uint32_t)p.out_mask) << 4;
+        off1 ^= ((off1 >> 7) & (uint32_t)p.out_mask) << 4;
+        store8<T>(reinterpret_cast<T*>(stage_out + off0), lo);
+        store8<T>(reinterpret_cast<T*>(stage_out + off1), hi8);
+        if (want_stats) {
+          float sv[16], ss[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float x0 = valid ? Traits<T>::round(lo[j]) : 0.f, x1 = valid ? Traits<T>::round(hi8[j]) : 0.f;
+            sv[j] = x0; ss[j] = x0 * x0;
+            sv[8 + j] = x1; ss[8 + j] = x1 * x1;
+          }
+          warp_colsum16(sv, lane);
+          warp_colsum16(ss, lane);
+          if ((lane & 1) == 0) {
+            const int col = colsum16_column(lane);
+            atomicAdd(&s_sum[c0 + col], sv[0]);
+            atomicAdd(&s_sq[c0 + col], ss[0]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (issuer) {
+        tma_store_3d(&p.o_map, stage_out, 0, w0, (b * p.D + d) * p.H + h);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (want_stats) {
+        const uint32_t next = u + gridDim.x;
+        const uint32_t per_b = (uint32_t)(p.D * p.H * p.ntw);
+        if (next >= p.units || next / per_b != (uint32_t)b) {
+          for (int c = et; c < p.Cout; c += 128) {
+            if (s_sum[c] != 0.f || s_sq[c] != 0.f) {
+              double* st = p.stats + ((long long)b * p.Cout + c) * 2;
+              atomicAdd(st, (double)s_sum[c]);
+              atomicAdd(st + 1, (double)s_sq[c]);
+              s_sum[c] = 0.f;
+              s_sq[c] = 0.f;
+            }
+          }
+        }
+      }
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// =====================================================================================================================
+// weight gradient
+// =====================================================================================================================
+__global__ void __launch_bounds__(C1_WG_THREADS, 2) conv_c1_wgrad_kernel(const __grid_constant__ C1Params p) {
+  extern __shared__ uint8_t dsmem_raw[];
+  __shared__ __align__(8) uint64_t a_full[C1_STAGES], y_full[C1_STAGES], empty_bar[C1_STAGES];
+  __shared__ __align__(8) uint64_t acc_full;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
+  const int a_stage_bytes = 128 * C1_ROWB;               // 8 KB: [128 voxels][32 taps]
+  const int y_stage_bytes = 128 * p.Cout * 2;            // [128 voxels][Cout]
+  uint8_t* a_base = dsmem;
+  uint8_t* y_base = a_base + C1_STAGES * a_stage_bytes + 1024;  // slack: the shifted (unused) M blocks read 3 rows past a stage
+  const bool have_work = blockIdx.x < p.units;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C1_STAGES; ++i) { mbar_init(&a_full[i], 4); mbar_init(&y_full[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) tmem_alloc(&tmem_slot, 64u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp < 8) {
+    // two groups of four builder warps take alternate tiles: one group's load latency (a new input line from L2 / HBM
+    // per tile, exposed by the proxy fence before the arrive) overlaps the other group's packing
+    const int grp = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
+    for (uint32_t gi = (uint32_t)grp, u = blockIdx.x + (uint32_t)grp * gridDim.x; u < p.units; gi += 2, u += 2 * gridDim.x) {
+      int b, d, h, w0;
+      c1_unit(p, u, b, d, h, w0);
+      const uint32_t stage = gi % C1_STAGES;
+      mbar_wait(&empty_bar[stage], ((gi / C1_STAGES) & 1u) ^ 1u);
+      uint8_t* st = a_base + (size_t)stage * a_stage_bytes;
+      if (p.xs == 1) c1_build_row<true>(p, st, r, b, d, h, w0 + r);
+      else c1_build_row<false>(p, st, r, b, d, h, w0 + r);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[stage]);
+    }
+  } else if (warp == 9) {
+    // ===== dY producer (rows past the end of a line are zero-filled by TMA) =====
+    uint32_t gi = 0;
+    for (uint32_t u = blockIdx.x; u < p.units; u += gridDim.x, ++gi) {
+      const uint32_t stage = gi % C1_STAGES;
+      mbar_wait(&empty_bar[stage], ((gi / C1_STAGES) & 1u) ^ 1u);
+      if (elect_one()) {
+        mbar_expect_tx(&y_full[stage], (uint32_t)y_stage_bytes);
+        tma_load_3d_tile(y_base + (size_t)stage * y_stage_bytes, &p.o_map, &y_full[stage], 0,
+                         (int)(p.ntw == 1 ? 0u : u % (uint32_t)p.ntw) * 128, (int)(p.ntw == 1 ? u : u / (uint32_t)p.ntw));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 8) {
+    // ===== MMA issuer: D[128 = (shift block, tap)][Cout] += A^T . dY, both operands MN-major =====
+    const uint32_t idesc = idesc_f16(p.is_f16 != 0, (uint32_t)p.Cout, true, true);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t a16 = __shfl_sync(0xffffffffu, (smem_u32(a_base) & 0x3FFFFu) >> 4, 0);
+    const uint32_t y16 = __shfl_sync(0xffffffffu, (smem_u32(y_base) & 0x3FFFFu) >> 4, 0);
+    const uint32_t yrow = (uint32_t)p.Cout * 2u;
+    const uint32_t hi_a = ((8u * C1_ROWB) >> 4) | (1u << 14) | (4u << 29);                  // SBO = 8 rows, SWIZZLE_64B
+    const uint32_t lbo_a = ((uint32_t)C1_ROWB >> 4) << 16;                                    // M blocks 1..3: shifted views (unused)
+    const uint32_t lay_y = yrow == 128 ? 2u : (yrow == 64 ? 4u : 6u);
+    const uint32_t hi_y = ((8u * yrow) >> 4) | (1u << 14) | (lay_y << 29);
+    uint32_t gi = 0;
+    for (uint32_t u = blockIdx.x; u < p.units; u += gridDim.x, ++gi) {
+      const uint32_t stage = gi % C1_STAGES;
+      mbar_wait(&a_full[stage], (gi / C1_STAGES) & 1u);
+      mbar_wait(&y_full[stage], (gi / C1_STAGES) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = (a16 + stage * (uint32_t)(a_stage_bytes >> 4)) | lbo_a;
+        const uint32_t sy = y16 + stage * (uint32_t)(y_stage_bytes >> 4);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_f16(tmem_u, ((uint64_t)hi_a << 32) | (uint64_t)(sa + (uint32_t)(kk * C1_ROWB)),
+                   ((uint64_t)hi_y << 32) | (uint64_t)(sy + (uint32_t)kk * yrow), idesc, (gi > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+      }
+      __syncwarp();
+    }
+    if (have_work) {
+      if (elect_one()) umma_commit(&acc_full);
+      __syncwarp();
+    }
+  } else if (have_work) {
+    // ===== epilogue (once): rows 0..26 of the accumulator = taps =====
+    const int q = warp & 3;
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    if (q == 0) {
+      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + (uint32_t)c0, r);
+        if (lane < 27) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float v = __uint_as_float(r[j]);
+            if (v != 0.f) atomicAdd(p.dw + ((long long)lane * p.Cout + c0 + j) * p.Cin_p, v);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64u);
+  }
+}
+
+// =====================================================================================================================
+// host
+// =====================================================================================================================
+static int c1_common(C1Params& q, const void* x, long long xs, int dtype, int B, int D, int H, int W, int Cout_p,
+                     void* mat, int ldc, int coff, bool swizzled_box) {
+  if (dtype != MTB200_BF16 && dtype != MTB200_F16) { set_error("conv_c1: 16-bit activations only"); return MTB200_ERR_UNSUPPORTED; }
+  if (!umma_encode_fn()) { set_error("conv_c1: no tensor-map encoder (not an sm_100 driver)"); return MTB200_ERR_UNSUPPORTED; }
+  if (Cout_p != 16 && Cout_p != 32 && Cout_p != 64) { set_error("conv_c1: Cout_p must be 16, 32 or 64"); return MTB200_ERR_UNSUPPORTED; }
+  if (ldc % 8 || coff % 8) { set_error("conv_c1: channel stride / offset must be multiples of 8"); return MTB200_ERR_UNSUPPORTED; }
+  memset(&q, 0, sizeof(q));
+  q.x = x; q.xs = xs;
+  q.B = B; q.D = D; q.H = H; q.W = W; q.Cout = Cout_p;
+  q.ntw = (W + 127) / 128;
+  if ((long long)B * D * H * q.ntw >= (1LL << 31) - 65536) { set_error("conv_c1: too many lines"); return MTB200_ERR_UNSUPPORTED; }
+  q.units = (uint32_t)((long long)B * D * H * q.ntw);
+  const int rowb = Cout_p * 2;
+  q.out_mask = rowb == 128 ? 7 : (rowb == 64 ? 3 : 1);
+  q.is_f16 = dtype == MTB200_F16;
+  cuuint64_t dims[3] = {(cuuint64_t)Cout_p, (cuuint64_t)W, (cuuint64_t)B * D * H};
+  cuuint64_t strides[2] = {(cuuint64_t)ldc * 2, (cuuint64_t)W * ldc * 2};
+  cuuint32_t box[3] = {(cuuint32_t)Cout_p, 128, 1};
+  (void)swizzled_box;
+  if (!umma_encode_map(&q.o_map, dtype, 3, (uint8_t*)mat + (size_t)coff * 2, dims, strides, box, rowb)) return MTB200_ERR_CUDA;
+  return MTB200_OK;
+}
+
+int conv_c1_fwd(const void* x, long long xs, const void* w, int Cin_p, const float* bias, void* out, int out_ldc,
+                int out_coff, int Cout_p, double* stats, int dtype, int B, int D, int H, int W, cudaStream_t s) {
+  static C1Params q;
+  if (int r = c1_common(q, x, xs, dtype, B, D, H, W, Cout_p, out, out_ldc, out_coff, true)) return r;
+  if (q.units == 0) return MTB200_OK;
+  q.w = w; q.Cin_p = Cin_p; q.bias = bias; q.stats = stats;
+  const int out_buf = ((128 * Cout_p * 2 + 1023) / 1024) * 1024;
+  const int smem = C1_STAGES * 128 * C1_ROWB + 4096 + 2 * out_buf + 1024;
+  const int gx = (int)min((long long)q.units, (long long)2 * num_sms());
+  cudaError_t e;
+  if (dtype == MTB200_BF16) {
+    e = cudaFuncSetAttribute(conv_c1_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) conv_c1_fwd_kernel<__nv_bfloat16><<<gx, C1_FWD_THREADS, smem, s>>>(q);
+  } else {
+    e = cudaFuncSetAttribute(conv_c1_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) conv_c1_fwd_kernel<__half><<<gx, C1_FWD_THREADS, smem, s>>>(q);
+  }
+  if (e != cudaSuccess) { set_error("conv_c1_fwd: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
+  return check_launch("conv_c1_fwd");
+}
+
+int conv_c1_wgrad(const void* x, long long xs, const void* dy, int dy_ldc, int dy_coff, int Cout_p, float* dw, int Cin_p,
+                  int dtype, int B, int D, int H, int W, cudaStream_t s) {
+  static C1Params q;
+  if (int r = c1_common(q, x, xs, dtype, B, D, H, W, Cout_p, const_cast<void*>(dy), dy_ldc, dy_coff, true)) return r;
+  if (q.units == 0) return MTB200_OK;
+  q.dw = dw; q.Cin_p = Cin_p;
+  const int smem = C1_STAGES * (128 * C1_ROWB + 128 * Cout_p * 2) + 1024 + 1024;
+  const int gx = (int)min((long long)q.units, (long long)2 * num_sms());
+  cudaError_t e = cudaFuncSetAttribute(conv_c1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { set_error("conv_c1_wgrad: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
+  conv_c1_wgrad_kernel<<<gx, C1_WG_THREADS, smem, s>>>(q);
+  return check_launch("conv_c1_wgrad");
+}
+
+}  // namespace mtb

@@ -28,7 +28,7 @@ constexpr int GM_MAX_OPS = 32;
 struct GmParams {
   CUtensorMap a_map, w_map, o_map[2];
   int B, tiles_d, tiles_h, tiles_w, bd, bh, bw;
-  long long ntiles;
+  uint32_t ntiles;
   int KC, Cout, ngroups, ncols;   // ncols = ngroups * Cout (accumulator width)
   int os[3];
   int grp_r[MTB200_MAX_GROUPS][3];
@@ -91,12 +91,16 @@ __global__ void __launch_bounds__(GM_THREADS, 1) conv_gm_umma_kernel(const __gri
     }
     __syncwarp();
     uint32_t gi = 0;
-    for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-      long long t = tile;
-      const int tw = (int)(t % p.tiles_w); t /= p.tiles_w;
-      const int th = (int)(t % p.tiles_h); t /= p.tiles_h;
-      const int td = (int)(t % p.tiles_d);
-      const int b = (int)(t / p.tiles_d);
+    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      // 32-bit tile decode (64-bit divisions in every epilogue thread cost a visible share of a tile)
+      uint32_t t = tile;
+      const uint32_t t1 = t / (uint32_t)p.tiles_w;
+      const int tw = (int)(t - t1 * (uint32_t)p.tiles_w);
+      const uint32_t t2 = t1 / (uint32_t)p.tiles_h;
+      const int th = (int)(t1 - t2 * (uint32_t)p.tiles_h);
+      const uint32_t t3 = t2 / (uint32_t)p.tiles_d;
+      const int td = (int)(t2 - t3 * (uint32_t)p.tiles_d);
+      const int b = (int)t3;
       const int d0 = td * p.bd, h0 = th * p.bh, w0 = tw * p.bw;
       for (int a = 0; a < p.nloads; ++a, ++gi) {
         const uint32_t stage = gi % (uint32_t)p.stages;
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) conv_gm_umma_kernel(const __gri
     mbar_wait(&w_full, 0);
     tc_fence_after();
     uint32_t gi = 0, k = 0;
-    for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++k) {
+    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++k) {
       const uint32_t buf = k & 1u;
       mbar_wait(&acc_empty[buf], ((k >> 1) & 1u) ^ 1u);
       tc_fence_after();
@@ -157,12 +161,16 @@ __global__ void __launch_bounds__(GM_THREADS, 1) conv_gm_umma_kernel(const __gri
     const int sbw = p.os[2] * p.bw, sbh = p.os[1] * p.bh;  // staged box extents along w, h (d: bd per parity half)
     const uint32_t orow_bytes = (uint32_t)p.Cout * 2u;
     uint32_t k = 0;
-    for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++k) {
-      long long t = tile;
-      const int tw = (int)(t % p.tiles_w); t /= p.tiles_w;
-      const int th = (int)(t % p.tiles_h); t /= p.tiles_h;
-      const int td = (int)(t % p.tiles_d);
-      const int b = (int)(t / p.tiles_d);
+    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++k) {
+      // 32-bit tile decode (64-bit divisions in every epilogue thread cost a visible share of a tile)
+      uint32_t t = tile;
+      const uint32_t t1 = t / (uint32_t)p.tiles_w;
+      const int tw = (int)(t - t1 * (uint32_t)p.tiles_w);
+      const uint32_t t2 = t1 / (uint32_t)p.tiles_h;
+      const int th = (int)(t1 - t2 * (uint32_t)p.tiles_h);
+      const uint32_t t3 = t2 / (uint32_t)p.tiles_d;
+      const int td = (int)(t2 - t3 * (uint32_t)p.tiles_d);
+      const int b = (int)t3;
       const uint32_t buf = k & 1u;
       mbar_wait(&acc_full[buf], (k >> 1) & 1u);
       tc_fence_after();
@@ -327,7 +335,8 @@ int conv_gm_umma(const mtb200_conv_params& p, cudaStream_t s) {
   if (best < 0) return MTB200_ERR_UNSUPPORTED;
   q.tiles_d = (p.Do + q.bd - 1) / q.bd; q.tiles_h = (p.Ho + q.bh - 1) / q.bh; q.tiles_w = (p.Wo + q.bw - 1) / q.bw;
   q.B = p.B;
-  q.ntiles = (long long)p.B * q.tiles_d * q.tiles_h * q.tiles_w;
+  if ((long long)p.B * q.tiles_d * q.tiles_h * q.tiles_w >= (1LL << 31) - 65536) return MTB200_ERR_UNSUPPORTED;
+  q.ntiles = (uint32_t)((long long)p.B * q.tiles_d * q.tiles_h * q.tiles_w);
   q.a_stage_bytes = 128 * rowb;
   q.w_bytes = gm_align1k((long long)nwt * wtile);
   const int orowb = p.Cout * 2;
@@ -367,7 +376,7 @@ int conv_gm_umma(const mtb200_conv_params& p, cudaStream_t s) {
     if (!umma_encode_map(&q.o_map[r0], p.dtype, 5, base, dims, strides, box, orowb)) return MTB200_ERR_CUDA;
   }
   const int smem = q.stages * q.a_stage_bytes + fixed;
-  const int gx = (int)min(q.ntiles, (long long)num_sms());
+  const int gx = (int)min((long long)q.ntiles, (long long)num_sms());
   cudaError_t e;
   if (p.dtype == MTB200_BF16) {
     e = cudaFuncSetAttribute(conv_gm_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

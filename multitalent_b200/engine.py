@@ -190,6 +190,9 @@ class ConvOp:
             self.dgrad_taps = taps_conv_dgrad(self.kernel, self.stride)
         self._packed = {}
         self.group = None  # PackGroup: every op of the network refreshed by one launch
+        # first layer on a single-channel patch: dedicated kernels with K = taps (csrc/conv_c1.cu)
+        self.c1 = (not transposed and self.Cin == 1 and self.kernel == (3, 3, 3) and self.stride == (1, 1, 1)
+                   and split == 0 and self.Cout_p in (16, 32, 64))
 
     def out_dims(self, dims):
         B, D, H, W = dims
@@ -381,7 +384,7 @@ class Engine:
 
     def __init__(self, dtype=torch.float32, impl=0):
         self.dtype = dtype
-        self.impl = impl  # 0 auto, 1 force FFMA, 2 force tcgen05
+        self.impl = impl  # 0 auto, 1 force FFMA, 2 force tcgen05 (3..7: one tcgen05 kernel family only, see mtb200.h; 8: as 2)
         self.wdtype = torch.float32 if dtype == torch.float32 else dtype
         self._materialize = None
         self._z64 = ZeroPool(torch.float64, 1 << 16)
@@ -414,9 +417,17 @@ class Engine:
         f = torch.zeros if zero else torch.empty
         return f(tuple(dims) + (ldc,), dtype=self.dtype, device=device)
 
-    def input_feat(self, x: torch.Tensor) -> Feat:
-        """NCDHW fp32 input (to_torch.py:18-31 contract) -> NDHWC materialised feature (zero-padded channels)."""
+    def use_c1(self, op: "ConvOp") -> bool:
+        """First-layer kernels (K = taps) apply: single input channel, 16-bit tensor-core path."""
+        return bool(op.c1 and self.materialize_inputs and self.impl in (0, 2, 8))
+
+    def input_feat(self, x: torch.Tensor, compact=False) -> Feat:
+        """NCDHW fp32 input (to_torch.py:18-31 contract) -> NDHWC materialised feature (zero-padded channels).
+        `compact` (single-channel input feeding the first-layer kernels): no channel padding, [B, D, H, W, 1]."""
         assert x.dim() == 5 and x.is_cuda, "input must be a [B, C, D, H, W] CUDA tensor"
+        if compact and x.shape[1] == 1:
+            B, _, D, H, W = x.shape
+            return Feat(x.detach().to(self.dtype).contiguous().view(B, D, H, W, 1), 0, 1, 1)
         x = x.detach().float().contiguous()
         B, Cc, D, H, W = x.shape
         Cp = pad_channels(Cc)
@@ -453,7 +464,8 @@ class Engine:
     # ---- forward primitives -------------------------------------------------------------------------------------
     def conv(self, op: ConvOp, x: Feat, out: Optional[Feat] = None, want_stats=False):
         """Raw convolution (or transposed convolution) of `x` into `out` (allocated if None).  Returns (out, stats)."""
-        assert x.Cp == op.Cin_p, "input slice width %d != conv's padded Cin %d" % (x.Cp, op.Cin_p)
+        c1 = self.use_c1(op) and x.xform is None
+        assert x.Cp == op.Cin_p or (c1 and x.Cp == 1), "input slice width %d != conv's padded Cin %d" % (x.Cp, op.Cin_p)
         x = self.operand(x)
         odims = op.out_dims(x.dims)
         dev = x.buf.device
@@ -461,6 +473,15 @@ class Engine:
             out = Feat(self.new_buf(odims, op.Cout_p, dev), 0, op.Cout, op.Cout_p)
         assert out.dims == odims and out.Cp == op.Cout_p
         stats = self._z64.take((odims[0], op.Cout_p, 2), dev) if want_stats else None
+        if c1:
+            B, D, H, W = x.dims
+            bias = _padded(op.bias, op.Cout_p)
+            L.call("mtb200_conv_c1_fwd", C.c_void_p(x.ptr() + x.coff * x.buf.element_size()), x.ldc,
+                   L.ptr(op.packed(self.wdtype, False)), op.Cin_p, L.ptr(bias), out.ptr(), out.ldc, out.coff, op.Cout_p,
+                   L.ptr(stats), L.dtype_enum(self.dtype), B, D, H, W, L.stream_ptr(),
+                   flops=self.conv_flops(op, odims), tag="conv_fwd",
+                   info=(1, op.Cout_p, tuple(odims[1:]), op.ntap, (1, 1, 1), (1, 1, 1)))
+            return out, stats
         grid = x.dims[1:] if op.transposed else odims[1:]
         self._conv_call(op.fwd_taps, x, op.packed(self.wdtype, False), _padded(op.bias, op.Cout_p), out, grid, stats,
                         False, op.Cin_p, op.Cout_p, flops=self.conv_flops(op, odims), tag="conv_fwd")
@@ -543,6 +564,17 @@ class Engine:
         x = self.operand(x)
         # ---- weight gradient (same tap table as the forward problem)
         dw = self._z32.take((op.ntap, op.Cout_p, op.Cin_p), dev)
+        if self.use_c1(op) and x.xform is None and not need_input_grad:
+            B, D, H, W = x.dims
+            L.call("mtb200_conv_c1_wgrad", C.c_void_p(x.ptr() + x.coff * x.buf.element_size()), x.ldc, dy.ptr(), dy.ldc,
+                   dy.coff, op.Cout_p, L.ptr(dw), op.Cin_p, dt, B, D, H, W, L.stream_ptr(),
+                   flops=self.conv_flops(op, dy.dims), tag="conv_wgrad",
+                   info=(1, op.Cout_p, tuple(dy.dims[1:]), op.ntap, (1, 1, 1), (1, 1, 1)))
+            self._finish_wgrad(tape, op, dw, dy, dt, dev, bias_grad_is_zero)
+            return
+        if x.Cp != op.Cin_p:
+            raise L.Mtb200Error("compact single-channel input: only the first-layer kernels can read it "
+                                "(no input gradient, 16-bit tensor-core path)")
         p = L.WgradParams()
         p.x, p.dy, p.dw = x.ptr(), dy.ptr(), dw.data_ptr()
         p.xform = x.xform.data_ptr() if x.xform is not None else None
@@ -557,6 +589,19 @@ class Engine:
         fl = self.conv_flops(op, dy.dims)
         L.call("mtb200_wgrad_taps", C.byref(p), L.stream_ptr(), flops=fl, tag="conv_wgrad",
                info=(op.Cin_p, op.Cout_p, (p.Do, p.Ho, p.Wo), op.ntap, op.fwd_taps.in_stride, op.fwd_taps.out_stride))
+        self._finish_wgrad(tape, op, dw, dy, dt, dev, bias_grad_is_zero)
+        # ---- data gradient
+        if not need_input_grad:
+            return
+        gx, have = tape.grad_feat(x)
+        grid = gx.dims[1:] if op.transposed else tuple(n // s for n, s in zip(gx.dims[1:], op.stride))
+        dyv = Feat(dy.buf, dy.coff, dy.C, dy.Cp)  # gradients carry no pending transform
+        self._conv_call(op.dgrad_taps, dyv, op.packed(self.wdtype, True), None, gx, grid, None, have, op.Cout_p,
+                        op.Cin_p, flops=fl, tag="conv_dgrad")
+        tape.mark(x)
+
+    def _finish_wgrad(self, tape, op: ConvOp, dw, dy: Feat, dt, dev, bias_grad_is_zero):
+        """Packed fp32 weight gradient -> the parameter's gradient (arena slot or autograd), plus the bias gradient."""
         gw = direct_grad(op.weight)
         if gw is not None:  # accumulate straight into the arena's gradient slot
             L.call("mtb200_unpack_wgrad", L.ptr(dw), op.Cout, op.Cin, op.ntap, int(op.transposed), op.Cout_p, op.Cin_p,
@@ -577,15 +622,6 @@ class Engine:
             L.call("mtb200_colsum", dy.ptr(), dt, dy.dims[0] * dy.nvox, dy.ldc, dy.coff, op.Cout_p, L.ptr(gb),
                    L.stream_ptr())
             tape.add_param_grad(op.bias, gb[:op.Cout])
-        # ---- data gradient
-        if not need_input_grad:
-            return
-        gx, have = tape.grad_feat(x)
-        grid = gx.dims[1:] if op.transposed else tuple(n // s for n, s in zip(gx.dims[1:], op.stride))
-        dyv = Feat(dy.buf, dy.coff, dy.C, dy.Cp)  # gradients carry no pending transform
-        self._conv_call(op.dgrad_taps, dyv, op.packed(self.wdtype, True), None, gx, grid, None, have, op.Cout_p,
-                        op.Cin_p, flops=fl, tag="conv_dgrad")
-        tape.mark(x)
 
     def conv_plain(self, tape: Optional[Tape], op: ConvOp, x: Feat, out: Optional[Feat] = None,
                    need_input_grad=True) -> Feat:

@@ -350,7 +350,7 @@ class Generic_UNet(SegmentationNetwork):
         if self._ops is None or self._ops['enc'][0][0][0].weight is not self.conv_blocks_context[0].blocks[0].conv.weight:
             self._build_ops()
         ops = self._ops
-        f = x if isinstance(x, Feat) else eng.input_feat(x)
+        f = x if isinstance(x, Feat) else eng.input_feat(x, compact=eng.use_c1(ops['enc'][0][0][0]))
         dev = f.buf.device
         skips = []
         first = True

@@ -242,6 +242,52 @@ def test_conv_group_merged_matches_ffma(dtype, kind, cin, cout, stride, dims, ac
     _close(res[1], res[0], dtype)
 
 
+C1_CASES = [
+    # cout, dims (B, D, H, W), compact input
+    (30, (2, 6, 10, 128), True),
+    (30, (1, 5, 7, 100), True),      # ragged w: masked statistics, clipped TMA store
+    (30, (1, 4, 9, 160), False),     # two w tiles (the second one 32 wide); channel 0 of a 16-channel NDHWC buffer
+    (60, (1, 3, 8, 48), True),       # Cout_p 64: 128-byte staging rows
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("cout,dims,compact", C1_CASES)
+def test_first_layer_kernels_match_ffma(dtype, cout, dims, compact):
+    """Conv3d(1 -> cout, 3x3x3) through the K = taps kernels (csrc/conv_c1.cu): forward with bias + InstanceNorm
+    statistics and the weight gradient, against the CUDA-core kernels on the padded NDHWC input."""
+    _require_tcgen05()
+    from multitalent_b200.engine import ConvOp, Engine, Tape
+    torch.manual_seed(4)
+    B, D, H, W = dims
+    x = torch.randn(B, 1, D, H, W, device=DEV)
+    conv = nn.Conv3d(1, cout, 3, 1, 1, bias=True).to(DEV)
+    op = ConvOp(conv.weight, conv.bias, (3, 3, 3), (1, 1, 1))
+    assert op.c1
+    gy = torch.randn(B, cout, D, H, W, device=DEV)
+    res = []
+    for impl in (1, 8):
+        eng = Engine(dtype, impl)
+        assert eng.use_c1(op) == (impl == 8)
+        tape = Tape()
+        xf = eng.input_feat(x, compact=compact and impl == 8)
+        y, st = eng.conv(op, xf, want_stats=True)
+        y2 = eng.conv_plain(tape, op, xf, need_input_grad=False)
+        eng.seed_grad(tape, y2, gy)
+        eng.run_backward(tape)
+        res.append((y.buf.clone(), st.clone(), tape.param_grads[id(conv.weight)].clone(),
+                    tape.param_grads[id(conv.bias)].clone()))
+    _close(res[1][0], res[0][0], dtype)
+    np.testing.assert_allclose(res[1][1].cpu().numpy(), res[0][1].cpu().numpy(),
+                               atol=2e-2 * float(res[0][1].abs().max()) + 1e-3)
+    gw0, gw1 = res[0][2].cpu().numpy(), res[1][2].cpu().numpy()
+    assert np.abs(gw1 - gw0).max() <= 2e-3 * np.abs(gw0).max() + 1e-6
+    np.testing.assert_allclose(res[1][3].cpu().numpy(), res[0][3].cpu().numpy(), rtol=1e-3, atol=1e-3)
+    ref = torch.nn.functional.conv3d(x.to(dtype).float(), conv.weight.to(dtype).float(), conv.bias, 1, 1)
+    got = res[1][0][..., :cout].permute(0, 4, 1, 2, 3).float()
+    assert float((got - ref).abs().max()) <= 2e-2 * float(ref.abs().max()) + 1e-3
+
+
 LINE_CASES = [
     # cin, cout, kernel, dims(B,D,H,W): stride 1, W >= 72 (an M tile is one h-line of 128 w voxels), Cin_p <= 64
     (30, 30, (3, 3, 3), (1, 6, 20, 128)),
