@@ -40,35 +40,64 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md "clocks" line).  In-process NVML
+    (initialised before the warm-up): forking `nvidia-smi` next to the launch loop costs a process spawn plus an NVML
+    attach per sample, which stalled the launching thread for tens of ms inside a 0.25 s timed region.  `nvidia-smi`
+    remains the fallback when pynvml is missing."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.01):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.index, self.period = index, period
+        self.samples, self._stop_evt, self.active = [], threading.Event(), threading.Event()
+        self.nv = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        if self.nv is not None:
+            nv = self.nv
+            mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            bits = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+            return mhz, self.max_mhz, [n for n, b in zip(self.NAMES, bits) if r & b]
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [s.strip() for s in out.strip().split(",")]
+        return float(parts[0]), float(parts[1]), [n for n, v in zip(self.NAMES, parts[2:6])
+                                                  if v.lower().startswith("active")]
 
     def run(self):
         while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [s.strip() for s in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+            if self.active.is_set():
+                try:
+                    self.samples.append(self._sample())
+                except Exception:
+                    pass
+            self._stop_evt.wait(self.period if self.nv is not None else 0.2)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=3)
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[3:7]) if v.lower().startswith("active")})
+        sm = [s[0] for s in self.samples]
+        mx = [s[1] for s in self.samples]
+        reasons = sorted({n for s in self.samples for n in s[2]})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples),
+                "source": "nvml (in-process)" if self.nv is not None else "nvidia-smi"}
 
 
 def cpu_oracle_step_factory(patch, seed=0):
@@ -144,6 +173,7 @@ def main():
     ap.add_argument("--patch", type=int, nargs=3, default=list(FULL_PATCH))
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (ncu passes only)")
     ap.add_argument("--no-profile", action="store_true", help="no per-launch CUDA events in the timed region")
     ap.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 force CUDA-core kernels, 2 force tcgen05")
     args = ap.parse_args()
@@ -188,21 +218,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)  # NVML attached before the warm-up; samples only while `active` is set
+    sampler.start()
     for _ in range(args.warmup):
         tr.train_step(d_data, d_tgt, valid, True)
     barrier()
 
     # ---- timed region: K steps, inputs resident in HBM (no per-launch instrumentation: this is `value`)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     n0 = L.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
-    e0.record()
-    for _ in range(args.steps):
+    sampler.active.set()
+    marks[0].record()
+    for i in range(args.steps):
         l, ce, dc = tr.train_step(d_data, d_tgt, valid, True)
-    e1.record()
+        marks[i + 1].record()
     barrier()
+    sampler.active.clear()
+    e0, e1 = marks[0], marks[-1]
+    ms_each = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
     launches = L.launch_count - n0
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -212,7 +246,7 @@ def main():
 
     # ---- the same K steps again with one CUDA-event pair around every launch (on the launching stream): per-kernel
     #      durations for the roofline section.  The events cost ~3 % of a step, which is why `value` is taken above.
-    ksum, ms_profiled = {}, None
+    ksum, ms_profiled, shapes = {}, None, {}
     if not args.no_profile:
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with L.KernelProfile() as kp:
@@ -224,6 +258,11 @@ def main():
             barrier()
         ksum = kp.summary()
         ms_profiled = p0.elapsed_time(p1) / args.steps
+        for tag, info, kms, fl, _nb in kp.per_launch():  # group launches by (family, problem shape)
+            g = shapes.setdefault((tag, repr(info)), {"launches": 0, "ms": 0.0, "flops": 0.0})
+            g["launches"] += 1
+            g["ms"] += kms
+            g["flops"] += fl
     clocks = sampler.stop()
 
     # ---- end to end through run_iteration: pinned host batch -> H2D -> step -> D2H of (l, ce, dc)
@@ -231,19 +270,21 @@ def main():
         while True:
             yield {'data': host_data, 'target': host_tgt, 'properties': batch['properties']}
     g = gen()
-    tr.run_iteration(g, True)
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(args.steps):
+    e2e_ms_per_step = None
+    if not args.no_e2e:
         tr.run_iteration(g, True)
-    t1.record()
-    barrier()
-    e2e_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_ms_per_step = float(e2e_ms.item()) / args.steps
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            tr.run_iteration(g, True)
+        t1.record()
+        barrier()
+        e2e_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        e2e_ms_per_step = float(e2e_ms.item()) / args.steps
 
     if rank != 0:
         return
@@ -251,21 +292,31 @@ def main():
     patches_per_step = args.batch * world
     vox_frac = float(np.prod(patch)) / float(np.prod(FULL_PATCH))
     value = patches_per_step / (ms_per_step * 1e-3)
-    e2e_value = patches_per_step / (e2e_ms_per_step * 1e-3)
+    e2e_value = patches_per_step / (e2e_ms_per_step * 1e-3) if e2e_ms_per_step else None
 
-    # roofline of the dominant kernel family (by device time inside the timed region)
-    conv = {k: v for k, v in ksum.items() if k.startswith("conv_")}
-    top = max(conv, key=lambda k: conv[k]["ms"]) if conv else None
+    # roofline of the dominant kernel = the (kernel family, problem shape) group with the most device time inside the
+    # timed region; algorithmic FLOPs per launch (true channel counts) / average measured launch duration
     total_kernel_ms = sum(v["ms"] for v in ksum.values())
+    conv_shapes = {k: v for k, v in shapes.items() if k[0].startswith("conv_") and v["flops"] > 0}
     roof = None
-    if top:
-        t = conv[top]
+    traffic_tab = {}
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from the committed ncu --set full
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic_tab = json.load(f)
+    if conv_shapes:
+        top = max(conv_shapes, key=lambda k: conv_shapes[k]["ms"])
+        t = conv_shapes[top]
         achieved = t["flops"] / (t["ms"] * 1e-3) / 1e12
         peak = pk["bf16_tflops_sustained"]
-        roof = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": pk["source"] + " (sustained bf16)",
+        fam = ksum[top[0]]
+        roof = {"kernel": top[0], "shape(Cin_p,Cout_p,grid,taps,in_stride,out_stride)": top[1], "bound": "tensor",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": traffic_tab.get("%s %s" % top), "peak_source": pk["source"] + " (sustained bf16)",
                 "launches": t["launches"], "share_of_kernel_time": t["ms"] / total_kernel_ms,
-                "flops_per_launch_avg": t["flops"] / t["launches"], "ms_per_launch_avg": t["ms"] / t["launches"]}
+                "flops_per_launch": t["flops"] / t["launches"], "ms_per_launch_avg": t["ms"] / t["launches"],
+                "family": {"launches": fam["launches"], "share_of_kernel_time": fam["ms"] / total_kernel_ms,
+                           "achieved": fam["flops"] / (fam["ms"] * 1e-3) / 1e12}}
     step_tflops = TRAIN_GFLOP_PER_PATCH * vox_frac * args.batch / ms_per_step  # GFLOP/ms == TFLOP/s
     line = {"metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -279,6 +330,11 @@ def main():
                     "ms_per_step": e2e_ms_per_step},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "ms_per_step_with_per_launch_events": ms_profiled,
+            "ms_each_step": [round(m, 3) for m in ms_each],
+            "top_shapes": [{"kernel": k[0], "shape": k[1], "launches": v["launches"],
+                            "ms_per_step": round(v["ms"] / args.steps, 4),
+                            "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["flops"] else None}
+                           for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])[:40]],
             "step_tflops_algorithmic": step_tflops / world * world if world == 1 else step_tflops,
             "step_frac_of_bf16_peak": step_tflops / pk["bf16_tflops_sustained"],
             "kernels": {k: {"launches": v["launches"], "ms_per_step": v["ms"] / args.steps,
