@@ -15,15 +15,17 @@
 // (dz, dx) of [96 = (dy, co)][Cin] K-major.  Four Q accumulators (96 TMEM columns each) rotate: the MMAs of line h'+1
 // overlap the epilogue of output line h'-1.
 //
-// Warp roles (11 warps): 0 = line producer (TMA), 1 = TMEM owner + MMA issuer, 2 = weight loader, 3..10 = epilogue
-// (two warps per TMEM lane quarter, 16 of the 32 output channels each).
+// Warp roles: 0 = line producer (TMA), 1 = TMEM owner + MMA issuer, 2 = weight loader, 3.. = EW epilogue warps
+// (EW / 4 warps per TMEM lane quarter, LN_CPT of the 32 output channels each).
 #include "umma.cuh"
 
 namespace mtb {
 
 using namespace um;
 
-constexpr int LN_THREADS = 352;   // 3 service warps + 8 epilogue warps
+// EW = epilogue warps: 8 (16 output channels per thread) or 16 (8 channels per thread; twice the warps to hide the
+// TMEM-load / store latencies of the per-line epilogue).  Threads = 3 service warps + EW epilogue warps.
+constexpr int ln_threads(int ew) { return 96 + 32 * ew; }
 constexpr int LN_MAX_STAGES = 6;
 constexpr int LN_QSLOTS = 4;
 constexpr int LN_WROWS = 130;   // 128 output columns + halo
@@ -47,6 +49,7 @@ struct LineParams {
   int grp_dzslot[9], grp_dxrow[9];    // which staged line, row offset (dx + 1)
   int grp_widx[9][3];            // weight slice of (group, dy = j - 1)
   int nhr, hlen, ntw;
+  int units;                     // work units walked by the persistent CTAs
   int accumulate, is_f16;
 };
 
@@ -56,14 +59,15 @@ __device__ __forceinline__ uint32_t ln_kmajor_hi(uint32_t row_bytes, uint32_t sb
   return ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
 }
 
-template <typename T, int ROWB>
-__global__ void __launch_bounds__(LN_THREADS, 1) conv_line_umma_kernel(const __grid_constant__ LineParams p) {
+template <typename T, int ROWB, int EW>
+__global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const __grid_constant__ LineParams p) {
+  constexpr int LN_CPT = 32 / (EW / 4);  // output channels per epilogue thread
   extern __shared__ uint8_t dsmem_raw[];
   __shared__ __align__(8) uint64_t st_full[LN_MAX_STAGES], st_empty[LN_MAX_STAGES];
   __shared__ __align__(8) uint64_t q_full[LN_QSLOTS], q_empty[LN_QSLOTS];
   __shared__ __align__(8) uint64_t w_full;
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_bias[LN_BN], s_sum[LN_BN], s_sq[LN_BN];
+  __shared__ float s_bias[LN_BN];
 
   constexpr int KSTEPS = ROWB / 32;
   constexpr uint32_t NCOLS = 3 * LN_BN;  // accumulator width
@@ -72,28 +76,32 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_line_umma_kernel(const __g
   uint8_t* st_base = dsmem;
   uint8_t* w_base = dsmem + (size_t)p.stages * p.stage_bytes;
 
-  // work unit: (b, d, h range, w tile)
-  int u = blockIdx.x;
-  const int hr = u % p.nhr; u /= p.nhr;
-  const int twi = u % p.ntw; u /= p.ntw;
-  const int d = u % p.D;
-  const int b = u / p.D;
-  const int hs = hr * p.hlen, he = min(p.H, hs + p.hlen);
-  const int w0 = twi * 128;
+  // PERSISTENT CTAs: blockIdx.x strides over the work units (b, d, h range, w tile); barriers, TMEM, weights and the
+  // pipeline state (global step counter `gs` -> stage ring / Q ring positions and parities) live for the whole kernel,
+  // so consecutive units overlap (the producer runs ahead into the next unit while the epilogue drains this one).
   const int n0 = blockIdx.y * LN_BN;
-  const int hfirst = max(hs - 1, 0), hlast = min(he, p.H - 1);
-  const int nsteps = hlast - hfirst + 1;
+  struct Unit { int b, d, hs, he, w0, hfirst, nsteps; };
+  auto decode = [&](int u) {
+    Unit t;
+    const int hr = u % p.nhr; u /= p.nhr;
+    const int twi = u % p.ntw; u /= p.ntw;
+    t.d = u % p.D;
+    t.b = u / p.D;
+    t.hs = hr * p.hlen;
+    t.he = min(p.H, t.hs + p.hlen);
+    t.w0 = twi * 128;
+    t.hfirst = max(t.hs - 1, 0);
+    t.nsteps = min(t.he, p.H - 1) - t.hfirst + 1;
+    return t;
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 1); }
-    for (int i = 0; i < LN_QSLOTS; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 8); }
+    for (int i = 0; i < LN_QSLOTS; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], EW); }
     mbar_init(&w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < LN_BN) {
-    s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f;
-    s_bias[threadIdx.x] = p.bias ? p.bias[n0 + threadIdx.x] : 0.f;
-  }
+  if (threadIdx.x < LN_BN) s_bias[threadIdx.x] = p.bias ? p.bias[n0 + threadIdx.x] : 0.f;
   if (warp == 1) tmem_alloc(&tmem_slot, 512u);
   tc_fence_before();
   __syncthreads();
@@ -102,18 +110,22 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_line_umma_kernel(const __g
 
   if (warp == 0) {
     // ===== line producer =====
-    for (int s = 0; s < nsteps; ++s) {
-      const int slot = s % p.stages;
-      mbar_wait(&st_empty[slot], (((uint32_t)(s / p.stages)) & 1u) ^ 1u);
-      if (elect_one()) {
-        mbar_expect_tx(&st_full[slot], (uint32_t)p.stage_tx);
-        uint8_t* dst = st_base + (size_t)slot * p.stage_bytes;
-        for (int z = 0; z < p.ndz; ++z)
-          for (int c = 0; c < p.nchunk; ++c)
-            tma_load_5d(dst + (size_t)z * p.line_bytes + (size_t)c * p.sub_bytes, &p.a_map, &st_full[slot], c * p.kcw,
-                        w0 - 1, hfirst + s, d + p.dz0 + z, b);
+    uint32_t gs = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+      const Unit t = decode(u);
+      for (int s = 0; s < t.nsteps; ++s, ++gs) {
+        const uint32_t slot = gs % (uint32_t)p.stages;
+        mbar_wait(&st_empty[slot], ((gs / (uint32_t)p.stages) & 1u) ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(&st_full[slot], (uint32_t)p.stage_tx);
+          uint8_t* dst = st_base + (size_t)slot * p.stage_bytes;
+          for (int z = 0; z < p.ndz; ++z)
+            for (int c = 0; c < p.nchunk; ++c)
+              tma_load_5d(dst + (size_t)z * p.line_bytes + (size_t)c * p.sub_bytes, &p.a_map, &st_full[slot], c * p.kcw,
+                          t.w0 - 1, t.hfirst + s, t.d + p.dz0 + z, t.b);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp == 2) {
     // ===== weight loader: every (group, dy, chunk) tile once =====
@@ -146,129 +158,155 @@ __global__ void __launch_bounds__(LN_THREADS, 1) conv_line_umma_kernel(const __g
     }
     mbar_wait(&w_full, 0);
     tc_fence_after();
-    for (int s = 0; s < nsteps; ++s) {
-      const int slot = s % p.stages;
-      const int qs = s % LN_QSLOTS;
-      mbar_wait(&q_empty[qs], (((uint32_t)(s / LN_QSLOTS)) & 1u) ^ 1u);
-      mbar_wait(&st_full[slot], ((uint32_t)(s / p.stages)) & 1u);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a_s = st16 + (uint32_t)slot * stage16;
-        const uint32_t dq = tmem_u + (uint32_t)qs * NCOLS;
+    uint32_t gs = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+      const int nsteps = decode(u).nsteps;
+      for (int s = 0; s < nsteps; ++s, ++gs) {
+        const uint32_t slot = gs % (uint32_t)p.stages;
+        const uint32_t qs = gs % LN_QSLOTS;
+        mbar_wait(&q_empty[qs], ((gs / LN_QSLOTS) & 1u) ^ 1u);
+        mbar_wait(&st_full[slot], (gs / (uint32_t)p.stages) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_s = st16 + slot * stage16;
+          const uint32_t dq = tmem_u + qs * NCOLS;
 #pragma unroll
-        for (int g = 0; g < 9; ++g) {
-          if (g < ngroups) {
+          for (int g = 0; g < 9; ++g) {
+            if (g < ngroups) {
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k)
-              umma_f16(dq, ln_desc64(hi, a_s + a_goff[g] + (uint32_t)(k * 2)), ln_desc64(hi, b_goff[g] + (uint32_t)(k * 2)),
-                       idesc, (g | k) ? 1u : 0u);
+              for (int k = 0; k < KSTEPS; ++k)
+                umma_f16(dq, ln_desc64(hi, a_s + a_goff[g] + (uint32_t)(k * 2)), ln_desc64(hi, b_goff[g] + (uint32_t)(k * 2)),
+                         idesc, (g | k) ? 1u : 0u);
+            }
           }
+          umma_commit(&st_empty[slot]);
+          umma_commit(&q_full[qs]);
         }
-        umma_commit(&st_empty[slot]);
-        umma_commit(&q_full[qs]);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    // ===== epilogue warps 3..10: TMEM lane quarter = warp % 4, channel half = (warp - 3) / 4; thread = one w column =====
+    // ===== epilogue warps 3..: TMEM lane quarter = warp % 4, channel part = (warp - 3) / 4; thread = one w column =====
     const int q = warp & 3;
-    const int half = (warp - 3) >> 2;
-    const int ww = w0 + q * 32 + lane;
-    const bool wvalid = ww < p.W;
+    const int part = (warp - 3) >> 2;
     T* out = reinterpret_cast<T*>(p.out);
-    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 16);
-    float csum[16], csq[16], bias[16];
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * LN_CPT);
+    float bias[LN_CPT];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { csum[j] = 0.f; csq[j] = 0.f; bias[j] = s_bias[half * 16 + j]; }
+    for (int j = 0; j < LN_CPT; ++j) bias[j] = s_bias[part * LN_CPT + j];
     const bool want_stats = p.stats != nullptr;
+    uint32_t gs0 = 0;  // global step index of the current unit's first line
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+      const Unit t = decode(u);
+      const int b = t.b, d = t.d, hs = t.hs, he = t.he, hfirst = t.hfirst;
+      const int ww = t.w0 + q * 32 + lane;
+      const bool wvalid = ww < p.W;
+      float csum[LN_CPT], csq[LN_CPT];
+#pragma unroll
+      for (int j = 0; j < LN_CPT; ++j) { csum[j] = 0.f; csq[j] = 0.f; }
 
-    auto emit = [&](int h) {
-      uint32_t r[3][16];
+      auto emit = [&](int h) {
+        uint32_t r[3][LN_CPT];
 #pragma unroll
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int hq = h + dy;
-        if (hq >= 0 && hq < p.H) {
-          tmem_ld16_async(tlane + (uint32_t)((hq - hfirst) % LN_QSLOTS) * NCOLS + (uint32_t)((dy + 1) * LN_BN), r[dy + 1]);
-        } else {  // out-of-volume line: zero contribution
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int hq = h + dy;
+          if (hq >= 0 && hq < p.H) {
+            tmem_ld_async(tlane + ((gs0 + (uint32_t)(hq - hfirst)) % LN_QSLOTS) * NCOLS + (uint32_t)((dy + 1) * LN_BN), r[dy + 1]);
+          } else {  // out-of-volume line: zero contribution
 #pragma unroll
-          for (int j = 0; j < 16; ++j) r[dy + 1][j] = 0u;
-        }
-      }
-      tmem_ld_fence(r[0]);
-      tmem_ld_fence(r[1]);
-      tmem_ld_fence(r[2]);
-      // the three accumulators are in registers: Q[h-1] is not needed by any later output line
-      tc_fence_before();
-      __syncwarp();
-      if (h - 1 >= hfirst && lane == 0) mbar_arrive(&q_empty[(h - 1 - hfirst) % LN_QSLOTS]);
-      if (wvalid) {
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          v[j] = bias[j] + __uint_as_float(r[0][j]) + __uint_as_float(r[1][j]) + __uint_as_float(r[2][j]);
-        T* orow = out + ((((long long)b * p.D + d) * p.H + h) * p.W + ww) * p.out_ldc + p.out_coff + n0 + half * 16;
-        if (p.accumulate) {
-          float ov[8];
-          load8<T>(orow, ov);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += ov[j];
-          load8<T>(orow + 8, ov);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[8 + j] += ov[j];
-        }
-        float lo[8], hi8[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi8[j] = v[8 + j]; }
-        store8<T>(orow, lo);
-        store8<T>(orow + 8, hi8);
-        if (want_stats) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float x = Traits<T>::round(v[j]);
-            csum[j] += x;
-            csq[j] = fmaf(x, x, csq[j]);
+            for (int j = 0; j < LN_CPT; ++j) r[dy + 1][j] = 0u;
           }
         }
-      }
-    };
+        tmem_ld_fence(r[0]);
+        tmem_ld_fence(r[1]);
+        tmem_ld_fence(r[2]);
+        // the three accumulators are in registers: Q[h-1] is not needed by any later output line
+        tc_fence_before();
+        __syncwarp();
+        if (h - 1 >= hfirst && lane == 0) mbar_arrive(&q_empty[(gs0 + (uint32_t)(h - 1 - hfirst)) % LN_QSLOTS]);
+        if (wvalid) {
+          float v[LN_CPT];
+#pragma unroll
+          for (int j = 0; j < LN_CPT; ++j)
+            v[j] = bias[j] + __uint_as_float(r[0][j]) + __uint_as_float(r[1][j]) + __uint_as_float(r[2][j]);
+          T* orow = out + ((((long long)b * p.D + d) * p.H + h) * p.W + ww) * p.out_ldc + p.out_coff + n0 + part * LN_CPT;
+#pragma unroll
+          for (int c8 = 0; c8 < LN_CPT; c8 += 8) {
+            float o8[8];
+            if (p.accumulate) {
+              load8<T>(orow + c8, o8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[c8 + j] += o8[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o8[j] = v[c8 + j];
+            store8<T>(orow + c8, o8);
+          }
+          if (want_stats) {
+#pragma unroll
+            for (int j = 0; j < LN_CPT; ++j) {
+              const float x = Traits<T>::round(v[j]);
+              csum[j] += x;
+              csq[j] = fmaf(x, x, csq[j]);
+            }
+          }
+        }
+      };
 
-    for (int s = 0; s < nsteps; ++s) {
-      const int hp = hfirst + s;
-      mbar_wait(&q_full[s % LN_QSLOTS], ((uint32_t)(s / LN_QSLOTS)) & 1u);
-      tc_fence_after();
-      if (hp - 1 >= hs) emit(hp - 1);
-      if (hp == p.H - 1 && hp < he) emit(hp);  // last line of the volume: Q[H] does not exist
-    }
-    if (want_stats) {
-      warp_colsum16(csum, lane);
-      warp_colsum16(csq, lane);
-      if ((lane & 1) == 0) {
-        const int col = colsum16_column(lane);
-        atomicAdd(&s_sum[half * 16 + col], csum[0]);
-        atomicAdd(&s_sq[half * 16 + col], csq[0]);
+      for (int s = 0; s < t.nsteps; ++s) {
+        const int hp = hfirst + s;
+        const uint32_t g = gs0 + (uint32_t)s;
+        mbar_wait(&q_full[g % LN_QSLOTS], (g / LN_QSLOTS) & 1u);
+        tc_fence_after();
+        if (hp - 1 >= hs) emit(hp - 1);
+        if (hp == p.H - 1 && hp < he) emit(hp);  // last line of the volume: Q[H] does not exist
       }
+      // emit(h) released Q[h-1] for h in [hs, he): the accumulators of lines he-1 .. hfirst+nsteps-1 are still held.
+      // Hand them back (every TMEM read of this warp has completed) so the next unit's MMAs can reuse the slots.
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0)
+        for (int hq = max(he - 1, hfirst); hq < hfirst + t.nsteps; ++hq) mbar_arrive(&q_empty[(gs0 + (uint32_t)(hq - hfirst)) % LN_QSLOTS]);
+      if (want_stats) {  // per-(b, channel) sums of this unit -> fp64 atomics (warp-level column sums first)
+        warp_colsum(csum, lane);
+        warp_colsum(csq, lane);
+        if (colsum_writer<LN_CPT>(lane)) {
+          const int col = part * LN_CPT + colsum_column<LN_CPT>(lane);
+          double* st = p.stats + ((long long)b * p.Cout + n0 + col) * 2;
+          atomicAdd(st, (double)csum[0]);
+          atomicAdd(st + 1, (double)csq[0]);
+        }
+      }
+      gs0 += (uint32_t)t.nsteps;
     }
   }
   __syncthreads();
-  if (p.stats && threadIdx.x < LN_BN) {
-    const int c = threadIdx.x;
-    if (s_sum[c] != 0.f || s_sq[c] != 0.f) {
-      double* st = p.stats + ((long long)b * p.Cout + n0 + c) * 2;
-      atomicAdd(st, (double)s_sum[c]);
-      atomicAdd(st + 1, (double)s_sq[c]);
-    }
-  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512u);
   }
 }
 
+template <typename T, int ROWB, int EW>
+static cudaError_t launch_line_ew(const LineParams& q, dim3 grid, int smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(conv_line_umma_kernel<T, ROWB, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) conv_line_umma_kernel<T, ROWB, EW><<<grid, ln_threads(EW), smem, s>>>(q);
+  return e;
+}
+
+// MTB200_LINE_EPI_WARPS=8|16 overrides the epilogue width (experiments); default 8 (measured faster, profiles/r1i_line_epi_ab.txt)
+static int line_epi_warps() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("MTB200_LINE_EPI_WARPS");
+    v = (e && atoi(e) == 16) ? 16 : 8;
+  }
+  return v;
+}
+
 template <typename T, int ROWB>
 static cudaError_t launch_line(const LineParams& q, dim3 grid, int smem, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(conv_line_umma_kernel<T, ROWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) conv_line_umma_kernel<T, ROWB><<<grid, LN_THREADS, smem, s>>>(q);
-  return e;
+  return line_epi_warps() == 8 ? launch_line_ew<T, ROWB, 8>(q, grid, smem, s) : launch_line_ew<T, ROWB, 16>(q, grid, smem, s);
 }
 
 static inline int ln_align1k(long long v) { return (int)(((v + 1023) / 1024) * 1024); }
@@ -351,18 +389,20 @@ int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s) {
   q.is_f16 = p.dtype == MTB200_F16;
   q.ntw = (p.Wo + 127) / 128;
   const int ny = p.Cout / LN_BN;
-  // split H into ranges: whole waves of the machine (one CTA per SM); every range recomputes two halo lines
+  // split H into ranges so that the units divide evenly over the persistent CTAs (one per SM and Cout block); every
+  // range recomputes two halo lines
+  const int gx_max = max(1, num_sms() / ny);
   {
-    const int sms = num_sms();
-    const long long base = (long long)p.B * p.Do * q.ntw * ny;
+    const long long base = (long long)p.B * p.Do * q.ntw;
     double best = -1;
     int best_nhr = 1;
     for (int nhr = 1; nhr <= max(1, p.Ho / 8); ++nhr) {
       const int hlen = (p.Ho + nhr - 1) / nhr;
       if ((p.Ho + hlen - 1) / hlen != nhr) continue;
-      const long long ctas = base * nhr;
-      const long long waves = (ctas + sms - 1) / sms;
-      const double eff = (double)ctas / (double)(waves * sms) * hlen / (hlen + 2.0 + 3.0);  // halo lines + prologue
+      const long long units = base * nhr;
+      const long long gx = units < gx_max ? units : (long long)gx_max;
+      const long long rounds = (units + gx - 1) / gx;
+      const double eff = (double)units / (double)(rounds * gx) * hlen / (hlen + 2.0);
       if (eff > best) { best = eff; best_nhr = nhr; }
     }
     q.nhr = best_nhr;
@@ -370,8 +410,9 @@ int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s) {
   }
   const long long units = (long long)p.B * p.Do * q.ntw * q.nhr;
   MTB_REQUIRE(units < (1LL << 31), "conv_line: too many work units");
+  q.units = (int)units;
   const int smem = max(116 * 1024, q.stages * q.stage_bytes + wbytes + 1024);  // one CTA per SM (512 TMEM columns each)
-  dim3 grid((unsigned)units, ny, 1);
+  dim3 grid((unsigned)(units < gx_max ? units : (long long)gx_max), ny, 1);
   cudaError_t e;
   if (p.dtype == MTB200_BF16) {
     e = rowb == 128 ? launch_line<__nv_bfloat16, 128>(q, grid, smem, s)

@@ -110,6 +110,21 @@ __device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[16]) {
                : "memory");
 }
 
+// 8-column variants (16 epilogue warps of the line kernel: 8 output channels per thread)
+__device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_async(uint32_t taddr, uint32_t (&r)[8]) { tmem_ld8_async(taddr, r); }
+__device__ __forceinline__ void tmem_ld_async(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16_async(taddr, r); }
+
 // K-major operand descriptor.  `row_bytes` = swizzle span = row pitch (128 / 64 / 32); `sbo` = byte distance between
 // consecutive 8-row groups.  base_offset stays 0: measured on the B200 (tools/umma_probe.cu), the swizzle is a pure
 // function of the shared-memory address, so any row-granular start and any group stride are legal.
@@ -149,6 +164,30 @@ __device__ __forceinline__ void warp_colsum16(float (&v)[16], int lane) {
 __device__ __forceinline__ int colsum16_column(int lane) {
   return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
+
+// same for 8 values per lane: v[0] = sum of column ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1); lanes that differ
+// only in bits 0..1 hold the same column
+__device__ __forceinline__ void warp_colsum8(float (&v)[8], int lane) {
+#pragma unroll
+  for (int off = 16, w = 8; off >= 4; off >>= 1, w >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < w / 2; ++j) {
+      const float send = up ? v[j] : v[j + w / 2];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+      v[j] = (up ? v[j + w / 2] : v[j]) + recv;
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ int colsum8_column(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
+
+// overload set so that callers templated / parameterised on the per-thread channel count need no branches
+__device__ __forceinline__ void warp_colsum(float (&v)[16], int lane) { warp_colsum16(v, lane); }
+__device__ __forceinline__ void warp_colsum(float (&v)[8], int lane) { warp_colsum8(v, lane); }
+template <int N> __device__ __forceinline__ int colsum_column(int lane) { return N == 16 ? colsum16_column(lane) : colsum8_column(lane); }
+template <int N> __device__ __forceinline__ bool colsum_writer(int lane) { return N == 16 ? (lane & 1) == 0 : (lane & 3) == 0; }
 
 }  // namespace um
 
