@@ -174,6 +174,9 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (ncu passes only)")
+    ap.add_argument("--no-infer", action="store_true", help="skip the sliding-window inference leg")
+    ap.add_argument("--infer-vol", type=int, nargs=3, default=[384, 320, 256],
+                    help="synthetic volume of the inference leg (27 tiles of 192x160x128 at step 0.5)")
     ap.add_argument("--no-profile", action="store_true", help="no per-launch CUDA events in the timed region")
     ap.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 force CUDA-core kernels, 2 force tcgen05")
     args = ap.parse_args()
@@ -286,6 +289,64 @@ def main():
             dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
         e2e_ms_per_step = float(e2e_ms.item()) / args.steps
 
+    # ---- inference leg (BASELINE.json metric: "train+infer"): sliding-window predict_3D of one synthetic volume per
+    #      rank (replicas only, no collective), patch 192x160x128, step 0.5, Gaussian weighting, no mirroring.
+    #      `value`: host volume in, probabilities + segmentation left on the device; `e2e`: the reference contract
+    #      (numpy in -> numpy out, i.e. including the D2H of the [47, X, Y, Z] fp32 probabilities).
+    infer = None
+    if not args.no_infer and patch == FULL_PATCH:
+        del d_data, d_tgt
+        tr._prefetched = {}
+        torch.cuda.empty_cache()
+        ivol = tuple(args.infer_vol)
+        vol = np.random.RandomState(7 + rank).randn(1, *ivol).astype(np.float32)
+        net = tr.network
+        steps_xyz = net._compute_steps_for_sliding_window(patch, ivol, 0.5)
+        ntiles = len(steps_xyz[0]) * len(steps_xyz[1]) * len(steps_xyz[2])
+        kw = dict(do_mirroring=False, mirror_axes=(0, 1, 2), use_sliding_window=True, step_size=0.5, use_gaussian=True,
+                  verbose=False)
+        ds, mode = net.do_ds, net.training
+        net.do_ds = False
+        net.eval()
+        try:
+            ikw = dict(kw, patch_size=patch, regions_class_order=tuple(range(47)), return_device_tensors=True)
+            small = vol[:, :patch[0], :patch[1], :patch[2] + 64]
+            net.predict_3D(small, **ikw)  # warm-up: two tiles
+            barrier()
+            i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_inf = L.launch_count
+            i0.record()
+            seg, prob = net.predict_3D(vol, **ikw)
+            i1.record()
+            barrier()
+            inf_launches = L.launch_count - n_inf
+            inf_ms = torch.tensor([i0.elapsed_time(i1)], dtype=torch.float64, device=dev)
+            del seg, prob
+            torch.cuda.empty_cache()
+            t_host = time.perf_counter()
+            seg_np, prob_np = tr.predict_preprocessed_data_return_seg_and_softmax(vol, do_mirroring=False, verbose=False)
+            torch.cuda.synchronize()
+            inf_e2e_s = torch.tensor([time.perf_counter() - t_host], dtype=torch.float64, device=dev)
+            d2h = int(seg_np.nbytes + prob_np.nbytes)
+            del seg_np, prob_np
+        finally:
+            net.train(mode)
+            net.do_ds = ds
+        if world > 1:
+            dist.all_reduce(inf_ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(inf_e2e_s, op=dist.ReduceOp.MAX)
+        infer = {"metric": "3D patches/sec (192x160x128) sliding-window inference", "unit": "patches/s",
+                 "value": world * ntiles / (float(inf_ms.item()) * 1e-3),
+                 "seconds_per_volume": float(inf_ms.item()) * 1e-3, "volume": list(ivol), "tiles_per_volume": ntiles,
+                 "volumes": world, "tile_batch": int(getattr(net, "inference_tile_batch", 4)), "mirroring": False,
+                 "gpu_launches": int(inf_launches),
+                 "includes": "H2D of the volume, per tile: gather + forward + sigmoid*Gaussian scatter-add, normalise + "
+                             "threshold; results left in HBM",
+                 "e2e": {"value": world * ntiles / float(inf_e2e_s.item()), "unit": "patches/s",
+                         "seconds_per_volume": float(inf_e2e_s.item()), "h2d_bytes": int(vol.nbytes),
+                         "d2h_bytes": d2h, "timing": "host wall clock around predict_preprocessed_data_return_seg_and_"
+                                                       "softmax (numpy in, numpy out)"}}
+
     if rank != 0:
         return
     pk = peaks()
@@ -328,7 +389,7 @@ def main():
                        "loss": loss_val},
             "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 12,
                     "ms_per_step": e2e_ms_per_step},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "infer": infer,
             "ms_per_step_with_per_launch_events": ms_profiled,
             "ms_each_step": [round(m, 3) for m in ms_each],
             "top_shapes": [{"kernel": k[0], "shape": k[1], "launches": v["launches"],

@@ -17,7 +17,9 @@ namespace mtb {
 using namespace um;
 
 constexpr int C1_STAGES = 4;
-constexpr int C1_FWD_THREADS = 416;    // 8 builder warps, MMA warp, 4 epilogue warps
+constexpr int C1_FWD_STAGES = 6;
+constexpr int C1_FWD_BUILDERS = 12;    // three groups of four builder warps take tiles round-robin
+constexpr int C1_FWD_THREADS = 32 * (C1_FWD_BUILDERS + 1 + 8);  // 12 builder warps, MMA warp, 8 epilogue warps
 constexpr int C1_WG_THREADS = 448;     // 8 builder warps, MMA warp, dY producer warp, 4 epilogue warps
 constexpr int C1_ROWB = 64;            // bytes per im2col row (32 taps x 2 B)
 
@@ -100,32 +102,36 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
 // =====================================================================================================================
 // forward
 // =====================================================================================================================
-template <typename T>
-__global__ void __launch_bounds__(C1_FWD_THREADS, 2) conv_c1_fwd_kernel(const __grid_constant__ C1Params p) {
+// One CTA per SM.  The epilogue was the critical path of the first version (4 warps, a 32-lane transposing butterfly and
+// shared-memory atomics per tile for the InstanceNorm statistics: the builders waited 40 % of the time for free stages,
+// profiles/r1i_ncu_full_taps_c1.txt): now 8 epilogue warps (two per TMEM lane quarter, each half of the channels) keep
+// the per-(b, channel) sums in REGISTERS across tiles and reduce them once per sample.  NCB = 16-channel blocks per
+// epilogue warp (Cout = 32 * NCB).
+template <typename T, int NCB>
+__global__ void __launch_bounds__(C1_FWD_THREADS, 1) conv_c1_fwd_kernel(const __grid_constant__ C1Params p) {
   extern __shared__ uint8_t dsmem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[C1_STAGES], empty_bar[C1_STAGES];
+  __shared__ __align__(8) uint64_t full_bar[C1_FWD_STAGES], empty_bar[C1_FWD_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_sum[64], s_sq[64], s_bias[64];
+  __shared__ float s_bias[64];
 
+  constexpr int MMA_WARP = C1_FWD_BUILDERS;
+  constexpr int EPI_WARP0 = C1_FWD_BUILDERS + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
   const int a_stage_bytes = 128 * C1_ROWB;                           // 8 KB
   uint8_t* a_base = dsmem;
-  uint8_t* b_tile = a_base + C1_STAGES * a_stage_bytes;              // [Cout][64 B], K-major, SWIZZLE_64B image
+  uint8_t* b_tile = a_base + C1_FWD_STAGES * a_stage_bytes;          // [Cout][64 B], K-major, SWIZZLE_64B image
   const int out_buf_bytes = ((128 * p.Cout * 2 + 1023) / 1024) * 1024;
   uint8_t* o_base = b_tile + 4096;
-  const uint32_t tmem_cols = p.Cout <= 16 ? 32u : (uint32_t)(2 * p.Cout);
+  const uint32_t tmem_cols = (uint32_t)(2 * p.Cout);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < C1_STAGES; ++i) { mbar_init(&full_bar[i], 4); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < C1_FWD_STAGES; ++i) { mbar_init(&full_bar[i], 4); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < 64) {
-    s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f;
-    s_bias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.Cout) ? p.bias[threadIdx.x] : 0.f;
-  }
+  if (threadIdx.x < 64) s_bias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.Cout) ? p.bias[threadIdx.x] : 0.f;
   // weight tile B[co][tap] from the packed weights (ci = 0), zero for taps 27..31
   for (int i = threadIdx.x; i < p.Cout * 4; i += blockDim.x) {
     const int co = i >> 2, c = i & 3;
@@ -143,23 +149,24 @@ __global__ void __launch_bounds__(C1_FWD_THREADS, 2) conv_c1_fwd_kernel(const __
     *reinterpret_cast<uint4*>(b_tile + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  if (warp == 8) tmem_alloc(&tmem_slot, tmem_cols);
+  if (warp == MMA_WARP) tmem_alloc(&tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp < 8) {
+  if (warp < C1_FWD_BUILDERS) {
     // ===== im2col builders: thread = one voxel of the tile =====
-    // two groups of four builder warps take alternate tiles: one group's load latency (a new input line from L2 / HBM
-    // per tile, exposed by the proxy fence before the arrive) overlaps the other group's packing
-    const int grp = warp >> 2;
+    // three groups of four builder warps take tiles round-robin: one group's load latency (a new input line from L2 /
+    // HBM per tile, exposed by the proxy fence before the arrive) overlaps the other groups' packing
+    constexpr uint32_t NG = C1_FWD_BUILDERS / 4;
+    const uint32_t grp = (uint32_t)warp >> 2;
     const int r = (warp & 3) * 32 + lane;
-    for (uint32_t gi = (uint32_t)grp, u = blockIdx.x + (uint32_t)grp * gridDim.x; u < p.units; gi += 2, u += 2 * gridDim.x) {
+    for (uint32_t gi = grp, u = blockIdx.x + grp * gridDim.x; u < p.units; gi += NG, u += NG * gridDim.x) {
       int b, d, h, w0;
       c1_unit(p, u, b, d, h, w0);
-      const uint32_t stage = gi % C1_STAGES;
-      mbar_wait(&empty_bar[stage], ((gi / C1_STAGES) & 1u) ^ 1u);
+      const uint32_t stage = gi % C1_FWD_STAGES;
+      mbar_wait(&empty_bar[stage], ((gi / C1_FWD_STAGES) & 1u) ^ 1u);
       uint8_t* st = a_base + (size_t)stage * a_stage_bytes;
       if (p.xs == 1) c1_build_row<true>(p, st, r, b, d, h, w0 + r);
       else c1_build_row<false>(p, st, r, b, d, h, w0 + r);
@@ -167,7 +174,7 @@ __global__ void __launch_bounds__(C1_FWD_THREADS, 2) conv_c1_fwd_kernel(const __
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[stage]);
     }
-  } else if (warp == 8) {
+  } else if (warp == MMA_WARP) {
     // ===== MMA issuer =====
     const uint32_t idesc = idesc_f16(p.is_f16 != 0, (uint32_t)p.Cout, false, false);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -176,9 +183,9 @@ __global__ void __launch_bounds__(C1_FWD_THREADS, 2) conv_c1_fwd_kernel(const __
     const uint32_t hi = (((8u * C1_ROWB) >> 4) & 0x3FFFu) | (1u << 14) | (4u << 29);  // SWIZZLE_64B
     uint32_t gi = 0;
     for (uint32_t u = blockIdx.x; u < p.units; u += gridDim.x, ++gi) {
-      const uint32_t stage = gi % C1_STAGES, buf = gi & 1u;
+      const uint32_t stage = gi % C1_FWD_STAGES, buf = gi & 1u;
       mbar_wait(&acc_empty[buf], ((gi >> 1) & 1u) ^ 1u);
-      mbar_wait(&full_bar[stage], (gi / C1_STAGES) & 1u);
+      mbar_wait(&full_bar[stage], (gi / C1_FWD_STAGES) & 1u);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sa = a16 + stage * (uint32_t)(a_stage_bytes >> 4);
@@ -193,25 +200,52 @@ __global__ void __launch_bounds__(C1_FWD_THREADS, 2) conv_c1_fwd_kernel(const __
       __syncwarp();
     }
   } else {
-    // ===== epilogue: warps 9..12, TMEM lane quarter = warp % 4 =====
+    // ===== epilogue: 8 warps, TMEM lane quarter = warp % 4, channel half = (warp - EPI_WARP0) / 4 =====
     const int q = warp & 3;
+    const int half = (warp - EPI_WARP0) >> 2;
     const int row = q * 32 + lane;
+    const int cbase = half * (16 * NCB);
     const bool want_stats = p.stats != nullptr;
-    const bool issuer = warp == 9 && lane == 0;
-    const int et = threadIdx.x - 288;  // 0..127
+    const bool issuer = warp == EPI_WARP0 && lane == 0;
+    float csum[NCB][16], csq[NCB][16];
+#pragma unroll
+    for (int i = 0; i < NCB; ++i)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { csum[i][j] = 0.f; csq[i][j] = 0.f; }
+    auto flush = [&](int b) {  // per-(b, channel) sums of this warp's rows -> fp64 atomics
+#pragma unroll
+      for (int i = 0; i < NCB; ++i) {
+        warp_colsum16(csum[i], lane);
+        warp_colsum16(csq[i], lane);
+        if ((lane & 1) == 0) {
+          double* st = p.stats + ((long long)b * p.Cout + cbase + i * 16 + colsum16_column(lane)) * 2;
+          atomicAdd(st, (double)csum[i][0]);
+          atomicAdd(st + 1, (double)csq[i][0]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { csum[i][j] = 0.f; csq[i][j] = 0.f; }
+      }
+    };
     uint32_t gi = 0;
+    int cur_b = -1;
     for (uint32_t u = blockIdx.x; u < p.units; u += gridDim.x, ++gi) {
       int b, d, h, w0;
       c1_unit(p, u, b, d, h, w0);
+      if (want_stats && b != cur_b) {
+        if (cur_b >= 0) flush(cur_b);
+        cur_b = b;
+      }
       const uint32_t buf = gi & 1u;
       uint8_t* stage_out = o_base + (size_t)buf * out_buf_bytes;
       if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&acc_full[buf], (gi >> 1) & 1u);
       tc_fence_after();
       const bool valid = w0 + row < p.W;
       const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.Cout;
-      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+#pragma unroll
+      for (int i = 0; i < NCB; ++i) {
+        const int c0 = cbase + i * 16;
         uint32_t r[16];
         tmem_ld16(tcol + (uint32_t)c0, r);
         float lo[8], hi8[8];
@@ -226,20 +260,12 @@ __global__ void __launch_bounds__(C1_FWD_THREADS, 2) conv_c1_fwd_kernel(const __
         off1 ^= ((off1 >> 7) & (uint32_t)p.out_mask) << 4;
         store8<T>(reinterpret_cast<T*>(stage_out + off0), lo);
         store8<T>(reinterpret_cast<T*>(stage_out + off1), hi8);
-        if (want_stats) {
-          float sv[16], ss[16];
+        if (want_stats && valid) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float x0 = valid ? Traits<T>::round(lo[j]) : 0.f, x1 = valid ? Traits<T>::round(hi8[j]) : 0.f;
-            sv[j] = x0; ss[j] = x0 * x0;
-            sv[8 + j] = x1; ss[8 + j] = x1 * x1;
-          }
-          warp_colsum16(sv, lane);
-          warp_colsum16(ss, lane);
-          if ((lane & 1) == 0) {
-            const int col = colsum16_column(lane);
-            atomicAdd(&s_sum[c0 + col], sv[0]);
-            atomicAdd(&s_sq[c0 + col], ss[0]);
+            const float x0 = Traits<T>::round(lo[j]), x1 = Traits<T>::round(hi8[j]);
+            csum[i][j] += x0; csq[i][j] = fmaf(x0, x0, csq[i][j]);
+            csum[i][8 + j] += x1; csq[i][8 + j] = fmaf(x1, x1, csq[i][8 + j]);
           }
         }
       }
@@ -247,31 +273,17 @@ __global__ void __launch_bounds__(C1_FWD_THREADS, 2) conv_c1_fwd_kernel(const __
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (issuer) {
         tma_store_3d(&p.o_map, stage_out, 0, w0, (b * p.D + d) * p.H + h);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      if (want_stats) {
-        const uint32_t next = u + gridDim.x;
-        const uint32_t per_b = (uint32_t)(p.D * p.H * p.ntw);
-        if (next >= p.units || next / per_b != (uint32_t)b) {
-          for (int c = et; c < p.Cout; c += 128) {
-            if (s_sum[c] != 0.f || s_sq[c] != 0.f) {
-              double* st = p.stats + ((long long)b * p.Cout + c) * 2;
-              atomicAdd(st, (double)s_sum[c]);
-              atomicAdd(st + 1, (double)s_sq[c]);
-              s_sum[c] = 0.f;
-              s_sq[c] = 0.f;
-            }
-          }
-        }
-      }
     }
+    if (want_stats && cur_b >= 0) flush(cur_b);
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -420,22 +432,28 @@ static int c1_common(C1Params& q, const void* x, long long xs, int dtype, int B,
   return MTB200_OK;
 }
 
+template <typename T, int NCB>
+static cudaError_t launch_c1_fwd(const C1Params& q, int gx, int smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(conv_c1_fwd_kernel<T, NCB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) conv_c1_fwd_kernel<T, NCB><<<gx, C1_FWD_THREADS, smem, s>>>(q);
+  return e;
+}
+
 int conv_c1_fwd(const void* x, long long xs, const void* w, int Cin_p, const float* bias, void* out, int out_ldc,
                 int out_coff, int Cout_p, double* stats, int dtype, int B, int D, int H, int W, cudaStream_t s) {
   static C1Params q;
   if (int r = c1_common(q, x, xs, dtype, B, D, H, W, Cout_p, out, out_ldc, out_coff, true)) return r;
   if (q.units == 0) return MTB200_OK;
   q.w = w; q.Cin_p = Cin_p; q.bias = bias; q.stats = stats;
+  if (Cout_p != 32 && Cout_p != 64) { set_error("conv_c1_fwd: Cout_p must be 32 or 64"); return MTB200_ERR_UNSUPPORTED; }
   const int out_buf = ((128 * Cout_p * 2 + 1023) / 1024) * 1024;
-  const int smem = C1_STAGES * 128 * C1_ROWB + 4096 + 2 * out_buf + 1024;
-  const int gx = (int)min((long long)q.units, (long long)2 * num_sms());
+  const int smem = C1_FWD_STAGES * 128 * C1_ROWB + 4096 + 2 * out_buf + 1024;
+  const int gx = (int)min((long long)q.units, (long long)num_sms());  // one persistent CTA per SM
   cudaError_t e;
   if (dtype == MTB200_BF16) {
-    e = cudaFuncSetAttribute(conv_c1_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) conv_c1_fwd_kernel<__nv_bfloat16><<<gx, C1_FWD_THREADS, smem, s>>>(q);
+    e = Cout_p == 32 ? launch_c1_fwd<__nv_bfloat16, 1>(q, gx, smem, s) : launch_c1_fwd<__nv_bfloat16, 2>(q, gx, smem, s);
   } else {
-    e = cudaFuncSetAttribute(conv_c1_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) conv_c1_fwd_kernel<__half><<<gx, C1_FWD_THREADS, smem, s>>>(q);
+    e = Cout_p == 32 ? launch_c1_fwd<__half, 1>(q, gx, smem, s) : launch_c1_fwd<__half, 2>(q, gx, smem, s);
   }
   if (e != cudaSuccess) { set_error("conv_c1_fwd: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
   return check_launch("conv_c1_fwd");

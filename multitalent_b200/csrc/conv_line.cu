@@ -51,6 +51,7 @@ struct LineParams {
   int nhr, hlen, ntw;
   int units;                     // work units walked by the persistent CTAs
   int accumulate, is_f16;
+  int dbg;                       // experiments only (MTB200_LINE_DBG): bit 0 = read one accumulator block per line
 };
 
 __device__ __forceinline__ uint64_t ln_desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
     const uint32_t w16 = __shfl_sync(0xffffffffu, (smem_u32(w_base) & 0x3FFFFu) >> 4, 0);
     const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, line16 = (uint32_t)p.line_bytes >> 4;
     const uint32_t wgroup16 = (uint32_t)p.wgroup_bytes >> 4;
-    const int ngroups = p.ngroups;
+    const int ngroups = (p.dbg & 8) ? 1 : p.ngroups;
     // per-group descriptor offsets live in (uniform) registers: the issue loop is a handful of adds per MMA.  The single
     // issuing warp pays the full latency of every dependent instruction, so nothing else may sit between two MMAs.
     uint32_t a_goff[9], b_goff[9];
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
           const int hq = h + dy;
-          if (hq >= 0 && hq < p.H) {
+          if (hq >= 0 && hq < p.H && !((p.dbg & 1) && dy != 0)) {
             tmem_ld_async(tlane + ((gs0 + (uint32_t)(hq - hfirst)) % LN_QSLOTS) * NCOLS + (uint32_t)((dy + 1) * LN_BN), r[dy + 1]);
           } else {  // out-of-volume line: zero contribution
 #pragma unroll
@@ -240,9 +241,9 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) o8[j] = v[c8 + j];
-            store8<T>(orow + c8, o8);
+            if (!(p.dbg & 2)) store8<T>(orow + c8, o8);
           }
-          if (want_stats) {
+          if (want_stats && !(p.dbg & 4)) {
 #pragma unroll
             for (int j = 0; j < LN_CPT; ++j) {
               const float x = Traits<T>::round(v[j]);
@@ -387,6 +388,7 @@ int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s) {
   q.out_ldc = p.out_ldc; q.out_coff = p.out_coff; q.Cout = p.Cout;
   q.accumulate = p.accumulate;
   q.is_f16 = p.dtype == MTB200_F16;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MTB200_LINE_DBG"); dbg = e ? atoi(e) : 0; } q.dbg = dbg; }
   q.ntw = (p.Wo + 127) / 128;
   const int ny = p.Cout / LN_BN;
   // split H into ranges so that the units divide evenly over the persistent CTAs (one per SM and Cout block); every

@@ -43,6 +43,7 @@ struct WgradLineParams {
   int xline_bytes;           // one staged X line, 1024-aligned
   int ybase;                 // offset of the dY window inside a stage
   int stage_bytes, stage_tx, stages;
+  int dbg, x_tx;             // experiments only (MTB200_WLINE_DBG): bit 0 = skip the dY loads, bit 1 = one K step per line
   int ndz, dz0;
   int nhr, hlen, ntw;
   int wt, nkk;               // w tile (128 / 64 / 32 voxels of one line) and its number of 16-voxel K steps
@@ -95,10 +96,10 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __
         mbar_wait(&st_empty[slot], ((sc / (uint32_t)p.stages) & 1u) ^ 1u);
         if (elect_one()) {
           uint8_t* dst = dsmem + (size_t)slot * p.stage_bytes;
-          mbar_expect_tx(&st_full[slot], (uint32_t)p.stage_tx);
+          mbar_expect_tx(&st_full[slot], (uint32_t)((p.dbg & 1) ? p.x_tx : p.stage_tx));
           for (int z = 0; z < p.ndz; ++z)
             tma_load_5d(dst + (size_t)z * p.xline_bytes, &p.x_map, &st_full[slot], c0, w0 - 1, hp, d + p.dz0 + z, b);
-          for (int sg = 0; sg < p.nseg; ++sg)  // lines hp-1, hp, hp+1 (or hp alone)
+          for (int sg = 0; sg < p.nseg && !(p.dbg & 1); ++sg)  // lines hp-1, hp, hp+1 (or hp alone)
             tma_load_5d(dst + p.ybase + p.seg_off[sg], &p.dy_map[sg], &st_full[slot], n0 + p.seg_c0[sg], w0,
                         hp - (p.nb == 3 ? 1 : 0), d, b);
         }
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __
     }
     const uint32_t s16 = __shfl_sync(0xffffffffu, (smem_u32(dsmem) & 0x3FFFFu) >> 4, 0);
     const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, xline16 = (uint32_t)p.xline_bytes >> 4;
-    const int ndz = p.ndz, nkk = p.nkk;
+    const int ndz = p.ndz, nkk = (p.dbg & 2) ? 1 : p.nkk;
     uint32_t sc = 0;
     for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
       const int hr = (int)(u % p.nhr);
@@ -263,6 +264,8 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   const int ywin_bytes = q.nseg == 2 ? q.seg_off[1] + wl_align1k((long long)q.nb * q.wt * 32) : wl_align1k((long long)q.nb * q.wt * 64);
   q.stage_bytes = wl_align1k(q.ybase + ywin_bytes);
   q.stage_tx = q.ndz * xrows * rowb + ybytes;
+  q.x_tx = q.ndz * xrows * rowb;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MTB200_WLINE_DBG"); dbg = e ? atoi(e) : 0; } q.dbg = dbg; }
   q.stages = min(WL_MAX_STAGES, (224 * 1024) / q.stage_bytes);
   if (q.stages < 2) return MTB200_ERR_UNSUPPORTED;
   {

@@ -192,7 +192,7 @@ class ConvOp:
         self.group = None  # PackGroup: every op of the network refreshed by one launch
         # first layer on a single-channel patch: dedicated kernels with K = taps (csrc/conv_c1.cu)
         self.c1 = (not transposed and self.Cin == 1 and self.kernel == (3, 3, 3) and self.stride == (1, 1, 1)
-                   and split == 0 and self.Cout_p in (16, 32, 64))
+                   and split == 0 and self.Cout_p in (32, 64))
 
     def out_dims(self, dims):
         B, D, H, W = dims

@@ -216,31 +216,62 @@ class MultiTalent_trainer_ddp(object):
         """MT:544-623 -> (total_loss, total_ce, total_dc)."""
         return multitalent_loss(output, target, valid_regions, self.ds_loss_weights)
 
-    def run_iteration(self, data_generator, do_backprop=True, run_online_evaluation=False):
-        """MT:324-370.  Returns three numpy scalars (the D2H sync of the reference is kept: it is the contract)."""
-        data_dict = next(data_generator)
+    def _stage_batch(self, data_dict):
+        """Start the host->device copies of one batch on the copy stream (pinned host memory: asynchronous).  Returns
+        (data, target, valid_regions, event after the data copy, event after the target copies): the targets are not
+        needed before the loss, so their copy may still be running under the forward pass."""
         data, target = data_dict['data'], data_dict['target']
         valid_regions = [p['valid_regions'] for p in data_dict['properties']]
         data = torch.as_tensor(data)
         target = [torch.as_tensor(t) for t in target]
-        ready = None
+        ready = tready = None
         if torch.cuda.is_available():
-            # the targets are not needed before the loss: their H2D copy runs on a side stream under the forward pass
-            main = torch.cuda.current_stream()
             if getattr(self, "_copy_stream", None) is None:
                 self._copy_stream = torch.cuda.Stream()
-            if all(t.is_pinned() for t in target if not t.is_cuda):
-                self._copy_stream.wait_stream(main)
+            host = [t for t in [data] + target if not t.is_cuda]
+            if host and all(t.is_pinned() for t in host):
+                # no wait on the compute stream: the staging tensors are allocated from the copy stream's own pool
                 with torch.cuda.stream(self._copy_stream):
-                    target = [t.cuda(non_blocking=True) for t in target]
+                    data = data.cuda(non_blocking=True)
                     ready = torch.cuda.Event()
                     ready.record(self._copy_stream)
-                for t in target:
-                    t.record_stream(main)
+                    target = [t.cuda(non_blocking=True) for t in target]
+                    tready = torch.cuda.Event()
+                    tready.record(self._copy_stream)
             else:
+                data = data.cuda(non_blocking=True)
                 target = [t.cuda(non_blocking=True) for t in target]
-            data = data.cuda(non_blocking=True)
-        l, ce, dc = self.train_step(data, target, valid_regions, do_backprop, target_ready=ready)
+        return data, target, valid_regions, ready, tready
+
+    def run_iteration(self, data_generator, do_backprop=True, run_online_evaluation=False):
+        """MT:324-370.  Returns three numpy scalars (the D2H sync of the reference is kept: it is the contract).
+
+        `prefetch_batches` (default on): the NEXT batch is pulled from `data_generator` and its H2D copy is issued on a
+        side stream while this step computes, so the copy of a step's inputs is hidden under the previous step (the
+        reference's `to_cuda` copies are synchronous with the step, to_torch.py:18-31).  The generator is therefore
+        advanced one batch ahead of the step that consumes it; a batch staged for one generator is only ever handed to
+        that generator's next call."""
+        pre = getattr(self, "_prefetched", None)
+        if pre is None:
+            pre = self._prefetched = {}
+        entry = pre.pop(id(data_generator), None)
+        staged = entry[1] if entry is not None and entry[0] is data_generator else None
+        if staged is None:
+            staged = self._stage_batch(next(data_generator))
+        data, target, valid_regions, ready, tready = staged
+        if ready is not None:
+            main = torch.cuda.current_stream()
+            main.wait_event(ready)
+            for t in [data] + target:
+                t.record_stream(main)
+        l, ce, dc = self.train_step(data, target, valid_regions, do_backprop, target_ready=tready)
+        if getattr(self, "prefetch_batches", True) and torch.cuda.is_available():
+            try:
+                nxt = next(data_generator)
+            except StopIteration:
+                nxt = None
+            if nxt is not None:
+                pre[id(data_generator)] = (data_generator, self._stage_batch(nxt))
         res = torch.stack((l.detach(), ce.detach(), dc.detach())).cpu().numpy()
         return res[0], res[1], res[2]
 

@@ -284,6 +284,48 @@ def test_trainer_step_matches_oracle_step(golden_small):
     assert np.isfinite(l2) and l2 != l
 
 
+def test_run_iteration_prefetch_matches_unprefetched(golden_small):
+    """run_iteration stages the NEXT batch's H2D copy under the current step (pinned host batches).  Three steps on three
+    different batches must give the same losses and parameters with and without the prefetch, and the generator must be
+    consumed exactly once per batch."""
+    from multitalent_b200.plans import default_plans
+    from multitalent_b200.training.network_training.MultiTalent_Trainer_DDP import MultiTalent_trainer_ddp
+    blob, meta = golden_small
+    plans = default_plans(patch_size=(8, 16, 16), batch_size=2)
+    plans['plans_per_stage'][1]['pool_op_kernel_sizes'] = meta["pool"]
+    plans['plans_per_stage'][1]['conv_kernel_sizes'] = meta["convk"]
+    plans['base_num_features'] = meta["base"]
+    sd = {k[len("param/"):]: torch.from_numpy(v) for k, v in blob.items() if k.startswith("param/")}
+    rng = np.random.RandomState(5)
+    batches = []
+    for i in range(3):
+        x = (blob["x"] + 0.1 * i * rng.randn(*blob["x"].shape)).astype(np.float32)
+        batches.append({'data': torch.from_numpy(x).pin_memory(),
+                        'target': [torch.from_numpy(np.roll(blob["target_%d" % k], i, axis=-1).copy()).pin_memory()
+                                   for k in range(3)],
+                        'properties': [{'valid_regions': tuple(v)} for v in meta["valid_regions"]]})
+    results = {}
+    for prefetch in (False, True):
+        tr = MultiTalent_trainer_ddp(plans, 0, 0, init_distributed=False)
+        tr.initialize(True)
+        tr.prefetch_batches = prefetch
+        tr.load_checkpoint_ram({'state_dict': dict(sd), 'epoch': 0})
+        pulled = []
+
+        def gen():
+            for i, b in enumerate(batches):
+                pulled.append(i)
+                yield b
+        g = gen()
+        losses = [tr.run_iteration(g, True) for _ in range(3)]
+        assert pulled == [0, 1, 2]
+        results[prefetch] = (np.array(losses, dtype=np.float64),
+                             torch.cat([p.detach().flatten().cpu() for p in tr.network.parameters()]))
+    np.testing.assert_allclose(results[True][0], results[False][0], rtol=1e-5, atol=1e-6)
+    assert float((results[True][1] - results[False][1]).abs().max()) < 1e-5
+    assert len({tuple(np.round(r, 6)) for r in results[True][0]}) == 3  # the three batches really differ
+
+
 # T1 tolerance = the reference's own autocast-vs-fp32 deviation (BASELINE.md section 5: bf16 0.19, fp16 0.024 max-abs on
 # logits of O(7)) with a 1.5x allowance for fp16: the statistic is a maximum over 6e5 logits and moves between 0.019 and
 # 0.028 with nothing but the fp32 summation ORDER inside one kernel (tools/c1_check.py: first layer through the K = taps

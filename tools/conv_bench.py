@@ -45,7 +45,10 @@ def main():
         flops = 2.0 * cin * cout * 27 * B * D * H * W
         for impl in a.impl:
             eng = Engine(dt, impl)
-            x = Feat(torch.randn(B, D, H, W, op.Cin_p, device="cuda").to(dt), 0, cin, op.Cin_p)
+            if cin == 1 and eng.use_c1(op):  # compact single-channel input, as the network feeds the first layer
+                x = Feat(torch.randn(B, D, H, W, 1, device="cuda").to(dt), 0, 1, 1)
+            else:
+                x = Feat(torch.randn(B, D, H, W, op.Cin_p, device="cuda").to(dt), 0, cin, op.Cin_p)
             dy = Feat(torch.randn(B, D, H, W, op.Cout_p, device="cuda").to(dt), 0, cout, op.Cout_p)
             for what in a.what:
                 def run():
