@@ -9,6 +9,15 @@ namespace mtb {
 constexpr int LT = 256;
 constexpr int MAX_LABELS = 64;
 
+// e = exp(-|z|), sigmoid(z) and softplus(-|z|) = log(1 + e) on the SFU (ex2 / rcp / lg2 approximations, ~1e-6 relative:
+// far inside the fp32 parity tolerance of the loss).  The precise expf / division / log1pf sequences made both passes
+// instruction-bound (lanes of one warp own different channel groups, so every channel's code is issued for the whole warp).
+__device__ __forceinline__ void sigmoid_terms(float z, float& e, float& sig) {
+  e = __expf(-fabsf(z));
+  const float r = __frcp_rn(1.f + e);
+  sig = z >= 0.f ? r : e * r;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(LT) mt_loss_stats_kernel(const T* __restrict__ logits, int ldc, int C,
                                                            const float* __restrict__ target, long long nvox,
@@ -17,44 +26,72 @@ __global__ void __launch_bounds__(LT) mt_loss_stats_kernel(const T* __restrict__
                                                            double* __restrict__ stats) {
   __shared__ uint64_t s_pos[MAX_LABELS];
   __shared__ float sh[LT][8];
+  __shared__ int s_act[8], s_nact;
   const int b = blockIdx.y;
   const int G = C / 8;
-  const int vstride = LT / G;
-  const int cg = threadIdx.x % G, vlane = threadIdx.x / G;
-  const bool active = vlane < vstride;
+  const uint64_t valid = valid_mask[b];
+  // only channel groups with a supervised channel are read: the threads of the block are spread over THOSE groups
+  // (a sample of a 1..13-region dataset touches 1..3 of the 6 groups; idle threads would only thin out the loads in flight)
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int g = 0; g < G; ++g)
+      if ((valid >> (g * 8)) & 0xffull) s_act[n++] = g;
+    s_nact = n;
+  }
   if (threadIdx.x < MAX_LABELS) s_pos[threadIdx.x] = threadIdx.x < n_labels ? pos_mask[threadIdx.x] : 0ull;
   __syncthreads();
-  const uint64_t valid = valid_mask[b];
+  const int nact = s_nact;
+  if (nact == 0) return;  // nothing supervised in this sample (uniform across the block)
+  const int vstride = LT / nact;
+  const int ai = threadIdx.x % nact, vlane = threadIdx.x / nact;
+  const int cg = s_act[ai];
+  const bool active = vlane < vstride;
   const unsigned vbits = (unsigned)((valid >> (cg * 8)) & 0xffull);
-  const long long per = (nvox + gridDim.x - 1) / gridDim.x;
-  const long long v0 = (long long)blockIdx.x * per, v1 = min(nvox, v0 + per);
-
   float part[4][8];
 #pragma unroll
   for (int q = 0; q < 4; ++q)
 #pragma unroll
     for (int j = 0; j < 8; ++j) part[q][j] = 0.f;
 
-  if (active && vbits) {
+  if (active) {
     const T* base = logits + (long long)b * nvox * ldc + cg * 8;
     const float* tb = target + (long long)b * nvox;
-    for (long long v = v0 + vlane; v < v1; v += vstride) {
-      float z[8];
-      load8<T>(base + v * ldc, z);
-      const int lab = (int)tb[v];
-      const uint64_t pm = ((unsigned)lab < (unsigned)MAX_LABELS) ? s_pos[lab] : 0ull;
-      const unsigned ybits = (unsigned)((pm >> (cg * 8)) & 0xffull);
+    constexpr int U = 4;  // voxels in flight per thread
+    const long long per = (nvox + gridDim.x - 1) / gridDim.x;
+    const long long v0 = (long long)blockIdx.x * per, v1 = min(nvox, v0 + per);
+    for (long long v = v0 + vlane; v < v1; v += (long long)U * vstride) {
+      float z[U][8];
+      int lab[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (vbits & (1u << j)) {
-          const float y = (ybits >> j) & 1u ? 1.f : 0.f;
-          const float e = expf(-fabsf(z[j]));
-          const float bce = fmaxf(z[j], 0.f) - z[j] * y + log1pf(e);
-          const float sig = z[j] >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
-          part[0][j] += bce;
-          part[1][j] = fmaf(sig, y, part[1][j]);
-          part[2][j] += sig;
-          part[3][j] += y;
+      for (int u = 0; u < U; ++u) {
+        const long long vv = v + (long long)u * vstride;
+        if (vv < v1) {
+          load8<T>(base + vv * ldc, z[u]);
+          lab[u] = (int)tb[vv];
+        } else {
+          lab[u] = -1;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (lab[u] < 0) continue;   // past the end (labels are >= 0)
+        const uint64_t pm = ((unsigned)lab[u] < (unsigned)MAX_LABELS) ? s_pos[lab[u]] : 0ull;
+        const unsigned ybits = (unsigned)((pm >> (cg * 8)) & 0xffull);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (vbits & (1u << j)) {
+            const float zz = z[u][j];
+            const float y = (ybits >> j) & 1u ? 1.f : 0.f;
+            float e, sig;
+            sigmoid_terms(zz, e, sig);
+            // log1p(e): e < 2^-12 -> e - e^2/2 (log(1+e) would lose the low bits of e in the rounding of 1 + e)
+            const float l1p = e < 2.44140625e-4f ? e * (1.f - 0.5f * e) : __logf(1.f + e);
+            const float bce = fmaxf(zz, 0.f) - zz * y + l1p;
+            part[0][j] += bce;
+            part[1][j] = fmaf(sig, y, part[1][j]);
+            part[2][j] += sig;
+            part[3][j] += y;
+          }
         }
       }
     }
@@ -66,11 +103,11 @@ __global__ void __launch_bounds__(LT) mt_loss_stats_kernel(const T* __restrict__
 #pragma unroll
     for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] = active ? part[q][j] : 0.f;
     __syncthreads();
-    for (int idx = threadIdx.x; idx < G * 8; idx += LT) {
-      const int g = idx / 8, j = idx % 8;
-      float s = 0.f;
-      for (int vl = 0; vl < vstride; ++vl) s += sh[vl * G + g][j];
-      if (s != 0.f) atomicAdd(dst + (long long)(g * 8 + j) * 4 + q, (double)s);
+    for (int idx = threadIdx.x; idx < nact * 8; idx += LT) {
+      const int a = idx / 8, j = idx % 8;
+      float sum = 0.f;
+      for (int vl = 0; vl < vstride; ++vl) sum += sh[vl * nact + a][j];
+      if (sum != 0.f) atomicAdd(dst + (long long)(s_act[a] * 8 + j) * 4 + q, (double)sum);
     }
   }
 }
@@ -135,6 +172,9 @@ int mt_loss_finalize(const double* stats, const double* pooled, const uint64_t* 
 }
 
 // ---- pass 2: dlogits ----------------------------------------------------------------------------------------------
+// Measured (profiles/r1j_ncu_full_loss.txt): 3.0 GB of DRAM traffic in 0.83 ms at full resolution.  More loads in flight
+// (2 / 4 voxels per thread), coefficients in shared memory, SFU math and a chunked grid-stride order were all tried and
+// none moved it (0.97 -> 1.04 / 1.13 / 1.05 / 1.40 ms per step): left as the simple one-voxel loop.
 template <typename T>
 __global__ void __launch_bounds__(LT) mt_loss_bwd_kernel(const T* __restrict__ logits, int ldc, int C,
                                                          const float* __restrict__ target, long long nvox,
@@ -176,8 +216,8 @@ __global__ void __launch_bounds__(LT) mt_loss_bwd_kernel(const T* __restrict__ l
       for (int j = 0; j < 8; ++j) {
         if (vbits & (1u << j)) {
           const float y = (ybits >> j) & 1u ? 1.f : 0.f;
-          const float e = expf(-fabsf(z[j]));
-          const float sig = z[j] >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+          float e, sig;
+          sigmoid_terms(z[j], e, sig);
           d[j] = cf[j].x * (sig - y) - sig * (1.f - sig) * (y * cf[j].y - cf[j].z);
         } else {
           d[j] = 0.f;
