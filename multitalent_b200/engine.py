@@ -8,7 +8,9 @@ A conv writes its RAW output plus per-(b, c) sum / sum-of-squares; InstanceNorm 
 per-(b, c) affine `xform` and applied by the CONSUMER while it loads the tile (norm-on-load), so the reference's
 instnorm/lrelu read+write passes (generic_UNet.py:70) and torch.cat (generic_UNet.py:392) disappear.
 """
+import contextlib
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -389,6 +391,12 @@ class Engine:
         self._materialize = None
         self._z64 = ZeroPool(torch.float64, 1 << 16)
         self._z32 = ZeroPool(torch.float32, 1 << 22)
+        # weight gradients are only consumed by the optimizer: with arena parameters (gradients accumulated in place, no
+        # autograd tensors) they run on a second stream next to the dgrad / InstanceNorm-backward chain, which fills the
+        # SMs the small deep-level launches and every kernel's tail leave idle.  MTB200_WGRAD_STREAM=0 disables it.
+        self.overlap_wgrad = os.environ.get("MTB200_WGRAD_STREAM", "1") != "0"
+        self._side = {}
+        self._side_used = None
 
     def begin_step(self):
         """Called at the start of every network forward: re-zero what the previous step took from the pools."""
@@ -557,13 +565,24 @@ class Engine:
             else:
                 tape.add_param_grad(p, torch.zeros_like(p))
 
-    def _conv_bwd(self, tape, op: ConvOp, x: Feat, dy: Feat, need_input_grad, bias_grad_is_zero=False):
-        """Weight / bias gradient and data gradient of a (transposed) convolution given d(raw output)."""
-        dev = dy.buf.device
-        dt = L.dtype_enum(self.dtype)
-        x = self.operand(x)
-        # ---- weight gradient (same tap table as the forward problem)
-        dw = self._z32.take((op.ntap, op.Cout_p, op.Cin_p), dev)
+    @contextlib.contextmanager
+    def _wgrad_stream(self, op: ConvOp, dev):
+        """Side stream for one layer's weight-gradient launches (ordered after everything already queued on the current
+        stream, i.e. after d(raw output) was written); `run_backward` joins it.  Only with in-place arena gradients: a
+        gradient tensor handed to autograd would have to cross streams."""
+        if not (self.overlap_wgrad and dev.type == "cuda" and direct_grad(op.weight) is not None
+                and (op.bias is None or direct_grad(op.bias) is not None)):
+            yield
+            return
+        side = self._side.get(dev)
+        if side is None:
+            side = self._side[dev] = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        self._side_used = side
+        with torch.cuda.stream(side):
+            yield
+
+    def _wgrad(self, tape, op: ConvOp, x: Feat, dy: Feat, dw, dt, dev, need_input_grad, bias_grad_is_zero):
         if self.use_c1(op) and x.xform is None and not need_input_grad:
             B, D, H, W = x.dims
             L.call("mtb200_conv_c1_wgrad", C.c_void_p(x.ptr() + x.coff * x.buf.element_size()), x.ldc, dy.ptr(), dy.ldc,
@@ -586,13 +605,23 @@ class Engine:
         p.Do, p.Ho, p.Wo = x.dims[1:] if op.transposed else dy.dims[1:]
         op.fwd_taps.fill(p)
         p.impl = self.impl
-        fl = self.conv_flops(op, dy.dims)
-        L.call("mtb200_wgrad_taps", C.byref(p), L.stream_ptr(), flops=fl, tag="conv_wgrad",
+        L.call("mtb200_wgrad_taps", C.byref(p), L.stream_ptr(), flops=self.conv_flops(op, dy.dims), tag="conv_wgrad",
                info=(op.Cin_p, op.Cout_p, (p.Do, p.Ho, p.Wo), op.ntap, op.fwd_taps.in_stride, op.fwd_taps.out_stride))
         self._finish_wgrad(tape, op, dw, dy, dt, dev, bias_grad_is_zero)
+
+    def _conv_bwd(self, tape, op: ConvOp, x: Feat, dy: Feat, need_input_grad, bias_grad_is_zero=False):
+        """Weight / bias gradient and data gradient of a (transposed) convolution given d(raw output)."""
+        dev = dy.buf.device
+        dt = L.dtype_enum(self.dtype)
+        x = self.operand(x)
+        # ---- weight gradient (same tap table as the forward problem)
+        dw = self._z32.take((op.ntap, op.Cout_p, op.Cin_p), dev)
+        with self._wgrad_stream(op, dev):
+            self._wgrad(tape, op, x, dy, dw, dt, dev, need_input_grad, bias_grad_is_zero)
         # ---- data gradient
         if not need_input_grad:
             return
+        fl = self.conv_flops(op, dy.dims)
         gx, have = tape.grad_feat(x)
         grid = gx.dims[1:] if op.transposed else tuple(n // s for n, s in zip(gx.dims[1:], op.stride))
         dyv = Feat(dy.buf, dy.coff, dy.C, dy.Cp)  # gradients carry no pending transform
@@ -680,3 +709,6 @@ class Engine:
         for c in reversed(tape.closures):
             c()
         tape.closures = []
+        if self._side_used is not None:  # the optimizer (and the next forward's pool reset) must see every weight gradient
+            torch.cuda.current_stream().wait_stream(self._side_used)
+            self._side_used = None
