@@ -24,6 +24,23 @@ from .. import _lib as L
 from ..engine import Feat, ndhwc_view_info
 
 
+def _to_host_numpy(*tensors):
+    """Device tensors -> numpy arrays through page-locked staging buffers (torch's caching host allocator keeps them for
+    the next volume): the [47, X, Y, Z] fp32 probability volume is 6-25 GB, and a pageable `.cpu()` moves it at a few
+    GB/s.  Falls back to the pageable copy if page-locked memory cannot be had."""
+    outs, pinned = [], []
+    try:
+        for t in tensors:
+            h = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            pinned.append(h)
+        torch.cuda.current_stream().synchronize()
+        outs = [h.numpy() for h in pinned]
+    except RuntimeError:
+        outs = [t.cpu().numpy() for t in tensors]
+    return outs
+
+
 class NeuralNetwork(nn.Module):
     def __init__(self):
         super(NeuralNetwork, self).__init__()
@@ -240,7 +257,8 @@ class SegmentationNetwork(NeuralNetwork):
             return seg, acc
         if verbose:
             print("prediction done")
-        return seg.cpu().numpy(), acc.cpu().numpy()
+        seg_np, acc_np = _to_host_numpy(seg, acc)
+        return seg_np, acc_np
 
     def _internal_predict_3D_3Dconv(self, x: np.ndarray, min_size: Tuple[int, ...], do_mirroring: bool,
                                     mirror_axes: tuple = (0, 1, 2), regions_class_order: tuple = None,
@@ -259,7 +277,8 @@ class SegmentationNetwork(NeuralNetwork):
         seg, prob = seg[sl], prob[(slice(None),) + sl]
         if return_device_tensors:
             return seg, prob
-        return seg.cpu().numpy(), prob.cpu().numpy()
+        seg_np, prob_np = _to_host_numpy(seg.contiguous(), prob.contiguous())
+        return seg_np, prob_np
 
     def _internal_maybe_mirror_and_pred_3D(self, x: Union[np.ndarray, torch.Tensor], mirror_axes: tuple,
                                            do_mirroring: bool = True, mult: Union[np.ndarray, torch.Tensor] = None,
