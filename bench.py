@@ -140,10 +140,20 @@ def run_reference(args, rank, out=sys.stdout):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_patch = (96, 96, 64)  # 0.15 of the benchmark patch: keeps K+W steps within minutes on a few cores
-    frac = float(np.prod(sample_patch)) / float(np.prod(FULL_PATCH))
+    # bounded sample of the workload: 0.15 of the benchmark patch per step; if K+W steps of that would not finish within
+    # ~4 minutes on this host (timed on the first step), fall back to a 48x64x64 sample (0.05 of the patch)
+    sample_patch = (96, 96, 64)
     step = cpu_oracle_step_factory(sample_patch)
-    for _ in range(args.warmup):
+    t_probe = time.perf_counter()
+    step()
+    t_probe = time.perf_counter() - t_probe
+    done_warm = 1
+    if t_probe * (args.steps + args.warmup) > 240.0:
+        sample_patch = (48, 64, 64)
+        step = cpu_oracle_step_factory(sample_patch)
+        done_warm = 0
+    frac = float(np.prod(sample_patch)) / float(np.prod(FULL_PATCH))
+    for _ in range(max(0, args.warmup - done_warm)):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):

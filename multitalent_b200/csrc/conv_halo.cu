@@ -378,10 +378,15 @@ int conv_halo_umma(const mtb200_conv_params& p, cudaStream_t s) {
           } else if (left < 0) {
             continue;
           }
-          const double mma_cycles = (double)p.ntaps * tw * (p.Cin / 16) * (bn / 2.0);  // per plane of 128*tw voxels
+          // per plane of 128*tw voxels.  tcgen05.mma (M = 128, K = 16) costs max(N/2, 34.6 + 0.2375 N) cycles
+          // (profiles/r1h_umma_rate_probe.txt): narrow N tiles are operand-fetch bound, so N = 32 is NOT half of N = 64
+          const double mma_one = fmax(bn / 2.0, 34.6 + 0.2375 * bn);
+          const double mma_cycles = (double)p.ntaps * tw * (p.Cin / 16) * mma_one;
           const double wtraffic = res ? 0.0 : (double)p.ntaps * bn * p.Cin * 2;
           const double atraffic = (double)HL_HH * wh * p.Cin * 2;
-          double cost = (wtraffic + atraffic) / mma_cycles;
+          // cycles per output voxel and Cout: the slower of the tensor pipe and the L2->SM path (~40 B/cycle/SM); the
+          // Cout/bn CTAs of a column each stream the planes again
+          double cost = fmax(mma_cycles, (wtraffic + atraffic) / 40.0) / (128.0 * tw) * (p.Cout / bn);
           if (ring == 2) cost *= 1.05;  // less prefetch distance
           // tile-quantisation waste in w
           const int tiles_w = (p.Wo + 8 * tw - 1) / (8 * tw);
