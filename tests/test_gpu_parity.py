@@ -322,9 +322,9 @@ def test_run_iteration_prefetch_matches_unprefetched(golden_small):
         results[prefetch] = (np.array(losses, dtype=np.float64),
                              torch.cat([p.detach().flatten().cpu() for p in tr.network.parameters()]))
     np.testing.assert_allclose(results[True][0], results[False][0], rtol=1e-5, atol=1e-6)
-    # 2e-4: repeated runs of the SAME configuration (prefetch on or off, tools/prefetch_race.py) agree to ~1e-7 except for
-    # a rare second outcome in which one fp32-mode weight gradient of the third step differs by 6e-5 in the updated
-    # parameters -- independent of the prefetch and of the weight-gradient stream (known issues)
+    # 2e-4: repeated runs of the SAME configuration (prefetch on or off, tools/prefetch_race.py) agree to ~1e-7 except
+    # when the fp32 summation order inside the InstanceNorm statistics flips the LeakyReLU branch of a near-zero voxel
+    # (6e-5 in one weight tensor after three steps; DESIGN.md "Run-to-run variation")
     assert float((results[True][1] - results[False][1]).abs().max()) < 2e-4
     assert len({tuple(np.round(r, 6)) for r in results[True][0]}) == 3  # the three batches really differ
 
