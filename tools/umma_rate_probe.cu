@@ -34,6 +34,7 @@ struct Rate {
   int mn_major;     // 1: both operands MN-major (wgrad-style), SW128
   int distinct_a;   // 1: A start address moves by one row per MMA and by 16 KB blocks (conv taps); 0: fixed
   int distinct_b;   // 1: B start moves too
+  int sbo_rows;     // K-major A operand: rows between consecutive 8-row groups (8 = dense; 8*TW+2 = a halo tile's line pitch)
   int rounds;       // commits
   long long* clk;   // [gridDim.x]
 };
@@ -69,7 +70,8 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(const Rate p) {
       lbo_a = (64u >> 4) << 16;
       lbo_b = (8192u >> 4) << 16;
     } else {
-      hi_a = hi_b = (((uint32_t)(8 * p.row_bytes)) >> 4) | (1u << 14) | (layout << 29);
+      hi_b = (((uint32_t)(8 * p.row_bytes)) >> 4) | (1u << 14) | (layout << 29);
+      hi_a = (((uint32_t)(p.sbo_rows * p.row_bytes)) >> 4) | (1u << 14) | (layout << 29);
     }
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((p.mn_major ? 1u : 0u) << 15) | ((p.mn_major ? 1u : 0u) << 16) |
                            (((uint32_t)p.n >> 3) << 17) | ((128u >> 4) << 24);
@@ -129,7 +131,7 @@ int main() {
       for (int n : {32, 64, 96, 128, 160, 192, 224, 256}) {
         if (da == 0 && n != 64 && n != 96 && n != 192 && n != 256) continue;
         Rate p;
-        p.n = n; p.row_bytes = c.rb; p.mn_major = c.mn; p.distinct_a = da; p.distinct_b = da; p.rounds = 200; p.clk = dclk;
+        p.n = n; p.row_bytes = c.rb; p.mn_major = c.mn; p.distinct_a = da; p.distinct_b = da; p.sbo_rows = 8; p.rounds = 200; p.clk = dclk;
         rate_kernel<<<sms, 128, smem>>>(p);  // warm-up
         CK(cudaDeviceSynchronize());
         CK(cudaEventRecord(e0));
@@ -147,5 +149,27 @@ int main() {
         const double flops = 2.0 * 128 * n * 16 * mmas * sms;
         printf("%-10s %4d %9d %9d %12.1f %12.1f %10.1f\n", c.name, n, da, da, avg / mmas, ms * 1e6 / mmas, flops / (ms * 1e-3) / 1e12);
       }
+  printf("\n# K-major SW128, distinct (row-shifted) A views: A-operand 8-row-group pitch (SBO) sweep -- halo tiles use the line pitch\n");
+  printf("%-10s %4s %9s %12s %12s %10s\n", "layout", "N", "sbo_rows", "clk/MMA(avg)", "ns/MMA(evt)", "TFLOP/s");
+  for (int n : {64, 128})
+    for (int sbo : {8, 10, 16, 18, 24, 26, 34}) {
+      Rate p;
+      p.n = n; p.row_bytes = 128; p.mn_major = 0; p.distinct_a = 1; p.distinct_b = 1; p.sbo_rows = sbo; p.rounds = 200; p.clk = dclk;
+      rate_kernel<<<sms, 128, smem>>>(p);
+      CK(cudaDeviceSynchronize());
+      CK(cudaEventRecord(e0));
+      rate_kernel<<<sms, 128, smem>>>(p);
+      CK(cudaEventRecord(e1));
+      CK(cudaDeviceSynchronize());
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      std::vector<long long> h(sms);
+      CK(cudaMemcpy(h.data(), dclk, sms * sizeof(long long), cudaMemcpyDeviceToHost));
+      double avg = 0;
+      for (long long v : h) avg += (double)v;
+      avg /= sms;
+      const double mmas = 64.0 * p.rounds;
+      printf("%-10s %4d %9d %12.1f %12.1f %10.1f\n", "K-SW128", n, sbo, avg / mmas, ms * 1e6 / mmas, 2.0 * 128 * n * 16 * mmas * sms / (ms * 1e-3) / 1e12);
+    }
   return 0;
 }
