@@ -47,7 +47,7 @@ int sw_gather_tile(const float* vol, int Cin, int X, int Y, int Z, int x0, int y
 // One block = one (d, h) row segment of SEG consecutive w voxels x all channels.  Phase 1 reads the channels-last logits
 // (coalesced), applies sigmoid * weight * gauss, and parks them transposed in smem; phase 2 does the read-modify-write on
 // the channels-first accumulator with 128-byte coalesced rows.  Tiles of one launch never overlap => plain RMW.
-constexpr int SEG = 64;
+constexpr int SEG = 128;  // 64 measured 3.2 TB/s on the RMW (256-byte rows per class plane); 128 = whole 512-byte patch rows
 constexpr int AGG_T = 256;
 
 template <typename T>

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--vol", type=int, nargs=3, default=[512, 512, 512])
     ap.add_argument("--patch", type=int, nargs=3, default=[192, 160, 128])
     ap.add_argument("--tta", action="store_true")
+    ap.add_argument("--tb", type=int, default=0, help="tiles per network pass (0 = the network's default)")
     ap.add_argument("--dtype", default="bf16")
     a = ap.parse_args()
     dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[a.dtype]
@@ -33,6 +34,8 @@ def main():
     net = tr.network
     net.eval()
     net.do_ds = False
+    if a.tb:
+        net.inference_tile_batch = a.tb
     rng = np.random.RandomState(0)
     vol = rng.randn(1, *a.vol).astype(np.float32)
     steps = net._compute_steps_for_sliding_window(patch, tuple(a.vol), 0.5)
@@ -40,7 +43,8 @@ def main():
     kw = dict(do_mirroring=a.tta, mirror_axes=(0, 1, 2), use_sliding_window=True, step_size=0.5, patch_size=patch,
               regions_class_order=tuple(range(47)), use_gaussian=True, verbose=False, return_device_tensors=True)
     small = vol[:, :patch[0], :patch[1], :patch[2] + 64]
-    net.predict_3D(small, **kw)  # warm-up (2 tiles)
+    s0, p0 = net.predict_3D(vol, **kw)  # warm-up on the same volume (allocator, Gaussian map)
+    del s0, p0
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     seg, prob = net.predict_3D(vol, **kw)
