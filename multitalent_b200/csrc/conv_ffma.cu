@@ -26,7 +26,10 @@ __global__ void __launch_bounds__(FF_THREADS) conv_taps_ffma_kernel(const __grid
   __shared__ __align__(16) float As[FF_KC][FF_BM];
   __shared__ __align__(16) float Ws[FF_KC][BN];
   __shared__ RowInfo rows[FF_BM];
-  __shared__ float s_sum[2][BN], s_sq[2][BN];
+  // InstanceNorm statistics: per-thread partial sums over its 8 rows, then a FIXED-ORDER reduction over the 16 row
+  // groups (no shared-memory float atomics): the fp32 parity mode is reproducible run to run, so no LeakyReLU branch of a
+  // near-zero voxel flips between repetitions (DESIGN.md "Run-to-run variation")
+  __shared__ float s_part[2][2][16][BN];  // [sum | sum of squares][sample of the tile: first / second][row group][cout]
 
   const int tid = threadIdx.x;
   const int g = blockIdx.z;
@@ -43,7 +46,6 @@ __global__ void __launch_bounds__(FF_THREADS) conv_taps_ffma_kernel(const __grid
     if (m < M) r = decode_row(m, p.Do, p.Ho, p.Wo); else { r.b = -1; r.d = r.h = r.w = 0; }
     rows[tid] = r;
   }
-  if (tid < BN) { s_sum[0][tid] = s_sum[1][tid] = 0.f; s_sq[0][tid] = s_sq[1][tid] = 0.f; }
   __syncthreads();
 
   const T* __restrict__ in = reinterpret_cast<const T*>(p.in);
@@ -142,6 +144,9 @@ __global__ void __launch_bounds__(FF_THREADS) conv_taps_ffma_kernel(const __grid
     const int co = n0 + tn * TN + j;
     bsum[j] = (p.bias && co < p.Cout) ? p.bias[co] : 0.f;
   }
+  float ps0[TN], ps1[TN], pq0[TN], pq1[TN];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) { ps0[j] = ps1[j] = pq0[j] = pq1[j] = 0.f; }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const RowInfo r = rows[tm * 8 + i];
@@ -159,10 +164,11 @@ __global__ void __launch_bounds__(FF_THREADS) conv_taps_ffma_kernel(const __grid
       if (p.stats) {
         const float vr = Traits<T>::round(v);
         const int db = r.b - b_first;
-        if (db < 2) {
-          atomicAdd(&s_sum[db][tn * TN + j], vr);
-          atomicAdd(&s_sq[db][tn * TN + j], vr * vr);
-        } else {
+        if (db == 0) {
+          ps0[j] += vr; pq0[j] = fmaf(vr, vr, pq0[j]);
+        } else if (db == 1) {
+          ps1[j] += vr; pq1[j] = fmaf(vr, vr, pq1[j]);
+        } else {  // a 128-voxel tile spanning more than two samples (tiny volumes only)
           double* st = p.stats + ((long long)r.b * p.Cout + co) * 2;
           atomicAdd(st, (double)vr);
           atomicAdd(st + 1, (double)vr * vr);
@@ -171,14 +177,22 @@ __global__ void __launch_bounds__(FF_THREADS) conv_taps_ffma_kernel(const __grid
     }
   }
   if (p.stats) {
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      s_part[0][0][tm][tn * TN + j] = ps0[j]; s_part[0][1][tm][tn * TN + j] = ps1[j];
+      s_part[1][0][tm][tn * TN + j] = pq0[j]; s_part[1][1][tm][tn * TN + j] = pq1[j];
+    }
     __syncthreads();
     if (tid < 2 * BN) {
       const int db = tid / BN, c = tid % BN;
       const int co = n0 + c, b = b_first + db;
-      if (co < p.Cout && b >= 0 && b < p.B && (s_sum[db][c] != 0.f || s_sq[db][c] != 0.f)) {
+      float su = 0.f, sq = 0.f;
+#pragma unroll
+      for (int t = 0; t < 16; ++t) { su += s_part[0][db][t][c]; sq += s_part[1][db][t][c]; }
+      if (co < p.Cout && b >= 0 && b < p.B && (su != 0.f || sq != 0.f)) {
         double* st = p.stats + ((long long)b * p.Cout + co) * 2;
-        atomicAdd(st, (double)s_sum[db][c]);
-        atomicAdd(st + 1, (double)s_sq[db][c]);
+        atomicAdd(st, (double)su);
+        atomicAdd(st + 1, (double)sq);
       }
     }
   }

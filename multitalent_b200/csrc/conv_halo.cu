@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_umma_kernel(const __g
   __shared__ __align__(8) uint64_t w_full[HL_MAX_WSTAGES], w_empty[HL_MAX_WSTAGES];
   __shared__ __align__(8) uint64_t acc_full[HL_NSETS], acc_empty[HL_NSETS];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_bias[64], s_sum[64], s_sq[64];
+  __shared__ float s_bias[64], s_sum[4][64], s_sq[4][64];  // statistics: one slot per epilogue warp, no float atomics
 
   constexpr int KSTEPS = ROWB / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_umma_kernel(const __g
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 64) {
-    s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f;
+    for (int w = 0; w < 4; ++w) { s_sum[w][threadIdx.x] = 0.f; s_sq[w][threadIdx.x] = 0.f; }
     s_bias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.BN) ? p.bias[n0 + threadIdx.x] : 0.f;
   }
   if (warp == 1) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
@@ -294,8 +294,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_umma_kernel(const __g
           warp_colsum16(csq[cc], lane);
           if ((lane & 1) == 0) {
             const int col = colsum16_column(lane);
-            atomicAdd(&s_sum[cc * 16 + col], csum[cc][0]);
-            atomicAdd(&s_sq[cc * 16 + col], csq[cc][0]);
+            s_sum[q][cc * 16 + col] = csum[cc][0];  // once per CTA, one owner lane per (warp, column)
+            s_sq[q][cc * 16 + col] = csq[cc][0];
           }
         }
     }
@@ -303,10 +303,12 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_umma_kernel(const __g
   __syncthreads();
   if (p.stats) {
     for (int c = threadIdx.x; c < p.BN; c += HL_THREADS) {
-      if (s_sum[c] != 0.f || s_sq[c] != 0.f) {
+      const float su = ((s_sum[0][c] + s_sum[1][c]) + s_sum[2][c]) + s_sum[3][c];
+      const float sq = ((s_sq[0][c] + s_sq[1][c]) + s_sq[2][c]) + s_sq[3][c];
+      if (su != 0.f || sq != 0.f) {
         double* st = p.stats + ((long long)b * p.Cout + n0 + c) * 2;
-        atomicAdd(st, (double)s_sum[c]);
-        atomicAdd(st + 1, (double)s_sq[c]);
+        atomicAdd(st, (double)su);
+        atomicAdd(st + 1, (double)sq);
       }
     }
   }

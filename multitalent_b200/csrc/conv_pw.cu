@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(PW_THREADS, 2) conv_pw_umma_kernel(const __gri
   __shared__ __align__(8) uint64_t full_bar[PW_MAX_STAGES], empty_bar[PW_MAX_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], w_full;
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_sum[256], s_sq[256], s_bias[256];
+  __shared__ float s_sum[4][256], s_sq[4][256], s_bias[256];  // statistics: one slot per epilogue warp, no float atomics
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(PW_THREADS, 2) conv_pw_umma_kernel(const __gri
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < 256; i += PW_THREADS) {
-    s_sum[i] = 0.f; s_sq[i] = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { s_sum[w][i] = 0.f; s_sq[w][i] = 0.f; }
     s_bias[i] = (p.bias && i < p.BN) ? p.bias[n0 + i] : 0.f;
   }
   if (warp == 1) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
@@ -185,8 +186,8 @@ __global__ void __launch_bounds__(PW_THREADS, 2) conv_pw_umma_kernel(const __gri
           warp_colsum16(ss, lane);
           if ((lane & 1) == 0) {
             const int col = colsum16_column(lane);
-            atomicAdd(&s_sum[c0 + col], sv[0]);
-            atomicAdd(&s_sq[c0 + col], ss[0]);
+            s_sum[q][c0 + col] += sv[0];  // (warp, column) has exactly one owner lane
+            s_sq[q][c0 + col] += ss[0];
           }
         }
       }
@@ -207,12 +208,14 @@ __global__ void __launch_bounds__(PW_THREADS, 2) conv_pw_umma_kernel(const __gri
         if (next >= p.ntiles || next / p.tiles_per_b != (long long)tile / p.tiles_per_b) {
           const int b = (int)((long long)tile / p.tiles_per_b);
           for (int c = threadIdx.x - 64; c < p.BN; c += 128) {
-            if (s_sum[c] != 0.f || s_sq[c] != 0.f) {
+            const float su = ((s_sum[0][c] + s_sum[1][c]) + s_sum[2][c]) + s_sum[3][c];
+            const float sq = ((s_sq[0][c] + s_sq[1][c]) + s_sq[2][c]) + s_sq[3][c];
+            if (su != 0.f || sq != 0.f) {
               double* st = p.stats + ((long long)b * p.Cout_stride + n0 + c) * 2;
-              atomicAdd(st, (double)s_sum[c]);
-              atomicAdd(st + 1, (double)s_sq[c]);
-              s_sum[c] = 0.f;
-              s_sq[c] = 0.f;
+              atomicAdd(st, (double)su);
+              atomicAdd(st + 1, (double)sq);
+#pragma unroll
+              for (int w = 0; w < 4; ++w) { s_sum[w][c] = 0.f; s_sq[w][c] = 0.f; }
             }
           }
           // the next tile's first bar.sync orders these resets before any further accumulation
@@ -272,7 +275,7 @@ int conv_pw_umma(const mtb200_conv_params& p, cudaStream_t s) {
   int per_sm = q.tmem_cols <= 256 ? 2 : 1;
   int fixed = 0;
   for (;; per_sm = 1) {
-    const int budget = (per_sm == 2 ? 110 : 220) * 1024;
+    const int budget = (per_sm == 2 ? 102 : 212) * 1024;  // + 10.5 KB static (per-warp statistics slots, bias) + 1 KB reserved per CTA
     q.obufs = 2;
     fixed = q.nkc * q.w_chunk_bytes + 2 * q.out_buf_bytes + 1024;
     if ((budget - fixed) / q.a_stage_bytes < 3) {

@@ -118,7 +118,9 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
   __shared__ __align__(8) uint64_t empty_bar[UM_MAX_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_sum[256], s_sq[256], s_bias[256];
+  // statistics: one slot per epilogue warp (TMEM lane quarter), summed in a fixed order at the flush -- no float atomics,
+  // so the forward pass is reproducible run to run (DESIGN.md "Run-to-run variation")
+  __shared__ float s_sum[4][256], s_sq[4][256], s_bias[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
@@ -140,7 +142,8 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < 256; i += UMC_THREADS) {
-    s_sum[i] = 0.f; s_sq[i] = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { s_sum[w][i] = 0.f; s_sq[w][i] = 0.f; }
     s_bias[i] = (p.bias && i < p.BN) ? p.bias[n0 + i] : 0.f;
   }
   if (warp == 1) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
@@ -276,8 +279,8 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
           warp_colsum16(ss, lane);
           if ((lane & 1) == 0) {
             const int col = colsum16_column(lane);
-            atomicAdd(&s_sum[c0 + col], sv[0]);
-            atomicAdd(&s_sq[c0 + col], ss[0]);
+            s_sum[q][c0 + col] += sv[0];  // (q, column) has exactly one owner lane
+            s_sq[q][c0 + col] += ss[0];
           }
         }
       }
@@ -292,12 +295,14 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
         if (next >= p.ntiles || next / tiles_per_b != tile / tiles_per_b) {
           asm volatile("bar.sync 1, 128;" ::: "memory");
           for (int c = threadIdx.x - 64; c < p.BN; c += 128) {
-            if (s_sum[c] != 0.f || s_sq[c] != 0.f) {
+            const float su = ((s_sum[0][c] + s_sum[1][c]) + s_sum[2][c]) + s_sum[3][c];
+            const float sq = ((s_sq[0][c] + s_sq[1][c]) + s_sq[2][c]) + s_sq[3][c];
+            if (su != 0.f || sq != 0.f) {
               double* st = p.stats + ((long long)b * p.Cout + n0 + c) * 2;
-              atomicAdd(st, (double)s_sum[c]);
-              atomicAdd(st + 1, (double)s_sq[c]);
-              s_sum[c] = 0.f;
-              s_sq[c] = 0.f;
+              atomicAdd(st, (double)su);
+              atomicAdd(st + 1, (double)sq);
+#pragma unroll
+              for (int w = 0; w < 4; ++w) { s_sum[w][c] = 0.f; s_sq[w][c] = 0.f; }
             }
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
