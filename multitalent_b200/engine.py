@@ -574,11 +574,16 @@ class Engine:
                 and (op.bias is None or direct_grad(op.bias) is not None)):
             yield
             return
-        side = self._side.get(dev)
-        if side is None:
-            side = self._side[dev] = torch.cuda.Stream(dev)
+        # MTB200_WGRAD_STREAMS side streams taken round-robin per layer: the deep-level launches are a few dozen CTAs each,
+        # so more than two kernels can share the 148 SMs
+        pool = self._side.get(dev)
+        if pool is None:
+            n = max(1, int(os.environ.get("MTB200_WGRAD_STREAMS", "2")))
+            pool = self._side[dev] = [[torch.cuda.Stream(dev) for _ in range(n)], 0]
+        side = pool[0][pool[1] % len(pool[0])]
+        pool[1] += 1
         side.wait_stream(torch.cuda.current_stream(dev))
-        self._side_used = side
+        self._side_used = pool[0]
         with torch.cuda.stream(side):
             yield
 
@@ -710,5 +715,6 @@ class Engine:
             c()
         tape.closures = []
         if self._side_used is not None:  # the optimizer (and the next forward's pool reset) must see every weight gradient
-            torch.cuda.current_stream().wait_stream(self._side_used)
+            for st in self._side_used:
+                torch.cuda.current_stream().wait_stream(st)
             self._side_used = None
