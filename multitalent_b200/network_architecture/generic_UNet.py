@@ -352,6 +352,14 @@ class Generic_UNet(SegmentationNetwork):
         ops = self._ops
         f = x if isinstance(x, Feat) else eng.input_feat(x, compact=eng.use_c1(ops['enc'][0][0][0]))
         dev = f.buf.device
+        # Frozen-trunk fast path (fine-tuning with only the segmentation heads trainable, nnUNetTrainerV2_warmup.py:
+        # 122-124): when no parameter below the heads requires a gradient, the trunk records nothing on the tape and the
+        # backward pass is the heads' weight gradients alone -- no data gradient, no InstanceNorm backward.
+        ttape = tape
+        if tape is not None and not any(p.requires_grad for n, p in self.named_parameters()
+                                        if not n.startswith("seg_outputs.")):
+            ttape = None
+        head_dgrad = ttape is not None
         skips = []
         first = True
         mat = eng.materialize_inputs
@@ -366,13 +374,13 @@ class Generic_UNet(SegmentationNetwork):
                     cat = eng.new_buf(od, 2 * op.Cout_p, dev)
                     if not mat:
                         out = Feat(cat, op.Cout_p, op.Cout, op.Cout_p)
-                f = eng.conv_norm(tape, op, g, b, f, out, need_input_grad=not first)
+                f = eng.conv_norm(ttape, op, g, b, f, out, need_input_grad=not first)
                 if last and mat:
                     f.act = eng.materialize(f, out=Feat(cat, op.Cout_p, op.Cout, op.Cout_p))
                 first = False
             skips.append(f)
         for (op, g, b) in ops['bott']:
-            f = eng.conv_norm(tape, op, g, b, f)
+            f = eng.conv_norm(ttape, op, g, b, f)
         logits = []
         nu = len(ops['tu'])
         for u in range(nu):
@@ -381,7 +389,7 @@ class Generic_UNet(SegmentationNetwork):
             top = ops['tu'][u]
             assert top.Cout_p == skip.Cp and cat.shape[4] == 2 * skip.Cp
             # the transposed conv writes the first half of the same buffer: torch.cat (generic_UNet.py:392) vanishes
-            eng.conv_plain(tape, top, f, Feat(cat, 0, top.Cout, top.Cout_p))
+            eng.conv_plain(ttape, top, f, Feat(cat, 0, top.Cout, top.Cout_p))
             if mat:
                 f = Feat(cat, 0, top.Cout + skip.C, 2 * skip.Cp)
             else:
@@ -390,10 +398,10 @@ class Generic_UNet(SegmentationNetwork):
                 ident[:, :, 2] = 1.0
                 f = Feat(cat, 0, top.Cout + skip.C, 2 * skip.Cp, xform=torch.cat((ident, skip.xform), dim=1))
             for (op, g, b) in ops['dec'][u]:
-                f = eng.conv_norm(tape, op, g, b, f)
+                f = eng.conv_norm(ttape, op, g, b, f)
             if only_full_res and u != nu - 1:
                 continue
-            logits.append(eng.conv_plain(tape, ops['head'][u], f))
+            logits.append(eng.conv_plain(tape, ops['head'][u], f, need_input_grad=head_dgrad))
         return logits[::-1]
 
     def forward(self, x):

@@ -115,6 +115,14 @@ class SegmentationNetwork(NeuralNetwork):
     def native_dtype(self):
         raise NotImplementedError
 
+    def _require_sigmoid(self):
+        """The aggregation kernel applies the MultiTalent inference non-linearity itself (sigmoid, MT:43-46).  A network
+        with another `inference_apply_nonlin` (softmax of the single-task trainers) must not be aggregated silently
+        with the wrong function."""
+        if not isinstance(self.inference_apply_nonlin, nn.Sigmoid):
+            raise NotImplementedError("the native sliding-window predictor fuses sigmoid into its aggregation kernel; "
+                                      "inference_apply_nonlin=%r is not supported" % (self.inference_apply_nonlin,))
+
     # ---- reference API ----------------------------------------------------------------------------------------------
     def predict_3D(self, x: np.ndarray, do_mirroring: bool, mirror_axes: Tuple[int, ...] = (0, 1, 2),
                    use_sliding_window: bool = False, step_size: float = 0.5, patch_size: Tuple[int, ...] = None,
@@ -142,6 +150,7 @@ class SegmentationNetwork(NeuralNetwork):
             raise RuntimeError("the native predictor implements the 3D-conv path only (3d_fullres)")
         if region_vec is not None:
             raise NotImplementedError("region_vec conditioning is not part of the MultiTalent 3d_fullres path")
+        self._require_sigmoid()
         with torch.no_grad():
             if use_sliding_window:
                 return self._internal_predict_3D_3Dconv_tiled(x, step_size, do_mirroring, mirror_axes, patch_size,
@@ -287,6 +296,7 @@ class SegmentationNetwork(NeuralNetwork):
         Returns a CUDA fp32 tensor [1, C, X, Y, Z] like the reference."""
         assert len(x.shape) == 5, 'x must be (b, c, x, y, z)'
         assert x.shape[0] == 1, "the reference calls this with one tile at a time"
+        self._require_sigmoid()
         dev = next(self.parameters()).device
         xt = torch.as_tensor(x, dtype=torch.float32, device=dev)[0].contiguous()
         Cin, X, Y, Z = xt.shape
