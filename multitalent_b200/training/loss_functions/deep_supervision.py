@@ -1,20 +1,27 @@
-"""`MultipleOutputLoss2` -- nnunet/training/loss_functions/deep_supervision.py:30-54: weighted sum of a loss over the
-deep-supervision outputs (zero-weight scales are skipped, the first scale is always evaluated)."""
+"""`MultipleOutputLoss2`: deep-supervision wrapper with the interface of the reference class
+(nnunet/training/loss_functions/deep_supervision.py:30-54).  Semantics kept: the highest-resolution scale is always
+evaluated (even with weight 0), any further scale only when its weight is non-zero, result = weighted sum."""
 from torch import nn
 
 
 class MultipleOutputLoss2(nn.Module):
     def __init__(self, loss, weight_factors=None):
         super().__init__()
-        self.weight_factors = weight_factors
         self.loss = loss
+        self.weight_factors = weight_factors
+
+    def _scale_weights(self, n_scales):
+        if self.weight_factors is None:
+            return [1] * n_scales
+        return list(self.weight_factors)
 
     def forward(self, x, y):
-        assert isinstance(x, (tuple, list)), "x must be either tuple or list"
-        assert isinstance(y, (tuple, list)), "y must be either tuple or list"
-        weights = [1] * len(x) if self.weight_factors is None else self.weight_factors
-        l = weights[0] * self.loss(x[0], y[0])
-        for i in range(1, len(x)):
-            if weights[i] != 0:
-                l = l + weights[i] * self.loss(x[i], y[i])
-        return l
+        for name, seq in (("x", x), ("y", y)):
+            assert isinstance(seq, (tuple, list)), "%s must be either tuple or list" % name
+        w = self._scale_weights(len(x))
+        total = w[0] * self.loss(x[0], y[0])
+        for wi, xi, yi in zip(w[1:len(x)], x[1:], y[1:]):
+            if wi == 0:
+                continue
+            total = total + wi * self.loss(xi, yi)
+        return total
