@@ -29,6 +29,31 @@ FULL_PATCH = (192, 160, 128)
 TRAIN_GFLOP_PER_PATCH = 4769.7   # BASELINE.md section 2 (fwd + dgrad + wgrad, true channel counts)
 
 
+def cuda_kernel_name(tag, shape_repr):
+    """CUDA kernel that `mtb200_conv_taps` / `mtb200_wgrad_taps` dispatch this (family, shape) to in the 16-bit
+    tensor-core mode -- restates the rules of csrc/conv_umma.cu::conv_taps_umma / wgrad_taps_umma for the report (the ncu
+    launch list under profiles/ is the ground truth).  None if the shape is not a convolution."""
+    try:
+        cin, cout, grid, taps, istr, ostr = eval(shape_repr, {"__builtins__": {}})
+        unit = tuple(istr) == (1, 1, 1) and tuple(ostr) == (1, 1, 1)
+        w = grid[2]
+        if cin == 1:
+            return "conv_c1_wgrad_kernel" if tag == "conv_wgrad" else "conv_c1_fwd_kernel"
+        if tag == "conv_wgrad":
+            if unit and w >= 48 and (taps >= 9 or taps == 1) and (cin == 16 or cin % 32 == 0):
+                return "wgrad_line_umma_kernel"
+            return "wgrad_taps_umma_kernel"
+        if taps == 1 and unit:
+            return "conv_pw_umma_kernel"
+        if tuple(ostr) != (1, 1, 1) and tuple(istr) == (1, 1, 1) and grid[2] >= 64 and cin <= 64 and cout <= 64:
+            return "conv_gm_umma_kernel"  # output lattice problems at the top level: strided dgrad, ConvTranspose fwd
+        if unit and taps >= 9 and w >= 72 and cin <= 64 and cout % 32 == 0:
+            return "conv_line_umma_kernel"
+        return "conv_taps_umma_kernel"
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -400,7 +425,8 @@ def main():
         achieved = t["flops"] / (t["ms"] * 1e-3) / 1e12
         peak = pk["bf16_tflops_sustained"]
         fam = ksum[top[0]]
-        roof = {"kernel": top[0], "shape(Cin_p,Cout_p,grid,taps,in_stride,out_stride)": top[1], "bound": "tensor",
+        roof = {"kernel": top[0], "cuda_kernel": cuda_kernel_name(top[0], top[1]) if args.dtype != "fp32" else None,
+                "shape(Cin_p,Cout_p,grid,taps,in_stride,out_stride)": top[1], "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic_tab.get("%s %s" % top), "peak_source": pk["source"] + " (sustained bf16)",
                 "launches": t["launches"], "share_of_kernel_time": t["ms"] / total_kernel_ms,
