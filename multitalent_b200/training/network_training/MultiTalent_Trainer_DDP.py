@@ -31,6 +31,7 @@ from ...engine import bump_weights_epoch, pad_channels
 from ...network_architecture.generic_UNet import Generic_UNet, InitWeights_He
 from ...plans import default_plans
 from ..loss_functions.multitalent_loss import multitalent_loss
+from ..online_evaluation import OnlineEvaluationMixin
 
 
 def poly_lr(epoch, max_epochs, initial_lr, exponent=0.9):
@@ -82,7 +83,7 @@ class FlatArena:
         bump_weights_epoch()
 
 
-class MultiTalent_trainer_ddp(object):
+class MultiTalent_trainer_ddp(OnlineEvaluationMixin):
     def __init__(self, plans_file, fold, local_rank, output_folder=None, dataset_directory=None, batch_dice=True,
                  stage=None, unpack_data=True, deterministic=True, distribute_batch_size=False, fp16=False,
                  native_dtype=None, flat_optimizer=True, init_distributed=True):
@@ -264,7 +265,11 @@ class MultiTalent_trainer_ddp(object):
             main.wait_event(ready)
             for t in [data] + target:
                 t.record_stream(main)
-        l, ce, dc = self.train_step(data, target, valid_regions, do_backprop, target_ready=tready)
+        l, ce, dc = self.train_step(data, target, valid_regions, do_backprop, target_ready=tready,
+                                    keep_output=run_online_evaluation)
+        if run_online_evaluation:
+            self.run_online_evaluation(self._last_output, target, valid_regions)
+            self._last_output = None
         if getattr(self, "prefetch_batches", True) and torch.cuda.is_available():
             try:
                 nxt = next(data_generator)
@@ -275,7 +280,7 @@ class MultiTalent_trainer_ddp(object):
         res = torch.stack((l.detach(), ce.detach(), dc.detach())).cpu().numpy()
         return res[0], res[1], res[2]
 
-    def train_step(self, data, target, valid_regions, do_backprop=True, target_ready=None):
+    def train_step(self, data, target, valid_regions, do_backprop=True, target_ready=None, keep_output=False):
         """One optimisation step on device-resident tensors; returns device scalars (no sync).  `target_ready`: CUDA
         event after which `target` may be read (asynchronous H2D copy issued by `run_iteration`)."""
         if self.arena is not None:
@@ -287,6 +292,8 @@ class MultiTalent_trainer_ddp(object):
             if target_ready is not None:
                 torch.cuda.current_stream().wait_event(target_ready)
             l, ce, dc = self.compute_loss(output, target, valid_regions)
+            if keep_output:  # run_online_evaluation reads the highest-resolution logits after the step (MT:367-368)
+                self._last_output = tuple(o.detach() for o in output)
             if do_backprop:
                 (l * self.loss_scale if self.loss_scale != 1.0 else l).backward()
         if do_backprop:
