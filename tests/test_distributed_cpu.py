@@ -124,3 +124,71 @@ def test_two_rank_loss_and_gradient_match_reference_under_gloo():
         for g, gr in zip(res["grads"], ref["grads"]):
             scale = float(np.abs(gr).max()) + 1e-12
             assert float(np.abs(g - gr).max()) / scale < 1e-4
+
+
+# ---- online evaluation under two ranks (MT:372-410: per-rank counts all-gathered to [W, B, 47]) ---------------------------
+def _eval_worker(rank, world, initfile, use_reference, q):
+    sys.path.insert(0, ROOT)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", init_method=initfile, rank=rank, world_size=world)
+    try:
+        from types import SimpleNamespace
+        from multitalent_b200.training.online_evaluation import OnlineEvaluationMixin
+        logits, targets, valid = _rank_inputs(rank)
+
+        class Mine(OnlineEvaluationMixin):
+            pass
+        mine = Mine()
+        mine.run_online_evaluation([logits[0]], [targets[0]], valid)
+        res = {k: np.array(getattr(mine, k), dtype=np.float64) for k in
+               ("online_eval_foreground_dc", "online_eval_tp", "online_eval_fp", "online_eval_fn")}
+        if use_reference:
+            from oracle import ref_import
+            ref_import.install()
+            from nnunet.training.network_training.custom_trainers.MultiTalent.MultiTalent.MultiTalent_Trainer_DDP import \
+                MultiTalent_trainer_ddp as Ref
+            ref = SimpleNamespace(online_eval_foreground_dc=[], online_eval_tp=[], online_eval_fp=[], online_eval_fn=[])
+            Ref.run_online_evaluation(ref, [logits[0]], [targets[0]], valid)
+            res["ref"] = {k: np.array(getattr(ref, k), dtype=np.float64) for k in
+                          ("online_eval_foreground_dc", "online_eval_tp", "online_eval_fp", "online_eval_fn")}
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_eval(world, use_reference):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    init = "tcp://127.0.0.1:%d" % port
+    procs = [ctx.Process(target=_eval_worker, args=(r, world, init, use_reference, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = {}
+    for _ in range(world):
+        r, res = q.get(timeout=240)
+        out[r] = res
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return out
+
+
+def test_online_evaluation_gathers_counts_over_ranks():
+    sys.path.insert(0, ROOT)
+    from multitalent_b200.training.online_evaluation import hard_tp_fp_fn
+    out = _run_eval(2, os.path.isdir("/root/reference/nnunet"))
+    local = []
+    for r in range(2):
+        logits, targets, valid = _rank_inputs(r)
+        local.append([t.numpy().astype(np.float64) for t in hard_tp_fp_fn(logits[0], targets[0], valid)])
+    tp = np.stack([local[0][0], local[1][0]])            # [W, B, 47]
+    for r in range(2):
+        assert out[r]["online_eval_foreground_dc"].shape == (1, 2, 2, 47)   # one iteration, [W, B, 47]
+        np.testing.assert_allclose(out[r]["online_eval_tp"][0], tp.sum(0), rtol=0, atol=0)
+        if "ref" in out[r]:
+            for k, v in out[r]["ref"].items():
+                np.testing.assert_allclose(out[r][k], v, rtol=1e-6, atol=1e-7, err_msg=k)
