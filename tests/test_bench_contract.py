@@ -62,3 +62,18 @@ def test_native_arm_refuses_to_run_without_gpu():
                        capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode != 0 and r.stdout.strip() == ""
     assert "no CPU fallback" in r.stderr
+
+
+def test_roofline_kernel_naming_follows_the_dispatch_rules():
+    bench = _load_bench()
+    name = bench.cuda_kernel_name
+    unit = "(1, 1, 1), (1, 1, 1))"
+    assert name("conv_wgrad", "(32, 32, (192, 160, 128), 27, " + unit) == "wgrad_line_umma_kernel"
+    assert name("conv_wgrad", "(128, 128, (48, 40, 32), 27, " + unit) == "wgrad_taps_umma_kernel"       # W < 48
+    assert name("conv_fwd", "(64, 32, (192, 160, 128), 27, " + unit) == "conv_line_umma_kernel"
+    assert name("conv_fwd", "(64, 64, (96, 80, 64), 27, " + unit) == "conv_taps_umma_kernel"           # W < 72
+    assert name("conv_dgrad", "(48, 32, (192, 160, 128), 1, " + unit) == "conv_pw_umma_kernel"
+    assert name("conv_fwd", "(1, 32, (192, 160, 128), 27, " + unit) == "conv_c1_fwd_kernel"
+    assert name("conv_dgrad", "(64, 32, (96, 80, 64), 27, (1, 1, 1), (2, 2, 2))") == "conv_gm_umma_kernel"
+    assert name("conv_fwd", "(32, 64, (96, 80, 64), 27, (2, 2, 2), (1, 1, 1))") == "conv_taps_umma_kernel"
+    assert name("mtb200_norm_act", "None") is None
