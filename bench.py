@@ -3,11 +3,15 @@
 GPU, 13-dataset multi-head loss, clip + Nesterov SGD) on N B200s -- BASELINE.json `configs[1]`.
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run by the driver)
+    python bench.py --net resenc ...                         (BASELINE.json configs[2]: FabiansUNet, resenc plan, bs 4)
+    python bench.py --dtype fp16 ...                         (configs[1] as worded: fp16 + dynamic loss scaling)
     python bench.py --impl reference ...                     (the reference algorithm's CPU arm: oracle port on host cores)
 
 Prints ONE JSON line (rank 0).  `value` = whole-job patches/s with inputs resident in HBM; `e2e` = the same through
 `MultiTalent_trainer_ddp.run_iteration` with pinned HOST batches (H2D of data+targets and D2H of the loss inside the timed
-region); `roofline` = the dominant kernel family against MEASURED_PEAKS.json; `cpu_baseline` = the oracle on host cores.
+region); `roofline` = the dominant CUDA kernel against MEASURED_PEAKS.json plus whole-step fractions, the library
+(cuDNN under autocast) arm on the same GPU and the sliding-window inference leg as scalar keys; `cpu_baseline` = the
+oracle on host cores.
 """
 import argparse
 import json
@@ -26,32 +30,17 @@ import torch  # noqa: E402
 
 METRIC = "3D patches/sec (192x160x128, bs4) training step"
 FULL_PATCH = (192, 160, 128)
-TRAIN_GFLOP_PER_PATCH = 4769.7   # BASELINE.md section 2 (fwd + dgrad + wgrad, true channel counts)
-
-
-def cuda_kernel_name(tag, shape_repr):
-    """CUDA kernel that `mtb200_conv_taps` / `mtb200_wgrad_taps` dispatch this (family, shape) to in the 16-bit
-    tensor-core mode -- restates the rules of csrc/conv_umma.cu::conv_taps_umma / wgrad_taps_umma for the report (the ncu
-    launch list under profiles/ is the ground truth).  None if the shape is not a convolution."""
-    try:
-        cin, cout, grid, taps, istr, ostr = eval(shape_repr, {"__builtins__": {}})
-        unit = tuple(istr) == (1, 1, 1) and tuple(ostr) == (1, 1, 1)
-        w = grid[2]
-        if cin == 1:
-            return "conv_c1_wgrad_kernel" if tag == "conv_wgrad" else "conv_c1_fwd_kernel"
-        if tag == "conv_wgrad":
-            if unit and w >= 48 and (taps >= 9 or taps == 1) and (cin == 16 or cin % 32 == 0):
-                return "wgrad_line_umma_kernel"
-            return "wgrad_taps_umma_kernel"
-        if taps == 1 and unit:
-            return "conv_pw_umma_kernel"
-        if tuple(ostr) != (1, 1, 1) and tuple(istr) == (1, 1, 1) and grid[2] >= 64 and cin <= 64 and cout <= 64:
-            return "conv_gm_umma_kernel"  # output lattice problems at the top level: strided dgrad, ConvTranspose fwd
-        if unit and taps >= 9 and w >= 72 and cin <= 64 and cout % 32 == 0:
-            return "conv_line_umma_kernel"
-        return "conv_taps_umma_kernel"
-    except Exception:
-        return None
+# fwd + dgrad + wgrad GFLOP per 192x160x128 patch, true channel counts
+TRAIN_GFLOP_PER_PATCH = {"generic": 4769.7, "resenc": 7973.6}
+FWD_GFLOP_PER_PATCH = {"generic": 1592.0, "resenc": 2660.0}
+WORKLOAD = {
+    "generic": "Generic_UNet 3d_fullres (MultiTalent_bs4 plan) training step: fwd + 13-dataset multi-head BCE+Dice loss "
+               "+ bwd + clip12 + Nesterov SGD",
+    "resenc": "FabiansUNet residual-encoder U-Net (MultiTalent_resenc_bs4 plan) training step: fwd + 13-dataset "
+              "multi-head BCE+Dice loss + bwd + clip12 + Nesterov SGD",
+}
+GENERIC_POOL = [[2, 2, 2]] * 4 + [[1, 2, 2]]
+GENERIC_CONVK = [[3, 3, 3]] * 6
 
 
 def peaks():
@@ -125,37 +114,54 @@ class ClockSampler(threading.Thread):
                 "source": "nvml (in-process)" if self.nv is not None else "nvidia-smi"}
 
 
-def cpu_oracle_step_factory(patch, seed=0):
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on host cores (oracle port only -- nothing of the product is imported here)
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_oracle_step_factory(patch, net="generic", seed=0):
     """One training step of the reference algorithm on host cores: oracle forward + MultiTalent loss + backward +
     clip/SGD, bs 1, fp32 (the reference's own CPU path, restated)."""
     from oracle import unet_oracle as O
-    from multitalent_b200.network_architecture.generic_UNet import Generic_UNet, InitWeights_He
-    from torch import nn
-    pool = [[2, 2, 2]] * 4 + [[1, 2, 2]]
-    convk = [[3, 3, 3]] * 6
-    torch.manual_seed(seed)
-    net = Generic_UNet(1, 30, 47, 5, 2, 2, nn.Conv3d, nn.InstanceNorm3d, {'eps': 1e-5, 'affine': True}, nn.Dropout3d,
-                       {'p': 0, 'inplace': True}, nn.LeakyReLU, {'negative_slope': 1e-2, 'inplace': True}, True, False,
-                       lambda x: x, InitWeights_He(1e-2), pool, convk, False, True, True)
-    names = [n for n, _ in net.named_parameters()]
-    state = {"p": [p.detach().clone() for _, p in net.named_parameters()], "buf": [None] * len(names)}
+    if net == "generic":
+        pool, convk = GENERIC_POOL, GENERIC_CONVK
+        sd0 = O.generic_unet_random_state_dict(pool, convk, seed=seed)
+        scales = [[1, 1, 1]] + [list(s) for s in 1 / np.cumprod(np.vstack(pool), axis=0)][:-1]
+
+        def fwd(x, sd):
+            return O.generic_unet_forward(x, sd, pool, convk)
+        n_out = 5
+    else:
+        pool = [[1, 1, 1], [1, 2, 2]] + [[2, 2, 2]] * 4
+        convk = [[1, 3, 3]] + [[3, 3, 3]] * 5
+        be, bd = (1, 2, 3, 4, 4, 4), (1, 1, 1, 1, 1)
+        sd0 = O.fabians_unet_random_state_dict(be, pool, convk, bd, seed=seed)
+        scales = [[1, 1, 1]] + [list(s) for s in 1 / np.cumprod(np.vstack(pool[1:]), axis=0)][:-1]
+
+        def fwd(x, sd):
+            return O.fabians_unet_forward(x, sd, be, pool, convk, bd)
+        n_out = 5
+    names = list(sd0.keys())
+    state = {"p": [sd0[n].clone() for n in names], "buf": [None] * len(names)}
     rng = np.random.RandomState(1234)
     task = O.TASK_IDS[6]
     vol, lab = O.synthetic_ct_and_labels(patch, task, rng)
     x = torch.from_numpy(vol[None, None])
-    scales = [[1, 1, 1], [.5] * 3, [.25] * 3, [.125] * 3, [1 / 16] * 3]
     tg = [torch.from_numpy(t) for t in O.downsample_targets(lab[None, None], scales)]
     valid = [O.VALID_REGIONS[task]]
-    w = O.multitalent_ds_loss_weights(5)
+    w = O.multitalent_ds_loss_weights(n_out)
 
     def step():
         sd = {n: p.clone().requires_grad_(True) for n, p in zip(names, state["p"])}
-        out = O.generic_unet_forward(x, sd, pool, convk)
+        out = fwd(x, sd)
         l, _, _ = O.multitalent_loss(out, tg, valid, w)
         l.backward()
         state["p"], state["buf"], _ = O.clip_and_sgd_step(state["p"], [sd[n].grad for n in names], state["buf"], 1e-2)
-        return float(l)
+        return float(l.detach())
     return step
+
+
+def cpu_sample_patch(net):
+    # resenc has 6 resolution levels (down to 1/16, 1/32, 1/32): the sample must stay > 1 voxel at the bottom
+    return (96, 96, 64) if net == "generic" else (64, 128, 96)
 
 
 def run_reference(args, rank, out=sys.stdout):
@@ -165,17 +171,17 @@ def run_reference(args, rank, out=sys.stdout):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    # bounded sample of the workload: 0.15 of the benchmark patch per step; if K+W steps of that would not finish within
-    # ~4 minutes on this host (timed on the first step), fall back to a 48x64x64 sample (0.05 of the patch)
-    sample_patch = (96, 96, 64)
-    step = cpu_oracle_step_factory(sample_patch)
+    # bounded sample of the workload per step; if K+W steps of that would not finish within ~4 minutes on this host
+    # (timed on the first step), fall back to a smaller sample
+    sample_patch = cpu_sample_patch(args.net)
+    step = cpu_oracle_step_factory(sample_patch, args.net)
     t_probe = time.perf_counter()
     step()
     t_probe = time.perf_counter() - t_probe
     done_warm = 1
     if t_probe * (args.steps + args.warmup) > 240.0:
-        sample_patch = (48, 64, 64)
-        step = cpu_oracle_step_factory(sample_patch)
+        sample_patch = (48, 64, 64) if args.net == "generic" else (32, 64, 64)
+        step = cpu_oracle_step_factory(sample_patch, args.net)
         done_warm = 0
     frac = float(np.prod(sample_patch)) / float(np.prod(FULL_PATCH))
     for _ in range(max(0, args.warmup - done_warm)):
@@ -190,12 +196,56 @@ def run_reference(args, rank, out=sys.stdout):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Generic_UNet 3d_fullres training step, 13-dataset multi-head loss, CPU sample",
+            "config": {"workload": WORKLOAD[args.net] + " -- CPU sample", "net": args.net,
                        "patch": list(sample_patch), "batch_per_step": 1},
             "cpu_baseline": {"value": value, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=out, flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# library arm on the same GPU: the reference's ops (cuDNN / ATen under autocast) -- "the real bar", SURVEY.md 2a / 8d
+# ----------------------------------------------------------------------------------------------------------------------
+def gpu_reference_leg(sd, trainer, data, target, valid, amp_dtype, steps, warmup, net):
+    """patches/s of the reference's training step through the library on this GPU: oracle port on CUDA tensors =
+    F.conv3d / F.instance_norm / F.leaky_relu (cuDNN, cudnn.benchmark) under torch.autocast(amp_dtype), the reference's
+    Python loss loop, GradScaler, clip 12, torch.optim.SGD(nesterov).  Same batch, same warm-up discipline, CUDA events.
+    Timed twice: NCDHW tensors (what the reference does) and channels_last_3d (the library at its best)."""
+    from oracle.gpu_reference import GpuReference
+    sp = trainer.plans['plans_per_stage'][trainer.stage]
+    res = {}
+    for tag, cl in (("", False), ("_channels_last", True)):
+        try:
+            if net == "generic":
+                ref = GpuReference(sd, trainer.net_num_pool_op_kernel_sizes, trainer.net_conv_kernel_sizes, amp_dtype,
+                                   channels_last=cl, ds_loss_weights=trainer.ds_loss_weights)
+            else:
+                ref = GpuReference(sd, sp['pool_op_kernel_sizes'], sp['conv_kernel_sizes'], amp_dtype, channels_last=cl,
+                                   arch="fabians", blocks_enc=sp['num_blocks_encoder'],
+                                   blocks_dec=sp['num_blocks_decoder'], ds_loss_weights=trainer.ds_loss_weights)
+            for _ in range(warmup):
+                l = ref.train_step(data, target, valid)[0]
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                l = ref.train_step(data, target, valid)[0]
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            res["cudnn%s_ms_per_step" % tag] = ms
+            res["cudnn%s_patches_s" % tag] = data.shape[0] / (ms * 1e-3)
+            res["cudnn%s_loss" % tag] = float(l)
+            res["cudnn%s_peak_mem_gb" % tag] = torch.cuda.max_memory_allocated() / 2 ** 30
+        except Exception as exc:  # an out-of-memory library arm must not take the native numbers down with it
+            res["cudnn%s_error" % tag] = "%s: %s" % (type(exc).__name__, str(exc)[:160])
+        ref = None
+        torch.cuda.empty_cache()
+    res["cudnn_steps"], res["cudnn_warmup"] = steps, warmup
+    res["cudnn_mode"] = "torch %s, cuDNN %s, cudnn.benchmark, autocast(%s), GradScaler, python loss loop" % (
+        torch.__version__, torch.backends.cudnn.version(), str(amp_dtype).replace("torch.", ""))
+    return res
 
 
 def _claim_stdout():
@@ -214,14 +264,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--net", default="generic", choices=["generic", "resenc"],
+                    help="generic = BASELINE.json configs[1]; resenc = configs[2] (FabiansUNet, resenc plan, bs 4)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--patch", type=int, nargs=3, default=list(FULL_PATCH))
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (ncu passes only)")
     ap.add_argument("--no-infer", action="store_true", help="skip the sliding-window inference leg")
-    ap.add_argument("--infer-vol", type=int, nargs=3, default=[384, 320, 256],
-                    help="synthetic volume of the inference leg (27 tiles of 192x160x128 at step 0.5)")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the library (cuDNN autocast) arm")
+    ap.add_argument("--infer-vol", type=int, nargs=3, default=[512, 512, 512],
+                    help="synthetic volume of the inference leg (BASELINE.json configs[3]: 512^3 = 210 tiles at step 0.5)")
     ap.add_argument("--no-profile", action="store_true", help="no per-launch CUDA events in the timed region")
     ap.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 force CUDA-core kernels, 2 force tcgen05")
     args = ap.parse_args()
@@ -238,19 +291,19 @@ def main():
     from multitalent_b200.plans import default_plans
     from multitalent_b200.synthetic import synthetic_batch
     from multitalent_b200.training.network_training.MultiTalent_Trainer_DDP import MultiTalent_trainer_ddp
+    from multitalent_b200.training.network_training.MultiTalent_meets_resenc import MultiTalent_trainer_resenc_ddp
 
     assert torch.cuda.is_available(), "bench.py (native arm) needs a GPU; there is no CPU fallback"
     L.lib()
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.dtype]
     patch = tuple(args.patch)
-    tr = MultiTalent_trainer_ddp(default_plans(patch_size=patch, batch_size=args.batch), 0, local_rank,
-                                 native_dtype=dt, init_distributed=world > 1)
+    cls = MultiTalent_trainer_ddp if args.net == "generic" else MultiTalent_trainer_resenc_ddp
+    tr = cls(default_plans(args.net, patch_size=patch, batch_size=args.batch), 0, local_rank,
+             native_dtype=dt, init_distributed=world > 1)
     torch.manual_seed(0)  # same initial weights on every rank (they are broadcast anyway)
     tr.initialize(True)
     tr.network._engine.impl = args.kernel_impl
-    if args.dtype == "fp16":
-        tr.loss_scale = 4096.0  # static loss scale (the reference uses a dynamic GradScaler, MT:350-354)
     dev = torch.device("cuda", local_rank)
 
     batch = synthetic_batch(patch, args.batch, rank, tr.deep_supervision_scales)
@@ -260,6 +313,7 @@ def main():
     d_data = host_data.to(dev)
     d_tgt = [t.to(dev) for t in host_tgt]
     h2d = host_data.numel() * 4 + sum(t.numel() * 4 for t in host_tgt)
+    sd0 = {k: v.detach().clone() for k, v in tr.network.state_dict().items()}  # for the library arm: same start
 
     def barrier():
         if world > 1:
@@ -294,7 +348,7 @@ def main():
 
     # ---- the same K steps again with one CUDA-event pair around every launch (on the launching stream): per-kernel
     #      durations for the roofline section.  The events cost ~3 % of a step, which is why `value` is taken above.
-    ksum, ms_profiled, shapes = {}, None, {}
+    ksum, ms_profiled, shapes, kernels = {}, None, {}, {}
     if not args.no_profile:
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         # per-kernel durations are taken with the weight-gradient stream folded back into the main stream: two kernels
@@ -310,6 +364,7 @@ def main():
             barrier()
         eng.overlap_wgrad = overlap
         ksum = kp.summary()
+        kernels = kp.per_cuda_kernel()
         ms_profiled = p0.elapsed_time(p1) / args.steps
         for tag, info, kms, fl, _nb in kp.per_launch():  # group launches by (family, problem shape)
             g = shapes.setdefault((tag, repr(info)), {"launches": 0, "ms": 0.0, "flops": 0.0})
@@ -339,11 +394,21 @@ def main():
             dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
         e2e_ms_per_step = float(e2e_ms.item()) / args.steps
 
-    # ---- inference leg (BASELINE.json metric: "train+infer"): sliding-window predict_3D of one synthetic volume per
-    #      rank (replicas only, no collective), patch 192x160x128, step 0.5, Gaussian weighting, no mirroring.
-    #      `value`: host volume in, probabilities + segmentation left on the device; `e2e`: the reference contract
-    #      (numpy in -> numpy out, i.e. including the D2H of the [47, X, Y, Z] fp32 probabilities).
-    infer = None
+    # ---- library arm (rank 0 of a 1-GPU run): the reference's ops under autocast on the same batch, same GPU
+    cudnn = {}
+    if world == 1 and not args.no_gpu_reference and args.dtype != "fp32":
+        tr._prefetched = {}
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+        cudnn = gpu_reference_leg(sd0, tr, d_data, d_tgt, valid, dt, min(args.steps, 8), min(max(args.warmup, 2), 3),
+                                  args.net)
+
+    # ---- inference leg (BASELINE.json metric: "train+infer", configs[3]): sliding-window predict_3D of one synthetic
+    #      512^3 volume per rank (replicas only, no collective), patch 192x160x128, step 0.5, Gaussian weighting, no
+    #      mirroring.  `infer_patches_s`: host volume in, probabilities + segmentation left on the device;
+    #      `infer_e2e_patches_s`: the reference contract (numpy in -> numpy out, i.e. including the D2H of the
+    #      [47, X, Y, Z] fp32 probabilities).
+    infer = {}
     if not args.no_infer and patch == FULL_PATCH:
         del d_data, d_tgt
         tr._prefetched = {}
@@ -389,17 +454,15 @@ def main():
         if world > 1:
             dist.all_reduce(inf_ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(inf_e2e_s, op=dist.ReduceOp.MAX)
-        infer = {"metric": "3D patches/sec (192x160x128) sliding-window inference", "unit": "patches/s",
-                 "value": world * ntiles / (float(inf_ms.item()) * 1e-3),
-                 "seconds_per_volume": float(inf_ms.item()) * 1e-3, "volume": list(ivol), "tiles_per_volume": ntiles,
-                 "volumes": world, "tile_batch": int(getattr(net, "inference_tile_batch", 4)), "mirroring": False,
-                 "gpu_launches": int(inf_launches),
-                 "includes": "H2D of the volume, per tile: gather + forward + sigmoid*Gaussian scatter-add, normalise + "
-                             "threshold; results left in HBM",
-                 "e2e": {"value": world * ntiles / float(inf_e2e_s.item()), "unit": "patches/s",
-                         "seconds_per_volume": float(inf_e2e_s.item()), "h2d_bytes": int(vol.nbytes),
-                         "d2h_bytes": d2h, "timing": "host wall clock around predict_preprocessed_data_return_seg_and_"
-                                                       "softmax (numpy in, numpy out), second volume of a run"}}
+        pps = world * ntiles / (float(inf_ms.item()) * 1e-3)
+        infer = {"infer_patches_s": pps, "infer_seconds_per_volume": float(inf_ms.item()) * 1e-3,
+                 "infer_volume": "x".join(str(v) for v in ivol), "infer_tiles": ntiles,
+                 "infer_tile_batch": int(getattr(net, "inference_tile_batch", 4)), "infer_mirroring": False,
+                 "infer_gpu_launches": int(inf_launches),
+                 "infer_tflops": pps / world * FWD_GFLOP_PER_PATCH[args.net] * 1e-3,
+                 "infer_e2e_patches_s": world * ntiles / float(inf_e2e_s.item()),
+                 "infer_e2e_seconds_per_volume": float(inf_e2e_s.item()),
+                 "infer_h2d_bytes": int(vol.nbytes), "infer_d2h_bytes": d2h}
 
     if rank != 0:
         return
@@ -409,42 +472,69 @@ def main():
     value = patches_per_step / (ms_per_step * 1e-3)
     e2e_value = patches_per_step / (e2e_ms_per_step * 1e-3) if e2e_ms_per_step else None
 
-    # roofline of the dominant kernel = the (kernel family, problem shape) group with the most device time inside the
-    # timed region; algorithmic FLOPs per launch (true channel counts) / average measured launch duration
-    total_kernel_ms = sum(v["ms"] for v in ksum.values())
-    conv_shapes = {k: v for k, v in shapes.items() if k[0].startswith("conv_") and v["flops"] > 0}
-    roof = None
+    # roofline of the dominant kernel = the CUDA kernel (as dispatched inside the library, mtb200_last_kernel) with the
+    # largest share of the device time inside the timed region: algorithmic FLOPs (true channel counts) of its launches
+    # / their measured duration = average per launch over average per launch.
+    total_kernel_ms = sum(v["ms"] for v in kernels.values())
+    step_tflops = TRAIN_GFLOP_PER_PATCH[args.net] * vox_frac * args.batch / ms_per_step  # GFLOP/ms == TFLOP/s per GPU
+    roof = {}
     traffic_tab = {}
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from the committed ncu --set full
     if os.path.exists(tp):
         with open(tp) as f:
             traffic_tab = json.load(f)
-    if conv_shapes:
-        top = max(conv_shapes, key=lambda k: conv_shapes[k]["ms"])
-        t = conv_shapes[top]
-        achieved = t["flops"] / (t["ms"] * 1e-3) / 1e12
-        peak = pk["bf16_tflops_sustained"]
-        fam = ksum[top[0]]
-        roof = {"kernel": top[0], "cuda_kernel": cuda_kernel_name(top[0], top[1]) if args.dtype != "fp32" else None,
-                "shape(Cin_p,Cout_p,grid,taps,in_stride,out_stride)": top[1], "bound": "tensor",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic_tab.get("%s %s" % top), "peak_source": pk["source"] + " (sustained bf16)",
-                "launches": t["launches"], "share_of_kernel_time": t["ms"] / total_kernel_ms,
+    if kernels:
+        top = max(kernels, key=lambda k: kernels[k]["ms"])
+        t = kernels[top]
+        conv_ms = sum(v["ms"] for k, v in ksum.items() if k.startswith("conv_"))
+        conv_fl = sum(v["flops"] for k, v in ksum.items() if k.startswith("conv_"))
+        if t["flops"] > 0:
+            achieved = t["flops"] / (t["ms"] * 1e-3) / 1e12
+            peak, unit, bound = pk["bf16_tflops_sustained"], "TFLOP/s", "tensor"
+        else:  # a streaming kernel on top: report it against HBM instead (bytes are not tracked per launch -> None)
+            achieved, peak, unit, bound = None, pk["hbm_gbs"], "GB/s", "hbm"
+        tr_entry = traffic_tab.get("kernel:" + top)
+        roof = {"kernel": top + "_kernel", "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+                "frac": achieved / peak if achieved else None,
+                "traffic": tr_entry.get("dram_bytes_per_launch") if isinstance(tr_entry, dict) else tr_entry,
+                "algorithmic_bytes_per_launch": tr_entry.get("algorithmic_bytes_per_launch")
+                if isinstance(tr_entry, dict) else None,
+                "peak_source": pk["source"] + " (sustained bf16: kernels timed inside a long step)",
+                "launches_per_step": t["launches"] / args.steps,
+                "share_of_kernel_time": t["ms"] / total_kernel_ms,
                 "flops_per_launch": t["flops"] / t["launches"], "ms_per_launch_avg": t["ms"] / t["launches"],
-                "family": {"launches": fam["launches"], "share_of_kernel_time": fam["ms"] / total_kernel_ms,
-                           "achieved": fam["flops"] / (fam["ms"] * 1e-3) / 1e12}}
-    step_tflops = TRAIN_GFLOP_PER_PATCH * vox_frac * args.batch / ms_per_step  # GFLOP/ms == TFLOP/s
+                "ms_per_step": t["ms"] / args.steps,
+                # the whole path, not its best slice
+                "conv_family_tflops": conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms else None,
+                "family_frac": conv_fl / (conv_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"] if conv_ms else None,
+                "conv_share_of_kernel_time": conv_ms / total_kernel_ms if total_kernel_ms else None}
+    roof.update({"step_tflops": step_tflops, "step_frac_sustained": step_tflops / pk["bf16_tflops_sustained"],
+                 "step_frac_burst": step_tflops / pk["bf16_tflops"],
+                 "target_ms_per_step_at_half_burst": TRAIN_GFLOP_PER_PATCH[args.net] * vox_frac * args.batch /
+                 (0.5 * pk["bf16_tflops"])})
+    for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])[:12]:  # per-CUDA-kernel ms per step (scalars)
+        roof["ms_%s" % k] = round(v["ms"] / args.steps, 4)
+    if cudnn:
+        roof.update(cudnn)
+        best = max([cudnn.get("cudnn_patches_s") or 0.0, cudnn.get("cudnn_channels_last_patches_s") or 0.0])
+        if best > 0:
+            roof["vs_cudnn"] = value / best
+            roof["vs_cudnn_ncdhw"] = value / cudnn["cudnn_patches_s"] if cudnn.get("cudnn_patches_s") else None
+    if infer:
+        roof.update({k: infer[k] for k in ("infer_patches_s", "infer_seconds_per_volume", "infer_volume", "infer_tiles",
+                                          "infer_tflops", "infer_gpu_launches")})
+        roof["infer_frac_burst"] = infer["infer_tflops"] / pk["bf16_tflops"]
     line = {"metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": "Generic_UNet 3d_fullres (MultiTalent_bs4 plan) training step: fwd + 13-dataset "
-                                   "multi-head BCE+Dice loss + bwd + clip12 + Nesterov SGD",
-                       "patch": list(patch), "batch_per_gpu": args.batch, "global_batch": patches_per_step,
+            "config": {"workload": WORKLOAD[args.net], "net": args.net,
+                       "patch": "x".join(str(v) for v in patch), "batch_per_gpu": args.batch,
+                       "global_batch": patches_per_step,
                        "parallelism": "dp%d" % world, "l2": "working set (activations > 8 GB) far exceeds the 126 MB L2",
-                       "loss": loss_val},
+                       "loss": loss_val, "loss_scaling": tr.loss_scaling_description()},
             "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 12,
                     "ms_per_step": e2e_ms_per_step},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "infer": infer,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "ms_per_step_with_per_launch_events": ms_profiled,
             "per_launch_events_note": "second pass, weight-gradient stream serialised into the main stream",
             "ms_each_step": [round(m, 3) for m in ms_each],
@@ -452,27 +542,34 @@ def main():
                             "ms_per_step": round(v["ms"] / args.steps, 4),
                             "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["flops"] else None}
                            for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])[:40]],
-            "step_tflops_algorithmic": step_tflops / world * world if world == 1 else step_tflops,
-            "step_frac_of_bf16_peak": step_tflops / pk["bf16_tflops_sustained"],
+            "cuda_kernels": {k: {"launches": v["launches"], "ms_per_step": v["ms"] / args.steps,
+                                 "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] and v["ms"] else None}
+                             for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
             "kernels": {k: {"launches": v["launches"], "ms_per_step": v["ms"] / args.steps,
                             "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] and v["ms"] else None}
                         for k, v in sorted(ksum.items(), key=lambda kv: -kv[1]["ms"])}}
+    if infer:
+        line["e2e"].update({k: infer[k] for k in ("infer_e2e_patches_s", "infer_e2e_seconds_per_volume",
+                                                  "infer_h2d_bytes", "infer_d2h_bytes")})
+        line["config"].update({"infer_volume": infer["infer_volume"], "infer_tiles": infer["infer_tiles"],
+                               "infer_tile_batch": infer["infer_tile_batch"], "infer_mirroring": False})
+        line["infer"] = infer
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        sample_patch = (96, 96, 64)
+        sample_patch = cpu_sample_patch(args.net)
         frac = float(np.prod(sample_patch)) / float(np.prod(FULL_PATCH))
-        step = cpu_oracle_step_factory(sample_patch)
+        step = cpu_oracle_step_factory(sample_patch, args.net)
         step()
         c0 = time.perf_counter()
-        nrep = 2
+        nrep = 3
         for _ in range(nrep):
             step()
         cdt = (time.perf_counter() - c0) / nrep
         line["cpu_baseline"] = {"value": frac / cdt, "unit": "patches/s", "cores": torch.get_num_threads(),
                                 "kind": "port",
-                                "sample": "oracle fwd+loss+bwd+SGD, bs1, patch 96x96x64 (0.15 of 192x160x128), %d timed "
-                                          "steps after 1 warm-up, scaled by voxel count" % nrep}
+                                "sample": "oracle fwd+loss+bwd+SGD, bs1, patch %dx%dx%d (%.3f of 192x160x128), %d timed "
+                                          "steps after 1 warm-up, scaled by voxel count" % (sample_patch + (frac, nrep))}
     print(json.dumps(line), file=out, flush=True)
 
 

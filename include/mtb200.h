@@ -103,6 +103,10 @@ int mtb200_version(void);
 const char* mtb200_last_error(void);
 /* 1 if the tcgen05 path was compiled in and the current device is sm_100; 0 otherwise. */
 int mtb200_has_tcgen05(void);
+/* Name of the CUDA kernel family the calling thread's most recent entry point launched (e.g. "conv_line_umma",
+ * "wgrad_taps_umma", "conv_taps_ffma") -- what the dispatch inside mtb200_conv_taps / mtb200_wgrad_taps picked.
+ * Measurement only (bench.py groups its per-launch timings by it); "" before the first launch. */
+const char* mtb200_last_kernel(void);
 
 /* ---- a1/a2/a4/a5: conv -> (stats) ; replaces nn.Conv3d / nn.ConvTranspose3d calls at
  *      generic_UNet.py:57,66 (conv in ConvDropoutNormNonlin), :335-336 + :391 (tu), :350-351 + :394 (seg_outputs),
@@ -212,9 +216,17 @@ int mtb200_sw_finalize(float* acc, const float* nb, int32_t C, int64_t nvox, con
  *      MultiTalent_Trainer_DDP.py:351-353 / nnUNetTrainerV2.py:166-170 ---------------------------------------------- */
 int mtb200_sumsq(const float* g, int64_t n, double* out /* [1], caller zeroes */, void* stream);
 /* coef = min(1, max_norm/(sqrt(sumsq)*inv_scale + 1e-6)) * inv_scale; g' = g*coef + wd*p; buf = first ? g' : m*buf+g';
- * p -= lr*(g' + m*buf).  skip the whole update if sumsq is not finite (GradScaler semantics). */
+ * p -= lr*(g' + m*buf).  skip the whole update if sumsq is not finite (GradScaler.step semantics).  `dyn_scale` (device,
+ * may be NULL): the current dynamic loss scale; inv_scale is divided by dyn_scale[0] on the device (GradScaler.unscale_,
+ * MultiTalent_Trainer_DDP.py:351) so that fp16 training needs no host synchronisation. */
 int mtb200_sgd_step(float* p, const float* g, float* buf, int64_t n, const double* sumsq, float inv_scale,
-                    float max_norm, float lr, float momentum, float weight_decay, int32_t first_step, void* stream);
+                    float max_norm, float lr, float momentum, float weight_decay, int32_t first_step,
+                    const float* dyn_scale, void* stream);
+/* torch.cuda.amp.GradScaler.update (MultiTalent_Trainer_DDP.py:354) on the device: state = {scale, growth_tracker,
+ * found_inf of this step, skipped steps}; sumsq not finite -> scale *= backoff_factor, tracker = 0; else tracker += 1 and
+ * scale *= growth_factor every `growth_interval` clean steps. */
+int mtb200_loss_scale_update(const double* sumsq, float* state, float growth_factor, float backoff_factor,
+                             int32_t growth_interval, void* stream);
 
 /* ---- layout plumbing ------------------------------------------------------------------------------------------- */
 /* reference weight [Cout][Cin][kd][kh][kw] fp32 (Conv3d) or [Cin][Cout][kd][kh][kw] (ConvTranspose3d, transposed=1)

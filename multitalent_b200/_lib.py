@@ -82,6 +82,7 @@ SIGNATURES = {
     "mtb200_version": [],
     "mtb200_last_error": [],
     "mtb200_has_tcgen05": [],
+    "mtb200_last_kernel": [],
     "mtb200_conv_taps": [C.POINTER(ConvParams), _vp],
     "mtb200_wgrad_taps": [C.POINTER(WgradParams), _vp],
     "mtb200_conv_c1_fwd": [_vp, _i64, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
@@ -107,7 +108,8 @@ SIGNATURES = {
                             _i32, _i32, _i32, _vp],
     "mtb200_sw_finalize": [_vp, _vp, _i32, _i64, _vp, _vp, _vp],
     "mtb200_sumsq": [_vp, _i64, _vp, _vp],
-    "mtb200_sgd_step": [_vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _f32, _f32, _i32, _vp],
+    "mtb200_sgd_step": [_vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _vp],
+    "mtb200_loss_scale_update": [_vp, _vp, _f32, _f32, _i32, _vp],
     "mtb200_pack_weights": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "mtb200_pack_weights_batched": [_vp, _i32, _i32, _i32, _vp],
     "mtb200_unpack_wgrad": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp],
@@ -135,7 +137,7 @@ def lib():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(l, name)
             fn.argtypes = argtypes
-            fn.restype = C.c_char_p if name == "mtb200_last_error" else C.c_int
+            fn.restype = C.c_char_p if name in ("mtb200_last_error", "mtb200_last_kernel") else C.c_int
         _lib = l
     return _lib
 
@@ -159,12 +161,23 @@ class KernelProfile:
     def per_launch(self):
         """[(tag, info, ms, flops, bytes)] in launch order (tools/layer_profile.py)."""
         torch.cuda.synchronize()
-        return [(name, info, e0.elapsed_time(e1), flops, nbytes) for name, e0, e1, flops, nbytes, info in self.records]
+        return [(name, info, e0.elapsed_time(e1), flops, nbytes) for name, e0, e1, flops, nbytes, info, _k in self.records]
+
+    def per_cuda_kernel(self):
+        """{CUDA kernel family the library dispatched to (mtb200_last_kernel): {launches, ms, flops}}."""
+        torch.cuda.synchronize()
+        out = {}
+        for _name, e0, e1, flops, _nb, _info, kern in self.records:
+            d = out.setdefault(kern, {"launches": 0, "ms": 0.0, "flops": 0.0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+        return out
 
     def summary(self):
         torch.cuda.synchronize()
         out = {}
-        for name, e0, e1, flops, nbytes, _info in self.records:
+        for name, e0, e1, flops, nbytes, _info, _k in self.records:
             d = out.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
             d["launches"] += 1
             d["ms"] += e0.elapsed_time(e1)
@@ -190,7 +203,8 @@ def call(name, *args, flops=0.0, nbytes=0.0, tag=None, info=None):
         raise Mtb200Error("%s failed (%d): %s" % (name, r, msg.decode() if msg else "?"))
     if _profile is not None:
         e1.record()
-        _profile.records.append((tag or name, e0, e1, flops, nbytes, info))
+        kern = l.mtb200_last_kernel()
+        _profile.records.append((tag or name, e0, e1, flops, nbytes, info, kern.decode() if kern else name))
     launch_count += 1
     return r
 

@@ -15,7 +15,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local const char* g_last_kernel = "";
+
 int check_launch(const char* what) {
+  g_last_kernel = what;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
@@ -73,7 +76,8 @@ int sw_aggregate(const void*, int, int, int, int, int, int, int, const float*, f
 int sw_finalize(float*, const float*, int, long long, const float*, float*, cudaStream_t);
 int sumsq(const float*, long long, double*, cudaStream_t);
 int sgd_step(float*, const float*, float*, long long, const double*, float, float, float, float, float, int,
-             cudaStream_t);
+             const float*, cudaStream_t);
+int loss_scale_update(const double*, float*, float, float, int, cudaStream_t);
 int pack_weights(const float*, int, int, int, int, int, void*, int, int, int, int, int, cudaStream_t);
 int unpack_wgrad(const float*, int, int, int, int, int, int, int, int, float, int, float*, cudaStream_t);
 int pack_weights_batched(const void*, int, int, int, cudaStream_t);
@@ -98,6 +102,7 @@ extern "C" {
 int mtb200_version(void) { return MTB200_VERSION; }
 const char* mtb200_last_error(void) { return g_err; }
 int mtb200_has_tcgen05(void) { return umma_available(); }
+const char* mtb200_last_kernel(void) { return g_last_kernel; }
 
 int mtb200_conv_taps(const mtb200_conv_params* p, void* stream) {
   MTB_REQUIRE(p && p->in && p->out && p->w, "conv_taps: null pointer");
@@ -255,9 +260,17 @@ int mtb200_sumsq(const float* g, int64_t n, double* out, void* stream) {
 }
 
 int mtb200_sgd_step(float* p, const float* g, float* buf, int64_t n, const double* sumsq_, float inv_scale,
-                    float max_norm, float lr, float momentum, float weight_decay, int32_t first_step, void* stream) {
+                    float max_norm, float lr, float momentum, float weight_decay, int32_t first_step,
+                    const float* dyn_scale, void* stream) {
   MTB_REQUIRE(p && g && buf && sumsq_, "sgd_step: null pointer");
-  return sgd_step(p, g, buf, n, sumsq_, inv_scale, max_norm, lr, momentum, weight_decay, first_step, STREAM(stream));
+  return sgd_step(p, g, buf, n, sumsq_, inv_scale, max_norm, lr, momentum, weight_decay, first_step, dyn_scale,
+                  STREAM(stream));
+}
+
+int mtb200_loss_scale_update(const double* sumsq_, float* state, float growth_factor, float backoff_factor,
+                             int32_t growth_interval, void* stream) {
+  MTB_REQUIRE(sumsq_ && state && growth_interval >= 1, "loss_scale_update: bad arguments");
+  return loss_scale_update(sumsq_, state, growth_factor, backoff_factor, growth_interval, STREAM(stream));
 }
 
 int mtb200_pack_weights(const float* w, int32_t Cout, int32_t Cin, int32_t ntap, int32_t transposed, int32_t swap_io,

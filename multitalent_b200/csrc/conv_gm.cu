@@ -236,7 +236,7 @@ int conv_gm_umma(const mtb200_conv_params& p, cudaStream_t s) {
   if (p.Do * p.os[0] != p.Dof || p.Ho * p.os[1] != p.Hof || p.Wo * p.os[2] != p.Wof) return MTB200_ERR_UNSUPPORTED;
   if (p.ntaps > MTB200_MAX_TAPS) return MTB200_ERR_UNSUPPORTED;
 
-  static GmParams q;
+  static thread_local GmParams q;
   memset(&q, 0, sizeof(q));
   // groups must be exactly the residue classes of the output lattice
   bool seen[8] = {false, false, false, false, false, false, false, false};

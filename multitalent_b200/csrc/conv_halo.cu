@@ -347,7 +347,7 @@ int conv_halo_umma(const mtb200_conv_params& p, cudaStream_t s) {
   if (!spatial || !have_dz0 || p.ntaps < 9) return MTB200_ERR_UNSUPPORTED;  // 1x1x1: nothing to reuse
   if (p.Ho < 8 || p.Wo < 8) return MTB200_ERR_UNSUPPORTED;                  // tiny maps: tiles would be mostly padding
 
-  static HaloParams q;
+  static thread_local HaloParams q;
   memset(&q, 0, sizeof(q));
   q.kcw = p.Cin < 64 ? p.Cin : 64;
   q.nchunk = p.Cin / q.kcw;

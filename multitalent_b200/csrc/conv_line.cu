@@ -323,7 +323,7 @@ int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s) {
   if (p.Cout % LN_BN) return MTB200_ERR_UNSUPPORTED;
   if (p.Wo < 72 || p.Ho < 4) return MTB200_ERR_UNSUPPORTED;  // an M tile is one h-line of 128 w voxels
 
-  static LineParams q;
+  static thread_local LineParams q;
   memset(&q, 0, sizeof(q));
   // groups (dz, dx), each with all three dy taps
   int gid[3][3];

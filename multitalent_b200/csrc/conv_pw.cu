@@ -246,7 +246,7 @@ int conv_pw_umma(const mtb200_conv_params& p, cudaStream_t s) {
   if (M >= (1LL << 31) - 256) return MTB200_ERR_UNSUPPORTED;
   if (p.stats && nvox % 128) return MTB200_ERR_UNSUPPORTED;  // a tile must not straddle two samples
 
-  static PwParams q;
+  static thread_local PwParams q;
   memset(&q, 0, sizeof(q));
   q.KC = p.Cin <= 16 ? 16 : (p.Cin <= 32 ? 32 : 64);
   q.nkc = (p.Cin + q.KC - 1) / q.KC;

@@ -377,7 +377,7 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
   }
   EncodeTiledFn enc = get_encode_fn();
 
-  static UmmaConvParams q;  // large: keep off the stack (host calls are serialised by the GIL / one thread per process)
+  static thread_local UmmaConvParams q;  // large: keep off the stack; one instance per host thread (re-entrant per thread)
   memset(&q, 0, sizeof(q));
   q.KC = (p.Cin % 64 == 0) ? 64 : ((p.Cin % 32 == 0) ? 32 : 16);
   q.nkc = p.Cin / q.KC;
@@ -733,7 +733,7 @@ int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   EncodeTiledFn enc = get_encode_fn();
   const CUtensorMapDataType dt = p.dtype == MTB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 
-  static UmmaWgradParams q;
+  static thread_local UmmaWgradParams q;
   memset(&q, 0, sizeof(q));
   q.dw = p.dw;
   q.B = p.B; q.Cin = p.Cin; q.Cout = p.Cout;
@@ -816,7 +816,7 @@ int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   cudaError_t ce = cudaFuncSetAttribute(wgrad_taps_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (ce != cudaSuccess) { set_error("wgrad_taps(umma): cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return MTB200_ERR_CUDA; }
 
-  static CUtensorMap group_maps[MTB200_MAX_GROUPS];
+  static thread_local CUtensorMap group_maps[MTB200_MAX_GROUPS];
   int group_off[MTB200_MAX_GROUPS][3];
   if (merge) {
     q.merge_ng = merge_per;

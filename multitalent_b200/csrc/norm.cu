@@ -264,9 +264,12 @@ int in_bwd_reduce(const void* dact, int d_ldc, int d_coff, const void* y, int y_
 }
 
 // ---- backward pass 2 ------------------------------------------------------------------------------------------------
+// The engine runs this pass IN PLACE (dy == dact): those two pointers are therefore not __restrict__ and `dact` is read
+// with coherent loads (ld.global, not the read-only .nc path).  Each thread reads its own element before writing it; the
+// clamped tail re-reads are discarded.
 template <typename T, int NU>
-__global__ void __launch_bounds__(NT) in_bwd_apply_kernel(const T* __restrict__ dact, int d_ldc, int d_coff,
-                                                          const T* __restrict__ y, int y_ldc, int y_coff, T* __restrict__ dy,
+__global__ void __launch_bounds__(NT) in_bwd_apply_kernel(const T* dact, int d_ldc, int d_coff,
+                                                          const T* __restrict__ y, int y_ldc, int y_coff, T* dy,
                                                           int dy_ldc, int dy_coff, long long nvox, int B, int C,
                                                           const float4* __restrict__ xform,
                                                           const float2* __restrict__ meanrstd,
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(NT) in_bwd_apply_kernel(const T* __restrict__ 
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
       const long long vv = min(base + sp.vlane + (long long)u * sp.vstride, nvox - 1);
-      d[u].load(dbase + vv * d_ldc);
+      d[u].loadc(dbase + vv * d_ldc);  // `dy` may alias `dact` (in-place pass): coherent load, no __restrict__
       x[u].load(ybase + vv * y_ldc);
     }
 #pragma unroll
@@ -334,9 +337,9 @@ __global__ void __launch_bounds__(NT) in_bwd_apply_kernel(const T* __restrict__ 
 // streams with one write stream and needs the extra memory-level parallelism to reach the HBM roofline.
 //   dv = dact * lrelu'(sc * y + sh),   dy = k1 * (dv - m1 - xhat * m2) = k1 * dv + c1 * y + c0
 template <typename T, int NU>
-__global__ void __launch_bounds__(NT, 3) in_bwd_apply_smem_kernel(const T* __restrict__ dact, int d_ldc, int d_coff,
+__global__ void __launch_bounds__(NT, 3) in_bwd_apply_smem_kernel(const T* dact, int d_ldc, int d_coff,
                                                                   const T* __restrict__ y, int y_ldc, int y_coff,
-                                                                  T* __restrict__ dy, int dy_ldc, int dy_coff, long long nvox,
+                                                                  T* dy, int dy_ldc, int dy_coff, long long nvox,
                                                                   int B, int C, const float4* __restrict__ xform,
                                                                   const float2* __restrict__ meanrstd,
                                                                   const float* __restrict__ gamma,
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(NT, 3) in_bwd_apply_smem_kernel(const T* __res
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
       const long long vv = min(base + sp.vlane + (long long)u * sp.vstride, nvox - 1);
-      d[u].load(dbase + vv * d_ldc);
+      d[u].loadc(dbase + vv * d_ldc);  // `dy` may alias `dact` (in-place pass): coherent load, no __restrict__
       x[u].load(ybase + vv * y_ldc);
     }
     int cg = sp.cg;

@@ -36,9 +36,10 @@ int sumsq(const float* g, long long n, double* out, cudaStream_t s) {
 // ---- clip + SGD(nesterov) ------------------------------------------------------------------------------------------
 __global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n,
                                 const double* __restrict__ sumsq, float inv_scale, float max_norm, float lr,
-                                float momentum, float wd, int first) {
+                                float momentum, float wd, int first, const float* __restrict__ dyn_scale) {
   const double ss = *sumsq;
   if (!isfinite(ss)) return;  // GradScaler: skip the step on inf/nan gradients
+  if (dyn_scale) inv_scale /= dyn_scale[0];  // GradScaler.unscale_: the loss was multiplied by the current scale
   const float total_norm = (float)sqrt(ss) * inv_scale;
   float clip = max_norm / (total_norm + 1e-6f);
   clip = clip > 1.f ? 1.f : clip;
@@ -53,10 +54,35 @@ __global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__
 }
 
 int sgd_step(float* p, const float* g, float* buf, long long n, const double* sumsq_, float inv_scale, float max_norm,
-             float lr, float momentum, float wd, int first, cudaStream_t s) {
+             float lr, float momentum, float wd, int first, const float* dyn_scale, cudaStream_t s) {
   const int blocks = (int)max(1LL, min((long long)num_sms() * 8, (n + 255) / 256));
-  sgd_step_kernel<<<blocks, 256, 0, s>>>(p, g, buf, n, sumsq_, inv_scale, max_norm, lr, momentum, wd, first);
+  sgd_step_kernel<<<blocks, 256, 0, s>>>(p, g, buf, n, sumsq_, inv_scale, max_norm, lr, momentum, wd, first, dyn_scale);
   return check_launch("sgd_step");
+}
+
+// ---- GradScaler.update on the device ----------------------------------------------------------------------------------
+// state = {scale, growth_tracker, found_inf of this step, number of skipped steps}
+__global__ void loss_scale_update_kernel(const double* __restrict__ sumsq, float* __restrict__ state, float growth,
+                                         float backoff, int interval) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const bool bad = !isfinite(*sumsq);
+  float scale = state[0], tracker = state[1];
+  if (bad) {
+    scale *= backoff;
+    tracker = 0.f;
+    state[3] += 1.f;
+  } else {
+    tracker += 1.f;
+    if (tracker >= (float)interval) { scale *= growth; tracker = 0.f; }
+  }
+  state[0] = scale;
+  state[1] = tracker;
+  state[2] = bad ? 1.f : 0.f;
+}
+
+int loss_scale_update(const double* sumsq_, float* state, float growth, float backoff, int interval, cudaStream_t s) {
+  loss_scale_update_kernel<<<1, 32, 0, s>>>(sumsq_, state, growth, backoff, interval);
+  return check_launch("loss_scale_update");
 }
 
 // ---- weight packing ---------------------------------------------------------------------------------------------------

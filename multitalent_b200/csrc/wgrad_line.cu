@@ -232,7 +232,7 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   for (int t = 0; t < p.ntaps; ++t) all_dy0 = all_dy0 && p.tap_off[t][1] == 0;
   if (p.ntaps < 9 && !(p.ntaps == 1 && all_dy0)) return MTB200_ERR_UNSUPPORTED;
 
-  static WgradLineParams q;
+  static thread_local WgradLineParams q;
   memset(&q, 0, sizeof(q));
   for (int i = 0; i < 27; ++i) q.lut[i] = -1;
   int dzmin = 1, dzmax = -1;

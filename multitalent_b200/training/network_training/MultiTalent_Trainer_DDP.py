@@ -45,10 +45,9 @@ class FlatArena:
     def __init__(self, module: nn.Module):
         params = [p for p in module.parameters()]
 
-        def slot(p):
-            # 1-D parameters (bias, norm weight / bias) get a slot padded to the kernels' channel padding: the engine
-            # views them in place (engine._padded) and accumulates their gradients in place (engine.direct_grad)
-            return pad_channels(p.numel()) if p.dim() == 1 else (p.numel() + 3) // 4 * 4
+        # 1-D parameters (bias, norm weight / bias) get a slot padded to the kernels' channel padding: the engine
+        # views them in place (engine._padded) and accumulates their gradients in place (engine.direct_grad)
+        slot = self._slot
         n = sum(slot(p) for p in params)
         dev = params[0].device
         self.params = params
@@ -72,15 +71,84 @@ class FlatArena:
     def zero_grad(self):
         self.grad.zero_()
 
-    def step(self, lr, momentum, weight_decay, max_norm, inv_scale=1.0):
+    def step(self, lr, momentum, weight_decay, max_norm, inv_scale=1.0, scaler=None):
+        """clip_grad_norm_(max_norm) + SGD(nesterov) over the arena.  Gradients are multiplied by `inv_scale` (1 / world
+        size of the summed all-reduce) and, with a `DeviceGradScaler`, by 1 / its current loss scale (read on the
+        device); a non-finite gradient norm skips the update (GradScaler.step semantics) and the scaler then backs off."""
         st = L.stream_ptr()
         self.sumsq.zero_()
         L.call("mtb200_sumsq", L.ptr(self.grad), self.n, L.ptr(self.sumsq), st)
         L.call("mtb200_sgd_step", L.ptr(self.flat), L.ptr(self.grad), L.ptr(self.mom), self.n, L.ptr(self.sumsq),
-               float(inv_scale), float(max_norm), float(lr), float(momentum), float(weight_decay), int(self.first), st)
+               float(inv_scale), float(max_norm), float(lr), float(momentum), float(weight_decay), int(self.first),
+               L.ptr(scaler.state) if scaler is not None else None, st)
+        if scaler is not None:
+            scaler.update(self.sumsq)
         self.first = False
         # the kernel updated the arena behind torch's version counters: invalidate the packed-weight caches
         bump_weights_epoch()
+
+    # ---- torch.optim.SGD-format state (checkpoints interchangeable with the reference, network_trainer.py:256-286) ---
+    def sgd_state_dict(self, lr, momentum, weight_decay):
+        opt = torch.optim.SGD(self.params, lr, weight_decay=weight_decay, momentum=momentum, nesterov=True)
+        sd = opt.state_dict()
+        if not self.first:
+            off = 0
+            for i, p in enumerate(self.params):
+                k = p.numel()
+                sd['state'][i] = {'momentum_buffer': self.mom[off:off + k].view_as(p.data).detach().cpu().clone()}
+                off += self._slot(p)
+        return sd
+
+    def load_sgd_state_dict(self, sd):
+        state = sd.get('state', {})
+        self.mom.zero_()
+        off, any_buf = 0, False
+        for i, p in enumerate(self.params):
+            k = p.numel()
+            st = state.get(i, state.get(str(i)))
+            buf = st.get('momentum_buffer') if st else None
+            if buf is not None:
+                self.mom[off:off + k].copy_(buf.reshape(-1).to(self.mom.device, torch.float32))
+                any_buf = True
+            off += self._slot(p)
+        self.first = not any_buf
+
+    @staticmethod
+    def _slot(p):
+        return pad_channels(p.numel()) if p.dim() == 1 else (p.numel() + 3) // 4 * 4
+
+
+class DeviceGradScaler:
+    """torch.cuda.amp.GradScaler semantics (MultiTalent_Trainer_DDP.py:349-354: scale -> backward -> unscale_ -> clip ->
+    step -> update) with the state on the device, so the arena step needs no host synchronisation: `state` = fp32
+    {scale, growth_tracker, found_inf of the last step, skipped steps}.  `scale(l)` multiplies by the device scalar; the
+    SGD kernel unscales by it and skips the update when the gradient norm is not finite; `update` = GradScaler.update
+    (backoff x0.5 on inf/nan, growth x2 after `growth_interval` clean steps).  `state_dict` uses GradScaler's keys."""
+
+    def __init__(self, device, init_scale=2.0 ** 16, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000):
+        self.growth_factor, self.backoff_factor, self.growth_interval = growth_factor, backoff_factor, growth_interval
+        self.state = torch.tensor([init_scale, 0.0, 0.0, 0.0], dtype=torch.float32, device=device)
+
+    def scale(self, loss):
+        return loss * self.state[0]
+
+    def update(self, sumsq):
+        L.call("mtb200_loss_scale_update", L.ptr(sumsq), L.ptr(self.state), float(self.growth_factor),
+               float(self.backoff_factor), int(self.growth_interval), L.stream_ptr())
+
+    def get_scale(self):
+        return float(self.state[0].item())
+
+    def state_dict(self):
+        st = self.state.cpu()
+        return {"scale": float(st[0]), "growth_factor": self.growth_factor, "backoff_factor": self.backoff_factor,
+                "growth_interval": self.growth_interval, "_growth_tracker": int(st[1])}
+
+    def load_state_dict(self, sd):
+        self.growth_factor, self.backoff_factor = float(sd["growth_factor"]), float(sd["backoff_factor"])
+        self.growth_interval = int(sd["growth_interval"])
+        self.state[0] = float(sd["scale"])
+        self.state[1] = float(sd.get("_growth_tracker", 0))
 
 
 class MultiTalent_trainer_ddp(OnlineEvaluationMixin):
@@ -89,7 +157,8 @@ class MultiTalent_trainer_ddp(OnlineEvaluationMixin):
                  native_dtype=None, flat_optimizer=True, init_distributed=True):
         """Positional signature of MultiTalent_Trainer_DDP.py:31-32 (the tuple is pickled and replayed by
         model_restore.py:90).  Keyword-only extensions: `native_dtype` (torch.float32 | bfloat16 | float16; default
-        fp16 if `fp16` else fp32), `flat_optimizer`, `init_distributed`."""
+        fp16 if `fp16` else fp32), `flat_optimizer`, `init_distributed`.  float16 runs as the reference runs it
+        (MT:349-354): dynamic loss scaling with GradScaler semantics (`amp_grad_scaler`); bfloat16 / float32 need none."""
         self.init_args = (plans_file, fold, local_rank, output_folder, dataset_directory, batch_dice, stage, unpack_data,
                           deterministic, distribute_batch_size, fp16)
         self.plans_file, self.fold, self.local_rank = plans_file, fold, local_rank
@@ -107,7 +176,10 @@ class MultiTalent_trainer_ddp(OnlineEvaluationMixin):
         self.plans = None
         self.network = self.optimizer = self.arena = self.amp_grad_scaler = None
         self.ds_loss_weights = None
-        self.loss_scale = 1.0
+        self.loss_scale = 1.0  # optional STATIC factor on top (experiments); the dynamic scaler is `amp_grad_scaler`
+        # network_trainer.py:71-93 bookkeeping that the checkpoint format carries ('plot_stuff', 'best_stuff')
+        self.all_tr_losses, self.all_val_losses, self.all_val_losses_tr_mode, self.all_val_eval_metrics = [], [], [], []
+        self.best_epoch_based_on_MA_tr_loss = self.best_MA_tr_loss_for_patience = self.best_val_eval_criterion_MA = None
         np.random.seed(local_rank)
         torch.manual_seed(local_rank)
         if torch.cuda.is_available():
@@ -193,6 +265,20 @@ class MultiTalent_trainer_ddp(OnlineEvaluationMixin):
                                              weight_decay=self.weight_decay, momentum=0.99, nesterov=True)
         self.lr = self.initial_lr
         self.lr_scheduler = None
+        self._maybe_init_amp()
+
+    def _maybe_init_amp(self):
+        """network_trainer.py:400-402: a GradScaler whenever the arithmetic is fp16."""
+        if self.amp_grad_scaler is None and self.native_dtype == torch.float16 and torch.cuda.is_available():
+            if self.arena is not None:
+                self.amp_grad_scaler = DeviceGradScaler(self.arena.flat.device)
+            else:
+                self.amp_grad_scaler = torch.amp.GradScaler("cuda")
+
+    def loss_scaling_description(self):
+        if self.amp_grad_scaler is None:
+            return "none" if self.loss_scale == 1.0 else "static x%g" % self.loss_scale
+        return "dynamic (GradScaler semantics: init 65536, x0.5 on inf/nan, x2 after 2000 clean steps)"
 
     def _wrap_ddp(self):
         self.world_size = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
@@ -295,23 +381,31 @@ class MultiTalent_trainer_ddp(OnlineEvaluationMixin):
             if keep_output:  # run_online_evaluation reads the highest-resolution logits after the step (MT:367-368)
                 self._last_output = tuple(o.detach() for o in output)
             if do_backprop:
-                (l * self.loss_scale if self.loss_scale != 1.0 else l).backward()
+                ls = l * self.loss_scale if self.loss_scale != 1.0 else l
+                if self.amp_grad_scaler is not None:
+                    ls = self.amp_grad_scaler.scale(ls)        # MT:350
+                ls.backward()
         if do_backprop:
             if self.arena is not None:
                 if self.world_size > 1:
                     dist.all_reduce(self.arena.grad)
-                    inv = 1.0 / (self.loss_scale * self.world_size)
-                else:
-                    inv = 1.0 / self.loss_scale
-                self.arena.step(self.lr, 0.99, self.weight_decay, 12.0, inv)
+                inv = 1.0 / (self.loss_scale * self.world_size)
+                self.arena.step(self.lr, 0.99, self.weight_decay, 12.0, inv, scaler=self.amp_grad_scaler)
             else:
-                if self.world_size > 1:
-                    for p in self.network.parameters():
-                        if p.grad is not None:
+                params = [p for p in self.network.parameters() if p.grad is not None]
+                if self.world_size > 1 or self.loss_scale != 1.0:
+                    for p in params:
+                        if self.world_size > 1:
                             dist.all_reduce(p.grad)
-                            p.grad.div_(self.world_size)
-                torch.nn.utils.clip_grad_norm_(self.network.parameters(), 12)
-                self.optimizer.step()
+                        p.grad.div_(self.world_size * self.loss_scale)
+                if self.amp_grad_scaler is not None:           # MT:351-354
+                    self.amp_grad_scaler.unscale_(self.optimizer)
+                    torch.nn.utils.clip_grad_norm_(self.network.parameters(), 12)
+                    self.amp_grad_scaler.step(self.optimizer)
+                    self.amp_grad_scaler.update()
+                else:
+                    torch.nn.utils.clip_grad_norm_(self.network.parameters(), 12)
+                    self.optimizer.step()
         return l, ce, dc
 
     def predict_preprocessed_data_return_seg_and_softmax(self, data, do_mirroring=True, mirror_axes=None,
@@ -340,29 +434,81 @@ class MultiTalent_trainer_ddp(OnlineEvaluationMixin):
 
     # ---- checkpoints (network_trainer.py:256-286, nnUNetTrainerV2_DDP.py:636-669: key names are the contract) -------
     def save_checkpoint(self, fname, save_optimizer=True):
+        """network_trainer.py:256-286: the reference's key set, so that either side can load the other's file.  In arena
+        mode the optimizer state is written in torch.optim.SGD's format (momentum buffers per parameter)."""
         sd = {k: v.detach().cpu().clone() for k, v in self.network.state_dict().items()}
-        state = {'epoch': self.epoch + 1, 'state_dict': sd}
+        opt_sd = None
         if save_optimizer and self.arena is not None:
-            state['optimizer_state_dict'] = {'flat_momentum': self.arena.mom.cpu(), 'first': self.arena.first}
+            opt_sd = self.arena.sgd_state_dict(self.lr, 0.99, self.weight_decay)
         elif save_optimizer and self.optimizer is not None:
-            state['optimizer_state_dict'] = self.optimizer.state_dict()
+            opt_sd = self.optimizer.state_dict()
+        state = {'epoch': self.epoch + 1, 'state_dict': sd, 'optimizer_state_dict': opt_sd,
+                 'lr_scheduler_state_dict': None,
+                 'plot_stuff': (self.all_tr_losses, self.all_val_losses, self.all_val_losses_tr_mode,
+                                self.all_val_eval_metrics),
+                 'best_stuff': (self.best_epoch_based_on_MA_tr_loss, self.best_MA_tr_loss_for_patience,
+                                self.best_val_eval_criterion_MA)}
+        if self.amp_grad_scaler is not None:
+            state['amp_grad_scaler'] = self.amp_grad_scaler.state_dict()
         torch.save(state, fname)
         with open(fname + ".pkl", 'wb') as f:
             pickle.dump({'init': self.init_args, 'name': self.__class__.__name__, 'class': str(self.__class__),
                          'plans': self.plans}, f)
 
+    def load_checkpoint(self, fname, train=True):
+        """network_trainer.py:337-345."""
+        if not self.was_initialized:
+            self.initialize(train)
+        self.load_checkpoint_ram(torch.load(fname, map_location=torch.device('cpu'), weights_only=False), train)
+
     def load_checkpoint_ram(self, checkpoint, train=True):
+        """nnUNetTrainerV2_DDP.py:636-697: `module.` prefix heuristic (+ the legacy resenc head remap, :656-659),
+        GradScaler state, optimizer state (momentum), bookkeeping lists, epoch correction; then the poly learning rate
+        of the restored epoch (nnUNetTrainerV2.run_training -> maybe_update_lr(self.epoch))."""
         if not self.was_initialized:
             self.initialize(train)
         cur = self.network.state_dict()
+        legacy = {'module.decoder.segmentation_output.weight': 'decoder.deep_supervision_outputs.4.weight',
+                  'module.decoder.segmentation_output.bias': 'decoder.deep_supervision_outputs.4.bias'}
         new = {}
         for k, v in checkpoint['state_dict'].items():
-            key = k[7:] if (k not in cur and k.startswith('module.')) else k
+            key = k
+            if key not in cur:
+                key = legacy.get(key, key[7:] if key.startswith('module.') else key)
             new[key] = v
+        missing = [k for k in cur if k not in new]
+        unexpected = [k for k in new if k not in cur]
+        if missing or unexpected:  # nn.Module.load_state_dict(strict=True) semantics
+            raise RuntimeError("Error(s) in loading state_dict: missing keys %s, unexpected keys %s" % (missing, unexpected))
         with torch.no_grad():
             for k, v in new.items():
                 cur[k].copy_(v)  # in place: parameters may be views of the flat arena
+        bump_weights_epoch()
+        if self.amp_grad_scaler is not None and train and checkpoint.get('amp_grad_scaler') is not None:
+            self.amp_grad_scaler.load_state_dict(checkpoint['amp_grad_scaler'])
         self.epoch = checkpoint.get('epoch', 0)
+        if train:
+            opt_sd = checkpoint.get('optimizer_state_dict')
+            if opt_sd is not None:
+                if self.arena is not None:
+                    self.arena.load_sgd_state_dict(opt_sd)
+                elif self.optimizer is not None:
+                    self.optimizer.load_state_dict(opt_sd)
+        if 'plot_stuff' in checkpoint:
+            (self.all_tr_losses, self.all_val_losses, self.all_val_losses_tr_mode,
+             self.all_val_eval_metrics) = (list(x) for x in checkpoint['plot_stuff'])
+            # :683-693 (old off-by-one of finished runs); a checkpoint without a loss history keeps its epoch
+            if self.all_tr_losses and self.epoch != len(self.all_tr_losses):
+                self.epoch = len(self.all_tr_losses)
+                self.all_tr_losses = self.all_tr_losses[:self.epoch]
+                self.all_val_losses = self.all_val_losses[:self.epoch]
+                self.all_val_losses_tr_mode = self.all_val_losses_tr_mode[:self.epoch]
+                self.all_val_eval_metrics = self.all_val_eval_metrics[:self.epoch]
+        if 'best_stuff' in checkpoint:
+            (self.best_epoch_based_on_MA_tr_loss, self.best_MA_tr_loss_for_patience,
+             self.best_val_eval_criterion_MA) = checkpoint['best_stuff']
+        if train:
+            self.maybe_update_lr(self.epoch)
 
 
 class MultiTalent_trainer_ddp_2000ep(MultiTalent_trainer_ddp):

@@ -12,7 +12,11 @@ softmax Dice + CE with deep supervision (nnUNetTrainer.py:108, nnUNetTrainerV2.p
 reference computes every gradient during the heads-only phase and lets the optimizer ignore the trunk's; here
 `freeze_trunk_during_head_warmup` (default on) marks the trunk parameters as not requiring a gradient for that phase, which
 puts `Generic_UNet` on its frozen-trunk path (backward = the heads' weight gradients only).  The heads receive identical
-gradients either way (`tests/test_gpu_warmup_trainer.py`).
+gradients either way BEFORE clipping (`tests/test_gpu_warmup_trainer.py`).  Known deviation: the reference's
+`clip_grad_norm_(network.parameters(), 12)` also counts the (unused) trunk gradients, so whenever the full-network
+gradient norm exceeds 12 its head gradients are scaled by a smaller coefficient than here; reproducing that coefficient
+needs the trunk gradients, i.e. the full backward -- pass `freeze_trunk_during_head_warmup=False` for exact reference
+behaviour.
 
 Data loading, augmentation, validation and checkpoint files stay in the reference."""
 import numpy as np
@@ -147,6 +151,10 @@ class nnUNetTrainerV2_warmupsegheads(object):
                                              weight_decay=self.weight_decay, momentum=0.99, nesterov=True)
         self.seg_heads_only = seg_heads_only
         self.lr_scheduler = None
+        # network_trainer.py:400-402: GradScaler whenever the arithmetic is fp16 (dynamic loss scaling)
+        if getattr(self, "amp_grad_scaler", None) is None:
+            self.amp_grad_scaler = (torch.amp.GradScaler("cuda")
+                                    if self.native_dtype == torch.float16 and torch.cuda.is_available() else None)
 
     def maybe_update_lr(self, epoch=None):
         """:87-112 (the reference's training loop calls it without an argument: `self.epoch` decides)."""
@@ -158,13 +166,15 @@ class nnUNetTrainerV2_warmupsegheads(object):
         return lr
 
     def on_epoch_end(self):
-        """:114-120 -- switch to whole-network SGD when the head warm-up is over, then the epoch bookkeeping of
-        network_trainer.on_epoch_end (epoch counter + learning rate for the next epoch)."""
+        """:114-120 -- switch to whole-network SGD when the head warm-up is over, then network_trainer.on_epoch_end
+        (network_trainer.py:603-616): `maybe_update_lr()` runs with `self.epoch` still naming the epoch that just ended,
+        and only afterwards does the training loop increment the counter (:482-490).  So epoch e >= 1 trains at
+        warmup_lr(e - 1) and epoch `warmup_duration` is still a heads-only AdamW epoch -- exactly the reference's
+        sequence (tests/test_warmup_trainer_host.py drives this loop against the reference's)."""
         if self.epoch == self.warmup_duration:
             self.initialize_optimizer_and_scheduler(seg_heads_only=False)
+        self.maybe_update_lr()
         self.epoch += 1
-        if self.epoch < self.max_num_epochs:
-            self.maybe_update_lr()
         return self.epoch < self.max_num_epochs
 
     # ---- the hot path ------------------------------------------------------------------------------------------------
@@ -182,9 +192,17 @@ class nnUNetTrainerV2_warmupsegheads(object):
             output = self.network(data)
             l = self.loss(output, target)
         if do_backprop:
-            l.backward()
-            torch.nn.utils.clip_grad_norm_([p for p in self.network.parameters() if p.grad is not None], 12)
-            self.optimizer.step()
+            params = [p for p in self.network.parameters() if p.requires_grad]
+            if self.amp_grad_scaler is not None:   # nnUNetTrainerV2.py:246-252
+                self.amp_grad_scaler.scale(l).backward()
+                self.amp_grad_scaler.unscale_(self.optimizer)
+                torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 12)
+                self.amp_grad_scaler.step(self.optimizer)
+                self.amp_grad_scaler.update()
+            else:
+                l.backward()
+                torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 12)
+                self.optimizer.step()
         return l.detach().cpu().numpy()
 
     def predict_preprocessed_data_return_seg_and_softmax(self, data, do_mirroring=True, mirror_axes=None,

@@ -64,16 +64,26 @@ def test_native_arm_refuses_to_run_without_gpu():
     assert "no CPU fallback" in r.stderr
 
 
-def test_roofline_kernel_naming_follows_the_dispatch_rules():
+def test_cpu_arm_does_not_import_the_product():
+    """The CPU arm (`--impl reference`, `cpu_baseline`) is the oracle port only: building its step must not pull the
+    product package in."""
+    code = ("import sys; sys.path.insert(0, %r); import importlib.util as u; "
+            "spec = u.spec_from_file_location('b', %r); m = u.module_from_spec(spec); sys.argv = ['bench.py']; "
+            "spec.loader.exec_module(m); step = m.cpu_oracle_step_factory((32, 64, 64)); l = step(); "
+            "assert l == l; assert not any(k.startswith('multitalent_b200') for k in sys.modules), "
+            "[k for k in sys.modules if k.startswith('multitalent_b200')]" % (ROOT, os.path.join(ROOT, "bench.py")))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_resenc_cpu_arm_runs():
     bench = _load_bench()
-    name = bench.cuda_kernel_name
-    unit = "(1, 1, 1), (1, 1, 1))"
-    assert name("conv_wgrad", "(32, 32, (192, 160, 128), 27, " + unit) == "wgrad_line_umma_kernel"
-    assert name("conv_wgrad", "(128, 128, (48, 40, 32), 27, " + unit) == "wgrad_taps_umma_kernel"       # W < 48
-    assert name("conv_fwd", "(64, 32, (192, 160, 128), 27, " + unit) == "conv_line_umma_kernel"
-    assert name("conv_fwd", "(64, 64, (96, 80, 64), 27, " + unit) == "conv_taps_umma_kernel"           # W < 72
-    assert name("conv_dgrad", "(48, 32, (192, 160, 128), 1, " + unit) == "conv_pw_umma_kernel"
-    assert name("conv_fwd", "(1, 32, (192, 160, 128), 27, " + unit) == "conv_c1_fwd_kernel"
-    assert name("conv_dgrad", "(64, 32, (96, 80, 64), 27, (1, 1, 1), (2, 2, 2))") == "conv_gm_umma_kernel"
-    assert name("conv_fwd", "(32, 64, (96, 80, 64), 27, (2, 2, 2), (1, 1, 1))") == "conv_taps_umma_kernel"
-    assert name("mtb200_norm_act", "None") is None
+    step = bench.cpu_oracle_step_factory((32, 64, 64), "resenc")
+    l0 = step()
+    assert l0 == l0 and abs(l0) < 1e6
+
+
+def test_last_kernel_symbol_reports_the_dispatch():
+    from multitalent_b200 import _lib as L
+    k = L.lib().mtb200_last_kernel()
+    assert isinstance(k, bytes)

@@ -1,0 +1,213 @@
+"""T1 parity against the LIBRARY on the same GPU (SURVEY.md 8c last row): the reference's own
+ops (cuDNN / ATen through torch) run the oracle port on CUDA tensors -- `oracle/gpu_reference.py` -- in fp32 (TF32 off)
+and under `torch.autocast(bfloat16)`, and the tcgen05 path is judged against them:
+
+  * per layer, at the REAL benchmark shapes (192x160x128 and below, the production kernel dispatch `impl = 0`): forward,
+    data gradient and weight gradient of every convolution family against cuDNN fp32 on the same 16-bit-rounded operands
+    -- 2.5 ulp of the 16-bit storage type relative to max|ref| for stored tensors, 2e-3 of max|ref| for the fp32 weight
+    gradients (summation order over up to 3.9 M voxels);
+  * whole network, full 192x160x128 patch: max|logit - fp32 reference| within the reference's own autocast-vs-fp32
+    envelope measured in the same run, loss within 1 %, Dice agreement of the thresholded sigmoid masks, gradient cosine.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+FULL_PATCH = (192, 160, 128)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _require_tcgen05():
+    from multitalent_b200 import _lib as L
+    if L.lib().mtb200_has_tcgen05() != 1:
+        pytest.skip("device has no tcgen05 (not sm_100)")
+
+
+def _rel_err(got, ref):
+    return float((got.float() - ref.float()).abs().max()) / max(float(ref.float().abs().max()), 1e-12)
+
+
+ULP = {torch.bfloat16: 2.0 ** -8, torch.float16: 2.0 ** -11}
+
+# kind, cin, cout, kernel, stride, input dims (B, D, H, W), split -- the layer shapes of the benchmark network
+#  at batch 1; `split` = first half of a concatenated decoder input
+LAYERS = [
+    ("conv", 30, 30, (3, 3, 3), (1, 1, 1), (1, 192, 160, 128), 0),    # conv_line / wgrad_line, Cin_p 32
+    ("conv", 60, 30, (3, 3, 3), (1, 1, 1), (1, 192, 160, 128), 30),   # decoder concat input, Cin_p 64
+    ("conv", 1, 30, (3, 3, 3), (1, 1, 1), (1, 192, 160, 128), 0),     # first layer (K = taps kernels)
+    ("conv", 30, 47, (1, 1, 1), (1, 1, 1), (1, 192, 160, 128), 0),    # head: pointwise kernel, line wgrad
+    ("conv", 30, 60, (3, 3, 3), (2, 2, 2), (1, 192, 160, 128), 0),    # strided: per-tap fwd, group-merged dgrad
+    ("convT", 60, 30, (2, 2, 2), (2, 2, 2), (1, 96, 80, 64), 0),      # ConvTranspose3d: group-merged fwd
+    ("conv", 60, 60, (3, 3, 3), (1, 1, 1), (1, 96, 80, 64), 0),       # level 1
+    ("conv", 120, 60, (3, 3, 3), (1, 1, 1), (1, 96, 80, 64), 60),
+    ("conv", 60, 120, (3, 3, 3), (2, 2, 2), (1, 96, 80, 64), 0),
+    ("convT", 120, 60, (2, 2, 2), (2, 2, 2), (1, 48, 40, 32), 0),
+    ("conv", 120, 120, (3, 3, 3), (1, 1, 1), (2, 48, 40, 32), 0),     # level 2
+    ("conv", 240, 120, (3, 3, 3), (1, 1, 1), (1, 48, 40, 32), 120),
+    ("conv", 240, 240, (3, 3, 3), (1, 1, 1), (2, 24, 20, 16), 0),     # level 3
+    ("conv", 320, 320, (3, 3, 3), (1, 2, 2), (2, 12, 10, 8), 0),      # bottleneck stride (1, 2, 2)
+    ("convT", 320, 320, (1, 2, 2), (1, 2, 2), (2, 12, 5, 4), 0),
+]
+
+
+@pytest.mark.parametrize("kind,cin,cout,kernel,stride,dims,split", LAYERS)
+def test_layer_at_benchmark_shape_vs_cudnn(kind, cin, cout, kernel, stride, dims, split):
+    _require_tcgen05()
+    from multitalent_b200.engine import ConvOp, Engine, Feat, Tape
+    from oracle.gpu_reference import conv_reference, conv_reference_grads
+    dtype = torch.bfloat16
+    torch.manual_seed(11)
+    B, D, H, W = dims
+    transposed = kind == "convT"
+    if transposed:
+        mod = nn.ConvTranspose3d(cin, cout, kernel, stride, bias=False).to(DEV)
+    else:
+        mod = nn.Conv3d(cin, cout, kernel, stride, [(k - 1) // 2 for k in kernel], bias=False).to(DEV)
+    op = ConvOp(mod.weight, None, kernel, stride, transposed=transposed, split=split)
+    eng = Engine(dtype, 0)  # the production dispatch
+    # logical input, written into the (possibly split) padded NDHWC layout the way the network's buffers hold it
+    x = torch.randn(B, cin, D, H, W, device=DEV).to(dtype)
+    xb = torch.zeros(B, D, H, W, op.Cin_p, device=DEV, dtype=dtype)
+    xl = x.permute(0, 2, 3, 4, 1)
+    if split:
+        xb[..., :split] = xl[..., :split]
+        xb[..., op.split_p:op.split_p + cin - split] = xl[..., split:]
+    else:
+        xb[..., :cin] = xl
+    c1 = eng.use_c1(op)
+    xf = eng.input_feat(x.float(), compact=True) if c1 else Feat(xb, 0, cin, op.Cin_p)
+    tape = Tape()
+    y = eng.conv_plain(tape, op, xf, need_input_grad=not c1)
+    pad = [(k - 1) // 2 for k in kernel]
+    ref = conv_reference(x, mod.weight.to(dtype), stride, pad, transposed)
+    got = y.buf[..., :cout].permute(0, 4, 1, 2, 3)
+    e_f = _rel_err(got, ref)
+    assert e_f <= 2.5 * ULP[dtype], "forward: %.3e of max|ref|" % e_f
+    del got
+    gy = torch.randn_like(ref).to(dtype)
+    eng.seed_grad(tape, y, gy.float())
+    eng.run_backward(tape)
+    torch.cuda.synchronize()
+    rgx, rgw = conv_reference_grads(x, mod.weight.to(dtype), gy, stride, pad, transposed)
+    gw = tape.param_grads[id(mod.weight)]
+    e_w = _rel_err(gw, rgw)
+    assert e_w <= 2e-3, "weight gradient: %.3e of max|ref|" % e_w
+    if not c1:
+        gxb = tape.grad_feat(xf)[0].buf
+        if split:
+            gx = torch.cat((gxb[..., :split], gxb[..., op.split_p:op.split_p + cin - split]), dim=-1)
+        else:
+            gx = gxb[..., :cin]
+        e_d = _rel_err(gx.permute(0, 4, 1, 2, 3), rgx)
+        assert e_d <= 2.5 * ULP[dtype], "data gradient: %.3e of max|ref|" % e_d
+
+
+def _benchmark_net(dtype):
+    from multitalent_b200.plans import default_plans
+    from multitalent_b200.training.network_training.MultiTalent_Trainer_DDP import MultiTalent_trainer_ddp
+    tr = MultiTalent_trainer_ddp(default_plans(patch_size=FULL_PATCH, batch_size=1), 0, 0, native_dtype=dtype,
+                                 init_distributed=False, flat_optimizer=False)
+    torch.manual_seed(0)
+    tr.initialize(True)
+    return tr
+
+
+def test_full_patch_t1_parity_vs_reference_under_autocast():
+    """BASELINE.md section 5's T1 definition, executed: ours (bf16 tensor-core path) vs the reference's ops on the same
+    B200 in fp32 and under autocast(bf16).  The measured numbers are written to gpurun_out/t1_parity.json."""
+    _require_tcgen05()
+    from multitalent_b200.synthetic import synthetic_batch
+    from multitalent_b200.training.loss_functions.multitalent_loss import multitalent_loss
+    from oracle.gpu_reference import GpuReference, mask_dice, strict_fp32
+    tr = _benchmark_net(torch.bfloat16)
+    sd = {k: v.detach().clone() for k, v in tr.network.state_dict().items()}
+    pool, convk = tr.net_num_pool_op_kernel_sizes, tr.net_conv_kernel_sizes
+    batch = synthetic_batch(FULL_PATCH, 1, 0, tr.deep_supervision_scales)
+    x = torch.from_numpy(batch['data']).to(DEV)
+    tg = [torch.from_numpy(t).to(DEV) for t in batch['target']]
+    valid = [p['valid_regions'] for p in batch['properties']]
+
+    with strict_fp32():
+        r32 = GpuReference(sd, pool, convk, None)
+        (l32, ce32, dc32), g32 = r32.grads(x, tg, valid)
+        z32 = [o.float() for o in r32.forward(x)]
+    del r32
+    r16 = GpuReference(sd, pool, convk, torch.bfloat16)
+    (l16, _, _), g16r = r16.grads(x, tg, valid)
+    z16 = [o.float() for o in r16.forward(x)]
+    del r16
+    torch.cuda.empty_cache()
+
+    out = tr.network(x)
+    l, ce, dc = multitalent_loss(out, tg, valid, tr.ds_loss_weights)
+    l.backward()
+    zn = [o.detach().float() for o in out]
+    gn = {n: p.grad.detach() for n, p in tr.network.named_parameters()}
+
+    rep = {"patch": list(FULL_PATCH), "loss_fp32_ref": float(l32), "loss_autocast_ref": float(l16), "loss_native": float(l)}
+    for i in range(len(zn)):
+        env = float((z16[i] - z32[i]).abs().max())
+        mine = float((zn[i] - z32[i]).abs().max())
+        rep["scale%d" % i] = {"max_abs_ref_autocast_vs_fp32": env, "max_abs_native_vs_fp32": mine,
+                              "max_abs_logit": float(z32[i].abs().max())}
+        # inside the reference's own autocast-vs-fp32 envelope of THIS run (25 % slack for summation-order luck) or, for
+        # the tiny deep scales, the bf16 envelope BASELINE.md measured (0.19)
+        assert mine <= max(1.25 * env, 0.19), "scale %d: |native - fp32| %.4f vs envelope %.4f" % (i, mine, env)
+    p32, p16, pn = torch.sigmoid(z32[0]), torch.sigmoid(z16[0]), torch.sigmoid(zn[0])
+    rep["max_abs_sigmoid_native_vs_fp32"] = float((pn - p32).abs().max())
+    rep["max_abs_sigmoid_ref_autocast_vs_fp32"] = float((p16 - p32).abs().max())
+    d_ref, d_nat, d_nr = mask_dice(p16, p32), mask_dice(pn, p32), mask_dice(pn, p16)
+    rep.update(mask_dice_ref_autocast_vs_fp32=d_ref, mask_dice_native_vs_fp32=d_nat, mask_dice_native_vs_ref_autocast=d_nr)
+    # loss within 1 % of the fp32 reference
+    assert abs(float(l) - float(l32)) <= 1e-2 * max(1.0, abs(float(l32))), (float(l), float(l32))
+    # segmentation agreement: at least what the library's own bf16 run achieves against fp32 (random-init logits sit
+    # near the threshold, so 0.999 is reachable only where the library reaches it too)
+    assert d_nat >= min(0.999, d_ref - 2e-3), "mask Dice native/fp32 %.5f vs library-autocast/fp32 %.5f" % (d_nat, d_ref)
+    # gradients: cosine against the fp32 reference gradients, at least as good as the library's autocast run - 0.01
+    def cosine(ga, gb):
+        num = da = db = 0.0
+        for n in ga:
+            a, b = ga[n].double().flatten(), gb[n].double().flatten()
+            num += float((a * b).sum()); da += float((a * a).sum()); db += float((b * b).sum())
+        return num / (da ** 0.5 * db ** 0.5)
+    c_nat, c_ref = cosine(gn, g32), cosine(g16r, g32)
+    rep.update(grad_cosine_native_vs_fp32=c_nat, grad_cosine_ref_autocast_vs_fp32=c_ref)
+    assert c_nat > 0.98 and c_nat >= c_ref - 0.01, (c_nat, c_ref)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "t1_parity.json"), "w") as f:
+        json.dump(rep, f, indent=1)
+    print(json.dumps(rep))
+
+
+def test_library_training_step_matches_native_step_small(golden_small):
+    """One optimizer step (GradScaler / clip 12 / Nesterov SGD) of the library arm and of the native trainer from the
+    same weights on the small fixture: the updated parameters agree (fp32 mode, 1e-4) -- pins the `gpu_reference` bench
+    leg to the same algorithm as the product."""
+    from multitalent_b200.plans import default_plans
+    from multitalent_b200.training.network_training.MultiTalent_Trainer_DDP import MultiTalent_trainer_ddp
+    from oracle.gpu_reference import GpuReference, strict_fp32
+    blob, meta = golden_small
+    plans = default_plans(patch_size=blob["x"].shape[2:], batch_size=int(blob["x"].shape[0]))
+    plans['plans_per_stage'][1]['pool_op_kernel_sizes'] = meta["pool"]
+    plans['plans_per_stage'][1]['conv_kernel_sizes'] = meta["convk"]
+    plans['base_num_features'] = meta["base"]
+    tr = MultiTalent_trainer_ddp(plans, 0, 0, init_distributed=False)
+    tr.initialize(True)
+    sd = {k[len("param/"):]: torch.from_numpy(v) for k, v in blob.items() if k.startswith("param/")}
+    tr.load_checkpoint_ram({'state_dict': sd, 'epoch': 0})
+    x = torch.from_numpy(blob["x"]).to(DEV)
+    tg = [torch.from_numpy(blob["target_%d" % i]).to(DEV) for i in range(3)]
+    valid = meta["valid_regions"]
+    with strict_fp32():
+        ref = GpuReference(sd, meta["pool"], meta["convk"], None, ds_loss_weights=tr.ds_loss_weights)
+        lr_, _, _ = ref.train_step(x, tg, valid)
+    l, _, _ = tr.train_step(x, tg, valid, True)
+    assert abs(float(l) - float(lr_)) < 1e-3 * max(1.0, abs(float(lr_)))
+    worst = max(float((p.detach() - ref.params[n].detach()).abs().max()) for n, p in tr.network.named_parameters())
+    assert worst < 1e-4, "updated parameters differ by %.3e" % worst

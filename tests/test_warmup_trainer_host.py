@@ -110,3 +110,64 @@ def test_warmup_lr_matches_the_reference_method():
         s.epoch = epoch
         Ref.maybe_update_lr(s)
         assert s.optimizer.param_groups[0]['lr'] == pytest.approx(warmup_lr(epoch, 10, 50, 5e-4, 1e-2, 1060), rel=1e-12)
+
+
+def _drive_epochs(n_epochs):
+    """Our trainer's epoch bookkeeping with a stub optimizer (no network): (lr, optimizer kind) each epoch trains with."""
+    from multitalent_b200.training.network_training.nnUNetTrainerV2_warmup import nnUNetTrainerV2_warmupsegheads as Mine
+
+    class T(Mine):
+        def initialize_optimizer_and_scheduler(self, seg_heads_only=False):
+            self.optimizer = type("O", (), {"param_groups": [{"lr": None}]})()
+            self.kind = "adamw_heads" if seg_heads_only else "sgd_all"
+    t = T(None, 0)
+    t.initialize_optimizer_and_scheduler(True)
+    t.maybe_update_lr()                     # nnUNetTrainerV2.run_training: maybe_update_lr(self.epoch) before epoch 0
+    used = []
+    for _ in range(n_epochs):
+        used.append((t.optimizer.param_groups[0]['lr'], t.kind))
+        t.on_epoch_end()
+    return used
+
+
+def test_epoch_loop_lr_sequence_known_answers():
+    """network_trainer.py:482-490, 603-616: maybe_update_lr runs BEFORE the epoch counter is incremented, so epoch
+    e >= 1 trains at warmup_lr(e - 1); epoch 10 is still heads-only AdamW at 5e-4, epoch 11 the first SGD epoch at 2e-4,
+    and the last epoch (1059) still has a non-zero learning rate."""
+    used = _drive_epochs(1060)
+    f = lambda e: warmup_lr(e, 10, 50, 5e-4, 1e-2, 1060)  # noqa: E731
+    assert used[0] == (pytest.approx(f(0)), "adamw_heads")
+    for e in range(1, 1060):
+        assert used[e][0] == pytest.approx(f(e - 1), rel=1e-12), e
+        assert used[e][1] == ("adamw_heads" if e <= 10 else "sgd_all"), e
+    assert used[10][0] == pytest.approx(5e-4) and used[11][0] == pytest.approx(2e-4)
+    assert used[1059][0] > 0.0
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="needs /root/reference (build container)")
+def test_epoch_loop_lr_sequence_matches_the_reference_call_order():
+    """The reference's own methods driven in the reference's own order (run_training: maybe_update_lr(self.epoch) once,
+    then per epoch on_epoch_end -> [optimizer switch at epoch == warmup_duration] -> maybe_update_lr() -> epoch += 1)."""
+    from oracle import ref_import
+    ref_import.install()
+    from nnunet.training.network_training.nnUNet_variants.pretraining.nnUNetTrainerV2_warmup import nnUNetTrainerV2_warmupsegheads as Ref  # noqa: E501
+
+    class Stub:
+        warmup_duration, num_epochs_sgd_warmup, warmup_max_lr, initial_lr, max_num_epochs = 10, 50, 5e-4, 1e-2, 1060
+        lr, epoch = None, 0
+
+        def __init__(self):
+            self.optimizer = type("O", (), {"param_groups": [{"lr": None}]})()
+
+        def print_to_log_file(self, *a, **k):
+            pass
+    s = Stub()
+    Ref.maybe_update_lr(s, 0)
+    ref_used = []
+    for _ in range(200):
+        ref_used.append(s.optimizer.param_groups[0]['lr'])
+        Ref.maybe_update_lr(s)      # NetworkTrainer.on_epoch_end (network_trainer.py:609), self.epoch not yet incremented
+        s.epoch += 1                # network_trainer.py:490
+    mine = _drive_epochs(200)
+    for e, (a, b) in enumerate(zip(ref_used, mine)):
+        assert a == pytest.approx(b[0], rel=1e-12), e
