@@ -180,10 +180,13 @@ int mtb200_dcce_bwd(const void* logits, int32_t dtype, int32_t ldc, int32_t C, i
  *      MultiTalent_Trainer_DDP.py:567-594 (stats), :596-606 (Dice), and its autograd ------------------------------ */
 /* pass 1: stats[b][j][4] doubles += {sum bce, sum sigma*y, sum sigma, sum y} over the voxels of sample b for every
  * channel j whose bit is set in valid_mask[b]; y = bit j of pos_mask[label].  logits NDHWC [B][nvox][ldc]; target
- * float32 label map [B][nvox] (integer-valued, MultiTalent_Trainer_DDP.py:580-584). */
+ * float32 label map [B][nvox] (integer-valued, MultiTalent_Trainer_DDP.py:580-584).
+ * `hard` (may be NULL): [B][C][2] doubles += {sum [z > 0] * y, sum [z > 0]} -- the thresholded-prediction counts of
+ * run_online_evaluation (MultiTalent_Trainer_DDP.py:372-397: tp = hard[0], fp = hard[1] - hard[0], fn = sum y - hard[0])
+ * out of the same pass. */
 int mtb200_mt_loss_stats(const void* logits, int32_t dtype, int32_t ldc, int32_t C, const float* target, int32_t B,
                          int64_t nvox, const uint64_t* valid_mask, const uint64_t* pos_mask, int32_t n_labels,
-                         double* stats, void* stream);
+                         double* stats, double* hard, void* stream);
 /* tiny on-device finalize for one scale: local stats [B][C][4] + pooled {tp, sigma+y} of ALL ranks
  * pooled[B][C][2] (= sum over ranks of local {tp, sum sigma + sum y}; NULL = derive from the local stats, world 1)
  * -> losses[3] += w*{ce - dc, ce, dc}; coef[B][C][4] = {w/nvox, w*W*2/D, w*W*2*TP/D^2, valid} for pass 2 */
@@ -201,9 +204,11 @@ int mtb200_mt_loss_bwd(const void* logits, int32_t dtype, int32_t ldc, int32_t C
 int mtb200_sw_gather_tile(const float* vol, int32_t Cin, int32_t X, int32_t Y, int32_t Z, int32_t x0, int32_t y0,
                           int32_t z0, int32_t pd, int32_t ph, int32_t pw, int32_t flip, void* tile, int32_t dtype,
                           int32_t ldc, void* stream);
-/* acc[c][x0+d][y0+h][z0+w] += weight * gauss[d][h][w] * sigmoid(logits[fd(d)][fh(h)][fw(w)][c]),  c < C;
+/* acc[c][x0+d][y0+h][z0+w] += weight * gauss[d][h][w] * nonlin(logits[fd(d)][fh(h)][fw(w)][:])[c],  c < C;
  * if nb != NULL also nb[x0+d][..] += gauss[d][h][w]  (one weight volume instead of the reference's 47 copies).
- * gauss may be NULL (= 1).  apply_sigmoid=0 accumulates the raw values. */
+ * gauss may be NULL (= 1).  apply_sigmoid = the inference non-linearity (`inference_apply_nonlin`, neural_network.py:
+ * 531-586): 0 accumulates the raw values, 1 = sigmoid (MultiTalent, MultiTalent_Trainer_DDP.py:46), 2 = softmax over
+ * the C channels (softmax_helper, nnUNetTrainerV2.py:162 -- the fine-tuning trainers). */
 int mtb200_sw_aggregate(const void* logits, int32_t dtype, int32_t ldc, int32_t C, int32_t pd, int32_t ph, int32_t pw,
                         int32_t flip, const float* gauss, float weight, int32_t apply_sigmoid, float* acc, float* nb,
                         int32_t X, int32_t Y, int32_t Z, int32_t x0, int32_t y0, int32_t z0, void* stream);

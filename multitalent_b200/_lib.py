@@ -99,7 +99,7 @@ SIGNATURES = {
                             _i32, _f32, _vp],
     "mtb200_dcce_stats": [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _vp, _vp, _vp],
     "mtb200_dcce_bwd": [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _vp, _f32, _vp, _vp, _i32, _vp],
-    "mtb200_mt_loss_stats": [_vp, _i32, _i32, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp],
+    "mtb200_mt_loss_stats": [_vp, _i32, _i32, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp],
     "mtb200_mt_loss_finalize": [_vp, _vp, _vp, _i32, _i32, _i64, _f32, _f32, _vp, _vp, _vp],
     "mtb200_mt_loss_bwd": [_vp, _i32, _i32, _i32, _vp, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _vp],
     "mtb200_sw_gather_tile": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32,

@@ -65,7 +65,7 @@ int dcce_bwd(const void*, int, int, int, int, const float*, int, long long, cons
 int residual_bwd(const void*, int, int, const void*, int, int, void*, int, int, int, void*, int, int, int, int, long long, int,
                  float, cudaStream_t);
 int mt_loss_stats(const void*, int, int, int, const float*, int, long long, const uint64_t*, const uint64_t*, int,
-                  double*, cudaStream_t);
+                  double*, double*, cudaStream_t);
 int mt_loss_finalize(const double*, const double*, const uint64_t*, int, int, long long, float, float, float*, float*,
                      cudaStream_t);
 int mt_loss_bwd(const void*, int, int, int, const float*, int, long long, const uint64_t*, int, const float*,
@@ -214,9 +214,10 @@ int mtb200_dcce_bwd(const void* logits, int32_t dtype, int32_t ldc, int32_t C, i
 
 int mtb200_mt_loss_stats(const void* logits, int32_t dtype, int32_t ldc, int32_t C, const float* target, int32_t B,
                          int64_t nvox, const uint64_t* valid_mask, const uint64_t* pos_mask, int32_t n_labels,
-                         double* stats, void* stream) {
+                         double* stats, double* hard, void* stream) {
   MTB_REQUIRE(logits && target && valid_mask && pos_mask && stats, "mt_loss_stats: null pointer");
-  return mt_loss_stats(logits, dtype, ldc, C, target, B, nvox, valid_mask, pos_mask, n_labels, stats, STREAM(stream));
+  return mt_loss_stats(logits, dtype, ldc, C, target, B, nvox, valid_mask, pos_mask, n_labels, stats, hard,
+                       STREAM(stream));
 }
 
 int mtb200_mt_loss_finalize(const double* stats, const double* pooled, const uint64_t* valid_mask, int32_t B, int32_t C,

@@ -18,12 +18,16 @@ __device__ __forceinline__ void sigmoid_terms(float z, float& e, float& sig) {
   sig = z >= 0.f ? r : e * r;
 }
 
-template <typename T>
+// HARD: additionally count, per supervised (b, channel), the thresholded prediction (sigmoid(z) > 0.5 <=> z > 0) against
+// the same region target: hard[b][c] = {sum pred * y, sum pred} -- with sum y from the soft statistics that is the
+// tp / fp / fn of run_online_evaluation (MultiTalent_Trainer_DDP.py:372-397) out of the pass the loss makes anyway.
+template <typename T, bool HARD>
 __global__ void __launch_bounds__(LT) mt_loss_stats_kernel(const T* __restrict__ logits, int ldc, int C,
                                                            const float* __restrict__ target, long long nvox,
                                                            const uint64_t* __restrict__ valid_mask,
                                                            const uint64_t* __restrict__ pos_mask, int n_labels,
-                                                           double* __restrict__ stats) {
+                                                           double* __restrict__ stats, double* __restrict__ hard) {
+  constexpr int NQ = HARD ? 6 : 4;
   __shared__ uint64_t s_pos[MAX_LABELS];
   __shared__ float sh[LT][8];
   __shared__ int s_act[8], s_nact;
@@ -47,9 +51,9 @@ __global__ void __launch_bounds__(LT) mt_loss_stats_kernel(const T* __restrict__
   const int cg = s_act[ai];
   const bool active = vlane < vstride;
   const unsigned vbits = (unsigned)((valid >> (cg * 8)) & 0xffull);
-  float part[4][8];
+  float part[NQ][8];
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+  for (int q = 0; q < NQ; ++q)
 #pragma unroll
     for (int j = 0; j < 8; ++j) part[q][j] = 0.f;
 
@@ -91,6 +95,11 @@ __global__ void __launch_bounds__(LT) mt_loss_stats_kernel(const T* __restrict__
             part[1][j] = fmaf(sig, y, part[1][j]);
             part[2][j] += sig;
             part[3][j] += y;
+            if (HARD) {
+              const float pred = zz > 0.f ? 1.f : 0.f;
+              part[NQ - 2][j] += pred * y;
+              part[NQ - 1][j] += pred;
+            }
           }
         }
       }
@@ -98,7 +107,8 @@ __global__ void __launch_bounds__(LT) mt_loss_stats_kernel(const T* __restrict__
   }
   // block reduce over the voxel lanes, one double atomic per (channel, stat)
   double* dst = stats + (long long)b * C * 4;
-  for (int q = 0; q < 4; ++q) {
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] = active ? part[q][j] : 0.f;
@@ -107,7 +117,10 @@ __global__ void __launch_bounds__(LT) mt_loss_stats_kernel(const T* __restrict__
       const int a = idx / 8, j = idx % 8;
       float sum = 0.f;
       for (int vl = 0; vl < vstride; ++vl) sum += sh[vl * nact + a][j];
-      if (sum != 0.f) atomicAdd(dst + (long long)(s_act[a] * 8 + j) * 4 + q, (double)sum);
+      if (sum != 0.f) {
+        if (q < 4) atomicAdd(dst + (long long)(s_act[a] * 8 + j) * 4 + q, (double)sum);
+        else atomicAdd(hard + ((long long)b * C + s_act[a] * 8 + j) * 2 + (q - 4), (double)sum);
+      }
     }
   }
 }
@@ -120,12 +133,18 @@ static dim3 loss_grid(long long nvox, int B, int C) {
 }
 
 int mt_loss_stats(const void* logits, int dtype, int ldc, int C, const float* target, int B, long long nvox,
-                  const uint64_t* valid_mask, const uint64_t* pos_mask, int n_labels, double* stats, cudaStream_t s) {
+                  const uint64_t* valid_mask, const uint64_t* pos_mask, int n_labels, double* stats, double* hard,
+                  cudaStream_t s) {
   MTB_REQUIRE(C % 8 == 0 && C <= 64 && ldc % 8 == 0 && C <= ldc, "mt_loss_stats: C=%d (padded, <=64) ldc=%d", C, ldc);
   MTB_REQUIRE(n_labels <= MAX_LABELS, "mt_loss_stats: n_labels=%d > %d", n_labels, MAX_LABELS);
   dim3 grid = loss_grid(nvox, B, C);
-  MTB_DISPATCH_DTYPE(dtype, T, (mt_loss_stats_kernel<T><<<grid, LT, 0, s>>>(
-      reinterpret_cast<const T*>(logits), ldc, C, target, nvox, valid_mask, pos_mask, n_labels, stats)));
+  if (hard) {
+    MTB_DISPATCH_DTYPE(dtype, T, (mt_loss_stats_kernel<T, true><<<grid, LT, 0, s>>>(
+        reinterpret_cast<const T*>(logits), ldc, C, target, nvox, valid_mask, pos_mask, n_labels, stats, hard)));
+  } else {
+    MTB_DISPATCH_DTYPE(dtype, T, (mt_loss_stats_kernel<T, false><<<grid, LT, 0, s>>>(
+        reinterpret_cast<const T*>(logits), ldc, C, target, nvox, valid_mask, pos_mask, n_labels, stats, nullptr)));
+  }
   return check_launch("mt_loss_stats");
 }
 

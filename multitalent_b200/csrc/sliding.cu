@@ -45,8 +45,11 @@ int sw_gather_tile(const float* vol, int Cin, int X, int Y, int Z, int x0, int y
 
 // ---- aggregation -----------------------------------------------------------------------------------------------------
 // One block = one (d, h) row segment of SEG consecutive w voxels x all channels.  Phase 1 reads the channels-last logits
-// (coalesced), applies sigmoid * weight * gauss, and parks them transposed in smem; phase 2 does the read-modify-write on
-// the channels-first accumulator with 128-byte coalesced rows.  Tiles of one launch never overlap => plain RMW.
+// (coalesced), applies the inference non-linearity * weight * gauss, and parks them transposed in smem; phase 2 does the
+// read-modify-write on the channels-first accumulator with 128-byte coalesced rows.  Tiles of one launch never overlap
+// => plain RMW.  nonlin: 0 = none, 1 = sigmoid (MultiTalent, MultiTalent_Trainer_DDP.py:46), 2 = softmax over the C
+// channels (`softmax_helper` of the single-task trainers, nnUNetTrainerV2.py:162): the raw logits are parked first and
+// one thread per voxel normalises its column of the shared tile.
 constexpr int SEG = 128;  // 64 measured 3.2 TB/s on the RMW (256-byte rows per class plane); 128 = whole 512-byte patch rows
 constexpr int AGG_T = 256;
 
@@ -72,11 +75,11 @@ __global__ void __launch_bounds__(AGG_T) sw_aggregate_kernel(const T* __restrict
     const int sw = flipc(w, pw, flip & 1);
     float z[8];
     load8<T>(logits + (((long long)sd * ph + sh) * pw + sw) * ldc + cg * 8, z);
-    const float gw = weight * (gauss ? gauss[((long long)d * ph + h) * pw + w] : 1.f);
+    const float gw = apply_sigmoid == 2 ? 1.f : weight * (gauss ? gauss[((long long)d * ph + h) * pw + w] : 1.f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float v = z[j];
-      if (apply_sigmoid) {
+      if (apply_sigmoid == 1) {
         const float e = expf(-fabsf(v));
         v = v >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
       }
@@ -84,6 +87,21 @@ __global__ void __launch_bounds__(AGG_T) sw_aggregate_kernel(const T* __restrict
     }
   }
   __syncthreads();
+  if (apply_sigmoid == 2) {  // softmax over the channels of each voxel (column wl of the shared tile)
+    for (int wl = threadIdx.x; wl < nw; wl += AGG_T) {
+      float m = -INFINITY;
+      for (int c = 0; c < C; ++c) m = fmaxf(m, sm[c * (SEG + 1) + wl]);
+      float ssum = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float e = expf(sm[c * (SEG + 1) + wl] - m);
+        sm[c * (SEG + 1) + wl] = e;
+        ssum += e;
+      }
+      const float gw = weight * (gauss ? gauss[((long long)d * ph + h) * pw + w0 + wl] : 1.f) / ssum;
+      for (int c = 0; c < C; ++c) sm[c * (SEG + 1) + wl] *= gw;
+    }
+    __syncthreads();
+  }
   // phase 2
   const long long plane = (long long)Y * Z;
   const long long rowbase = ((long long)(x0 + d) * Y + (y0 + h)) * Z + z0 + w0;

@@ -255,6 +255,63 @@ class PlainConvUNetDecoder(nn.Module):
         return outs[::-1] if self.deep_supervision else outs
 
 
+class ResidualUNetDecoder(nn.Module):
+    """generic_modular_residual_UNet.py:142-270: transposed conv -> cat -> ResidualLayer per level; 1x1x1 heads (bias):
+    `deep_supervision_outputs` for every level but the highest-resolution one (only with deep supervision) and
+    `segmentation_output` for the highest resolution."""
+
+    def __init__(self, previous, num_classes, num_blocks_per_stage=None, network_props=None, deep_supervision=False,
+                 upscale_logits=False, block=BasicResidualBlock, block_kwargs=None):
+        super().__init__()
+        block_kwargs = block_kwargs or {}
+        self.num_classes, self.deep_supervision = num_classes, deep_supervision
+        self.props = previous.props if network_props is None else network_props
+        conv_op = self.props['conv_op']
+        if conv_op == nn.Conv2d:
+            transpconv, upsample_mode = nn.ConvTranspose2d, "bilinear"
+        elif conv_op == nn.Conv3d:
+            transpconv, upsample_mode = nn.ConvTranspose3d, "trilinear"
+        else:
+            raise ValueError("unknown convolution dimensionality, conv op: %s" % str(conv_op))
+        if num_blocks_per_stage is None:
+            num_blocks_per_stage = previous.num_blocks_per_stage[:-1][::-1]
+        assert len(num_blocks_per_stage) == len(previous.num_blocks_per_stage) - 1
+        self.stage_pool_kernel_size = previous.stage_pool_kernel_size
+        self.stage_output_features = previous.stage_output_features
+        self.stage_conv_op_kernel_size = previous.stage_conv_op_kernel_size
+        n = len(previous.stages) - 1
+        tus, stages, heads = [], [], []
+        cum_upsample = np.cumprod(np.vstack(self.stage_pool_kernel_size), axis=0).astype(int)
+        f_skip = None
+        for i, s in enumerate(np.arange(n)[::-1]):
+            f_below, f_skip = self.stage_output_features[s + 1], self.stage_output_features[s]
+            tus.append(transpconv(f_below, f_skip, self.stage_pool_kernel_size[s + 1], self.stage_pool_kernel_size[s + 1],
+                                  bias=False))
+            stages.append(ResidualLayer(2 * f_skip, f_skip, self.stage_conv_op_kernel_size[s], self.props,
+                                        num_blocks_per_stage[i], None, block, block_kwargs))
+            if deep_supervision and s != 0:
+                seg = conv_op(f_skip, num_classes, 1, 1, 0, 1, 1, bias=True)
+                heads.append(nn.Sequential(seg, Upsample(scale_factor=cum_upsample[s], mode=upsample_mode))
+                             if upscale_logits else seg)
+        self.segmentation_output = conv_op(f_skip, num_classes, 1, 1, 0, 1, 1, bias=True)
+        self.tus, self.stages = nn.ModuleList(tus), nn.ModuleList(stages)
+        self.deep_supervision_outputs = nn.ModuleList(heads)
+
+    def forward(self, skips):
+        skips = skips[::-1]
+        x = skips[0]
+        outs = []
+        for i in range(len(self.tus)):
+            x = self.stages[i](torch.cat((self.tus[i](x), skips[i + 1]), dim=1))
+            if self.deep_supervision and i != len(self.tus) - 1:
+                outs.append(self.deep_supervision_outputs[i](x))
+        seg = self.segmentation_output(x)
+        if self.deep_supervision:
+            outs.append(seg)
+            return outs[::-1]
+        return seg
+
+
 def init_last_bn_before_add_to_0(module):
     """MultiTalent_meets_resenc.py:31-34: the second norm of every residual block starts at zero."""
     if isinstance(module, BasicResidualBlock):
@@ -274,6 +331,64 @@ def _native_conv(c, need_k=(1, 3)):
 
 def _native_lrelu(a):
     return isinstance(a, nn.LeakyReLU) and abs(a.negative_slope - 1e-2) < 1e-12
+
+
+def _native_block(b):
+    """True if a BasicResidualBlock is something the kernels implement exactly."""
+    if type(b) is not BasicResidualBlock or b.use_avgpool_in_skip or not isinstance(b.dropout, nn.Identity):
+        return False
+    if not (_native_conv(b.conv1) and _native_conv(b.conv2) and _native_norm(b.norm1) and _native_norm(b.norm2)
+            and _native_lrelu(b.nonlin1) and _native_lrelu(b.nonlin2)):
+        return False
+    if isinstance(b.downsample_skip, nn.Sequential):
+        return _native_conv(b.downsample_skip[0], (1,)) and _native_norm(b.downsample_skip[1])
+    return True
+
+
+def _block_ops(b, split=0):
+    """(conv1, norm1, conv2, norm2, (skip conv, skip norm) | None) of one BasicResidualBlock.  `split`: logical
+    channels of the first half of a concatenated input (decoder blocks read the concat buffer)."""
+    skip = None
+    if isinstance(b.downsample_skip, nn.Sequential):
+        c = b.downsample_skip[0]
+        skip = (ConvOp(c.weight, c.bias, c.kernel_size, c.stride, split=split), b.downsample_skip[1])
+    return (ConvOp(b.conv1.weight, b.conv1.bias, b.conv1.kernel_size, b.conv1.stride, split=split), b.norm1,
+            ConvOp(b.conv2.weight, b.conv2.bias, b.conv2.kernel_size, b.conv2.stride), b.norm2, skip)
+
+
+def _run_block(eng, tape, blk, f, out=None):
+    """BasicResidualBlock.forward (conv_blocks.py:201-213) on the kernels: conv1-IN-LReLU, conv2-IN, skip (1x1x1 conv-IN
+    or the identity), add, LReLU."""
+    c1, n1, c2, n2, skip = blk
+    a = eng.conv_norm(tape, c1, n1.weight, n1.bias, f)
+    a = eng.conv_norm(tape, c2, n2.weight, n2.bias, a, slope=1.0)       # norm2 only: the add comes first
+    if skip is not None:
+        r = eng.conv_norm(tape, skip[0], skip[1].weight, skip[1].bias, f, slope=1.0)
+    else:
+        # identity skip: the very tensor conv1 consumed (its materialised activation on the tensor-core path, the raw
+        # tensor + pending transform on the norm-on-load path), so that both consumers leave their gradients in the same
+        # buffer
+        r = f.act if f.act is not None else f
+    return eng.residual_act(tape, a, r, out=out)
+
+
+def _run_encoder(eng, tape, ops, f, dev):
+    """ResidualUNetEncoder.forward (generic_modular_residual_UNet.py:98-112) -> list of skips (bottleneck last).  Every
+    stage output but the bottleneck is written straight into the second half of the decoder's concat buffer."""
+    op, nrm = ops['stem']
+    f = eng.conv_norm(tape, op, nrm.weight, nrm.bias, f, need_input_grad=False)
+    n_stages = len(ops['enc'])
+    skips = []
+    for s, blocks in enumerate(ops['enc']):
+        for bi, blk in enumerate(blocks):
+            out = None
+            if bi == len(blocks) - 1 and s < n_stages - 1:
+                od = blk[0].out_dims(f.dims)
+                cat = eng.new_buf(od, 2 * blk[2].Cout_p, dev)
+                out = Feat(cat, blk[2].Cout_p, blk[2].Cout, blk[2].Cout_p)
+            f = _run_block(eng, tape, blk, f, out=out)
+        skips.append(f)
+    return skips
 
 
 class FabiansUNet(SegmentationNetwork):
@@ -326,15 +441,8 @@ class FabiansUNet(SegmentationNetwork):
         if not (_native_conv(e.initial_conv, (3,)) and _native_norm(e.initial_norm) and _native_lrelu(e.initial_nonlin)):
             return False
         for st in e.stages:
-            for b in st.convs:
-                if type(b) is not BasicResidualBlock or b.use_avgpool_in_skip or not isinstance(b.dropout, nn.Identity):
-                    return False
-                if not (_native_conv(b.conv1) and _native_conv(b.conv2) and _native_norm(b.norm1) and _native_norm(b.norm2)
-                        and _native_lrelu(b.nonlin1) and _native_lrelu(b.nonlin2)):
-                    return False
-                if isinstance(b.downsample_skip, nn.Sequential):
-                    if not (_native_conv(b.downsample_skip[0], (1,)) and _native_norm(b.downsample_skip[1])):
-                        return False
+            if not all(_native_block(b) for b in st.convs):
+                return False
         for t in d.tus:
             if not isinstance(t, nn.ConvTranspose3d) or t.bias is not None or tuple(t.kernel_size) != tuple(t.stride):
                 return False
@@ -349,18 +457,7 @@ class FabiansUNet(SegmentationNetwork):
         e, d = self.encoder, self.decoder
         ops = {'stem': (ConvOp(e.initial_conv.weight, e.initial_conv.bias, e.initial_conv.kernel_size,
                                e.initial_conv.stride), e.initial_norm)}
-        stages = []
-        for st in e.stages:
-            blocks = []
-            for b in st.convs:
-                skip = None
-                if isinstance(b.downsample_skip, nn.Sequential):
-                    c = b.downsample_skip[0]
-                    skip = (ConvOp(c.weight, c.bias, c.kernel_size, c.stride), b.downsample_skip[1])
-                blocks.append((ConvOp(b.conv1.weight, b.conv1.bias, b.conv1.kernel_size, b.conv1.stride), b.norm1,
-                               ConvOp(b.conv2.weight, b.conv2.bias, b.conv2.kernel_size, b.conv2.stride), b.norm2, skip))
-            stages.append(blocks)
-        ops['enc'] = stages
+        ops['enc'] = [[_block_ops(b) for b in st.convs] for st in e.stages]
         dec = []
         for i in range(len(d.tus)):
             t = d.tus[i]
@@ -387,42 +484,28 @@ class FabiansUNet(SegmentationNetwork):
         ops = self._ops
         dev = x.buf.device if isinstance(x, Feat) else x.device
         f = x if isinstance(x, Feat) else eng.input_feat(x)
-        op, nrm = ops['stem']
-        f = eng.conv_norm(tape, op, nrm.weight, nrm.bias, f, need_input_grad=False)
-        n_stages = len(ops['enc'])
-        skips = []
-        for s, blocks in enumerate(ops['enc']):
-            for bi, (c1, n1, c2, n2, skip) in enumerate(blocks):
-                a = eng.conv_norm(tape, c1, n1.weight, n1.bias, f)
-                a = eng.conv_norm(tape, c2, n2.weight, n2.bias, a, slope=1.0)       # norm2 only: the add comes first
-                if skip is not None:
-                    r = eng.conv_norm(tape, skip[0], skip[1].weight, skip[1].bias, f, slope=1.0)
-                else:
-                    # identity skip: the very tensor conv1 consumed (its materialised activation on the tensor-core
-                    # path, the raw tensor + pending transform on the norm-on-load path), so that both consumers leave
-                    # their gradients in the same buffer
-                    r = f.act if f.act is not None else f
-                out = None
-                if bi == len(blocks) - 1 and s < n_stages - 1:
-                    # the stage output is a skip: it is written straight into the second half of the decoder's concat
-                    # buffer, so torch.cat (generic_modular_UNet.py:265) disappears
-                    cat = eng.new_buf(a.dims, 2 * a.Cp, dev)
-                    out = Feat(cat, a.Cp, a.C, a.Cp)
-                f = eng.residual_act(tape, a, r, out=out)
-            skips.append(f)
+        # frozen-trunk fast path (fine-tuning with only the heads trainable, nnUNetTrainerV2_warmup.py:470-476): nothing
+        # below the heads is recorded, the backward pass is the heads' weight gradients alone
+        ttape = tape
+        if tape is not None and not any(p.requires_grad for n, p in self.named_parameters()
+                                        if not n.startswith("decoder.deep_supervision_outputs.")):
+            ttape = None
+        skips = _run_encoder(eng, ttape, ops, f, dev)
+        n_stages = len(skips)
+        f = skips[-1]
         logits = []
         nd = len(ops['dec'])
         for i, (tu, convs, head) in enumerate(ops['dec']):
             skip = skips[n_stages - 2 - i]
             cat = skip.buf
             assert tu.Cout_p == skip.Cp and cat.shape[4] == 2 * skip.Cp
-            eng.conv_plain(tape, tu, f, Feat(cat, 0, tu.Cout, tu.Cout_p))
+            eng.conv_plain(ttape, tu, f, Feat(cat, 0, tu.Cout, tu.Cout_p))
             f = Feat(cat, 0, tu.Cout + skip.C, 2 * skip.Cp)
             for (op, nrm) in convs:
-                f = eng.conv_norm(tape, op, nrm.weight, nrm.bias, f)
+                f = eng.conv_norm(ttape, op, nrm.weight, nrm.bias, f)
             if head is None or (only_full_res and i != nd - 1):
                 continue
-            logits.append(eng.conv_plain(tape, ConvOpCache.get(self, head), f))
+            logits.append(eng.conv_plain(tape, ConvOpCache.get(self, head), f, need_input_grad=ttape is not None))
         return logits[::-1]
 
     def native_logits(self, tile: Feat) -> Feat:
@@ -444,6 +527,135 @@ class FabiansUNet(SegmentationNetwork):
             return list(outs) if want_ds else outs[0]
         if self._native_ok and not x.is_cuda:
             raise L.Mtb200Error("FabiansUNet (MultiTalent configuration) runs on the native CUDA path only; got a %s "
+                                "tensor. There is no CPU fallback." % x.device)
+        return self.decoder(self.encoder(x))
+
+
+class ResidualUNet(SegmentationNetwork):
+    """generic_modular_residual_UNet.py:273-318: residual encoder + RESIDUAL decoder (`ResidualUNetDecoder`) -- the
+    `ResidualUNet` module API BASELINE.json's north star names.  Same kernels as `FabiansUNet`; the decoder levels are
+    `ResidualLayer`s whose first block reads the concat buffer through both its 3x3x3 conv and its 1x1x1 skip conv.
+    `native_dtype` / `native_impl` are keyword-only extensions."""
+    use_this_for_batch_size_computation_2D = 858931200.0
+    use_this_for_batch_size_computation_3D = 727842816.0
+    default_base_num_features = 24
+    default_conv_per_stage = (2, 2, 2, 2, 2, 2, 2, 2)
+
+    def __init__(self, input_channels, base_num_features, num_blocks_per_stage_encoder, feat_map_mul_on_downscale,
+                 pool_op_kernel_sizes, conv_kernel_sizes, props, num_classes, num_blocks_per_stage_decoder,
+                 deep_supervision=False, upscale_logits=False, max_features=512, initializer=None,
+                 block=BasicResidualBlock, block_kwargs=None, native_dtype=torch.float32, native_impl=0):
+        super().__init__()
+        block_kwargs = block_kwargs or {}
+        self.do_ds = deep_supervision
+        self.conv_op = props['conv_op']
+        self.num_classes = num_classes
+        self.upscale_logits = upscale_logits
+        self.encoder = ResidualUNetEncoder(input_channels, base_num_features, num_blocks_per_stage_encoder,
+                                           feat_map_mul_on_downscale, pool_op_kernel_sizes, conv_kernel_sizes, props,
+                                           default_return_skips=True, max_num_features=max_features, block=block,
+                                           block_kwargs=block_kwargs)
+        self.decoder = ResidualUNetDecoder(self.encoder, num_classes, num_blocks_per_stage_decoder, props,
+                                           deep_supervision, upscale_logits, block=block, block_kwargs=block_kwargs)
+        self.input_shape_must_be_divisible_by = np.prod(np.vstack(pool_op_kernel_sizes), 0, dtype=np.int64)
+        if initializer is not None:
+            self.apply(initializer)
+        self._engine = Engine(native_dtype, native_impl)
+        self._ops = None
+        self._native_ok = self._check_native()
+
+    def set_native_dtype(self, dtype, impl=None):
+        self._engine = Engine(dtype, self._engine.impl if impl is None else impl)
+
+    def native_dtype(self):
+        return self._engine.dtype
+
+    def native_input_channels_padded(self):
+        return pad_channels(self.encoder.initial_conv.in_channels)
+
+    def _heads(self):
+        """1x1x1 head of each decoder level (None where the level has none), lowest resolution first."""
+        d = self.decoder
+        n = len(d.tus)
+        ds = list(d.deep_supervision_outputs)
+        return [(ds[i] if i < len(ds) else None) for i in range(n - 1)] + [d.segmentation_output]
+
+    def _check_native(self):
+        e, d = self.encoder, self.decoder
+        if self.conv_op != nn.Conv3d or self.upscale_logits or self.num_classes > 64:
+            return False
+        if not (_native_conv(e.initial_conv, (3,)) and _native_norm(e.initial_norm) and _native_lrelu(e.initial_nonlin)):
+            return False
+        for st in list(e.stages) + list(d.stages):
+            if not all(_native_block(b) for b in st.convs):
+                return False
+        for t in d.tus:
+            if not isinstance(t, nn.ConvTranspose3d) or t.bias is not None or tuple(t.kernel_size) != tuple(t.stride):
+                return False
+        return all(h is None or (isinstance(h, nn.Conv3d) and tuple(h.kernel_size) == (1, 1, 1)) for h in self._heads())
+
+    def _build_ops(self):
+        e, d = self.encoder, self.decoder
+        ops = {'stem': (ConvOp(e.initial_conv.weight, e.initial_conv.bias, e.initial_conv.kernel_size,
+                               e.initial_conv.stride), e.initial_norm),
+               'enc': [[_block_ops(b) for b in st.convs] for st in e.stages]}
+        dec = []
+        for i in range(len(d.tus)):
+            t = d.tus[i]
+            tu = ConvOp(t.weight, None, t.kernel_size, t.stride, transposed=True)
+            blocks = [_block_ops(b, split=t.out_channels if j == 0 else 0) for j, b in enumerate(d.stages[i].convs)]
+            dec.append((tu, blocks))
+        ops['dec'] = dec
+        self._ops = ops
+        PackGroup(collect_ops(ops))
+        self.__dict__['_ops_key'] = e.initial_conv.weight
+
+    def _native_forward(self, x, tape, only_full_res=False):
+        """ResidualUNet.forward (:304-306) = encoder (:98-112) + ResidualUNetDecoder.forward (:224-248)."""
+        L.lib()  # fail loudly if the CUDA library is missing
+        eng = self._engine
+        if self._ops is None or self.__dict__.get('_ops_key') is not self.encoder.initial_conv.weight:
+            self._build_ops()
+        ops = self._ops
+        dev = x.buf.device if isinstance(x, Feat) else x.device
+        f = x if isinstance(x, Feat) else eng.input_feat(x)
+        skips = _run_encoder(eng, tape, ops, f, dev)
+        n_stages = len(skips)
+        f = skips[-1]
+        heads = self._heads()
+        logits = []
+        nd = len(ops['dec'])
+        for i, (tu, blocks) in enumerate(ops['dec']):
+            skip = skips[n_stages - 2 - i]
+            cat = skip.buf
+            assert tu.Cout_p == skip.Cp and cat.shape[4] == 2 * skip.Cp
+            eng.conv_plain(tape, tu, f, Feat(cat, 0, tu.Cout, tu.Cout_p))
+            f = Feat(cat, 0, tu.Cout + skip.C, 2 * skip.Cp)
+            for blk in blocks:
+                f = _run_block(eng, tape, blk, f)
+            if heads[i] is None or (only_full_res and i != nd - 1):
+                continue
+            logits.append(eng.conv_plain(tape, ConvOpCache.get(self, heads[i]), f))
+        return logits[::-1]
+
+    def native_logits(self, tile: Feat) -> Feat:
+        self._engine.begin_step()
+        return self._native_forward(tile, None, only_full_res=True)[0]
+
+    def forward(self, x):
+        if self._native_ok and x.is_cuda:
+            want_ds = bool(self.decoder.deep_supervision)
+            params = tuple(self.parameters())
+            if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+                n_out = len(self.decoder.tus) if want_ds else 1
+                outs = _UNetFunction.apply(self, x, n_out, *params)
+            else:
+                self._engine.begin_step()
+                feats = self._native_forward(x, None, only_full_res=not want_ds)
+                outs = tuple(f.as_ncdhw() for f in feats)
+            return list(outs) if want_ds else outs[0]
+        if self._native_ok and not x.is_cuda:
+            raise L.Mtb200Error("ResidualUNet (MultiTalent configuration) runs on the native CUDA path only; got a %s "
                                 "tensor. There is no CPU fallback." % x.device)
         return self.decoder(self.encoder(x))
 

@@ -115,13 +115,18 @@ class SegmentationNetwork(NeuralNetwork):
     def native_dtype(self):
         raise NotImplementedError
 
-    def _require_sigmoid(self):
-        """The aggregation kernel applies the MultiTalent inference non-linearity itself (sigmoid, MT:43-46).  A network
-        with another `inference_apply_nonlin` (softmax of the single-task trainers) must not be aggregated silently
-        with the wrong function."""
-        if not isinstance(self.inference_apply_nonlin, nn.Sigmoid):
-            raise NotImplementedError("the native sliding-window predictor fuses sigmoid into its aggregation kernel; "
-                                      "inference_apply_nonlin=%r is not supported" % (self.inference_apply_nonlin,))
+    def _nonlin_mode(self) -> int:
+        """The aggregation kernel applies the inference non-linearity itself: 1 = sigmoid (MultiTalent, MT:43-46),
+        2 = softmax over the channels (`softmax_helper` of the single-task / fine-tuning trainers, nnUNetTrainerV2.py:162).
+        Anything else must not be aggregated silently with the wrong function."""
+        f = self.inference_apply_nonlin
+        if isinstance(f, nn.Sigmoid):
+            return 1
+        if (isinstance(f, nn.Softmax) and f.dim == 1) or getattr(f, "__name__", "") == "softmax_helper":
+            return 2
+        raise NotImplementedError("the native sliding-window predictor fuses the inference non-linearity into its "
+                                  "aggregation kernel (sigmoid or channel softmax); inference_apply_nonlin=%r is not "
+                                  "supported" % (f,))
 
     # ---- reference API ----------------------------------------------------------------------------------------------
     def predict_3D(self, x: np.ndarray, do_mirroring: bool, mirror_axes: Tuple[int, ...] = (0, 1, 2),
@@ -150,7 +155,7 @@ class SegmentationNetwork(NeuralNetwork):
             raise RuntimeError("the native predictor implements the 3D-conv path only (3d_fullres)")
         if region_vec is not None:
             raise NotImplementedError("region_vec conditioning is not part of the MultiTalent 3d_fullres path")
-        self._require_sigmoid()
+        self._nonlin_mode()
         with torch.no_grad():
             if use_sliding_window:
                 return self._internal_predict_3D_3Dconv_tiled(x, step_size, do_mirroring, mirror_axes, patch_size,
@@ -226,6 +231,7 @@ class SegmentationNetwork(NeuralNetwork):
         acc = torch.zeros((C, X, Y, Z), dtype=torch.float32, device=dev)
         nb = torch.zeros((X, Y, Z), dtype=torch.float32, device=dev)
         mirrors, n_results = self._mirror_list(do_mirroring, mirror_axes)
+        nonlin = self._nonlin_mode()
         dt = self.native_dtype()
         cin_p = self.native_input_channels_padded()
         pd, ph, pw = patch_size
@@ -246,7 +252,7 @@ class SegmentationNetwork(NeuralNetwork):
             lstride = pd * ph * pw * logits.ldc * esize
             for b, (sx, sy, sz, mi, dims) in enumerate(chunk):
                 L.call("mtb200_sw_aggregate", C_void(logits.ptr() + b * lstride), L.dtype_enum(dt), logits.ldc, C, pd, ph,
-                       pw, _flip_bits(dims), L.ptr(gauss), 1.0 / n_results, 1, L.ptr(acc), L.ptr(nb) if mi == 0 else None,
+                       pw, _flip_bits(dims), L.ptr(gauss), 1.0 / n_results, nonlin, L.ptr(acc), L.ptr(nb) if mi == 0 else None,
                        X, Y, Z, sx, sy, sz, st)
         # undo the padding (neural_network.py:397-402) -- crop BEFORE normalising, as the reference does
         sl = tuple([slice(0, C)] + list(slicer[1:]))
@@ -296,7 +302,7 @@ class SegmentationNetwork(NeuralNetwork):
         Returns a CUDA fp32 tensor [1, C, X, Y, Z] like the reference."""
         assert len(x.shape) == 5, 'x must be (b, c, x, y, z)'
         assert x.shape[0] == 1, "the reference calls this with one tile at a time"
-        self._require_sigmoid()
+        nonlin = self._nonlin_mode()
         dev = next(self.parameters()).device
         xt = torch.as_tensor(x, dtype=torch.float32, device=dev)[0].contiguous()
         Cin, X, Y, Z = xt.shape
@@ -314,5 +320,5 @@ class SegmentationNetwork(NeuralNetwork):
                    cin_p, st)
             logits = self.native_logits(Feat(tile, 0, Cin, cin_p))
             L.call("mtb200_sw_aggregate", logits.ptr(), L.dtype_enum(dt), logits.ldc, C, X, Y, Z, fb, L.ptr(g),
-                   1.0 / n_results, 1, L.ptr(acc), None, X, Y, Z, 0, 0, 0, st)
+                   1.0 / n_results, nonlin, L.ptr(acc), None, X, Y, Z, 0, 0, 0, st)
         return acc[None]

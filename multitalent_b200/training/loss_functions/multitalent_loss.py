@@ -62,7 +62,7 @@ def _as_ndhwc(t: torch.Tensor, dtype):
 
 class _MultiTalentLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, valid_mask, weights, group, targets, *logits):
+    def forward(ctx, valid_mask, weights, group, targets, hard_out, *logits):
         dev = logits[0].device
         world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         pos = _pos_mask(dev)
@@ -81,8 +81,15 @@ class _MultiTalentLossFn(torch.autograd.Function):
             tgt = tgt.detach().float().contiguous()
             nvox = z.shape[2] * z.shape[3] * z.shape[4]
             s = torch.zeros((B, C8, 4), dtype=torch.float64, device=dev)
+            hard = None
+            if hard_out is not None and i == 0:  # online evaluation reads the highest-resolution output (MT:373-374)
+                hard = torch.zeros((B, C8, 2), dtype=torch.float64, device=dev)
             L.call("mtb200_mt_loss_stats", L.ptr(zv), L.dtype_enum(dt), ldc, C8, L.ptr(tgt), B, nvox, L.ptr(valid_mask),
-                   L.ptr(pos), NUM_LABELS, L.ptr(s), st)
+                   L.ptr(pos), NUM_LABELS, L.ptr(s), L.ptr(hard), st)
+            if hard is not None:
+                tp = hard[:, :Cc, 0]
+                hard_out.update(tp=tp.float(), fp=(hard[:, :Cc, 1] - tp).float(), fn=(s[:, :Cc, 3] - tp).float(),
+                                logits=logits[0])
             views[i] = (zv, ldc, dt, tgt, nvox)
             stats[i] = s
         pooled = {i: None for i in active}
@@ -119,12 +126,12 @@ class _MultiTalentLossFn(torch.autograd.Function):
                    NUM_LABELS, L.ptr(ctx.coefs[i]), L.ptr(gs), L.ptr(dz), ldc, st)
             grads[i] = dz.permute(0, 4, 1, 2, 3)[:, :Cc]
         for i in range(ctx.n):
-            if grads[i] is None and ctx.needs_input_grad[4 + i]:
+            if grads[i] is None and ctx.needs_input_grad[5 + i]:
                 B, Cc, D, H, W = ctx.shapes[i]
                 Cp = pad_channels(Cc)
                 grads[i] = torch.zeros((B, D, H, W, Cp), dtype=ctx.views[ctx.active[0]][2],
                                        device=g_loss.device).permute(0, 4, 1, 2, 3)[:, :Cc]
-        return (None, None, None, None) + tuple(grads)
+        return (None, None, None, None, None) + tuple(grads)
 
 
 _VALID_MASK_CACHE = {}
@@ -145,13 +152,15 @@ def valid_mask_tensor(valid_regions: Sequence[Sequence[str]], device) -> torch.T
     return t
 
 
-def multitalent_loss(outputs, targets, valid_regions, ds_loss_weights, group=None):
+def multitalent_loss(outputs, targets, valid_regions, ds_loss_weights, group=None, hard_out=None):
     """(total_loss, total_ce, total_dc) as 0-dim CUDA tensors; `total_loss` is differentiable w.r.t. `outputs`.
-    Only d(total_loss) is propagated (the trainer calls `l.backward()`; ce/dc are reporting values, MT:370)."""
+    Only d(total_loss) is propagated (the trainer calls `l.backward()`; ce/dc are reporting values, MT:370).
+    `hard_out` (a dict, optional): filled with the hard tp / fp / fn [B, 47] of the highest-resolution output (the
+    counts `run_online_evaluation` needs, MT:372-397) computed inside the loss's own statistics pass."""
     if not isinstance(outputs, (tuple, list)):
         outputs, targets = (outputs,), (targets,) if not isinstance(targets, (tuple, list)) else targets
     if not outputs[0].is_cuda:
         raise L.Mtb200Error("multitalent_loss runs on the native CUDA path only; logits are on %s" % outputs[0].device)
     vm = valid_regions if torch.is_tensor(valid_regions) else valid_mask_tensor(valid_regions, outputs[0].device)
     weights = [float(w) for w in ds_loss_weights][:len(outputs)]
-    return _MultiTalentLossFn.apply(vm, weights, group, list(targets), *outputs)
+    return _MultiTalentLossFn.apply(vm, weights, group, list(targets), hard_out, *outputs)

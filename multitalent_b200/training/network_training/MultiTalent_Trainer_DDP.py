@@ -32,6 +32,7 @@ from ...network_architecture.generic_UNet import Generic_UNet, InitWeights_He
 from ...plans import default_plans
 from ..loss_functions.multitalent_loss import multitalent_loss
 from ..online_evaluation import OnlineEvaluationMixin
+from ..validation import ValidationMixin
 
 
 def poly_lr(epoch, max_epochs, initial_lr, exponent=0.9):
@@ -151,7 +152,7 @@ class DeviceGradScaler:
         self.state[1] = float(sd.get("_growth_tracker", 0))
 
 
-class MultiTalent_trainer_ddp(OnlineEvaluationMixin):
+class MultiTalent_trainer_ddp(OnlineEvaluationMixin, ValidationMixin):
     def __init__(self, plans_file, fold, local_rank, output_folder=None, dataset_directory=None, batch_dice=True,
                  stage=None, unpack_data=True, deterministic=True, distribute_batch_size=False, fp16=False,
                  native_dtype=None, flat_optimizer=True, init_distributed=True):
@@ -175,6 +176,7 @@ class MultiTalent_trainer_ddp(OnlineEvaluationMixin):
         self.was_initialized = False
         self.plans = None
         self.network = self.optimizer = self.arena = self.amp_grad_scaler = None
+        self.dataset_val = None
         self.ds_loss_weights = None
         self.loss_scale = 1.0  # optional STATIC factor on top (experiments); the dynamic scaler is `amp_grad_scaler`
         # network_trainer.py:71-93 bookkeeping that the checkpoint format carries ('plot_stuff', 'best_stuff')
@@ -300,8 +302,12 @@ class MultiTalent_trainer_ddp(OnlineEvaluationMixin):
 
     # ---- the hot path ----------------------------------------------------------------------------------------------
     def compute_loss(self, output, target, valid_regions):
-        """MT:544-623 -> (total_loss, total_ce, total_dc)."""
-        return multitalent_loss(output, target, valid_regions, self.ds_loss_weights)
+        """MT:544-623 -> (total_loss, total_ce, total_dc).  When the step will be followed by `run_online_evaluation`
+        (`_want_hard_stats`), the statistics pass also counts the hard tp / fp / fn of the full-resolution output."""
+        hard = {} if getattr(self, "_want_hard_stats", False) else None
+        res = multitalent_loss(output, target, valid_regions, self.ds_loss_weights, hard_out=hard)
+        self._hard_stats = hard
+        return res
 
     def _stage_batch(self, data_dict):
         """Start the host->device copies of one batch on the copy stream (pinned host memory: asynchronous).  Returns
@@ -377,7 +383,9 @@ class MultiTalent_trainer_ddp(OnlineEvaluationMixin):
             output = self.network(data)
             if target_ready is not None:
                 torch.cuda.current_stream().wait_event(target_ready)
+            self._want_hard_stats = bool(keep_output)
             l, ce, dc = self.compute_loss(output, target, valid_regions)
+            self._want_hard_stats = False
             if keep_output:  # run_online_evaluation reads the highest-resolution logits after the step (MT:367-368)
                 self._last_output = tuple(o.detach() for o in output)
             if do_backprop:

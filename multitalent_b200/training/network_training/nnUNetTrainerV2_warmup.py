@@ -136,9 +136,9 @@ class nnUNetTrainerV2_warmupsegheads(object):
     def initialize_optimizer_and_scheduler(self, seg_heads_only=False):
         """nnUNetTrainerV2_warmup.py:122-134."""
         assert self.network is not None, "self.initialize_network must be called first"
-        trunk = [p for n, p in self.network.named_parameters() if not n.startswith("seg_outputs.")]
+        trunk = [p for n, p in self.network.named_parameters() if not n.startswith(self.head_prefix)]
         if seg_heads_only:
-            self.optimizer = torch.optim.AdamW(self.network.seg_outputs.parameters(), 3e-3,
+            self.optimizer = torch.optim.AdamW(self.head_module().parameters(), 3e-3,
                                                weight_decay=self.weight_decay, amsgrad=True)
             if self.freeze_trunk_during_head_warmup:
                 for p in trunk:
@@ -155,6 +155,12 @@ class nnUNetTrainerV2_warmupsegheads(object):
         if getattr(self, "amp_grad_scaler", None) is None:
             self.amp_grad_scaler = (torch.amp.GradScaler("cuda")
                                     if self.native_dtype == torch.float16 and torch.cuda.is_available() else None)
+
+    head_prefix = "seg_outputs."
+
+    def head_module(self):
+        """The segmentation heads the first phase trains (nnUNetTrainerV2_warmup.py:123)."""
+        return self.network.seg_outputs
 
     def maybe_update_lr(self, epoch=None):
         """:87-112 (the reference's training loop calls it without an argument: `self.epoch` decides)."""
@@ -209,16 +215,15 @@ class nnUNetTrainerV2_warmupsegheads(object):
                                                          use_sliding_window=True, step_size=0.5, use_gaussian=True,
                                                          pad_border_mode='constant', pad_kwargs=None, all_in_gpu=False,
                                                          verbose=True, mixed_precision=True):
-        """nnUNetTrainerV2.py:198-217.  NOTE: the native predictor's aggregation kernel implements the MultiTalent sigmoid
-        only; for this softmax network `predict_3D` raises NotImplementedError (softmax aggregation is the next step of
-        this row) instead of aggregating with the wrong function."""
+        """nnUNetTrainerV2.py:198-217: deep supervision off, eval mode, tiled prediction with the softmax inference
+        non-linearity fused into the aggregation kernel (`mtb200_sw_aggregate`, nonlin = 2), argmax segmentation."""
         if pad_border_mode == 'constant' and pad_kwargs is None:
             pad_kwargs = {'constant_values': 0}
         if do_mirroring and mirror_axes is None:
             mirror_axes = (0, 1, 2)
         net = self.network
-        ds, mode = net.do_ds, net.training
-        net.do_ds = False
+        ds, mode = self._get_ds(), net.training
+        self._set_ds(False)
         net.eval()
         try:
             return net.predict_3D(data, do_mirroring=do_mirroring, mirror_axes=mirror_axes or (),
@@ -228,4 +233,50 @@ class nnUNetTrainerV2_warmupsegheads(object):
                                   all_in_gpu=all_in_gpu, verbose=verbose, mixed_precision=mixed_precision)
         finally:
             net.train(mode)
-            net.do_ds = ds
+            self._set_ds(ds)
+
+    def _get_ds(self):
+        return self.network.do_ds
+
+    def _set_ds(self, v):
+        self.network.do_ds = v
+
+
+class nnUNetTrainerV2_warmupsegheads_resenc(nnUNetTrainerV2_warmupsegheads):
+    """nnUNetTrainerV2_warmup.py:441-560: the same three-phase schedule on the residual-encoder network (`FabiansUNet`
+    built from the plan's `num_blocks_encoder` / `num_blocks_decoder`, softmax inference, `init_last_bn_before_add_to_0`);
+    the heads are `decoder.deep_supervision_outputs`; deep-supervision scales skip the first (unstrided) pooling entry
+    (:483-489); prediction toggles `decoder.deep_supervision` (:507-528)."""
+    head_prefix = "decoder.deep_supervision_outputs."
+
+    def head_module(self):
+        return self.network.decoder.deep_supervision_outputs
+
+    def initialize(self, training=True, force_load_plans=False):
+        if self.was_initialized:
+            return
+        super().initialize(training, force_load_plans)
+        # :483-489 -- recompute scales / loss weights for the resenc pooling list (first entry = unstrided stem stage)
+        self.deep_supervision_scales = [[1, 1, 1]] + list(
+            list(i) for i in 1 / np.cumprod(np.vstack(self.net_num_pool_op_kernel_sizes[1:]), axis=0))[:-1]
+
+    def initialize_network(self):
+        """:451-468."""
+        from ...network_architecture.generic_modular_residual_UNet import (FabiansUNet, get_default_network_config,
+                                                                            init_last_bn_before_add_to_0)
+        cfg = get_default_network_config(3, None, norm_type="in")
+        sp = self.plans['plans_per_stage'][self.stage]
+        self.network = FabiansUNet(self.num_input_channels, self.base_num_features, sp['num_blocks_encoder'], 2,
+                                   sp['pool_op_kernel_sizes'], sp['conv_kernel_sizes'], cfg, self.num_classes,
+                                   sp['num_blocks_decoder'], True, False, 320, InitWeights_He(1e-2),
+                                   native_dtype=self.native_dtype)
+        if torch.cuda.is_available():
+            self.network.cuda()
+        self.network.inference_apply_nonlin = softmax_helper
+        self.network.apply(init_last_bn_before_add_to_0)
+
+    def _get_ds(self):
+        return self.network.decoder.deep_supervision
+
+    def _set_ds(self, v):
+        self.network.decoder.deep_supervision = v

@@ -4,10 +4,12 @@
 
 Per sample b and supervised region r (channel j_r): prediction = sigmoid(z) > 0.5 (i.e. z > 0), ground truth =
 OR_{l in regions[r]} (target == l); tp / fp / fn counted over the voxels of the highest-resolution output; channels the
-sample's dataset does not label stay 0.  The reference walks a Python double loop with one masked sum per (b, r); here
-the region membership of every voxel is ONE table lookup (`label -> 47 booleans`) and the three counts are boolean
-reductions -- plain torch ops on whatever device the tensors live on (validation is not on the hot path; no kernel).
-The counts are exact integers, so the result equals the reference's float32 sums below 2^24 voxels per (b, region)."""
+sample's dataset does not label stay 0.  The reference walks a Python double loop with one masked sum per (b, r).  Here,
+inside a trainer step, the three counts come out of the loss's own statistics kernel (`mtb200_mt_loss_stats`, `hard`
+output: the validation iteration reads the logits once for loss AND evaluation); called stand-alone, the region membership
+of every voxel is ONE table lookup (`label -> 47 booleans`) and the counts are boolean reductions in plain torch ops on
+whatever device the tensors live on.  The counts are exact integers, so the result equals the reference's float32 sums
+below 2^24 voxels per (b, region)."""
 from typing import Sequence
 
 import numpy as np
@@ -75,7 +77,12 @@ class OnlineEvaluationMixin:
         if not hasattr(self, "online_eval_tp"):
             self._online_eval_reset()
             self.all_val_eval_metrics = getattr(self, "all_val_eval_metrics", [])
-        tp, fp, fn = hard_tp_fp_fn(output[0], target[0], valid_regions)
+        fused = getattr(self, "_hard_stats", None)
+        if fused and fused.get("logits") is not None and fused["logits"].data_ptr() == output[0].data_ptr():
+            tp, fp, fn = fused["tp"], fused["fp"], fused["fn"]   # counted by the loss kernel of this very step
+        else:
+            tp, fp, fn = hard_tp_fp_fn(output[0], target[0], valid_regions)
+        self._hard_stats = None
         tp_hard = _gather_ranks(tp).cpu().numpy()
         fp_hard = _gather_ranks(fp).cpu().numpy()
         fn_hard = _gather_ranks(fn).cpu().numpy()

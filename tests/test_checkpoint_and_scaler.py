@@ -84,7 +84,8 @@ def test_checkpoint_round_trip_resumes_identically(tmp_path):
     assert info['name'] == 'MultiTalent_trainer_ddp' and len(info['init']) == 11
     b = make()
     with torch.no_grad():
-        b.arena.flat.add_(0.5)                         # make sure the load really restores everything
+        for prm in b.network.parameters():             # make sure the load really restores everything
+            prm.add_(0.5)
     b.load_checkpoint(f, train=True)
     assert b.epoch == 8 and b.lr == pytest.approx(1e-2 * (1 - 8 / 1000) ** 0.9)
     assert torch.equal(b.arena.flat, a.arena.flat) and torch.equal(b.arena.mom, a.arena.mom) and not b.arena.first

@@ -92,3 +92,40 @@ def test_matches_the_reference_methods():
     # reference quirk kept: the accumulators are [B, 47] per iteration, so the "per class" list has one row per batch slot
     assert len(per_class) == 3 and all(len(r) == 47 for r in per_class)
     assert mine.online_eval_tp == [] and ref.online_eval_tp == []
+
+
+@pytest.mark.gpu
+def test_fused_hard_counts_from_the_loss_kernel_equal_the_standalone_evaluation(monkeypatch):
+    """Inside a trainer step the hard tp / fp / fn come out of `mtb200_mt_loss_stats` (the validation iteration reads the
+    logits once for loss and evaluation): identical to the stand-alone boolean reductions, fp32 and bf16 storage, and
+    the stand-alone pass is really not run."""
+    import multitalent_b200.training.online_evaluation as OE
+    from multitalent_b200.plans import default_plans
+    from multitalent_b200.synthetic import synthetic_batch
+    from multitalent_b200.training.network_training.MultiTalent_Trainer_DDP import MultiTalent_trainer_ddp
+    patch = (16, 32, 32)
+    plans = default_plans(patch_size=patch, batch_size=3)
+    plans['plans_per_stage'][1]['pool_op_kernel_sizes'] = [[2, 2, 2], [2, 2, 2], [1, 2, 2]]
+    plans['plans_per_stage'][1]['conv_kernel_sizes'] = [[3, 3, 3]] * 4
+    for dtype in (torch.float32, torch.bfloat16):
+        tr = MultiTalent_trainer_ddp(plans, 0, 0, init_distributed=False, native_dtype=dtype)
+        torch.manual_seed(0)
+        tr.initialize(True)
+        batch = synthetic_batch(patch, 3, 2, tr.deep_supervision_scales)
+        valid = [p['valid_regions'] for p in batch['properties']]
+        # stand-alone counts on the same logits
+        with torch.no_grad():
+            out = tr.network(torch.from_numpy(batch['data']).cuda())
+        tp, fp, fn = OE.hard_tp_fp_fn(out[0], torch.from_numpy(batch['target'][0]).cuda(), valid)
+        assert float(tp.sum()) + float(fp.sum()) > 0 and float(fn.sum()) + float(tp.sum()) > 0
+
+        def boom(*a, **k):
+            raise AssertionError("the stand-alone evaluation pass must not run inside a trainer step")
+        monkeypatch.setattr(OE, "hard_tp_fp_fn", boom)
+        tr.run_iteration(iter([batch]), do_backprop=False, run_online_evaluation=True)
+        monkeypatch.undo()
+        assert np.array_equal(np.array(tr.online_eval_tp[0]), tp.sum(0).cpu().numpy())
+        assert np.array_equal(np.array(tr.online_eval_fp[0]), fp.sum(0).cpu().numpy())
+        assert np.array_equal(np.array(tr.online_eval_fn[0]), fn.sum(0).cpu().numpy())
+        per_class = tr.finish_online_evaluation()
+        assert len(per_class) == 47 and len(tr.all_val_eval_metrics) >= 1
