@@ -258,6 +258,16 @@ int mtb200_pack_weights_batched(const mtb200_pack_desc* descs, int32_t n, int32_
 int mtb200_unpack_wgrad(const float* dw, int32_t Cout, int32_t Cin, int32_t ntap, int32_t transposed, int32_t Cout_p,
                         int32_t Cin_p, int32_t split, int32_t split_p, float scale, int32_t accumulate, float* grad,
                         void* stream);
+/* The same for every layer of a step in ONE launch: grad += dw per descriptor.  Layer i owns blocks
+ * [blk_begin_i, blk_begin_{i+1}) of MTB200_UNPACK_CHUNK reference-layout elements each; `descs` lives in device memory. */
+#define MTB200_UNPACK_CHUNK 4096
+typedef struct {
+  const float* dw; /* packed [ntap][Cout_p][Cin_p] fp32 */
+  float* grad;     /* reference layout ([Cout][Cin][taps] or, transposed, [Cin][Cout][taps]) */
+  int32_t Cout, Cin, ntap, transposed, Cout_p, Cin_p, split, split_p;
+  int32_t blk_begin, reserved;
+} mtb200_unpack_desc;
+int mtb200_unpack_wgrad_batched(const mtb200_unpack_desc* descs, int32_t n, int32_t total_blocks, void* stream);
 /* NCDHW fp32 [B][C][nvox] <-> NDHWC `dtype` [B][nvox][ldc] (+coff); padded channels are written as 0 */
 int mtb200_ncdhw_to_ndhwc(const float* src, int32_t B, int32_t C, int64_t nvox, void* dst, int32_t dtype, int32_t ldc,
                           int32_t coff, int32_t Cp, void* stream);

@@ -75,6 +75,16 @@ class PackDesc(C.Structure):
     ]
 
 
+class UnpackDesc(C.Structure):
+    _fields_ = [
+        ("dw", C.c_void_p), ("grad", C.c_void_p),
+        ("Cout", C.c_int32), ("Cin", C.c_int32), ("ntap", C.c_int32), ("transposed", C.c_int32),
+        ("Cout_p", C.c_int32), ("Cin_p", C.c_int32), ("split", C.c_int32), ("split_p", C.c_int32),
+        ("blk_begin", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+UNPACK_CHUNK = 4096
 _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
 # name -> argtypes; every symbol include/mtb200.h declares (tests/test_abi.py checks the two lists agree)
@@ -112,6 +122,7 @@ SIGNATURES = {
     "mtb200_loss_scale_update": [_vp, _vp, _f32, _f32, _i32, _vp],
     "mtb200_pack_weights": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "mtb200_pack_weights_batched": [_vp, _i32, _i32, _i32, _vp],
+    "mtb200_unpack_wgrad_batched": [_vp, _i32, _i32, _vp],
     "mtb200_unpack_wgrad": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp],
     "mtb200_ncdhw_to_ndhwc": [_vp, _i32, _i32, _i64, _vp, _i32, _i32, _i32, _i32, _vp],
     "mtb200_ndhwc_to_ncdhw": [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _vp],

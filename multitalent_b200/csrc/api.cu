@@ -81,6 +81,7 @@ int loss_scale_update(const double*, float*, float, float, int, cudaStream_t);
 int pack_weights(const float*, int, int, int, int, int, void*, int, int, int, int, int, cudaStream_t);
 int unpack_wgrad(const float*, int, int, int, int, int, int, int, int, float, int, float*, cudaStream_t);
 int pack_weights_batched(const void*, int, int, int, cudaStream_t);
+int unpack_wgrad_batched(const void*, int, int, cudaStream_t);
 int ncdhw_to_ndhwc(const float*, int, int, long long, void*, int, int, int, int, cudaStream_t);
 int ndhwc_to_ncdhw(const void*, int, int, int, int, int, long long, float*, cudaStream_t);
 
@@ -294,6 +295,11 @@ int mtb200_unpack_wgrad(const float* dw, int32_t Cout, int32_t Cin, int32_t ntap
   MTB_REQUIRE(dw && grad, "unpack_wgrad: null pointer");
   return unpack_wgrad(dw, Cout, Cin, ntap, transposed, Cout_p, Cin_p, split, split_p, scale, accumulate, grad,
                       STREAM(stream));
+}
+
+int mtb200_unpack_wgrad_batched(const mtb200_unpack_desc* descs, int32_t n, int32_t total_blocks, void* stream) {
+  MTB_REQUIRE(descs || n == 0, "unpack_wgrad_batched: null descriptor table");
+  return unpack_wgrad_batched(descs, n, total_blocks, STREAM(stream));
 }
 
 int mtb200_ncdhw_to_ndhwc(const float* src, int32_t B, int32_t C, int64_t nvox, void* dst, int32_t dtype, int32_t ldc,

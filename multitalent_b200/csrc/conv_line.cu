@@ -15,6 +15,12 @@
 // (dz, dx) of [96 = (dy, co)][Cin] K-major.  Four Q accumulators (96 TMEM columns each) rotate: the MMAs of line h'+1
 // overlap the epilogue of output line h'-1.
 //
+// Narrow maps (36 <= W <= 64, the second U-Net level): an M tile is TWO depth planes (d, d+1) of one 64-wide h-line,
+// interleaved row by row -- the TMA box is taken over (C, D = 2, W = 66) with D as the faster shared-memory dimension
+// (tensor-map dimensions may be listed in any order), so tile row = 2 * w + plane, a dx tap is a TWO-row shift of the
+// descriptor start, and everything else (dz = another box one plane further, dy merged into N, Q ring, lane-local
+// epilogue) is unchanged: thread m of the epilogue owns voxel (w = m / 2, plane d + m % 2).
+//
 // Warp roles: 0 = line producer (TMA), 1 = TMEM owner + MMA issuer, 2 = weight loader, 3.. = EW epilogue warps
 // (EW / 4 warps per TMEM lane quarter, LN_CPT of the 32 output channels each).
 #include "umma.cuh"
@@ -49,6 +55,7 @@ struct LineParams {
   int grp_dzslot[9], grp_dxrow[9];    // which staged line, row offset (dx + 1)
   int grp_widx[9][3];            // weight slice of (group, dy = j - 1)
   int nhr, hlen, ntw;
+  int P, wt, dgroups;            // planes per M tile (1 or 2), w voxels per tile (128 / P), D / P
   int units;                     // work units walked by the persistent CTAs
   int accumulate, is_f16;
   int dbg;                       // experiments only (MTB200_LINE_DBG): bit 0 = read one accumulator block per line
@@ -86,11 +93,11 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
     Unit t;
     const int hr = u % p.nhr; u /= p.nhr;
     const int twi = u % p.ntw; u /= p.ntw;
-    t.d = u % p.D;
-    t.b = u / p.D;
+    t.d = (u % p.dgroups) * p.P;
+    t.b = u / p.dgroups;
     t.hs = hr * p.hlen;
     t.he = min(p.H, t.hs + p.hlen);
-    t.w0 = twi * 128;
+    t.w0 = twi * p.wt;
     t.hfirst = max(t.hs - 1, 0);
     t.nsteps = min(t.he, p.H - 1) - t.hfirst + 1;
     return t;
@@ -121,9 +128,13 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
           mbar_expect_tx(&st_full[slot], (uint32_t)p.stage_tx);
           uint8_t* dst = st_base + (size_t)slot * p.stage_bytes;
           for (int z = 0; z < p.ndz; ++z)
-            for (int c = 0; c < p.nchunk; ++c)
-              tma_load_5d(dst + (size_t)z * p.line_bytes + (size_t)c * p.sub_bytes, &p.a_map, &st_full[slot], c * p.kcw,
-                          t.w0 - 1, t.hfirst + s, t.d + p.dz0 + z, t.b);
+            for (int c = 0; c < p.nchunk; ++c) {
+              uint8_t* sub = dst + (size_t)z * p.line_bytes + (size_t)c * p.sub_bytes;
+              if (p.P == 1)  // map dims (C, W, H, D, B)
+                tma_load_5d(sub, &p.a_map, &st_full[slot], c * p.kcw, t.w0 - 1, t.hfirst + s, t.d + p.dz0 + z, t.b);
+              else           // map dims (C, D, W, H, B): planes d+dz, d+dz+1 interleaved row by row
+                tma_load_5d(sub, &p.a_map, &st_full[slot], c * p.kcw, t.d + p.dz0 + z, t.w0 - 1, t.hfirst + s, t.b);
+            }
         }
         __syncwarp();
       }
@@ -154,7 +165,7 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
     uint32_t a_goff[9], b_goff[9];
 #pragma unroll
     for (int g = 0; g < 9; ++g) {
-      a_goff[g] = (uint32_t)p.grp_dzslot[g] * line16 + (uint32_t)(p.grp_dxrow[g] * (ROWB / 16));
+      a_goff[g] = (uint32_t)p.grp_dzslot[g] * line16 + (uint32_t)(p.grp_dxrow[g] * p.P * (ROWB / 16));
       b_goff[g] = w16 + (uint32_t)g * wgroup16;
     }
     mbar_wait(&w_full, 0);
@@ -199,8 +210,9 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
     uint32_t gs0 = 0;  // global step index of the current unit's first line
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
       const Unit t = decode(u);
-      const int b = t.b, d = t.d, hs = t.hs, he = t.he, hfirst = t.hfirst;
-      const int ww = t.w0 + q * 32 + lane;
+      const int m = q * 32 + lane;  // tile row = TMEM lane
+      const int b = t.b, d = t.d + (p.P == 2 ? (m & 1) : 0), hs = t.hs, he = t.he, hfirst = t.hfirst;
+      const int ww = t.w0 + (p.P == 2 ? (m >> 1) : m);
       const bool wvalid = ww < p.W;
       float csum[LN_CPT], csq[LN_CPT];
 #pragma unroll
@@ -321,7 +333,12 @@ int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s) {
     return MTB200_ERR_UNSUPPORTED;
   if (p.Cin != 16 && p.Cin != 32 && p.Cin != 64) return MTB200_ERR_UNSUPPORTED;  // one chunk (nchunk == 1)
   if (p.Cout % LN_BN) return MTB200_ERR_UNSUPPORTED;
-  if (p.Wo < 72 || p.Ho < 4) return MTB200_ERR_UNSUPPORTED;  // an M tile is one h-line of 128 w voxels
+  // an M tile is one h-line of 128 w voxels, or (narrow maps) two depth planes of one 64-wide h-line
+  static int pair_ok = -1;  // MTB200_LINE_PAIR=0 disables the two-plane variant; cleared if its tensor map is refused
+  if (pair_ok < 0) { const char* e = getenv("MTB200_LINE_PAIR"); pair_ok = (e && atoi(e) == 0) ? 0 : 1; }
+  const int P = p.Wo >= 72 ? 1 : 2;
+  if (p.Ho < 4) return MTB200_ERR_UNSUPPORTED;
+  if (P == 2 && (!pair_ok || p.Wo < 36 || p.Wo > 64 || (p.Do & 1) || p.Cin < 32)) return MTB200_ERR_UNSUPPORTED;
 
   static thread_local LineParams q;
   memset(&q, 0, sizeof(q));
@@ -356,10 +373,14 @@ int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s) {
   q.kcw = p.Cin < 64 ? p.Cin : 64;
   q.nchunk = p.Cin / q.kcw;
   const int rowb = q.kcw * 2;
-  q.sub_bytes = ln_align1k((long long)LN_WROWS * rowb);
+  q.P = P;
+  q.wt = 128 / P;
+  q.dgroups = p.Do / P;
+  const int box_rows = (q.wt + 2) * P;  // 130, or 66 w positions x 2 planes = 132
+  q.sub_bytes = ln_align1k((long long)box_rows * rowb);
   q.line_bytes = q.sub_bytes * q.nchunk;
   q.stage_bytes = q.line_bytes * q.ndz;
-  q.stage_tx = q.ndz * q.nchunk * LN_WROWS * rowb;
+  q.stage_tx = q.ndz * q.nchunk * box_rows * rowb;
   q.wchunk_bytes = ln_align1k(3LL * LN_BN * rowb);
   q.wgroup_bytes = q.wchunk_bytes * q.nchunk;
   const int wbytes = q.wgroup_bytes * q.ngroups;
@@ -367,13 +388,24 @@ int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s) {
   q.stages = min(LN_MAX_STAGES, (smem_budget - wbytes) / q.stage_bytes);
   if (q.stages < 2) return MTB200_ERR_UNSUPPORTED;
 
-  {
+  if (P == 1) {
     cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.Di, (cuuint64_t)p.B};
     cuuint64_t strides[4] = {(cuuint64_t)p.in_ldc * 2, (cuuint64_t)p.Wi * p.in_ldc * 2,
                              (cuuint64_t)p.Hi * p.Wi * p.in_ldc * 2, (cuuint64_t)p.Di * p.Hi * p.Wi * p.in_ldc * 2};
     cuuint32_t box[5] = {(cuuint32_t)q.kcw, (cuuint32_t)LN_WROWS, 1, 1, 1};
     if (!umma_encode_map(&q.a_map, p.dtype, 5, (uint8_t*)p.in + (size_t)p.in_coff * 2, dims, strides, box, rowb))
       return MTB200_ERR_CUDA;
+  } else {
+    // dimensions listed as (C, D, W, H, B): the box [kcw][2 planes][wt + 2] lands in shared memory with the plane index
+    // varying faster than w, i.e. tile row = 2 * w + plane (strides need not be sorted; out-of-volume = zero fill)
+    cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Di, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.B};
+    cuuint64_t strides[4] = {(cuuint64_t)p.Hi * p.Wi * p.in_ldc * 2, (cuuint64_t)p.in_ldc * 2,
+                             (cuuint64_t)p.Wi * p.in_ldc * 2, (cuuint64_t)p.Di * p.Hi * p.Wi * p.in_ldc * 2};
+    cuuint32_t box[5] = {(cuuint32_t)q.kcw, 2, (cuuint32_t)(q.wt + 2), 1, 1};
+    if (!umma_encode_map(&q.a_map, p.dtype, 5, (uint8_t*)p.in + (size_t)p.in_coff * 2, dims, strides, box, rowb)) {
+      pair_ok = 0;  // this driver insists on sorted strides: use the other kernels from now on
+      return MTB200_ERR_UNSUPPORTED;
+    }
   }
   {
     int n_widx = 0;
@@ -389,13 +421,13 @@ int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s) {
   q.accumulate = p.accumulate;
   q.is_f16 = p.dtype == MTB200_F16;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MTB200_LINE_DBG"); dbg = e ? atoi(e) : 0; } q.dbg = dbg; }
-  q.ntw = (p.Wo + 127) / 128;
+  q.ntw = (p.Wo + q.wt - 1) / q.wt;
   const int ny = p.Cout / LN_BN;
   // split H into ranges so that the units divide evenly over the persistent CTAs (one per SM and Cout block); every
   // range recomputes two halo lines
   const int gx_max = max(1, num_sms() / ny);
   {
-    const long long base = (long long)p.B * p.Do * q.ntw;
+    const long long base = (long long)p.B * q.dgroups * q.ntw;
     double best = -1;
     int best_nhr = 1;
     for (int nhr = 1; nhr <= max(1, p.Ho / 8); ++nhr) {
@@ -410,7 +442,7 @@ int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s) {
     q.nhr = best_nhr;
     q.hlen = (p.Ho + q.nhr - 1) / q.nhr;
   }
-  const long long units = (long long)p.B * p.Do * q.ntw * q.nhr;
+  const long long units = (long long)p.B * q.dgroups * q.ntw * q.nhr;
   MTB_REQUIRE(units < (1LL << 31), "conv_line: too many work units");
   q.units = (int)units;
   const int smem = max(116 * 1024, q.stages * q.stage_bytes + wbytes + 1024);  // one CTA per SM (512 TMEM columns each)

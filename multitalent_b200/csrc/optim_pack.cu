@@ -200,6 +200,38 @@ int unpack_wgrad(const float* dw, int Cout, int Cin, int ntap, int transposed, i
   return check_launch("unpack_wgrad");
 }
 
+// ---- every weight gradient of a step in ONE launch ----------------------------------------------------------------------
+// A block owns UNPACK_CHUNK consecutive elements of one layer's reference-layout gradient (descriptor found by binary
+// search on the block index, as in pack_weights_batched): 160 tiny launches per step become one.
+constexpr int UNPACK_CHUNK = 4096;
+
+__global__ void __launch_bounds__(256) unpack_wgrad_batched_kernel(const mtb200_unpack_desc* __restrict__ descs, int n) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (descs[mid].blk_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const mtb200_unpack_desc d = descs[lo];
+  const long long total = (long long)d.Cout * d.Cin * d.ntap;
+  const long long i0 = (long long)((int)blockIdx.x - d.blk_begin) * UNPACK_CHUNK;
+  const long long i1 = min(total, i0 + UNPACK_CHUNK);
+  const int inner = d.transposed ? d.Cout : d.Cin;
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+    const int t = (int)(i % d.ntap);
+    const int a = (int)((i / d.ntap) % inner);
+    const int b = (int)(i / ((long long)d.ntap * inner));
+    const int co = d.transposed ? a : b, ci = d.transposed ? b : a;
+    const int cip = (d.split > 0 && ci >= d.split) ? ci - d.split + d.split_p : ci;
+    d.grad[i] += d.dw[((long long)t * d.Cout_p + co) * d.Cin_p + cip];
+  }
+}
+
+int unpack_wgrad_batched(const void* descs, int n, int total_blocks, cudaStream_t s) {
+  if (n <= 0 || total_blocks <= 0) return MTB200_OK;
+  unpack_wgrad_batched_kernel<<<total_blocks, 256, 0, s>>>(reinterpret_cast<const mtb200_unpack_desc*>(descs), n);
+  return check_launch("unpack_wgrad_batched");
+}
+
 // ---- NCDHW fp32 <-> NDHWC --------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, int C, long long nvox, T* __restrict__ dst, int ldc,

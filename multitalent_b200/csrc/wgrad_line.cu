@@ -215,6 +215,10 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __
 }
 
 static inline int wl_align1k(long long v) { return (int)(((v + 1023) / 1024) * 1024); }
+static int env_int_wl(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 
 // Returns MTB200_ERR_UNSUPPORTED when the problem is outside this kernel's envelope (caller falls back).
 int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
@@ -226,8 +230,10 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   if (p.Cin != 16 && p.Cin % 32 != 0) return MTB200_ERR_UNSUPPORTED;
   // every (Cin chunk, Cout block) pair re-streams both operands from L2: worth it while the pair count is small
   const bool cout48 = p.Cout == 48 && p.Cin <= 32;  // the 47 heads on the widest maps: one column block of 32 + 16
-  if (!cout48 && (p.Cout % WL_BN || (p.Cin / 32) * (p.Cout / WL_BN) > 32)) return MTB200_ERR_UNSUPPORTED;
-  if (p.Wo < 48 || p.Ho < 4) return MTB200_ERR_UNSUPPORTED;  // narrower maps: no gain over the per-tap kernel
+  // MTB200_WLINE_MINW / MTB200_WLINE_MAXPAIRS: envelope knobs for A/B measurements (defaults = what measured fastest)
+  static const int min_w = env_int_wl("MTB200_WLINE_MINW", 32), max_pairs = env_int_wl("MTB200_WLINE_MAXPAIRS", 32);
+  if (!cout48 && (p.Cout % WL_BN || (p.Cin / 32) * (p.Cout / WL_BN) > max_pairs)) return MTB200_ERR_UNSUPPORTED;
+  if (p.Wo < min_w || p.Wo < 16 || p.Ho < 4) return MTB200_ERR_UNSUPPORTED;
   bool all_dy0 = true;
   for (int t = 0; t < p.ntaps; ++t) all_dy0 = all_dy0 && p.tap_off[t][1] == 0;
   if (p.ntaps < 9 && !(p.ntaps == 1 && all_dy0)) return MTB200_ERR_UNSUPPORTED;
@@ -248,7 +254,7 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   q.kcw = p.Cin < 32 ? p.Cin : 32;
   const int nchunk = p.Cin / q.kcw;
   const int rowb = q.kcw * 2;
-  q.wt = p.Wo > 64 ? 128 : 64;
+  q.wt = p.Wo > 64 ? 128 : (p.Wo > 32 ? 64 : (p.Wo > 16 ? 32 : 16));  // K = the voxels of one line, 16 per MMA
   q.nkk = q.wt / 16;
   const int xrows = q.wt + 2;
   q.xline_bytes = wl_align1k((long long)(xrows + 8) * rowb);  // + rows touched by the unused shifted blocks

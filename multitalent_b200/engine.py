@@ -397,6 +397,11 @@ class Engine:
         self.overlap_wgrad = os.environ.get("MTB200_WGRAD_STREAM", "1") != "0"
         self._side = {}
         self._side_used = None
+        # arena mode: the packed fp32 weight gradients of a step are folded into the parameters' gradient slots by ONE
+        # launch at the end of the backward pass (MTB200_UNPACK_BATCHED=0: one launch per layer, as before)
+        self.batch_unpack = os.environ.get("MTB200_UNPACK_BATCHED", "1") != "0"
+        self._pending_unpack = []
+        self._unpack_tables = {}
 
     def begin_step(self):
         """Called at the start of every network forward: re-zero what the previous step took from the pools."""
@@ -637,7 +642,10 @@ class Engine:
     def _finish_wgrad(self, tape, op: ConvOp, dw, dy: Feat, dt, dev, bias_grad_is_zero):
         """Packed fp32 weight gradient -> the parameter's gradient (arena slot or autograd), plus the bias gradient."""
         gw = direct_grad(op.weight)
-        if gw is not None:  # accumulate straight into the arena's gradient slot
+        if gw is not None and self.batch_unpack and gw.is_contiguous():
+            self._pending_unpack.append((op, dw, gw))  # folded in by run_backward's single batched launch
+            tape.direct_done.add(id(op.weight))
+        elif gw is not None:  # accumulate straight into the arena's gradient slot
             L.call("mtb200_unpack_wgrad", L.ptr(dw), op.Cout, op.Cin, op.ntap, int(op.transposed), op.Cout_p, op.Cin_p,
                    op.split, op.split_p, 1.0, 1, L.ptr(gw), L.stream_ptr())
             tape.direct_done.add(id(op.weight))
@@ -718,3 +726,28 @@ class Engine:
             for st in self._side_used:
                 torch.cuda.current_stream().wait_stream(st)
             self._side_used = None
+        self._flush_unpack()
+
+    def _flush_unpack(self):
+        """grad += dw for every layer of this step in one launch.  The descriptor table lives on the device and is cached
+        by the (dw, grad) pointers: the pools hand out the same addresses every step, so there is no per-step H2D copy."""
+        pend, self._pending_unpack = self._pending_unpack, []
+        if not pend:
+            return
+        key = tuple((dw.data_ptr(), gw.data_ptr()) for _, dw, gw in pend)
+        hit = self._unpack_tables.get(key)
+        if hit is None:
+            if len(self._unpack_tables) > 8:
+                self._unpack_tables.clear()
+            descs = (L.UnpackDesc * len(pend))()
+            blk = 0
+            for d, (op, dw, gw) in zip(descs, pend):
+                d.dw, d.grad = dw.data_ptr(), gw.data_ptr()
+                d.Cout, d.Cin, d.ntap, d.transposed = op.Cout, op.Cin, op.ntap, int(op.transposed)
+                d.Cout_p, d.Cin_p, d.split, d.split_p = op.Cout_p, op.Cin_p, op.split, op.split_p
+                d.blk_begin = blk
+                blk += (op.Cout * op.Cin * op.ntap + L.UNPACK_CHUNK - 1) // L.UNPACK_CHUNK
+            table = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(pend[0][1].device)
+            hit = self._unpack_tables[key] = (table, len(pend), blk)
+        table, n, blocks = hit
+        L.call("mtb200_unpack_wgrad_batched", L.ptr(table), n, blocks, L.stream_ptr(), tag="mtb200_unpack_wgrad")

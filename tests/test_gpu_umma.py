@@ -316,6 +316,12 @@ LINE_CASES = [
     (1, 30, (3, 3, 3), (1, 5, 24, 160)),      # Cin_p 16, two w tiles (the second one 32 wide)
     (20, 24, (1, 3, 3), (1, 3, 40, 96)),      # 9 taps, a single staged plane; h split into ranges
     (30, 30, (3, 3, 3), (1, 2, 160, 128)),    # long in h: accumulator / stage ring wrap-around
+    # narrow maps: two depth planes per M tile, interleaved row by row (tile row = 2 w + plane)
+    (60, 60, (3, 3, 3), (1, 6, 12, 64)),      # the level-1 shape: Cin_p 64, two Cout blocks
+    (30, 60, (3, 3, 3), (2, 4, 9, 48)),       # Cin_p 32 (64-byte rows), ragged w (16 masked columns), odd h
+    (60, 30, (3, 3, 3), (1, 8, 10, 56)),      # ragged, several plane pairs
+    (20, 24, (1, 3, 3), (1, 4, 16, 40)),      # 9 taps: a single staged box per step
+    (60, 60, (3, 3, 3), (1, 2, 100, 64)),     # long in h: ring wrap-around with plane pairs
 ]
 
 
@@ -369,6 +375,9 @@ WGRAD_LINE_CASES = [
     (120, 60, (3, 3, 3), (1, 4, 8, 64), 60),     # 4 chunks
     (60, 60, (3, 3, 3), (1, 3, 6, 56), 0),       # ragged 64-wide tile
     (120, 120, (3, 3, 3), (1, 3, 5, 64), 0),     # 4 chunks x 4 Cout blocks
+    (120, 120, (3, 3, 3), (2, 6, 10, 32), 0),    # 32-wide lines (level 2): two K steps per line
+    (240, 120, (3, 3, 3), (1, 5, 8, 32), 120),   # 8 chunks x 4 Cout blocks = 32 pairs, concatenated input
+    (60, 60, (3, 3, 3), (1, 4, 6, 24), 0),       # ragged 32-wide tile
     (30, 47, (1, 1, 1), (1, 4, 10, 128), 0),     # 1x1x1 head: one-line window, Cout 48 = segments of 32 + 16 channels
     (1, 47, (1, 1, 1), (2, 3, 6, 64), 0),        # Cin_p 16, 64-wide lines
     (30, 47, (1, 1, 1), (1, 2, 5, 100), 0),      # ragged
