@@ -68,6 +68,19 @@ typedef struct {
   int32_t tap_off[MTB200_MAX_TAPS][3];
   int32_t tap_widx[MTB200_MAX_TAPS];
   int32_t accumulate;   /* 1: out += result (gradient accumulation into a skip buffer) */
+  /* Optional fused InstanceNorm-backward reduction (data-gradient launches): when `red` is non-NULL and the kernel the
+   * problem is dispatched to supports it (line-streaming and pointwise tcgen05 kernels -- ask mtb200_last_kernel()), the
+   * epilogue treats its FINAL output tile g = d(loss)/d(activation) of the producing layer, whose RAW conv output is
+   * red_y (NDHWC, same dtype / grid as `out`), and accumulates
+   *     red[b][c][0] += sum_v dv,   red[b][c][1] += sum_v dv * xhat,     dv = g * lrelu'(scale*y + shift), xhat = (y-mean)*rstd
+   * with red_xform [B][Cout][4] = {scale, shift, slope, -} and red_meanrstd [B][Cout][2] -- exactly what
+   * mtb200_in_bwd_reduce computes in a separate pass over g and y (InstanceNorm3d + LeakyReLU backward, the autograd of
+   * generic_UNet.py:63-70).  Kernels without support ignore the fields. */
+  const void* red_y;
+  const float* red_xform;
+  const float* red_meanrstd;
+  double* red;
+  int32_t red_ldc, red_coff;
   int32_t impl;         /* 0 = auto, 1 = CUDA-core FFMA kernel, 2 = tcgen05 kernels (fastest applicable of the three),
                            3 = tcgen05 per-tap kernel only, 4 = tcgen05 plane-streaming kernel only,
                            5 = tcgen05 line-streaming kernel (dy taps merged into N) only,

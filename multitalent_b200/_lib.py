@@ -42,7 +42,10 @@ class ConvParams(C.Structure):
         ("ntaps", C.c_int32),
         ("tap_off", (C.c_int32 * 3) * MAX_TAPS),
         ("tap_widx", C.c_int32 * MAX_TAPS),
-        ("accumulate", C.c_int32), ("impl", C.c_int32),
+        ("accumulate", C.c_int32),
+        ("red_y", C.c_void_p), ("red_xform", C.c_void_p), ("red_meanrstd", C.c_void_p), ("red", C.c_void_p),
+        ("red_ldc", C.c_int32), ("red_coff", C.c_int32),
+        ("impl", C.c_int32),
     ]
 
 
@@ -179,6 +182,7 @@ class KernelProfile:
         torch.cuda.synchronize()
         out = {}
         for _name, e0, e1, flops, _nb, _info, kern in self.records:
+            kern = kern.split("+")[0]  # "+red" = the same kernel with the fused reduction epilogue
             d = out.setdefault(kern, {"launches": 0, "ms": 0.0, "flops": 0.0})
             d["launches"] += 1
             d["ms"] += e0.elapsed_time(e1)

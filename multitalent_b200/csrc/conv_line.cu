@@ -59,6 +59,12 @@ struct LineParams {
   int units;                     // work units walked by the persistent CTAs
   int accumulate, is_f16;
   int dbg;                       // experiments only (MTB200_LINE_DBG): bit 0 = read one accumulator block per line
+  // fused InstanceNorm-backward reduction (RED kernels, see mtb200_conv_params::red)
+  const void* red_y;
+  const float4* red_xform;
+  const float2* red_meanrstd;
+  double* red;
+  int red_ldc, red_coff;
 };
 
 __device__ __forceinline__ uint64_t ln_desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
@@ -67,7 +73,11 @@ __device__ __forceinline__ uint32_t ln_kmajor_hi(uint32_t row_bytes, uint32_t sb
   return ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
 }
 
-template <typename T, int ROWB, int EW>
+// RED = data-gradient launch with the InstanceNorm-backward reduction of the PRODUCING layer fused into the epilogue: the
+// thread that holds g = d(loss)/d(activation) of a voxel also reads the 16 raw conv outputs y of that voxel and accumulates
+// sum dv, sum dv * xhat per (b, channel) exactly like the forward statistics (fixed order inside the CTA, fp64 atomics
+// across CTAs) -- the separate pass over g and y (mtb200_in_bwd_reduce, 4 B per element) disappears.
+template <typename T, int ROWB, int EW, bool RED>
 __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const __grid_constant__ LineParams p) {
   constexpr int LN_CPT = 32 / (EW / 4);  // output channels per epilogue thread
   extern __shared__ uint8_t dsmem_raw[];
@@ -76,6 +86,8 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
   __shared__ __align__(8) uint64_t w_full;
   __shared__ uint32_t tmem_slot;
   __shared__ float s_bias[LN_BN];
+  __shared__ float4 s_rc[LN_BN];     // RED: {scale, shift, rstd, -mean * rstd} of (current sample, channel)
+  __shared__ float s_rslope[LN_BN];  // RED: LeakyReLU slope
 
   constexpr int KSTEPS = ROWB / 32;
   constexpr uint32_t NCOLS = 3 * LN_BN;  // accumulator width
@@ -206,10 +218,24 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
     float bias[LN_CPT];
 #pragma unroll
     for (int j = 0; j < LN_CPT; ++j) bias[j] = s_bias[part * LN_CPT + j];
-    const bool want_stats = p.stats != nullptr;
+    const bool want_stats = !RED && p.stats != nullptr;
+    int cur_b = -1;
     uint32_t gs0 = 0;  // global step index of the current unit's first line
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
       const Unit t = decode(u);
+      if (RED && t.b != cur_b) {  // per-(sample, channel) constants of the fused reduction (uniform over the epilogue warps)
+        asm volatile("bar.sync 1, %0;" ::"r"(EW * 32) : "memory");
+        const int et = (int)threadIdx.x - 96;
+        if (et < LN_BN) {
+          const long long i = (long long)t.b * p.Cout + n0 + et;
+          const float4 f = p.red_xform[i];
+          const float2 mr = p.red_meanrstd[i];
+          s_rc[et] = make_float4(f.x, f.y, mr.y, -mr.x * mr.y);
+          s_rslope[et] = f.z;
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(EW * 32) : "memory");
+        cur_b = t.b;
+      }
       const int m = q * 32 + lane;  // tile row = TMEM lane
       const int b = t.b, d = t.d + (p.P == 2 ? (m & 1) : 0), hs = t.hs, he = t.he, hfirst = t.hfirst;
       const int ww = t.w0 + (p.P == 2 ? (m >> 1) : m);
@@ -220,6 +246,13 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
 
       auto emit = [&](int h) {
         uint32_t r[3][LN_CPT];
+        Raw8<T> yraw[LN_CPT / 8];
+        if (RED && wvalid) {  // issued first: the global-load latency hides behind the TMEM loads
+          const T* yrow = reinterpret_cast<const T*>(p.red_y) +
+                          ((((long long)b * p.D + d) * p.H + h) * p.W + ww) * p.red_ldc + p.red_coff + n0 + part * LN_CPT;
+#pragma unroll
+          for (int c8 = 0; c8 < LN_CPT / 8; ++c8) yraw[c8].load(yrow + c8 * 8);
+        }
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
           const int hq = h + dy;
@@ -263,6 +296,17 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
               csq[j] = fmaf(x, x, csq[j]);
             }
           }
+          if (RED) {  // csum = sum dv, csq = sum dv * xhat (the same fixed-order reduction as the statistics)
+#pragma unroll
+            for (int j = 0; j < LN_CPT; ++j) {
+              const float g = Traits<T>::round(v[j]);  // what in_bwd_apply will read back
+              const float yv = yraw[j >> 3].get(j & 7);
+              const float4 c = s_rc[part * LN_CPT + j];
+              const float dv = fmaf(yv, c.x, c.y) > 0.f ? g : g * s_rslope[part * LN_CPT + j];
+              csum[j] += dv;
+              csq[j] = fmaf(dv, fmaf(yv, c.z, c.w), csq[j]);
+            }
+          }
         }
       };
 
@@ -280,12 +324,12 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
       __syncwarp();
       if (lane == 0)
         for (int hq = max(he - 1, hfirst); hq < hfirst + t.nsteps; ++hq) mbar_arrive(&q_empty[(gs0 + (uint32_t)(hq - hfirst)) % LN_QSLOTS]);
-      if (want_stats) {  // per-(b, channel) sums of this unit -> fp64 atomics (warp-level column sums first)
+      if (want_stats || RED) {  // per-(b, channel) sums of this unit -> fp64 atomics (warp-level column sums first)
         warp_colsum(csum, lane);
         warp_colsum(csq, lane);
         if (colsum_writer<LN_CPT>(lane)) {
           const int col = part * LN_CPT + colsum_column<LN_CPT>(lane);
-          double* st = p.stats + ((long long)b * p.Cout + n0 + col) * 2;
+          double* st = (RED ? p.red : p.stats) + ((long long)b * p.Cout + n0 + col) * 2;
           atomicAdd(st, (double)csum[0]);
           atomicAdd(st + 1, (double)csq[0]);
         }
@@ -300,11 +344,15 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
   }
 }
 
+template <typename T, int ROWB, int EW, bool RED>
+static cudaError_t launch_line_red(const LineParams& q, dim3 grid, int smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(conv_line_umma_kernel<T, ROWB, EW, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) conv_line_umma_kernel<T, ROWB, EW, RED><<<grid, ln_threads(EW), smem, s>>>(q);
+  return e;
+}
 template <typename T, int ROWB, int EW>
 static cudaError_t launch_line_ew(const LineParams& q, dim3 grid, int smem, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(conv_line_umma_kernel<T, ROWB, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) conv_line_umma_kernel<T, ROWB, EW><<<grid, ln_threads(EW), smem, s>>>(q);
-  return e;
+  return q.red ? launch_line_red<T, ROWB, EW, true>(q, grid, smem, s) : launch_line_red<T, ROWB, EW, false>(q, grid, smem, s);
 }
 
 // MTB200_LINE_EPI_WARPS=8|16 overrides the epilogue width (experiments); default 8 (measured faster, profiles/r1i_line_epi_ab.txt)
@@ -416,6 +464,15 @@ int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s) {
     if (!umma_encode_map(&q.w_map, p.dtype, 3, (void*)p.w, dims, strides, box, rowb)) return MTB200_ERR_CUDA;
   }
   q.out = p.out; q.bias = p.bias; q.stats = p.stats;
+  // fused reduction of the producing layer's InstanceNorm backward (data-gradient launches; MTB200_FUSE_RED=0: off)
+  static int fuse_red = -1;
+  if (fuse_red < 0) { const char* e = getenv("MTB200_FUSE_RED"); fuse_red = (e && atoi(e) == 0) ? 0 : 1; }
+  if (p.red && fuse_red && !p.stats && p.red_y && p.red_xform && p.red_meanrstd && p.red_ldc % 8 == 0 && p.red_coff % 8 == 0) {
+    q.red = p.red; q.red_y = p.red_y;
+    q.red_xform = reinterpret_cast<const float4*>(p.red_xform);
+    q.red_meanrstd = reinterpret_cast<const float2*>(p.red_meanrstd);
+    q.red_ldc = p.red_ldc; q.red_coff = p.red_coff;
+  }
   q.B = p.B; q.D = p.Do; q.H = p.Ho; q.W = p.Wo;
   q.out_ldc = p.out_ldc; q.out_coff = p.out_coff; q.Cout = p.Cout;
   q.accumulate = p.accumulate;
@@ -457,7 +514,7 @@ int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s) {
                     : (rowb == 64 ? launch_line<__half, 64>(q, grid, smem, s) : launch_line<__half, 32>(q, grid, smem, s));
   }
   if (e != cudaSuccess) { set_error("conv_line: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
-  return check_launch("conv_line_umma");
+  return check_launch(q.red ? "conv_line_umma+red" : "conv_line_umma");
 }
 
 }  // namespace mtb

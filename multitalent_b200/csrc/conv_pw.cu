@@ -26,6 +26,7 @@ struct PwParams {
   const float* bias;
   double* stats;
   long long tiles_per_b;   // voxels per sample / 128 (statistics only)
+  long long ntiles_rows;   // voxels in the whole tensor
   int ntiles;
   int KC, nkc, BN;         // channels per K chunk, chunks, N = padded Cout
   int OB, nob, out_mask;   // staging column block (channels), blocks, swizzle mask (7 / 3 / 1, 0 = dense)
@@ -35,6 +36,12 @@ struct PwParams {
   int obufs;               // staging buffers: 2, or 1 when two do not fit beside the weights
   int Cout_stride;         // stats row length (padded Cout)
   int is_f16;
+  // fused InstanceNorm-backward reduction of the producing layer (see mtb200_conv_params::red): the statistics slots
+  // then accumulate {sum dv, sum dv * xhat} instead of {sum x, sum x^2}
+  const void* red_y;
+  const float4* red_xform;
+  const float2* red_meanrstd;
+  int red_ldc, red_coff;
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -56,7 +63,12 @@ __global__ void __launch_bounds__(PW_THREADS, 2) conv_pw_umma_kernel(const __gri
   __shared__ __align__(8) uint64_t full_bar[PW_MAX_STAGES], empty_bar[PW_MAX_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], w_full;
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_sum[4][256], s_sq[4][256], s_bias[256];  // statistics: one slot per epilogue warp, no float atomics
+  __shared__ float s_sum[4][256], s_sq[4][256];  // statistics: one slot per epilogue warp, no float atomics
+  __shared__ __align__(16) float s_bias[256];
+  // fused reduction (N <= 64, no bias): {scale, shift, rstd, -mean * rstd} per channel ALIASES the bias table (two CTAs
+  // per SM leave no room for another kilobyte of static shared memory), the LeakyReLU slopes get 256 bytes of their own
+  float4* s_rc = reinterpret_cast<float4*>(s_bias);
+  __shared__ float s_rslope[64];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
@@ -142,11 +154,27 @@ __global__ void __launch_bounds__(PW_THREADS, 2) conv_pw_umma_kernel(const __gri
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const bool want_stats = p.stats != nullptr;
+    const bool red = want_stats && p.red_y != nullptr;
     const bool issuer = threadIdx.x == 64;
     const uint32_t ob_bytes = 128u * (uint32_t)p.OB * 2u;  // one staged column block
     uint32_t k = 0;
+    int cur_b = -1;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++k) {
       const uint32_t buf = k & 1u;
+      if (red) {  // constants of (sample, channel); a tile never straddles two samples (host check)
+        const int b = (int)((long long)tile / p.tiles_per_b);
+        if (b != cur_b) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int c = threadIdx.x - 64; c < p.BN; c += 128) {
+            const long long i = (long long)b * p.Cout_stride + n0 + c;
+            const float4 f = p.red_xform[i];
+            const float2 mr = p.red_meanrstd[i];
+            s_rc[c] = make_float4(f.x, f.y, mr.y, -mr.x * mr.y);
+            s_rslope[c] = f.z;
+          }
+          cur_b = b;  // the bar.sync below orders these writes before their first use
+        }
+      }
       uint8_t* stage_out = o_base + (size_t)(p.obufs == 2 ? buf : 0u) * p.out_buf_bytes;
       // the bulk store that last read this staging buffer (tile k-2, or k-1) must have finished reading shared memory
       if (issuer) {
@@ -157,14 +185,19 @@ __global__ void __launch_bounds__(PW_THREADS, 2) conv_pw_umma_kernel(const __gri
       mbar_wait(&acc_full[buf], (k >> 1) & 1u);
       tc_fence_after();
       const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.BN;
+      const T* yrow = red ? reinterpret_cast<const T*>(p.red_y) + ((long long)tile * 128 + row) * p.red_ldc + p.red_coff + n0
+                          : nullptr;
+      const bool row_ok = (long long)tile * 128 + row < (long long)p.ntiles_rows;
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         uint32_t r[16];
+        Raw8<T> y0, y1;
+        if (red && row_ok) { y0.load(yrow + c0); y1.load(yrow + c0 + 8); }  // before the TMEM wait: latency overlaps
         tmem_ld16(tcol + (uint32_t)c0, r);
         float lo[8], hi8[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          lo[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
-          hi8[j] = __uint_as_float(r[8 + j]) + s_bias[c0 + 8 + j];
+          lo[j] = __uint_as_float(r[j]) + (red ? 0.f : s_bias[c0 + j]);
+          hi8[j] = __uint_as_float(r[8 + j]) + (red ? 0.f : s_bias[c0 + 8 + j]);
         }
         const int blk = c0 / p.OB, cin = c0 - blk * p.OB;
         uint32_t off0 = (uint32_t)row * (uint32_t)p.OB * 2u + (uint32_t)cin * 2u;
@@ -179,8 +212,17 @@ __global__ void __launch_bounds__(PW_THREADS, 2) conv_pw_umma_kernel(const __gri
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float x0 = Traits<T>::round(lo[j]), x1 = Traits<T>::round(hi8[j]);
-            sv[j] = x0; ss[j] = x0 * x0;
-            sv[8 + j] = x1; ss[8 + j] = x1 * x1;
+            if (red) {  // {dv, dv * xhat} of the producing layer's InstanceNorm + LeakyReLU backward
+              const float4 ca = s_rc[c0 + j], cb = s_rc[c0 + 8 + j];
+              const float ya = row_ok ? y0.get(j) : 0.f, yb = row_ok ? y1.get(j) : 0.f;
+              const float da = !row_ok ? 0.f : (fmaf(ya, ca.x, ca.y) > 0.f ? x0 : x0 * s_rslope[c0 + j]);
+              const float db = !row_ok ? 0.f : (fmaf(yb, cb.x, cb.y) > 0.f ? x1 : x1 * s_rslope[c0 + 8 + j]);
+              sv[j] = da; ss[j] = da * fmaf(ya, ca.z, ca.w);
+              sv[8 + j] = db; ss[8 + j] = db * fmaf(yb, cb.z, cb.w);
+            } else {
+              sv[j] = x0; ss[j] = x0 * x0;
+              sv[8 + j] = x1; ss[8 + j] = x1 * x1;
+            }
           }
           warp_colsum16(sv, lane);
           warp_colsum16(ss, lane);
@@ -290,6 +332,19 @@ int conv_pw_umma(const mtb200_conv_params& p, cudaStream_t s) {
   q.tiles_per_b = max(1LL, nvox / 128);
   q.widx = p.tap_widx[0];
   q.bias = p.bias; q.stats = p.stats;
+  q.ntiles_rows = M;
+  // fused reduction of the producing layer's InstanceNorm backward (data-gradient launches; MTB200_FUSE_RED=0: off)
+  static int fuse_red = -1;
+  if (fuse_red < 0) { const char* e = getenv("MTB200_FUSE_RED"); fuse_red = (e && atoi(e) == 0) ? 0 : 1; }
+  const bool red = p.red && fuse_red && !p.stats && !p.bias && p.red_y && p.red_xform && p.red_meanrstd && q.BN <= 64 &&
+                   p.Cout == q.BN && nvox % 128 == 0 && p.red_ldc % 8 == 0 && p.red_coff % 8 == 0;
+  if (red) {
+    q.stats = p.red;  // the statistics slots and their flush carry {sum dv, sum dv * xhat}
+    q.red_y = p.red_y;
+    q.red_xform = reinterpret_cast<const float4*>(p.red_xform);
+    q.red_meanrstd = reinterpret_cast<const float2*>(p.red_meanrstd);
+    q.red_ldc = p.red_ldc; q.red_coff = p.red_coff;
+  }
   q.Cout_stride = p.Cout;
   q.is_f16 = p.dtype == MTB200_F16;
   {
@@ -326,7 +381,7 @@ int conv_pw_umma(const mtb200_conv_params& p, cudaStream_t s) {
     if (e == cudaSuccess) conv_pw_umma_kernel<__half><<<grid, PW_THREADS, smem, s>>>(q);
   }
   if (e != cudaSuccess) { set_error("conv_pw: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
-  return check_launch("conv_pw_umma");
+  return check_launch(q.red_y ? "conv_pw_umma+red" : "conv_pw_umma");
 }
 
 }  // namespace mtb

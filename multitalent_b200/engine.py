@@ -125,6 +125,9 @@ class Feat:
     xform: Optional[torch.Tensor] = None     # [B, Cp, 4] pending {scale, shift, slope, 0}; None = already materialised
     meanrstd: Optional[torch.Tensor] = None  # [B, Cp, 2]
     act: Optional["Feat"] = None             # cached materialised activation f(raw) (tensor-core path)
+    raw_of: Optional["Feat"] = None          # on a materialised activation: the raw conv output it was computed from
+    single_consumer: bool = False            # exactly one layer consumes this output: its dgrad holds the FINAL d(act)
+    red_fused: Optional[torch.Tensor] = None  # InstanceNorm-backward sums already accumulated by that dgrad's epilogue
 
     @property
     def dims(self):
@@ -400,6 +403,8 @@ class Engine:
         # arena mode: the packed fp32 weight gradients of a step are folded into the parameters' gradient slots by ONE
         # launch at the end of the backward pass (MTB200_UNPACK_BATCHED=0: one launch per layer, as before)
         self.batch_unpack = os.environ.get("MTB200_UNPACK_BATCHED", "1") != "0"
+        # InstanceNorm-backward reduction fused into the consumer's data-gradient epilogue where the kernel supports it
+        self.fuse_red = os.environ.get("MTB200_FUSE_RED", "1") != "0"
         self._pending_unpack = []
         self._unpack_tables = {}
 
@@ -456,7 +461,9 @@ class Engine:
         return 2.0 * op.Cin * op.Cout * n * (1 if op.transposed else op.ntap)
 
     def _conv_call(self, table: TapTable, x: Feat, w_packed, bias_p, out: Feat, grid_dims, stats, accumulate, Cin_p,
-                   Cout_p, flops=0.0, tag="conv_fwd"):
+                   Cout_p, flops=0.0, tag="conv_fwd", red=None):
+        """`red` = (raw Feat of the layer whose d(activation) this launch writes, fp64 [B, Cp, 2] accumulator): offer the
+        fused InstanceNorm-backward reduction to the kernel.  Returns True if the dispatched kernel took it."""
         p = L.ConvParams()
         p.inp, p.out, p.w = x.ptr(), out.ptr(), w_packed.data_ptr()
         p.bias = bias_p.data_ptr() if bias_p is not None else None
@@ -471,8 +478,13 @@ class Engine:
         table.fill(p)
         p.accumulate = int(accumulate)
         p.impl = self.impl
+        if red is not None:
+            raw, acc = red
+            p.red_y, p.red_ldc, p.red_coff = raw.ptr(), raw.ldc, raw.coff
+            p.red_xform, p.red_meanrstd, p.red = raw.xform.data_ptr(), raw.meanrstd.data_ptr(), acc.data_ptr()
         L.call("mtb200_conv_taps", C.byref(p), L.stream_ptr(), flops=flops, tag=tag,
                info=(Cin_p, Cout_p, tuple(grid_dims), len(table.taps), table.in_stride, table.out_stride))
+        return red is not None and (L.lib().mtb200_last_kernel() or b"").endswith(b"+red")
 
     # ---- forward primitives -------------------------------------------------------------------------------------
     def conv(self, op: ConvOp, x: Feat, out: Optional[Feat] = None, want_stats=False):
@@ -513,6 +525,8 @@ class Engine:
         if out is None:
             out = Feat(self.new_buf(x.dims, x.Cp, x.buf.device), 0, x.C, x.Cp)
         B = x.dims[0]
+        if res is None:
+            out.raw_of = x
         L.call("mtb200_norm_act", x.ptr(), x.ldc, x.coff, out.ptr(), out.ldc, out.coff, L.dtype_enum(self.dtype), B,
                x.nvox, x.Cp, L.ptr(x.xform), res.ptr() if res is not None else None,
                res.ldc if res is not None else 0, res.coff if res is not None else 0,
@@ -540,10 +554,12 @@ class Engine:
             self._zero_param_grads(tape, op, gamma_param, beta_param)
             return
         g, _ = tape.grad_feat(src)
-        red = self._z64.take((B, y.Cp, 2), dev)
         dt = L.dtype_enum(self.dtype)
-        L.call("mtb200_in_bwd_reduce", g.ptr(), g.ldc, g.coff, y.ptr(), y.ldc, y.coff, dt, B, y.nvox, y.Cp,
-               L.ptr(y.xform), L.ptr(y.meanrstd), L.ptr(red), L.stream_ptr())
+        red, y.red_fused = y.red_fused, None
+        if red is None:  # the consumer's data-gradient kernel did not accumulate the sums: separate pass over g and y
+            red = self._z64.take((B, y.Cp, 2), dev)
+            L.call("mtb200_in_bwd_reduce", g.ptr(), g.ldc, g.coff, y.ptr(), y.ldc, y.coff, dt, B, y.nvox, y.Cp,
+                   L.ptr(y.xform), L.ptr(y.meanrstd), L.ptr(red), L.stream_ptr())
         dgamma, dbeta = direct_grad(gamma_param, y.Cp), direct_grad(beta_param, y.Cp)
         direct = dgamma is not None and dbeta is not None
         if not direct:
@@ -635,8 +651,17 @@ class Engine:
         gx, have = tape.grad_feat(x)
         grid = gx.dims[1:] if op.transposed else tuple(n // s for n, s in zip(gx.dims[1:], op.stride))
         dyv = Feat(dy.buf, dy.coff, dy.C, dy.Cp)  # gradients carry no pending transform
-        self._conv_call(op.dgrad_taps, dyv, op.packed(self.wdtype, True), None, gx, grid, None, have, op.Cout_p,
-                        op.Cin_p, flops=fl, tag="conv_dgrad")
+        # this launch writes the FINAL d(activation) of a single-consumer layer: offer the fused InstanceNorm-backward
+        # reduction (sum dv, sum dv * xhat) to the kernel's epilogue
+        red = None
+        raw = x.raw_of
+        if (self.fuse_red and raw is not None and raw.single_consumer and not have and raw.xform is not None
+                and raw.meanrstd is not None and raw.Cp == gx.Cp and raw.dims == gx.dims and self.materialize_inputs):
+            red = (raw, self._z64.take((gx.dims[0], raw.Cp, 2), dev))
+        took = self._conv_call(op.dgrad_taps, dyv, op.packed(self.wdtype, True), None, gx, grid, None, have, op.Cout_p,
+                               op.Cin_p, flops=fl, tag="conv_dgrad", red=red)
+        if took:
+            raw.red_fused = red[1]
         tape.mark(x)
 
     def _finish_wgrad(self, tape, op: ConvOp, dw, dy: Feat, dt, dev, bias_grad_is_zero):

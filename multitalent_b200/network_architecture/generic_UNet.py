@@ -375,12 +375,14 @@ class Generic_UNet(SegmentationNetwork):
                     if not mat:
                         out = Feat(cat, op.Cout_p, op.Cout, op.Cout_p)
                 f = eng.conv_norm(ttape, op, g, b, f, out, need_input_grad=not first)
+                f.single_consumer = not last  # the stage output also feeds the decoder (skip connection)
                 if last and mat:
                     f.act = eng.materialize(f, out=Feat(cat, op.Cout_p, op.Cout, op.Cout_p))
                 first = False
             skips.append(f)
         for (op, g, b) in ops['bott']:
             f = eng.conv_norm(ttape, op, g, b, f)
+            f.single_consumer = True  # next bottleneck conv / the first transposed conv
         logits = []
         nu = len(ops['tu'])
         for u in range(nu):
@@ -397,8 +399,11 @@ class Generic_UNet(SegmentationNetwork):
                 ident[:, :, 0] = 1.0
                 ident[:, :, 2] = 1.0
                 f = Feat(cat, 0, top.Cout + skip.C, 2 * skip.Cp, xform=torch.cat((ident, skip.xform), dim=1))
-            for (op, g, b) in ops['dec'][u]:
+            nd = len(ops['dec'][u])
+            for i, (op, g, b) in enumerate(ops['dec'][u]):
                 f = eng.conv_norm(ttape, op, g, b, f)
+                # the level's last conv feeds its head AND the next transposed conv -- except at full resolution
+                f.single_consumer = i < nd - 1 or u == nu - 1
             if only_full_res and u != nu - 1:
                 continue
             logits.append(eng.conv_plain(tape, ops['head'][u], f, need_input_grad=head_dgrad))

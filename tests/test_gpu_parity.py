@@ -411,3 +411,25 @@ def test_config0_full_patch_forward_and_loss_vs_cpu_oracle():
         assert float((torch.sigmoid(a.float().cpu()) - torch.sigmoid(b)).abs().max()) < 1e-3
     for a, b in zip(l, ref_l):
         assert abs(a.item() - b.item()) < 1e-3 * max(1.0, abs(b.item()))
+
+
+def test_fused_reduction_leaves_the_training_step_unchanged(golden_small):
+    """Whole small network, bf16: gradients with the InstanceNorm-backward reduction fused into the data-gradient
+    epilogues (default) vs the separate reduce pass."""
+    from conftest import build_small_net
+    from multitalent_b200.training.loss_functions.multitalent_loss import multitalent_loss
+    blob, meta = golden_small
+    x = torch.from_numpy(blob["x"]).to(DEV)
+    tg = [torch.from_numpy(blob["target_%d" % i]).to(DEV) for i in range(3)]
+    grads = []
+    for fuse in (True, False):
+        net = build_small_net(meta, blob, dtype=torch.bfloat16)
+        net._engine.fuse_red = fuse
+        out = net(x)
+        l, _, _ = multitalent_loss(out, tg, meta["valid_regions"], blob["ds_loss_weights"])
+        l.backward()
+        grads.append((l.item(), {n: p.grad.detach().float().cpu() for n, p in net.named_parameters()}))
+    assert grads[0][0] == grads[1][0]
+    for n in grads[0][1]:
+        a, b = grads[0][1][n], grads[1][1][n]
+        assert float((a - b).abs().max()) <= 5e-3 * float(b.abs().max()) + 1e-7, n

@@ -22,7 +22,7 @@ def _require_tcgen05():
 
 
 def _close(a, b, dtype):
-    a, b = a.float().cpu().numpy(), b.float().cpu().numpy()
+    a, b = a.detach().float().cpu().numpy(), b.detach().float().cpu().numpy()
     scale = max(np.abs(b).max(), 1e-6)
     ulp = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -11
     err = np.abs(a - b).max() / scale
@@ -34,8 +34,9 @@ def _lib_ref(x, w, bias, stride, kernel, dtype):
     Products of 16-bit values are exact in fp32, so only the summation order (and the final rounding of the stored
     result) may differ from the tensor-core kernel."""
     from oracle.gpu_reference import conv_reference
-    y = conv_reference(x.to(dtype), w.to(dtype), stride, [(k - 1) // 2 for k in kernel])
-    return y if bias is None else y + bias.view(1, -1, 1, 1, 1)
+    with torch.no_grad():
+        y = conv_reference(x.to(dtype), w.to(dtype), stride, [(k - 1) // 2 for k in kernel])
+        return y if bias is None else y + bias.view(1, -1, 1, 1, 1)
 
 
 def _lib_ref_grads(x, w, gy, stride, kernel, dtype):
@@ -392,6 +393,10 @@ def test_wgrad_line_streaming_matches_ffma(dtype, cin, cout, kernel, dims, split
     from multitalent_b200.engine import ConvOp, Engine, Feat, Tape
     torch.manual_seed(1)
     B, D, H, W = dims
+    if W < 48:  # narrower lines are inside the kernel's envelope but not dispatched by default (MTB200_WLINE_MINW)
+        import os
+        if int(os.environ.get("MTB200_WLINE_MINW", "48")) > W:
+            pytest.skip("32-wide lines need MTB200_WLINE_MINW=32 (set before the library is first used)")
     conv = nn.Conv3d(cin, cout, kernel, 1, [(k - 1) // 2 for k in kernel], bias=True).to(DEV)
     op = ConvOp(conv.weight, conv.bias, kernel, (1, 1, 1), split=split)
     xb = torch.randn(B, D, H, W, op.Cin_p, device=DEV).to(dtype)
@@ -529,3 +534,51 @@ def test_network_bf16_tensor_core_path_matches_cuda_core_path(golden_small):
         a, b = grads[0][2][n].double(), grads[1][2][n].double()
         num += float((a * b).sum()); den_a += float((a * a).sum()); den_b += float((b * b).sum())
     assert num / (den_a ** 0.5 * den_b ** 0.5) > 0.98
+
+
+@pytest.mark.parametrize("dims,cmid,kernel2", [
+    ((2, 4, 12, 128), 30, (3, 3, 3)),   # consumer dgrad = line kernel, one h-line per M tile
+    ((1, 6, 10, 64), 60, (3, 3, 3)),    # line kernel, two planes per M tile
+    ((2, 4, 8, 64), 30, (1, 1, 1)),     # consumer = 1x1x1 head: pointwise kernel
+])
+def test_fused_instancenorm_backward_reduction_matches_separate_pass(dims, cmid, kernel2):
+    """conv -> IN -> LReLU -> conv: the consumer's data-gradient epilogue accumulates sum dv / sum dv*xhat of the first
+    layer (mtb200_conv_params::red).  Same gradients as with the separate mtb200_in_bwd_reduce pass, and the fused path
+    is really taken."""
+    _require_tcgen05()
+    from multitalent_b200 import _lib as L
+    from multitalent_b200.engine import ConvOp, Engine, Tape
+    dtype = torch.bfloat16
+    torch.manual_seed(5)
+    B, D, H, W = dims
+    x = torch.randn(B, 30, D, H, W, device=DEV)
+    c1 = nn.Conv3d(30, cmid, 3, 1, 1, bias=True).to(DEV)
+    n1 = nn.InstanceNorm3d(cmid, affine=True).to(DEV)
+    with torch.no_grad():
+        n1.weight.copy_(0.5 + torch.rand(cmid, device=DEV))
+        n1.bias.copy_(0.3 * torch.randn(cmid, device=DEV))
+    c2 = nn.Conv3d(cmid, 47 if kernel2 == (1, 1, 1) else 30, kernel2, 1, [(k - 1) // 2 for k in kernel2], bias=False).to(DEV)
+    op1, op2 = ConvOp(c1.weight, c1.bias, (3, 3, 3), (1, 1, 1)), ConvOp(c2.weight, None, kernel2, (1, 1, 1))
+    gy = torch.randn(B, c2.out_channels, D, H, W, device=DEV)
+    res = []
+    for fuse in (False, True):
+        eng = Engine(dtype, 0)
+        eng.fuse_red = fuse
+        tape = Tape()
+        xf = eng.input_feat(x)
+        y1 = eng.conv_norm(tape, op1, n1.weight, n1.bias, xf, need_input_grad=True)
+        y1.single_consumer = True
+        y2 = eng.conv_plain(tape, op2, y1)
+        eng.seed_grad(tape, y2, gy)
+        n0 = L.launch_count
+        with L.KernelProfile() as kp:
+            eng.run_backward(tape)
+        names = [r[0] for r in kp.records]
+        assert ("mtb200_in_bwd_reduce" in names) == (not fuse), names
+        g = {k: tape.param_grads[id(p)].clone() for k, p in (("w1", c1.weight), ("gamma", n1.weight), ("beta", n1.bias),
+                                                             ("w2", c2.weight))}
+        g["gx"] = tape.grad_feat(xf)[0].buf.clone()
+        res.append(g)
+    for k in res[0]:
+        a, b = res[0][k].float(), res[1][k].float()
+        assert float((a - b).abs().max()) <= 2e-3 * float(a.abs().max()) + 1e-6, k

@@ -124,8 +124,9 @@ def test_fused_hard_counts_from_the_loss_kernel_equal_the_standalone_evaluation(
         monkeypatch.setattr(OE, "hard_tp_fp_fn", boom)
         tr.run_iteration(iter([batch]), do_backprop=False, run_online_evaluation=True)
         monkeypatch.undo()
-        assert np.array_equal(np.array(tr.online_eval_tp[0]), tp.sum(0).cpu().numpy())
-        assert np.array_equal(np.array(tr.online_eval_fp[0]), fp.sum(0).cpu().numpy())
-        assert np.array_equal(np.array(tr.online_eval_fn[0]), fn.sum(0).cpu().numpy())
+        # the reference's accumulators hold [B, 47] per iteration (sum over the RANK axis only, MT:404-407)
+        assert np.array_equal(np.array(tr.online_eval_tp[0]), tp.cpu().numpy())
+        assert np.array_equal(np.array(tr.online_eval_fp[0]), fp.cpu().numpy())
+        assert np.array_equal(np.array(tr.online_eval_fn[0]), fn.cpu().numpy())
         per_class = tr.finish_online_evaluation()
         assert len(per_class) == 47 and len(tr.all_val_eval_metrics) >= 1
