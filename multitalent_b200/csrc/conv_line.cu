@@ -244,14 +244,24 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
 #pragma unroll
       for (int j = 0; j < LN_CPT; ++j) { csum[j] = 0.f; csq[j] = 0.f; }
 
+      // RED: the raw outputs y of line h were requested one line earlier (their global-load latency would otherwise sit
+      // in the critical path of every line); emit(h) consumes them and requests line h + 1
+      Raw8<T> ynext[LN_CPT / 8];
+      auto ylines = [&](int h) {
+        const T* yrow = reinterpret_cast<const T*>(p.red_y) +
+                        ((((long long)b * p.D + d) * p.H + h) * p.W + ww) * p.red_ldc + p.red_coff + n0 + part * LN_CPT;
+#pragma unroll
+        for (int c8 = 0; c8 < LN_CPT / 8; ++c8) ynext[c8].load(yrow + c8 * 8);
+      };
+      if (RED && wvalid) ylines(hs);
+
       auto emit = [&](int h) {
         uint32_t r[3][LN_CPT];
         Raw8<T> yraw[LN_CPT / 8];
-        if (RED && wvalid) {  // issued first: the global-load latency hides behind the TMEM loads
-          const T* yrow = reinterpret_cast<const T*>(p.red_y) +
-                          ((((long long)b * p.D + d) * p.H + h) * p.W + ww) * p.red_ldc + p.red_coff + n0 + part * LN_CPT;
+        if (RED && wvalid) {
 #pragma unroll
-          for (int c8 = 0; c8 < LN_CPT / 8; ++c8) yraw[c8].load(yrow + c8 * 8);
+          for (int c8 = 0; c8 < LN_CPT / 8; ++c8) yraw[c8] = ynext[c8];
+          if (h + 1 < he) ylines(h + 1);
         }
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {

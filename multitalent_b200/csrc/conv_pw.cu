@@ -19,6 +19,7 @@ namespace mtb {
 using namespace um;
 
 constexpr int PW_THREADS = 192;
+constexpr int PW_RED_MAX16 = 4;  // fused reduction: N <= 64 = four 16-channel column groups
 constexpr int PW_MAX_STAGES = 8;
 
 struct PwParams {
@@ -159,6 +160,13 @@ __global__ void __launch_bounds__(PW_THREADS, 2) conv_pw_umma_kernel(const __gri
     const uint32_t ob_bytes = 128u * (uint32_t)p.OB * 2u;  // one staged column block
     uint32_t k = 0;
     int cur_b = -1;
+    Raw8<T> yn[PW_RED_MAX16][2];
+    if (red && (long long)blockIdx.x * 128 + row < (long long)p.ntiles_rows) {  // y of the first tile
+      const T* yrow = reinterpret_cast<const T*>(p.red_y) + ((long long)blockIdx.x * 128 + row) * p.red_ldc + p.red_coff + n0;
+#pragma unroll
+      for (int i = 0; i < PW_RED_MAX16; ++i)
+        if (i * 16 < p.BN) { yn[i][0].load(yrow + i * 16); yn[i][1].load(yrow + i * 16 + 8); }
+    }
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++k) {
       const uint32_t buf = k & 1u;
       if (red) {  // constants of (sample, channel); a tile never straddles two samples (host check)
@@ -185,13 +193,30 @@ __global__ void __launch_bounds__(PW_THREADS, 2) conv_pw_umma_kernel(const __gri
       mbar_wait(&acc_full[buf], (k >> 1) & 1u);
       tc_fence_after();
       const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.BN;
-      const T* yrow = red ? reinterpret_cast<const T*>(p.red_y) + ((long long)tile * 128 + row) * p.red_ldc + p.red_coff + n0
-                          : nullptr;
+      // fused reduction: this tile's raw outputs y were requested while the PREVIOUS tile was processed (their global-load
+      // latency would otherwise sit in the critical path of every tile); request the next tile's now
       const bool row_ok = (long long)tile * 128 + row < (long long)p.ntiles_rows;
+      Raw8<T> yc[PW_RED_MAX16][2];
+      if (red) {
+#pragma unroll
+        for (int i = 0; i < PW_RED_MAX16; ++i) { yc[i][0] = yn[i][0]; yc[i][1] = yn[i][1]; }
+        const long long nrow = ((long long)tile + gridDim.x) * 128 + row;
+        if (nrow < (long long)p.ntiles_rows) {
+          const T* yrow = reinterpret_cast<const T*>(p.red_y) + nrow * p.red_ldc + p.red_coff + n0;
+#pragma unroll
+          for (int i = 0; i < PW_RED_MAX16; ++i)
+            if (i * 16 < p.BN) { yn[i][0].load(yrow + i * 16); yn[i][1].load(yrow + i * 16 + 8); }
+        }
+      }
+#pragma unroll 1
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         uint32_t r[16];
         Raw8<T> y0, y1;
-        if (red && row_ok) { y0.load(yrow + c0); y1.load(yrow + c0 + 8); }  // before the TMEM wait: latency overlaps
+        if (red) {
+#pragma unroll
+          for (int i = 0; i < PW_RED_MAX16; ++i)
+            if (i * 16 == c0) { y0 = yc[i][0]; y1 = yc[i][1]; }
+        }
         tmem_ld16(tcol + (uint32_t)c0, r);
         float lo[8], hi8[8];
 #pragma unroll
