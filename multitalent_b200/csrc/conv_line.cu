@@ -215,9 +215,11 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
     const int part = (warp - 3) >> 2;
     T* out = reinterpret_cast<T*>(p.out);
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * LN_CPT);
-    float bias[LN_CPT];
+    float bias[LN_CPT];  // RED (data gradient: no bias) keeps the InstanceNorm scale of its channels here instead
 #pragma unroll
-    for (int j = 0; j < LN_CPT; ++j) bias[j] = s_bias[part * LN_CPT + j];
+    for (int j = 0; j < LN_CPT; ++j) bias[j] = RED ? 0.f : s_bias[part * LN_CPT + j];
+    float rshift[RED ? LN_CPT : 1];
+    float rslope = 0.f;
     const bool want_stats = !RED && p.stats != nullptr;
     int cur_b = -1;
     uint32_t gs0 = 0;  // global step index of the current unit's first line
@@ -235,6 +237,13 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
         }
         asm volatile("bar.sync 1, %0;" ::"r"(EW * 32) : "memory");
         cur_b = t.b;
+#pragma unroll
+        for (int j = 0; j < LN_CPT; ++j) {  // per-channel constants live in registers for the whole sample
+          const float4 c = s_rc[part * LN_CPT + j];
+          bias[j] = c.x;
+          rshift[j] = c.y;
+        }
+        rslope = s_rslope[part * LN_CPT];  // one LeakyReLU slope per layer
       }
       const int m = q * 32 + lane;  // tile row = TMEM lane
       const int b = t.b, d = t.d + (p.P == 2 ? (m & 1) : 0), hs = t.hs, he = t.he, hfirst = t.hfirst;
@@ -284,7 +293,7 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
           float v[LN_CPT];
 #pragma unroll
           for (int j = 0; j < LN_CPT; ++j)
-            v[j] = bias[j] + __uint_as_float(r[0][j]) + __uint_as_float(r[1][j]) + __uint_as_float(r[2][j]);
+            v[j] = (RED ? 0.f : bias[j]) + __uint_as_float(r[0][j]) + __uint_as_float(r[1][j]) + __uint_as_float(r[2][j]);
           T* orow = out + ((((long long)b * p.D + d) * p.H + h) * p.W + ww) * p.out_ldc + p.out_coff + n0 + part * LN_CPT;
 #pragma unroll
           for (int c8 = 0; c8 < LN_CPT; c8 += 8) {
@@ -306,15 +315,14 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
               csq[j] = fmaf(x, x, csq[j]);
             }
           }
-          if (RED) {  // csum = sum dv, csq = sum dv * xhat (the same fixed-order reduction as the statistics)
+          if (RED) {  // csum = sum dv, csq = sum dv * y; xhat = y * rstd - mean * rstd is applied once per unit at the flush
 #pragma unroll
             for (int j = 0; j < LN_CPT; ++j) {
               const float g = Traits<T>::round(v[j]);  // what in_bwd_apply will read back
               const float yv = yraw[j >> 3].get(j & 7);
-              const float4 c = s_rc[part * LN_CPT + j];
-              const float dv = fmaf(yv, c.x, c.y) > 0.f ? g : g * s_rslope[part * LN_CPT + j];
+              const float dv = fmaf(yv, bias[j], rshift[j]) > 0.f ? g : g * rslope;
               csum[j] += dv;
-              csq[j] = fmaf(dv, fmaf(yv, c.z, c.w), csq[j]);
+              csq[j] = fmaf(dv, yv, csq[j]);
             }
           }
         }
@@ -340,8 +348,14 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
         if (colsum_writer<LN_CPT>(lane)) {
           const int col = part * LN_CPT + colsum_column<LN_CPT>(lane);
           double* st = (RED ? p.red : p.stats) + ((long long)b * p.Cout + n0 + col) * 2;
-          atomicAdd(st, (double)csum[0]);
-          atomicAdd(st + 1, (double)csq[0]);
+          if (RED) {  // sum dv * xhat = rstd * sum dv * y - mean * rstd * sum dv
+            const float4 c = s_rc[col];
+            atomicAdd(st, (double)csum[0]);
+            atomicAdd(st + 1, (double)c.z * (double)csq[0] + (double)c.w * (double)csum[0]);
+          } else {
+            atomicAdd(st, (double)csum[0]);
+            atomicAdd(st + 1, (double)csq[0]);
+          }
         }
       }
       gs0 += (uint32_t)t.nsteps;

@@ -359,8 +359,10 @@ int conv_pw_umma(const mtb200_conv_params& p, cudaStream_t s) {
   q.bias = p.bias; q.stats = p.stats;
   q.ntiles_rows = M;
   // fused reduction of the producing layer's InstanceNorm backward (data-gradient launches; MTB200_FUSE_RED=0: off)
-  static int fuse_red = -1;
-  if (fuse_red < 0) { const char* e = getenv("MTB200_FUSE_RED"); fuse_red = (e && atoi(e) == 0) ? 0 : 1; }
+  // Off by default: the per-tile transposing reduction makes this HBM-streaming kernel latency-bound (head data gradient
+  // at 192x160x128: 0.41 -> 1.45 ms, profiles/r2d_ncu_red.txt), more than the separate pass costs (0.38 ms).
+  const char* fuse_env = getenv("MTB200_FUSE_RED_PW");  // read per call: tests toggle it
+  const bool fuse_red = fuse_env && atoi(fuse_env) == 1;
   const bool red = p.red && fuse_red && !p.stats && !p.bias && p.red_y && p.red_xform && p.red_meanrstd && q.BN <= 64 &&
                    p.Cout == q.BN && nvox % 128 == 0 && p.red_ldc % 8 == 0 && p.red_coff % 8 == 0;
   if (red) {

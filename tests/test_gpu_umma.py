@@ -541,13 +541,15 @@ def test_network_bf16_tensor_core_path_matches_cuda_core_path(golden_small):
     ((1, 6, 10, 64), 60, (3, 3, 3)),    # line kernel, two planes per M tile
     ((2, 4, 8, 64), 30, (1, 1, 1)),     # consumer = 1x1x1 head: pointwise kernel
 ])
-def test_fused_instancenorm_backward_reduction_matches_separate_pass(dims, cmid, kernel2):
+def test_fused_instancenorm_backward_reduction_matches_separate_pass(dims, cmid, kernel2, monkeypatch):
     """conv -> IN -> LReLU -> conv: the consumer's data-gradient epilogue accumulates sum dv / sum dv*xhat of the first
     layer (mtb200_conv_params::red).  Same gradients as with the separate mtb200_in_bwd_reduce pass, and the fused path
     is really taken."""
     _require_tcgen05()
     from multitalent_b200 import _lib as L
     from multitalent_b200.engine import ConvOp, Engine, Tape
+    if kernel2 == (1, 1, 1):  # the pointwise kernel's fused epilogue is not dispatched by default (slower than the pass)
+        monkeypatch.setenv("MTB200_FUSE_RED_PW", "1")
     dtype = torch.bfloat16
     torch.manual_seed(5)
     B, D, H, W = dims
