@@ -565,9 +565,14 @@ class Engine:
         if not direct:
             dgamma = torch.zeros(y.Cp, dtype=torch.float32, device=dev)
             dbeta = torch.zeros(y.Cp, dtype=torch.float32, device=dev)
-        L.call("mtb200_in_bwd_apply", g.ptr(), g.ldc, g.coff, y.ptr(), y.ldc, y.coff, g.ptr(), g.ldc, g.coff, dt, B,
+        # d(raw output) goes to a compact buffer of its own (not in place): both inputs stay on the read-only load path, and
+        # the weight / data gradient kernels read dense rows even where g is one half of a concat gradient buffer
+        dy = Feat(self.new_buf(y.dims, y.Cp, dev), 0, y.C, y.Cp)
+        tape.keep.append(dy.buf)  # read by the weight-gradient side stream: must outlive this closure
+        L.call("mtb200_in_bwd_apply", g.ptr(), g.ldc, g.coff, y.ptr(), y.ldc, y.coff, dy.ptr(), dy.ldc, dy.coff, dt, B,
                y.nvox, y.Cp, L.ptr(y.xform), L.ptr(y.meanrstd), L.ptr(gamma), L.ptr(red), L.ptr(dgamma), L.ptr(dbeta),
                L.stream_ptr())
+        g = dy
         if direct:
             tape.direct_done.update((id(gamma_param), id(beta_param)))
         else:
