@@ -457,7 +457,7 @@ def main():
         pps = world * ntiles / (float(inf_ms.item()) * 1e-3)
         infer = {"infer_patches_s": pps, "infer_seconds_per_volume": float(inf_ms.item()) * 1e-3,
                  "infer_volume": "x".join(str(v) for v in ivol), "infer_tiles": ntiles,
-                 "infer_tile_batch": int(getattr(net, "inference_tile_batch", 4)), "infer_mirroring": False,
+                 "infer_tile_batch": int(getattr(net, "inference_tile_batch", 8)), "infer_mirroring": False,
                  "infer_gpu_launches": int(inf_launches),
                  "infer_tflops": pps / world * FWD_GFLOP_PER_PATCH[args.net] * 1e-3,
                  "infer_e2e_patches_s": world * ntiles / float(inf_e2e_s.item()),
