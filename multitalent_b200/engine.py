@@ -11,6 +11,7 @@ instnorm/lrelu read+write passes (generic_UNet.py:70) and torch.cat (generic_UNe
 import contextlib
 import ctypes as C
 import os
+import weakref
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -125,7 +126,9 @@ class Feat:
     xform: Optional[torch.Tensor] = None     # [B, Cp, 4] pending {scale, shift, slope, 0}; None = already materialised
     meanrstd: Optional[torch.Tensor] = None  # [B, Cp, 2]
     act: Optional["Feat"] = None             # cached materialised activation f(raw) (tensor-core path)
-    raw_of: Optional["Feat"] = None          # on a materialised activation: the raw conv output it was computed from
+    raw_of: Optional[Callable] = None        # on a materialised activation: weak reference to the raw conv output it was
+    #                                          computed from (weak: raw.act -> activation must not close a cycle, or every
+    #                                          step's buffers would wait for the cyclic garbage collector)
     single_consumer: bool = False            # exactly one layer consumes this output: its dgrad holds the FINAL d(act)
     red_fused: Optional[torch.Tensor] = None  # InstanceNorm-backward sums already accumulated by that dgrad's epilogue
 
@@ -547,7 +550,7 @@ class Engine:
             out = Feat(self.new_buf(x.dims, x.Cp, x.buf.device), 0, x.C, x.Cp)
         B = x.dims[0]
         if res is None:
-            out.raw_of = x
+            out.raw_of = weakref.ref(x)
         L.call("mtb200_norm_act", x.ptr(), x.ldc, x.coff, out.ptr(), out.ldc, out.coff, L.dtype_enum(self.dtype), B,
                x.nvox, x.Cp, L.ptr(x.xform), res.ptr() if res is not None else None,
                res.ldc if res is not None else 0, res.coff if res is not None else 0,
@@ -679,7 +682,7 @@ class Engine:
         # this launch writes the FINAL d(activation) of a single-consumer layer: offer the fused InstanceNorm-backward
         # reduction (sum dv, sum dv * xhat) to the kernel's epilogue
         red = None
-        raw = x.raw_of
+        raw = x.raw_of() if x.raw_of is not None else None
         if (self.fuse_red and raw is not None and raw.single_consumer and not have and raw.xform is not None
                 and raw.meanrstd is not None and raw.Cp == gx.Cp and raw.dims == gx.dims and self.materialize_inputs):
             red = (raw, self._z64.take((gx.dims[0], raw.Cp, 2), dev))

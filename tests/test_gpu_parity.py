@@ -433,3 +433,31 @@ def test_fused_reduction_leaves_the_training_step_unchanged(golden_small):
     for n in grads[0][1]:
         a, b = grads[0][1][n], grads[1][1][n]
         assert float((a - b).abs().max()) <= 5e-3 * float(b.abs().max()) + 1e-7, n
+
+
+def test_training_steps_do_not_accumulate_device_memory(golden_small):
+    """Buffers of a step must be released by reference counting when the step ends (no Feat <-> Feat cycles waiting for the
+    cyclic garbage collector): reserved device memory is flat after the allocator's first steps."""
+    import gc
+    from multitalent_b200.plans import default_plans
+    from multitalent_b200.synthetic import synthetic_batch
+    from multitalent_b200.training.network_training.MultiTalent_Trainer_DDP import MultiTalent_trainer_ddp
+    patch = (32, 64, 64)
+    tr = MultiTalent_trainer_ddp(default_plans(patch_size=patch, batch_size=2), 0, 0, native_dtype=torch.bfloat16,
+                                 init_distributed=False)
+    tr.initialize(True)
+    b = synthetic_batch(patch, 2, 0, tr.deep_supervision_scales)
+    x = torch.from_numpy(b['data']).cuda()
+    tg = [torch.from_numpy(t).cuda() for t in b['target']]
+    valid = [p['valid_regions'] for p in b['properties']]
+    gc.collect()
+    gc.disable()
+    try:
+        alloc = []
+        for _ in range(8):
+            tr.train_step(x, tg, valid, True)
+            torch.cuda.synchronize()
+            alloc.append(torch.cuda.memory_allocated())
+    finally:
+        gc.enable()
+    assert alloc[-1] == alloc[3], "allocated bytes per step: %s" % alloc
