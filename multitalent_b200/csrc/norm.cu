@@ -264,10 +264,10 @@ int in_bwd_reduce(const void* dact, int d_ldc, int d_coff, const void* y, int y_
 }
 
 // ---- backward pass 2 ------------------------------------------------------------------------------------------------
-// `dy` may alias `dact` (in-place): those two pointers are therefore not __restrict__, and an aliased `dact` is read with
-// coherent loads (ld.global, not the read-only .nc path; each thread reads its own element before writing it, the clamped
-// tail re-reads are discarded).  The engine writes dy to a buffer of its own, which keeps both inputs on the read-only
-// path (the coherent loads cost 0.3 ms per training step at 192x160x128).
+// `dy` may alias `dact` (in-place; how the engine runs it): those two pointers are therefore not __restrict__, and an
+// aliased `dact` is read with coherent loads (ld.global, not the read-only .nc path; each thread reads its own element
+// before writing it, the clamped tail re-reads are discarded).  A separate output buffer keeps both inputs on the
+// read-only path, but measured SLOWER end to end (r2h: 5.03 vs 4.06 ms per step).
 template <typename T, int NU>
 __global__ void __launch_bounds__(NT) in_bwd_apply_kernel(const T* dact, int d_ldc, int d_coff,
                                                           const T* __restrict__ y, int y_ldc, int y_coff, T* dy,

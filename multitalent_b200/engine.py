@@ -410,6 +410,9 @@ class Engine:
         self.fuse_red = os.environ.get("MTB200_FUSE_RED", "1") != "0"
         self._pending_unpack = []
         self._unpack_tables = {}
+        # data parallel: called once in the backward pass, when every gradient except those of the first encoder stages is
+        # final (set by the trainer; the network places the call, see Generic_UNet._native_forward)
+        self.backward_mark: Optional[Callable] = None
 
     def begin_step(self):
         """Called at the start of every network forward: re-zero what the previous step took from the pools."""
@@ -757,6 +760,9 @@ class Engine:
                 torch.cuda.current_stream().wait_stream(st)
             self._side_used = None
         self._flush_unpack()
+
+    def side_streams_in_use(self):
+        return list(self._side_used) if self._side_used is not None else []
 
     def _flush_unpack(self):
         """grad += dw for every layer of this step in one launch.  The descriptor table lives on the device and is cached

@@ -380,6 +380,11 @@ class Generic_UNet(SegmentationNetwork):
                     f.act = eng.materialize(f, out=Feat(cat, op.Cout_p, op.Cout, op.Cout_p))
                 first = False
             skips.append(f)
+            # data parallel: in the backward pass everything recorded AFTER this point (deeper encoder stages,
+            # bottleneck, whole decoder, heads: > 99 % of the gradient bytes) is finished when this closure runs -- the
+            # trainer starts the gradient all-reduce there, under the backward of the two widest encoder stages
+            if ttape is not None and eng.backward_mark is not None and len(skips) == 2 and len(ops['enc']) > 2:
+                ttape.closures.append(eng.backward_mark)
         for (op, g, b) in ops['bott']:
             f = eng.conv_norm(ttape, op, g, b, f)
             f.single_consumer = True  # next bottleneck conv / the first transposed conv

@@ -292,6 +292,57 @@ class MultiTalent_trainer_ddp(OnlineEvaluationMixin, ValidationMixin):
                 else:
                     for p in self.network.parameters():
                         dist.broadcast(p.data, 0)
+        self._setup_overlapped_allreduce()
+
+    # ---- gradient exchange (replaces the DDP reducer of MT:121) --------------------------------------------------------
+    def _setup_overlapped_allreduce(self):
+        """Arena ranges for the two-part gradient all-reduce.  In the backward pass the gradients of everything but the
+        first two encoder stages (> 99 % of the bytes: decoder, bottleneck, deep encoder stages, heads) are final while
+        those two widest stages are still being differentiated: that part is all-reduced on a communication stream under
+        the rest of the backward pass, the small remainder afterwards.  MTB200_EARLY_ALLREDUCE=0: one all-reduce at the end."""
+        self._early_ranges = None
+        self._early_issued = False
+        net = self.network
+        if (self.arena is None or self.world_size <= 1 or os.environ.get("MTB200_EARLY_ALLREDUCE", "1") == "0"
+                or not hasattr(net, "conv_blocks_context") or len(net.conv_blocks_context) < 4):
+            return
+        late = {id(p) for st in list(net.conv_blocks_context)[:2] for p in st.parameters()}
+        off, lo, hi = 0, None, None
+        for p in self.arena.params:
+            k = FlatArena._slot(p)
+            if id(p) in late:
+                lo = off if lo is None else lo
+                hi = off + k
+            off += k
+        if lo is None:
+            return
+        self._late_range = (lo, hi)
+        self._early_ranges = [(a, b) for a, b in ((0, lo), (hi, self.arena.n)) if b > a]
+        self._comm_stream = torch.cuda.Stream()
+        net._engine.backward_mark = self._early_allreduce
+
+    def _early_allreduce(self):
+        """Backward-pass closure (placed by the network after its second encoder stage): fold the finished weight
+        gradients into the arena and all-reduce the early ranges on the communication stream."""
+        eng = self.network._engine
+        main, comm = torch.cuda.current_stream(), self._comm_stream
+        comm.wait_stream(main)
+        for st in eng.side_streams_in_use():   # weight-gradient launches of the finished layers
+            comm.wait_stream(st)
+        with torch.cuda.stream(comm):
+            eng._flush_unpack()
+            for a, b in self._early_ranges:
+                dist.all_reduce(self.arena.grad[a:b])
+        self._early_issued = True
+
+    def _finish_allreduce(self):
+        if self._early_ranges is not None and self._early_issued:
+            self._early_issued = False
+            a, b = self._late_range
+            dist.all_reduce(self.arena.grad[a:b])
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+        else:
+            dist.all_reduce(self.arena.grad)
 
     def maybe_update_lr(self, epoch=None):
         """nnUNetTrainerV2.py:393-408."""
@@ -396,7 +447,7 @@ class MultiTalent_trainer_ddp(OnlineEvaluationMixin, ValidationMixin):
         if do_backprop:
             if self.arena is not None:
                 if self.world_size > 1:
-                    dist.all_reduce(self.arena.grad)
+                    self._finish_allreduce()
                 inv = 1.0 / (self.loss_scale * self.world_size)
                 self.arena.step(self.lr, 0.99, self.weight_decay, 12.0, inv, scaler=self.amp_grad_scaler)
             else:
