@@ -287,6 +287,28 @@ int mtb200_ncdhw_to_ndhwc(const float* src, int32_t B, int32_t C, int64_t nvox, 
 int mtb200_ndhwc_to_ncdhw(const void* src, int32_t dtype, int32_t ldc, int32_t coff, int32_t B, int32_t C, int64_t nvox,
                           float* dst, void* stream);
 
+/* ---- the steps either side of the hot path on device-resident volumes ------------------------ */
+/* patch crop + pad out of a preprocessed case [C][X][Y][Z] fp32: dst[c][i][j][k] = src[c][lb + (i,j,k)] where that lies
+ * inside the case, else pad_values[c] (edge_mode 0: np.pad 'constant') or the nearest edge voxel (edge_mode 1: 'edge');
+ * replaces the slice + np.pad pairs of DataLoader3D.generate_train_batch, training/dataloading/dataset_loading.py:
+ * 340-378 (data channels padded with `pad_kwargs_data`, the label channel with -1). */
+int mtb200_crop_pad(const float* src, int32_t C, int32_t X, int32_t Y, int32_t Z, int32_t lbx, int32_t lby, int32_t lbz,
+                    float* dst, int32_t pd, int32_t ph, int32_t pw, int32_t edge_mode, const float* pad_values,
+                    void* stream);
+/* nearest-neighbour resize of NC label volumes [X][Y][Z] -> [X2][Y2][Z2] with skimage's pixel-centre convention
+ * (src index = floor((o + 0.5) * in / out), clamped); replaces resize_segmentation(order 0) inside
+ * downsample_seg_for_ds_transform2, training/data_augmentation/downsampling.py:87-104 (deep-supervision targets). */
+int mtb200_resize_nearest(const float* src, int64_t NC, int32_t X, int32_t Y, int32_t Z, float* dst, int32_t X2,
+                          int32_t Y2, int32_t Z2, void* stream);
+/* probability volume [C][X][Y][Z] fp32 -> original grid [X2][Y2][Z2] with per-axis interpolation order (0 nearest,
+ * 1 linear; "separate z" = order 0 along the low-resolution axis), pixel-centre coordinates, edge clamping; optional
+ * resampled probabilities (`prob`, fp32 or fp16 as the reference's npz) and the label map seg[v] = class_order[last c with
+ * p_c > 0.5] (class_order NULL: argmax); replaces resample_data_or_seg + the threshold loop of
+ * save_segmentation_nifti_from_softmax, inference/segmentation_export.py:77-123, preprocessing/preprocessing.py:109-197. */
+int mtb200_resample_probs(const float* src, int32_t C, int32_t X, int32_t Y, int32_t Z, int32_t X2, int32_t Y2, int32_t Z2,
+                          int32_t order_x, int32_t order_y, int32_t order_z, void* prob, int32_t prob_is_f16,
+                          const float* class_order, uint8_t* seg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,6 +129,9 @@ SIGNATURES = {
     "mtb200_unpack_wgrad": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp],
     "mtb200_ncdhw_to_ndhwc": [_vp, _i32, _i32, _i64, _vp, _i32, _i32, _i32, _i32, _vp],
     "mtb200_ndhwc_to_ncdhw": [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _vp],
+    "mtb200_crop_pad": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp],
+    "mtb200_resize_nearest": [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp],
+    "mtb200_resample_probs": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp],
 }
 
 _lib = None

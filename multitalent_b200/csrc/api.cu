@@ -84,6 +84,10 @@ int pack_weights_batched(const void*, int, int, int, cudaStream_t);
 int unpack_wgrad_batched(const void*, int, int, cudaStream_t);
 int ncdhw_to_ndhwc(const float*, int, int, long long, void*, int, int, int, int, cudaStream_t);
 int ndhwc_to_ncdhw(const void*, int, int, int, int, int, long long, float*, cudaStream_t);
+int crop_pad(const float*, int, int, int, int, int, int, int, float*, int, int, int, int, const float*, cudaStream_t);
+int resize_nearest(const float*, long long, int, int, int, float*, int, int, int, cudaStream_t);
+int resample_probs(const float*, int, int, int, int, int, int, int, int, int, int, void*, int, const float*,
+                   unsigned char*, cudaStream_t);
 
 static int validate_taps(int ngroups, const int32_t* begin, int ntaps) {
   MTB_REQUIRE(ngroups >= 1 && ngroups <= MTB200_MAX_GROUPS, "ngroups=%d out of range", ngroups);
@@ -312,6 +316,30 @@ int mtb200_ndhwc_to_ncdhw(const void* src, int32_t dtype, int32_t ldc, int32_t c
                           float* dst, void* stream) {
   MTB_REQUIRE(src && dst, "ndhwc_to_ncdhw: null pointer");
   return ndhwc_to_ncdhw(src, dtype, ldc, coff, B, C, nvox, dst, STREAM(stream));
+}
+
+int mtb200_crop_pad(const float* src, int32_t C, int32_t X, int32_t Y, int32_t Z, int32_t lbx, int32_t lby, int32_t lbz,
+                    float* dst, int32_t pd, int32_t ph, int32_t pw, int32_t edge_mode, const float* pad_values,
+                    void* stream) {
+  MTB_REQUIRE(src && dst && C >= 1 && X >= 1 && Y >= 1 && Z >= 1, "crop_pad: bad arguments");
+  return crop_pad(src, C, X, Y, Z, lbx, lby, lbz, dst, pd, ph, pw, edge_mode, pad_values, STREAM(stream));
+}
+
+int mtb200_resize_nearest(const float* src, int64_t NC, int32_t X, int32_t Y, int32_t Z, float* dst, int32_t X2,
+                          int32_t Y2, int32_t Z2, void* stream) {
+  MTB_REQUIRE(src && dst && X >= 1 && Y >= 1 && Z >= 1 && X2 >= 1 && Y2 >= 1 && Z2 >= 1, "resize_nearest: bad arguments");
+  return resize_nearest(src, NC, X, Y, Z, dst, X2, Y2, Z2, STREAM(stream));
+}
+
+int mtb200_resample_probs(const float* src, int32_t C, int32_t X, int32_t Y, int32_t Z, int32_t X2, int32_t Y2, int32_t Z2,
+                          int32_t order_x, int32_t order_y, int32_t order_z, void* prob, int32_t prob_is_f16,
+                          const float* class_order, uint8_t* seg, void* stream) {
+  MTB_REQUIRE(src && (prob || seg) && C >= 1, "resample_probs: bad arguments");
+  MTB_REQUIRE(order_x >= 0 && order_x <= 1 && order_y >= 0 && order_y <= 1 && order_z >= 0 && order_z <= 1,
+              "resample_probs: interpolation orders 0 (nearest) and 1 (linear) are implemented, got %d %d %d", order_x,
+              order_y, order_z);
+  return resample_probs(src, C, X, Y, Z, X2, Y2, Z2, order_x, order_y, order_z, prob, prob_is_f16, class_order, seg,
+                        STREAM(stream));
 }
 
 }  // extern "C"

@@ -98,6 +98,20 @@ def _decorate(module):
     elif name == "batchgenerators.augmentations.utils":
         from oracle.unet_oracle import pad_nd_image  # our restatement of the un-vendored third-party helper
         module.pad_nd_image = pad_nd_image
+    elif name == "batchgenerators.dataloading.data_loader":
+        # restated base class of the un-vendored batchgenerators (>= 0.23): its constructor only stores its arguments
+        class SlimDataLoaderBase(object):
+            def __init__(self, data, batch_size, number_of_threads_in_multithreaded=None):
+                self._data, self.batch_size = data, batch_size
+                self.number_of_threads_in_multithreaded = number_of_threads_in_multithreaded
+                self.thread_id = 0
+
+            def __iter__(self):
+                return self
+
+            def __next__(self):
+                return self.generate_train_batch()
+        module.SlimDataLoaderBase = SlimDataLoaderBase
 
 
 _installed = False

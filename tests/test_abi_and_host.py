@@ -35,12 +35,31 @@ def test_library_exports_every_declared_symbol():
     assert lib.mtb200_version() == 100
 
 
-def test_struct_layout_matches_header():
-    # sizes derived from the header: 6 pointers + ints; guards against ctypes/C drift
-    n_int_conv = 2 + 1 + 6 + 6 + 3 + 3 + 3 + 1 + (L.MAX_GROUPS + 1) + 3 * L.MAX_GROUPS + 1 + 3 * L.MAX_TAPS + L.MAX_TAPS + 2
-    assert ctypes.sizeof(L.ConvParams) == 6 * 8 + 4 * n_int_conv + (4 * n_int_conv) % 8
-    n_int_wg = 1 + 1 + 6 + 6 + 3 + 3 + 3 + 1 + (L.MAX_GROUPS + 1) + 3 * L.MAX_GROUPS + 1 + 3 * L.MAX_TAPS + L.MAX_TAPS + 1
-    assert ctypes.sizeof(L.WgradParams) == 4 * 8 + 4 * n_int_wg + (4 * n_int_wg) % 8
+def test_struct_layout_matches_header(tmp_path):
+    """sizeof / offsetof of the parameter blocks as the C compiler lays them out from include/mtb200.h == the ctypes
+    Structures of multitalent_b200/_lib.py (guards against ctypes/C drift)."""
+    import subprocess
+    fields = {"mtb200_conv_params": (L.ConvParams, ["in", "stats", "dtype", "Cin", "Do", "ngroups", "ntaps", "tap_widx",
+                                                     "accumulate", "red_y", "red", "red_ldc", "impl"]),
+              "mtb200_wgrad_params": (L.WgradParams, ["x", "xform", "dtype", "Cout", "ntaps", "tap_widx", "impl"]),
+              "mtb200_pack_desc": (L.PackDesc, ["w", "packed_swap", "Cout", "blk_begin"]),
+              "mtb200_unpack_desc": (L.UnpackDesc, ["dw", "grad", "Cout", "blk_begin"])}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "mtb200.h"', 'int main(void) {']
+    for st, (_, fl) in fields.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (st, st))
+        for f in fl:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (st, f, st, f))
+    lines += ['return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = str(tmp_path / "layout")
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe], check=True)
+    got = dict(l.split() for l in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines())
+    rename = {"in": "inp", "is": "is_", "os": "os_"}
+    for st, (cls, fl) in fields.items():
+        assert int(got[st]) == ctypes.sizeof(cls), st
+        for f in fl:
+            assert int(got["%s.%s" % (st, f)]) == getattr(cls, rename.get(f, f)).offset, (st, f)
 
 
 def test_pad_channels():
