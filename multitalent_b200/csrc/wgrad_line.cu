@@ -48,6 +48,8 @@ struct WgradLineParams {
   int nhr, hlen, ntw;
   int wt, nkk;               // w tile (128 / 64 / 32 voxels of one line) and its number of 16-voxel K steps
   long long units;
+  int npy, npz, nslots;      // (Cin chunk, Cout block) pairs and the number of CTA slots that walk the units
+  int cosched;               // 1: the pairs of a unit run side by side (default); 0: pair-major grid (A/B measurements)
   int lut[27];               // [dz+1][dy+1][dx+1] -> weight slice or -1
   int is_f16;
 };
@@ -65,8 +67,14 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __
   const uint32_t NCOLS = (uint32_t)p.ntot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
-  const int c0 = blockIdx.y * p.kcw;
-  const int n0 = blockIdx.z * p.cout_blk;
+  // CTA -> (pair, slot).  The pairs of ONE unit sit in neighbouring CTAs and run at the same time, so the X chunk / dY
+  // block a unit needs is fetched from DRAM once and served to the other pairs by the L2; pairs along grid.y / grid.z ran
+  // one after the other and re-streamed both tensors from DRAM per pair (r2j ncu: 4.5 GB for 0.76 GB of operands).
+  const int npairs = p.npy * p.npz;
+  const int pair = p.cosched ? (int)blockIdx.x % npairs : (int)blockIdx.x / p.nslots;
+  const int slot = p.cosched ? (int)blockIdx.x / npairs : (int)blockIdx.x % p.nslots;
+  const int c0 = (pair % p.npy) * p.kcw;
+  const int n0 = (pair / p.npy) * p.cout_blk;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 1); }
@@ -78,12 +86,12 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  const bool have_work = (long long)blockIdx.x < p.units;
+  const bool have_work = (long long)slot < p.units;
 
   if (warp == 0) {
     // ===== producer =====
     uint32_t sc = 0;  // global step counter of this CTA
-    for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+    for (long long u = slot; u < p.units; u += p.nslots) {
       long long t = u;
       const int hr = (int)(t % p.nhr); t /= p.nhr;
       const int twi = (int)(t % p.ntw); t /= p.ntw;
@@ -130,7 +138,7 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __
     const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, xline16 = (uint32_t)p.xline_bytes >> 4;
     const int ndz = p.ndz, nkk = (p.dbg & 2) ? 1 : p.nkk;
     uint32_t sc = 0;
-    for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+    for (long long u = slot; u < p.units; u += p.nslots) {
       const int hr = (int)(u % p.nhr);
       const int hs = hr * p.hlen, he = min(p.H, hs + p.hlen);
       for (int hp = hs; hp < he; ++hp, ++sc) {
@@ -302,8 +310,13 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   q.is_f16 = p.dtype == MTB200_F16;
   q.ntw = (p.Wo + q.wt - 1) / q.wt;
   const int sms = num_sms();
+  q.npy = nchunk;
+  q.npz = p.Cout / q.cout_blk;
+  const int npairs = q.npy * q.npz;
+  q.cosched = env_int_wl("MTB200_WLINE_COSCHED", 1) != 0;
+  const int slots_max = q.cosched ? max(1, sms / npairs) : sms;
   {
-    // split H into ranges so that every persistent CTA gets (almost) the same number of steps
+    // split H into ranges so that every persistent slot gets (almost) the same number of steps
     const long long base = (long long)p.B * p.Do * q.ntw;
     double best = -1;
     int best_nhr = 1;
@@ -311,7 +324,7 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
       const int hlen = (p.Ho + nhr - 1) / nhr;
       if ((p.Ho + hlen - 1) / hlen != nhr) continue;
       const long long units = base * nhr;
-      const long long g = units < sms ? units : sms;
+      const long long g = units < slots_max ? units : slots_max;
       const long long per = (units + g - 1) / g;
       const double eff = (double)units / (double)(per * g);
       if (eff > best + 1e-9) { best = eff; best_nhr = nhr; }
@@ -320,9 +333,9 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
     q.hlen = (p.Ho + q.nhr - 1) / q.nhr;
   }
   q.units = (long long)p.B * p.Do * q.ntw * q.nhr;
-  const int gx = (int)(q.units < sms ? q.units : sms);
+  q.nslots = (int)(q.units < slots_max ? q.units : slots_max);
   const int smem = max(116 * 1024, q.stages * q.stage_bytes + 1024);  // one CTA per SM (512 TMEM columns each)
-  dim3 grid((unsigned)gx, nchunk, p.Cout / q.cout_blk);
+  dim3 grid((unsigned)(q.nslots * npairs), 1, 1);
   cudaError_t e = cudaSuccess;
 #define WL_LAUNCH(RB, NS)                                                                                         \
   do {                                                                                                            \

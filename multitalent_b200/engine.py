@@ -413,11 +413,15 @@ class Engine:
         # data parallel: called once in the backward pass, when every gradient except those of the first encoder stages is
         # final (set by the trainer; the network places the call, see Generic_UNet._native_forward)
         self.backward_mark: Optional[Callable] = None
+        self.apply_inplace = os.environ.get("MTB200_APPLY_INPLACE", "1") != "0"
+        self._dy_bufs = []   # d(raw output) buffers when not in place: reused from step to step in call order
+        self._dy_next = 0
 
     def begin_step(self):
         """Called at the start of every network forward: re-zero what the previous step took from the pools."""
         self._z64.reset()
         self._z32.reset()
+        self._dy_next = 0
 
     @property
     def materialize_inputs(self) -> bool:
@@ -491,6 +495,22 @@ class Engine:
         L.call("mtb200_conv_taps", C.byref(p), L.stream_ptr(), flops=flops, tag=tag,
                info=(Cin_p, Cout_p, tuple(grid_dims), len(table.taps), table.in_stride, table.out_stride))
         return red is not None and (L.lib().mtb200_last_kernel() or b"").endswith(b"+red")
+
+    def _dy_buffer(self, dims, Cp, dev):
+        """The i-th d(raw output) buffer of this step (MTB200_APPLY_INPLACE=0): persistent across steps -- the weight-gradient
+        side streams that read it are joined before the next step starts -- and re-created when the shape changes."""
+        i = self._dy_next
+        self._dy_next += 1
+        shape = tuple(dims) + (Cp,)
+        if i < len(self._dy_bufs):
+            t = self._dy_bufs[i]
+            if tuple(t.shape) == shape and t.dtype == self.dtype and t.device == dev:
+                return t
+            self._dy_bufs[i] = t = torch.empty(shape, dtype=self.dtype, device=dev)
+            return t
+        t = torch.empty(shape, dtype=self.dtype, device=dev)
+        self._dy_bufs.append(t)
+        return t
 
     # ---- forward primitives -------------------------------------------------------------------------------------
     def conv(self, op: ConvOp, x: Feat, out: Optional[Feat] = None, want_stats=False):
@@ -571,11 +591,16 @@ class Engine:
         if not direct:
             dgamma = torch.zeros(y.Cp, dtype=torch.float32, device=dev)
             dbeta = torch.zeros(y.Cp, dtype=torch.float32, device=dev)
-        # in place (dy overwrites d(act)): measured faster than a separate output buffer (r2h: 4.06 vs 5.03 ms per step, and
-        # the consumers of a separate buffer ran slower too); the kernel reads an aliased operand with coherent loads
-        L.call("mtb200_in_bwd_apply", g.ptr(), g.ldc, g.coff, y.ptr(), y.ldc, y.coff, g.ptr(), g.ldc, g.coff, dt, B,
+        # In place by default (dy overwrites d(act); the kernel reads an aliased operand with coherent loads).
+        # MTB200_APPLY_INPLACE=0: a persistent compact buffer per layer instead, both inputs on the read-only load path.
+        if self.apply_inplace:
+            dy = g
+        else:
+            dy = Feat(self._dy_buffer(y.dims, y.Cp, dev), 0, y.C, y.Cp)
+        L.call("mtb200_in_bwd_apply", g.ptr(), g.ldc, g.coff, y.ptr(), y.ldc, y.coff, dy.ptr(), dy.ldc, dy.coff, dt, B,
                y.nvox, y.Cp, L.ptr(y.xform), L.ptr(y.meanrstd), L.ptr(gamma), L.ptr(red), L.ptr(dgamma), L.ptr(dbeta),
                L.stream_ptr())
+        g = dy
         if direct:
             tape.direct_done.update((id(gamma_param), id(beta_param)))
         else:
