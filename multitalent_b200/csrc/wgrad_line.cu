@@ -238,10 +238,11 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   if (p.Cin != 16 && p.Cin % 32 != 0) return MTB200_ERR_UNSUPPORTED;
   // every (Cin chunk, Cout block) pair re-streams both operands from L2: worth it while the pair count is small
   const bool cout48 = p.Cout == 48 && p.Cin <= 32;  // the 47 heads on the widest maps: one column block of 32 + 16
-  // MTB200_WLINE_MINW / MTB200_WLINE_MAXPAIRS: envelope knobs for A/B measurements (defaults = what measured fastest:
-  // 32-wide lines work -- tests cover them -- but every (Cin chunk, Cout block) pair re-streams both operands, and with
-  // 16..32 pairs at the third level the per-tap kernel is faster: 128->128 at 48x40x32 1.00 vs 1.25 ms, r2b)
-  static const int min_w = env_int_wl("MTB200_WLINE_MINW", 48), max_pairs = env_int_wl("MTB200_WLINE_MAXPAIRS", 32);
+  // MTB200_WLINE_MINW / MTB200_WLINE_MAXPAIRS: envelope knobs for A/B measurements (defaults = what measured fastest).
+  // 32-wide lines (third level, 16..32 pairs) lost to the per-tap kernel while every pair re-streamed its operands from
+  // DRAM (128->128 at 48x40x32: 1.25 vs 1.00 ms, r2b) and win since the pairs of a unit are co-scheduled (0.89 vs 1.04 ms,
+  // r2l); 16-wide lines (64 pairs) still lose (0.92 vs 0.41 ms).
+  static const int min_w = env_int_wl("MTB200_WLINE_MINW", 32), max_pairs = env_int_wl("MTB200_WLINE_MAXPAIRS", 32);
   if (!cout48 && (p.Cout % WL_BN || (p.Cin / 32) * (p.Cout / WL_BN) > max_pairs)) return MTB200_ERR_UNSUPPORTED;
   if (p.Wo < min_w || p.Wo < 16 || p.Ho < 4) return MTB200_ERR_UNSUPPORTED;
   bool all_dy0 = true;

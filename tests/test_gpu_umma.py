@@ -378,7 +378,7 @@ WGRAD_LINE_CASES = [
     (120, 120, (3, 3, 3), (1, 3, 5, 64), 0),     # 4 chunks x 4 Cout blocks
     (120, 120, (3, 3, 3), (2, 6, 10, 32), 0),    # 32-wide lines (level 2): two K steps per line
     (240, 120, (3, 3, 3), (1, 5, 8, 32), 120),   # 8 chunks x 4 Cout blocks = 32 pairs, concatenated input
-    (60, 60, (3, 3, 3), (1, 4, 6, 24), 0),       # ragged 32-wide tile
+    (60, 60, (3, 3, 3), (1, 4, 6, 28), 0),       # ragged 32-wide tile
     (30, 47, (1, 1, 1), (1, 4, 10, 128), 0),     # 1x1x1 head: one-line window, Cout 48 = segments of 32 + 16 channels
     (1, 47, (1, 1, 1), (2, 3, 6, 64), 0),        # Cin_p 16, 64-wide lines
     (30, 47, (1, 1, 1), (1, 2, 5, 100), 0),      # ragged
@@ -393,10 +393,6 @@ def test_wgrad_line_streaming_matches_ffma(dtype, cin, cout, kernel, dims, split
     from multitalent_b200.engine import ConvOp, Engine, Feat, Tape
     torch.manual_seed(1)
     B, D, H, W = dims
-    if W < 48:  # narrower lines are inside the kernel's envelope but not dispatched by default (MTB200_WLINE_MINW)
-        import os
-        if int(os.environ.get("MTB200_WLINE_MINW", "48")) > W:
-            pytest.skip("32-wide lines need MTB200_WLINE_MINW=32 (set before the library is first used)")
     conv = nn.Conv3d(cin, cout, kernel, 1, [(k - 1) // 2 for k in kernel], bias=True).to(DEV)
     op = ConvOp(conv.weight, conv.bias, kernel, (1, 1, 1), split=split)
     xb = torch.randn(B, D, H, W, op.Cin_p, device=DEV).to(dtype)
