@@ -40,6 +40,7 @@ static EncodeTiledFn get_encode_fn() {
 int conv_halo_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_halo.cu
 int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_line.cu
 int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s);  // wgrad_line.cu
+int wgrad_line_s2_umma(const mtb200_wgrad_params& p, cudaStream_t s);  // wgrad_line_s2.cu
 int conv_pw_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_pw.cu
 int conv_gm_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_gm.cu
 
@@ -725,7 +726,9 @@ int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
     if (p.is[k] < 1 || p.is[k] > 2 || p.os[k] < 1 || p.os[k] > 2) { set_error("wgrad_taps(umma): stride"); return MTB200_ERR_UNSUPPORTED; }
   const long long M = (long long)p.B * p.Do * p.Ho * p.Wo;
   if (M == 0) return MTB200_OK;
-  if (p.impl != 3) {  // line-streaming kernel first (impl 3 = per-tap kernel only, impl 5 = line-streaming only)
+  if (p.impl != 3) {  // line-streaming kernels first (impl 3 = per-tap kernel only, impl 5 = line-streaming only)
+    const int r2 = wgrad_line_s2_umma(p, s);  // stride-2 3x3x3 layers
+    if (r2 != MTB200_ERR_UNSUPPORTED) return r2;
     const int r = wgrad_line_umma(p, s);
     if (r != MTB200_ERR_UNSUPPORTED) return r;
     if (p.impl == 5) { set_error("wgrad_taps(umma): problem outside the line-streaming kernel's envelope"); return r; }

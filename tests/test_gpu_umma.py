@@ -580,3 +580,38 @@ def test_fused_instancenorm_backward_reduction_matches_separate_pass(dims, cmid,
     for k in res[0]:
         a, b = res[0][k].float(), res[1][k].float()
         assert float((a - b).abs().max()) <= 2e-3 * float(a.abs().max()) + 1e-6, k
+
+
+@pytest.mark.parametrize("cin,cout,dims", [
+    (30, 60, (1, 8, 12, 128)),     # the top strided layer's shape class: Cin_p 32, two Cout blocks, 64 output voxels per line
+    (30, 60, (2, 4, 8, 100)),      # ragged: 50 output voxels in a 64-wide tile
+    (60, 120, (1, 6, 16, 64)),     # second strided layer: 2 Cin chunks x 4 Cout blocks, 32 output voxels per line
+    (30, 30, (1, 4, 40, 128)),     # long in h: h ranges, boundary lines shared between units
+])
+def test_strided_wgrad_line_streaming_matches_library(cin, cout, dims):
+    """Stride-2 3x3x3 weight gradient through the parity-box line kernel (csrc/wgrad_line_s2.cu): against the CUDA-core
+    kernel and against autograd through the library convolution on the same bf16 operands."""
+    _require_tcgen05()
+    from multitalent_b200 import _lib as L
+    from multitalent_b200.engine import ConvOp, Engine, Feat, Tape
+    dtype = torch.bfloat16
+    torch.manual_seed(7)
+    B, D, H, W = dims
+    conv = nn.Conv3d(cin, cout, 3, 2, 1, bias=False).to(DEV)
+    op = ConvOp(conv.weight, None, (3, 3, 3), (2, 2, 2))
+    xb = torch.zeros(B, D, H, W, op.Cin_p, device=DEV, dtype=dtype)
+    xb[..., :cin] = torch.randn(B, D, H, W, cin, device=DEV).to(dtype)
+    dyb = torch.zeros(B, D // 2, H // 2, W // 2, op.Cout_p, device=DEV, dtype=dtype)
+    dyb[..., :cout] = torch.randn(B, D // 2, H // 2, W // 2, cout, device=DEV).to(dtype)
+    gws = []
+    for impl in (1, 0):
+        eng = Engine(dtype, impl)
+        tape = Tape()
+        with L.KernelProfile() as kp:
+            eng._conv_bwd(tape, op, Feat(xb, 0, cin, op.Cin_p), Feat(dyb, 0, cout, op.Cout_p), False, bias_grad_is_zero=True)
+        if impl == 0:
+            assert any(r[6] == "wgrad_line_s2_umma" for r in kp.records), [r[6] for r in kp.records]
+        gws.append(tape.param_grads[id(conv.weight)].clone())
+    assert float((gws[1] - gws[0]).abs().max()) <= 2e-3 * float(gws[0].abs().max()) + 1e-6
+    _, rgw = _lib_ref_grads(_logical(xb, cin), conv.weight, _logical(dyb, cout), (2, 2, 2), (3, 3, 3), dtype)
+    assert float((gws[1] - rgw).abs().max()) <= 2e-3 * float(rgw.abs().max()) + 1e-6
