@@ -541,7 +541,7 @@ def main():
             "top_shapes": [{"kernel": k[0], "shape": k[1], "launches": v["launches"],
                             "ms_per_step": round(v["ms"] / args.steps, 4),
                             "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["flops"] else None}
-                           for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])[:40]],
+                           for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])[:80]],
             "cuda_kernels": {k: {"launches": v["launches"], "ms_per_step": v["ms"] / args.steps,
                                  "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] and v["ms"] else None}
                              for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},

@@ -180,6 +180,11 @@ class KernelProfile:
         torch.cuda.synchronize()
         return [(name, info, e0.elapsed_time(e1), flops, nbytes) for name, e0, e1, flops, nbytes, info, _k in self.records]
 
+    def per_launch_kernels(self):
+        """[(tag, info, ms, flops, bytes, CUDA kernel)] in launch order."""
+        torch.cuda.synchronize()
+        return [(name, info, e0.elapsed_time(e1), flops, nbytes, k) for name, e0, e1, flops, nbytes, info, k in self.records]
+
     def per_cuda_kernel(self):
         """{CUDA kernel family the library dispatched to (mtb200_last_kernel): {launches, ms, flops}}."""
         torch.cuda.synchronize()

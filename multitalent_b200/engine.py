@@ -556,7 +556,9 @@ class Engine:
         L.call("mtb200_norm_act", x.ptr(), x.ldc, x.coff, out.ptr(), out.ldc, out.coff, L.dtype_enum(self.dtype), B,
                x.nvox, x.Cp, L.ptr(x.xform), res.ptr() if res is not None else None,
                res.ldc if res is not None else 0, res.coff if res is not None else 0,
-               L.ptr(res.xform) if res is not None else None, float(slope2), L.stream_ptr())
+               L.ptr(res.xform) if res is not None else None, float(slope2), L.stream_ptr(),
+               nbytes=(2 if res is None else 3) * B * x.nvox * x.Cp * x.buf.element_size(),
+               info=("norm_act", x.Cp, x.ldc, out.ldc, tuple(x.dims[1:])))
         return out
 
     # ---- composite layers with tape ------------------------------------------------------------------------------
@@ -585,7 +587,9 @@ class Engine:
         if red is None:  # the consumer's data-gradient kernel did not accumulate the sums: separate pass over g and y
             red = self._z64.take((B, y.Cp, 2), dev)
             L.call("mtb200_in_bwd_reduce", g.ptr(), g.ldc, g.coff, y.ptr(), y.ldc, y.coff, dt, B, y.nvox, y.Cp,
-                   L.ptr(y.xform), L.ptr(y.meanrstd), L.ptr(red), L.stream_ptr())
+                   L.ptr(y.xform), L.ptr(y.meanrstd), L.ptr(red), L.stream_ptr(),
+                   nbytes=2 * B * y.nvox * y.Cp * y.buf.element_size(),
+                   info=("in_bwd_reduce", y.Cp, g.ldc, y.ldc, tuple(y.dims[1:])))
         dgamma, dbeta = direct_grad(gamma_param, y.Cp), direct_grad(beta_param, y.Cp)
         direct = dgamma is not None and dbeta is not None
         if not direct:
@@ -599,7 +603,8 @@ class Engine:
             dy = Feat(self._dy_buffer(y.dims, y.Cp, dev), 0, y.C, y.Cp)
         L.call("mtb200_in_bwd_apply", g.ptr(), g.ldc, g.coff, y.ptr(), y.ldc, y.coff, dy.ptr(), dy.ldc, dy.coff, dt, B,
                y.nvox, y.Cp, L.ptr(y.xform), L.ptr(y.meanrstd), L.ptr(gamma), L.ptr(red), L.ptr(dgamma), L.ptr(dbeta),
-               L.stream_ptr())
+               L.stream_ptr(), nbytes=3 * B * y.nvox * y.Cp * y.buf.element_size(),
+               info=("in_bwd_apply", y.Cp, g.ldc, y.ldc, tuple(y.dims[1:])))
         g = dy
         if direct:
             tape.direct_done.update((id(gamma_param), id(beta_param)))

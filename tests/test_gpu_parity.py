@@ -351,7 +351,9 @@ def test_run_iteration_prefetch_matches_unprefetched(golden_small):
         results[prefetch] = (np.array(losses, dtype=np.float64),
                              torch.cat([p.detach().flatten().cpu() for p in tr.network.parameters()]))
     np.testing.assert_allclose(results[True][0], results[False][0], rtol=1e-5, atol=1e-6)
-    assert float((results[True][1] - results[False][1]).abs().max()) < 1e-5
+    # three SGD steps apart: the split-K weight gradients use fp32 atomics (run-to-run variation ~1e-5 of a tensor's largest
+    # entry, DESIGN.md "Run-to-run reproducibility"), a wrong batch would move the parameters by >1e-2
+    assert float((results[True][1] - results[False][1]).abs().max()) < 2e-4
     assert len({tuple(np.round(r, 6)) for r in results[True][0]}) == 3  # the three batches really differ
 
 

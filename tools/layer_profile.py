@@ -37,18 +37,19 @@ def main():
     torch.cuda.synchronize()
     with L.KernelProfile() as kp:
         tr.train_step(d, t, valid, True)
-    rows = kp.per_launch()
+    rows = kp.per_launch_kernels()
     tot = sum(r[2] for r in rows)
     print("# one training step, patch %s bs %d %s: %d launches, %.2f ms of kernel time" % (patch, a.batch, a.dtype, len(rows), tot))
     agg = {}
-    for name, info, ms, fl, nb in rows:
-        k = (name, info)
-        g = agg.setdefault(k, [0, 0.0, 0.0])
-        g[0] += 1; g[1] += ms; g[2] += fl
-    print("%-22s %-60s %5s %9s %6s %9s" % ("kernel", "Cin_p,Cout_p,grid,taps,is,os", "n", "ms", "%", "TFLOP/s"))
-    for (name, info), (n, ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print("%-22s %-60s %5d %9.3f %6.1f %9s" % (name, str(info) if info else "", n, ms, 100 * ms / tot,
-                                                     ("%.1f" % (fl / ms / 1e9)) if fl else "-"))
+    for name, info, ms, fl, nb, kern in rows:
+        k = (name + ":" + kern, info)
+        g = agg.setdefault(k, [0, 0.0, 0.0, 0.0])
+        g[0] += 1; g[1] += ms; g[2] += fl; g[3] += nb
+    print("%-44s %-60s %5s %9s %6s %9s %8s" % ("entry:kernel", "Cin_p,Cout_p,grid,taps,is,os", "n", "ms", "%", "TFLOP/s", "GB/s"))
+    for (name, info), (n, ms, fl, nb) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print("%-44s %-60s %5d %9.3f %6.1f %9s %8s" % (name, str(info) if info else "", n, ms, 100 * ms / tot,
+                                                         ("%.1f" % (fl / ms / 1e9)) if fl else "-",
+                                                         ("%.0f" % (nb / ms / 1e6)) if nb else "-"))
 
 
 if __name__ == "__main__":
