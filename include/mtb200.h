@@ -210,6 +210,33 @@ int mtb200_mt_loss_bwd(const void* logits, int32_t dtype, int32_t ldc, int32_t C
                        int64_t nvox, const uint64_t* pos_mask, int32_t n_labels, const float* coef, const float* gscale,
                        void* dlogits, int32_t d_ldc, void* stream);
 
+/* a5 + a9 backward in one pass (generic_UNet.py:349-351 backward + MultiTalent_Trainer_DDP.py:567-606 backward): pass 2 of
+ * the loss, the head's data gradient and the head's weight gradient of ONE 1x1x1 segmentation head (no bias).  A sample of
+ * a partially labelled dataset supervises a contiguous run of output channels; `win_c0[b]` (a multiple of 8) is the first
+ * channel of the 16-channel window that contains every supervised channel of sample b (coef[b][j][3] != 0 only inside it).
+ *   d[b][v][j]   = mtb200_mt_loss_bwd's formula, rounded to `dtype`, for j in the window of b (never written to memory)
+ *   dx[b][v][ci] (+)= sum_j d[b][v][j] * W[j][ci]            W: `w_swap`, packed [Cin][Cout] (mtb200_pack_weights, swap_io)
+ *   dw[j][ci]    += sum_{b,v} d[b][v][j] * x[b][v][ci]        dw: packed fp32 [Cout][Cin]
+ * 16-bit tensors only, Cin (padded) 32 or 64; MTB200_ERR_UNSUPPORTED otherwise (the caller runs the three separate
+ * passes). */
+#define MTB200_MAX_HEAD_BATCH 16
+typedef struct {
+  const void* logits;        /* [B][nvox][z_ldc] */
+  const float* target;       /* [B][nvox] label ids */
+  const float* coef;         /* [B][C8][4] from mtb200_mt_loss_finalize */
+  const float* gscale;       /* device scalar (upstream gradient x loss scale) or NULL */
+  const uint64_t* pos_mask;  /* [n_labels] label -> bitmask of positive output channels */
+  const void* x;             /* head input (materialised activation) [B][nvox][x_ldc], channels x_coff .. x_coff + Cin */
+  const void* w_swap;        /* [Cin][Cout], dtype */
+  void* dx;                  /* [B][nvox][dx_ldc], channels dx_coff .. dx_coff + Cin */
+  float* dw;                 /* [Cout][Cin] */
+  int64_t nvox;
+  int32_t dtype, B, z_ldc, C8, n_labels, x_ldc, x_coff, Cin, Cout, dx_ldc, dx_coff;
+  int32_t accumulate;        /* 1: dx += (another consumer already wrote its share) */
+  int32_t win_c0[MTB200_MAX_HEAD_BATCH];
+} mtb200_head_bwd_params;
+int mtb200_head_bwd_fused(const mtb200_head_bwd_params* p, void* stream);
+
 /* ---- a14/a15/a16: sliding-window predictor; replaces neural_network.py:374-394 (tile loop + host numpy accumulate),
  *      :531-589 (mirror TTA), :405 (normalise), :415-417 (threshold) ------------------------------------------------ */
 /* tile[0][d][h][w][c] = vol[c][x0+fd(d)][y0+fh(h)][z0+fw(w)] with optional flips (bit0: W, bit1: H, bit2: D);

@@ -87,6 +87,21 @@ class UnpackDesc(C.Structure):
     ]
 
 
+MAX_HEAD_BATCH = 16
+
+
+class HeadBwdParams(C.Structure):
+    _fields_ = [
+        ("logits", C.c_void_p), ("target", C.c_void_p), ("coef", C.c_void_p), ("gscale", C.c_void_p),
+        ("pos_mask", C.c_void_p), ("x", C.c_void_p), ("w_swap", C.c_void_p), ("dx", C.c_void_p), ("dw", C.c_void_p),
+        ("nvox", C.c_int64),
+        ("dtype", C.c_int32), ("B", C.c_int32), ("z_ldc", C.c_int32), ("C8", C.c_int32), ("n_labels", C.c_int32),
+        ("x_ldc", C.c_int32), ("x_coff", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32), ("dx_ldc", C.c_int32),
+        ("dx_coff", C.c_int32), ("accumulate", C.c_int32),
+        ("win_c0", C.c_int32 * MAX_HEAD_BATCH),
+    ]
+
+
 UNPACK_CHUNK = 4096
 _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
@@ -115,6 +130,7 @@ SIGNATURES = {
     "mtb200_mt_loss_stats": [_vp, _i32, _i32, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp],
     "mtb200_mt_loss_finalize": [_vp, _vp, _vp, _i32, _i32, _i64, _f32, _f32, _vp, _vp, _vp],
     "mtb200_mt_loss_bwd": [_vp, _i32, _i32, _i32, _vp, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _vp],
+    "mtb200_head_bwd_fused": [C.POINTER(HeadBwdParams), _vp],
     "mtb200_sw_gather_tile": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32,
                               _vp],
     "mtb200_sw_aggregate": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _f32, _i32, _vp, _vp, _i32, _i32, _i32,

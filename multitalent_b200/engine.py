@@ -408,6 +408,14 @@ class Engine:
         self.batch_unpack = os.environ.get("MTB200_UNPACK_BATCHED", "1") != "0"
         # InstanceNorm-backward reduction fused into the consumer's data-gradient epilogue where the kernel supports it
         self.fuse_red = os.environ.get("MTB200_FUSE_RED", "1") != "0"
+        # Heads under the MultiTalent loss: loss pass 2 + head data gradient + head weight gradient as ONE kernel
+        # (mtb200_head_bwd_fused).  The loss's backward leaves a descriptor in `lazy_heads` instead of writing d(logits).
+        self.fuse_head = os.environ.get("MTB200_FUSE_HEAD", "1") != "0"
+        self.fusable_heads = {}  # logits buffer pointer -> True, for the heads of the current step the kernel covers
+        self.lazy_heads = {}     # logits buffer pointer -> what the fused kernel needs from the loss
+        self.wgrad_order = int(os.environ.get("MTB200_WGRAD_ORDER", "0"))
+        self.bwd_priority = os.environ.get("MTB200_BWD_PRIO", "0") != "0"
+        self._hp = {}
         self._pending_unpack = []
         self._unpack_tables = {}
         # data parallel: called once in the backward pass, when every gradient except those of the first encoder stages is
@@ -422,6 +430,8 @@ class Engine:
         self._z64.reset()
         self._z32.reset()
         self._dy_next = 0
+        self.fusable_heads.clear()
+        self.lazy_heads.clear()
 
     @property
     def materialize_inputs(self) -> bool:
@@ -625,7 +635,7 @@ class Engine:
                 tape.add_param_grad(p, torch.zeros_like(p))
 
     @contextlib.contextmanager
-    def _wgrad_stream(self, op: ConvOp, dev):
+    def _wgrad_stream(self, op: ConvOp, dev, after=None):
         """Side stream for one layer's weight-gradient launches (ordered after everything already queued on the current
         stream, i.e. after d(raw output) was written); `run_backward` joins it.  Only with in-place arena gradients: a
         gradient tensor handed to autograd would have to cross streams."""
@@ -641,7 +651,10 @@ class Engine:
             pool = self._side[dev] = [[torch.cuda.Stream(dev) for _ in range(n)], 0]
         side = pool[0][pool[1] % len(pool[0])]
         pool[1] += 1
-        side.wait_stream(torch.cuda.current_stream(dev))
+        if after is not None:
+            side.wait_event(after)
+        else:
+            side.wait_stream(torch.cuda.current_stream(dev))
         self._side_used = pool[0]
         with torch.cuda.stream(side):
             yield
@@ -680,8 +693,19 @@ class Engine:
         x = self.operand(x)
         # ---- weight gradient (same tap table as the forward problem)
         dw = self._z32.take((op.ntap, op.Cout_p, op.Cin_p), dev)
-        with self._wgrad_stream(op, dev):
-            self._wgrad(tape, op, x, dy, dw, dt, dev, need_input_grad, bias_grad_is_zero)
+        # Launch order (MTB200_WGRAD_ORDER).  0: weight gradient first (as in round 1) -- its persistent CTAs take every SM
+        # and the data gradient, which the rest of the backward chain waits for, queues behind it.  1 (default): data
+        # gradient first; the weight gradient depends only on d(raw output) and is enqueued behind it on the side stream,
+        # so it shares the SMs with the HBM-bound InstanceNorm-backward passes of the NEXT layer instead of delaying them.
+        # 2: as 1, but the weight gradient also waits for the data gradient to finish.
+        order = self.wgrad_order if (need_input_grad and self.overlap_wgrad and dev.type == "cuda") else 0
+        ready = None
+        if order == 1:
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(dev))
+        if order == 0:
+            with self._wgrad_stream(op, dev):
+                self._wgrad(tape, op, x, dy, dw, dt, dev, need_input_grad, bias_grad_is_zero)
         # ---- data gradient
         if not need_input_grad:
             return
@@ -701,6 +725,32 @@ class Engine:
         if took:
             raw.red_fused = red[1]
         tape.mark(x)
+        if order:
+            with self._wgrad_stream(op, dev, after=ready):
+                self._wgrad(tape, op, x, dy, dw, dt, dev, need_input_grad, bias_grad_is_zero)
+
+    def _head_bwd_fused(self, tape, op: ConvOp, x: Feat, y: Feat, spec):
+        """d(loss)/d(logits) (never stored) -> head data gradient + head weight gradient, one launch."""
+        dev = y.buf.device
+        dt = L.dtype_enum(self.dtype)
+        x = self.operand(x)
+        gx, have = tape.grad_feat(x)
+        dw = self._z32.take((op.ntap, op.Cout_p, op.Cin_p), dev)
+        p = L.HeadBwdParams()
+        p.logits, p.target, p.coef = y.ptr(), spec["target"].data_ptr(), spec["coef"].data_ptr()
+        p.gscale, p.pos_mask = spec["gscale"].data_ptr(), spec["pos"].data_ptr()
+        p.x, p.w_swap, p.dx, p.dw = x.ptr(), op.packed(self.wdtype, True).data_ptr(), gx.ptr(), dw.data_ptr()
+        p.nvox, p.dtype, p.B = y.nvox, dt, y.dims[0]
+        p.z_ldc, p.C8, p.n_labels = y.ldc, spec["C8"], spec["n_labels"]
+        p.x_ldc, p.x_coff, p.Cin, p.Cout = x.ldc, x.coff, op.Cin_p, op.Cout_p
+        p.dx_ldc, p.dx_coff, p.accumulate = gx.ldc, gx.coff, int(have)
+        for b, c0 in enumerate(spec["win"]):
+            p.win_c0[b] = c0
+        L.call("mtb200_head_bwd_fused", C.byref(p), L.stream_ptr(), flops=2 * self.conv_flops(op, y.dims),
+               tag="conv_head_bwd", info=(op.Cin_p, op.Cout_p, tuple(y.dims[1:]), 1, (1, 1, 1), (1, 1, 1)))
+        tape.mark(x)
+        tape.keep.append(spec)
+        self._finish_wgrad(tape, op, dw, None, dt, dev, bias_grad_is_zero=True)
 
     def _finish_wgrad(self, tape, op: ConvOp, dw, dy: Feat, dt, dev, bias_grad_is_zero):
         """Packed fp32 weight gradient -> the parameter's gradient (arena slot or autograd), plus the bias gradient."""
@@ -729,11 +779,20 @@ class Engine:
             tape.add_param_grad(op.bias, gb[:op.Cout])
 
     def conv_plain(self, tape: Optional[Tape], op: ConvOp, x: Feat, out: Optional[Feat] = None,
-                   need_input_grad=True) -> Feat:
-        """Convolution with no normalisation after it (transposed-conv upsampling, 1x1x1 heads)."""
+                   need_input_grad=True, head=False) -> Feat:
+        """Convolution with no normalisation after it (transposed-conv upsampling, 1x1x1 heads).  `head`: a segmentation
+        head whose output goes to the loss -- its backward may arrive as a `lazy_heads` descriptor (fused kernel)."""
         y, _ = self.conv(op, x, out)
+        if (head and tape is not None and self.fuse_head and need_input_grad and op.bias is None and op.ntap == 1
+                and not op.transposed and op.Cin_p in (32, 64) and self.materialize_inputs and y.coff == 0
+                and y.ldc == y.Cp and y.dims[0] <= L.MAX_HEAD_BATCH):
+            self.fusable_heads[y.buf.data_ptr()] = True
         if tape is not None:
             def bwd():
+                spec = self.lazy_heads.pop(y.buf.data_ptr(), None)
+                if spec is not None:
+                    self._head_bwd_fused(tape, op, x, y, spec)
+                    return
                 if not tape.has_grad(y):
                     self._zero_param_grads(tape, op)
                     return
@@ -782,8 +841,21 @@ class Engine:
         tape.mark(y)
 
     def run_backward(self, tape: Tape):
-        for c in reversed(tape.closures):
-            c()
+        if self.bwd_priority and torch.cuda.is_available():
+            # the dgrad / InstanceNorm-backward chain on a high-priority stream: when an SM frees up, its blocks are
+            # placed before the queued weight-gradient CTAs of the side streams
+            cur = torch.cuda.current_stream()
+            hp = self._hp.get(cur.device)
+            if hp is None:
+                hp = self._hp[cur.device] = torch.cuda.Stream(cur.device, priority=-1)
+            hp.wait_stream(cur)
+            with torch.cuda.stream(hp):
+                for c in reversed(tape.closures):
+                    c()
+            cur.wait_stream(hp)
+        else:
+            for c in reversed(tape.closures):
+                c()
         tape.closures = []
         if self._side_used is not None:  # the optimizer (and the next forward's pool reset) must see every weight gradient
             for st in self._side_used:

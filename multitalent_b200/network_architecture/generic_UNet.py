@@ -141,7 +141,8 @@ class _UNetFunction(torch.autograd.Function):
         net, tape = ctx.net, ctx.tape
         eng = net._engine
         for f, g in zip(ctx.feats, grads):
-            if g is not None:
+            # a head whose d(logits) stayed with the loss (engine.lazy_heads) is seeded by the fused kernel itself
+            if g is not None and f.buf.data_ptr() not in eng.lazy_heads:
                 eng.seed_grad(tape, f, g)
         eng.run_backward(tape)
         out = []
@@ -411,7 +412,7 @@ class Generic_UNet(SegmentationNetwork):
                 f.single_consumer = i < nd - 1 or u == nu - 1
             if only_full_res and u != nu - 1:
                 continue
-            logits.append(eng.conv_plain(tape, ops['head'][u], f, need_input_grad=head_dgrad))
+            logits.append(eng.conv_plain(tape, ops['head'][u], f, need_input_grad=head_dgrad, head=True))
         return logits[::-1]
 
     def forward(self, x):

@@ -505,7 +505,8 @@ class FabiansUNet(SegmentationNetwork):
                 f = eng.conv_norm(ttape, op, nrm.weight, nrm.bias, f)
             if head is None or (only_full_res and i != nd - 1):
                 continue
-            logits.append(eng.conv_plain(tape, ConvOpCache.get(self, head), f, need_input_grad=ttape is not None))
+            logits.append(eng.conv_plain(tape, ConvOpCache.get(self, head), f, need_input_grad=ttape is not None,
+                                         head=True))
         return logits[::-1]
 
     def native_logits(self, tile: Feat) -> Feat:
@@ -635,7 +636,7 @@ class ResidualUNet(SegmentationNetwork):
                 f = _run_block(eng, tape, blk, f)
             if heads[i] is None or (only_full_res and i != nd - 1):
                 continue
-            logits.append(eng.conv_plain(tape, ConvOpCache.get(self, heads[i]), f))
+            logits.append(eng.conv_plain(tape, ConvOpCache.get(self, heads[i]), f, head=True))
         return logits[::-1]
 
     def native_logits(self, tile: Feat) -> Feat:

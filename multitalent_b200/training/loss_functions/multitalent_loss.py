@@ -62,7 +62,7 @@ def _as_ndhwc(t: torch.Tensor, dtype):
 
 class _MultiTalentLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, valid_mask, weights, group, targets, hard_out, *logits):
+    def forward(ctx, valid_mask, weights, group, targets, hard_out, lazy, *logits):
         dev = logits[0].device
         world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         pos = _pos_mask(dev)
@@ -109,6 +109,7 @@ class _MultiTalentLossFn(torch.autograd.Function):
         ctx.shapes = [tuple(z.shape) for z in logits]
         ctx.pos = pos
         ctx.C8 = C8
+        ctx.lazy = lazy
         return losses[0], losses[1], losses[2]
 
     @staticmethod
@@ -119,6 +120,17 @@ class _MultiTalentLossFn(torch.autograd.Function):
         for i in ctx.active:
             zv, ldc, dt, tgt, nvox = ctx.views[i]
             B, Cc, D, H, W = ctx.shapes[i]
+            if ctx.lazy is not None:
+                # the network's engine runs this head's backward as ONE kernel (loss pass 2 + head data gradient + head
+                # weight gradient, mtb200_head_bwd_fused): d(logits) is never written.  What flows through autograd is a
+                # zero-stride placeholder of the right shape; the descriptor travels beside it, keyed by the buffer.
+                eng, win = ctx.lazy
+                if (eng.fusable_heads.get(zv.data_ptr()) and dt in (torch.bfloat16, torch.float16) and ldc == ctx.C8
+                        and ctx.needs_input_grad[6 + i]):
+                    eng.lazy_heads[zv.data_ptr()] = {"target": tgt, "coef": ctx.coefs[i], "gscale": gs, "pos": ctx.pos,
+                                                     "C8": ctx.C8, "n_labels": NUM_LABELS, "win": win}
+                    grads[i] = torch.zeros((), dtype=dt, device=zv.device).expand(B, Cc, D, H, W)
+                    continue
             dz = torch.empty((B, D, H, W, ldc), dtype=dt, device=zv.device)
             if ldc > ctx.C8:
                 dz[..., ctx.C8:].zero_()
@@ -126,12 +138,12 @@ class _MultiTalentLossFn(torch.autograd.Function):
                    NUM_LABELS, L.ptr(ctx.coefs[i]), L.ptr(gs), L.ptr(dz), ldc, st)
             grads[i] = dz.permute(0, 4, 1, 2, 3)[:, :Cc]
         for i in range(ctx.n):
-            if grads[i] is None and ctx.needs_input_grad[5 + i]:
+            if grads[i] is None and ctx.needs_input_grad[6 + i]:
                 B, Cc, D, H, W = ctx.shapes[i]
                 Cp = pad_channels(Cc)
                 grads[i] = torch.zeros((B, D, H, W, Cp), dtype=ctx.views[ctx.active[0]][2],
                                        device=g_loss.device).permute(0, 4, 1, 2, 3)[:, :Cc]
-        return (None, None, None, None, None) + tuple(grads)
+        return (None, None, None, None, None, None) + tuple(grads)
 
 
 _VALID_MASK_CACHE = {}
@@ -152,9 +164,37 @@ def valid_mask_tensor(valid_regions: Sequence[Sequence[str]], device) -> torch.T
     return t
 
 
-def multitalent_loss(outputs, targets, valid_regions, ds_loss_weights, group=None, hard_out=None):
+_WINDOW_CACHE = {}
+
+
+def head_windows(valid_regions, C8, width=16):
+    """Per sample: first channel (a multiple of 8) of a `width`-channel window that holds every supervised output channel
+    of the sample's dataset (the regions of one dataset are consecutive output channels, Task100 tables), or None when
+    some sample's channels do not fit one window -- then the heads run the unfused passes."""
+    key = (tuple(tuple(v) for v in valid_regions), C8, width)
+    if key not in _WINDOW_CACHE:
+        if len(_WINDOW_CACHE) > 4096:
+            _WINDOW_CACHE.clear()
+        win = []
+        for v in valid_regions:
+            m = valid_channel_mask(v)
+            if m == 0:
+                win.append(0)
+                continue
+            first, last = (m & -m).bit_length() - 1, m.bit_length() - 1
+            c0 = max(0, min(first // 8 * 8, C8 - width))
+            if last >= c0 + width or first < c0:
+                win = None
+                break
+            win.append(c0)
+        _WINDOW_CACHE[key] = tuple(win) if win is not None else None
+    return _WINDOW_CACHE[key]
+
+
+def multitalent_loss(outputs, targets, valid_regions, ds_loss_weights, group=None, hard_out=None, engine=None):
     """(total_loss, total_ce, total_dc) as 0-dim CUDA tensors; `total_loss` is differentiable w.r.t. `outputs`.
     Only d(total_loss) is propagated (the trainer calls `l.backward()`; ce/dc are reporting values, MT:370).
+    `engine`: the `Engine` of the network that produced `outputs` (optional) -- enables the fused head backward.
     `hard_out` (a dict, optional): filled with the hard tp / fp / fn [B, 47] of the highest-resolution output (the
     counts `run_online_evaluation` needs, MT:372-397) computed inside the loss's own statistics pass."""
     if not isinstance(outputs, (tuple, list)):
@@ -163,4 +203,10 @@ def multitalent_loss(outputs, targets, valid_regions, ds_loss_weights, group=Non
         raise L.Mtb200Error("multitalent_loss runs on the native CUDA path only; logits are on %s" % outputs[0].device)
     vm = valid_regions if torch.is_tensor(valid_regions) else valid_mask_tensor(valid_regions, outputs[0].device)
     weights = [float(w) for w in ds_loss_weights][:len(outputs)]
-    return _MultiTalentLossFn.apply(vm, weights, group, list(targets), hard_out, *outputs)
+    # `engine` (the network's kernel layer): lets the heads' backward run fused with the loss's second pass
+    lazy = None
+    if engine is not None and getattr(engine, "fuse_head", False) and not torch.is_tensor(valid_regions):
+        win = head_windows(valid_regions, (outputs[0].shape[1] + 7) // 8 * 8)
+        if win is not None:
+            lazy = (engine, win)
+    return _MultiTalentLossFn.apply(vm, weights, group, list(targets), hard_out, lazy, *outputs)

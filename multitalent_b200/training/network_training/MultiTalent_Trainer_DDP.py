@@ -356,7 +356,8 @@ class MultiTalent_trainer_ddp(OnlineEvaluationMixin, ValidationMixin):
         """MT:544-623 -> (total_loss, total_ce, total_dc).  When the step will be followed by `run_online_evaluation`
         (`_want_hard_stats`), the statistics pass also counts the hard tp / fp / fn of the full-resolution output."""
         hard = {} if getattr(self, "_want_hard_stats", False) else None
-        res = multitalent_loss(output, target, valid_regions, self.ds_loss_weights, hard_out=hard)
+        res = multitalent_loss(output, target, valid_regions, self.ds_loss_weights, hard_out=hard,
+                               engine=getattr(self.network, "_engine", None))
         self._hard_stats = hard
         return res
 

@@ -28,6 +28,7 @@ def main():
     torch.manual_seed(0)
     tr.initialize(True)
     tr.network._engine.impl = a.impl
+    tr.network._engine.overlap_wgrad = False  # per-kernel durations: nothing else shares the SMs
     batch = synthetic_batch(patch, a.batch, 0, tr.deep_supervision_scales)
     valid = [p['valid_regions'] for p in batch['properties']]
     d = torch.from_numpy(batch['data']).cuda()
