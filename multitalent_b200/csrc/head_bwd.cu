@@ -75,7 +75,8 @@ template <> __device__ __forceinline__ float2 hb_unpack2<__half>(uint32_t w) {
 __device__ __forceinline__ uint64_t hb_desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
 
 // CIN = padded input channels of the head (32: full resolution, 64: second level)
-template <typename T, int CIN>
+// ACC: d(input) += (the level's transposed convolution already wrote its share)
+template <typename T, int CIN, bool ACC>
 __global__ void __launch_bounds__(HB_THREADS, CIN == 32 ? 3 : 2) head_bwd_fused_kernel(const __grid_constant__ HeadBwdParams p) {
   constexpr int ROWB = CIN * 2;            // bytes per input row
   constexpr int ACT_BYTES = 128 * ROWB;    // one staged input tile
@@ -208,6 +209,18 @@ __global__ void __launch_bounds__(HB_THREADS, CIN == 32 ? 3 : 2) head_bwd_fused_
     };
     auto epilogue = [&](uint32_t i, long long t) {
       const uint32_t buf = i & 1u;
+      // accumulate: the other consumer's share of d(input), requested before the wait for the tensor core so that its
+      // DRAM latency overlaps it (same rows / pieces as the write-out below)
+      uint4 old[ACC ? NCH : 1];
+      if (ACC) {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+          const long long v = min(t * 128 + q * 32 + j * RPI + lane / NCH, p.nvox - 1);
+          const T* src = dxb + v * p.dx_ldc + (lane % NCH) * 8;
+          asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(old[j].x), "=r"(old[j].y), "=r"(old[j].z), "=r"(old[j].w) : "l"(src));
+        }
+      }
       mbar_wait(&d1_full[buf], (i >> 1) & 1u);
       tc_fence_after();
       // accumulator row -> 16-bit -> this warp's staging rows (pieces XOR-swizzled: conflict-free both ways)
@@ -239,9 +252,8 @@ __global__ void __launch_bounds__(HB_THREADS, CIN == 32 ? 3 : 2) head_bwd_fused_
         const long long v = t * 128 + q * 32 + row;
         if (v < p.nvox) {
           uint4* dst = reinterpret_cast<uint4*>(dxb + v * p.dx_ldc + piece * 8);
-          if (p.accumulate) {
-            const uint4 o = *dst;
-            const uint32_t* ow = reinterpret_cast<const uint32_t*>(&o);
+          if (ACC) {
+            const uint32_t* ow = reinterpret_cast<const uint32_t*>(&old[ACC ? j : 0]);
             uint32_t* ww = reinterpret_cast<uint32_t*>(&w);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -358,16 +370,21 @@ int head_bwd_fused(const mtb200_head_bwd_params& p, cudaStream_t s) {
   const int smem = HB_STAGES * 128 * rowb + 1024 + 2 * 4096 + ((p.Cin * 32 + 1023) / 1024) * 1024 + 4 * 32 * rowb + 1024;
   dim3 grid((unsigned)(q.cps * p.B));
   cudaError_t e = cudaSuccess;
-#define HB_LAUNCH(T, CIN)                                                                                          \
-  do {                                                                                                             \
-    e = cudaFuncSetAttribute(head_bwd_fused_kernel<T, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);    \
-    if (e == cudaSuccess) head_bwd_fused_kernel<T, CIN><<<grid, HB_THREADS, smem, s>>>(q);                         \
+#define HB_LAUNCH2(T, CIN, ACC)                                                                                      \
+  do {                                                                                                               \
+    e = cudaFuncSetAttribute(head_bwd_fused_kernel<T, CIN, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+    if (e == cudaSuccess) head_bwd_fused_kernel<T, CIN, ACC><<<grid, HB_THREADS, smem, s>>>(q);                      \
+  } while (0)
+#define HB_LAUNCH(T, CIN)                                                     \
+  do {                                                                        \
+    if (p.accumulate) HB_LAUNCH2(T, CIN, true); else HB_LAUNCH2(T, CIN, false); \
   } while (0)
   if (p.dtype == MTB200_BF16) {
     if (p.Cin == 32) HB_LAUNCH(__nv_bfloat16, 32); else HB_LAUNCH(__nv_bfloat16, 64);
   } else {
     if (p.Cin == 32) HB_LAUNCH(__half, 32); else HB_LAUNCH(__half, 64);
   }
+#undef HB_LAUNCH2
 #undef HB_LAUNCH
   if (e != cudaSuccess) { set_error("head_bwd_fused: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
   return check_launch("head_bwd_fused");

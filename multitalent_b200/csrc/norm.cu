@@ -9,6 +9,15 @@ namespace mtb {
 
 constexpr int NT = 256;
 
+// norm_tma.cu
+int in_bwd_apply_tma(const void* dact, int d_ldc, int d_coff, const void* y, int y_ldc, int y_coff, void* dy, int dy_ldc,
+                     int dy_coff, int dtype, int B, long long nvox, int C, const float* xform, const float* meanrstd,
+                     const float* gamma, const double* red, float* dgamma, float* dbeta, cudaStream_t s);
+int norm_act_tma(const void* y, int in_ldc, int in_coff, void* out, int out_ldc, int out_coff, int dtype, int B,
+                 long long nvox, int C, const float* xform, cudaStream_t s);
+int in_bwd_reduce_tma(const void* dact, int d_ldc, int d_coff, const void* y, int y_ldc, int y_coff, int dtype, int B,
+                      long long nvox, int C, const float* xform, const float* meanrstd, double* red, cudaStream_t s);
+
 struct Span {  // work split of one sample's voxels over gridDim.x blocks
   long long v0, v1;
   int cg, vlane, vstride;
@@ -188,6 +197,10 @@ int norm_act(const void* y, int in_ldc, int in_coff, void* out, int out_ldc, int
   MTB_REQUIRE(C % 8 == 0 && C / 8 <= NT && in_ldc % 8 == 0 && in_coff % 8 == 0 && out_ldc % 8 == 0 && out_coff % 8 == 0,
               "norm_act: channel counts/strides must be multiples of 8 (C=%d)", C);
   if (res) MTB_REQUIRE(res_ldc % 8 == 0 && res_coff % 8 == 0, "norm_act: residual stride/offset must be x8");
+  if (!res && dtype != MTB200_F32) {
+    const int r = norm_act_tma(y, in_ldc, in_coff, out, out_ldc, out_coff, dtype, B, nvox, C, xform, s);
+    if (r != MTB200_ERR_UNSUPPORTED) return r;
+  }
   dim3 grid = span_grid(nvox, B, C);
 #define MTB_NORM_ACT(NU_)                                                                                        \
   MTB_DISPATCH_DTYPE(dtype, T, (norm_act_kernel<T, NU_><<<grid, NT, 0, s>>>(                                     \
@@ -253,6 +266,10 @@ int in_bwd_reduce(const void* dact, int d_ldc, int d_coff, const void* y, int y_
                   long long nvox, int C, const float* xform, const float* meanrstd, double* red, cudaStream_t s) {
   MTB_REQUIRE(C % 8 == 0 && C / 8 <= NT && d_ldc % 8 == 0 && d_coff % 8 == 0 && y_ldc % 8 == 0 && y_coff % 8 == 0,
               "in_bwd_reduce: channel counts/strides must be multiples of 8 (C=%d)", C);
+  if (dtype != MTB200_F32) {
+    const int r = in_bwd_reduce_tma(dact, d_ldc, d_coff, y, y_ldc, y_coff, dtype, B, nvox, C, xform, meanrstd, red, s);
+    if (r != MTB200_ERR_UNSUPPORTED) return r;
+  }
   dim3 grid = span_grid(nvox, B, C);
 #define MTB_IN_RED(NU_)                                                                                          \
   MTB_DISPATCH_DTYPE(dtype, T, (in_bwd_reduce_kernel<T, NU_><<<grid, NT, 0, s>>>(                                \
@@ -410,6 +427,11 @@ int in_bwd_apply(const void* dact, int d_ldc, int d_coff, const void* y, int y_l
   MTB_REQUIRE(C % 8 == 0 && C / 8 <= NT && d_ldc % 8 == 0 && d_coff % 8 == 0 && y_ldc % 8 == 0 && y_coff % 8 == 0 &&
                   dy_ldc % 8 == 0 && dy_coff % 8 == 0,
               "in_bwd_apply: channel counts/strides must be multiples of 8 (C=%d)", C);
+  if (dtype != MTB200_F32) {  // TMA-pipelined version (norm_tma.cu); UNSUPPORTED = outside its envelope or switched off
+    const int r = in_bwd_apply_tma(dact, d_ldc, d_coff, y, y_ldc, y_coff, dy, dy_ldc, dy_coff, dtype, B, nvox, C, xform,
+                                   meanrstd, gamma, red, dgamma, dbeta, s);
+    if (r != MTB200_ERR_UNSUPPORTED) return r;
+  }
   dim3 grid = span_grid(nvox, B, C);
 #define MTB_IN_APPLY(NU_)                                                                                        \
   MTB_DISPATCH_DTYPE(dtype, T, (in_bwd_apply_kernel<T, NU_><<<grid, NT, 0, s>>>(                                 \
