@@ -15,7 +15,7 @@ INCLUDE = os.path.join(REPO_ROOT, "include")
 LIB_PATH = os.path.join(PKG_DIR, "libmtb200.so")
 OBJ_DIR = os.path.join(PKG_DIR, "build")
 
-SOURCES = ["api.cu", "conv_ffma.cu", "conv_umma.cu", "conv_halo.cu", "conv_line.cu", "conv_pw.cu", "head_bwd.cu", "conv_gm.cu", "conv_c1.cu", "wgrad_line.cu", "wgrad_line_s2.cu", "norm.cu", "norm_tma.cu", "loss.cu", "loss_softmax.cu", "sliding.cu", "optim_pack.cu", "dataio.cu"]
+SOURCES = ["api.cu", "conv_ffma.cu", "conv_umma.cu", "conv_halo.cu", "conv_line.cu", "conv_pw.cu", "head_bwd.cu", "conv_gm.cu", "conv_c1.cu", "wgrad_line.cu", "wgrad_line_s2.cu", "wgrad_rows.cu", "norm.cu", "norm_tma.cu", "loss.cu", "loss_softmax.cu", "sliding.cu", "optim_pack.cu", "dataio.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",

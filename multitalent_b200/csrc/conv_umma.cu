@@ -41,6 +41,7 @@ int conv_halo_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_halo.c
 int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_line.cu
 int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s);  // wgrad_line.cu
 int wgrad_line_s2_umma(const mtb200_wgrad_params& p, cudaStream_t s);  // wgrad_line_s2.cu
+int wgrad_rows_umma(const mtb200_wgrad_params& p, cudaStream_t s);     // wgrad_rows.cu
 int conv_pw_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_pw.cu
 int conv_gm_umma(const mtb200_conv_params& p, cudaStream_t s);  // conv_gm.cu
 
@@ -729,6 +730,8 @@ int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   if (p.impl != 3) {  // line-streaming kernels first (impl 3 = per-tap kernel only, impl 5 = line-streaming only)
     const int r2 = wgrad_line_s2_umma(p, s);  // stride-2 3x3x3 layers
     if (r2 != MTB200_ERR_UNSUPPORTED) return r2;
+    const int r3 = wgrad_rows_umma(p, s);     // wide stride-1 layers below the second level (128-channel blocks)
+    if (r3 != MTB200_ERR_UNSUPPORTED) return r3;
     const int r = wgrad_line_umma(p, s);
     if (r != MTB200_ERR_UNSUPPORTED) return r;
     if (p.impl == 5) { set_error("wgrad_taps(umma): problem outside the line-streaming kernel's envelope"); return r; }

@@ -50,7 +50,8 @@ LAYERS = [
     ("convT", 120, 60, (2, 2, 2), (2, 2, 2), (1, 48, 40, 32), 0),
     ("conv", 120, 120, (3, 3, 3), (1, 1, 1), (2, 48, 40, 32), 0),     # level 2
     ("conv", 240, 120, (3, 3, 3), (1, 1, 1), (1, 48, 40, 32), 120),
-    ("conv", 240, 240, (3, 3, 3), (1, 1, 1), (2, 24, 20, 16), 0),     # level 3
+    ("conv", 240, 240, (3, 3, 3), (1, 1, 1), (2, 24, 20, 16), 0),     # level 3 (wgrad_rows: 128-channel blocks)
+    ("conv", 480, 240, (3, 3, 3), (1, 1, 1), (1, 24, 20, 16), 240),
     ("conv", 320, 320, (3, 3, 3), (1, 2, 2), (2, 12, 10, 8), 0),      # bottleneck stride (1, 2, 2)
     ("convT", 320, 320, (1, 2, 2), (1, 2, 2), (2, 12, 5, 4), 0),
 ]
