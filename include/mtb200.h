@@ -228,6 +228,8 @@ typedef struct {
   const uint64_t* pos_mask;  /* [n_labels] label -> bitmask of positive output channels */
   const void* x;             /* head input (materialised activation) [B][nvox][x_ldc], channels x_coff .. x_coff + Cin */
   const void* w_swap;        /* [Cin][Cout], dtype */
+  const void* w_fwd;         /* [Cout][Cin], dtype: needed when `logits` is NULL (deferred head: the window of the logits is
+                              * recomputed from x on the tensor core, rounded to dtype -- the values a stored tensor holds) */
   void* dx;                  /* [B][nvox][dx_ldc], channels dx_coff .. dx_coff + Cin */
   float* dw;                 /* [Cout][Cin] */
   int64_t nvox;
@@ -236,6 +238,22 @@ typedef struct {
   int32_t win_c0[MTB200_MAX_HEAD_BATCH];
 } mtb200_head_bwd_params;
 int mtb200_head_bwd_fused(const mtb200_head_bwd_params* p, void* stream);
+/* Forward of a DEFERRED head under the MultiTalent loss: loss pass 1 (mtb200_mt_loss_stats' sums, same arithmetic) computed
+ * straight from the head's input -- logits window = x . W^T on the tensor core, rounded to dtype, never written to memory.
+ * stats[B][C8][4] += {sum bce, sum sigma*y, sum sigma, sum y}; hard (may be NULL): [B][C8][2] += {sum [z>0] y, sum [z>0]}. */
+typedef struct {
+  const void* x;             /* head input [B][nvox][x_ldc], channels x_coff .. x_coff + Cin */
+  const void* w_fwd;         /* [Cout][Cin], dtype (mtb200_pack_weights, forward layout) */
+  const float* target;       /* [B][nvox] label ids */
+  const uint64_t* valid_mask;/* [B] supervised output channels */
+  const uint64_t* pos_mask;  /* [n_labels] */
+  double* stats;
+  double* hard;
+  int64_t nvox;
+  int32_t dtype, B, C8, n_labels, x_ldc, x_coff, Cin, Cout;
+  int32_t win_c0[MTB200_MAX_HEAD_BATCH];
+} mtb200_head_fwd_params;
+int mtb200_head_fwd_stats(const mtb200_head_fwd_params* p, void* stream);
 
 /* ---- a14/a15/a16: sliding-window predictor; replaces neural_network.py:374-394 (tile loop + host numpy accumulate),
  *      :531-589 (mirror TTA), :405 (normalise), :415-417 (threshold) ------------------------------------------------ */

@@ -93,11 +93,23 @@ MAX_HEAD_BATCH = 16
 class HeadBwdParams(C.Structure):
     _fields_ = [
         ("logits", C.c_void_p), ("target", C.c_void_p), ("coef", C.c_void_p), ("gscale", C.c_void_p),
-        ("pos_mask", C.c_void_p), ("x", C.c_void_p), ("w_swap", C.c_void_p), ("dx", C.c_void_p), ("dw", C.c_void_p),
+        ("pos_mask", C.c_void_p), ("x", C.c_void_p), ("w_swap", C.c_void_p), ("w_fwd", C.c_void_p), ("dx", C.c_void_p),
+        ("dw", C.c_void_p),
         ("nvox", C.c_int64),
         ("dtype", C.c_int32), ("B", C.c_int32), ("z_ldc", C.c_int32), ("C8", C.c_int32), ("n_labels", C.c_int32),
         ("x_ldc", C.c_int32), ("x_coff", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32), ("dx_ldc", C.c_int32),
         ("dx_coff", C.c_int32), ("accumulate", C.c_int32),
+        ("win_c0", C.c_int32 * MAX_HEAD_BATCH),
+    ]
+
+
+class HeadFwdParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("w_fwd", C.c_void_p), ("target", C.c_void_p), ("valid_mask", C.c_void_p),
+        ("pos_mask", C.c_void_p), ("stats", C.c_void_p), ("hard", C.c_void_p),
+        ("nvox", C.c_int64),
+        ("dtype", C.c_int32), ("B", C.c_int32), ("C8", C.c_int32), ("n_labels", C.c_int32), ("x_ldc", C.c_int32),
+        ("x_coff", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
         ("win_c0", C.c_int32 * MAX_HEAD_BATCH),
     ]
 
@@ -131,6 +143,7 @@ SIGNATURES = {
     "mtb200_mt_loss_finalize": [_vp, _vp, _vp, _i32, _i32, _i64, _f32, _f32, _vp, _vp, _vp],
     "mtb200_mt_loss_bwd": [_vp, _i32, _i32, _i32, _vp, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _vp],
     "mtb200_head_bwd_fused": [C.POINTER(HeadBwdParams), _vp],
+    "mtb200_head_fwd_stats": [C.POINTER(HeadFwdParams), _vp],
     "mtb200_sw_gather_tile": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32,
                               _vp],
     "mtb200_sw_aggregate": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _f32, _i32, _vp, _vp, _i32, _i32, _i32,

@@ -71,6 +71,7 @@ int mt_loss_finalize(const double*, const double*, const uint64_t*, int, int, lo
 int mt_loss_bwd(const void*, int, int, int, const float*, int, long long, const uint64_t*, int, const float*,
                 const float*, void*, int, cudaStream_t);
 int head_bwd_fused(const mtb200_head_bwd_params& p, cudaStream_t s);  // head_bwd.cu
+int head_fwd_stats(const mtb200_head_fwd_params& p, cudaStream_t s);  // head_bwd.cu
 int sw_gather_tile(const float*, int, int, int, int, int, int, int, int, int, int, int, void*, int, int, cudaStream_t);
 int sw_aggregate(const void*, int, int, int, int, int, int, int, const float*, float, int, float*, float*, int, int, int,
                  int, int, int, cudaStream_t);
@@ -240,9 +241,13 @@ int mtb200_mt_loss_bwd(const void* logits, int32_t dtype, int32_t ldc, int32_t C
                      STREAM(stream));
 }
 int mtb200_head_bwd_fused(const mtb200_head_bwd_params* p, void* stream) {
-  MTB_REQUIRE(p && p->logits && p->target && p->coef && p->pos_mask && p->x && p->w_swap && p->dx && p->dw,
+  MTB_REQUIRE(p && (p->logits || p->w_fwd) && p->target && p->coef && p->pos_mask && p->x && p->w_swap && p->dx && p->dw,
               "head_bwd_fused: null pointer");
   return head_bwd_fused(*p, (cudaStream_t)stream);
+}
+int mtb200_head_fwd_stats(const mtb200_head_fwd_params* p, void* stream) {
+  MTB_REQUIRE(p && p->x && p->w_fwd && p->target && p->valid_mask && p->pos_mask && p->stats, "head_fwd_stats: null pointer");
+  return head_fwd_stats(*p, (cudaStream_t)stream);
 }
 
 int mtb200_sw_gather_tile(const float* vol, int32_t Cin, int32_t X, int32_t Y, int32_t Z, int32_t x0, int32_t y0,

@@ -37,6 +37,10 @@ struct HeadBwdParams {
   const float* gscale;
   const uint64_t* pos_mask;
   const void* w_swap;  // [Cin][Cout_p] 16 bit
+  const void* w_fwd;   // [Cout_p][Cin] 16 bit: recompute mode (logits == nullptr) and the forward statistics kernel
+  double* stats;       // forward kernel: [B][C8][4] += {sum bce, sum sigma*y, sum sigma, sum y}
+  double* hard;        // forward kernel (optional): [B][C8][2] += {sum [z > 0] * y, sum [z > 0]}
+  const uint64_t* valid_mask;  // forward kernel: [B] supervised channels
   void* dx;
   float* dw;           // [Cout_p][Cin] fp32
   long long nvox, tiles_per_b;
@@ -76,16 +80,19 @@ __device__ __forceinline__ uint64_t hb_desc64(uint32_t hi, uint32_t lo) { return
 
 // CIN = padded input channels of the head (32: full resolution, 64: second level)
 // ACC: d(input) += (the level's transposed convolution already wrote its share)
-template <typename T, int CIN, bool ACC>
+// RC:  the logits were never stored (deferred head, mtb200_head_fwd_stats): MMA 0 recomputes the window
+//      z[128 vox][16] = X (K-major A: the same input tile) x Wwin[16][Cin] (K-major B) one tile ahead, the compute warps read
+//      it from TMEM and round it to the storage type first -- the values the stored logits would have had
+template <typename T, int CIN, bool ACC, bool RC>
 __global__ void __launch_bounds__(HB_THREADS, CIN == 32 ? 3 : 2) head_bwd_fused_kernel(const __grid_constant__ HeadBwdParams p) {
   constexpr int ROWB = CIN * 2;            // bytes per input row
   constexpr int ACT_BYTES = 128 * ROWB;    // one staged input tile
   constexpr int NCH = ROWB / 16;           // 16-byte pieces per output row
   constexpr int RPI = 32 / NCH;            // rows one warp-wide store instruction covers
-  constexpr uint32_t TMEM_COLS = CIN == 32 ? 128u : 256u;
+  constexpr uint32_t TMEM_COLS = CIN == 32 ? 128u : 256u;  // 2 CIN (dX x 2) + 16 (dW) + 32 (RC: logits x 2)
   extern __shared__ uint8_t dsmem_raw[];
   __shared__ __align__(8) uint64_t act_full[HB_STAGES], act_empty[HB_STAGES];
-  __shared__ __align__(8) uint64_t a_full[2], a_empty[2], d1_full[2], d1_empty[2], d2_full;
+  __shared__ __align__(8) uint64_t a_full[2], a_empty[2], d1_full[2], d1_empty[2], d2_full, z_full[2], z_empty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ uint64_t s_pos[HB_MAX_LABELS];
   __shared__ float4 s_cf[HB_WIN];
@@ -96,6 +103,8 @@ __global__ void __launch_bounds__(HB_THREADS, CIN == 32 ? 3 : 2) head_bwd_fused_
   uint8_t* a_base = act_base + HB_STAGES * ACT_BYTES + 1024;     // 2 x 4 KB  DL tiles
   uint8_t* w_base = a_base + 2 * 4096;                           // CIN x 32 B weight window (K-major, SWIZZLE_32B)
   uint8_t* o_base = w_base + ((CIN * 32 + 1023) / 1024) * 1024;  // 4 warps x 32 rows x ROWB output transposition
+  uint8_t* w0_base = o_base + 4 * 32 * ROWB;                     // RC: 16 x ROWB forward weight window (K-major, swizzled)
+  constexpr uint32_t ZCOL = 2 * CIN + HB_WIN;                    // RC: two 16-column logit accumulators
 
   const int b = (int)blockIdx.x / p.cps, slot = (int)blockIdx.x % p.cps;
   const int c0 = p.win_c0[b];
@@ -107,6 +116,7 @@ __global__ void __launch_bounds__(HB_THREADS, CIN == 32 ? 3 : 2) head_bwd_fused_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1);
       mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], 128);
+      mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], 128);
     }
     mbar_init(&d2_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -125,6 +135,15 @@ __global__ void __launch_bounds__(HB_THREADS, CIN == 32 ? 3 : 2) head_bwd_fused_
     const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.w_swap) +
                                                     (long long)row * p.Cout_p + c0 + piece * 8);
     *reinterpret_cast<uint4*>(w_base + row * 32 + ((piece ^ ((row >> 2) & 1)) * 16)) = v;
+  }
+  if (RC) {  // forward weight rows c0 .. c0 + 16: [16][Cin], 16-byte pieces swizzled as SWIZZLE_64B / SWIZZLE_128B
+    for (int idx = threadIdx.x; idx < HB_WIN * NCH; idx += HB_THREADS) {
+      const int row = idx / NCH, piece = idx % NCH;
+      const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.w_fwd) +
+                                                      (long long)(c0 + row) * CIN + piece * 8);
+      const int sw = NCH == 4 ? (piece ^ ((row >> 1) & 3)) : (piece ^ (row & 7));
+      *reinterpret_cast<uint4*>(w0_base + row * ROWB + sw * 16) = v;
+    }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == 1) tmem_alloc(&tmem_slot, TMEM_COLS);
@@ -161,11 +180,32 @@ __global__ void __launch_bounds__(HB_THREADS, CIN == 32 ? 3 : 2) head_bwd_fused_
     const uint32_t lbo_x = ((uint32_t)ROWB >> 4) << 16;  // M blocks past the first: row-shifted junk, never read back
     const uint32_t hi_d = ((8u * 32u) >> 4) | (1u << 14) | (6u << 29);
     const uint32_t lbo_d = (256u >> 4) << 16;
+    // RC: K-major descriptors of MMA 0 (conv_pw.cu: SBO = 8 rows, 32 bytes per K step inside the swizzled row)
+    const uint32_t idesc0 = idesc_f16(p.is_f16 != 0, (uint32_t)HB_WIN, false, false);
+    const uint32_t hi_k = ((8u * ROWB) >> 4) | (1u << 14) | ((ROWB == 128 ? 2u : 4u) << 29);
+    const uint32_t w0_16 = __shfl_sync(0xffffffffu, (smem_u32(w0_base) & 0x3FFFFu) >> 4, 0);
+    auto mma0 = [&](uint32_t i) {  // logits window of tile i (warp-uniform; waits for its input tile and a free z buffer)
+      const uint32_t buf = i & 1u, stage = i % HB_STAGES;
+      mbar_wait(&act_full[stage], (i / HB_STAGES) & 1u);
+      mbar_wait(&z_empty[buf], ((i >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t x_t = act16 + stage * ((uint32_t)ACT_BYTES >> 4);
+#pragma unroll
+        for (int ks = 0; ks < CIN / 16; ++ks)
+          umma_f16(tmem_u + ZCOL + buf * HB_WIN, hb_desc64(hi_k, x_t + 2u * ks), hb_desc64(hi_k, w0_16 + 2u * ks), idesc0,
+                   ks ? 1u : 0u);
+        umma_commit(&z_full[buf]);
+      }
+      __syncwarp();
+    };
+    if (RC && have_work) mma0(0);
     uint32_t i = 0;
     for (long long t = slot; t < ntiles; t += p.cps, ++i) {
       const uint32_t buf = i & 1u, stage = i % HB_STAGES;
+      if (RC && t + p.cps < ntiles) mma0(i + 1);
       mbar_wait(&a_full[buf], (i >> 1) & 1u);
-      mbar_wait(&act_full[stage], (i / HB_STAGES) & 1u);
+      if (!RC) mbar_wait(&act_full[stage], (i / HB_STAGES) & 1u);
       mbar_wait(&d1_empty[buf], ((i >> 1) & 1u) ^ 1u);
       tc_fence_after();
       if (elect_one()) {
@@ -203,8 +243,10 @@ __global__ void __launch_bounds__(HB_THREADS, CIN == 32 ? 3 : 2) head_bwd_fused_
     float lab = 0.f, nlab = 0.f;
     auto fetch = [&](long long t, Raw8<T>& a, Raw8<T>& c, float& l) {
       const long long v = min(t * 128 + m, p.nvox - 1);  // rows past the sample: clamped re-read, masked below
-      a.load(zb + v * p.z_ldc);
-      c.load(zb + v * p.z_ldc + 8);
+      if (!RC) {
+        a.load(zb + v * p.z_ldc);
+        c.load(zb + v * p.z_ldc + 8);
+      }
       l = __ldg(tb + v);
     };
     auto epilogue = [&](uint32_t i, long long t) {
@@ -277,12 +319,20 @@ __global__ void __launch_bounds__(HB_THREADS, CIN == 32 ? 3 : 2) head_bwd_fused_
       const int li = (int)lab;
       const uint64_t pm = (inside && (unsigned)li < (unsigned)HB_MAX_LABELS) ? s_pos[li] : 0ull;
       const unsigned ybits = (unsigned)((pm >> c0) & 0xffffull);
+      uint32_t zr[16];
+      if (RC) {
+        mbar_wait(&z_full[buf], (i >> 1) & 1u);
+        tc_fence_after();
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + ZCOL + buf * HB_WIN, zr);
+        tc_fence_before();
+        mbar_arrive(&z_empty[buf]);
+      }
       float d[HB_WIN];
 #pragma unroll
       for (int j = 0; j < HB_WIN; ++j) {
         d[j] = 0.f;
         if (vbits & (1u << j)) {
-          const float zz = j < 8 ? z0.get(j) : z1.get(j - 8);
+          const float zz = RC ? Traits<T>::round(__uint_as_float(zr[j])) : (j < 8 ? z0.get(j) : z1.get(j - 8));
           const float y = (ybits >> j) & 1u ? 1.f : 0.f;
           const float4 cf = s_cf[j];
           float sig;
@@ -330,6 +380,165 @@ __global__ void __launch_bounds__(HB_THREADS, CIN == 32 ? 3 : 2) head_bwd_fused_
   }
 }
 
+// ---- forward of a deferred head: loss pass 1 straight from the head's input ----------------------------------------------
+// z[128 vox][16] = X x Wwin^T on the tensor core (the window of the sample's dataset), rounded to the storage type, then
+// mt_loss_stats' arithmetic per supervised channel; the logits are never written.  Per-thread partial sums live in
+// registers for the whole CTA (one sample per CTA), are combined in a fixed order inside the CTA and leave as one fp64
+// atomic per (channel, statistic).  HARD: also the thresholded-prediction counts of run_online_evaluation.
+template <typename T, int CIN, bool HARD>
+__global__ void __launch_bounds__(HB_THREADS, 2) head_fwd_stats_kernel(const __grid_constant__ HeadBwdParams p) {
+  constexpr int ROWB = CIN * 2;
+  constexpr int ACT_BYTES = 128 * ROWB;
+  constexpr int NCH = ROWB / 16;
+  constexpr int NQ = HARD ? 6 : 4;
+  extern __shared__ uint8_t dsmem_raw[];
+  __shared__ __align__(8) uint64_t act_full[HB_STAGES], act_empty[HB_STAGES], z_full[2], z_empty[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint64_t s_pos[HB_MAX_LABELS];
+  __shared__ float s_part[4][NQ * HB_WIN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* act_base = dsmem;
+  uint8_t* w0_base = act_base + HB_STAGES * ACT_BYTES;
+  const int b = (int)blockIdx.x / p.cps, slot = (int)blockIdx.x % p.cps;
+  const int c0 = p.win_c0[b];
+  const long long ntiles = p.tiles_per_b;
+  const bool have_work = slot < ntiles;
+  const unsigned vbits = (unsigned)((p.valid_mask[b] >> c0) & 0xffffull);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < HB_STAGES; ++i) { mbar_init(&act_full[i], 1); mbar_init(&act_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < HB_MAX_LABELS) s_pos[threadIdx.x] = (int)threadIdx.x < p.n_labels ? p.pos_mask[threadIdx.x] : 0ull;
+  for (int idx = threadIdx.x; idx < HB_WIN * NCH; idx += HB_THREADS) {
+    const int row = idx / NCH, piece = idx % NCH;
+    const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.w_fwd) +
+                                                    (long long)(c0 + row) * CIN + piece * 8);
+    const int sw = NCH == 4 ? (piece ^ ((row >> 1) & 3)) : (piece ^ (row & 7));
+    *reinterpret_cast<uint4*>(w0_base + row * ROWB + sw * 16) = v;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 1) tmem_alloc(&tmem_slot, 32u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    uint32_t i = 0;
+    for (long long t = slot; t < ntiles; t += p.cps, ++i) {
+      const uint32_t stage = i % HB_STAGES;
+      mbar_wait(&act_empty[stage], ((i / HB_STAGES) & 1u) ^ 1u);
+      if (elect_one()) {
+        mbar_expect_tx(&act_full[stage], (uint32_t)ACT_BYTES);
+        hb_tma_load_2d(act_base + (size_t)stage * ACT_BYTES, &p.x_map, &act_full[stage], 0,
+                       (int)((long long)b * p.nvox + t * 128));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t idesc0 = idesc_f16(p.is_f16 != 0, (uint32_t)HB_WIN, false, false);
+    const uint32_t hi_k = ((8u * ROWB) >> 4) | (1u << 14) | ((ROWB == 128 ? 2u : 4u) << 29);
+    const uint32_t act16 = __shfl_sync(0xffffffffu, (smem_u32(act_base) & 0x3FFFFu) >> 4, 0);
+    const uint32_t w0_16 = __shfl_sync(0xffffffffu, (smem_u32(w0_base) & 0x3FFFFu) >> 4, 0);
+    uint32_t i = 0;
+    for (long long t = slot; t < ntiles; t += p.cps, ++i) {
+      const uint32_t buf = i & 1u, stage = i % HB_STAGES;
+      mbar_wait(&act_full[stage], (i / HB_STAGES) & 1u);
+      mbar_wait(&z_empty[buf], ((i >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t x_t = act16 + stage * ((uint32_t)ACT_BYTES >> 4);
+#pragma unroll
+        for (int ks = 0; ks < CIN / 16; ++ks)
+          umma_f16(tmem_u + buf * HB_WIN, hb_desc64(hi_k, x_t + 2u * ks), hb_desc64(hi_k, w0_16 + 2u * ks), idesc0,
+                   ks ? 1u : 0u);
+        umma_commit(&z_full[buf]);
+        umma_commit(&act_empty[stage]);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    float part[NQ][HB_WIN];
+#pragma unroll
+    for (int a = 0; a < NQ; ++a)
+#pragma unroll
+      for (int j = 0; j < HB_WIN; ++j) part[a][j] = 0.f;
+    const float* tb = p.target + (long long)b * p.nvox;
+    if (have_work) {
+      float lab = __ldg(tb + min((long long)slot * 128 + m, p.nvox - 1));
+      uint32_t i = 0;
+      for (long long t = slot; t < ntiles; t += p.cps, ++i) {
+        const uint32_t buf = i & 1u;
+        const long long tn = t + p.cps;
+        float nlab = 0.f;
+        if (tn < ntiles) nlab = __ldg(tb + min(tn * 128 + m, p.nvox - 1));
+        uint32_t zr[16];
+        mbar_wait(&z_full[buf], (i >> 1) & 1u);
+        tc_fence_after();
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * HB_WIN, zr);
+        tc_fence_before();
+        mbar_arrive(&z_empty[buf]);
+        if (t * 128 + m < p.nvox) {
+          const int li = (int)lab;
+          const uint64_t pm = (unsigned)li < (unsigned)HB_MAX_LABELS ? s_pos[li] : 0ull;
+          const unsigned ybits = (unsigned)((pm >> c0) & 0xffffull);
+#pragma unroll
+          for (int j = 0; j < HB_WIN; ++j) {
+            if (vbits & (1u << j)) {
+              const float zz = Traits<T>::round(__uint_as_float(zr[j]));
+              const float y = (ybits >> j) & 1u ? 1.f : 0.f;
+              const float e = __expf(-fabsf(zz));
+              const float r = __frcp_rn(1.f + e);
+              const float sig = zz >= 0.f ? r : e * r;
+              const float l1p = e < 2.44140625e-4f ? e * (1.f - 0.5f * e) : __logf(1.f + e);
+              part[0][j] += fmaxf(zz, 0.f) - zz * y + l1p;
+              part[1][j] = fmaf(sig, y, part[1][j]);
+              part[2][j] += sig;
+              part[3][j] += y;
+              if (HARD) {
+                const float pred = zz > 0.f ? 1.f : 0.f;
+                part[NQ - 2][j] += pred * y;
+                part[NQ - 1][j] += pred;
+              }
+            }
+          }
+        }
+        lab = nlab;
+      }
+    }
+    // lanes -> warp -> CTA in a fixed order, then one double atomic per (channel, statistic)
+#pragma unroll
+    for (int a = 0; a < NQ; ++a)
+#pragma unroll
+      for (int j = 0; j < HB_WIN; ++j) {
+        const float v = warp_sum(part[a][j]);
+        if (lane == 0) s_part[q][a * HB_WIN + j] = v;
+      }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int idx = (warp - 2) * 32 + lane;
+    if (idx < NQ * HB_WIN) {
+      const int a = idx / HB_WIN, j = idx % HB_WIN;
+      const float v = s_part[0][idx] + s_part[1][idx] + s_part[2][idx] + s_part[3][idx];
+      if ((vbits & (1u << j)) && v != 0.f) {
+        if (a < 4) atomicAdd(p.stats + ((long long)b * p.C8 + c0 + j) * 4 + a, (double)v);
+        else atomicAdd(p.hard + ((long long)b * p.C8 + c0 + j) * 2 + (a - 4), (double)v);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 32u);
+  }
+}
+
 int umma_available();
 
 int head_bwd_fused(const mtb200_head_bwd_params& p, cudaStream_t s) {
@@ -355,6 +564,7 @@ int head_bwd_fused(const mtb200_head_bwd_params& p, cudaStream_t s) {
     if (!umma_encode_map(&q.x_map, p.dtype, 2, (uint8_t*)p.x + (size_t)p.x_coff * 2, dims, strides, box, p.Cin * 2))
       return MTB200_ERR_CUDA;
   }
+  q.w_fwd = p.w_fwd;
   q.logits = p.logits; q.target = p.target; q.coef = reinterpret_cast<const float4*>(p.coef); q.gscale = p.gscale;
   q.pos_mask = p.pos_mask; q.w_swap = p.w_swap; q.dx = p.dx; q.dw = p.dw;
   q.nvox = p.nvox; q.tiles_per_b = (p.nvox + 127) / 128;
@@ -367,13 +577,18 @@ int head_bwd_fused(const mtb200_head_bwd_params& p, cudaStream_t s) {
   if (cps > q.tiles_per_b) cps = q.tiles_per_b;
   q.cps = (int)cps;
   const int rowb = p.Cin * 2;
-  const int smem = HB_STAGES * 128 * rowb + 1024 + 2 * 4096 + ((p.Cin * 32 + 1023) / 1024) * 1024 + 4 * 32 * rowb + 1024;
+  const int smem = HB_STAGES * 128 * rowb + 1024 + 2 * 4096 + ((p.Cin * 32 + 1023) / 1024) * 1024 + 4 * 32 * rowb +
+                   HB_WIN * rowb + 1024;
   dim3 grid((unsigned)(q.cps * p.B));
   cudaError_t e = cudaSuccess;
-#define HB_LAUNCH2(T, CIN, ACC)                                                                                      \
-  do {                                                                                                               \
-    e = cudaFuncSetAttribute(head_bwd_fused_kernel<T, CIN, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-    if (e == cudaSuccess) head_bwd_fused_kernel<T, CIN, ACC><<<grid, HB_THREADS, smem, s>>>(q);                      \
+#define HB_LAUNCH3(T, CIN, ACC, RC)                                                                                      \
+  do {                                                                                                                   \
+    e = cudaFuncSetAttribute(head_bwd_fused_kernel<T, CIN, ACC, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+    if (e == cudaSuccess) head_bwd_fused_kernel<T, CIN, ACC, RC><<<grid, HB_THREADS, smem, s>>>(q);                      \
+  } while (0)
+#define HB_LAUNCH2(T, CIN, ACC)                                                   \
+  do {                                                                            \
+    if (p.logits) HB_LAUNCH3(T, CIN, ACC, false); else HB_LAUNCH3(T, CIN, ACC, true); \
   } while (0)
 #define HB_LAUNCH(T, CIN)                                                     \
   do {                                                                        \
@@ -385,9 +600,62 @@ int head_bwd_fused(const mtb200_head_bwd_params& p, cudaStream_t s) {
     if (p.Cin == 32) HB_LAUNCH(__half, 32); else HB_LAUNCH(__half, 64);
   }
 #undef HB_LAUNCH2
+#undef HB_LAUNCH3
 #undef HB_LAUNCH
   if (e != cudaSuccess) { set_error("head_bwd_fused: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
   return check_launch("head_bwd_fused");
+}
+
+int head_fwd_stats(const mtb200_head_fwd_params& p, cudaStream_t s) {
+  if (!umma_available()) { set_error("head_fwd_stats: no sm_100 device / driver entry point"); return MTB200_ERR_UNSUPPORTED; }
+  if (p.dtype != MTB200_BF16 && p.dtype != MTB200_F16) { set_error("head_fwd_stats: 16-bit tensors only"); return MTB200_ERR_UNSUPPORTED; }
+  if (p.Cin != 32 && p.Cin != 64) { set_error("head_fwd_stats: Cin %d (32 or 64)", p.Cin); return MTB200_ERR_UNSUPPORTED; }
+  MTB_REQUIRE(p.B >= 1 && p.B <= MTB200_MAX_HEAD_BATCH, "head_fwd_stats: batch %d (max %d)", p.B, MTB200_MAX_HEAD_BATCH);
+  MTB_REQUIRE(p.x_ldc % 8 == 0 && p.x_coff % 8 == 0 && p.Cout % 8 == 0 && p.C8 % 8 == 0, "head_fwd_stats: alignment");
+  MTB_REQUIRE(p.n_labels <= HB_MAX_LABELS, "head_fwd_stats: n_labels=%d > %d", p.n_labels, HB_MAX_LABELS);
+  MTB_REQUIRE(p.nvox > 0 && (long long)p.B * p.nvox < (1LL << 31), "head_fwd_stats: %lld voxels", (long long)p.nvox);
+  for (int b = 0; b < p.B; ++b)
+    MTB_REQUIRE(p.win_c0[b] >= 0 && p.win_c0[b] % 8 == 0 && p.win_c0[b] + HB_WIN <= p.Cout && p.win_c0[b] + HB_WIN <= p.C8,
+                "head_fwd_stats: window of sample %d starts at channel %d", b, p.win_c0[b]);
+  static thread_local HeadBwdParams q;
+  memset(&q, 0, sizeof(q));
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)p.Cin, (cuuint64_t)((long long)p.B * p.nvox)};
+    cuuint64_t strides[1] = {(cuuint64_t)p.x_ldc * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.Cin, 128};
+    if (!umma_encode_map(&q.x_map, p.dtype, 2, (uint8_t*)p.x + (size_t)p.x_coff * 2, dims, strides, box, p.Cin * 2))
+      return MTB200_ERR_CUDA;
+  }
+  q.target = p.target; q.pos_mask = p.pos_mask; q.valid_mask = p.valid_mask; q.w_fwd = p.w_fwd; q.stats = p.stats; q.hard = p.hard;
+  q.nvox = p.nvox; q.tiles_per_b = (p.nvox + 127) / 128;
+  q.C8 = p.C8; q.n_labels = p.n_labels; q.Cout_p = p.Cout; q.B = p.B; q.is_f16 = p.dtype == MTB200_F16;
+  for (int b = 0; b < p.B; ++b) q.win_c0[b] = p.win_c0[b];
+  long long cps = ((long long)num_sms() * 2) / p.B;  // two CTAs per SM (the partial sums take ~100 registers per thread)
+  if (cps < 1) cps = 1;
+  if (cps > q.tiles_per_b) cps = q.tiles_per_b;
+  q.cps = (int)cps;
+  const int rowb = p.Cin * 2;
+  const int smem = HB_STAGES * 128 * rowb + HB_WIN * rowb + 2048;
+  dim3 grid((unsigned)(q.cps * p.B));
+  cudaError_t e = cudaSuccess;
+#define HF_LAUNCH2(T, CIN, HARD)                                                                                     \
+  do {                                                                                                               \
+    e = cudaFuncSetAttribute(head_fwd_stats_kernel<T, CIN, HARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+    if (e == cudaSuccess) head_fwd_stats_kernel<T, CIN, HARD><<<grid, HB_THREADS, smem, s>>>(q);                     \
+  } while (0)
+#define HF_LAUNCH(T, CIN)                                                \
+  do {                                                                   \
+    if (p.hard) HF_LAUNCH2(T, CIN, true); else HF_LAUNCH2(T, CIN, false); \
+  } while (0)
+  if (p.dtype == MTB200_BF16) {
+    if (p.Cin == 32) HF_LAUNCH(__nv_bfloat16, 32); else HF_LAUNCH(__nv_bfloat16, 64);
+  } else {
+    if (p.Cin == 32) HF_LAUNCH(__half, 32); else HF_LAUNCH(__half, 64);
+  }
+#undef HF_LAUNCH
+#undef HF_LAUNCH2
+  if (e != cudaSuccess) { set_error("head_fwd_stats: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
+  return check_launch("head_fwd_stats");
 }
 
 }  // namespace mtb

@@ -413,6 +413,13 @@ class Engine:
         self.fuse_head = os.environ.get("MTB200_FUSE_HEAD", "1") != "0"
         self.fusable_heads = {}  # logits buffer pointer -> True, for the heads of the current step the kernel covers
         self.lazy_heads = {}     # logits buffer pointer -> what the fused kernel needs from the loss
+        # Deferred heads (set by the trainer around the network call of a training step, never by default): a fusable head
+        # is not computed at all in the forward pass -- the loss's first pass evaluates the logits window on the tensor core
+        # from the head's input (mtb200_head_fwd_stats) and the fused backward recomputes it.  The network then returns a
+        # zero-stride placeholder for that output; only multitalent_loss(engine=...) may consume it.
+        self.defer_head_fwd = os.environ.get("MTB200_DEFER_HEAD", "1") != "0"
+        self.defer_heads = False
+        self.deferred = {}       # placeholder pointer -> {"x": head input, "op": head}
         self.wgrad_order = int(os.environ.get("MTB200_WGRAD_ORDER", "0"))
         self.bwd_priority = os.environ.get("MTB200_BWD_PRIO", "0") != "0"
         self._hp = {}
@@ -432,6 +439,7 @@ class Engine:
         self._dy_next = 0
         self.fusable_heads.clear()
         self.lazy_heads.clear()
+        self.deferred.clear()
 
     @property
     def materialize_inputs(self) -> bool:
@@ -737,7 +745,9 @@ class Engine:
         gx, have = tape.grad_feat(x)
         dw = self._z32.take((op.ntap, op.Cout_p, op.Cin_p), dev)
         p = L.HeadBwdParams()
-        p.logits, p.target, p.coef = y.ptr(), spec["target"].data_ptr(), spec["coef"].data_ptr()
+        p.logits = None if spec.get("deferred") else y.ptr()  # deferred: the kernel recomputes the window from x
+        p.w_fwd = op.packed(self.wdtype, False).data_ptr()
+        p.target, p.coef = spec["target"].data_ptr(), spec["coef"].data_ptr()
         p.gscale, p.pos_mask = spec["gscale"].data_ptr(), spec["pos"].data_ptr()
         p.x, p.w_swap, p.dx, p.dw = x.ptr(), op.packed(self.wdtype, True).data_ptr(), gx.ptr(), dw.data_ptr()
         p.nvox, p.dtype, p.B = y.nvox, dt, y.dims[0]
@@ -782,10 +792,18 @@ class Engine:
                    need_input_grad=True, head=False) -> Feat:
         """Convolution with no normalisation after it (transposed-conv upsampling, 1x1x1 heads).  `head`: a segmentation
         head whose output goes to the loss -- its backward may arrive as a `lazy_heads` descriptor (fused kernel)."""
-        y, _ = self.conv(op, x, out)
-        if (head and tape is not None and self.fuse_head and need_input_grad and op.bias is None and op.ntap == 1
-                and not op.transposed and op.Cin_p in (32, 64) and self.materialize_inputs and y.coff == 0
-                and y.ldc == y.Cp and y.dims[0] <= L.MAX_HEAD_BATCH):
+        fusable = (head and tape is not None and self.fuse_head and need_input_grad and op.bias is None and op.ntap == 1
+                   and not op.transposed and op.Cin_p in (32, 64) and self.materialize_inputs and out is None
+                   and x.dims[0] <= L.MAX_HEAD_BATCH)
+        deferred = fusable and self.defer_heads
+        if deferred:
+            # not computed: a zero-stride placeholder of the logits' shape stands in (its one-element storage is the key)
+            ph = torch.zeros(8, dtype=self.dtype, device=x.buf.device)[:1].expand(tuple(x.dims) + (op.Cout_p,))
+            y = Feat(ph, 0, op.Cout, op.Cout_p)
+            self.deferred[ph.data_ptr()] = {"x": x, "op": op}
+        else:
+            y, _ = self.conv(op, x, out)
+        if fusable:
             self.fusable_heads[y.buf.data_ptr()] = True
         if tape is not None:
             def bwd():
@@ -793,6 +811,9 @@ class Engine:
                 if spec is not None:
                     self._head_bwd_fused(tape, op, x, y, spec)
                     return
+                if deferred:
+                    raise L.Mtb200Error("a deferred head's output reached the backward pass without the fused loss "
+                                        "(multitalent_loss(..., engine=network._engine) must consume it)")
                 if not tape.has_grad(y):
                     self._zero_param_grads(tape, op)
                     return

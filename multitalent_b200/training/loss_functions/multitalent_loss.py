@@ -13,6 +13,7 @@ reference's 15 tiny collectives; the backward needs NO collective: every rank ho
 all-reduced gradient (distributed.py:71) is exactly world_size x the local closed form, which pass 2 evaluates:
     dL/dz = w_i [ (sigma - y)/N_vox  -  W * sigma (1 - sigma) (2 y D - 2 TP) / D^2 ]        for supervised (b, j), else 0.
 """
+import ctypes
 from typing import List, Optional, Sequence
 
 import torch
@@ -74,6 +75,39 @@ class _MultiTalentLossFn(torch.autograd.Function):
         for i in active:
             z = logits[i]
             dt = z.dtype if z.dtype in (torch.float32, torch.bfloat16, torch.float16) else torch.float32
+            dspec = lazy[0].deferred.get(z.data_ptr()) if lazy is not None else None
+            if dspec is not None and lazy[1] is None:
+                raise L.Mtb200Error("deferred head, but the supervised channels of this batch do not fit the 16-channel "
+                                    "windows of the fused kernels")
+            if dspec is not None:
+                # deferred head: no logits exist.  Pass 1 runs on the head's input (tensor core), mtb200_head_fwd_stats.
+                eng, win = lazy
+                tgt = targets[i].detach().float().contiguous()
+                nvox = z.shape[2] * z.shape[3] * z.shape[4]
+                assert tgt.shape[0] == B and tgt.numel() == B * nvox, "target does not match the deferred logits"
+                s = torch.zeros((B, C8, 4), dtype=torch.float64, device=dev)
+                hard = None
+                if hard_out is not None and i == 0:
+                    hard = torch.zeros((B, C8, 2), dtype=torch.float64, device=dev)
+                x, op = eng.operand(dspec["x"]), dspec["op"]
+                assert op.Cout_p == C8, (op.Cout_p, C8)
+                p = L.HeadFwdParams()
+                p.x, p.w_fwd, p.target = x.ptr(), op.packed(eng.wdtype, False).data_ptr(), tgt.data_ptr()
+                p.valid_mask, p.pos_mask, p.stats = valid_mask.data_ptr(), pos.data_ptr(), s.data_ptr()
+                p.hard = hard.data_ptr() if hard is not None else None
+                p.nvox, p.dtype, p.B, p.C8, p.n_labels = nvox, L.dtype_enum(dt), B, C8, NUM_LABELS
+                p.x_ldc, p.x_coff, p.Cin, p.Cout = x.ldc, x.coff, op.Cin_p, op.Cout_p
+                for b, c0 in enumerate(win):
+                    p.win_c0[b] = c0
+                L.call("mtb200_head_fwd_stats", ctypes.byref(p), st, flops=eng.conv_flops(op, (B,) + tuple(z.shape[2:])),
+                       tag="conv_head_fwd", info=(op.Cin_p, op.Cout_p, tuple(z.shape[2:]), 1, (1, 1, 1), (1, 1, 1)))
+                if hard is not None:
+                    tp = hard[:, :Cc, 0]
+                    hard_out.update(tp=tp.float(), fp=(hard[:, :Cc, 1] - tp).float(), fn=(s[:, :Cc, 3] - tp).float(),
+                                    logits=None)
+                views[i] = (z, C8, dt, tgt, nvox)
+                stats[i] = s
+                continue
             zv, ldc = _as_ndhwc(z, dt)
             tgt = targets[i]
             assert tgt.shape[0] == B and tgt.numel() == B * z.shape[2] * z.shape[3] * z.shape[4], \
@@ -120,17 +154,21 @@ class _MultiTalentLossFn(torch.autograd.Function):
         for i in ctx.active:
             zv, ldc, dt, tgt, nvox = ctx.views[i]
             B, Cc, D, H, W = ctx.shapes[i]
-            if ctx.lazy is not None:
+            if ctx.lazy is not None and ctx.lazy[1] is not None:
                 # the network's engine runs this head's backward as ONE kernel (loss pass 2 + head data gradient + head
                 # weight gradient, mtb200_head_bwd_fused): d(logits) is never written.  What flows through autograd is a
                 # zero-stride placeholder of the right shape; the descriptor travels beside it, keyed by the buffer.
                 eng, win = ctx.lazy
+                deferred = zv.data_ptr() in eng.deferred
                 if (eng.fusable_heads.get(zv.data_ptr()) and dt in (torch.bfloat16, torch.float16) and ldc == ctx.C8
                         and ctx.needs_input_grad[6 + i]):
                     eng.lazy_heads[zv.data_ptr()] = {"target": tgt, "coef": ctx.coefs[i], "gscale": gs, "pos": ctx.pos,
-                                                     "C8": ctx.C8, "n_labels": NUM_LABELS, "win": win}
+                                                     "C8": ctx.C8, "n_labels": NUM_LABELS, "win": win,
+                                                     "deferred": deferred}
                     grads[i] = torch.zeros((), dtype=dt, device=zv.device).expand(B, Cc, D, H, W)
                     continue
+            if ctx.lazy is not None and zv.data_ptr() in ctx.lazy[0].deferred:
+                raise L.Mtb200Error("deferred head: the fused backward is not available for this output")
             dz = torch.empty((B, D, H, W, ldc), dtype=dt, device=zv.device)
             if ldc > ctx.C8:
                 dz[..., ctx.C8:].zero_()
@@ -206,7 +244,7 @@ def multitalent_loss(outputs, targets, valid_regions, ds_loss_weights, group=Non
     # `engine` (the network's kernel layer): lets the heads' backward run fused with the loss's second pass
     lazy = None
     if engine is not None and getattr(engine, "fuse_head", False) and not torch.is_tensor(valid_regions):
-        win = head_windows(valid_regions, (outputs[0].shape[1] + 7) // 8 * 8)
-        if win is not None:
-            lazy = (engine, win)
+        lazy = (engine, head_windows(valid_regions, (outputs[0].shape[1] + 7) // 8 * 8))
+    elif engine is not None and getattr(engine, "deferred", None):
+        lazy = (engine, None)  # deferred heads present but no window information: the forward pass below refuses
     return _MultiTalentLossFn.apply(vm, weights, group, list(targets), hard_out, lazy, *outputs)

@@ -30,7 +30,7 @@ from ...dataset_conversion.Task100_MultiTalent import MultiTalent_regions
 from ...engine import bump_weights_epoch, pad_channels
 from ...network_architecture.generic_UNet import Generic_UNet, InitWeights_He
 from ...plans import default_plans
-from ..loss_functions.multitalent_loss import multitalent_loss
+from ..loss_functions.multitalent_loss import head_windows, multitalent_loss
 from ..online_evaluation import OnlineEvaluationMixin
 from ..validation import ValidationMixin
 
@@ -431,8 +431,22 @@ class MultiTalent_trainer_ddp(OnlineEvaluationMixin, ValidationMixin):
             self.arena.zero_grad()
         elif self.optimizer is not None:
             self.optimizer.zero_grad()
+        # training steps that do not hand their logits to anybody (no online evaluation): the fusable heads are deferred --
+        # computed inside the loss's statistics pass and recomputed inside the fused backward, never written to memory
+        eng = getattr(self.network, "_engine", None)
+        defer = bool(eng is not None and do_backprop and not keep_output and getattr(eng, "fuse_head", False)
+                     and getattr(eng, "defer_head_fwd", False) and not torch.is_tensor(valid_regions)
+                     and self.network.training
+                     and head_windows(valid_regions, (int(getattr(self.network, "num_classes", 0)) + 7) // 8 * 8)
+                     is not None)
         with torch.set_grad_enabled(do_backprop):
-            output = self.network(data)
+            if eng is not None:
+                eng.defer_heads = defer
+            try:
+                output = self.network(data)
+            finally:
+                if eng is not None:
+                    eng.defer_heads = False
             if target_ready is not None:
                 torch.cuda.current_stream().wait_event(target_ready)
             self._want_hard_stats = bool(keep_output)

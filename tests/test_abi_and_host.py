@@ -42,7 +42,9 @@ def test_struct_layout_matches_header(tmp_path):
     fields = {"mtb200_conv_params": (L.ConvParams, ["in", "stats", "dtype", "Cin", "Do", "ngroups", "ntaps", "tap_widx",
                                                      "accumulate", "red_y", "red", "red_ldc", "impl"]),
               "mtb200_wgrad_params": (L.WgradParams, ["x", "xform", "dtype", "Cout", "ntaps", "tap_widx", "impl"]),
-              "mtb200_head_bwd_params": (L.HeadBwdParams, ["logits", "dw", "nvox", "dtype", "Cin", "accumulate", "win_c0"]),
+              "mtb200_head_bwd_params": (L.HeadBwdParams, ["logits", "w_fwd", "dw", "nvox", "dtype", "Cin", "accumulate",
+                                                           "win_c0"]),
+              "mtb200_head_fwd_params": (L.HeadFwdParams, ["x", "hard", "nvox", "dtype", "Cout", "win_c0"]),
               "mtb200_pack_desc": (L.PackDesc, ["w", "packed_swap", "Cout", "blk_begin"]),
               "mtb200_unpack_desc": (L.UnpackDesc, ["dw", "grad", "Cout", "blk_begin"])}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "mtb200.h"', 'int main(void) {']

@@ -185,3 +185,86 @@ def test_training_step_with_and_without_head_fusion():
         if scale < 1e-6 * float(ga.abs().max()):
             continue
         assert float((a - b).abs().max()) <= 2e-2 * scale, (n, float((a - b).abs().max()), scale)
+
+
+@pytest.mark.parametrize("Cin_p,dims,hard", [(32, (8, 16, 24), True), (64, (6, 10, 16), False), (32, (5, 7, 9), False)])
+def test_head_fwd_stats_matches_separate_passes(Cin_p, dims, hard):
+    """mtb200_head_fwd_stats (logits window on the tensor core, never stored) against pointwise head + mtb200_mt_loss_stats
+    on the stored 16-bit logits, and against a torch evaluation of the same sums."""
+    from multitalent_b200 import _lib as L
+    dtype, B = torch.bfloat16, 3
+    windows = [(0, [0, 1]), (8, list(range(9, 22))), (32, [43, 44, 45, 46])]
+    pr = _problem(B, dims, Cin_p, dtype, windows, seed=7 + Cin_p)
+    nvox = pr["nvox"]
+    w_fwd = pr["w_swap"].t().contiguous()          # [Cout_p][Cin]
+    valid = torch.tensor([sum(1 << j for j in chans) for _, chans in windows], dtype=torch.int64, device="cuda")
+    stats = torch.zeros(B, 48, 4, dtype=torch.float64, device="cuda")
+    hd = torch.zeros(B, 48, 2, dtype=torch.float64, device="cuda") if hard else None
+    p = L.HeadFwdParams()
+    p.x, p.w_fwd, p.target = pr["x"].data_ptr(), w_fwd.data_ptr(), pr["tgt"].data_ptr()
+    p.valid_mask, p.pos_mask, p.stats = valid.data_ptr(), pr["pos"].data_ptr(), stats.data_ptr()
+    p.hard = hd.data_ptr() if hard else None
+    p.nvox, p.dtype, p.B, p.C8, p.n_labels = nvox, L.dtype_enum(dtype), B, 48, pr["n_labels"]
+    p.x_ldc, p.x_coff, p.Cin, p.Cout = Cin_p, 0, Cin_p, 48
+    for b, (c0, _) in enumerate(windows):
+        p.win_c0[b] = c0
+    L.call("mtb200_head_fwd_stats", C.byref(p), L.stream_ptr())
+    # separate passes: logits = x @ W^T rounded to bf16 (what the pointwise kernel stores), then the statistics kernel
+    z = (pr["x"].float() @ w_fwd.float().t()).to(dtype).contiguous()
+    stats2 = torch.zeros_like(stats)
+    hd2 = torch.zeros(B, 48, 2, dtype=torch.float64, device="cuda") if hard else None
+    L.call("mtb200_mt_loss_stats", z.data_ptr(), L.dtype_enum(dtype), 48, 48, pr["tgt"].data_ptr(), B, nvox,
+           valid.data_ptr(), pr["pos"].data_ptr(), pr["n_labels"], stats2.data_ptr(),
+           hd2.data_ptr() if hard else None, L.stream_ptr())
+    torch.cuda.synchronize()
+    scale = stats2.abs().amax(dim=(0, 1)).clamp_min(1e-9)
+    err = ((stats - stats2).abs() / scale).max()
+    assert float(err) < 2e-4, (float(err), stats[0, :2], stats2[0, :2])
+    if hard:
+        # a logit within rounding of 0 may flip its thresholded prediction between the two accumulation orders
+        assert float((hd - hd2).abs().max()) <= 2.0, (hd - hd2).abs().max()
+    # torch evaluation of sum sigma * y and sum y on the stored logits
+    lab = pr["tgt"].long()
+    y = ((pr["pos"][lab].unsqueeze(-1) >> torch.arange(48, device="cuda")) & 1).double()
+    sig = torch.sigmoid(z.double())
+    for b, (c0, chans) in enumerate(windows):
+        for j in chans:
+            assert abs(float(stats[b, j, 1]) - float((sig[b, :, j] * y[b, :, j]).sum())) <= 1e-3 * max(1.0, float(y[b, :, j].sum()))
+            assert float(stats[b, j, 3]) == float(y[b, :, j].sum())
+
+
+def test_training_step_with_deferred_heads():
+    """Heads deferred into the loss (no logits in memory) vs heads computed by the network: same loss, same gradients."""
+    from multitalent_b200 import _lib as L
+    from multitalent_b200.plans import default_plans
+    from multitalent_b200.synthetic import synthetic_batch
+    from multitalent_b200.training.network_training.MultiTalent_Trainer_DDP import MultiTalent_trainer_ddp
+    patch, B = (16, 32, 32), 3
+    plans = default_plans(patch_size=patch, batch_size=B)
+    plans['plans_per_stage'][1]['pool_op_kernel_sizes'] = [[2, 2, 2], [2, 2, 2], [1, 2, 2]]
+    plans['plans_per_stage'][1]['conv_kernel_sizes'] = [[3, 3, 3]] * 4
+    res = {}
+    for defer in (False, True):
+        tr = MultiTalent_trainer_ddp(plans, 0, 0, init_distributed=False, native_dtype=torch.bfloat16)
+        torch.manual_seed(0)
+        tr.initialize(True)
+        tr.lr = 0.0
+        tr.weight_decay = 0.0
+        tr.network._engine.defer_head_fwd = defer
+        batch = synthetic_batch(patch, B, 6, tr.deep_supervision_scales)
+        data = torch.from_numpy(batch['data']).cuda()
+        tgt = [torch.from_numpy(t).cuda() for t in batch['target']]
+        valid = [p['valid_regions'] for p in batch['properties']]
+        with L.KernelProfile() as kp:
+            l, ce, dc = tr.train_step(data, tgt, valid, True)
+        names = {r[5] for r in kp.per_launch_kernels()}
+        assert ("head_fwd_stats" in names) == defer, names
+        res[defer] = (float(l.detach()), float(ce), float(dc), tr.arena.grad.clone())
+        # a step that keeps its output (online evaluation) must not defer
+        l2, _, _ = tr.train_step(data, tgt, valid, True, keep_output=True)
+        assert tr._last_output[0].shape[1] == 47 and float(tr._last_output[0].float().abs().max()) > 0
+    for k in range(3):
+        assert abs(res[True][k] - res[False][k]) <= 1e-5 * max(1.0, abs(res[False][k])), (k, res[True][k], res[False][k])
+    ga, gb = res[False][3].double(), res[True][3].double()
+    cos = float((ga * gb).sum() / (ga.norm() * gb.norm()))
+    assert cos > 0.99999, cos
