@@ -18,8 +18,9 @@ using namespace um;
 
 constexpr int C1_STAGES = 4;
 constexpr int C1_FWD_STAGES = 6;
-constexpr int C1_FWD_BUILDERS = 12;    // three groups of four builder warps take tiles round-robin
-constexpr int C1_FWD_THREADS = 32 * (C1_FWD_BUILDERS + 1 + 8);  // 12 builder warps, MMA warp, 8 epilogue warps
+constexpr int C1_FWD_BUILDERS = 8;     // two groups of four builder warps take tiles round-robin
+constexpr int C1_FWD_EPI = 16;         // two groups of eight epilogue warps take alternate tiles (= the two TMEM buffers)
+constexpr int C1_FWD_THREADS = 32 * (C1_FWD_BUILDERS + 1 + C1_FWD_EPI);
 constexpr int C1_WG_THREADS = 448;     // 8 builder warps, MMA warp, dY producer warp, 4 epilogue warps
 constexpr int C1_ROWB = 64;            // bytes per im2col row (32 taps x 2 B)
 
@@ -107,7 +108,14 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
 // profiles/r1i_ncu_full_taps_c1.txt): now 8 epilogue warps (two per TMEM lane quarter, each half of the channels) keep
 // the per-(b, channel) sums in REGISTERS across tiles and reduce them once per sample.  NCB = 16-channel blocks per
 // epilogue warp (Cout = 32 * NCB).
-template <typename T, int NCB>
+//
+// LINES (compact volumes): K = the nine (dz, dy) input LINES instead of the 27 taps.  A builder thread owns one voxel column
+// w of the tile's 130 (halo included) and writes ONE 32-byte row A[w][k] = x[d+dz][h+dy][w] (9 two-byte loads, zeros for
+// k = 9..15); the three dx taps are ROW-SHIFTED views of that tile (start row dx + 1), i.e. 3 MMAs of K = 16 against
+// B_dx[co][9 lines].  A third of the loads and of the packing work of the 27-tap im2col (which limited the first version to
+// 0.74 ms for a 0.17 ms HBM stream).  (Fetching the lines by TMA and shifting by coordinates is not possible: a one-voxel
+// shift of a single-channel line is a 2-byte offset, and bulk tensor copies start on 16-byte boundaries.)
+template <typename T, int NCB, bool LINES>
 __global__ void __launch_bounds__(C1_FWD_THREADS, 1) conv_c1_fwd_kernel(const __grid_constant__ C1Params p) {
   extern __shared__ uint8_t dsmem_raw[];
   __shared__ __align__(8) uint64_t full_bar[C1_FWD_STAGES], empty_bar[C1_FWD_STAGES];
@@ -119,11 +127,11 @@ __global__ void __launch_bounds__(C1_FWD_THREADS, 1) conv_c1_fwd_kernel(const __
   constexpr int EPI_WARP0 = C1_FWD_BUILDERS + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
-  const int a_stage_bytes = 128 * C1_ROWB;                           // 8 KB
+  const int a_stage_bytes = LINES ? 5120 : 128 * C1_ROWB;            // 8 KB im2col tile / 130 (+ slack) rows of 32 bytes
   uint8_t* a_base = dsmem;
   uint8_t* b_tile = a_base + C1_FWD_STAGES * a_stage_bytes;          // [Cout][64 B], K-major, SWIZZLE_64B image
   const int out_buf_bytes = ((128 * p.Cout * 2 + 1023) / 1024) * 1024;
-  uint8_t* o_base = b_tile + 4096;
+  uint8_t* o_base = b_tile + (LINES ? 8192 : 4096);                  // LINES: three [Cout][32 B] tiles (one per dx)
   const uint32_t tmem_cols = (uint32_t)(2 * p.Cout);
 
   if (threadIdx.x == 0) {
@@ -132,8 +140,24 @@ __global__ void __launch_bounds__(C1_FWD_THREADS, 1) conv_c1_fwd_kernel(const __
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 64) s_bias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.Cout) ? p.bias[threadIdx.x] : 0.f;
+  if (LINES) {
+    // B_dx[co][k = (dz, dy)] (32-byte rows, SWIZZLE_32B image), zero for k = 9..15; and the rows 9..15 of every line box
+    for (int i = threadIdx.x; i < 3 * p.Cout * 2; i += blockDim.x) {
+      const int dx = i / (p.Cout * 2), co = (i >> 1) % p.Cout, c = i & 1;
+      const uint16_t* wp = reinterpret_cast<const uint16_t*>(p.w);
+      uint32_t wd[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k0 = c * 8 + 2 * j, k1 = k0 + 1;
+        const uint32_t lo = k0 < 9 ? (uint32_t)wp[((long long)(k0 * 3 + dx) * p.Cout + co) * p.Cin_p] : 0u;
+        const uint32_t hi = k1 < 9 ? (uint32_t)wp[((long long)(k1 * 3 + dx) * p.Cout + co) * p.Cin_p] : 0u;
+        wd[j] = lo | (hi << 16);
+      }
+      *reinterpret_cast<uint4*>(b_tile + dx * 2048 + co * 32 + ((c ^ ((co >> 2) & 1)) * 16)) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    }
+  }
   // weight tile B[co][tap] from the packed weights (ci = 0), zero for taps 27..31
-  for (int i = threadIdx.x; i < p.Cout * 4; i += blockDim.x) {
+  for (int i = threadIdx.x; !LINES && i < p.Cout * 4; i += blockDim.x) {
     const int co = i >> 2, c = i & 3;
     const uint16_t* wp = reinterpret_cast<const uint16_t*>(p.w);
     uint32_t wd[4];
@@ -155,7 +179,61 @@ __global__ void __launch_bounds__(C1_FWD_THREADS, 1) conv_c1_fwd_kernel(const __
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp < C1_FWD_BUILDERS) {
+  if (LINES && warp < C1_FWD_BUILDERS) {
+    // ===== line-tile builders: thread = one voxel column of the tile (130 with the halo: threads 0, 1 take a second row) =====
+    constexpr uint32_t NG = C1_FWD_BUILDERS / 4;
+    const uint32_t grp = (uint32_t)warp >> 2;
+    const int r0 = (warp & 3) * 32 + lane;
+    const uint16_t* xv = reinterpret_cast<const uint16_t*>(p.x);
+    const long long sh = p.W, sd = (long long)p.H * p.W;
+    // the nine line values of tile row r (voxel column w0 - 1 + r) of work unit u
+    auto fetch = [&](uint32_t u, int r, uint32_t (&v)[9]) {
+      int b, d, h, w0;
+      c1_unit(p, u, b, d, h, w0);
+      const int w = w0 - 1 + r;
+      const bool okw = (unsigned)w < (unsigned)p.W;
+      const uint16_t* plane = xv + (((long long)b * p.D + d) * p.H + h) * p.W;
+#pragma unroll
+      for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+          const bool ok = okw && (unsigned)(d + dz) < (unsigned)p.D && (unsigned)(h + dy) < (unsigned)p.H;
+          v[(dz + 1) * 3 + (dy + 1)] = ok ? (uint32_t)__ldg(plane + dz * sd + dy * sh + w) : 0u;
+        }
+    };
+    auto put = [&](uint8_t* st, int r, const uint32_t (&v)[9]) {
+      const uint4 c0 = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+      const uint4 c1 = make_uint4(v[8], 0u, 0u, 0u);
+      const int sw = (r >> 2) & 1;  // SWIZZLE_32B image: 16-byte pieces of rows 4..7 of every 8 swapped
+      *reinterpret_cast<uint4*>(st + r * 32 + (sw ? 16 : 0)) = c0;
+      *reinterpret_cast<uint4*>(st + r * 32 + (sw ? 0 : 16)) = c1;
+    };
+    // software pipeline: the loads of this group's NEXT tile are in flight while the current one is packed and handed over
+    // (a tile's lines come from L2 / HBM: their latency was the critical path of the whole kernel)
+    uint32_t va[9], vb[9], na[9], nb[9];
+    const uint32_t ustep = NG * gridDim.x;
+    uint32_t u = blockIdx.x + grp * gridDim.x;
+    if (u < p.units) {
+      fetch(u, r0, na);
+      if (r0 < 2) fetch(u, r0 + 128, nb);
+    }
+    for (uint32_t gi = grp; u < p.units; gi += NG, u += ustep) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { va[k] = na[k]; vb[k] = nb[k]; }
+      if (u + ustep < p.units) {
+        fetch(u + ustep, r0, na);
+        if (r0 < 2) fetch(u + ustep, r0 + 128, nb);
+      }
+      const uint32_t stage = gi % C1_FWD_STAGES;
+      mbar_wait(&empty_bar[stage], ((gi / C1_FWD_STAGES) & 1u) ^ 1u);
+      uint8_t* st = a_base + (size_t)stage * a_stage_bytes;
+      put(st, r0, va);
+      if (r0 < 2) put(st, r0 + 128, vb);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+    }
+  } else if (warp < C1_FWD_BUILDERS) {
     // ===== im2col builders: thread = one voxel of the tile =====
     // three groups of four builder warps take tiles round-robin: one group's load latency (a new input line from L2 /
     // HBM per tile, exposed by the proxy fence before the arrive) overlaps the other groups' packing
@@ -181,6 +259,8 @@ __global__ void __launch_bounds__(C1_FWD_THREADS, 1) conv_c1_fwd_kernel(const __
     const uint32_t a16 = __shfl_sync(0xffffffffu, (smem_u32(a_base) & 0x3FFFFu) >> 4, 0);
     const uint32_t b16 = __shfl_sync(0xffffffffu, (smem_u32(b_tile) & 0x3FFFFu) >> 4, 0);
     const uint32_t hi = (((8u * C1_ROWB) >> 4) & 0x3FFFu) | (1u << 14) | (4u << 29);  // SWIZZLE_64B
+    // LINES: A and B K-major with 32-byte rows (SWIZZLE_32B, SBO = 8 rows); a dx tap = A from row dx + 1 on
+    const uint32_t hi_b = ((8u * 32u) >> 4) | (1u << 14) | (6u << 29);
     uint32_t gi = 0;
     for (uint32_t u = blockIdx.x; u < p.units; u += gridDim.x, ++gi) {
       const uint32_t stage = gi % C1_FWD_STAGES, buf = gi & 1u;
@@ -190,23 +270,34 @@ __global__ void __launch_bounds__(C1_FWD_THREADS, 1) conv_c1_fwd_kernel(const __
       if (elect_one()) {
         const uint32_t sa = a16 + stage * (uint32_t)(a_stage_bytes >> 4);
         const uint32_t dcol = tmem_u + buf * (uint32_t)p.Cout;
+        if (LINES) {
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
-          umma_f16(dcol, ((uint64_t)hi << 32) | (uint64_t)(sa + 2u * ks), ((uint64_t)hi << 32) | (uint64_t)(b16 + 2u * ks),
-                   idesc, ks ? 1u : 0u);
+          for (int j = 0; j < 3; ++j)  // dx = j - 1: rows j .. j + 127 of the line tile against B_dx
+            umma_f16(dcol, ((uint64_t)hi_b << 32) | (uint64_t)(sa + (uint32_t)(j * 2)),
+                     ((uint64_t)hi_b << 32) | (uint64_t)(b16 + (uint32_t)(j * 128)), idesc, j ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            umma_f16(dcol, ((uint64_t)hi << 32) | (uint64_t)(sa + 2u * ks), ((uint64_t)hi << 32) | (uint64_t)(b16 + 2u * ks),
+                     idesc, ks ? 1u : 0u);
+        }
         umma_commit(&empty_bar[stage]);
         umma_commit(&acc_full[buf]);
       }
       __syncwarp();
     }
   } else {
-    // ===== epilogue: 8 warps, TMEM lane quarter = warp % 4, channel half = (warp - EPI_WARP0) / 4 =====
+    // ===== epilogue: two groups of 8 warps (group = tile parity = TMEM buffer = staging buffer: the per-tile chain of
+    // TMEM load -> arithmetic -> staging -> barrier -> bulk store is latency, so two tiles are drained at the same time);
+    // inside a group: TMEM lane quarter = warp % 4, channel half = (warp in group) / 4 =====
+    const int eg = (warp - EPI_WARP0) >> 3;
     const int q = warp & 3;
-    const int half = (warp - EPI_WARP0) >> 2;
+    const int half = ((warp - EPI_WARP0) & 7) >> 2;
     const int row = q * 32 + lane;
     const int cbase = half * (16 * NCB);
     const bool want_stats = p.stats != nullptr;
-    const bool issuer = warp == EPI_WARP0 && lane == 0;
+    const bool issuer = ((warp - EPI_WARP0) & 7) == 0 && lane == 0;
+    const int bar_id = 1 + eg;
     float csum[NCB][16], csq[NCB][16];
 #pragma unroll
     for (int i = 0; i < NCB; ++i)
@@ -226,9 +317,8 @@ __global__ void __launch_bounds__(C1_FWD_THREADS, 1) conv_c1_fwd_kernel(const __
         for (int j = 0; j < 16; ++j) { csum[i][j] = 0.f; csq[i][j] = 0.f; }
       }
     };
-    uint32_t gi = 0;
     int cur_b = -1;
-    for (uint32_t u = blockIdx.x; u < p.units; u += gridDim.x, ++gi) {
+    for (uint32_t gi = (uint32_t)eg, u = blockIdx.x + (uint32_t)eg * gridDim.x; u < p.units; gi += 2, u += 2 * gridDim.x) {
       int b, d, h, w0;
       c1_unit(p, u, b, d, h, w0);
       if (want_stats && b != cur_b) {
@@ -236,9 +326,9 @@ __global__ void __launch_bounds__(C1_FWD_THREADS, 1) conv_c1_fwd_kernel(const __
         cur_b = b;
       }
       const uint32_t buf = gi & 1u;
-      uint8_t* stage_out = o_base + (size_t)buf * out_buf_bytes;
-      if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      uint8_t* stage_out = o_base + (size_t)(eg * 2 + ((gi >> 1) & 1u)) * out_buf_bytes;  // two staging buffers per group
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // this group's store before the last
+      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
       mbar_wait(&acc_full[buf], (gi >> 1) & 1u);
       tc_fence_after();
       const bool valid = w0 + row < p.W;
@@ -273,7 +363,7 @@ __global__ void __launch_bounds__(C1_FWD_THREADS, 1) conv_c1_fwd_kernel(const __
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
       if (issuer) {
         tma_store_3d(&p.o_map, stage_out, 0, w0, (b * p.D + d) * p.H + h);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -433,9 +523,15 @@ static int c1_common(C1Params& q, const void* x, long long xs, int dtype, int B,
 }
 
 template <typename T, int NCB>
-static cudaError_t launch_c1_fwd(const C1Params& q, int gx, int smem, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(conv_c1_fwd_kernel<T, NCB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) conv_c1_fwd_kernel<T, NCB><<<gx, C1_FWD_THREADS, smem, s>>>(q);
+static cudaError_t launch_c1_fwd(const C1Params& q, int gx, int smem, bool tma_in, cudaStream_t s) {
+  cudaError_t e;
+  if (tma_in) {
+    e = cudaFuncSetAttribute(conv_c1_fwd_kernel<T, NCB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) conv_c1_fwd_kernel<T, NCB, true><<<gx, C1_FWD_THREADS, smem, s>>>(q);
+  } else {
+    e = cudaFuncSetAttribute(conv_c1_fwd_kernel<T, NCB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) conv_c1_fwd_kernel<T, NCB, false><<<gx, C1_FWD_THREADS, smem, s>>>(q);
+  }
   return e;
 }
 
@@ -447,13 +543,16 @@ int conv_c1_fwd(const void* x, long long xs, const void* w, int Cin_p, const flo
   q.w = w; q.Cin_p = Cin_p; q.bias = bias; q.stats = stats;
   if (Cout_p != 32 && Cout_p != 64) { set_error("conv_c1_fwd: Cout_p must be 32 or 64"); return MTB200_ERR_UNSUPPORTED; }
   const int out_buf = ((128 * Cout_p * 2 + 1023) / 1024) * 1024;
-  const int smem = C1_FWD_STAGES * 128 * C1_ROWB + 4096 + 2 * out_buf + 1024;
+  // K = lines variant: compact volume (MTB200_C1_LINES=0: the 27-tap im2col kernel)
+  static const int lines_on = [] { const char* e = getenv("MTB200_C1_LINES"); return e ? atoi(e) : 1; }();
+  const bool tma_in = lines_on && xs == 1;
+  const int smem = C1_FWD_STAGES * (tma_in ? 5120 : 128 * C1_ROWB) + (tma_in ? 8192 : 4096) + 4 * out_buf + 1024;
   const int gx = (int)min((long long)q.units, (long long)num_sms());  // one persistent CTA per SM
   cudaError_t e;
   if (dtype == MTB200_BF16) {
-    e = Cout_p == 32 ? launch_c1_fwd<__nv_bfloat16, 1>(q, gx, smem, s) : launch_c1_fwd<__nv_bfloat16, 2>(q, gx, smem, s);
+    e = Cout_p == 32 ? launch_c1_fwd<__nv_bfloat16, 1>(q, gx, smem, tma_in, s) : launch_c1_fwd<__nv_bfloat16, 2>(q, gx, smem, tma_in, s);
   } else {
-    e = Cout_p == 32 ? launch_c1_fwd<__half, 1>(q, gx, smem, s) : launch_c1_fwd<__half, 2>(q, gx, smem, s);
+    e = Cout_p == 32 ? launch_c1_fwd<__half, 1>(q, gx, smem, tma_in, s) : launch_c1_fwd<__half, 2>(q, gx, smem, tma_in, s);
   }
   if (e != cudaSuccess) { set_error("conv_c1_fwd: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
   return check_launch("conv_c1_fwd");
