@@ -86,6 +86,12 @@ typedef struct {
                            5 = tcgen05 line-streaming kernel (dy taps merged into N) only,
                            6 = tcgen05 pointwise (1x1x1) streaming kernel only,
                            7 = tcgen05 group-merged lattice kernel (stride-2 dgrad / ConvTranspose fwd) only */
+  /* PLANAR concatenation (the two halves of a decoder input as two compact tensors instead of interleaved channels: a
+   * consumer of ONE half then reads whole 128-byte lines; interleaved 32-channel halves cost twice the DRAM traffic).
+   * in_split > 0: `in` is [2][B][D][H][W][in_ldc]; input channel c lives in half c / in_split at channel c % in_split
+   * (Cin == 2 * in_split, in_coff == 0).  out_split: the same for `out` (data gradient of such a layer).  Only the
+   * line-streaming tensor-core kernel implements it (MTB200_ERR_UNSUPPORTED otherwise). */
+  int32_t in_split, out_split;
 } mtb200_conv_params;
 
 /* Weight-gradient of the same tap-table problem:
@@ -109,6 +115,7 @@ typedef struct {
   int32_t tap_off[MTB200_MAX_TAPS][3];
   int32_t tap_widx[MTB200_MAX_TAPS];
   int32_t impl;
+  int32_t in_split;     /* planar halves of x, as mtb200_conv_params::in_split */
 } mtb200_wgrad_params;
 
 /* ---- library / error handling -------------------------------------------------------------------------------- */

@@ -46,6 +46,7 @@ class ConvParams(C.Structure):
         ("red_y", C.c_void_p), ("red_xform", C.c_void_p), ("red_meanrstd", C.c_void_p), ("red", C.c_void_p),
         ("red_ldc", C.c_int32), ("red_coff", C.c_int32),
         ("impl", C.c_int32),
+        ("in_split", C.c_int32), ("out_split", C.c_int32),
     ]
 
 
@@ -66,6 +67,7 @@ class WgradParams(C.Structure):
         ("tap_off", (C.c_int32 * 3) * MAX_TAPS),
         ("tap_widx", C.c_int32 * MAX_TAPS),
         ("impl", C.c_int32),
+        ("in_split", C.c_int32),
     ]
 
 

@@ -45,6 +45,8 @@ int wgrad_taps_ffma(const mtb200_wgrad_params& p, cudaStream_t s);
 int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s);   // conv_umma.cu
 int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s); // conv_umma.cu
 int umma_available();
+int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s);    // conv_line.cu
+int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s);  // wgrad_line.cu
 int conv_c1_fwd(const void*, long long, const void*, int, const float*, void*, int, int, int, double*, int, int, int, int,
                 int, cudaStream_t);  // conv_c1.cu
 int conv_c1_wgrad(const void*, long long, const void*, int, int, int, float*, int, int, int, int, int, int, cudaStream_t);
@@ -114,9 +116,17 @@ const char* mtb200_last_kernel(void) { return g_last_kernel; }
 int mtb200_conv_taps(const mtb200_conv_params* p, void* stream) {
   MTB_REQUIRE(p && p->in && p->out && p->w, "conv_taps: null pointer");
   if (int r = validate_taps(p->ngroups, p->group_tap_begin, p->ntaps)) return r;
-  MTB_REQUIRE(p->in_coff + p->Cin <= p->in_ldc && p->out_coff + p->Cout <= p->out_ldc,
+  MTB_REQUIRE((p->in_split ? (p->in_coff == 0 && p->Cin == 2 * p->in_split && p->in_split <= p->in_ldc)
+                           : p->in_coff + p->Cin <= p->in_ldc) &&
+                  (p->out_split ? (p->out_coff == 0 && p->Cout == 2 * p->out_split && p->out_split <= p->out_ldc)
+                                : p->out_coff + p->Cout <= p->out_ldc),
               "conv_taps: channel slice exceeds ldc (in %d+%d/%d, out %d+%d/%d)", p->in_coff, p->Cin, p->in_ldc,
               p->out_coff, p->Cout, p->out_ldc);
+  if (p->in_split || p->out_split) {  // planar halves: the line-streaming tensor-core kernel only
+    const int r = (umma_available() && p->dtype != MTB200_F32) ? conv_line_umma(*p, STREAM(stream)) : MTB200_ERR_UNSUPPORTED;
+    if (r == MTB200_ERR_UNSUPPORTED) set_error("conv_taps: planar halves (in_split / out_split) outside the line kernel's envelope");
+    return r;
+  }
   if (p->impl >= 2 || (p->impl == 0 && umma_available() && p->dtype != MTB200_F32)) {
     int r = conv_taps_umma(*p, STREAM(stream));
     if (r != MTB200_ERR_UNSUPPORTED || p->impl >= 2) return r;
@@ -127,6 +137,11 @@ int mtb200_conv_taps(const mtb200_conv_params* p, void* stream) {
 int mtb200_wgrad_taps(const mtb200_wgrad_params* p, void* stream) {
   MTB_REQUIRE(p && p->x && p->dy && p->dw, "wgrad_taps: null pointer");
   if (int r = validate_taps(p->ngroups, p->group_tap_begin, p->ntaps)) return r;
+  if (p->in_split) {  // planar halves: the line-streaming tensor-core kernel only
+    const int r = (umma_available() && p->dtype != MTB200_F32) ? wgrad_line_umma(*p, STREAM(stream)) : MTB200_ERR_UNSUPPORTED;
+    if (r == MTB200_ERR_UNSUPPORTED) set_error("wgrad_taps: planar halves (in_split) outside the line kernel's envelope");
+    return r;
+  }
   if (p->impl >= 2 || (p->impl == 0 && umma_available() && p->dtype != MTB200_F32)) {
     int r = wgrad_taps_umma(*p, STREAM(stream));
     if (r != MTB200_ERR_UNSUPPORTED) return r;  // shapes the tensor-core kernel does not cover use the CUDA-core one

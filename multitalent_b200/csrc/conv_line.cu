@@ -58,6 +58,8 @@ struct LineParams {
   int P, wt, dgroups;            // planes per M tile (1 or 2), w voxels per tile (128 / P), D / P
   int units;                     // work units walked by the persistent CTAs
   int accumulate, is_f16;
+  int in_split;                  // planar input halves: chunk c is sample b + c * B of a [2B] tensor (channel 0)
+  int out_split;                 // planar output halves: Cout block n0 goes to half n0 / out_split
   int dbg;                       // experiments only (MTB200_LINE_DBG): bit 0 = read one accumulator block per line
   // fused InstanceNorm-backward reduction (RED kernels, see mtb200_conv_params::red)
   const void* red_y;
@@ -142,7 +144,9 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
           for (int z = 0; z < p.ndz; ++z)
             for (int c = 0; c < p.nchunk; ++c) {
               uint8_t* sub = dst + (size_t)z * p.line_bytes + (size_t)c * p.sub_bytes;
-              if (p.P == 1)  // map dims (C, W, H, D, B)
+              if (p.in_split)  // planar halves: chunk c = the whole channel range of half c (sample index b + c * B)
+                tma_load_5d(sub, &p.a_map, &st_full[slot], 0, t.w0 - 1, t.hfirst + s, t.d + p.dz0 + z, t.b + c * p.B);
+              else if (p.P == 1)  // map dims (C, W, H, D, B)
                 tma_load_5d(sub, &p.a_map, &st_full[slot], c * p.kcw, t.w0 - 1, t.hfirst + s, t.d + p.dz0 + z, t.b);
               else           // map dims (C, D, W, H, B): planes d+dz, d+dz+1 interleaved row by row
                 tma_load_5d(sub, &p.a_map, &st_full[slot], c * p.kcw, t.d + p.dz0 + z, t.w0 - 1, t.hfirst + s, t.b);
@@ -171,6 +175,8 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
     const uint32_t w16 = __shfl_sync(0xffffffffu, (smem_u32(w_base) & 0x3FFFFu) >> 4, 0);
     const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, line16 = (uint32_t)p.line_bytes >> 4;
     const uint32_t wgroup16 = (uint32_t)p.wgroup_bytes >> 4;
+    const uint32_t sub16 = (uint32_t)p.sub_bytes >> 4, wchunk16 = (uint32_t)p.wchunk_bytes >> 4;
+    const int nchunk = p.nchunk;
     const int ngroups = (p.dbg & 8) ? 1 : p.ngroups;
     // per-group descriptor offsets live in (uniform) registers: the issue loop is a handful of adds per MMA.  The single
     // issuing warp pays the full latency of every dependent instruction, so nothing else may sit between two MMAs.
@@ -197,10 +203,12 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
 #pragma unroll
           for (int g = 0; g < 9; ++g) {
             if (g < ngroups) {
+              for (int c = 0; c < nchunk; ++c) {  // channel chunks (2 for planar halves, else 1)
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k)
-                umma_f16(dq, ln_desc64(hi, a_s + a_goff[g] + (uint32_t)(k * 2)), ln_desc64(hi, b_goff[g] + (uint32_t)(k * 2)),
-                         idesc, (g | k) ? 1u : 0u);
+                for (int k = 0; k < KSTEPS; ++k)
+                  umma_f16(dq, ln_desc64(hi, a_s + a_goff[g] + (uint32_t)c * sub16 + (uint32_t)(k * 2)),
+                           ln_desc64(hi, b_goff[g] + (uint32_t)c * wchunk16 + (uint32_t)(k * 2)), idesc, (g | c | k) ? 1u : 0u);
+              }
             }
           }
           umma_commit(&st_empty[slot]);
@@ -214,6 +222,11 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
     const int q = warp & 3;
     const int part = (warp - 3) >> 2;
     T* out = reinterpret_cast<T*>(p.out);
+    int n0o = n0;  // channel offset of this CTA's block inside its output tensor
+    if (p.out_split) {  // planar output halves: [2][B][D][H][W][out_ldc]
+      out += (long long)(n0 / p.out_split) * p.B * p.D * p.H * p.W * p.out_ldc;
+      n0o = n0 % p.out_split;
+    }
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * LN_CPT);
     float bias[LN_CPT];  // RED (data gradient: no bias) keeps the InstanceNorm scale of its channels here instead
 #pragma unroll
@@ -294,7 +307,7 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
 #pragma unroll
           for (int j = 0; j < LN_CPT; ++j)
             v[j] = (RED ? 0.f : bias[j]) + __uint_as_float(r[0][j]) + __uint_as_float(r[1][j]) + __uint_as_float(r[2][j]);
-          T* orow = out + ((((long long)b * p.D + d) * p.H + h) * p.W + ww) * p.out_ldc + p.out_coff + n0 + part * LN_CPT;
+          T* orow = out + ((((long long)b * p.D + d) * p.H + h) * p.W + ww) * p.out_ldc + p.out_coff + n0o + part * LN_CPT;
 #pragma unroll
           for (int c8 = 0; c8 < LN_CPT; c8 += 8) {
             float o8[8];
@@ -403,7 +416,9 @@ int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s) {
     if (p.is[k] != 1 || p.os[k] != 1 || p.group_ooff[0][k] != 0) return MTB200_ERR_UNSUPPORTED;
   if (p.Do != p.Di || p.Ho != p.Hi || p.Wo != p.Wi || p.Dof != p.Do || p.Hof != p.Ho || p.Wof != p.Wo)
     return MTB200_ERR_UNSUPPORTED;
-  if (p.Cin != 16 && p.Cin != 32 && p.Cin != 64) return MTB200_ERR_UNSUPPORTED;  // one chunk (nchunk == 1)
+  if (p.Cin != 16 && p.Cin != 32 && p.Cin != 64) return MTB200_ERR_UNSUPPORTED;  // one chunk, or two planar halves
+  if (p.in_split && (p.in_split != 32 || p.Cin != 64 || p.in_coff != 0 || p.Wo < 72)) return MTB200_ERR_UNSUPPORTED;
+  if (p.out_split && (p.out_split % LN_BN || p.Cout != 2 * p.out_split || p.out_coff != 0 || p.red)) return MTB200_ERR_UNSUPPORTED;
   if (p.Cout % LN_BN) return MTB200_ERR_UNSUPPORTED;
   // an M tile is one h-line of 128 w voxels, or (narrow maps) two depth planes of one 64-wide h-line
   static int pair_ok = -1;  // MTB200_LINE_PAIR=0 disables the two-plane variant; cleared if its tensor map is refused
@@ -442,8 +457,9 @@ int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s) {
     for (int j = 0; j < 3; ++j)
       if (q.grp_widx[g][j] < 0) return MTB200_ERR_UNSUPPORTED;  // needs all three dy taps of every (dz, dx)
 
-  q.kcw = p.Cin < 64 ? p.Cin : 64;
+  q.kcw = p.in_split ? p.in_split : (p.Cin < 64 ? p.Cin : 64);
   q.nchunk = p.Cin / q.kcw;
+  q.in_split = p.in_split; q.out_split = p.out_split;
   const int rowb = q.kcw * 2;
   q.P = P;
   q.wt = 128 / P;
@@ -461,7 +477,9 @@ int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s) {
   if (q.stages < 2) return MTB200_ERR_UNSUPPORTED;
 
   if (P == 1) {
-    cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.Di, (cuuint64_t)p.B};
+    // planar halves: one tensor of 2B samples with in_split channels each
+    cuuint64_t dims[5] = {(cuuint64_t)(p.in_split ? p.in_split : p.Cin), (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.Di,
+                          (cuuint64_t)(p.in_split ? 2 * p.B : p.B)};
     cuuint64_t strides[4] = {(cuuint64_t)p.in_ldc * 2, (cuuint64_t)p.Wi * p.in_ldc * 2,
                              (cuuint64_t)p.Hi * p.Wi * p.in_ldc * 2, (cuuint64_t)p.Di * p.Hi * p.Wi * p.in_ldc * 2};
     cuuint32_t box[5] = {(cuuint32_t)q.kcw, (cuuint32_t)LN_WROWS, 1, 1, 1};

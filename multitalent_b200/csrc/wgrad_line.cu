@@ -50,6 +50,7 @@ struct WgradLineParams {
   long long units;
   int npy, npz, nslots;      // (Cin chunk, Cout block) pairs and the number of CTA slots that walk the units
   int cosched;               // 1: the pairs of a unit run side by side (default); 0: pair-major grid (A/B measurements)
+  int in_split;              // planar X halves: Cin chunk i is sample b + i * B of a [2B] tensor (channel 0)
   int lut[27];               // [dz+1][dy+1][dx+1] -> weight slice or -1
   int is_f16;
 };
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __
   const int slot = p.cosched ? (int)blockIdx.x / npairs : (int)blockIdx.x % p.nslots;
   const int c0 = (pair % p.npy) * p.kcw;
   const int n0 = (pair / p.npy) * p.cout_blk;
+  const int xc0 = p.in_split ? 0 : c0, xb0 = p.in_split ? (pair % p.npy) * p.B : 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 1); }
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __
           uint8_t* dst = dsmem + (size_t)slot * p.stage_bytes;
           mbar_expect_tx(&st_full[slot], (uint32_t)((p.dbg & 1) ? p.x_tx : p.stage_tx));
           for (int z = 0; z < p.ndz; ++z)
-            tma_load_5d(dst + (size_t)z * p.xline_bytes, &p.x_map, &st_full[slot], c0, w0 - 1, hp, d + p.dz0 + z, b);
+            tma_load_5d(dst + (size_t)z * p.xline_bytes, &p.x_map, &st_full[slot], xc0, w0 - 1, hp, d + p.dz0 + z, b + xb0);
           for (int sg = 0; sg < p.nseg && !(p.dbg & 1); ++sg)  // lines hp-1, hp, hp+1 (or hp alone)
             tma_load_5d(dst + p.ybase + p.seg_off[sg], &p.dy_map[sg], &st_full[slot], n0 + p.seg_c0[sg], w0,
                         hp - (p.nb == 3 ? 1 : 0), d, b);
@@ -236,6 +238,7 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   if (p.Do != p.Di || p.Ho != p.Hi || p.Wo != p.Wi || p.Dof != p.Do || p.Hof != p.Ho || p.Wof != p.Wo)
     return MTB200_ERR_UNSUPPORTED;
   if (p.Cin != 16 && p.Cin % 32 != 0) return MTB200_ERR_UNSUPPORTED;
+  if (p.in_split && (p.in_split != 32 || p.Cin != 64 || p.in_coff != 0)) return MTB200_ERR_UNSUPPORTED;
   // every (Cin chunk, Cout block) pair re-streams both operands from L2: worth it while the pair count is small
   const bool cout48 = p.Cout == 48 && p.Cin <= 32;  // the 47 heads on the widest maps: one column block of 32 + 16
   // MTB200_WLINE_MINW / MTB200_WLINE_MAXPAIRS: envelope knobs for A/B measurements (defaults = what measured fastest).
@@ -286,7 +289,8 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   q.stages = min(WL_MAX_STAGES, (224 * 1024) / q.stage_bytes);
   if (q.stages < 2) return MTB200_ERR_UNSUPPORTED;
   {
-    cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.Di, (cuuint64_t)p.B};
+    cuuint64_t dims[5] = {(cuuint64_t)(p.in_split ? p.in_split : p.Cin), (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.Di,
+                          (cuuint64_t)(p.in_split ? 2 * p.B : p.B)};
     cuuint64_t strides[4] = {(cuuint64_t)p.in_ldc * 2, (cuuint64_t)p.Wi * p.in_ldc * 2,
                              (cuuint64_t)p.Hi * p.Wi * p.in_ldc * 2, (cuuint64_t)p.Di * p.Hi * p.Wi * p.in_ldc * 2};
     cuuint32_t box[5] = {(cuuint32_t)q.kcw, (cuuint32_t)xrows, 1, 1, 1};
@@ -309,6 +313,7 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   q.B = p.B; q.D = p.Do; q.H = p.Ho; q.W = p.Wo;
   q.Cin = p.Cin; q.Cout = p.Cout;
   q.is_f16 = p.dtype == MTB200_F16;
+  q.in_split = p.in_split;
   q.ntw = (p.Wo + q.wt - 1) / q.wt;
   const int sms = num_sms();
   q.npy = nchunk;

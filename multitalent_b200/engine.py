@@ -131,10 +131,23 @@ class Feat:
     #                                          step's buffers would wait for the cyclic garbage collector)
     single_consumer: bool = False            # exactly one layer consumes this output: its dgrad holds the FINAL d(act)
     red_fused: Optional[torch.Tensor] = None  # InstanceNorm-backward sums already accumulated by that dgrad's epilogue
+    # PLANAR concatenation (full-resolution skip level of the tensor-core path): `planar` = the [2, B, D, H, W, Cp] tensor
+    # whose halves are the up-sampled features (0) and the skip (1), each a compact NDHWC tensor.  `half` = 0 / 1: this
+    # Feat is one half (buf = planar[half], an ordinary compact feature); None: the concatenation of both (buf = the
+    # [2B, D, H, W, Cp] view; only the line-streaming conv kernels read / write it, mtb200_conv_params::in_split).
+    planar: Optional[torch.Tensor] = None
+    half: Optional[int] = None
 
     @property
     def dims(self):
+        if self.planar is not None and self.half is None:
+            return (self.buf.shape[0] // 2,) + tuple(self.buf.shape[1:4])
         return tuple(self.buf.shape[:4])
+
+    @property
+    def split(self):
+        """Channels per planar half when this Feat is a planar concatenation, else 0."""
+        return self.buf.shape[4] if (self.planar is not None and self.half is None) else 0
 
     @property
     def ldc(self):
@@ -358,23 +371,37 @@ class Tape:
         self.direct_done = set()  # ids of parameters whose gradient went straight into their arena slot
         self.keep = []  # keep python references to buffers alive
 
+    @staticmethod
+    def _key_blocks(f: Feat):
+        """(gradient-buffer key, 16-channel blocks of it that `f` covers).  The halves and the concatenation of a planar
+        buffer share ONE gradient buffer of the same planar layout (keyed by the planar tensor)."""
+        if f.planar is not None:
+            n16 = f.planar.shape[5] // 16
+            h0, h1 = (0, 2) if f.half is None else (f.half, f.half + 1)
+            return id(f.planar), set(range(h0 * n16, h1 * n16))
+        return id(f.buf), set(range(f.coff // 16, (f.coff + f.Cp) // 16))
+
     def grad_feat(self, f: Feat) -> Tuple[Feat, bool]:
         """Gradient slice matching `f` and whether it already holds a value (=> producers must accumulate)."""
-        k = id(f.buf)
+        k, blocks = self._key_blocks(f)
         if k not in self.grad_bufs:
-            self.grad_bufs[k] = torch.empty_like(f.buf)
+            self.grad_bufs[k] = torch.empty_like(f.planar if f.planar is not None else f.buf)
             self.grad_init[k] = set()
-        blocks = set(range(f.coff // 16, (f.coff + f.Cp) // 16))
         have = blocks & self.grad_init[k]
         assert not have or have == blocks, "partially initialised gradient slice"
-        return Feat(self.grad_bufs[k], f.coff, f.C, f.Cp), bool(have)
+        gb = self.grad_bufs[k]
+        if f.planar is not None:
+            buf = gb.view((-1,) + tuple(gb.shape[2:])) if f.half is None else gb[f.half]
+            return Feat(buf, 0, f.C, f.Cp, planar=gb, half=f.half), bool(have)
+        return Feat(gb, f.coff, f.C, f.Cp), bool(have)
 
     def mark(self, f: Feat):
-        self.grad_init[id(f.buf)] |= set(range(f.coff // 16, (f.coff + f.Cp) // 16))
+        k, blocks = self._key_blocks(f)
+        self.grad_init[k] |= blocks
 
     def has_grad(self, f: Feat) -> bool:
-        k = id(f.buf)
-        return k in self.grad_init and set(range(f.coff // 16, (f.coff + f.Cp) // 16)) <= self.grad_init[k]
+        k, blocks = self._key_blocks(f)
+        return k in self.grad_init and blocks <= self.grad_init[k]
 
     def add_param_grad(self, p, g):
         if p is None:
@@ -417,6 +444,7 @@ class Engine:
         # is not computed at all in the forward pass -- the loss's first pass evaluates the logits window on the tensor core
         # from the head's input (mtb200_head_fwd_stats) and the fused backward recomputes it.  The network then returns a
         # zero-stride placeholder for that output; only multitalent_loss(engine=...) may consume it.
+        self.planar_concat = os.environ.get("MTB200_PLANAR", "1") != "0"
         self.defer_head_fwd = os.environ.get("MTB200_DEFER_HEAD", "1") != "0"
         self.defer_heads = False
         self.deferred = {}       # placeholder pointer -> {"x": head input, "op": head}
@@ -463,6 +491,15 @@ class Engine:
         f = torch.zeros if zero else torch.empty
         return f(tuple(dims) + (ldc,), dtype=self.dtype, device=device)
 
+    def planar_concat_ok(self, half_Cp: int, dims) -> bool:
+        """Planar skip / up-sampling halves for a decoder level (instead of interleaved channels in one buffer)?  Where a
+        half is 32 channels = 64 bytes per voxel, every kernel that touches ONE half of the interleaved buffer (strided
+        conv of the next encoder stage, InstanceNorm passes of the skip, transposed conv and its gradients) moved whole
+        128-byte lines for 64 useful bytes.  Needs the line-streaming kernels for the level's first decoder conv."""
+        _, D, H, W = dims
+        return bool(self.planar_concat and self.materialize_inputs and self.impl in (0, 2, 8) and half_Cp == 32
+                    and W >= 72 and H >= 4)
+
     def use_c1(self, op: "ConvOp") -> bool:
         """First-layer kernels (K = taps) apply: single input channel, 16-bit tensor-core path."""
         return bool(op.c1 and self.materialize_inputs and self.impl in (0, 2, 8))
@@ -502,6 +539,7 @@ class Engine:
         p.in_ldc, p.in_coff, p.Cin = x.ldc, x.coff, Cin_p
         _, p.Dof, p.Hof, p.Wof = out.dims
         p.out_ldc, p.out_coff, p.Cout = out.ldc, out.coff, Cout_p
+        p.in_split, p.out_split = x.split, out.split  # planar concatenations (line-streaming kernels only)
         p.Do, p.Ho, p.Wo = grid_dims
         table.fill(p)
         p.accumulate = int(accumulate)
@@ -685,6 +723,7 @@ class Engine:
         p.dtype = dt
         p.B, p.Di, p.Hi, p.Wi = x.dims
         p.in_ldc, p.in_coff, p.Cin = x.ldc, x.coff, op.Cin_p
+        p.in_split = x.split
         _, p.Dof, p.Hof, p.Wof = dy.dims
         p.out_ldc, p.out_coff, p.Cout = dy.ldc, dy.coff, op.Cout_p
         p.Do, p.Ho, p.Wo = x.dims[1:] if op.transposed else dy.dims[1:]

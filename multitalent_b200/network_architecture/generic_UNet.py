@@ -372,13 +372,18 @@ class Generic_UNet(SegmentationNetwork):
                     # the stage output is the skip: it goes straight into the second half of the concat buffer --
                     # raw (norm-on-load kernels) or, for the TMA-fed tensor-core kernels, as the materialised activation
                     od = op.out_dims(f.dims)
-                    cat = eng.new_buf(od, 2 * op.Cout_p, dev)
+                    planar = eng.planar_concat_ok(op.Cout_p, od)
+                    if planar:  # two compact halves [2, B, D, H, W, Cp]: 0 = up-sampled features, 1 = this skip
+                        cat = torch.empty((2,) + tuple(od) + (op.Cout_p,), dtype=eng.dtype, device=dev)
+                    else:
+                        cat = eng.new_buf(od, 2 * op.Cout_p, dev)
                     if not mat:
                         out = Feat(cat, op.Cout_p, op.Cout, op.Cout_p)
                 f = eng.conv_norm(ttape, op, g, b, f, out, need_input_grad=not first)
                 f.single_consumer = not last  # the stage output also feeds the decoder (skip connection)
                 if last and mat:
-                    f.act = eng.materialize(f, out=Feat(cat, op.Cout_p, op.Cout, op.Cout_p))
+                    f.act = eng.materialize(f, out=(Feat(cat[1], 0, op.Cout, op.Cout_p, planar=cat, half=1) if planar
+                                                    else Feat(cat, op.Cout_p, op.Cout, op.Cout_p)))
                 first = False
             skips.append(f)
             # data parallel: in the backward pass everything recorded AFTER this point (deeper encoder stages,
@@ -393,12 +398,21 @@ class Generic_UNet(SegmentationNetwork):
         nu = len(ops['tu'])
         for u in range(nu):
             skip = skips[-(u + 1)]
-            cat = skip.act.buf if mat else skip.buf
             top = ops['tu'][u]
-            assert top.Cout_p == skip.Cp and cat.shape[4] == 2 * skip.Cp
-            # the transposed conv writes the first half of the same buffer: torch.cat (generic_UNet.py:392) vanishes
-            eng.conv_plain(ttape, top, f, Feat(cat, 0, top.Cout, top.Cout_p))
-            if mat:
+            assert top.Cout_p == skip.Cp
+            base = skip.act.planar if mat else None
+            if base is not None:  # planar halves: the transposed conv writes half 0, the level's first conv reads both
+                eng.conv_plain(ttape, top, f, Feat(base[0], 0, top.Cout, top.Cout_p, planar=base, half=0))
+                f = Feat(base.view((-1,) + tuple(base.shape[2:])), 0, top.Cout + skip.C, 2 * skip.Cp, planar=base)
+                cat = None
+            else:
+                cat = skip.act.buf if mat else skip.buf
+                assert cat.shape[4] == 2 * skip.Cp
+                # the transposed conv writes the first half of the same buffer: torch.cat (generic_UNet.py:392) vanishes
+                eng.conv_plain(ttape, top, f, Feat(cat, 0, top.Cout, top.Cout_p))
+            if base is not None:
+                pass
+            elif mat:
                 f = Feat(cat, 0, top.Cout + skip.C, 2 * skip.Cp)
             else:
                 ident = torch.zeros((cat.shape[0], skip.Cp, 4), dtype=torch.float32, device=dev)

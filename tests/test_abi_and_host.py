@@ -40,8 +40,8 @@ def test_struct_layout_matches_header(tmp_path):
     Structures of multitalent_b200/_lib.py (guards against ctypes/C drift)."""
     import subprocess
     fields = {"mtb200_conv_params": (L.ConvParams, ["in", "stats", "dtype", "Cin", "Do", "ngroups", "ntaps", "tap_widx",
-                                                     "accumulate", "red_y", "red", "red_ldc", "impl"]),
-              "mtb200_wgrad_params": (L.WgradParams, ["x", "xform", "dtype", "Cout", "ntaps", "tap_widx", "impl"]),
+                                                     "accumulate", "red_y", "red", "red_ldc", "impl", "in_split", "out_split"]),
+              "mtb200_wgrad_params": (L.WgradParams, ["x", "xform", "dtype", "Cout", "ntaps", "tap_widx", "impl", "in_split"]),
               "mtb200_head_bwd_params": (L.HeadBwdParams, ["logits", "w_fwd", "dw", "nvox", "dtype", "Cin", "accumulate",
                                                            "win_c0"]),
               "mtb200_head_fwd_params": (L.HeadFwdParams, ["x", "hard", "nvox", "dtype", "Cout", "win_c0"]),

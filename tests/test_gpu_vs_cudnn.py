@@ -17,6 +17,8 @@ import pytest
 import torch
 from torch import nn
 
+from multitalent_b200 import _lib as L
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 FULL_PATCH = (192, 160, 128)
@@ -212,3 +214,47 @@ def test_library_training_step_matches_native_step_small(golden_small):
     assert abs(float(l) - float(lr_)) < 1e-3 * max(1.0, abs(float(lr_)))
     worst = max(float((p.detach() - ref.params[n].detach()).abs().max()) for n, p in tr.network.named_parameters())
     assert worst < 1e-4, "updated parameters differ by %.3e" % worst
+
+
+def test_planar_concat_layer_vs_cudnn():
+    """The first decoder conv of the full-resolution level with PLANAR input halves (mtb200_conv_params::in_split /
+    out_split: up-sampled features and skip as two compact tensors): forward, data gradient (written back into two
+    planar halves) and weight gradient against cuDNN fp32 on the same bf16 operands."""
+    _require_tcgen05()
+    from multitalent_b200.engine import ConvOp, Engine, Feat, Tape
+    from oracle.gpu_reference import conv_reference, conv_reference_grads
+    dtype = torch.bfloat16
+    torch.manual_seed(5)
+    B, D, H, W = 2, 24, 32, 128
+    cin, cout, split = 60, 30, 30
+    mod = nn.Conv3d(cin, cout, 3, 1, 1, bias=False).to(DEV)
+    op = ConvOp(mod.weight, None, (3, 3, 3), (1, 1, 1), split=split)
+    eng = Engine(dtype, 0)
+    assert eng.planar_concat_ok(32, (B, D, H, W))
+    x = torch.randn(B, cin, D, H, W, device=DEV).to(dtype)
+    base = torch.zeros(2, B, D, H, W, 32, device=DEV, dtype=dtype)
+    xl = x.permute(0, 2, 3, 4, 1)
+    base[0][..., :split] = xl[..., :split]
+    base[1][..., :cin - split] = xl[..., split:]
+    xf = Feat(base.view(2 * B, D, H, W, 32), 0, cin, 64, planar=base)
+    assert xf.dims == (B, D, H, W) and xf.split == 32
+    tape = Tape()
+    y = eng.conv_plain(tape, op, xf)
+    assert L.lib().mtb200_last_kernel() == b"conv_line_umma"
+    ref = conv_reference(x, mod.weight.to(dtype), (1, 1, 1), [1, 1, 1], False)
+    e_f = _rel_err(y.buf[..., :cout].permute(0, 4, 1, 2, 3), ref)
+    assert e_f <= 2.5 * ULP[dtype], "forward: %.3e of max|ref|" % e_f
+    gy = torch.randn_like(ref).to(dtype)
+    eng.seed_grad(tape, y, gy.float())
+    eng.run_backward(tape)
+    torch.cuda.synchronize()
+    rgx, rgw = conv_reference_grads(x, mod.weight.to(dtype), gy, (1, 1, 1), [1, 1, 1], False)
+    e_w = _rel_err(tape.param_grads[id(mod.weight)], rgw)
+    assert e_w <= 2e-3, "weight gradient: %.3e of max|ref|" % e_w
+    g = tape.grad_feat(xf)[0].planar                    # [2, B, D, H, W, 32]
+    gx = torch.cat((g[0][..., :split], g[1][..., :cin - split]), dim=-1).permute(0, 4, 1, 2, 3)
+    e_d = _rel_err(gx, rgx)
+    assert e_d <= 2.5 * ULP[dtype], "data gradient: %.3e of max|ref|" % e_d
+    # the halves are ordinary compact features for everything else: same gradient buffer, keyed by the planar tensor
+    gh, have = tape.grad_feat(Feat(base[1], 0, cin - split, 32, planar=base, half=1))
+    assert have and gh.buf.data_ptr() == g[1].data_ptr()
