@@ -79,7 +79,9 @@ __device__ __forceinline__ uint32_t ln_kmajor_hi(uint32_t row_bytes, uint32_t sb
 // thread that holds g = d(loss)/d(activation) of a voxel also reads the 16 raw conv outputs y of that voxel and accumulates
 // sum dv, sum dv * xhat per (b, channel) exactly like the forward statistics (fixed order inside the CTA, fp64 atomics
 // across CTAs) -- the separate pass over g and y (mtb200_in_bwd_reduce, 4 B per element) disappears.
-template <typename T, int ROWB, int EW, bool RED>
+// NCH = channel chunks per line (compile time: the MMA issue loop must stay a straight run of instructions): 1, or 2 for
+// planar input halves.
+template <typename T, int ROWB, int EW, bool RED, int NCH>
 __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const __grid_constant__ LineParams p) {
   constexpr int LN_CPT = 32 / (EW / 4);  // output channels per epilogue thread
   extern __shared__ uint8_t dsmem_raw[];
@@ -176,7 +178,6 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
     const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, line16 = (uint32_t)p.line_bytes >> 4;
     const uint32_t wgroup16 = (uint32_t)p.wgroup_bytes >> 4;
     const uint32_t sub16 = (uint32_t)p.sub_bytes >> 4, wchunk16 = (uint32_t)p.wchunk_bytes >> 4;
-    const int nchunk = p.nchunk;
     const int ngroups = (p.dbg & 8) ? 1 : p.ngroups;
     // per-group descriptor offsets live in (uniform) registers: the issue loop is a handful of adds per MMA.  The single
     // issuing warp pays the full latency of every dependent instruction, so nothing else may sit between two MMAs.
@@ -203,7 +204,8 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
 #pragma unroll
           for (int g = 0; g < 9; ++g) {
             if (g < ngroups) {
-              for (int c = 0; c < nchunk; ++c) {  // channel chunks (2 for planar halves, else 1)
+#pragma unroll
+              for (int c = 0; c < NCH; ++c) {  // channel chunks (2 for planar halves, else 1)
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k)
                   umma_f16(dq, ln_desc64(hi, a_s + a_goff[g] + (uint32_t)c * sub16 + (uint32_t)(k * 2)),
@@ -381,15 +383,19 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
   }
 }
 
-template <typename T, int ROWB, int EW, bool RED>
+template <typename T, int ROWB, int EW, bool RED, int NCH>
 static cudaError_t launch_line_red(const LineParams& q, dim3 grid, int smem, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(conv_line_umma_kernel<T, ROWB, EW, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) conv_line_umma_kernel<T, ROWB, EW, RED><<<grid, ln_threads(EW), smem, s>>>(q);
+  cudaError_t e = cudaFuncSetAttribute(conv_line_umma_kernel<T, ROWB, EW, RED, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) conv_line_umma_kernel<T, ROWB, EW, RED, NCH><<<grid, ln_threads(EW), smem, s>>>(q);
   return e;
 }
 template <typename T, int ROWB, int EW>
 static cudaError_t launch_line_ew(const LineParams& q, dim3 grid, int smem, cudaStream_t s) {
-  return q.red ? launch_line_red<T, ROWB, EW, true>(q, grid, smem, s) : launch_line_red<T, ROWB, EW, false>(q, grid, smem, s);
+  if (q.nchunk == 2) {  // planar input halves (64-byte rows, forward launches)
+    if (ROWB != 64 || q.red) return cudaErrorInvalidValue;
+    return launch_line_red<T, 64, EW, false, 2>(q, grid, smem, s);
+  }
+  return q.red ? launch_line_red<T, ROWB, EW, true, 1>(q, grid, smem, s) : launch_line_red<T, ROWB, EW, false, 1>(q, grid, smem, s);
 }
 
 // MTB200_LINE_EPI_WARPS=8|16 overrides the epilogue width (experiments); default 8 (measured faster, profiles/r1i_line_epi_ab.txt)
@@ -417,7 +423,7 @@ int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s) {
   if (p.Do != p.Di || p.Ho != p.Hi || p.Wo != p.Wi || p.Dof != p.Do || p.Hof != p.Ho || p.Wof != p.Wo)
     return MTB200_ERR_UNSUPPORTED;
   if (p.Cin != 16 && p.Cin != 32 && p.Cin != 64) return MTB200_ERR_UNSUPPORTED;  // one chunk, or two planar halves
-  if (p.in_split && (p.in_split != 32 || p.Cin != 64 || p.in_coff != 0 || p.Wo < 72)) return MTB200_ERR_UNSUPPORTED;
+  if (p.in_split && (p.in_split != 32 || p.Cin != 64 || p.in_coff != 0 || p.Wo < 72 || p.red)) return MTB200_ERR_UNSUPPORTED;
   if (p.out_split && (p.out_split % LN_BN || p.Cout != 2 * p.out_split || p.out_coff != 0 || p.red)) return MTB200_ERR_UNSUPPORTED;
   if (p.Cout % LN_BN) return MTB200_ERR_UNSUPPORTED;
   // an M tile is one h-line of 128 w voxels, or (narrow maps) two depth planes of one 64-wide h-line

@@ -15,4 +15,5 @@ timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-profile --no-e2e --no-infer --no-gpu-reference > /dev/null 2> gpurun_out/ncu_full_${TAG}.err
 python tools/ncu_summary.py full gpurun_out/prof_${TAG}.ncu-rep > gpurun_out/ncu_full_${TAG}.txt 2>&1
 cat gpurun_out/ncu_full_${TAG}.txt
+rm -f gpurun_out/prof_${TAG}.ncu-rep   # the summaries are what gets committed; the report would overflow the 64 MiB return path
 python tools/show_bench.py gpurun_out/bench_${TAG}.json | head -70
