@@ -26,6 +26,7 @@ using namespace um;
 
 constexpr int HB_THREADS = 192;
 constexpr int HB_STAGES = 4;
+constexpr int HF_STAGES = 8;  // forward statistics kernel: its only HBM stream is the input tile -- keep 8 x 2 CTAs in flight per SM
 constexpr int HB_WIN = 16;
 constexpr int HB_MAX_LABELS = 64;
 
@@ -391,8 +392,9 @@ __global__ void __launch_bounds__(HB_THREADS, 2) head_fwd_stats_kernel(const __g
   constexpr int ACT_BYTES = 128 * ROWB;
   constexpr int NCH = ROWB / 16;
   constexpr int NQ = HARD ? 6 : 4;
+  constexpr int NST = CIN == 32 ? HF_STAGES : 6;  // 64-channel inputs: 6 x 16 KB so that two CTAs still share an SM
   extern __shared__ uint8_t dsmem_raw[];
-  __shared__ __align__(8) uint64_t act_full[HB_STAGES], act_empty[HB_STAGES], z_full[2], z_empty[2];
+  __shared__ __align__(8) uint64_t act_full[HF_STAGES], act_empty[HF_STAGES], z_full[2], z_empty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ uint64_t s_pos[HB_MAX_LABELS];
   __shared__ float s_part[4][NQ * HB_WIN];
@@ -400,7 +402,7 @@ __global__ void __launch_bounds__(HB_THREADS, 2) head_fwd_stats_kernel(const __g
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* act_base = dsmem;
-  uint8_t* w0_base = act_base + HB_STAGES * ACT_BYTES;
+  uint8_t* w0_base = act_base + NST * ACT_BYTES;
   const int b = (int)blockIdx.x / p.cps, slot = (int)blockIdx.x % p.cps;
   const int c0 = p.win_c0[b];
   const long long ntiles = p.tiles_per_b;
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(HB_THREADS, 2) head_fwd_stats_kernel(const __g
   const unsigned vbits = (unsigned)((p.valid_mask[b] >> c0) & 0xffffull);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < HB_STAGES; ++i) { mbar_init(&act_full[i], 1); mbar_init(&act_empty[i], 1); }
+    for (int i = 0; i < NST; ++i) { mbar_init(&act_full[i], 1); mbar_init(&act_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -430,8 +432,8 @@ __global__ void __launch_bounds__(HB_THREADS, 2) head_fwd_stats_kernel(const __g
   if (warp == 0) {
     uint32_t i = 0;
     for (long long t = slot; t < ntiles; t += p.cps, ++i) {
-      const uint32_t stage = i % HB_STAGES;
-      mbar_wait(&act_empty[stage], ((i / HB_STAGES) & 1u) ^ 1u);
+      const uint32_t stage = i % NST;
+      mbar_wait(&act_empty[stage], ((i / NST) & 1u) ^ 1u);
       if (elect_one()) {
         mbar_expect_tx(&act_full[stage], (uint32_t)ACT_BYTES);
         hb_tma_load_2d(act_base + (size_t)stage * ACT_BYTES, &p.x_map, &act_full[stage], 0,
@@ -447,8 +449,8 @@ __global__ void __launch_bounds__(HB_THREADS, 2) head_fwd_stats_kernel(const __g
     const uint32_t w0_16 = __shfl_sync(0xffffffffu, (smem_u32(w0_base) & 0x3FFFFu) >> 4, 0);
     uint32_t i = 0;
     for (long long t = slot; t < ntiles; t += p.cps, ++i) {
-      const uint32_t buf = i & 1u, stage = i % HB_STAGES;
-      mbar_wait(&act_full[stage], (i / HB_STAGES) & 1u);
+      const uint32_t buf = i & 1u, stage = i % NST;
+      mbar_wait(&act_full[stage], (i / NST) & 1u);
       mbar_wait(&z_empty[buf], ((i >> 1) & 1u) ^ 1u);
       tc_fence_after();
       if (elect_one()) {
@@ -635,7 +637,7 @@ int head_fwd_stats(const mtb200_head_fwd_params& p, cudaStream_t s) {
   if (cps > q.tiles_per_b) cps = q.tiles_per_b;
   q.cps = (int)cps;
   const int rowb = p.Cin * 2;
-  const int smem = HB_STAGES * 128 * rowb + HB_WIN * rowb + 2048;
+  const int smem = (p.Cin == 32 ? HF_STAGES : 6) * 128 * rowb + HB_WIN * rowb + 2048;
   dim3 grid((unsigned)(q.cps * p.B));
   cudaError_t e = cudaSuccess;
 #define HF_LAUNCH2(T, CIN, HARD)                                                                                     \
