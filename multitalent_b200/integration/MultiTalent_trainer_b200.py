@@ -56,7 +56,8 @@ class MultiTalent_trainer_ddp_b200(MultiTalent_trainer_ddp):
         self.network.inference_apply_nonlin = nn.Sigmoid()
 
     def compute_loss(self, output, target, valid_regions):   # replaces MT:544-623
-        return multitalent_loss(output, target, valid_regions, self.ds_loss_weights)
+        return multitalent_loss(output, target, valid_regions, self.ds_loss_weights,
+                                engine=getattr(self.network, "_engine", None))
 
 
 class MultiTalent_trainer_resenc_ddp_b200(MultiTalent_trainer_resenc_ddp):
@@ -73,7 +74,8 @@ class MultiTalent_trainer_resenc_ddp_b200(MultiTalent_trainer_resenc_ddp):
         self.network.inference_apply_nonlin = nn.Sigmoid()
 
     def compute_loss(self, output, target, valid_regions):   # replaces MultiTalent_meets_resenc.py:713-798
-        return multitalent_loss(output, target, valid_regions, self.ds_loss_weights)
+        return multitalent_loss(output, target, valid_regions, self.ds_loss_weights,
+                                engine=getattr(self.network, "_engine", None))
 
 
 # BASELINE.json's name for the MultiTalent trainer
