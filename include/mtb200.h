@@ -261,6 +261,23 @@ typedef struct {
   int32_t win_c0[MTB200_MAX_HEAD_BATCH];
 } mtb200_head_fwd_params;
 int mtb200_head_fwd_stats(const mtb200_head_fwd_params* p, void* stream);
+/* Inference (a5 + a14/a15): head -> non-linearity -> x weight x Gaussian -> scatter-add of ONE tile into the sliding-window
+ * accumulators, the logits never stored (generic_UNet.py:349-351 + neural_network.py:374-394, 531-589):
+ *   z[v][c] = round_dtype(bias[c] + sum_ci W[c][ci] x[v][ci]);  f = sigmoid (nonlin 1) / softmax over the C classes (2) / id (0)
+ *   acc[c][x0 + d][y0 + h][z0 + w] += weight * gauss[d][h][w] * f(z)[src(d, h, w)][c],   src = the flipped voxel (`flip` bits
+ *   0 / 1 / 2 = w / h / d) of the tile that went through the network;  nb[...] += gauss[d][h][w]  (nb may be NULL).
+ * Tiles of consecutive launches may overlap (stream order).  16-bit, Cin (padded) 32 or 64, at most 48 padded classes. */
+typedef struct {
+  const void* x;          /* head input of the tile [pd][ph][pw][x_ldc], channels x_coff .. x_coff + Cin */
+  const void* w_fwd;      /* [Cout][Cin], dtype */
+  const float* bias;      /* [Cout] or NULL */
+  const float* gauss;     /* [pd][ph][pw] or NULL */
+  float* acc;             /* [C][X][Y][Z] */
+  float* nb;              /* [X][Y][Z] or NULL */
+  float weight;
+  int32_t dtype, x_ldc, x_coff, Cin, Cout, C, pd, ph, pw, flip, nonlin, X, Y, Z, x0, y0, z0;
+} mtb200_head_agg_params;
+int mtb200_head_aggregate(const mtb200_head_agg_params* p, void* stream);
 
 /* ---- a14/a15/a16: sliding-window predictor; replaces neural_network.py:374-394 (tile loop + host numpy accumulate),
  *      :531-589 (mirror TTA), :405 (normalise), :415-417 (threshold) ------------------------------------------------ */

@@ -116,6 +116,17 @@ class HeadFwdParams(C.Structure):
     ]
 
 
+class HeadAggParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("w_fwd", C.c_void_p), ("bias", C.c_void_p), ("gauss", C.c_void_p), ("acc", C.c_void_p),
+        ("nb", C.c_void_p), ("weight", C.c_float),
+        ("dtype", C.c_int32), ("x_ldc", C.c_int32), ("x_coff", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
+        ("C", C.c_int32), ("pd", C.c_int32), ("ph", C.c_int32), ("pw", C.c_int32), ("flip", C.c_int32),
+        ("nonlin", C.c_int32), ("X", C.c_int32), ("Y", C.c_int32), ("Z", C.c_int32), ("x0", C.c_int32),
+        ("y0", C.c_int32), ("z0", C.c_int32),
+    ]
+
+
 UNPACK_CHUNK = 4096
 _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
@@ -146,6 +157,7 @@ SIGNATURES = {
     "mtb200_mt_loss_bwd": [_vp, _i32, _i32, _i32, _vp, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _vp],
     "mtb200_head_bwd_fused": [C.POINTER(HeadBwdParams), _vp],
     "mtb200_head_fwd_stats": [C.POINTER(HeadFwdParams), _vp],
+    "mtb200_head_aggregate": [C.POINTER(HeadAggParams), _vp],
     "mtb200_sw_gather_tile": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32,
                               _vp],
     "mtb200_sw_aggregate": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _f32, _i32, _vp, _vp, _i32, _i32, _i32,

@@ -74,6 +74,7 @@ int mt_loss_bwd(const void*, int, int, int, const float*, int, long long, const 
                 const float*, void*, int, cudaStream_t);
 int head_bwd_fused(const mtb200_head_bwd_params& p, cudaStream_t s);  // head_bwd.cu
 int head_fwd_stats(const mtb200_head_fwd_params& p, cudaStream_t s);  // head_bwd.cu
+int head_aggregate(const mtb200_head_agg_params& p, cudaStream_t s);  // head_bwd.cu
 int sw_gather_tile(const float*, int, int, int, int, int, int, int, int, int, int, int, void*, int, int, cudaStream_t);
 int sw_aggregate(const void*, int, int, int, int, int, int, int, const float*, float, int, float*, float*, int, int, int,
                  int, int, int, cudaStream_t);
@@ -259,6 +260,10 @@ int mtb200_head_bwd_fused(const mtb200_head_bwd_params* p, void* stream) {
   MTB_REQUIRE(p && (p->logits || p->w_fwd) && p->target && p->coef && p->pos_mask && p->x && p->w_swap && p->dx && p->dw,
               "head_bwd_fused: null pointer");
   return head_bwd_fused(*p, (cudaStream_t)stream);
+}
+int mtb200_head_aggregate(const mtb200_head_agg_params* p, void* stream) {
+  MTB_REQUIRE(p && p->x && p->w_fwd && p->acc, "head_aggregate: null pointer");
+  return head_aggregate(*p, (cudaStream_t)stream);
 }
 int mtb200_head_fwd_stats(const mtb200_head_fwd_params* p, void* stream) {
   MTB_REQUIRE(p && p->x && p->w_fwd && p->target && p->valid_mask && p->pos_mask && p->stats, "head_fwd_stats: null pointer");

@@ -541,6 +541,165 @@ __global__ void __launch_bounds__(HB_THREADS, 2) head_fwd_stats_kernel(const __g
   }
 }
 
+// ---- inference: head -> non-linearity x Gaussian weight -> scatter-add into the sliding-window accumulators ------------------
+// (generic_UNet.py:349-351 + neural_network.py:374-394, 531-589.)  The logits of a tile never reach memory: MMA (N = padded
+// class count) -> TMEM -> one thread per SOURCE voxel: + bias, round to the storage type (the values the stored logits had),
+// sigmoid / softmax / identity, x weight x gauss[destination voxel], read-modify-write of the C channel-first accumulators at
+// the un-flipped destination (a warp covers 32 consecutive w voxels: 128-byte rows per class).  One launch per tile, tiles
+// in stream order (overlapping tiles must not race; the reference accumulates in tile order too).
+constexpr int HA_STAGES = 6;
+struct HeadAggParams {
+  CUtensorMap x_map;
+  const void* w_fwd;      // [Cout_p][Cin]
+  const float* bias;      // [Cout_p] or null
+  const float* gauss;     // [pd][ph][pw] or null
+  float* acc;             // [C][X][Y][Z]
+  float* nb;              // [X][Y][Z] or null
+  float weight;
+  int C, Cout_p, pd, ph, pw, flip, nonlin, X, Y, Z, x0, y0, z0, ntiles, is_f16;
+  long long nvox;
+};
+
+template <typename T, int CIN>
+__global__ void __launch_bounds__(HB_THREADS, 2) head_aggregate_kernel(const __grid_constant__ HeadAggParams p) {
+  constexpr int ROWB = CIN * 2;
+  constexpr int ACT_BYTES = 128 * ROWB;
+  constexpr int NCH = ROWB / 16;
+  constexpr int NP = 48;  // padded class count (TMEM columns per accumulator)
+  extern __shared__ uint8_t dsmem_raw[];
+  __shared__ __align__(8) uint64_t act_full[HA_STAGES], act_empty[HA_STAGES], z_full[2], z_empty[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_bias[NP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* act_base = dsmem;
+  uint8_t* w_base = act_base + HA_STAGES * ACT_BYTES;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < HA_STAGES; ++i) { mbar_init(&act_full[i], 1); mbar_init(&act_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < NP) s_bias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.Cout_p) ? p.bias[threadIdx.x] : 0.f;
+  for (int idx = threadIdx.x; idx < NP * NCH; idx += HB_THREADS) {
+    const int row = idx / NCH, piece = idx % NCH;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row < p.Cout_p)
+      v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.w_fwd) + (long long)row * CIN + piece * 8);
+    const int sw = NCH == 4 ? (piece ^ ((row >> 1) & 3)) : (piece ^ (row & 7));
+    *reinterpret_cast<uint4*>(w_base + row * ROWB + sw * 16) = v;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 1) tmem_alloc(&tmem_slot, 128u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    uint32_t i = 0;
+    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++i) {
+      const uint32_t stage = i % HA_STAGES;
+      mbar_wait(&act_empty[stage], ((i / HA_STAGES) & 1u) ^ 1u);
+      if (elect_one()) {
+        mbar_expect_tx(&act_full[stage], (uint32_t)ACT_BYTES);
+        hb_tma_load_2d(act_base + (size_t)stage * ACT_BYTES, &p.x_map, &act_full[stage], 0, t * 128);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t idesc0 = idesc_f16(p.is_f16 != 0, (uint32_t)NP, false, false);
+    const uint32_t hi_k = ((8u * ROWB) >> 4) | (1u << 14) | ((ROWB == 128 ? 2u : 4u) << 29);
+    const uint32_t act16 = __shfl_sync(0xffffffffu, (smem_u32(act_base) & 0x3FFFFu) >> 4, 0);
+    const uint32_t w16 = __shfl_sync(0xffffffffu, (smem_u32(w_base) & 0x3FFFFu) >> 4, 0);
+    uint32_t i = 0;
+    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++i) {
+      const uint32_t buf = i & 1u, stage = i % HA_STAGES;
+      mbar_wait(&act_full[stage], (i / HA_STAGES) & 1u);
+      mbar_wait(&z_empty[buf], ((i >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t x_t = act16 + stage * ((uint32_t)ACT_BYTES >> 4);
+#pragma unroll
+        for (int ks = 0; ks < CIN / 16; ++ks)
+          umma_f16(tmem_u + buf * 64u, hb_desc64(hi_k, x_t + 2u * ks), hb_desc64(hi_k, w16 + 2u * ks), idesc0, ks ? 1u : 0u);
+        umma_commit(&z_full[buf]);
+        umma_commit(&act_empty[stage]);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const long long plane = (long long)p.Y * p.Z, cstride = (long long)p.X * plane;
+    uint32_t i = 0;
+    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++i) {
+      const uint32_t buf = i & 1u;
+      // source voxel of this thread and its un-flipped destination
+      const long long v = (long long)t * 128 + m;
+      const bool inside = v < p.nvox;
+      const int sw_ = (int)(v % p.pw);
+      const int rem = (int)(v / p.pw);
+      const int sh_ = rem % p.ph, sd_ = rem / p.ph;
+      const int d = (p.flip & 4) ? p.pd - 1 - sd_ : sd_, h = (p.flip & 2) ? p.ph - 1 - sh_ : sh_;
+      const int w = (p.flip & 1) ? p.pw - 1 - sw_ : sw_;
+      float gw = p.weight;
+      if (inside && p.gauss) gw *= __ldg(p.gauss + ((long long)d * p.ph + h) * p.pw + w);
+      uint32_t r[3][16];
+      mbar_wait(&z_full[buf], (i >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 64u;
+      tmem_ld16_async(tl, r[0]);
+      tmem_ld16_async(tl + 16u, r[1]);
+      tmem_ld16_async(tl + 32u, r[2]);
+      tmem_ld_fence(r[0]); tmem_ld_fence(r[1]); tmem_ld_fence(r[2]);
+      tc_fence_before();
+      mbar_arrive(&z_empty[buf]);
+      if (!inside) continue;
+      float val[NP];
+#pragma unroll
+      for (int c = 0; c < NP; ++c) val[c] = Traits<T>::round(__uint_as_float(r[c >> 4][c & 15]) + s_bias[c]);
+      if (p.nonlin == 1) {
+#pragma unroll
+        for (int c = 0; c < NP; ++c) {
+          const float e = expf(-fabsf(val[c]));
+          val[c] = (val[c] >= 0.f ? 1.f / (1.f + e) : e / (1.f + e)) * gw;
+        }
+      } else if (p.nonlin == 2) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < NP; ++c) if (c < p.C) mx = fmaxf(mx, val[c]);
+        float ssum = 0.f;
+#pragma unroll
+        for (int c = 0; c < NP; ++c) { val[c] = c < p.C ? expf(val[c] - mx) : 0.f; ssum += val[c]; }
+        const float g2 = gw / ssum;
+#pragma unroll
+        for (int c = 0; c < NP; ++c) val[c] *= g2;
+      } else {
+#pragma unroll
+        for (int c = 0; c < NP; ++c) val[c] *= gw;
+      }
+      float* dst = p.acc + ((long long)(p.x0 + d) * p.Y + (p.y0 + h)) * p.Z + p.z0 + w;
+      // fire-and-forget reductions (RED.ADD.F32): the tiles of one launch never overlap and launches are stream ordered, so
+      // every location receives exactly one add per launch -- the same sums as a read-modify-write, without holding a
+      // register per outstanding load (47 classes x 128 threads in flight per CTA)
+#pragma unroll
+      for (int c = 0; c < NP; ++c)
+        if (c < p.C) atomicAdd(dst + (long long)c * cstride, val[c]);
+      if (p.nb) {
+        float* nbp = p.nb + ((long long)(p.x0 + d) * p.Y + (p.y0 + h)) * p.Z + p.z0 + w;
+        atomicAdd(nbp, p.gauss ? __ldg(p.gauss + ((long long)d * p.ph + h) * p.pw + w) : 1.f);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128u);
+  }
+}
+
 int umma_available();
 
 int head_bwd_fused(const mtb200_head_bwd_params& p, cudaStream_t s) {
@@ -658,6 +817,48 @@ int head_fwd_stats(const mtb200_head_fwd_params& p, cudaStream_t s) {
 #undef HF_LAUNCH2
   if (e != cudaSuccess) { set_error("head_fwd_stats: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
   return check_launch("head_fwd_stats");
+}
+
+int head_aggregate(const mtb200_head_agg_params& p, cudaStream_t s) {
+  if (!umma_available()) { set_error("head_aggregate: no sm_100 device / driver entry point"); return MTB200_ERR_UNSUPPORTED; }
+  if (p.dtype != MTB200_BF16 && p.dtype != MTB200_F16) { set_error("head_aggregate: 16-bit tensors only"); return MTB200_ERR_UNSUPPORTED; }
+  if (p.Cin != 32 && p.Cin != 64) { set_error("head_aggregate: Cin %d (32 or 64)", p.Cin); return MTB200_ERR_UNSUPPORTED; }
+  if (p.Cout > 48 || p.Cout % 8 || p.C > p.Cout) { set_error("head_aggregate: %d classes (padded %d; at most 48)", p.C, p.Cout); return MTB200_ERR_UNSUPPORTED; }
+  MTB_REQUIRE(p.x_ldc % 8 == 0 && p.x_coff % 8 == 0, "head_aggregate: alignment");
+  MTB_REQUIRE(p.x0 >= 0 && p.y0 >= 0 && p.z0 >= 0 && p.x0 + p.pd <= p.X && p.y0 + p.ph <= p.Y && p.z0 + p.pw <= p.Z,
+              "head_aggregate: tile outside the volume");
+  const long long nvox = (long long)p.pd * p.ph * p.pw;
+  MTB_REQUIRE(nvox > 0 && nvox < (1LL << 31), "head_aggregate: %lld voxels", nvox);
+  static thread_local HeadAggParams q;
+  memset(&q, 0, sizeof(q));
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)p.Cin, (cuuint64_t)nvox};
+    cuuint64_t strides[1] = {(cuuint64_t)p.x_ldc * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.Cin, 128};
+    if (!umma_encode_map(&q.x_map, p.dtype, 2, (uint8_t*)p.x + (size_t)p.x_coff * 2, dims, strides, box, p.Cin * 2))
+      return MTB200_ERR_CUDA;
+  }
+  q.w_fwd = p.w_fwd; q.bias = p.bias; q.gauss = p.gauss; q.acc = p.acc; q.nb = p.nb; q.weight = p.weight;
+  q.C = p.C; q.Cout_p = p.Cout; q.pd = p.pd; q.ph = p.ph; q.pw = p.pw; q.flip = p.flip; q.nonlin = p.nonlin;
+  q.X = p.X; q.Y = p.Y; q.Z = p.Z; q.x0 = p.x0; q.y0 = p.y0; q.z0 = p.z0;
+  q.nvox = nvox; q.ntiles = (int)((nvox + 127) / 128); q.is_f16 = p.dtype == MTB200_F16;
+  const int rowb = p.Cin * 2;
+  const int smem = HA_STAGES * 128 * rowb + 48 * rowb + 2048;
+  const int gx = min(q.ntiles, 2 * num_sms());
+  cudaError_t e = cudaSuccess;
+#define HA_LAUNCH(T, CIN)                                                                                          \
+  do {                                                                                                             \
+    e = cudaFuncSetAttribute(head_aggregate_kernel<T, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);    \
+    if (e == cudaSuccess) head_aggregate_kernel<T, CIN><<<gx, HB_THREADS, smem, s>>>(q);                           \
+  } while (0)
+  if (p.dtype == MTB200_BF16) {
+    if (p.Cin == 32) HA_LAUNCH(__nv_bfloat16, 32); else HA_LAUNCH(__nv_bfloat16, 64);
+  } else {
+    if (p.Cin == 32) HA_LAUNCH(__half, 32); else HA_LAUNCH(__half, 64);
+  }
+#undef HA_LAUNCH
+  if (e != cudaSuccess) { set_error("head_aggregate: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
+  return check_launch("head_aggregate");
 }
 
 }  // namespace mtb

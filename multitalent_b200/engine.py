@@ -448,6 +448,11 @@ class Engine:
         self.defer_head_fwd = os.environ.get("MTB200_DEFER_HEAD", "1") != "0"
         self.defer_heads = False
         self.deferred = {}       # placeholder pointer -> {"x": head input, "op": head}
+        # Inference: the sliding-window predictor asks for the head's INPUT instead of the logits (`capture_head`) and runs
+        # head -> sigmoid x Gaussian -> scatter-add as one kernel per tile (mtb200_head_aggregate)
+        self.fuse_head_aggregate = os.environ.get("MTB200_FUSE_HEAD_AGG", "1") != "0"
+        self.capture_head = False
+        self.captured_head = None
         self.wgrad_order = int(os.environ.get("MTB200_WGRAD_ORDER", "0"))
         self.bwd_priority = os.environ.get("MTB200_BWD_PRIO", "0") != "0"
         self._hp = {}
@@ -834,6 +839,11 @@ class Engine:
         fusable = (head and tape is not None and self.fuse_head and need_input_grad and op.bias is None and op.ntap == 1
                    and not op.transposed and op.Cin_p in (32, 64) and self.materialize_inputs and out is None
                    and x.dims[0] <= L.MAX_HEAD_BATCH)
+        if (head and tape is None and self.capture_head and op.ntap == 1 and not op.transposed and op.Cin_p in (32, 64)
+                and op.Cout_p <= 48 and self.materialize_inputs and out is None):
+            self.captured_head = (self.operand(x), op)  # the predictor consumes the head's input itself
+            ph = torch.zeros(8, dtype=self.dtype, device=x.buf.device)[:1].expand(tuple(x.dims) + (op.Cout_p,))
+            return Feat(ph, 0, op.Cout, op.Cout_p)
         deferred = fusable and self.defer_heads
         if deferred:
             # not computed: a zero-stride placeholder of the logits' shape stands in (its one-element storage is the key)

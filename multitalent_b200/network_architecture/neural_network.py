@@ -18,6 +18,7 @@ import numpy as np
 import torch
 from torch import nn
 
+import ctypes
 from ctypes import c_void_p as C_void
 
 from .. import _lib as L
@@ -248,7 +249,39 @@ class SegmentationNetwork(NeuralNetwork):
             for b, (sx, sy, sz, mi, dims) in enumerate(chunk):
                 L.call("mtb200_sw_gather_tile", L.ptr(vol), Cin, X, Y, Z, sx, sy, sz, pd, ph, pw, _flip_bits(dims),
                        C_void(tile.data_ptr() + b * tile_elems * esize), L.dtype_enum(dt), cin_p, st)
-            logits = self.native_logits(Feat(tile[:len(chunk)], 0, Cin, cin_p))
+            eng = getattr(self, "_engine", None)
+            fuse = eng is not None and getattr(eng, "fuse_head_aggregate", False) and dt != torch.float32
+            if fuse:  # ask the network for the head's input: head -> non-linearity x Gaussian -> scatter-add is ONE kernel
+                eng.capture_head, eng.captured_head = True, None
+            try:
+                logits = self.native_logits(Feat(tile[:len(chunk)], 0, Cin, cin_p))
+            finally:
+                if fuse:
+                    eng.capture_head = False
+            cap = eng.captured_head if fuse else None
+            if cap is not None:
+                hx, hop = cap
+                eng.captured_head = None
+                assert hop.Cout == C and tuple(hx.dims[1:]) == (pd, ph, pw)
+                hp = L.HeadAggParams()
+                hp.w_fwd = hop.packed(eng.wdtype, False).data_ptr()
+                bias = None
+                if hop.bias is not None:
+                    bias = torch.zeros(hop.Cout_p, dtype=torch.float32, device=dev)
+                    bias[:hop.Cout] = hop.bias.detach().float()
+                hp.bias = bias.data_ptr() if bias is not None else None
+                hp.gauss = gauss.data_ptr() if gauss is not None else None
+                hp.acc, hp.weight = acc.data_ptr(), 1.0 / n_results
+                hp.dtype, hp.x_ldc, hp.x_coff, hp.Cin, hp.Cout, hp.C = L.dtype_enum(dt), hx.ldc, hx.coff, hop.Cin_p, hop.Cout_p, C
+                hp.pd, hp.ph, hp.pw, hp.nonlin = pd, ph, pw, nonlin
+                hp.X, hp.Y, hp.Z = X, Y, Z
+                xstride = pd * ph * pw * hx.ldc * esize
+                for b, (sx, sy, sz, mi, dims) in enumerate(chunk):
+                    hp.x = hx.ptr() + b * xstride
+                    hp.nb = nb.data_ptr() if mi == 0 else None
+                    hp.flip, hp.x0, hp.y0, hp.z0 = _flip_bits(dims), sx, sy, sz
+                    L.call("mtb200_head_aggregate", ctypes.byref(hp), st)
+                continue
             lstride = pd * ph * pw * logits.ldc * esize
             for b, (sx, sy, sz, mi, dims) in enumerate(chunk):
                 L.call("mtb200_sw_aggregate", C_void(logits.ptr() + b * lstride), L.dtype_enum(dt), logits.ldc, C, pd, ph,

@@ -44,6 +44,7 @@ def test_struct_layout_matches_header(tmp_path):
               "mtb200_wgrad_params": (L.WgradParams, ["x", "xform", "dtype", "Cout", "ntaps", "tap_widx", "impl", "in_split"]),
               "mtb200_head_bwd_params": (L.HeadBwdParams, ["logits", "w_fwd", "dw", "nvox", "dtype", "Cin", "accumulate",
                                                            "win_c0"]),
+              "mtb200_head_agg_params": (L.HeadAggParams, ["x", "nb", "weight", "dtype", "flip", "z0"]),
               "mtb200_head_fwd_params": (L.HeadFwdParams, ["x", "hard", "nvox", "dtype", "Cout", "win_c0"]),
               "mtb200_pack_desc": (L.PackDesc, ["w", "packed_swap", "Cout", "blk_begin"]),
               "mtb200_unpack_desc": (L.UnpackDesc, ["dw", "grad", "Cout", "blk_begin"])}

@@ -268,3 +268,35 @@ def test_training_step_with_deferred_heads():
     ga, gb = res[False][3].double(), res[True][3].double()
     cos = float((ga * gb).sum() / (ga.norm() * gb.norm()))
     assert cos > 0.99999, cos
+
+
+@pytest.mark.parametrize("mirror", [False, True])
+def test_sliding_window_with_fused_head_aggregate(mirror):
+    """predict_3D with head -> sigmoid x Gaussian -> scatter-add as one kernel per tile (mtb200_head_aggregate) against the
+    same predictor with the pointwise head + mtb200_sw_aggregate: the accumulated probabilities agree to fp32 rounding."""
+    from multitalent_b200 import _lib as L
+    from multitalent_b200.plans import default_plans
+    from multitalent_b200.training.network_training.MultiTalent_Trainer_DDP import MultiTalent_trainer_ddp
+    patch = (16, 32, 32)
+    plans = default_plans(patch_size=patch, batch_size=2)
+    plans['plans_per_stage'][1]['pool_op_kernel_sizes'] = [[2, 2, 2], [2, 2, 2], [1, 2, 2]]
+    plans['plans_per_stage'][1]['conv_kernel_sizes'] = [[3, 3, 3]] * 4
+    tr = MultiTalent_trainer_ddp(plans, 0, 0, init_distributed=False, native_dtype=torch.bfloat16)
+    torch.manual_seed(0)
+    tr.initialize(False)
+    net = tr.network
+    net.eval()
+    net.do_ds = False
+    vol = np.random.RandomState(3).randn(1, 24, 40, 56).astype(np.float32)
+    kw = dict(do_mirroring=mirror, mirror_axes=(0, 1, 2), use_sliding_window=True, step_size=0.5, patch_size=patch,
+              regions_class_order=tuple(range(47)), use_gaussian=True, verbose=False, return_device_tensors=True)
+    res = {}
+    for fuse in (False, True):
+        net._engine.fuse_head_aggregate = fuse
+        with L.KernelProfile() as kp:
+            seg, prob = net.predict_3D(vol, **kw)
+        names = {r[5] for r in kp.per_launch_kernels()}
+        assert ("head_aggregate" in names) == fuse, names
+        res[fuse] = (seg.clone(), prob.clone())
+    assert float((res[True][1] - res[False][1]).abs().max()) <= 2e-6
+    assert torch.equal(res[True][0], res[False][0])
