@@ -91,6 +91,30 @@ __device__ __forceinline__ void c1_unit(const C1Params& p, uint32_t u, int& b, i
   w0 = (int)tw * 128;
 }
 
+// (b, d, h, w tile) of a work unit, advanced by a FIXED unit stride with carries instead of divisions: the three 32-bit
+// divisions of c1_unit per tile in every builder and epilogue thread were a third of the forward kernel's instructions
+struct C1Walk {
+  int b, d, h, tw;
+  int sb, sd, sh, stw;
+  __device__ __forceinline__ void init(const C1Params& p, uint32_t u, uint32_t stride) {
+    int w0;
+    c1_unit(p, u, b, d, h, w0);
+    tw = w0 >> 7;
+    const uint32_t ntw = (uint32_t)p.ntw, H = (uint32_t)p.H, D = (uint32_t)p.D;
+    stw = (int)(stride % ntw);
+    uint32_t r = stride / ntw;
+    sh = (int)(r % H); r /= H;
+    sd = (int)(r % D);
+    sb = (int)(r / D);
+  }
+  __device__ __forceinline__ void next(const C1Params& p) {
+    tw += stw; h += sh; d += sd; b += sb;
+    if (tw >= p.ntw) { tw -= p.ntw; ++h; }
+    if (h >= p.H) { h -= p.H; ++d; }
+    if (d >= p.D) { d -= p.D; ++b; }
+  }
+};
+
 __device__ __forceinline__ void tma_load_3d_tile(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   tma_load_3d(dst, map, bar, c0, c1, c2);
 }
@@ -187,9 +211,8 @@ __global__ void __launch_bounds__(C1_FWD_THREADS, 1) conv_c1_fwd_kernel(const __
     const uint16_t* xv = reinterpret_cast<const uint16_t*>(p.x);
     const long long sh = p.W, sd = (long long)p.H * p.W;
     // the nine line values of tile row r (voxel column w0 - 1 + r) of work unit u
-    auto fetch = [&](uint32_t u, int r, uint32_t (&v)[9]) {
-      int b, d, h, w0;
-      c1_unit(p, u, b, d, h, w0);
+    auto fetch = [&](const C1Walk& k, int r, uint32_t (&v)[9]) {
+      const int b = k.b, d = k.d, h = k.h, w0 = k.tw * 128;
       const int w = w0 - 1 + r;
       const bool okw = (unsigned)w < (unsigned)p.W;
       const uint16_t* plane = xv + (((long long)b * p.D + d) * p.H + h) * p.W;
@@ -213,16 +236,19 @@ __global__ void __launch_bounds__(C1_FWD_THREADS, 1) conv_c1_fwd_kernel(const __
     uint32_t va[9], vb[9], na[9], nb[9];
     const uint32_t ustep = NG * gridDim.x;
     uint32_t u = blockIdx.x + grp * gridDim.x;
+    C1Walk wk;
+    wk.init(p, u < p.units ? u : 0u, ustep);
     if (u < p.units) {
-      fetch(u, r0, na);
-      if (r0 < 2) fetch(u, r0 + 128, nb);
+      fetch(wk, r0, na);
+      if (r0 < 2) fetch(wk, r0 + 128, nb);
     }
     for (uint32_t gi = grp; u < p.units; gi += NG, u += ustep) {
 #pragma unroll
       for (int k = 0; k < 9; ++k) { va[k] = na[k]; vb[k] = nb[k]; }
       if (u + ustep < p.units) {
-        fetch(u + ustep, r0, na);
-        if (r0 < 2) fetch(u + ustep, r0 + 128, nb);
+        wk.next(p);
+        fetch(wk, r0, na);
+        if (r0 < 2) fetch(wk, r0 + 128, nb);
       }
       const uint32_t stage = gi % C1_FWD_STAGES;
       mbar_wait(&empty_bar[stage], ((gi / C1_FWD_STAGES) & 1u) ^ 1u);
@@ -318,9 +344,16 @@ __global__ void __launch_bounds__(C1_FWD_THREADS, 1) conv_c1_fwd_kernel(const __
       }
     };
     int cur_b = -1;
+    C1Walk wk;
+    {
+      const uint32_t u0 = blockIdx.x + (uint32_t)eg * gridDim.x;
+      wk.init(p, u0 < p.units ? u0 : 0u, 2 * gridDim.x);
+    }
+    bool first_tile = true;
     for (uint32_t gi = (uint32_t)eg, u = blockIdx.x + (uint32_t)eg * gridDim.x; u < p.units; gi += 2, u += 2 * gridDim.x) {
-      int b, d, h, w0;
-      c1_unit(p, u, b, d, h, w0);
+      if (!first_tile) wk.next(p);
+      first_tile = false;
+      const int b = wk.b, d = wk.d, h = wk.h, w0 = wk.tw * 128;
       if (want_stats && b != cur_b) {
         if (cur_b >= 0) flush(cur_b);
         cur_b = b;
