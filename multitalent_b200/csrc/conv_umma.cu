@@ -159,11 +159,11 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
     if (niter > 0) {
       uint32_t gi = 0;  // global pipeline iteration of this CTA
       for (long long tile = tile0; tile < p.ntiles; tile += p.ctas_per_combo) {
-        long long t = tile;
-        const int tw = (int)(t % p.tiles_w); t /= p.tiles_w;
-        const int th = (int)(t % p.tiles_h); t /= p.tiles_h;
-        const int td = (int)(t % p.tiles_d);
-        const int b = (int)(t / p.tiles_d);
+        uint32_t t = (uint32_t)tile;  // ntiles < 2^31 (host check): 32-bit divisions, a fifth of the 64-bit ones' instructions
+        const int tw = (int)(t % (uint32_t)p.tiles_w); t /= (uint32_t)p.tiles_w;
+        const int th = (int)(t % (uint32_t)p.tiles_h); t /= (uint32_t)p.tiles_h;
+        const int td = (int)(t % (uint32_t)p.tiles_d);
+        const int b = (int)(t / (uint32_t)p.tiles_d);
         const int d0 = td * p.bd, h0 = th * p.bh, w0 = tw * p.bw;
         int tp = tap_begin, kc = 0;
         for (int it = 0; it < niter; ++it, ++gi) {
@@ -225,11 +225,11 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
     const bool want_stats = p.stats != nullptr;
     uint32_t k = 0;
     for (long long tile = tile0; tile < p.ntiles; tile += p.ctas_per_combo, ++k) {
-      long long t = tile;
-      const int tw = (int)(t % p.tiles_w); t /= p.tiles_w;
-      const int th = (int)(t % p.tiles_h); t /= p.tiles_h;
-      const int td = (int)(t % p.tiles_d);
-      const int b = (int)(t / p.tiles_d);
+      uint32_t t = (uint32_t)tile;
+      const int tw = (int)(t % (uint32_t)p.tiles_w); t /= (uint32_t)p.tiles_w;
+      const int th = (int)(t % (uint32_t)p.tiles_h); t /= (uint32_t)p.tiles_h;
+      const int td = (int)(t % (uint32_t)p.tiles_d);
+      const int b = (int)(t / (uint32_t)p.tiles_d);
       const int od = td * p.bd + rd, oh = th * p.bh + rh, ow = tw * p.bw + rw;
       const bool valid = od < p.Do && oh < p.Ho && ow < p.Wo;
       const long long ovox = (((long long)b * p.Dof + (od * p.os[0] + p.group_ooff[g][0])) * p.Hof +
@@ -585,11 +585,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) wgrad_taps_umma_kernel(const __
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (long long br = brick0; br < brick1; ++br) {
-        long long t = br;
-        const int tw = (int)(t % p.tiles_w); t /= p.tiles_w;
-        const int th = (int)(t % p.tiles_h); t /= p.tiles_h;
-        const int td = (int)(t % p.tiles_d);
-        const int b = (int)(t / p.tiles_d);
+        uint32_t t = (uint32_t)br;  // nbricks < 2^31: 32-bit divisions (the 64-bit chain was ~400 instructions per brick)
+        const int tw = (int)(t % (uint32_t)p.tiles_w); t /= (uint32_t)p.tiles_w;
+        const int th = (int)(t % (uint32_t)p.tiles_h); t /= (uint32_t)p.tiles_h;
+        const int td = (int)(t % (uint32_t)p.tiles_d);
+        const int b = (int)(t / (uint32_t)p.tiles_d);
         const int d0 = td * p.bd, h0 = th * p.bh, w0 = tw * p.bw;
         // dY brick (shared by every M-tile of this brick)
         mbar_wait(&b_empty[bs], bph ^ 1u);

@@ -637,11 +637,11 @@ __global__ void __launch_bounds__(HB_THREADS, 2) head_aggregate_kernel(const __g
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++i) {
       const uint32_t buf = i & 1u;
       // source voxel of this thread and its un-flipped destination
-      const long long v = (long long)t * 128 + m;
-      const bool inside = v < p.nvox;
-      const int sw_ = (int)(v % p.pw);
-      const int rem = (int)(v / p.pw);
-      const int sh_ = rem % p.ph, sd_ = rem / p.ph;
+      const uint32_t v = (uint32_t)t * 128u + (uint32_t)m;  // nvox < 2^31 (host check): 32-bit divisions
+      const bool inside = (long long)v < p.nvox;
+      const uint32_t rem = v / (uint32_t)p.pw;
+      const int sw_ = (int)(v - rem * (uint32_t)p.pw);
+      const int sd_ = (int)(rem / (uint32_t)p.ph), sh_ = (int)(rem - (uint32_t)sd_ * (uint32_t)p.ph);
       const int d = (p.flip & 4) ? p.pd - 1 - sd_ : sd_, h = (p.flip & 2) ? p.ph - 1 - sh_ : sh_;
       const int w = (p.flip & 1) ? p.pw - 1 - sw_ : sw_;
       float gw = p.weight;
