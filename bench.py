@@ -514,6 +514,13 @@ def main():
                  (0.5 * pk["bf16_tflops"])})
     for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])[:12]:  # per-CUDA-kernel ms per step (scalars)
         roof["ms_%s" % k] = round(v["ms"] / args.steps, 4)
+    # the HBM-bound passes against the measured copy bandwidth: algorithmic bytes (2 reads + 1 write, 1 + 1, 2 reads of the
+    # 16-bit tensors) / their measured durations
+    for k in ("in_bwd_apply_tma", "norm_act_tma", "in_bwd_reduce_tma"):
+        v = kernels.get(k)
+        if v and v.get("bytes") and v["ms"] > 0:
+            roof["gbs_%s" % k] = round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)
+            roof["hbm_frac_%s" % k] = round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"], 3)
     if cudnn:
         roof.update(cudnn)
         best = max([cudnn.get("cudnn_patches_s") or 0.0, cudnn.get("cudnn_channels_last_patches_s") or 0.0])

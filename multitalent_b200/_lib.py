@@ -232,12 +232,13 @@ class KernelProfile:
         """{CUDA kernel family the library dispatched to (mtb200_last_kernel): {launches, ms, flops}}."""
         torch.cuda.synchronize()
         out = {}
-        for _name, e0, e1, flops, _nb, _info, kern in self.records:
+        for _name, e0, e1, flops, nb, _info, kern in self.records:
             kern = kern.split("+")[0]  # "+red" = the same kernel with the fused reduction epilogue
-            d = out.setdefault(kern, {"launches": 0, "ms": 0.0, "flops": 0.0})
+            d = out.setdefault(kern, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
             d["launches"] += 1
             d["ms"] += e0.elapsed_time(e1)
             d["flops"] += flops
+            d["bytes"] += nb
         return out
 
     def summary(self):

@@ -437,6 +437,7 @@ class MultiTalent_trainer_ddp(OnlineEvaluationMixin, ValidationMixin):
         defer = bool(eng is not None and do_backprop and not keep_output and getattr(eng, "fuse_head", False)
                      and getattr(eng, "defer_head_fwd", False) and not torch.is_tensor(valid_regions)
                      and self.network.training
+                     and type(self).compute_loss is MultiTalent_trainer_ddp.compute_loss  # a custom loss needs real logits
                      and head_windows(valid_regions, (int(getattr(self.network, "num_classes", 0)) + 7) // 8 * 8)
                      is not None)
         with torch.set_grad_enabled(do_backprop):
