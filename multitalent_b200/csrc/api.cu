@@ -1,6 +1,7 @@
 // extern "C" surface of libmtb200.so (see include/mtb200.h).  Thin argument checks + dispatch; no device memory is
 // owned here and nothing throws or aborts across the boundary.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -25,6 +26,11 @@ int check_launch(const char* what) {
     return MTB200_ERR_CUDA;
   }
   return MTB200_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("MTB200_PDL"); return !e || atoi(e) != 0; }();
+  return on;
 }
 
 int num_sms() {

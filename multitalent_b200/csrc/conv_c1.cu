@@ -141,6 +141,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
 // shift of a single-channel line is a 2-byte offset, and bulk tensor copies start on 16-byte boundaries.)
 template <typename T, int NCB, bool LINES>
 __global__ void __launch_bounds__(C1_FWD_THREADS, 1) conv_c1_fwd_kernel(const __grid_constant__ C1Params p) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   extern __shared__ uint8_t dsmem_raw[];
   __shared__ __align__(8) uint64_t full_bar[C1_FWD_STAGES], empty_bar[C1_FWD_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
@@ -416,6 +417,7 @@ __global__ void __launch_bounds__(C1_FWD_THREADS, 1) conv_c1_fwd_kernel(const __
 // weight gradient
 // =====================================================================================================================
 __global__ void __launch_bounds__(C1_WG_THREADS, 2) conv_c1_wgrad_kernel(const __grid_constant__ C1Params p) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   extern __shared__ uint8_t dsmem_raw[];
   __shared__ __align__(8) uint64_t a_full[C1_STAGES], y_full[C1_STAGES], empty_bar[C1_STAGES];
   __shared__ __align__(8) uint64_t acc_full;
@@ -560,10 +562,10 @@ static cudaError_t launch_c1_fwd(const C1Params& q, int gx, int smem, bool tma_i
   cudaError_t e;
   if (tma_in) {
     e = cudaFuncSetAttribute(conv_c1_fwd_kernel<T, NCB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) conv_c1_fwd_kernel<T, NCB, true><<<gx, C1_FWD_THREADS, smem, s>>>(q);
+    if (e == cudaSuccess) launch_pdl(conv_c1_fwd_kernel<T, NCB, true>, dim3(gx), dim3(C1_FWD_THREADS), (size_t)(smem), s, q);
   } else {
     e = cudaFuncSetAttribute(conv_c1_fwd_kernel<T, NCB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) conv_c1_fwd_kernel<T, NCB, false><<<gx, C1_FWD_THREADS, smem, s>>>(q);
+    if (e == cudaSuccess) launch_pdl(conv_c1_fwd_kernel<T, NCB, false>, dim3(gx), dim3(C1_FWD_THREADS), (size_t)(smem), s, q);
   }
   return e;
 }
@@ -601,7 +603,7 @@ int conv_c1_wgrad(const void* x, long long xs, const void* dy, int dy_ldc, int d
   const int gx = (int)min((long long)q.units, (long long)2 * num_sms());
   cudaError_t e = cudaFuncSetAttribute(conv_c1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { set_error("conv_c1_wgrad: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
-  conv_c1_wgrad_kernel<<<gx, C1_WG_THREADS, smem, s>>>(q);
+  launch_pdl(conv_c1_wgrad_kernel, dim3(gx), dim3(C1_WG_THREADS), (size_t)(smem), s, q);
   return check_launch("conv_c1_wgrad");
 }
 

@@ -58,6 +58,7 @@ __device__ __forceinline__ void tma_reduce_add_5d(const CUtensorMap* map, const 
 
 template <typename T>
 __global__ void __launch_bounds__(GM_THREADS, 1) conv_gm_umma_kernel(const __grid_constant__ GmParams p) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   extern __shared__ uint8_t dsmem_raw[];
   __shared__ __align__(8) uint64_t full_bar[GM_MAX_STAGES], empty_bar[GM_MAX_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], w_full;
@@ -380,10 +381,10 @@ int conv_gm_umma(const mtb200_conv_params& p, cudaStream_t s) {
   cudaError_t e;
   if (p.dtype == MTB200_BF16) {
     e = cudaFuncSetAttribute(conv_gm_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) conv_gm_umma_kernel<__nv_bfloat16><<<gx, GM_THREADS, smem, s>>>(q);
+    if (e == cudaSuccess) launch_pdl(conv_gm_umma_kernel<__nv_bfloat16>, dim3(gx), dim3(GM_THREADS), (size_t)(smem), s, q);
   } else {
     e = cudaFuncSetAttribute(conv_gm_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) conv_gm_umma_kernel<__half><<<gx, GM_THREADS, smem, s>>>(q);
+    if (e == cudaSuccess) launch_pdl(conv_gm_umma_kernel<__half>, dim3(gx), dim3(GM_THREADS), (size_t)(smem), s, q);
   }
   if (e != cudaSuccess) { set_error("conv_gm: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
   return check_launch("conv_gm_umma");

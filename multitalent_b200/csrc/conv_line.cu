@@ -83,6 +83,7 @@ __device__ __forceinline__ uint32_t ln_kmajor_hi(uint32_t row_bytes, uint32_t sb
 // planar input halves.
 template <typename T, int ROWB, int EW, bool RED, int NCH>
 __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const __grid_constant__ LineParams p) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   constexpr int LN_CPT = 32 / (EW / 4);  // output channels per epilogue thread
   extern __shared__ uint8_t dsmem_raw[];
   __shared__ __align__(8) uint64_t st_full[LN_MAX_STAGES], st_empty[LN_MAX_STAGES];
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(ln_threads(EW), 1) conv_line_umma_kernel(const
 template <typename T, int ROWB, int EW, bool RED, int NCH>
 static cudaError_t launch_line_red(const LineParams& q, dim3 grid, int smem, cudaStream_t s) {
   cudaError_t e = cudaFuncSetAttribute(conv_line_umma_kernel<T, ROWB, EW, RED, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) conv_line_umma_kernel<T, ROWB, EW, RED, NCH><<<grid, ln_threads(EW), smem, s>>>(q);
+  if (e == cudaSuccess) launch_pdl(conv_line_umma_kernel<T, ROWB, EW, RED, NCH>, dim3(grid), dim3(ln_threads(EW)), (size_t)(smem), s, q);
   return e;
 }
 template <typename T, int ROWB, int EW>

@@ -60,6 +60,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 
 template <typename T>
 __global__ void __launch_bounds__(PW_THREADS, 2) conv_pw_umma_kernel(const __grid_constant__ PwParams p) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   extern __shared__ uint8_t dsmem_raw[];
   __shared__ __align__(8) uint64_t full_bar[PW_MAX_STAGES], empty_bar[PW_MAX_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], w_full;
@@ -402,10 +403,10 @@ int conv_pw_umma(const mtb200_conv_params& p, cudaStream_t s) {
   cudaError_t e;
   if (p.dtype == MTB200_BF16) {
     e = cudaFuncSetAttribute(conv_pw_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) conv_pw_umma_kernel<__nv_bfloat16><<<grid, PW_THREADS, smem, s>>>(q);
+    if (e == cudaSuccess) launch_pdl(conv_pw_umma_kernel<__nv_bfloat16>, dim3(grid), dim3(PW_THREADS), (size_t)(smem), s, q);
   } else {
     e = cudaFuncSetAttribute(conv_pw_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) conv_pw_umma_kernel<__half><<<grid, PW_THREADS, smem, s>>>(q);
+    if (e == cudaSuccess) launch_pdl(conv_pw_umma_kernel<__half>, dim3(grid), dim3(PW_THREADS), (size_t)(smem), s, q);
   }
   if (e != cudaSuccess) { set_error("conv_pw: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
   return check_launch(q.red_y ? "conv_pw_umma+red" : "conv_pw_umma");

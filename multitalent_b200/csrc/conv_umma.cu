@@ -115,6 +115,7 @@ struct UmmaConvParams {
 // which hides the per-stage barrier round trip of the single issuing thread.
 template <typename T>
 __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __grid_constant__ UmmaConvParams p) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   extern __shared__ uint8_t dsmem_raw[];
   __shared__ __align__(8) uint64_t full_bar[UM_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[UM_MAX_STAGES];
@@ -476,10 +477,10 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
   cudaError_t e;
   if (p.dtype == MTB200_BF16) {
     e = cudaFuncSetAttribute(conv_taps_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) conv_taps_umma_kernel<__nv_bfloat16><<<grid, UMC_THREADS, smem, s>>>(q);
+    if (e == cudaSuccess) launch_pdl(conv_taps_umma_kernel<__nv_bfloat16>, dim3(grid), dim3(UMC_THREADS), (size_t)(smem), s, q);
   } else {
     e = cudaFuncSetAttribute(conv_taps_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) conv_taps_umma_kernel<__half><<<grid, UMC_THREADS, smem, s>>>(q);
+    if (e == cudaSuccess) launch_pdl(conv_taps_umma_kernel<__half>, dim3(grid), dim3(UMC_THREADS), (size_t)(smem), s, q);
   }
   if (e != cudaSuccess) { set_error("conv_taps(umma): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
   return check_launch("conv_taps_umma");
@@ -540,6 +541,7 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32
 }
 
 __global__ void __launch_bounds__(UM_THREADS, 1) wgrad_taps_umma_kernel(const __grid_constant__ UmmaWgradParams p) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   extern __shared__ uint8_t dsmem_raw[];
   __shared__ __align__(8) uint64_t a_full[WG_MAX_ASTAGES], a_empty[WG_MAX_ASTAGES];
   __shared__ __align__(8) uint64_t b_full[2], b_empty[2];
@@ -895,7 +897,7 @@ int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
     q.bricks_per_cta = (int)((q.nbricks + ksplit - 1) / ksplit);
     ksplit = (q.nbricks + q.bricks_per_cta - 1) / q.bricks_per_cta;
     dim3 grid((unsigned)ksplit, tile_groups, nz);
-    wgrad_taps_umma_kernel<<<grid, UM_THREADS, smem, s>>>(q);
+    launch_pdl(wgrad_taps_umma_kernel, dim3(grid), dim3(UM_THREADS), (size_t)(smem), s, q);
     int r = check_launch("wgrad_taps_umma");
     if (r) return r;
   }

@@ -86,6 +86,7 @@ __device__ __forceinline__ uint64_t hb_desc64(uint32_t hi, uint32_t lo) { return
 //      it from TMEM and round it to the storage type first -- the values the stored logits would have had
 template <typename T, int CIN, bool ACC, bool RC>
 __global__ void __launch_bounds__(HB_THREADS, CIN == 32 ? 3 : 2) head_bwd_fused_kernel(const __grid_constant__ HeadBwdParams p) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   constexpr int ROWB = CIN * 2;            // bytes per input row
   constexpr int ACT_BYTES = 128 * ROWB;    // one staged input tile
   constexpr int NCH = ROWB / 16;           // 16-byte pieces per output row
@@ -388,6 +389,7 @@ __global__ void __launch_bounds__(HB_THREADS, CIN == 32 ? 3 : 2) head_bwd_fused_
 // atomic per (channel, statistic).  HARD: also the thresholded-prediction counts of run_online_evaluation.
 template <typename T, int CIN, bool HARD>
 __global__ void __launch_bounds__(HB_THREADS, 2) head_fwd_stats_kernel(const __grid_constant__ HeadBwdParams p) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   constexpr int ROWB = CIN * 2;
   constexpr int ACT_BYTES = 128 * ROWB;
   constexpr int NCH = ROWB / 16;
@@ -562,6 +564,7 @@ struct HeadAggParams {
 
 template <typename T, int CIN>
 __global__ void __launch_bounds__(HB_THREADS, 2) head_aggregate_kernel(const __grid_constant__ HeadAggParams p) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   constexpr int ROWB = CIN * 2;
   constexpr int ACT_BYTES = 128 * ROWB;
   constexpr int NCH = ROWB / 16;
@@ -745,7 +748,7 @@ int head_bwd_fused(const mtb200_head_bwd_params& p, cudaStream_t s) {
 #define HB_LAUNCH3(T, CIN, ACC, RC)                                                                                      \
   do {                                                                                                                   \
     e = cudaFuncSetAttribute(head_bwd_fused_kernel<T, CIN, ACC, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-    if (e == cudaSuccess) head_bwd_fused_kernel<T, CIN, ACC, RC><<<grid, HB_THREADS, smem, s>>>(q);                      \
+    if (e == cudaSuccess) launch_pdl(head_bwd_fused_kernel<T, CIN, ACC, RC>, dim3(grid), dim3(HB_THREADS), (size_t)(smem), s, q);                      \
   } while (0)
 #define HB_LAUNCH2(T, CIN, ACC)                                                   \
   do {                                                                            \
@@ -802,7 +805,7 @@ int head_fwd_stats(const mtb200_head_fwd_params& p, cudaStream_t s) {
 #define HF_LAUNCH2(T, CIN, HARD)                                                                                     \
   do {                                                                                                               \
     e = cudaFuncSetAttribute(head_fwd_stats_kernel<T, CIN, HARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-    if (e == cudaSuccess) head_fwd_stats_kernel<T, CIN, HARD><<<grid, HB_THREADS, smem, s>>>(q);                     \
+    if (e == cudaSuccess) launch_pdl(head_fwd_stats_kernel<T, CIN, HARD>, dim3(grid), dim3(HB_THREADS), (size_t)(smem), s, q);                     \
   } while (0)
 #define HF_LAUNCH(T, CIN)                                                \
   do {                                                                   \
@@ -849,7 +852,7 @@ int head_aggregate(const mtb200_head_agg_params& p, cudaStream_t s) {
 #define HA_LAUNCH(T, CIN)                                                                                          \
   do {                                                                                                             \
     e = cudaFuncSetAttribute(head_aggregate_kernel<T, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);    \
-    if (e == cudaSuccess) head_aggregate_kernel<T, CIN><<<gx, HB_THREADS, smem, s>>>(q);                           \
+    if (e == cudaSuccess) launch_pdl(head_aggregate_kernel<T, CIN>, dim3(gx), dim3(HB_THREADS), (size_t)(smem), s, q);                           \
   } while (0)
   if (p.dtype == MTB200_BF16) {
     if (p.Cin == 32) HA_LAUNCH(__nv_bfloat16, 32); else HA_LAUNCH(__nv_bfloat16, 64);

@@ -153,6 +153,7 @@ __global__ void mt_loss_finalize_kernel(const double* __restrict__ stats, const 
                                         const uint64_t* __restrict__ valid_mask, int B, int C, double inv_nvox,
                                         float weight, float world, float* __restrict__ losses,
                                         float4* __restrict__ coef) {
+  pdl_wait();
   __shared__ double s_ce[256], s_dc[256];
   double ce = 0.0, dc = 0.0;
   for (int i = threadIdx.x; i < B * C; i += blockDim.x) {
@@ -185,7 +186,7 @@ __global__ void mt_loss_finalize_kernel(const double* __restrict__ stats, const 
 int mt_loss_finalize(const double* stats, const double* pooled, const uint64_t* valid_mask, int B, int C, long long nvox,
                      float weight, float world_size, float* losses, float* coef, cudaStream_t s) {
   MTB_REQUIRE(C <= 64, "mt_loss_finalize: C=%d", C);
-  mt_loss_finalize_kernel<<<1, 256, 0, s>>>(stats, pooled, valid_mask, B, C, 1.0 / (double)nvox, weight, world_size,
+  launch_pdl(mt_loss_finalize_kernel, dim3(1), dim3(256), (size_t)(0), s, stats, pooled, valid_mask, B, C, 1.0 / (double)nvox, weight, world_size,
                                             losses, reinterpret_cast<float4*>(coef));
   return check_launch("mt_loss_finalize");
 }

@@ -58,6 +58,7 @@ static dim3 span_grid(long long nvox, int B, int C) {
 __global__ void in_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, int B, int C, double inv_n, float eps, float slope,
                                    float4* __restrict__ xform, float2* __restrict__ meanrstd) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int c = i % C;
@@ -73,7 +74,7 @@ __global__ void in_finalize_kernel(const double* __restrict__ stats, const float
 int in_finalize(const double* stats, const float* gamma, const float* beta, int B, int C, long long nvox, float eps,
                 float slope, float* xform, float* meanrstd, cudaStream_t s) {
   const int n = B * C;
-  in_finalize_kernel<<<(n + 127) / 128, 128, 0, s>>>(stats, gamma, beta, B, C, 1.0 / (double)nvox, eps, slope,
+  launch_pdl(in_finalize_kernel, dim3((n + 127) / 128), dim3(128), (size_t)(0), s, stats, gamma, beta, B, C, 1.0 / (double)nvox, eps, slope,
                                                      reinterpret_cast<float4*>(xform),
                                                      reinterpret_cast<float2*>(meanrstd));
   return check_launch("in_finalize");

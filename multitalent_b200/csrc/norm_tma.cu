@@ -66,6 +66,7 @@ template <> struct StVec<__half> {
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(ST_THREADS, 1) in_stream_tma_kernel(const __grid_constant__ StreamParams p) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   constexpr int NIN = MODE == 1 ? 1 : 2;
   constexpr int NOUT = MODE == 2 ? 0 : 1;
   extern __shared__ uint8_t dsmem_raw[];
@@ -275,7 +276,7 @@ static int stream_tma_launch(int mode, const void* a, int a_ldc, int a_coff, con
 #define ST_LAUNCH(T, MODE)                                                                                         \
   do {                                                                                                             \
     e = cudaFuncSetAttribute(in_stream_tma_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);    \
-    if (e == cudaSuccess) in_stream_tma_kernel<T, MODE><<<grid, ST_THREADS, smem, s>>>(q);                         \
+    if (e == cudaSuccess) launch_pdl(in_stream_tma_kernel<T, MODE>, dim3(grid), dim3(ST_THREADS), (size_t)(smem), s, q);                         \
   } while (0)
   if (dtype == MTB200_BF16) {
     if (mode == 0) ST_LAUNCH(__nv_bfloat16, 0); else if (mode == 1) ST_LAUNCH(__nv_bfloat16, 1); else ST_LAUNCH(__nv_bfloat16, 2);

@@ -6,6 +6,7 @@ namespace mtb {
 
 // ---- sum of squares ----------------------------------------------------------------------------------------------
 __global__ void sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ out) {
+  pdl_wait();
   double acc = 0.0;
   const long long n4 = n / 4;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -29,7 +30,7 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, double* _
 int sumsq(const float* g, long long n, double* out, cudaStream_t s) {
   MTB_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "sumsq: pointer must be 16-byte aligned");
   const int blocks = (int)max(1LL, min((long long)num_sms() * 4, (n / 4 + 255) / 256));
-  sumsq_kernel<<<blocks, 256, 0, s>>>(g, n, out);
+  launch_pdl(sumsq_kernel, dim3(blocks), dim3(256), (size_t)(0), s, g, n, out);
   return check_launch("sumsq");
 }
 
@@ -37,6 +38,7 @@ int sumsq(const float* g, long long n, double* out, cudaStream_t s) {
 __global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n,
                                 const double* __restrict__ sumsq, float inv_scale, float max_norm, float lr,
                                 float momentum, float wd, int first, const float* __restrict__ dyn_scale) {
+  pdl_wait();
   const double ss = *sumsq;
   if (!isfinite(ss)) return;  // GradScaler: skip the step on inf/nan gradients
   if (dyn_scale) inv_scale /= dyn_scale[0];  // GradScaler.unscale_: the loss was multiplied by the current scale
@@ -56,7 +58,7 @@ __global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__
 int sgd_step(float* p, const float* g, float* buf, long long n, const double* sumsq_, float inv_scale, float max_norm,
              float lr, float momentum, float wd, int first, const float* dyn_scale, cudaStream_t s) {
   const int blocks = (int)max(1LL, min((long long)num_sms() * 8, (n + 255) / 256));
-  sgd_step_kernel<<<blocks, 256, 0, s>>>(p, g, buf, n, sumsq_, inv_scale, max_norm, lr, momentum, wd, first, dyn_scale);
+  launch_pdl(sgd_step_kernel, dim3(blocks), dim3(256), (size_t)(0), s, p, g, buf, n, sumsq_, inv_scale, max_norm, lr, momentum, wd, first, dyn_scale);
   return check_launch("sgd_step");
 }
 
@@ -128,6 +130,7 @@ int pack_weights(const float* w, int Cout, int Cin, int ntap, int transposed, in
 // memory, and written out as full 32-byte rows of both packed layouts.
 template <typename WT>
 __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const mtb200_pack_desc* __restrict__ descs, int n) {
+  pdl_wait();
   __shared__ float tile[16 * 16 * 33];
   int lo = 0, hi = n - 1;
   while (lo < hi) {
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const mtb200_
 
 int pack_weights_batched(const void* descs, int n, int total_blocks, int wdtype, cudaStream_t s) {
   if (n <= 0 || total_blocks <= 0) return MTB200_OK;
-  MTB_DISPATCH_DTYPE(wdtype, WT, (pack_weights_batched_kernel<WT><<<total_blocks, 256, 0, s>>>(
+  MTB_DISPATCH_DTYPE(wdtype, WT, (launch_pdl(pack_weights_batched_kernel<WT>, dim3(total_blocks), dim3(256), (size_t)(0), s, 
       reinterpret_cast<const mtb200_pack_desc*>(descs), n)));
   return check_launch("pack_weights_batched");
 }
@@ -206,6 +209,7 @@ int unpack_wgrad(const float* dw, int Cout, int Cin, int ntap, int transposed, i
 constexpr int UNPACK_CHUNK = 4096;
 
 __global__ void __launch_bounds__(256) unpack_wgrad_batched_kernel(const mtb200_unpack_desc* __restrict__ descs, int n) {
+  pdl_wait();
   int lo = 0, hi = n - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(256) unpack_wgrad_batched_kernel(const mtb200_
 
 int unpack_wgrad_batched(const void* descs, int n, int total_blocks, cudaStream_t s) {
   if (n <= 0 || total_blocks <= 0) return MTB200_OK;
-  unpack_wgrad_batched_kernel<<<total_blocks, 256, 0, s>>>(reinterpret_cast<const mtb200_unpack_desc*>(descs), n);
+  launch_pdl(unpack_wgrad_batched_kernel, dim3(total_blocks), dim3(256), (size_t)(0), s, reinterpret_cast<const mtb200_unpack_desc*>(descs), n);
   return check_launch("unpack_wgrad_batched");
 }
 

@@ -60,6 +60,7 @@ __device__ __forceinline__ uint64_t wl_desc64(uint32_t hi, uint32_t lo) { return
 // ROWB = bytes per X row = kcw * 2 (64: four 32-channel blocks, 32: eight 16-channel blocks); NSEG = Cout segments per CTA
 template <int ROWB, int NSEG>
 __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_line_umma_kernel(const __grid_constant__ WgradLineParams p) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   extern __shared__ uint8_t dsmem_raw[];
   __shared__ __align__(8) uint64_t st_full[WL_MAX_STAGES], st_empty[WL_MAX_STAGES];
   __shared__ __align__(8) uint64_t acc_full;
@@ -346,7 +347,7 @@ int wgrad_line_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
 #define WL_LAUNCH(RB, NS)                                                                                         \
   do {                                                                                                            \
     e = cudaFuncSetAttribute(wgrad_line_umma_kernel<RB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
-    if (e == cudaSuccess) wgrad_line_umma_kernel<RB, NS><<<grid, WL_THREADS, smem, s>>>(q);                       \
+    if (e == cudaSuccess) launch_pdl(wgrad_line_umma_kernel<RB, NS>, dim3(grid), dim3(WL_THREADS), (size_t)(smem), s, q);                       \
   } while (0)
   if (rowb == 64) {
     if (q.nseg == 1) WL_LAUNCH(64, 1); else WL_LAUNCH(64, 2);

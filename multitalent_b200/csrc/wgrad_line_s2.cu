@@ -47,6 +47,7 @@ struct WgradS2Params {
 __device__ __forceinline__ uint64_t ws_desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
 
 __global__ void __launch_bounds__(WS_THREADS, 1) wgrad_line_s2_umma_kernel(const __grid_constant__ WgradS2Params p) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   extern __shared__ uint8_t dsmem_raw[];
   __shared__ __align__(8) uint64_t st_full[WS_MAX_STAGES], st_empty[WS_MAX_STAGES];
   __shared__ __align__(8) uint64_t acc_full;
@@ -293,7 +294,7 @@ int wgrad_line_s2_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   const int smem = max(116 * 1024, q.stages * q.stage_bytes + 1024);
   cudaError_t e = cudaFuncSetAttribute(wgrad_line_s2_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { set_error("wgrad_line_s2: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
-  wgrad_line_s2_umma_kernel<<<dim3((unsigned)(q.nslots * npairs)), WS_THREADS, smem, s>>>(q);
+  launch_pdl(wgrad_line_s2_umma_kernel, dim3(dim3((unsigned)(q.nslots * npairs))), dim3(WS_THREADS), (size_t)(smem), s, q);
   return check_launch("wgrad_line_s2_umma");
 }
 

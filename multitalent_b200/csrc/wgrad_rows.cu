@@ -44,6 +44,7 @@ struct WgradRowsParams {
 __device__ __forceinline__ uint64_t wr_desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
 
 __global__ void __launch_bounds__(WR_THREADS, 1) wgrad_rows_umma_kernel(const __grid_constant__ WgradRowsParams p) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   extern __shared__ uint8_t dsmem_raw[];
   __shared__ __align__(8) uint64_t st_full[WR_MAX_STAGES], st_empty[WR_MAX_STAGES];
   __shared__ __align__(8) uint64_t acc_full;
@@ -249,7 +250,7 @@ int wgrad_rows_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   dim3 grid((unsigned)(per_slot_ctas * nslots), 1, 1);
   cudaError_t e = cudaFuncSetAttribute(wgrad_rows_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { set_error("wgrad_rows: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
-  wgrad_rows_umma_kernel<<<grid, WR_THREADS, smem, s>>>(q);
+  launch_pdl(wgrad_rows_umma_kernel, dim3(grid), dim3(WR_THREADS), (size_t)(smem), s, q);
   return check_launch("wgrad_rows_umma");
 }
 
