@@ -298,6 +298,11 @@ int mtb200_sw_aggregate(const void* logits, int32_t dtype, int32_t ldc, int32_t 
  * or argmax if class_order == NULL (seg then holds the channel index as float). */
 int mtb200_sw_finalize(float* acc, const float* nb, int32_t C, int64_t nvox, const float* class_order, float* seg,
                        void* stream);
+/* The same for a SLAB of the volume: `acc`, `nb`, `seg` point at the slab's first voxel, the classes of `acc` are
+ * `class_stride` voxels apart (the whole volume), `nvox` voxels are finalised.  Lets the predictor normalise, threshold and
+ * ship the planes no later tile can touch while the remaining tiles are still being computed. */
+int mtb200_sw_finalize_slab(float* acc, const float* nb, int32_t C, int64_t class_stride, int64_t nvox,
+                            const float* class_order, float* seg, void* stream);
 
 /* ---- a12: clip_grad_norm_(12) + SGD(nesterov) on a flat fp32 parameter arena; replaces
  *      MultiTalent_Trainer_DDP.py:351-353 / nnUNetTrainerV2.py:166-170 ---------------------------------------------- */

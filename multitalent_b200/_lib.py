@@ -163,6 +163,7 @@ SIGNATURES = {
     "mtb200_sw_aggregate": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _f32, _i32, _vp, _vp, _i32, _i32, _i32,
                             _i32, _i32, _i32, _vp],
     "mtb200_sw_finalize": [_vp, _vp, _i32, _i64, _vp, _vp, _vp],
+    "mtb200_sw_finalize_slab": [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp],
     "mtb200_sumsq": [_vp, _i64, _vp, _vp],
     "mtb200_sgd_step": [_vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _vp],
     "mtb200_loss_scale_update": [_vp, _vp, _f32, _f32, _i32, _vp],

@@ -84,7 +84,7 @@ int head_aggregate(const mtb200_head_agg_params& p, cudaStream_t s);  // head_bw
 int sw_gather_tile(const float*, int, int, int, int, int, int, int, int, int, int, int, void*, int, int, cudaStream_t);
 int sw_aggregate(const void*, int, int, int, int, int, int, int, const float*, float, int, float*, float*, int, int, int,
                  int, int, int, cudaStream_t);
-int sw_finalize(float*, const float*, int, long long, const float*, float*, cudaStream_t);
+int sw_finalize(float*, const float*, int, long long, long long, const float*, float*, cudaStream_t);
 int sumsq(const float*, long long, double*, cudaStream_t);
 int sgd_step(float*, const float*, float*, long long, const double*, float, float, float, float, float, int,
              const float*, cudaStream_t);
@@ -294,7 +294,12 @@ int mtb200_sw_aggregate(const void* logits, int32_t dtype, int32_t ldc, int32_t 
 int mtb200_sw_finalize(float* acc, const float* nb, int32_t C, int64_t nvox, const float* class_order, float* seg,
                        void* stream) {
   MTB_REQUIRE(acc && nb, "sw_finalize: null pointer");
-  return sw_finalize(acc, nb, C, nvox, class_order, seg, STREAM(stream));
+  return sw_finalize(acc, nb, C, nvox, nvox, class_order, seg, STREAM(stream));
+}
+int mtb200_sw_finalize_slab(float* acc, const float* nb, int32_t C, int64_t class_stride, int64_t nvox,
+                            const float* class_order, float* seg, void* stream) {
+  MTB_REQUIRE(acc && nb && class_stride >= nvox, "sw_finalize_slab: bad arguments");
+  return sw_finalize(acc, nb, C, class_stride, nvox, class_order, seg, STREAM(stream));
 }
 
 int mtb200_sumsq(const float* g, int64_t n, double* out, void* stream) {

@@ -147,13 +147,13 @@ int sw_aggregate(const void* logits, int dtype, int ldc, int C, int pd, int ph, 
 
 // ---- finalize: normalise + threshold ----------------------------------------------------------------------------------
 __global__ void sw_finalize_kernel(float* __restrict__ acc, const float* __restrict__ nb, int C, long long nvox,
-                                   const float* __restrict__ class_order, float* __restrict__ seg) {
+                                   const float* __restrict__ class_order, float* __restrict__ seg, long long cstride) {
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (long long)gridDim.x * blockDim.x) {
     const float n = nb[v];
     float sv = 0.f, best = -INFINITY;
     for (int c = 0; c < C; ++c) {
-      const float p = acc[(long long)c * nvox + v] / n;  // IEEE division, as numpy's in-place /=
-      acc[(long long)c * nvox + v] = p;
+      const float p = acc[(long long)c * cstride + v] / n;  // IEEE division, as numpy's in-place /=
+      acc[(long long)c * cstride + v] = p;
       if (class_order) {
         if (p > 0.5f) sv = class_order[c];
       } else if (p > best) {
@@ -165,11 +165,11 @@ __global__ void sw_finalize_kernel(float* __restrict__ acc, const float* __restr
   }
 }
 
-int sw_finalize(float* acc, const float* nb, int C, long long nvox, const float* class_order, float* seg,
+int sw_finalize(float* acc, const float* nb, int C, long long cstride, long long nvox, const float* class_order, float* seg,
                 cudaStream_t s) {
   const int blocks = (int)min((long long)num_sms() * 8, (nvox + 255) / 256);
   if (blocks == 0) return MTB200_OK;
-  sw_finalize_kernel<<<blocks, 256, 0, s>>>(acc, nb, C, nvox, class_order, seg);
+  sw_finalize_kernel<<<blocks, 256, 0, s>>>(acc, nb, C, nvox, class_order, seg, cstride);
   return check_launch("sw_finalize");
 }
 
