@@ -180,3 +180,22 @@ def test_region_bitmasks():
     assert pos[43] == (1 << chan['64_both_kidneys']) | (1 << chan['64_kidney_tumor'])
     assert valid_channel_mask(('03_liver', '03_cancer')) == 0b11
     assert bin(valid_channel_mask(tuple(chan))).count("1") == 47
+
+
+def test_head_windows_cover_every_dataset():
+    """Host logic of the fused head kernels: every Task100 dataset's supervised channels fit one 16-channel window that
+    starts on a multiple of 8 and ends inside the padded 48 channels; a spread-out (synthetic) region set does not."""
+    from multitalent_b200.dataset_conversion.Task100_MultiTalent import (MultiTalent_region_output_idx_mapping,
+                                                                          MultiTalent_task_ids, MultiTalent_valid_regions,
+                                                                          valid_channel_mask)
+    from multitalent_b200.training.loss_functions.multitalent_loss import head_windows
+    regs = [MultiTalent_valid_regions[t] for t in MultiTalent_task_ids]
+    win = head_windows(regs, 48)
+    assert win is not None and len(win) == len(regs)
+    for c0, r in zip(win, regs):
+        m = valid_channel_mask(r)
+        assert c0 % 8 == 0 and 0 <= c0 and c0 + 16 <= 48
+        assert m >> (c0 + 16) == 0 and m & ((1 << c0) - 1) == 0, (c0, bin(m))
+    names = sorted(MultiTalent_region_output_idx_mapping, key=MultiTalent_region_output_idx_mapping.get)
+    assert head_windows([(names[0], names[-1])], 48) is None     # channels 0 and 46: no 16-channel window
+    assert head_windows([()], 48) == (0,)                        # nothing supervised: any window
