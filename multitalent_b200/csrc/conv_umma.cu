@@ -113,7 +113,14 @@ struct UmmaConvParams {
 // TMA / MMA warps are already on tile k+1; barrier setup, TMEM allocation and descriptor fetch are paid once per CTA.
 // Two CTAs share an SM when the N tile is <= 128 (2 x 2 x BN <= 512 TMEM columns): their MMA-issue loops interleave,
 // which hides the per-stage barrier round trip of the single issuing thread.
-template <typename T>
+//
+// PAIR (r2, `MTB200_TAPS_PAIR`): the CTAs of a 2-cluster (two SMs of one TPC) work on two consecutive spatial tiles with ONE
+// tcgen05.mma.cta_group::2 (M = 256): each CTA fetches its own 128-voxel activation box and HALF of the weight tile's N
+// rows, so the weight stream through L2 -> SM (the bound of this kernel) is halved and N tiles up to 256 fit.  Only the
+// rank-0 CTA issues MMAs and owns the `full` barriers (both CTAs' TMA bytes are counted there); tcgen05.commit multicasts
+// the "slot free" / "accumulator complete" arrivals to both CTAs, the epilogue warps of both arrive on rank 0's
+// `acc_empty`.
+template <typename T, bool PAIR>
 __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __grid_constant__ UmmaConvParams p) {
   pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   extern __shared__ uint8_t dsmem_raw[];
@@ -128,12 +135,17 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* dsmem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsmem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t row_bytes = p.KC * 2;
-  const uint32_t a_bytes = 128u * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // cluster dims (2, 1, 1): rank == blockIdx.x & 1
+  const uint32_t b_rows = PAIR ? (uint32_t)p.BN / 2u : (uint32_t)p.BN;  // weight rows this CTA fetches
+  const uint32_t a_bytes = 128u * row_bytes, b_bytes = b_rows * row_bytes;
   const uint32_t stage_bytes = ((a_bytes + b_bytes + 1023u) / 1024u) * 1024u;
 
-  const int combo = blockIdx.x % p.ncombo;
+  // a "unit" is what one MMA chain covers: one spatial tile, or the pair's two consecutive tiles (2u, 2u + 1)
+  const int unit_cta = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int combo = unit_cta % p.ncombo;
   const int nb = combo % p.ny, g = combo / p.ny;
-  const long long tile0 = blockIdx.x / p.ncombo;
+  const long long tile0 = unit_cta / p.ncombo;
+  const long long nunits = PAIR ? (p.ntiles + 1) / 2 : p.ntiles;
   const int n0 = nb * p.BN;
   const int tap_begin = p.group_tap_begin[g], tap_end = p.group_tap_begin[g + 1];
   const int niter = (tap_end - tap_begin) * p.nkc;
@@ -141,7 +153,7 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], PAIR ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < 256; i += UMC_THREADS) {
@@ -149,9 +161,13 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
     for (int w = 0; w < 4; ++w) { s_sum[w][i] = 0.f; s_sq[w][i] = 0.f; }
     s_bias[i] = (p.bias && i < p.BN) ? p.bias[n0 + i] : 0.f;
   }
-  if (warp == 1) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(&tmem_slot, (uint32_t)p.tmem_cols);  // the same warp of both CTAs: same columns in both TMEMs
+    else tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
@@ -159,8 +175,10 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
     // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
     if (niter > 0) {
       uint32_t gi = 0;  // global pipeline iteration of this CTA
-      for (long long tile = tile0; tile < p.ntiles; tile += p.ctas_per_combo) {
-        uint32_t t = (uint32_t)tile;  // ntiles < 2^31 (host check): 32-bit divisions, a fifth of the 64-bit ones' instructions
+      for (long long u = tile0; u < nunits; u += p.ctas_per_combo) {
+        // ntiles < 2^31 (host check): 32-bit divisions, a fifth of the 64-bit ones' instructions.  The odd pair tile past
+        // the end decodes to b == B: its box is out of bounds on the batch axis and arrives as zeros
+        uint32_t t = PAIR ? (uint32_t)(2 * u) + rank : (uint32_t)u;
         const int tw = (int)(t % (uint32_t)p.tiles_w); t /= (uint32_t)p.tiles_w;
         const int th = (int)(t % (uint32_t)p.tiles_h); t /= (uint32_t)p.tiles_h;
         const int td = (int)(t % (uint32_t)p.tiles_d);
@@ -172,10 +190,18 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
           mbar_wait(&empty_bar[stage], ((gi / (uint32_t)p.stages) & 1u) ^ 1u);
           if (elect_one()) {
             uint8_t* sa = dsmem + (size_t)stage * stage_bytes;
-            mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-            tma_load_5d(sa, &p.a_maps[p.tap_map[tp]], &full_bar[stage], kc * p.KC, w0 + p.tap_coff[tp][2],
-                        h0 + p.tap_coff[tp][1], d0 + p.tap_coff[tp][0], b);
-            tma_load_3d(sa + a_bytes, &p.w_map, &full_bar[stage], kc * p.KC, n0, p.tap_widx[tp]);
+            if (PAIR) {
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (a_bytes + b_bytes));  // both CTAs' boxes
+              tma_load_5d_pair(sa, &p.a_maps[p.tap_map[tp]], &full_bar[stage], kc * p.KC, w0 + p.tap_coff[tp][2],
+                               h0 + p.tap_coff[tp][1], d0 + p.tap_coff[tp][0], b);
+              tma_load_3d_pair(sa + a_bytes, &p.w_map, &full_bar[stage], kc * p.KC, n0 + (int)(rank * b_rows),
+                               p.tap_widx[tp]);
+            } else {
+              mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+              tma_load_5d(sa, &p.a_maps[p.tap_map[tp]], &full_bar[stage], kc * p.KC, w0 + p.tap_coff[tp][2],
+                          h0 + p.tap_coff[tp][1], d0 + p.tap_coff[tp][0], b);
+              tma_load_3d(sa + a_bytes, &p.w_map, &full_bar[stage], kc * p.KC, n0, p.tap_widx[tp]);
+            }
           }
           __syncwarp();
           if (++kc == p.nkc) { kc = 0; ++tp; }
@@ -184,10 +210,11 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
     }
   } else if (warp == 1) {
     // ===== MMA issuer: warp-uniform loop, one elected lane issues (descriptors stay in uniform registers) =====
-    if (niter > 0) {
-      // instruction descriptor: D=f32, A/B = bf16 or f16, both K-major, N, M=128
+    if (niter > 0 && rank == 0) {
+      // instruction descriptor: D=f32, A/B = bf16 or f16, both K-major, N, M=128 (256 across the pair)
       const uint32_t fmt = p.is_f16 ? 0u : 1u;
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) |
+                             (((PAIR ? 256u : 128u) >> 4) << 24);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t s16 = __shfl_sync(0xffffffffu, (smem_u32(dsmem) & 0x3FFFFu) >> 4, 0);
       const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
@@ -195,7 +222,7 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
       const uint32_t stage16 = stage_bytes >> 4, a16 = a_bytes >> 4;
       const int ksteps = p.KC / 16;
       uint32_t gi = 0, k = 0;
-      for (long long tile = tile0; tile < p.ntiles; tile += p.ctas_per_combo, ++k) {
+      for (long long u = tile0; u < nunits; u += p.ctas_per_combo, ++k) {
         const uint32_t buf = k & 1u;
         mbar_wait(&acc_empty[buf], ((k >> 1) & 1u) ^ 1u);
         tc_fence_after();
@@ -207,11 +234,18 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
           if (elect_one()) {
             const uint32_t sa = s16 + stage * stage16;
             const uint32_t sb = sa + a16;
-            for (int ks = 0; ks < ksteps; ++ks)
-              umma_f16(dcol, ((uint64_t)hi << 32) | (uint64_t)(sa + 2u * ks), ((uint64_t)hi << 32) | (uint64_t)(sb + 2u * ks),
-                       idesc, (it > 0 || ks > 0) ? 1u : 0u);
-            umma_commit(&empty_bar[stage]);  // frees the smem slot once the MMAs above have read it
-            if (it == niter - 1) umma_commit(&acc_full[buf]);  // accumulator complete
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(sa + 2u * ks), bd = ((uint64_t)hi << 32) | (uint64_t)(sb + 2u * ks);
+              if (PAIR) umma_f16_pair(dcol, ad, bd, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+              else umma_f16(dcol, ad, bd, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+            }
+            if (PAIR) {
+              umma_commit_pair(&empty_bar[stage]);  // frees the slot in BOTH CTAs
+              if (it == niter - 1) umma_commit_pair(&acc_full[buf]);
+            } else {
+              umma_commit(&empty_bar[stage]);  // frees the smem slot once the MMAs above have read it
+              if (it == niter - 1) umma_commit(&acc_full[buf]);  // accumulator complete
+            }
           }
           __syncwarp();
         }
@@ -225,14 +259,15 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
     T* out = reinterpret_cast<T*>(p.out);
     const bool want_stats = p.stats != nullptr;
     uint32_t k = 0;
-    for (long long tile = tile0; tile < p.ntiles; tile += p.ctas_per_combo, ++k) {
+    for (long long u = tile0; u < nunits; u += p.ctas_per_combo, ++k) {
+      const long long tile = PAIR ? 2 * u + rank : u;
       uint32_t t = (uint32_t)tile;
       const int tw = (int)(t % (uint32_t)p.tiles_w); t /= (uint32_t)p.tiles_w;
       const int th = (int)(t % (uint32_t)p.tiles_h); t /= (uint32_t)p.tiles_h;
       const int td = (int)(t % (uint32_t)p.tiles_d);
       const int b = (int)(t / (uint32_t)p.tiles_d);
       const int od = td * p.bd + rd, oh = th * p.bh + rh, ow = tw * p.bw + rw;
-      const bool valid = od < p.Do && oh < p.Ho && ow < p.Wo;
+      const bool valid = od < p.Do && oh < p.Ho && ow < p.Wo && (!PAIR || tile < p.ntiles);
       const long long ovox = (((long long)b * p.Dof + (od * p.os[0] + p.group_ooff[g][0])) * p.Hof +
                               (oh * p.os[1] + p.group_ooff[g][1])) * p.Wof + (ow * p.os[2] + p.group_ooff[g][2]);
       T* orow = out + ovox * p.out_ldc + p.out_coff + n0;
@@ -290,11 +325,14 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
       if (niter > 0) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_leader(&acc_empty[buf]);
+          else mbar_arrive(&acc_empty[buf]);
+        }
       }
       if (want_stats) {
         // flush the per-(b, channel) partials when this CTA moves on to another sample (or is done)
-        const long long next = tile + p.ctas_per_combo;
+        const long long next = tile + (PAIR ? 2 : 1) * p.ctas_per_combo;
         if (next >= p.ntiles || next / tiles_per_b != tile / tiles_per_b) {
           asm volatile("bar.sync 1, 128;" ::: "memory");
           for (int c = threadIdx.x - 64; c < p.BN; c += 128) {
@@ -313,10 +351,13 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
       }
     }
   }
-  __syncthreads();
+  tc_fence_before();
+  if (PAIR) cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other may still signal it / read its tiles
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -391,6 +432,23 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
     for (int c = 160; c >= 16; c -= 16)
       if (p.Cout % c == 0) { q.BN = c; break; }
   }
+  // CTA pairs (cta_group::2, M = 256): one tap group with taps, >= 2 tiles; N tile = whole Cout up to 256 (each CTA of
+  // the pair fetches half of its rows).  MTB200_TAPS_PAIR=0 switches the pairs off (5 - 20 % slower on every
+  // layer of the stack, profiles/r2w_pair.txt)
+  bool pair = false;
+  {
+    static const int mode = [] { const char* e = getenv("MTB200_TAPS_PAIR"); return e ? atoi(e) : -1; }();
+    bool eligible = p.ngroups == 1 && p.group_tap_begin[1] > p.group_tap_begin[0] && p.Cout % 32 == 0;
+    int bn2 = p.Cout;
+    if (bn2 > 256) {
+      bn2 = 0;
+      for (int c = 256; c >= 32; c -= 32)
+        if (p.Cout % c == 0) { bn2 = c; break; }
+    }
+    eligible = eligible && bn2 >= 32;
+    if (mode != 0) pair = eligible;
+    if (pair) q.BN = bn2;
+  }
   q.tmem_cols = 32;
   while (q.tmem_cols < 2 * q.BN) q.tmem_cols *= 2;  // two accumulators (tile k drains while tile k+1 accumulates)
   // brick: powers of two with product 128 minimising the number of tiles (ties: widest in w)
@@ -448,7 +506,7 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
     for (int t = 0; t < p.ntaps; ++t) n_widx = max(n_widx, p.tap_widx[t] + 1);
     cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, (cuuint64_t)n_widx};
     cuuint64_t strides[2] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Cin * p.Cout * 2};
-    cuuint32_t box[3] = {(cuuint32_t)q.KC, (cuuint32_t)q.BN, 1};
+    cuuint32_t box[3] = {(cuuint32_t)q.KC, (cuuint32_t)(pair ? q.BN / 2 : q.BN), 1};
     if (!encode_map(enc, &q.w_map, dt, 3, (void*)p.w, dims, strides, box, row_bytes)) return MTB200_ERR_CUDA;
   }
   q.out = p.out; q.bias = p.bias; q.stats = p.stats;
@@ -461,7 +519,7 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
   q.accumulate = p.accumulate;
   q.is_f16 = p.dtype == MTB200_F16;
 
-  const int stage_bytes = ((128 * row_bytes + q.BN * row_bytes + 1023) / 1024) * 1024;
+  const int stage_bytes = ((128 * row_bytes + (pair ? q.BN / 2 : q.BN) * row_bytes + 1023) / 1024) * 1024;
   const int per_sm = q.tmem_cols <= 256 ? 2 : 1;  // CTAs per SM (TMEM: 512 columns per SM)
   const int budget = per_sm == 2 ? 100 * 1024 : 200 * 1024;
   q.stages = max(2, min(UM_MAX_STAGES, budget / stage_bytes));
@@ -472,15 +530,31 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
   q.ncombo = q.ny * p.ngroups;
   const int slots = num_sms() * per_sm;
   if (q.ncombo > slots) { set_error("conv_taps(umma): %d (N tile, group) combinations exceed the CTA slots", q.ncombo); return MTB200_ERR_UNSUPPORTED; }
+  cudaError_t e;
+  if (pair) {
+    // persistent PAIRS: ctas_per_combo counts pairs, the grid is twice that (cluster dims (2, 1, 1))
+    const int pair_slots = slots / 2;
+    if (q.ncombo > pair_slots) { set_error("conv_taps(umma): %d N tiles exceed the CTA pair slots", q.ncombo); return MTB200_ERR_UNSUPPORTED; }
+    q.ctas_per_combo = (int)min((long long)(pair_slots / q.ncombo), (ntiles + 1) / 2);
+    dim3 grid((unsigned)(2 * q.ctas_per_combo * q.ncombo), 1, 1);
+    if (p.dtype == MTB200_BF16) {
+      e = cudaFuncSetAttribute(conv_taps_umma_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e == cudaSuccess) e = launch_pdl_cluster(conv_taps_umma_kernel<__nv_bfloat16, true>, grid, dim3(UMC_THREADS), (size_t)smem, s, 2, q);
+    } else {
+      e = cudaFuncSetAttribute(conv_taps_umma_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e == cudaSuccess) e = launch_pdl_cluster(conv_taps_umma_kernel<__half, true>, grid, dim3(UMC_THREADS), (size_t)smem, s, 2, q);
+    }
+    if (e != cudaSuccess) { set_error("conv_taps(umma, pair): launch: %s", cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
+    return check_launch("conv_taps_umma(pair)");
+  }
   q.ctas_per_combo = (int)min((long long)(slots / q.ncombo), ntiles);
   dim3 grid((unsigned)(q.ctas_per_combo * q.ncombo), 1, 1);
-  cudaError_t e;
   if (p.dtype == MTB200_BF16) {
-    e = cudaFuncSetAttribute(conv_taps_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) launch_pdl(conv_taps_umma_kernel<__nv_bfloat16>, dim3(grid), dim3(UMC_THREADS), (size_t)(smem), s, q);
+    e = cudaFuncSetAttribute(conv_taps_umma_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) launch_pdl(conv_taps_umma_kernel<__nv_bfloat16, false>, dim3(grid), dim3(UMC_THREADS), (size_t)(smem), s, q);
   } else {
-    e = cudaFuncSetAttribute(conv_taps_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) launch_pdl(conv_taps_umma_kernel<__half>, dim3(grid), dim3(UMC_THREADS), (size_t)(smem), s, q);
+    e = cudaFuncSetAttribute(conv_taps_umma_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) launch_pdl(conv_taps_umma_kernel<__half, false>, dim3(grid), dim3(UMC_THREADS), (size_t)(smem), s, q);
   }
   if (e != cudaSuccess) { set_error("conv_taps(umma): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
   return check_launch("conv_taps_umma");

@@ -396,7 +396,9 @@ __global__ void __launch_bounds__(HB_THREADS, 2) head_fwd_stats_kernel(const __g
   constexpr int NQ = HARD ? 6 : 4;
   constexpr int NST = CIN == 32 ? HF_STAGES : 6;  // 64-channel inputs: 6 x 16 KB so that two CTAs still share an SM
   extern __shared__ uint8_t dsmem_raw[];
-  __shared__ __align__(8) uint64_t act_full[HF_STAGES], act_empty[HF_STAGES], z_full[2], z_empty[2];
+  constexpr int NZ = 8;  // logit accumulators in flight (16 TMEM columns each): the MMA -> TMEM -> threads -> MMA round trip
+                         // is ~1 us, two buffers kept the tensor core idle most of the time
+  __shared__ __align__(8) uint64_t act_full[HF_STAGES], act_empty[HF_STAGES], z_full[NZ], z_empty[NZ];
   __shared__ uint32_t tmem_slot;
   __shared__ uint64_t s_pos[HB_MAX_LABELS];
   __shared__ float s_part[4][NQ * HB_WIN];
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(HB_THREADS, 2) head_fwd_stats_kernel(const __g
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(&act_full[i], 1); mbar_init(&act_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], 128); }
+    for (int i = 0; i < NZ; ++i) { mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < HB_MAX_LABELS) s_pos[threadIdx.x] = (int)threadIdx.x < p.n_labels ? p.pos_mask[threadIdx.x] : 0ull;
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(HB_THREADS, 2) head_fwd_stats_kernel(const __g
     *reinterpret_cast<uint4*>(w0_base + row * ROWB + sw * 16) = v;
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  if (warp == 1) tmem_alloc(&tmem_slot, 32u);
+  if (warp == 1) tmem_alloc(&tmem_slot, (uint32_t)(NZ * HB_WIN));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -451,9 +453,9 @@ __global__ void __launch_bounds__(HB_THREADS, 2) head_fwd_stats_kernel(const __g
     const uint32_t w0_16 = __shfl_sync(0xffffffffu, (smem_u32(w0_base) & 0x3FFFFu) >> 4, 0);
     uint32_t i = 0;
     for (long long t = slot; t < ntiles; t += p.cps, ++i) {
-      const uint32_t buf = i & 1u, stage = i % NST;
+      const uint32_t buf = i % NZ, stage = i % NST;
       mbar_wait(&act_full[stage], (i / NST) & 1u);
-      mbar_wait(&z_empty[buf], ((i >> 1) & 1u) ^ 1u);
+      mbar_wait(&z_empty[buf], ((i / NZ) & 1u) ^ 1u);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t x_t = act16 + stage * ((uint32_t)ACT_BYTES >> 4);
@@ -479,12 +481,12 @@ __global__ void __launch_bounds__(HB_THREADS, 2) head_fwd_stats_kernel(const __g
       float lab = __ldg(tb + min((long long)slot * 128 + m, p.nvox - 1));
       uint32_t i = 0;
       for (long long t = slot; t < ntiles; t += p.cps, ++i) {
-        const uint32_t buf = i & 1u;
+        const uint32_t buf = i % NZ;
         const long long tn = t + p.cps;
         float nlab = 0.f;
         if (tn < ntiles) nlab = __ldg(tb + min(tn * 128 + m, p.nvox - 1));
         uint32_t zr[16];
-        mbar_wait(&z_full[buf], (i >> 1) & 1u);
+        mbar_wait(&z_full[buf], (i / NZ) & 1u);
         tc_fence_after();
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * HB_WIN, zr);
         tc_fence_before();
@@ -539,7 +541,7 @@ __global__ void __launch_bounds__(HB_THREADS, 2) head_fwd_stats_kernel(const __g
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 32u);
+    tmem_dealloc(tmem_base, (uint32_t)(NZ * HB_WIN));
   }
 }
 

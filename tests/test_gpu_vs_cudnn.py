@@ -56,6 +56,10 @@ LAYERS = [
     ("conv", 480, 240, (3, 3, 3), (1, 1, 1), (1, 24, 20, 16), 240),
     ("conv", 320, 320, (3, 3, 3), (1, 2, 2), (2, 12, 10, 8), 0),      # bottleneck stride (1, 2, 2)
     ("convT", 320, 320, (1, 2, 2), (1, 2, 2), (2, 12, 5, 4), 0),
+    # odd tile counts (27 / 15 tiles of 128 voxels): the CTA-pair (cta_group::2) kernel's last pair has one tile past the end
+    ("conv", 120, 120, (3, 3, 3), (1, 1, 1), (3, 12, 10, 8), 0),
+    ("conv", 320, 320, (3, 3, 3), (1, 1, 1), (3, 5, 7, 9), 0),
+    ("conv", 120, 60, (3, 3, 3), (1, 1, 1), (1, 9, 10, 24), 0),
 ]
 
 
