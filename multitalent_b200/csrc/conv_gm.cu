@@ -10,23 +10,25 @@
 //     transposed conv: 1 load, one N = 256 MMA);
 //   * every weight tile stays resident in shared memory (27 x 4 KB), stacked so that a run's tiles form one K-major
 //     [N][K] operand;
-//   * the epilogue stages the (2bd x 2bh x 2bw) output brick in swizzled shared memory, one d-parity half at a time,
-//     and writes it with ONE 5-D TMA store per half (reduce-add when the gradient buffer already holds the
-//     decoder's contribution), instead of half-filled sectors from per-lane stores.
+//   * the epilogue stages the (2bd x 2bh x 2bw) output brick in swizzled shared memory, one (d-parity, h-parity)
+//     quarter at a time (bd x bh x 2bw voxels = 16 KB at 32 channels), and writes it with ONE 5-D TMA store per quarter
+//     (reduce-add when the gradient buffer already holds the decoder's contribution), instead of half-filled sectors
+//     from per-lane stores.
 // Persistent CTAs, one per SM (512 TMEM columns = two accumulators).  Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA
-// issuer, 2..5 = epilogue.
+// issuer, 2..5 = epilogue of the d-parity-0 half, 6..9 = epilogue of the d-parity-1 half (own staging buffer, own bulk
+// store group: the kernel is bound by this TMEM -> bf16 -> shared -> TMA-store chain, so the two halves run side by side).
 #include "umma.cuh"
 
 namespace mtb {
 
 using namespace um;
 
-constexpr int GM_THREADS = 192;
+constexpr int GM_THREADS = 320;
 constexpr int GM_MAX_STAGES = 6;
 constexpr int GM_MAX_OPS = 32;
 
 struct GmParams {
-  CUtensorMap a_map, w_map, o_map[2];
+  CUtensorMap a_map, w_map, o_map[4];   // o_map[2 * r0 + r1]: the output sub-lattice d = os0*q + r0, h = os1*q + r1
   int B, tiles_d, tiles_h, tiles_w, bd, bh, bw;
   uint32_t ntiles;
   int KC, Cout, ngroups, ncols;   // ncols = ngroups * Cout (accumulator width)
@@ -39,6 +41,8 @@ struct GmParams {
   int nwt;                        // weight tiles
   int wt_widx[MTB200_MAX_TAPS], wt_off[MTB200_MAX_TAPS];
   int stages, a_stage_bytes, w_bytes, out_half_bytes, out_mask;
+  int hsplit;                     // 1: the staging buffer holds one (d, h) parity QUARTER per store (when the resident
+                                  // weights leave no room for two half bricks), 0: one d-parity half
   int accumulate, is_f16;
 };
 
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) conv_gm_umma_kernel(const __gri
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * p.os[0]); }
     mbar_init(&w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -154,12 +158,17 @@ __global__ void __launch_bounds__(GM_THREADS, 1) conv_gm_umma_kernel(const __gri
       }
     }
   } else {
-    // ===== epilogue: warps 2..5; thread = one voxel q of the brick (TMEM lane), all groups =====
+    // ===== epilogue: set 0 = warps 2..5, set 1 = warps 6..9; thread = one voxel q of the brick (TMEM lane), the groups
+    // of the set's d-parity half =====
     const int q = warp & 3;
+    const int set = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int qw = row % p.bw, qh = (row / p.bw) % p.bh, qd = row / (p.bw * p.bh);
-    const bool issuer = threadIdx.x == 64;
-    const int sbw = p.os[2] * p.bw, sbh = p.os[1] * p.bh;  // staged box extents along w, h (d: bd per parity half)
+    const bool issuer = threadIdx.x == 64 + 128 * set;
+    uint8_t* o_set = o_base + (size_t)set * p.out_half_bytes;
+    if (set < p.os[0]) {
+    const int sbw = p.os[2] * p.bw, sbh = p.os[1] * p.bh;  // staged box extents along w, h
+    const int nparts = p.hsplit ? p.os[1] : 1;
     const uint32_t orow_bytes = (uint32_t)p.Cout * 2u;
     uint32_t k = 0;
     for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++k) {
@@ -176,43 +185,66 @@ __global__ void __launch_bounds__(GM_THREADS, 1) conv_gm_umma_kernel(const __gri
       mbar_wait(&acc_full[buf], (k >> 1) & 1u);
       tc_fence_after();
       const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.ncols;
-      for (int r0 = 0; r0 < p.os[0]; ++r0) {
-        // the bulk store of the previous half must have finished reading the staging buffer
+      const int r0 = set;
+      for (int r1 = 0; r1 < nparts; ++r1) {
+        // the bulk store of the previous part must have finished reading the staging buffer
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
         for (int g = 0; g < p.ngroups; ++g) {
-          if (p.grp_r[g][0] != r0) continue;
-          const uint32_t srow = (uint32_t)((qd * sbh + (p.os[1] * qh + p.grp_r[g][1])) * sbw + (p.os[2] * qw + p.grp_r[g][2]));
-          for (int c0 = 0; c0 < p.Cout; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(tcol + (uint32_t)(g * p.Cout + c0), r);
-            float lo[8], hi8[8];
+          if (p.grp_r[g][0] != r0 || (p.hsplit && p.grp_r[g][1] != r1)) continue;
+          const uint32_t srow = p.hsplit ? (uint32_t)((qd * p.bh + qh) * sbw + (p.os[2] * qw + p.grp_r[g][2]))
+                                         : (uint32_t)((qd * sbh + (p.os[1] * qh + p.grp_r[g][1])) * sbw + (p.os[2] * qw + p.grp_r[g][2]));
+          if ((p.Cout & 31) == 0) {
+            // 32 columns per round: both TMEM loads in flight before the first conversion
+            for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+              uint32_t ra[16], rb[16];
+              tmem_ld16_async(tcol + (uint32_t)(g * p.Cout + c0), ra);
+              tmem_ld16_async(tcol + (uint32_t)(g * p.Cout + c0 + 16), rb);
+              tmem_ld_fence(ra);
+              tmem_ld_fence(rb);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { lo[j] = __uint_as_float(r[j]); hi8[j] = __uint_as_float(r[8 + j]); }
-            uint32_t off0 = srow * orow_bytes + (uint32_t)c0 * 2u;
-            uint32_t off1 = off0 + 16u;
-            off0 ^= ((off0 >> 7) & (uint32_t)p.out_mask) << 4;
-            off1 ^= ((off1 >> 7) & (uint32_t)p.out_mask) << 4;
-            store8<T>(reinterpret_cast<T*>(o_base + off0), lo);
-            store8<T>(reinterpret_cast<T*>(o_base + off1), hi8);
+              for (int h = 0; h < 4; ++h) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(h < 2 ? ra[(h & 1) * 8 + j] : rb[(h & 1) * 8 + j]);
+                uint32_t off = srow * orow_bytes + (uint32_t)(c0 + 8 * h) * 2u;
+                off ^= ((off >> 7) & (uint32_t)p.out_mask) << 4;
+                store8<T>(reinterpret_cast<T*>(o_set + off), v);
+              }
+            }
+          } else {
+            for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+              uint32_t r[16];
+              tmem_ld16(tcol + (uint32_t)(g * p.Cout + c0), r);
+              float lo[8], hi8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { lo[j] = __uint_as_float(r[j]); hi8[j] = __uint_as_float(r[8 + j]); }
+              uint32_t off0 = srow * orow_bytes + (uint32_t)c0 * 2u;
+              uint32_t off1 = off0 + 16u;
+              off0 ^= ((off0 >> 7) & (uint32_t)p.out_mask) << 4;
+              off1 ^= ((off1 >> 7) & (uint32_t)p.out_mask) << 4;
+              store8<T>(reinterpret_cast<T*>(o_set + off0), lo);
+              store8<T>(reinterpret_cast<T*>(o_set + off1), hi8);
+            }
           }
         }
-        if (r0 == p.os[0] - 1) {  // every TMEM read of this tile is done: hand the accumulator back
+        if (r1 == nparts - 1) {  // every TMEM read of this set's half is done: hand its share of the accumulator back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
         if (issuer) {
-          const int c1 = p.os[2] * tw * p.bw, c2 = p.os[1] * th * p.bh, c3 = td * p.bd;
-          if (p.accumulate) tma_reduce_add_5d(&p.o_map[r0], o_base, 0, c1, c2, c3, b);
-          else tma_store_5d(&p.o_map[r0], o_base, 0, c1, c2, c3, b);
+          const int c1 = p.os[2] * tw * p.bw, c2 = (p.hsplit ? 1 : p.os[1]) * th * p.bh, c3 = td * p.bd;
+          if (p.accumulate) tma_reduce_add_5d(&p.o_map[2 * r0 + r1], o_set, 0, c1, c2, c3, b);
+          else tma_store_5d(&p.o_map[2 * r0 + r1], o_set, 0, c1, c2, c3, b);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
   }
   __syncthreads();
   if (warp == 1) {
@@ -341,13 +373,26 @@ int conv_gm_umma(const mtb200_conv_params& p, cudaStream_t s) {
   q.a_stage_bytes = 128 * rowb;
   q.w_bytes = gm_align1k((long long)nwt * wtile);
   const int orowb = p.Cout * 2;
-  q.out_half_bytes = gm_align1k((long long)q.bd * (p.os[1] * q.bh) * (p.os[2] * q.bw) * orowb);
+  // one staging buffer per d-parity half (epilogue set): the whole half brick when that leaves >= 4 load stages (one
+  // store per set and tile: transposed conv 0.47 -> 0.27 ms), else one h-parity quarter at a time (strided dgrad: 27
+  // resident weight tiles)
   q.out_mask = orowb == 128 ? 7 : (orowb == 64 ? 3 : 1);
   const int budget = 226 * 1024;
-  const int fixed = q.w_bytes + q.out_half_bytes + 1024;
-  q.stages = min(GM_MAX_STAGES, (budget - fixed) / q.a_stage_bytes);
+  int fixed = 0;
+  static const int gm_dbg = [] { const char* e = getenv("MTB200_GM_DBG"); return e ? atoi(e) : 0; }();  // bit 1: quarters always
+  for (q.hsplit = (gm_dbg & 2) ? 1 : 0; q.hsplit < 2; ++q.hsplit) {
+    q.out_half_bytes = gm_align1k((long long)q.bd * ((q.hsplit ? 1 : p.os[1]) * q.bh) * (p.os[2] * q.bw) * orowb);
+    fixed = q.w_bytes + p.os[0] * q.out_half_bytes + 1024;
+    q.stages = min(GM_MAX_STAGES, (budget - fixed) / q.a_stage_bytes);
+    if (q.stages >= 4 || p.os[1] == 1) break;
+  }
+  if (q.hsplit > 1) q.hsplit = 1;
   if (q.stages < 2) return MTB200_ERR_UNSUPPORTED;
   q.accumulate = p.accumulate;
+  {  // experiments only (timing, wrong results): MTB200_GM_DBG=1 stores instead of reduce-adding
+    static const int dbg = [] { const char* e = getenv("MTB200_GM_DBG"); return e ? atoi(e) : 0; }();
+    if (dbg & 1) q.accumulate = 0;
+  }
   q.is_f16 = p.dtype == MTB200_F16;
   {
     cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.Di, (cuuint64_t)p.B};
@@ -365,17 +410,21 @@ int conv_gm_umma(const mtb200_conv_params& p, cudaStream_t s) {
     cuuint32_t box[3] = {(cuuint32_t)q.KC, (cuuint32_t)p.Cout, 1};
     if (!umma_encode_map(&q.w_map, p.dtype, 3, (void*)p.w, dims, strides, box, rowb)) return MTB200_ERR_CUDA;
   }
-  for (int r0 = 0; r0 < p.os[0]; ++r0) {
-    // output voxels with d = os0 * qd + r0: base shifted by r0 planes, d stride multiplied by os0
-    const long long ext_d = (p.Dof - r0 + p.os[0] - 1) / p.os[0];
-    cuuint64_t dims[5] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wof, (cuuint64_t)p.Hof, (cuuint64_t)ext_d, (cuuint64_t)p.B};
-    cuuint64_t strides[4] = {(cuuint64_t)p.out_ldc * 2, (cuuint64_t)p.Wof * p.out_ldc * 2,
-                             (cuuint64_t)p.Hof * p.Wof * p.out_ldc * 2 * p.os[0],
-                             (cuuint64_t)p.Dof * p.Hof * p.Wof * p.out_ldc * 2};
-    cuuint32_t box[5] = {(cuuint32_t)p.Cout, (cuuint32_t)(p.os[2] * q.bw), (cuuint32_t)(p.os[1] * q.bh), (cuuint32_t)q.bd, 1};
-    uint8_t* base = (uint8_t*)p.out + ((size_t)r0 * p.Hof * p.Wof * p.out_ldc + p.out_coff) * 2;
-    if (!umma_encode_map(&q.o_map[r0], p.dtype, 5, base, dims, strides, box, orowb)) return MTB200_ERR_CUDA;
-  }
+  for (int r0 = 0; r0 < p.os[0]; ++r0)
+    for (int r1 = 0; r1 < (q.hsplit ? p.os[1] : 1); ++r1) {
+      const int hs = q.hsplit ? p.os[1] : 1;  // h stride of the stored sub-lattice
+      // output voxels with d = os0 * qd + r0, h = os1 * qh + r1: base shifted by r0 planes and r1 lines, the d and h
+      // strides multiplied by os0, os1
+      const long long ext_d = (p.Dof - r0 + p.os[0] - 1) / p.os[0];
+      const long long ext_h = (p.Hof - r1 + hs - 1) / hs;
+      cuuint64_t dims[5] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wof, (cuuint64_t)ext_h, (cuuint64_t)ext_d, (cuuint64_t)p.B};
+      cuuint64_t strides[4] = {(cuuint64_t)p.out_ldc * 2, (cuuint64_t)p.Wof * p.out_ldc * 2 * hs,
+                               (cuuint64_t)p.Hof * p.Wof * p.out_ldc * 2 * p.os[0],
+                               (cuuint64_t)p.Dof * p.Hof * p.Wof * p.out_ldc * 2};
+      cuuint32_t box[5] = {(cuuint32_t)p.Cout, (cuuint32_t)(p.os[2] * q.bw), (cuuint32_t)((p.os[1] / hs) * q.bh), (cuuint32_t)q.bd, 1};
+      uint8_t* base = (uint8_t*)p.out + (((size_t)r0 * p.Hof + r1) * p.Wof * p.out_ldc + p.out_coff) * 2;
+      if (!umma_encode_map(&q.o_map[2 * r0 + r1], p.dtype, 5, base, dims, strides, box, orowb)) return MTB200_ERR_CUDA;
+    }
   const int smem = q.stages * q.a_stage_bytes + fixed;
   const int gx = (int)min((long long)q.ntiles, (long long)num_sms());
   cudaError_t e;
