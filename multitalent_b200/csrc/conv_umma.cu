@@ -577,24 +577,25 @@ constexpr int WG_MAX_ASTAGES = 8;
 
 struct UmmaWgradParams {
   CUtensorMap x_maps[8];
-  CUtensorMap dy_map;
-  CUtensorMap dy_maps_merged[MTB200_MAX_GROUPS];  // merge mode: one dY lattice per tap group
+  // One kernel launch covers `nlaunch` independent sub-problems ("slots", blockIdx.z / nz): the tap groups of a
+  // multi-group problem (each with its own dY lattice) -- or, in merge mode, runs of `merge_ng` groups side by side in N.
+  CUtensorMap dy_maps[MTB200_MAX_GROUPS];         // dY lattice of group g (merge mode: slot l uses groups l*merge_ng ...)
   int merge_ng, merge_cout;                       // merge mode: groups side by side in N (N = ng * Cout), else 0
-  int merge_widx[MTB200_MAX_GROUPS];
-  int merge_off[MTB200_MAX_GROUPS][3];
+  int grp_widx[MTB200_MAX_GROUPS];                // merge mode: weight slice of group g
+  int grp_off[MTB200_MAX_GROUPS][3];              // dY brick offset of group g
+  int slot_tap_begin[MTB200_MAX_GROUPS];          // first tap of slot l (every slot has the same number of taps)
+  int nz;                                         // N tiles per slot
   float* dw;
   int B, tiles_d, tiles_h, tiles_w, bd, bh, bw;
   long long nbricks;
   int bricks_per_cta;
   int Cin, Cout;            // padded channel counts
   int cbx, cby, BN;         // block widths (channels) of the X / dY boxes, N tile
-  int tap_begin, tap_end;   // taps of this launch (one group)
   int blocks_per_tap;       // Cin / cbx
   int nblocks;              // (tap_end - tap_begin) * blocks_per_tap
   int blocks_per_tile;      // 128 / cbx
   int ntiles, tiles_per_cta;
   int astages, tmem_cols;
-  int dy_off[3];
   int tap_map[MTB200_MAX_TAPS];
   int tap_coff[MTB200_MAX_TAPS][3];
   int tap_widx[MTB200_MAX_TAPS];
@@ -635,7 +636,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) wgrad_taps_umma_kernel(const __
   const long long brick1 = min(p.nbricks, brick0 + p.bricks_per_cta);
   const int tile0 = blockIdx.y * p.tiles_per_cta;
   const int tile1 = min(p.ntiles, tile0 + p.tiles_per_cta);
-  const int n0 = blockIdx.z * p.BN;
+  const int slot = (int)blockIdx.z / p.nz;
+  const int n0 = ((int)blockIdx.z - slot * p.nz) * p.BN;
+  const int tap_begin = p.slot_tap_begin[slot];
   const int nbricks = (int)max(0LL, brick1 - brick0);
   const int ntl = tile1 - tile0;
 
@@ -674,15 +677,16 @@ __global__ void __launch_bounds__(UM_THREADS, 1) wgrad_taps_umma_kernel(const __
           mbar_expect_tx(&b_full[bs], WG_KB * p.BN * 2);
           if (p.merge_ng) {  // one dY brick per tap group (its own output lattice), side by side along N
             const int nblk = p.merge_cout / p.cby;
-            for (int j = 0; j < p.merge_ng; ++j)
+            for (int j = 0; j < p.merge_ng; ++j) {
+              const int g = slot * p.merge_ng + j;
               for (int h = 0; h < nblk; ++h)
-                tma_load_5d(b_base + (size_t)bs * b_stage_bytes + (size_t)(j * nblk + h) * yblock_bytes,
-                            &p.dy_maps_merged[j], &b_full[bs], h * p.cby, w0 + p.merge_off[j][2], h0 + p.merge_off[j][1],
-                            d0 + p.merge_off[j][0], b);
+                tma_load_5d(b_base + (size_t)bs * b_stage_bytes + (size_t)(j * nblk + h) * yblock_bytes, &p.dy_maps[g],
+                            &b_full[bs], h * p.cby, w0 + p.grp_off[g][2], h0 + p.grp_off[g][1], d0 + p.grp_off[g][0], b);
+            }
           } else {
             for (int j = 0; j < p.BN / p.cby; ++j)
-              tma_load_5d(b_base + (size_t)bs * b_stage_bytes + (size_t)j * yblock_bytes, &p.dy_map, &b_full[bs],
-                          n0 + j * p.cby, w0 + p.dy_off[2], h0 + p.dy_off[1], d0 + p.dy_off[0], b);
+              tma_load_5d(b_base + (size_t)bs * b_stage_bytes + (size_t)j * yblock_bytes, &p.dy_maps[slot], &b_full[bs],
+                          n0 + j * p.cby, w0 + p.grp_off[slot][2], h0 + p.grp_off[slot][1], d0 + p.grp_off[slot][0], b);
           }
         }
         __syncwarp();
@@ -695,7 +699,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) wgrad_taps_umma_kernel(const __
             for (int i = 0; i < p.blocks_per_tile; ++i) {
               int gb = tl * p.blocks_per_tile + i;
               if (gb >= p.nblocks) gb = 0;  // padding rows of the last tile: duplicate block 0 (never written back)
-              const int tp = p.tap_begin + gb / p.blocks_per_tap;
+              const int tp = tap_begin + gb / p.blocks_per_tap;
               const int c0 = (gb % p.blocks_per_tap) * p.cbx;
               tma_load_5d(a_base + (size_t)as * a_stage_bytes + (size_t)i * xblock_bytes, &p.x_maps[p.tap_map[tp]],
                           &a_full[as], c0, w0 + p.tap_coff[tp][2], h0 + p.tap_coff[tp][1], d0 + p.tap_coff[tp][0], b);
@@ -761,7 +765,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) wgrad_taps_umma_kernel(const __
     for (int tl = 0; tl < ntl; ++tl) {
       const int gb = (tile0 + tl) * p.blocks_per_tile + row / p.cbx;
       const bool valid = gb < p.nblocks;
-      const int tp = p.tap_begin + (valid ? gb / p.blocks_per_tap : 0);
+      const int tp = tap_begin + (valid ? gb / p.blocks_per_tap : 0);
       const int ci = (valid ? (gb % p.blocks_per_tap) * p.cbx : 0) + row % p.cbx;
       float* dst = p.dw + ((long long)p.tap_widx[tp] * p.Cout + n0) * p.Cin + ci;
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
@@ -771,7 +775,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) wgrad_taps_umma_kernel(const __
           float* dc = dst + (long long)c0 * p.Cin;
           if (p.merge_ng) {  // column block -> (tap group, channel)
             const int g = c0 / p.merge_cout;
-            dc = p.dw + ((long long)p.merge_widx[g] * p.Cout + (c0 - g * p.merge_cout)) * p.Cin + ci;
+            dc = p.dw + ((long long)p.grp_widx[slot * p.merge_ng + g] * p.Cout + (c0 - g * p.merge_cout)) * p.Cin + ci;
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -899,11 +903,8 @@ int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
   cudaError_t ce = cudaFuncSetAttribute(wgrad_taps_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (ce != cudaSuccess) { set_error("wgrad_taps(umma): cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return MTB200_ERR_CUDA; }
 
-  static thread_local CUtensorMap group_maps[MTB200_MAX_GROUPS];
-  int group_off[MTB200_MAX_GROUPS][3];
-  if (merge) {
-    q.merge_ng = merge_per;
-    q.merge_cout = p.Cout;
+  // dY lattice of every tap group: out coordinate = o * os + ooff
+  {
     const int ODims[3] = {p.Dof, p.Hof, p.Wof};
     for (int g = 0; g < p.ngroups; ++g) {
       int par[3];
@@ -912,7 +913,7 @@ int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
       for (int k = 0; k < 3; ++k) {
         const int off = p.group_ooff[g][k];
         par[k] = ((off % p.os[k]) + p.os[k]) % p.os[k];
-        group_off[g][k] = floor_div(off - par[k], p.os[k]);
+        q.grp_off[g][k] = floor_div(off - par[k], p.os[k]);
         ext[k] = (ODims[k] - par[k] + p.os[k] - 1) / p.os[k];
         if (ext[k] < 1) { set_error("wgrad_taps(umma): empty dY lattice"); return MTB200_ERR_UNSUPPORTED; }
       }
@@ -923,55 +924,48 @@ int wgrad_taps_umma(const mtb200_wgrad_params& p, cudaStream_t s) {
       strides[2] = (cuuint64_t)p.Hof * p.Wof * p.out_ldc * e * p.os[0];
       strides[3] = (cuuint64_t)p.Dof * p.Hof * p.Wof * p.out_ldc * e;
       uint8_t* base = (uint8_t*)p.dy + ((((long long)par[0] * p.Hof + par[1]) * p.Wof + par[2]) * p.out_ldc + p.out_coff) * e;
-      if (!encode_map(enc, &group_maps[g], dt, 5, base, dims, strides, box, q.cby * 2)) return MTB200_ERR_CUDA;
+      if (!encode_map(enc, &q.dy_maps[g], dt, 5, base, dims, strides, box, q.cby * 2)) return MTB200_ERR_CUDA;
+      q.grp_widx[g] = p.group_tap_begin[g + 1] > p.group_tap_begin[g] ? p.tap_widx[p.group_tap_begin[g]] : 0;
     }
   }
-  // one launch per group (the dY brick depends on the group's output offset); merge mode: `merge_per` groups per launch
-  for (int g = 0; g < p.ngroups; g += (merge ? merge_per : 1)) {
-    q.tap_begin = p.group_tap_begin[g];
-    q.tap_end = p.group_tap_begin[g + 1];
-    for (int j = 0; j < merge_per && merge; ++j) {
-      q.dy_maps_merged[j] = group_maps[g + j];
-      q.merge_widx[j] = p.tap_widx[p.group_tap_begin[g + j]];
-      for (int k = 0; k < 3; ++k) q.merge_off[j][k] = group_off[g + j][k];
-    }
-    if (q.tap_end == q.tap_begin) continue;
-    q.nblocks = (q.tap_end - q.tap_begin) * q.blocks_per_tap;
-    q.ntiles = (q.nblocks + q.blocks_per_tile - 1) / q.blocks_per_tile;
-    // dY map for this group: out coordinate = o * os + ooff
-    {
-      int par[3], coord[3];
-      const int ODims[3] = {p.Dof, p.Hof, p.Wof};
-      cuuint64_t dims[5], strides[4];
-      long long ext[3];
-      for (int k = 0; k < 3; ++k) {
-        const int off = p.group_ooff[g][k];
-        par[k] = ((off % p.os[k]) + p.os[k]) % p.os[k];
-        coord[k] = floor_div(off - par[k], p.os[k]);
-        ext[k] = (ODims[k] - par[k] + p.os[k] - 1) / p.os[k];
-        if (ext[k] < 1) { set_error("wgrad_taps(umma): empty dY lattice"); return MTB200_ERR_UNSUPPORTED; }
-        q.dy_off[k] = coord[k];
+  if (merge) { q.merge_ng = merge_per; q.merge_cout = p.Cout; }
+  // Slots: one per tap group (merge mode: per run of `merge_per` groups).  Groups with the same number of taps share ONE
+  // launch (grid.z = slots x N tiles) -- the transposed convolutions of the deep levels were 4 - 8 serialised launches
+  // of ~30 CTAs each; a group without taps has nothing to do.  Groups with different tap counts: one launch each.
+  const int per = merge ? merge_per : 1;
+  const int nslots_all = p.ngroups / per;
+  bool uniform = true;
+  for (int g = 0; g < p.ngroups; ++g)
+    uniform = uniform && (p.group_tap_begin[g + 1] - p.group_tap_begin[g]) == (p.group_tap_begin[1] - p.group_tap_begin[0]);
+  // the kernel indexes dy_maps / grp_off by slot (or slot * merge_ng + j): a launch of a single slot l > 0 moves that
+  // slot's entries to the front
+  const UmmaWgradParams all = q;
+  for (int l0 = 0; l0 < nslots_all; l0 += (uniform ? nslots_all : 1)) {
+    const int nslots = uniform ? nslots_all : 1;
+    for (int l = 0; l < nslots; ++l) {
+      q.slot_tap_begin[l] = p.group_tap_begin[(l0 + l) * per];
+      for (int j = 0; j < per; ++j) {
+        const int gs = (l0 + l) * per + j, gd = l * per + j;
+        q.dy_maps[gd] = all.dy_maps[gs];
+        q.grp_widx[gd] = all.grp_widx[gs];
+        for (int k = 0; k < 3; ++k) q.grp_off[gd][k] = all.grp_off[gs][k];
       }
-      cuuint32_t box[5] = {(cuuint32_t)q.cby, (cuuint32_t)q.bw, (cuuint32_t)q.bh, (cuuint32_t)q.bd, 1};
-      dims[0] = p.Cout; dims[1] = ext[2]; dims[2] = ext[1]; dims[3] = ext[0]; dims[4] = p.B;
-      strides[0] = (cuuint64_t)p.out_ldc * e * p.os[2];
-      strides[1] = (cuuint64_t)p.Wof * p.out_ldc * e * p.os[1];
-      strides[2] = (cuuint64_t)p.Hof * p.Wof * p.out_ldc * e * p.os[0];
-      strides[3] = (cuuint64_t)p.Dof * p.Hof * p.Wof * p.out_ldc * e;
-      uint8_t* base = (uint8_t*)p.dy + ((((long long)par[0] * p.Hof + par[1]) * p.Wof + par[2]) * p.out_ldc + p.out_coff) * e;
-      if (!encode_map(enc, &q.dy_map, dt, 5, base, dims, strides, box, q.cby * 2)) return MTB200_ERR_CUDA;
     }
+    const int ntaps_slot = p.group_tap_begin[l0 * per + 1] - p.group_tap_begin[l0 * per];
+    if (ntaps_slot == 0) continue;
+    q.nblocks = ntaps_slot * q.blocks_per_tap;
+    q.ntiles = (q.nblocks + q.blocks_per_tile - 1) / q.blocks_per_tile;
     q.tiles_per_cta = min(q.ntiles, max_tiles_tmem);
     const int tile_groups = (q.ntiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
     q.tmem_cols = 32;
     while (q.tmem_cols < q.tiles_per_cta * q.BN) q.tmem_cols *= 2;
-    const int nz = merge ? 1 : p.Cout / q.BN;
+    q.nz = merge ? 1 : p.Cout / q.BN;
     // split over voxel bricks so that the grid covers the machine about twice, with >= 4 bricks per CTA
-    long long want = max(1LL, (2LL * num_sms()) / ((long long)tile_groups * nz));
+    long long want = max(1LL, (2LL * num_sms()) / ((long long)tile_groups * q.nz * nslots));
     long long ksplit = min(want, max(1LL, q.nbricks / 4));
     q.bricks_per_cta = (int)((q.nbricks + ksplit - 1) / ksplit);
     ksplit = (q.nbricks + q.bricks_per_cta - 1) / q.bricks_per_cta;
-    dim3 grid((unsigned)ksplit, tile_groups, nz);
+    dim3 grid((unsigned)ksplit, tile_groups, q.nz * nslots);
     launch_pdl(wgrad_taps_umma_kernel, dim3(grid), dim3(UM_THREADS), (size_t)(smem), s, q);
     int r = check_launch("wgrad_taps_umma");
     if (r) return r;
