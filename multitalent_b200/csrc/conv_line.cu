@@ -416,8 +416,36 @@ static cudaError_t launch_line(const LineParams& q, dim3 grid, int smem, cudaStr
 
 static inline int ln_align1k(long long v) { return (int)(((v + 1023) / 1024) * 1024); }
 
+static int conv_line_launch(const mtb200_conv_params& p, cudaStream_t s, int w_pitch, int w_coff);
+
 // Returns MTB200_ERR_UNSUPPORTED when the problem is outside this kernel's envelope (caller falls back).
+//
+// 128 input channels (the first decoder convolution of the second level, 128 -> 64 at 96x80x64: its 9 x 96 x 128 weight
+// tiles per CTA would need 221 KB): TWO passes over one 64-channel half of the input each, conv(x) = conv_lo(x[:64]) +
+// conv_hi(x[64:]) -- the first stores bias + partial sum in the output's 16-bit type, the second adds its half on top
+// (`accumulate`) and takes the InstanceNorm statistics of the final values.  One extra rounding of the partial sum
+// (<= 0.5 ulp of the 16-bit type), 0.25 GB of extra traffic.  Measured 0.91 ms against 1.01 ms on the CTA-pair per-tap
+// kernel (the 64-channel halves of 256-byte rows stream slower than a dense 64-channel tensor): not worth a second
+// rounding, so OFF unless MTB200_LINE_2PASS=1.
 int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s) {
+  static const int two_pass = [] { const char* e = getenv("MTB200_LINE_2PASS"); return (e && atoi(e) == 1) ? 1 : 0; }();
+  if (two_pass && p.Cin == 128 && !p.in_split && !p.red && !p.xform) {
+    mtb200_conv_params a = p;
+    a.Cin = 64; a.stats = nullptr;
+    const int r = conv_line_launch(a, s, 128, 0);
+    if (r != MTB200_OK) return r;  // outside the envelope: nothing was launched
+    mtb200_conv_params b = p;
+    b.Cin = 64; b.in_coff = p.in_coff + 64; b.bias = nullptr; b.accumulate = 1;
+    const int r2 = conv_line_launch(b, s, 128, 64);
+    if (r2 == MTB200_ERR_UNSUPPORTED) { set_error("conv_line: second half of a two-pass launch refused"); return MTB200_ERR_CUDA; }
+    return r2;
+  }
+  return conv_line_launch(p, s, 0, 0);
+}
+
+// w_pitch / w_coff: the weights are a [tap][Cout][w_pitch] array of which this launch uses channels [w_coff, w_coff + Cin)
+// (0 = dense [tap][Cout][Cin])
+static int conv_line_launch(const mtb200_conv_params& p, cudaStream_t s, int w_pitch, int w_coff) {
   if (p.ngroups != 1) return MTB200_ERR_UNSUPPORTED;
   for (int k = 0; k < 3; ++k)
     if (p.is[k] != 1 || p.os[k] != 1 || p.group_ooff[0][k] != 0) return MTB200_ERR_UNSUPPORTED;
@@ -508,9 +536,10 @@ int conv_line_umma(const mtb200_conv_params& p, cudaStream_t s) {
     int n_widx = 0;
     for (int t = 0; t < p.ntaps; ++t) n_widx = max(n_widx, p.tap_widx[t] + 1);
     cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, (cuuint64_t)n_widx};
-    cuuint64_t strides[2] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Cin * p.Cout * 2};
+    const long long wp = w_pitch ? w_pitch : p.Cin;
+    cuuint64_t strides[2] = {(cuuint64_t)wp * 2, (cuuint64_t)wp * p.Cout * 2};
     cuuint32_t box[3] = {(cuuint32_t)q.kcw, (cuuint32_t)LN_BN, 1};
-    if (!umma_encode_map(&q.w_map, p.dtype, 3, (void*)p.w, dims, strides, box, rowb)) return MTB200_ERR_CUDA;
+    if (!umma_encode_map(&q.w_map, p.dtype, 3, (uint8_t*)p.w + (size_t)w_coff * 2, dims, strides, box, rowb)) return MTB200_ERR_CUDA;
   }
   q.out = p.out; q.bias = p.bias; q.stats = p.stats;
   // fused reduction of the producing layer's InstanceNorm backward (data-gradient launches; MTB200_FUSE_RED=0: off)
