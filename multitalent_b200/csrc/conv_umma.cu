@@ -103,9 +103,16 @@ struct UmmaConvParams {
   int tap_coff[MTB200_MAX_TAPS][3];
   int tap_widx[MTB200_MAX_TAPS];
   int nkc, KC, BN, stages, tmem_cols;
-  int ny, ncombo, ctas_per_combo;   // N tiles, (N tile, group) combinations, persistent CTAs per combination
+  int ny, ncombo, ctas_per_combo;   // N tiles, (N tile, group, split) combinations, persistent CTAs per combination
+  int ngroups_k;                    // tap groups
   long long ntiles;                 // spatial tiles (all batches)
   int accumulate, is_f16;
+  // split over taps (deep levels: a handful of tiles would leave most SMs idle): combination = (N tile, group, split),
+  // split k accumulates taps [k * taps/nsplit, ...) and stores its fp32 partial tile into slab k of `scratch`
+  // ([nsplit][voxels][Cout]); split_reduce_kernel adds the slabs in a fixed order, + bias, rounds, stores, statistics
+  int nsplit;
+  float* scratch;
+  long long mtot;                   // output voxels (all batches)
 };
 
 // Persistent: CTA c owns the (N tile, tap group) combination c % ncombo and walks the spatial tiles c / ncombo,
@@ -143,11 +150,12 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
   // a "unit" is what one MMA chain covers: one spatial tile, or the pair's two consecutive tiles (2u, 2u + 1)
   const int unit_cta = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int combo = unit_cta % p.ncombo;
-  const int nb = combo % p.ny, g = combo / p.ny;
+  const int nb = combo % p.ny, g = (combo / p.ny) % p.ngroups_k, ks = combo / (p.ny * p.ngroups_k);
   const long long tile0 = unit_cta / p.ncombo;
   const long long nunits = PAIR ? (p.ntiles + 1) / 2 : p.ntiles;
   const int n0 = nb * p.BN;
-  const int tap_begin = p.group_tap_begin[g], tap_end = p.group_tap_begin[g + 1];
+  const int taps_per = (p.group_tap_begin[g + 1] - p.group_tap_begin[g]) / p.nsplit;  // host: divisible
+  const int tap_begin = p.group_tap_begin[g] + ks * taps_per, tap_end = tap_begin + taps_per;
   const int niter = (tap_end - tap_begin) * p.nkc;
   const long long tiles_per_b = (long long)p.tiles_d * p.tiles_h * p.tiles_w;
 
@@ -288,6 +296,14 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = s_bias[c0 + j];
         }
+        if (p.nsplit > 1) {  // fp32 partial tile of this tap split (no bias / statistics: split_reduce_kernel)
+          if (valid) {
+            float4* sc = reinterpret_cast<float4*>(p.scratch + ((size_t)ks * p.mtot + ovox) * p.Cout + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sc[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          continue;
+        }
         if (valid) {
           if (p.accumulate) {
             float o[8];
@@ -361,6 +377,64 @@ __global__ void __launch_bounds__(UMC_THREADS, 2) conv_taps_umma_kernel(const __
   }
 }
 
+// Second half of a tap-split launch: out[v][c] = round(bias[c] + sum_k scratch[k][v][c] (+ out[v][c])), slabs added in
+// the fixed order k = 0, 1, ... (run-to-run reproducible), InstanceNorm statistics of the rounded values.  Block =
+// (Cout / 8 channel groups) x rows; grid = (chunks of a sample's voxels, B).
+template <typename T>
+__global__ void __launch_bounds__(256) split_reduce_kernel(const float* __restrict__ scratch, int nsplit, long long mtot,
+                                                           int vox_per_b, int Cout, T* __restrict__ out, int out_ldc,
+                                                           int out_coff, const float* __restrict__ bias,
+                                                           double* __restrict__ stats, int accumulate, int chunk) {
+  pdl_wait();
+  __shared__ float s_red[256][17];
+  const int ncg = Cout >> 3;
+  const int rows = 256 / ncg;
+  const int cg = threadIdx.x % ncg, r = threadIdx.x / ncg;
+  const int b = blockIdx.y;
+  const int v0 = blockIdx.x * chunk, v1 = min(vox_per_b, v0 + chunk);
+  float bs[8], su[8], sq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { bs[j] = bias ? bias[cg * 8 + j] : 0.f; su[j] = 0.f; sq[j] = 0.f; }
+  if (r < rows) {
+    for (int v = v0 + r; v < v1; v += rows) {
+      const long long gv = (long long)b * vox_per_b + v;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int k = 0; k < nsplit; ++k) {
+        float x[8];
+        load8<float>(scratch + ((size_t)k * mtot + gv) * Cout + cg * 8, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += x[j];
+      }
+      T* o = out + gv * out_ldc + out_coff + cg * 8;
+      float old[8];
+      if (accumulate) load8<T>(o, old);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += bs[j] + (accumulate ? old[j] : 0.f);
+      store8<T>(o, acc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x = Traits<T>::round(acc[j]);
+        su[j] += x;
+        sq[j] = fmaf(x, x, sq[j]);
+      }
+    }
+  }
+  if (stats) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s_red[threadIdx.x][j] = su[j]; s_red[threadIdx.x][8 + j] = sq[j]; }
+    __syncthreads();
+    // one thread per (channel, statistic): fixed summation order over the rows
+    for (int i = threadIdx.x; i < Cout * 2; i += 256) {
+      const int c = i >> 1, which = i & 1;
+      float t = 0.f;
+      for (int rr = 0; rr < rows; ++rr) t += s_red[rr * ncg + (c >> 3)][which * 8 + (c & 7)];
+      if (t != 0.f) atomicAdd(stats + ((long long)b * Cout + c) * 2 + which, (double)t);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
@@ -380,6 +454,29 @@ static bool encode_map(EncodeTiledFn enc, CUtensorMap* m, CUtensorMapDataType dt
     return false;
   }
   return true;
+}
+
+// second half of a tap-split launch (see UmmaConvParams::nsplit); frees the slabs in stream order
+static int split_reduce(const mtb200_conv_params& p, int nsplit, float* scratch, int status, cudaStream_t s) {
+  if (status == MTB200_OK) {
+    const long long M = (long long)p.B * p.Do * p.Ho * p.Wo;
+    const int vox_per_b = p.Do * p.Ho * p.Wo;
+    const int rows = 256 / (p.Cout / 8);
+    // ~4 blocks per SM over all samples; a block walks `chunk` voxels, `rows` at a time
+    int chunks = max(1, min((vox_per_b + rows - 1) / rows, (4 * num_sms() + p.B - 1) / p.B));
+    const int chunk = (vox_per_b + chunks - 1) / chunks;
+    chunks = (vox_per_b + chunk - 1) / chunk;
+    dim3 grid((unsigned)chunks, (unsigned)p.B, 1);
+    if (p.dtype == MTB200_BF16)
+      launch_pdl(split_reduce_kernel<__nv_bfloat16>, grid, dim3(256), (size_t)0, s, (const float*)scratch, nsplit, M, vox_per_b,
+                 p.Cout, (__nv_bfloat16*)p.out, p.out_ldc, p.out_coff, p.bias, p.stats, p.accumulate, chunk);
+    else
+      launch_pdl(split_reduce_kernel<__half>, grid, dim3(256), (size_t)0, s, (const float*)scratch, nsplit, M, vox_per_b,
+                 p.Cout, (__half*)p.out, p.out_ldc, p.out_coff, p.bias, p.stats, p.accumulate, chunk);
+    status = check_launch("split_reduce");
+  }
+  cudaFreeAsync(scratch, s);
+  return status;
 }
 
 int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
@@ -528,8 +625,55 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
   if (per_sm == 1) smem = max(smem, 116 * 1024);
   q.ntiles = ntiles;
   q.ny = p.Cout / q.BN;
-  q.ncombo = q.ny * p.ngroups;
+  q.ngroups_k = p.ngroups;
+  q.nsplit = 1;
+  q.mtot = M;
   const int slots = num_sms() * per_sm;
+  // Tap split (MTB200_TAPS_SPLIT=0: off): the deep levels have 8 - 30 tiles, so most SMs would idle while a few CTAs walk
+  // 27 taps x Cin / 64 chunks each.  Split the taps into nsplit equal runs (fp32 partial slabs + a reduce kernel) when the
+  // unsplit launch would fill less than half of the machine; nsplit minimises rounds / nsplit + the reduce pass's share.
+  float* scratch = nullptr;
+  {
+    static const int split_on = [] { const char* e = getenv("MTB200_TAPS_SPLIT"); return e ? atoi(e) : 1; }();  // > 1: forced
+    const long long units = (pair ? (ntiles + 1) / 2 : ntiles) * q.ny;
+    const long long uslots = pair ? slots / 2 : slots;
+    bool ok = split_on && p.ngroups == 1 && units * 2 <= uslots && p.Cout % 16 == 0 && p.Cout <= 2048 &&
+              p.Dof == p.Do && p.Hof == p.Ho && p.Wof == p.Wo;
+    for (int k = 0; k < 3; ++k) ok = ok && p.os[k] == 1 && p.group_ooff[0][k] == 0;
+    if (ok) {
+      const int nt = p.group_tap_begin[1] - p.group_tap_begin[0];
+      // relative cost model fitted to tools/conv_bench.py (profiles/r2w_tap_split.txt): rounds / nsplit for the main loop,
+      // 0.05 per split for the slabs' traffic; unsplit = 1, a split must promise < 0.85
+      double best = 0.85;
+      for (int ns = 2; ns <= nt; ++ns) {
+        if (nt % ns) continue;
+        const long long rounds = (units * ns + uslots - 1) / uslots;
+        const double cost = (double)rounds / ns + 0.05 * ns;
+        if (cost < best) { best = cost; q.nsplit = ns; }
+      }
+      if (split_on > 1 && nt % split_on == 0) q.nsplit = split_on;
+    }
+    if (q.nsplit > 1) {
+      const size_t bytes = (size_t)q.nsplit * (size_t)M * p.Cout * sizeof(float);
+      // the device's default pool gives freed blocks back to the driver at the next synchronisation unless told to keep
+      // them (a fresh physical allocation per call costs ~0.3 ms)
+      static thread_local int pool_dev = -1;
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (pool_dev != dev) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+          unsigned long long keep = 1ull << 30;
+          cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        pool_dev = dev;
+      }
+      if (cudaMallocAsync(&scratch, bytes, s) != cudaSuccess) { cudaGetLastError(); q.nsplit = 1; scratch = nullptr; }
+    }
+    if (q.nsplit > 1) { q.scratch = scratch; q.bias = nullptr; q.stats = nullptr; q.accumulate = 0; }
+  }
+  q.ncombo = q.ny * p.ngroups * q.nsplit;
   if (q.ncombo > slots) { set_error("conv_taps(umma): %d (N tile, group) combinations exceed the CTA slots", q.ncombo); return MTB200_ERR_UNSUPPORTED; }
   cudaError_t e;
   if (pair) {
@@ -545,8 +689,9 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
       e = cudaFuncSetAttribute(conv_taps_umma_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e == cudaSuccess) e = launch_pdl_cluster(conv_taps_umma_kernel<__half, true>, grid, dim3(UMC_THREADS), (size_t)smem, s, 2, q);
     }
-    if (e != cudaSuccess) { set_error("conv_taps(umma, pair): launch: %s", cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
-    return check_launch("conv_taps_umma(pair)");
+    if (e != cudaSuccess) { set_error("conv_taps(umma, pair): launch: %s", cudaGetErrorString(e)); if (scratch) cudaFreeAsync(scratch, s); return MTB200_ERR_CUDA; }
+    const int r = check_launch("conv_taps_umma(pair)");
+    return scratch ? split_reduce(p, q.nsplit, scratch, r, s) : r;
   }
   q.ctas_per_combo = (int)min((long long)(slots / q.ncombo), ntiles);
   dim3 grid((unsigned)(q.ctas_per_combo * q.ncombo), 1, 1);
@@ -557,8 +702,9 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
     e = cudaFuncSetAttribute(conv_taps_umma_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) launch_pdl(conv_taps_umma_kernel<__half, false>, dim3(grid), dim3(UMC_THREADS), (size_t)(smem), s, q);
   }
-  if (e != cudaSuccess) { set_error("conv_taps(umma): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MTB200_ERR_CUDA; }
-  return check_launch("conv_taps_umma");
+  if (e != cudaSuccess) { set_error("conv_taps(umma): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); if (scratch) cudaFreeAsync(scratch, s); return MTB200_ERR_CUDA; }
+  const int r = check_launch("conv_taps_umma");
+  return scratch ? split_reduce(p, q.nsplit, scratch, r, s) : r;
 }
 
 // =====================================================================================================================

@@ -24,6 +24,8 @@ LAYERS = {
     "l3b": (240, 240, (4, 24, 20, 16), 0),
     "l3d": (480, 240, (4, 24, 20, 16), 240),
     "l4b": (320, 320, (4, 12, 10, 8), 0),
+    "l4d": (640, 320, (4, 12, 10, 8), 320),
+    "l5b": (320, 320, (4, 12, 5, 4), 0),
 }
 
 
