@@ -456,6 +456,8 @@ static bool encode_map(EncodeTiledFn enc, CUtensorMap* m, CUtensorMapDataType dt
   return true;
 }
 
+static bool g_pair_refused = false;  // set when a cluster launch of the PAIR instantiation was refused
+
 // second half of a tap-split launch (see UmmaConvParams::nsplit); frees the slabs in stream order
 static int split_reduce(const mtb200_conv_params& p, int nsplit, float* scratch, int status, cudaStream_t s) {
   if (status == MTB200_OK) {
@@ -544,7 +546,7 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
         if (p.Cout % c == 0) { bn2 = c; break; }
     }
     eligible = eligible && bn2 >= 32;
-    if (mode != 0) pair = eligible;
+    if (mode != 0 && !g_pair_refused) pair = eligible;
     if (pair) q.BN = bn2;
   }
   q.tmem_cols = 32;
@@ -689,7 +691,14 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
       e = cudaFuncSetAttribute(conv_taps_umma_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e == cudaSuccess) e = launch_pdl_cluster(conv_taps_umma_kernel<__half, true>, grid, dim3(UMC_THREADS), (size_t)smem, s, 2, q);
     }
-    if (e != cudaSuccess) { set_error("conv_taps(umma, pair): launch: %s", cudaGetErrorString(e)); if (scratch) cudaFreeAsync(scratch, s); return MTB200_ERR_CUDA; }
+    if (e != cudaSuccess) {
+      // a device / driver that refuses 2-CTA cluster launches (MIG slices, cluster scheduling disabled): nothing was
+      // launched, use the single-CTA instantiation from now on
+      cudaGetLastError();
+      if (scratch) cudaFreeAsync(scratch, s);
+      g_pair_refused = true;
+      return conv_taps_umma(p, s);
+    }
     const int r = check_launch("conv_taps_umma(pair)");
     return scratch ? split_reduce(p, q.nsplit, scratch, r, s) : r;
   }

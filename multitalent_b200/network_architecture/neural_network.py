@@ -14,6 +14,7 @@ behaviour as the reference; what differs is where the work happens:
 """
 from typing import List, Tuple, Union
 
+import os
 import numpy as np
 import torch
 from torch import nn
@@ -237,7 +238,7 @@ class SegmentationNetwork(NeuralNetwork):
         cin_p = self.native_input_channels_padded()
         pd, ph, pw = patch_size
         # TB tiles go through the network as one batch (the deep levels of a single 192x160x128 tile cannot fill 148 SMs)
-        TB = max(1, int(getattr(self, "inference_tile_batch", 8)))
+        TB = max(1, int(os.environ.get("MTB200_INFER_TB", 0)) or int(getattr(self, "inference_tile_batch", 8)))
         tile = torch.empty((TB, pd, ph, pw, cin_p), dtype=dt, device=dev)
         st = L.stream_ptr()
         work = [(sx, sy, sz, mi, dims) for sx in steps[0] for sy in steps[1] for sz in steps[2]
