@@ -83,6 +83,23 @@ def taps_conv_fwd(kernel, stride) -> TapTable:
     return TapTable(taps, [0, len(taps)], [(0, 0, 0)], tuple(stride), (1, 1, 1))
 
 
+_WPAIR_TAPS = {}
+
+
+def wpair_taps(stride) -> TapTable:
+    """Conv3d(3x3x3, stride (sd, sh, 2)) on the [.., W/2, 2C] pair view of its input: output voxel q reads the pair q
+    (taps kx = 1, 2) and the odd voxel of the pair q - 1 (kx = 0); the w stride of the view is 1."""
+    key = tuple(stride)
+    if key not in _WPAIR_TAPS:
+        taps = []
+        for kz in range(3):
+            for ky in range(3):
+                taps.append(((kz - 1, ky - 1, 0), (kz * 3 + ky) * 2))
+                taps.append(((kz - 1, ky - 1, -1), (kz * 3 + ky) * 2 + 1))
+        _WPAIR_TAPS[key] = TapTable(taps, [0, len(taps)], [(0, 0, 0)], (stride[0], stride[1], 1), (1, 1, 1))
+    return _WPAIR_TAPS[key]
+
+
 def taps_conv_dgrad(kernel, stride) -> TapTable:
     """Data gradient of the above: d_in[s*q + r] = sum_{k: (r - k + p) % s == 0} W[k]^T dy[q + (r - k + p)/s].
     One group per residue class r (prod(stride) groups); every input voxel is written exactly once."""
@@ -445,6 +462,8 @@ class Engine:
         # from the head's input (mtb200_head_fwd_stats) and the fused backward recomputes it.  The network then returns a
         # zero-stride placeholder for that output; only multitalent_loss(engine=...) may consume it.
         self.planar_concat = os.environ.get("MTB200_PLANAR", "1") != "0"
+        # stride-2 forward on the w-pair view of a dense 32-channel input (Engine.conv / wpair_taps)
+        self.wpairs = os.environ.get("MTB200_WPAIRS", "1") != "0"
         self.defer_head_fwd = os.environ.get("MTB200_DEFER_HEAD", "1") != "0"
         self.defer_heads = False
         self.deferred = {}       # placeholder pointer -> {"x": head input, "op": head}
@@ -595,9 +614,39 @@ class Engine:
                    info=(1, op.Cout_p, tuple(odims[1:]), op.ntap, (1, 1, 1), (1, 1, 1)))
             return out, stats
         grid = x.dims[1:] if op.transposed else odims[1:]
+        if self._use_wpairs(op, x):
+            # stride 2 along w on a dense 32-channel tensor: voxels (2q, 2q + 1) are ONE 128-byte row of the
+            # [B, D, H, W/2, 64] view of the same buffer -- 18 taps of 64 channels on dense rows instead of 27 taps of 32
+            # channels on every other 64-byte row (see wpair_taps)
+            B, D, H, W = x.dims
+            xv = Feat(x.buf.view(B, D, H, W // 2, 2 * x.ldc), 0, 2 * x.ldc, 2 * x.ldc)
+            self._conv_call(wpair_taps(op.stride), xv, self._wpair_weights(op), _padded(op.bias, op.Cout_p), out, grid,
+                            stats, False, 2 * op.Cin_p, op.Cout_p, flops=self.conv_flops(op, odims), tag="conv_fwd")
+            return out, stats
         self._conv_call(op.fwd_taps, x, op.packed(self.wdtype, False), _padded(op.bias, op.Cout_p), out, grid, stats,
                         False, op.Cin_p, op.Cout_p, flops=self.conv_flops(op, odims), tag="conv_fwd")
         return out, stats
+
+    def _use_wpairs(self, op: ConvOp, x: Feat) -> bool:
+        return (self.wpairs and not op.transposed and op.kernel == (3, 3, 3) and op.stride[2] == 2 and op.Cin_p == 32
+                and x.ldc == 32 and x.coff == 0 and (x.planar is None or x.half is not None) and x.xform is None and x.dims[3] % 2 == 0
+                and x.buf.is_contiguous() and self.dtype in (torch.bfloat16, torch.float16) and self.impl in (0, 2, 3))
+
+    def _wpair_weights(self, op: ConvOp):
+        """[18][Cout_p][64] from the packed [27][Cout_p][32]: slice (kz, ky, 0) = [W(kx=1) | W(kx=2)] (the pair at the
+        output's own position), slice (kz, ky, 1) = [0 | W(kx=0)] (the pair one to the left: only its odd voxel)."""
+        wp = op.packed(self.wdtype, False)
+        ver = (op.weight._version, _weights_epoch, op.weight.data_ptr(), wp.data_ptr())
+        hit = op._packed.get("wpair")
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        w4 = wp.view(3, 3, 3, op.Cout_p, 32)
+        wv = hit[1] if hit is not None else torch.zeros((3, 3, 2, op.Cout_p, 64), dtype=wp.dtype, device=wp.device)
+        wv[:, :, 0, :, :32] = w4[:, :, 1]
+        wv[:, :, 0, :, 32:] = w4[:, :, 2]
+        wv[:, :, 1, :, 32:] = w4[:, :, 0]
+        op._packed["wpair"] = (ver, wv)
+        return wv
 
     def finalize_norm(self, y: Feat, stats, gamma, beta, slope=LRELU_SLOPE):
         B = y.dims[0]
