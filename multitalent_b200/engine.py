@@ -100,6 +100,24 @@ def wpair_taps(stride) -> TapTable:
     return _WPAIR_TAPS[key]
 
 
+def _pair_convT_taps(kernel) -> TapTable:
+    """Forward tap table of the transposed convolution with kernel == stride == (k0, k1, 1) that a ConvTranspose3d with
+    kernel (k0, k1, 2) is on the w-pair view of its output."""
+    key = ("Tf",) + tuple(kernel)
+    if key not in _WPAIR_TAPS:
+        _WPAIR_TAPS[key] = taps_convT_fwd((kernel[0], kernel[1], 1))
+    return _WPAIR_TAPS[key]
+
+
+def wpair_taps_convT_dgrad(kernel) -> TapTable:
+    """Data gradient of ConvTranspose3d(kernel == stride, kernel[2] == 2) on the [.., W/2, 2C] pair view of dy."""
+    key = ("T",) + tuple(kernel)
+    if key not in _WPAIR_TAPS:
+        taps = [((kz, ky, 0), kz * kernel[1] + ky) for kz in range(kernel[0]) for ky in range(kernel[1])]
+        _WPAIR_TAPS[key] = TapTable(taps, [0, len(taps)], [(0, 0, 0)], (kernel[0], kernel[1], 1), (1, 1, 1))
+    return _WPAIR_TAPS[key]
+
+
 def taps_conv_dgrad(kernel, stride) -> TapTable:
     """Data gradient of the above: d_in[s*q + r] = sum_{k: (r - k + p) % s == 0} W[k]^T dy[q + (r - k + p)/s].
     One group per residue class r (prod(stride) groups); every input voxel is written exactly once."""
@@ -623,6 +641,15 @@ class Engine:
             self._conv_call(wpair_taps(op.stride), xv, self._wpair_weights(op), _padded(op.bias, op.Cout_p), out, grid,
                             stats, False, 2 * op.Cin_p, op.Cout_p, flops=self.conv_flops(op, odims), tag="conv_fwd")
             return out, stats
+        if (op.bias is None and stats is None and self._wpairs_convT(op, out) and out.xform is None):
+            # ConvTranspose3d(k == s, kx = 2) with 32 output channels on the w-pair view of its OUTPUT: kernel (k0, k1, 1),
+            # 64 output channels (kx, co) -- the packed weights [(kz, ky, kx)][32][Cin] are [(kz, ky)][64][Cin] as they lie
+            B, D, H, W = out.dims
+            ov = Feat(out.buf.view(B, D, H, W // 2, 64), 0, 64, 64)
+            wv = op.packed(self.wdtype, False).view(op.ntap // 2, 64, op.Cin_p)
+            self._conv_call(_pair_convT_taps(op.kernel), x, wv, None, ov, grid, None, False, op.Cin_p, 64,
+                            flops=self.conv_flops(op, odims), tag="conv_fwd")
+            return out, stats
         self._conv_call(op.fwd_taps, x, op.packed(self.wdtype, False), _padded(op.bias, op.Cout_p), out, grid, stats,
                         False, op.Cin_p, op.Cout_p, flops=self.conv_flops(op, odims), tag="conv_fwd")
         return out, stats
@@ -631,6 +658,26 @@ class Engine:
         return (self.wpairs and not op.transposed and op.kernel == (3, 3, 3) and op.stride[2] == 2 and op.Cin_p == 32
                 and x.ldc == 32 and x.coff == 0 and (x.planar is None or x.half is not None) and x.xform is None and x.dims[3] % 2 == 0
                 and x.buf.is_contiguous() and self.dtype in (torch.bfloat16, torch.float16) and self.impl in (0, 2, 3))
+
+    def _wpairs_convT(self, op: ConvOp, dy: Feat) -> bool:
+        return (self.wpairs and op.transposed and op.stride[2] == 2 and op.Cout_p == 32 and dy.ldc == 32 and dy.coff == 0
+                and dy.dims[3] % 2 == 0 and dy.buf.is_contiguous() and (dy.planar is None or dy.half is not None)
+                and self.dtype in (torch.bfloat16, torch.float16) and self.impl in (0, 2, 3))
+
+    def _wpair_weights_convT(self, op: ConvOp):
+        """[k0 k1][Cin_p][64] from the data-gradient layout [k0 k1 2][Cin_p][32]: K = (kx, co)."""
+        wd = op.packed(self.wdtype, True)
+        ver = (op.weight._version, _weights_epoch, op.weight.data_ptr(), wd.data_ptr())
+        hit = op._packed.get("wpairT")
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        k0, k1, _ = op.kernel
+        w4 = wd.view(k0, k1, 2, op.Cin_p, 32)
+        wv = hit[1] if hit is not None else torch.empty((k0, k1, op.Cin_p, 64), dtype=wd.dtype, device=wd.device)
+        wv[..., :32] = w4[:, :, 0]
+        wv[..., 32:] = w4[:, :, 1]
+        op._packed["wpairT"] = (ver, wv)
+        return wv
 
     def _wpair_weights(self, op: ConvOp):
         """[18][Cout_p][64] from the packed [27][Cout_p][32]: slice (kz, ky, 0) = [W(kx=1) | W(kx=2)] (the pair at the
@@ -781,7 +828,14 @@ class Engine:
         _, p.Dof, p.Hof, p.Wof = dy.dims
         p.out_ldc, p.out_coff, p.Cout = dy.ldc, dy.coff, op.Cout_p
         p.Do, p.Ho, p.Wo = x.dims[1:] if op.transposed else dy.dims[1:]
-        op.fwd_taps.fill(p)
+        if self._wpairs_convT(op, dy):
+            # ConvTranspose3d(k == s, kx = 2) with 32 output channels: on the [.., W/2, 64] pair view of dy it is a
+            # transposed convolution with kernel (k0, k1, 1) and 64 output channels (kx, co), and its weight gradient
+            # [k0 k1][64][Cin] IS dw[(kz, ky, kx)][32][Cin] -- the same memory; the dY bricks become dense 128-byte rows
+            p.Wof, p.out_ldc, p.Cout = dy.dims[3] // 2, 64, 64
+            _pair_convT_taps(op.kernel).fill(p)
+        else:
+            op.fwd_taps.fill(p)
         p.impl = self.impl
         L.call("mtb200_wgrad_taps", C.byref(p), L.stream_ptr(), flops=self.conv_flops(op, dy.dims), tag="conv_wgrad",
                info=(op.Cin_p, op.Cout_p, (p.Do, p.Ho, p.Wo), op.ntap, op.fwd_taps.in_stride, op.fwd_taps.out_stride))
@@ -821,8 +875,17 @@ class Engine:
         if (self.fuse_red and raw is not None and raw.single_consumer and not have and raw.xform is not None
                 and raw.meanrstd is not None and raw.Cp == gx.Cp and raw.dims == gx.dims and self.materialize_inputs):
             red = (raw, self._z64.take((gx.dims[0], raw.Cp, 2), dev))
-        took = self._conv_call(op.dgrad_taps, dyv, op.packed(self.wdtype, True), None, gx, grid, None, have, op.Cout_p,
-                               op.Cin_p, flops=fl, tag="conv_dgrad", red=red)
+        if self._wpairs_convT(op, dy):
+            # data gradient of ConvTranspose3d(k == s) with 32 output channels: d_in[q] = sum_k W[k]^T dy[s q + k]; the
+            # taps kx = 0, 1 are ONE 128-byte row of the [.., W/2, 64] pair view of dy -- k0 k1 taps of K = 64 on dense
+            # rows instead of k0 k1 2 taps of K = 32 on every other 64-byte row
+            B, D, H, W = dyv.dims
+            dyp = Feat(dyv.buf.view(B, D, H, W // 2, 64), 0, 64, 64)
+            took = self._conv_call(wpair_taps_convT_dgrad(op.kernel), dyp, self._wpair_weights_convT(op), None, gx, grid,
+                                   None, have, 64, op.Cin_p, flops=fl, tag="conv_dgrad", red=red)
+        else:
+            took = self._conv_call(op.dgrad_taps, dyv, op.packed(self.wdtype, True), None, gx, grid, None, have,
+                                   op.Cout_p, op.Cin_p, flops=fl, tag="conv_dgrad", red=red)
         if took:
             raw.red_fused = red[1]
         tape.mark(x)
