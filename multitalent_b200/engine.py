@@ -100,6 +100,31 @@ def wpair_taps(stride) -> TapTable:
     return _WPAIR_TAPS[key]
 
 
+def wpair_weights(wp: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Weights of `wpair_taps`: [18][Cout][2C] from the packed forward layout [27][Cout][C] of a 3x3x3 convolution.
+    Slice (kz, ky, 0) = [W(kx=1) | W(kx=2)] (the pair at the output's own position), slice (kz, ky, 1) = [0 | W(kx=0)]
+    (the pair one to the left: only its odd voxel)."""
+    Co, Ci = wp.shape[1], wp.shape[2]
+    w4 = wp.view(3, 3, 3, Co, Ci)
+    wv = out if out is not None else torch.zeros((3, 3, 2, Co, 2 * Ci), dtype=wp.dtype, device=wp.device)
+    wv[:, :, 0, :, :Ci] = w4[:, :, 1]
+    wv[:, :, 0, :, Ci:] = w4[:, :, 2]
+    wv[:, :, 1, :, Ci:] = w4[:, :, 0]
+    return wv
+
+
+def wpair_weights_convT_dgrad(wd: torch.Tensor, kernel, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Weights of `wpair_taps_convT_dgrad`: [k0 k1][Cin][2 Cout] from the data-gradient layout [k0 k1 2][Cin][Cout] of a
+    ConvTranspose3d(k == s): K = (kx, co)."""
+    k0, k1 = kernel[0], kernel[1]
+    Ci, Co = wd.shape[1], wd.shape[2]
+    w4 = wd.view(k0, k1, 2, Ci, Co)
+    wv = out if out is not None else torch.empty((k0, k1, Ci, 2 * Co), dtype=wd.dtype, device=wd.device)
+    wv[..., :Co] = w4[:, :, 0]
+    wv[..., Co:] = w4[:, :, 1]
+    return wv
+
+
 def _pair_convT_taps(kernel) -> TapTable:
     """Forward tap table of the transposed convolution with kernel == stride == (k0, k1, 1) that a ConvTranspose3d with
     kernel (k0, k1, 2) is on the w-pair view of its output."""
@@ -671,11 +696,7 @@ class Engine:
         hit = op._packed.get("wpairT")
         if hit is not None and hit[0] == ver:
             return hit[1]
-        k0, k1, _ = op.kernel
-        w4 = wd.view(k0, k1, 2, op.Cin_p, 32)
-        wv = hit[1] if hit is not None else torch.empty((k0, k1, op.Cin_p, 64), dtype=wd.dtype, device=wd.device)
-        wv[..., :32] = w4[:, :, 0]
-        wv[..., 32:] = w4[:, :, 1]
+        wv = wpair_weights_convT_dgrad(wd, op.kernel, hit[1] if hit is not None else None)
         op._packed["wpairT"] = (ver, wv)
         return wv
 
@@ -687,11 +708,7 @@ class Engine:
         hit = op._packed.get("wpair")
         if hit is not None and hit[0] == ver:
             return hit[1]
-        w4 = wp.view(3, 3, 3, op.Cout_p, 32)
-        wv = hit[1] if hit is not None else torch.zeros((3, 3, 2, op.Cout_p, 64), dtype=wp.dtype, device=wp.device)
-        wv[:, :, 0, :, :32] = w4[:, :, 1]
-        wv[:, :, 0, :, 32:] = w4[:, :, 2]
-        wv[:, :, 1, :, 32:] = w4[:, :, 0]
+        wv = wpair_weights(wp, hit[1] if hit is not None else None)
         op._packed["wpair"] = (ver, wv)
         return wv
 

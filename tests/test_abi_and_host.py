@@ -110,6 +110,47 @@ def test_tap_tables_conv(kernel, stride):
     np.testing.assert_allclose(got, x.grad.numpy(), atol=1e-10)
 
 
+def _wpair_view(t):
+    """NCDHW [B, C, D, H, W] -> the w-pair view [B, 2C, D, H, W/2] with channel index pw * C + c (what the NDHWC buffer
+    looks like when two neighbouring voxels are read as one row)."""
+    B, Cc, D, H, W = t.shape
+    return np.ascontiguousarray(t.reshape(B, Cc, D, H, W // 2, 2).transpose(0, 5, 1, 2, 3, 4).reshape(B, 2 * Cc, D, H, W // 2))
+
+
+@pytest.mark.parametrize("stride", [(2, 2, 2), (1, 2, 2)])
+def test_wpair_tables_strided_conv(stride):
+    """Engine.conv's stride-2 forward on the pair view: 18 taps of 2C channels == Conv3d(3x3x3, stride (.., 2))."""
+    torch.manual_seed(1)
+    x = torch.randn(1, 3, 4, 6, 8, dtype=torch.float64)
+    w = torch.randn(2, 3, 3, 3, 3, dtype=torch.float64)
+    y = torch.nn.functional.conv3d(x, w, stride=stride, padding=1)
+    wp = w.permute(2, 3, 4, 0, 1).reshape(27, 2, 3).contiguous()  # [tap][co][ci]
+    wv = E.wpair_weights(wp).reshape(18, 2, 6).numpy()
+    got = _dense_conv_from_taps(E.wpair_taps(stride), _wpair_view(x.numpy()), wv, y.shape[2:], y.shape[2:])
+    np.testing.assert_allclose(got, y.numpy(), atol=1e-10)
+
+
+@pytest.mark.parametrize("kernel", [(2, 2, 2), (1, 2, 2)])
+def test_wpair_tables_conv_transpose(kernel):
+    """ConvTranspose3d(k == s, kx = 2) on the pair view of its output (forward) and of dy (data gradient); the forward
+    weights and the weight gradient need no repacking: [(kz, ky, kx)][co][ci] is [(kz, ky)][(kx, co)][ci] as it lies."""
+    torch.manual_seed(2)
+    x = torch.randn(1, 3, 2, 3, 2, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(3, 2, *kernel, dtype=torch.float64)  # [Cin][Cout][k]
+    y = torch.nn.functional.conv_transpose3d(x, w, stride=kernel)
+    wp = w.permute(2, 3, 4, 1, 0).reshape(-1, 2, 3).contiguous()  # [tap][co][ci]
+    table = E._pair_convT_taps(kernel)
+    yv_shape = (y.shape[2], y.shape[3], y.shape[4] // 2)
+    got = _dense_conv_from_taps(table, x.detach().numpy(), wp.reshape(-1, 4, 3).numpy(), yv_shape, x.shape[2:])
+    np.testing.assert_allclose(got, _wpair_view(y.detach().numpy()), atol=1e-10)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    wd = wp.permute(0, 2, 1).contiguous()  # [tap][ci][co]
+    wv = E.wpair_weights_convT_dgrad(wd, kernel).reshape(-1, 3, 4).numpy()
+    got = _dense_conv_from_taps(E.wpair_taps_convT_dgrad(kernel), _wpair_view(gy.numpy()), wv, x.shape[2:], x.shape[2:])
+    np.testing.assert_allclose(got, x.grad.numpy(), atol=1e-10)
+
+
 @pytest.mark.parametrize("kernel", [(2, 2, 2), (1, 2, 2)])
 def test_tap_tables_conv_transpose(kernel):
     torch.manual_seed(0)
