@@ -125,6 +125,39 @@ def wpair_weights_convT_dgrad(wd: torch.Tensor, kernel, out: Optional[torch.Tens
     return wv
 
 
+def wpair_taps_conv_dgrad(stride) -> TapTable:
+    """Data gradient of Conv3d(3x3x3, stride (sd, sh, 2)) on the [.., W/2, 2C] pair view of d_in: the output pair
+    (2q, 2q + 1) = the residues rw = 0, 1 of q, so only (rz, ry) remain as groups and the pair is 2C output channels
+    (rw, ci).  W taps: dy[q] feeds rw = 0 through kx = 1 and rw = 1 through kx = 2; dy[q + 1] feeds rw = 1 through kx = 0."""
+    key = ("D",) + tuple(stride)
+    if key not in _WPAIR_TAPS:
+        def dim_taps(r, s):
+            return [(k, (r - k + 1) // s) for k in range(3) if (r - k + 1) % s == 0]
+        taps, begin, ooff = [], [0], []
+        for rz in range(stride[0]):
+            for ry in range(stride[1]):
+                for kz, oz in dim_taps(rz, stride[0]):
+                    for ky, oy in dim_taps(ry, stride[1]):
+                        for woff in (0, 1):
+                            taps.append(((oz, oy, woff), (kz * 3 + ky) * 2 + woff))
+                begin.append(len(taps))
+                ooff.append((rz, ry, 0))
+        _WPAIR_TAPS[key] = TapTable(taps, begin, ooff, (1, 1, 1), (stride[0], stride[1], 1))
+    return _WPAIR_TAPS[key]
+
+
+def wpair_weights_conv_dgrad(wd: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Weights of `wpair_taps_conv_dgrad`: [18][2 Cin][Cout] from the data-gradient layout [27][Cin][Cout]: slice
+    (kz, ky, 0) = rows [W(kx=1); W(kx=2)], slice (kz, ky, 1) = rows [0; W(kx=0)]."""
+    Ci, Co = wd.shape[1], wd.shape[2]
+    w4 = wd.view(3, 3, 3, Ci, Co)
+    wv = out if out is not None else torch.zeros((3, 3, 2, 2 * Ci, Co), dtype=wd.dtype, device=wd.device)
+    wv[:, :, 0, :Ci] = w4[:, :, 1]
+    wv[:, :, 0, Ci:] = w4[:, :, 2]
+    wv[:, :, 1, Ci:] = w4[:, :, 0]
+    return wv
+
+
 def _pair_convT_taps(kernel) -> TapTable:
     """Forward tap table of the transposed convolution with kernel == stride == (k0, k1, 1) that a ConvTranspose3d with
     kernel (k0, k1, 2) is on the w-pair view of its output."""
@@ -507,6 +540,7 @@ class Engine:
         self.planar_concat = os.environ.get("MTB200_PLANAR", "1") != "0"
         # stride-2 forward on the w-pair view of a dense 32-channel input (Engine.conv / wpair_taps)
         self.wpairs = os.environ.get("MTB200_WPAIRS", "1") != "0"
+        self.wpairs_dgrad = os.environ.get("MTB200_WPAIRS_DGRAD", "1") != "0"
         self.defer_head_fwd = os.environ.get("MTB200_DEFER_HEAD", "1") != "0"
         self.defer_heads = False
         self.deferred = {}       # placeholder pointer -> {"x": head input, "op": head}
@@ -892,7 +926,23 @@ class Engine:
         if (self.fuse_red and raw is not None and raw.single_consumer and not have and raw.xform is not None
                 and raw.meanrstd is not None and raw.Cp == gx.Cp and raw.dims == gx.dims and self.materialize_inputs):
             red = (raw, self._z64.take((gx.dims[0], raw.Cp, 2), dev))
-        if self._wpairs_convT(op, dy):
+        if (self.wpairs_dgrad and self.wpairs and not op.transposed and op.kernel == (3, 3, 3) and op.stride[2] == 2
+                and op.Cin_p == 32 and gx.ldc == 32 and gx.coff == 0 and gx.buf.is_contiguous() and gx.dims[3] % 2 == 0
+                and (gx.planar is None or gx.half is not None) and op.Cout_p in (16, 32, 64)
+                and self.dtype in (torch.bfloat16, torch.float16) and self.impl in (0, 2)):
+            # data gradient of the strided 3x3x3 convolution into a dense 32-channel tensor: on the pair view of d_in the 8
+            # residue groups become 4 groups of 64 channels (rw, ci) -- 128-byte rows for the group-merged kernel's store
+            B, D, H, W = gx.dims
+            gxv = Feat(gx.buf.view(B, D, H, W // 2, 64), 0, 64, 64)
+            wd = op.packed(self.wdtype, True)
+            ver = (op.weight._version, _weights_epoch, op.weight.data_ptr(), wd.data_ptr())
+            hit = op._packed.get("wpairD")
+            if hit is None or hit[0] != ver:
+                hit = (ver, wpair_weights_conv_dgrad(wd, hit[1] if hit is not None else None))
+                op._packed["wpairD"] = hit
+            took = self._conv_call(wpair_taps_conv_dgrad(op.stride), dyv, hit[1], None, gxv, grid, None, have, op.Cout_p,
+                                   64, flops=fl, tag="conv_dgrad", red=None)
+        elif self._wpairs_convT(op, dy):
             # data gradient of ConvTranspose3d(k == s) with 32 output channels: d_in[q] = sum_k W[k]^T dy[s q + k]; the
             # taps kx = 0, 1 are ONE 128-byte row of the [.., W/2, 64] pair view of dy -- k0 k1 taps of K = 64 on dense
             # rows instead of k0 k1 2 taps of K = 32 on every other 64-byte row

@@ -130,6 +130,22 @@ def test_wpair_tables_strided_conv(stride):
     np.testing.assert_allclose(got, y.numpy(), atol=1e-10)
 
 
+@pytest.mark.parametrize("stride", [(2, 2, 2), (1, 2, 2)])
+def test_wpair_tables_strided_conv_dgrad(stride):
+    """Data gradient of the strided convolution written through the pair view of d_in (4 groups of 2C channels)."""
+    torch.manual_seed(3)
+    x = torch.randn(1, 3, 4, 6, 8, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(2, 3, 3, 3, 3, dtype=torch.float64)
+    y = torch.nn.functional.conv3d(x, w, stride=stride, padding=1)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    wd = w.permute(2, 3, 4, 1, 0).reshape(27, 3, 2).contiguous()  # [tap][ci][co]
+    wv = E.wpair_weights_conv_dgrad(wd).reshape(18, 6, 2).numpy()
+    gv_shape = (x.shape[2], x.shape[3], x.shape[4] // 2)
+    got = _dense_conv_from_taps(E.wpair_taps_conv_dgrad(stride), gy.numpy(), wv, gv_shape, y.shape[2:])
+    np.testing.assert_allclose(got, _wpair_view(x.grad.numpy()), atol=1e-10)
+
+
 @pytest.mark.parametrize("kernel", [(2, 2, 2), (1, 2, 2)])
 def test_wpair_tables_conv_transpose(kernel):
     """ConvTranspose3d(k == s, kx = 2) on the pair view of its output (forward) and of dy (data gradient); the forward
