@@ -210,6 +210,11 @@ constexpr int UNPACK_CHUNK = 4096;
 
 __global__ void __launch_bounds__(256) unpack_wgrad_batched_kernel(const mtb200_unpack_desc* __restrict__ descs, int n) {
   pdl_wait();
+  // the chunk's (outer, inner) channel pairs x taps, staged so that BOTH sides are coalesced: the packed buffer
+  // [tap][Cout_p][Cin_p] is read tap by tap along consecutive pairs (= consecutive ci of one cout row; the first version
+  // gathered one 4-byte element per 32-byte sector and paid three 64-bit divisions per element), the reference-layout
+  // gradient [outer][inner][tap] is then updated along consecutive addresses
+  __shared__ float stage[UNPACK_CHUNK + 64];
   int lo = 0, hi = n - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
@@ -220,6 +225,24 @@ __global__ void __launch_bounds__(256) unpack_wgrad_batched_kernel(const mtb200_
   const long long i0 = (long long)((int)blockIdx.x - d.blk_begin) * UNPACK_CHUNK;
   const long long i1 = min(total, i0 + UNPACK_CHUNK);
   const int inner = d.transposed ? d.Cout : d.Cin;
+  const int ntap = d.ntap;
+  const long long p0 = i0 / ntap;                         // first (outer, inner) pair of the chunk
+  const int npair = (int)((i1 - 1) / ntap - p0) + 1;      // <= UNPACK_CHUNK / ntap + 2
+  if (npair * ntap <= UNPACK_CHUNK + 64) {
+    const int a0 = (int)(p0 % inner), b0 = (int)(p0 / inner);
+    for (int e = threadIdx.x; e < npair * ntap; e += 256) {
+      const int t = e / npair, pr = e - t * npair;
+      int a = a0 + pr, b = b0;
+      while (a >= inner) { a -= inner; ++b; }              // a chunk spans a few outer rows at most (or inner is tiny)
+      const int co = d.transposed ? a : b, ci = d.transposed ? b : a;
+      const int cip = (d.split > 0 && ci >= d.split) ? ci - d.split + d.split_p : ci;
+      stage[pr * ntap + t] = b < (d.transposed ? d.Cin : d.Cout) ? d.dw[((long long)t * d.Cout_p + co) * d.Cin_p + cip] : 0.f;
+    }
+    __syncthreads();
+    const long long base = p0 * ntap;
+    for (long long i = i0 + threadIdx.x; i < i1; i += 256) d.grad[i] += stage[(int)(i - base)];
+    return;
+  }
   for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
     const int t = (int)(i % d.ntap);
     const int a = (int)((i / d.ntap) % inner);
