@@ -538,7 +538,8 @@ int conv_taps_umma(const mtb200_conv_params& p, cudaStream_t s) {
   {
     static const int mode = [] { const char* e = getenv("MTB200_TAPS_PAIR"); return e ? atoi(e) : -1; }();
     // (64-byte rows, i.e. the strided 32 -> 64 layer at full resolution, measured 30 % SLOWER in pairs)
-    bool eligible = p.ngroups == 1 && p.group_tap_begin[1] > p.group_tap_begin[0] && p.Cout % 32 == 0 && q.KC == 64;
+    bool eligible = (p.ngroups == 1 || mode == 2) && p.Cout % 32 == 0 && q.KC == 64;  // mode 2: multi-group problems too
+    for (int g = 0; g < p.ngroups; ++g) eligible = eligible && p.group_tap_begin[g + 1] > p.group_tap_begin[g];
     int bn2 = p.Cout;
     if (bn2 > 256) {
       bn2 = 0;
