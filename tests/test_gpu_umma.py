@@ -584,6 +584,7 @@ def test_fused_instancenorm_backward_reduction_matches_separate_pass(dims, cmid,
 
 @pytest.mark.parametrize("cin,cout,dims", [
     (30, 60, (1, 8, 12, 128)),     # the top strided layer's shape class: Cin_p 32, two Cout blocks, 64 output voxels per line
+    (30, 60, (2, 4, 8, 200)),      # ragged: 100 output voxels in two 64-wide tiles
     (30, 60, (2, 4, 8, 100)),      # ragged: 50 output voxels in a 64-wide tile
     (60, 120, (1, 6, 16, 64)),     # second strided layer: 2 Cin chunks x 4 Cout blocks, 32 output voxels per line
     (30, 30, (1, 4, 40, 128)),     # long in h: h ranges, boundary lines shared between units
@@ -609,7 +610,7 @@ def test_strided_wgrad_line_streaming_matches_library(cin, cout, dims):
         tape = Tape()
         with L.KernelProfile() as kp:
             eng._conv_bwd(tape, op, Feat(xb, 0, cin, op.Cin_p), Feat(dyb, 0, cout, op.Cout_p), False, bias_grad_is_zero=True)
-        if impl == 0:
+        if impl == 0 and W // 2 >= 64:  # narrower output lines go to the per-tap kernel (MTB200_WLINE_S2_MINW, default 64)
             assert any(r[6] == "wgrad_line_s2_umma" for r in kp.records), [r[6] for r in kp.records]
         gws.append(tape.param_grads[id(conv.weight)].clone())
     assert float((gws[1] - gws[0]).abs().max()) <= 2e-3 * float(gws[0].abs().max()) + 1e-6
