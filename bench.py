@@ -263,6 +263,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--settle-steps", type=int, default=30,
+                    help="untimed steps before the W warm-up steps (clock / memory-pool settling on a fresh box)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--net", default="generic", choices=["generic", "resenc"],
                     help="generic = BASELINE.json configs[1]; resenc = configs[2] (FabiansUNet, resenc plan, bs 4)")
@@ -322,6 +324,13 @@ def main():
 
     sampler = ClockSampler(local_rank)  # NVML attached before the warm-up; samples only while `active` is set
     sampler.start()
+    # settle phase (reported as config.settle_steps; same count on every rank): a fresh box occasionally ran the first
+    # seconds of its first process 10 - 25 % slow (memory pools, tensor-map and module first use, power state) -- 36.2 /
+    # 38.1 / 41.5 ms against 32.6 on the same box seconds later.  These steps are untimed, like the W warm-up steps that
+    # follow them.
+    for _ in range(max(0, args.settle_steps)):
+        tr.train_step(d_data, d_tgt, valid, True)
+    barrier()
     for _ in range(args.warmup):
         tr.train_step(d_data, d_tgt, valid, True)
     barrier()
@@ -538,7 +547,8 @@ def main():
                        "patch": "x".join(str(v) for v in patch), "batch_per_gpu": args.batch,
                        "global_batch": patches_per_step,
                        "parallelism": "dp%d" % world, "l2": "working set (activations > 8 GB) far exceeds the 126 MB L2",
-                       "loss": loss_val, "loss_scaling": tr.loss_scaling_description()},
+                       "loss": loss_val, "loss_scaling": tr.loss_scaling_description(),
+                       "settle_steps": int(max(0, args.settle_steps))},
             "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 12,
                     "ms_per_step": e2e_ms_per_step},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
