@@ -146,6 +146,23 @@ def test_wpair_tables_strided_conv_dgrad(stride):
     np.testing.assert_allclose(got, _wpair_view(x.grad.numpy()), atol=1e-10)
 
 
+@pytest.mark.parametrize("stride", [(2, 2, 2), (1, 2, 2)])
+def test_wpair_dgrad_table_fits_the_group_merged_kernel(stride):
+    """csrc/conv_gm.cu's envelope, restated: the groups are exactly the residue classes of the output lattice, no group
+    has two taps at one input offset, at most 32 distinct offsets -- otherwise the pair-view data gradient would fall
+    back to the per-tap kernel without anyone noticing."""
+    t = E.wpair_taps_conv_dgrad(stride)
+    assert t.in_stride == (1, 1, 1) and t.out_stride == (stride[0], stride[1], 1)
+    assert sorted(t.group_ooff) == sorted((a, b, 0) for a in range(stride[0]) for b in range(stride[1]))
+    offsets = set()
+    for g in range(len(t.group_ooff)):
+        offs = [t.taps[i][0] for i in range(t.group_begin[g], t.group_begin[g + 1])]
+        assert len(offs) >= 1 and len(set(offs)) == len(offs)
+        offsets.update(offs)
+    assert len(offsets) <= 32 and len(t.taps) == 18
+    assert sorted(w for _, w in t.taps) == list(range(18))  # every virtual weight slice used exactly once
+
+
 @pytest.mark.parametrize("kernel", [(2, 2, 2), (1, 2, 2)])
 def test_wpair_tables_conv_transpose(kernel):
     """ConvTranspose3d(k == s, kx = 2) on the pair view of its output (forward) and of dy (data gradient); the forward
